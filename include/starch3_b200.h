@@ -1,0 +1,148 @@
+/*
+ * starch3_b200.h -- C ABI of the B200-native starch3 compression hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every entry point names the reference interface it replaces
+ * (hpp = /root/reference/include/starch3api.hpp, bz/ = the reference's vendored
+ * third-party/bzip2-1.0.6.tar.gz).  All entry points run on the GPU; there is
+ * no CPU fallback -- without a usable CUDA device s3g_init fails.
+ *
+ * Conventions: every function returns S3G_OK (0) or a negative S3G_E_* code;
+ * s3g_last_error() returns a thread-local message for the last failure.
+ * A context is bound to one device and one CUDA stream and is single-caller.
+ */
+#ifndef STARCH3_B200_H_
+#define STARCH3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define S3G_API __attribute__((visibility("default")))
+#else
+#define S3G_API
+#endif
+
+#define S3G_OK            0
+#define S3G_E_CUDA       -1   /* CUDA runtime error / no device                      */
+#define S3G_E_PARAM      -2   /* bad argument (hpp:842-848 maps these to EINVAL)      */
+#define S3G_E_NOMEM      -3   /* allocation failed (hpp:176 ... ENOMEM)               */
+#define S3G_E_MALFORMED  -4   /* BED line with fewer than three fields               */
+#define S3G_E_CAPACITY   -5   /* caller-provided output buffer too small             */
+#define S3G_E_LIMIT      -6   /* input exceeds a documented limit                     */
+
+typedef struct s3g_ctx s3g_ctx;
+
+/* Replaces Starch::initialize_out_compression_stream / initialize_bz_stream_ptr
+ * (hpp:771-785, :819-855): creates the compressor state, here a device context. */
+S3G_API int  s3g_init(int device, s3g_ctx **out);
+/* Replaces Starch::delete_out_compression_stream / delete_bz_stream_ptr (hpp:787-801, :864-880). */
+S3G_API void s3g_destroy(s3g_ctx *ctx);
+S3G_API const char *s3g_last_error(void);
+/* Run all kernels of this context on `cuda_stream` (a cudaStream_t); NULL = the context's own stream. */
+S3G_API int  s3g_set_stream(s3g_ctx *ctx, void *cuda_stream);
+/* Number of kernels launched by this context since creation (bench.py `gpu_launches`). */
+S3G_API uint64_t s3g_launch_count(const s3g_ctx *ctx);
+
+/* One entry per chromosome stream, in input order.  Mirrors what
+ * process_tf_buffer (hpp:393-407) is handed: current_chr, line_count, the
+ * transformed buffer -- plus the declared-but-never-computed base counts
+ * (hpp:61-62) and the position of the chromosome's bzip2 stream. */
+typedef struct s3g_chrom {
+    uint64_t name_off;         /* offset of the name in the INPUT buffer */
+    uint32_t name_len;
+    uint32_t n_blocks;         /* bzip2 blocks in this stream */
+    uint64_t tf_off, tf_len;   /* transformed stream inside the tf buffer */
+    int64_t  line_count;       /* hpp:503 */
+    int64_t  bases_nonunique;  /* sum(stop-start) */
+    int64_t  bases_unique;     /* bases covered by the union of the intervals */
+    uint64_t bz_off, bz_len;   /* compressed stream inside the streams buffer */
+} s3g_chrom;
+
+typedef struct s3g_result {
+    uint8_t   *archive;        /* host: complete archive (ARCHIVE_FORMAT.md); owned by the library */
+    uint64_t   archive_size;
+    uint64_t   streams_off;    /* where the concatenated bzip2 streams start inside archive */
+    s3g_chrom *chroms;         /* host */
+    uint64_t   n_chroms;
+    uint64_t   n_lines, n_blocks;
+    uint64_t   tf_bytes;       /* total transformed bytes */
+    uint64_t   dropped_tail_bytes; /* unterminated last line, dropped like produce_line hpp:181-190 */
+    void      *d_streams;      /* device: concatenated bzip2 streams (valid until the next call on ctx) */
+    uint64_t   streams_size;
+    double     device_ms;      /* CUDA-event time, first kernel to last kernel */
+} s3g_result;
+
+/*
+ * The whole hot path: tokenise + transform + per-chromosome bzip2 + container.
+ * Replaces the produce_line / consume_line / update_chr / consume_tf_buffer
+ * pipeline (hpp:158-391, started at /root/reference/src/starch3.cpp:36-59) and
+ * the BZ2_bzCompress loop process_tf_buffer (hpp:393) was evidently meant to run.
+ *   bed, n          host buffer with the sorted BED text
+ *   block_size_100k 1..9 (the reference hard-codes 9, hpp:837)
+ *   note            metadata note (hpp:803-809), may be NULL
+ */
+S3G_API int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int block_size_100k,
+                     const char *note, s3g_result *res);
+/* Same, input already resident in device memory (16-byte aligned); the archive
+ * is still assembled on the host unless `want_archive` is 0, in which case only
+ * d_streams / chroms are produced (the device-resident measurement of bench.py). */
+S3G_API int s3g_compress_bed_device(s3g_ctx *ctx, const void *d_bed, uint64_t n, int block_size_100k,
+                            const char *note, int want_archive, s3g_result *res);
+S3G_API void s3g_result_free(s3g_result *res);
+
+/* ---- stage entry points (host buffers in / out), for the parity tests ---- */
+
+/* Kernel (1): produce_line + consume_line tokenizer (hpp:158-199, :220-309).
+ * Outputs (each may be NULL): line_start[n_lines+1], start[], stop[], rem_off[]
+ * (offset of the remainder relative to the line start; == line length when the
+ * line has no fourth field), chrom_change[] (1 where strcmp(chr, previous chr) != 0, hpp:331). */
+S3G_API int s3g_tokenize(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, uint64_t cap_lines, uint64_t *n_lines,
+                 uint64_t *line_start, int64_t *start, int64_t *stop, uint32_t *rem_off, uint8_t *chrom_change);
+
+/* Kernels (1)+(2): update_transformation_state (hpp:428-504) for all lines. */
+S3G_API int s3g_transform(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, uint8_t *tf, uint64_t tf_cap, uint64_t *tf_len,
+                  s3g_chrom *chroms, uint64_t chrom_cap, uint64_t *n_chroms, uint64_t *dropped_tail_bytes);
+
+/* Kernel (3a): RLE1 + block CRC + block cut (bz/bzlib.c:225-338, :370-412) of ONE stream. */
+typedef struct s3g_blockdesc {
+    uint64_t in_start, in_end; /* input bytes committed to this block */
+    uint32_t nblock;           /* bytes after RLE1 */
+    uint32_t crc;              /* finalised block CRC (bz/compress.c:606) */
+    uint8_t  in_use[256];      /* bz/bzlib.c:232, :247 */
+} s3g_blockdesc;
+S3G_API int s3g_rle1(s3g_ctx *ctx, const uint8_t *in, uint64_t n, int block_size_100k,
+             s3g_blockdesc *desc, uint64_t desc_cap, uint64_t *n_blocks,
+             uint8_t *rle_out, uint64_t rle_cap);
+
+/* Kernel (3b): BZ2_blockSort (bz/blocksort.c:1031-1089) for a batch of blocks.
+ * blocks = concatenated block bytes, off[n_blocks+1] their boundaries (each block <= 900000 bytes).
+ * ptr_out receives the sorted rotation starts at the same offsets; orig_ptr[b] as bz/blocksort.c:1083-1086. */
+S3G_API int s3g_bwt(s3g_ctx *ctx, const uint8_t *blocks, const uint64_t *off, uint64_t n_blocks,
+            uint32_t *ptr_out, int32_t *orig_ptr);
+
+/* Kernel (3c): generateMTFValues (bz/compress.c:120-231) of one block given its sorted order.
+ * mtfv needs n+1 slots; freq[258]. */
+S3G_API int s3g_mtf(s3g_ctx *ctx, const uint8_t *block, uint32_t n, const uint32_t *ptr, const uint8_t *in_use,
+            uint16_t *mtfv, uint32_t *n_mtf, int32_t *freq);
+
+/* Kernel (3d): sendMTFValues (bz/compress.c:239-598) of one block: table selection and emission.
+ * selector[18002], len[6*258]; bits receives the block body (mapping table .. last symbol), MSB first. */
+S3G_API int s3g_huff(s3g_ctx *ctx, const uint16_t *mtfv, uint32_t n_mtf, const int32_t *freq, const uint8_t *in_use,
+             int32_t *n_groups, int32_t *n_selectors, uint8_t *selector, uint8_t *len,
+             uint8_t *bits, uint64_t bits_cap, uint64_t *n_bits);
+
+/* Kernels (3a-e): one complete bzip2 stream; the unit the reference's patched
+ * BZ2_bzCompressInit / BZ2_bzCompress(BZ_FINISH) / BZ2_bzCompressEnd trio (bz/bzlib.h:103-117)
+ * produces for one chromosome. */
+S3G_API int s3g_bz_compress(s3g_ctx *ctx, const uint8_t *in, uint64_t n, int block_size_100k,
+                    uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARCH3_B200_H_ */

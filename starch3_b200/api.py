@@ -1,0 +1,274 @@
+"""ctypes binding of include/starch3_b200.h.
+
+Python mirror of the reference's operator surface for this path: a `Context` plays the
+role of the `starch3::Starch` object's compression stream (starch3api.hpp:771-888) and
+`Context.compress_bed` the role of the produce_line/consume_line/process_tf_buffer
+pipeline (starch3api.hpp:158-407).  Errors raise `Starch3Error` carrying the C-ABI code;
+the reference prints "Error: ..." and exits with an errno-style code
+(starch3api.hpp:175-176, :841-848) -- the CLI wrapper maps the codes back.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(HERE, "libstarch3_b200.so")
+
+S3G_OK, S3G_E_CUDA, S3G_E_PARAM, S3G_E_NOMEM, S3G_E_MALFORMED, S3G_E_CAPACITY, S3G_E_LIMIT = 0, -1, -2, -3, -4, -5, -6
+
+C_ABI_SYMBOLS = [
+    "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count",
+    "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free",
+    "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
+]
+
+
+class Starch3Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"s3g error {code}: {msg}")
+        self.code = code
+
+
+class CChrom(C.Structure):
+    _fields_ = [("name_off", C.c_uint64), ("name_len", C.c_uint32), ("n_blocks", C.c_uint32),
+                ("tf_off", C.c_uint64), ("tf_len", C.c_uint64), ("line_count", C.c_int64),
+                ("bases_nonunique", C.c_int64), ("bases_unique", C.c_int64),
+                ("bz_off", C.c_uint64), ("bz_len", C.c_uint64)]
+
+
+class CResult(C.Structure):
+    _fields_ = [("archive", C.POINTER(C.c_uint8)), ("archive_size", C.c_uint64), ("streams_off", C.c_uint64),
+                ("chroms", C.POINTER(CChrom)), ("n_chroms", C.c_uint64), ("n_lines", C.c_uint64),
+                ("n_blocks", C.c_uint64), ("tf_bytes", C.c_uint64), ("dropped_tail_bytes", C.c_uint64),
+                ("d_streams", C.c_void_p), ("streams_size", C.c_uint64), ("device_ms", C.c_double)]
+
+
+class CBlockDesc(C.Structure):
+    _fields_ = [("in_start", C.c_uint64), ("in_end", C.c_uint64), ("nblock", C.c_uint32), ("crc", C.c_uint32),
+                ("in_use", C.c_uint8 * 256)]
+
+
+def have_library():
+    return os.path.exists(lib_path)
+
+
+def build_library(verbose=False):
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc"), "-j8"], stdout=out)
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not have_library():
+            raise Starch3Error(S3G_E_CUDA, f"{lib_path} is missing: build it with `make -C starch3_b200/csrc` "
+                                           "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(lib_path)
+        vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+        L.s3g_init.argtypes = [i32, C.POINTER(vp)]
+        L.s3g_destroy.argtypes = [vp]; L.s3g_destroy.restype = None
+        L.s3g_last_error.restype = C.c_char_p
+        L.s3g_set_stream.argtypes = [vp, vp]
+        L.s3g_launch_count.argtypes = [vp]; L.s3g_launch_count.restype = u64
+        L.s3g_compress_bed.argtypes = [vp, vp, u64, i32, C.c_char_p, C.POINTER(CResult)]
+        L.s3g_compress_bed_device.argtypes = [vp, vp, u64, i32, C.c_char_p, i32, C.POINTER(CResult)]
+        L.s3g_result_free.argtypes = [C.POINTER(CResult)]; L.s3g_result_free.restype = None
+        L.s3g_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(u64), vp, vp, vp, vp, vp]
+        L.s3g_transform.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64), C.POINTER(u64)]
+        L.s3g_rle1.argtypes = [vp, vp, u64, i32, vp, u64, C.POINTER(u64), vp, u64]
+        L.s3g_bwt.argtypes = [vp, vp, vp, u64, vp, vp]
+        L.s3g_mtf.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32), vp]
+        L.s3g_huff.argtypes = [vp, vp, C.c_uint32, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, vp, vp, u64,
+                               C.POINTER(u64)]
+        L.s3g_bz_compress.argtypes = [vp, vp, u64, i32, vp, u64, C.POINTER(u64)]
+        _lib = L
+    return _lib
+
+
+def _u8(a):
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(a, dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Result:
+    """Host-side view of an s3g_result (copied out; the C result is freed)."""
+
+    def __init__(self, cres, bed_bytes=None, keep_archive=True):
+        self.n_lines = cres.n_lines
+        self.n_blocks = cres.n_blocks
+        self.tf_bytes = cres.tf_bytes
+        self.dropped_tail_bytes = cres.dropped_tail_bytes
+        self.device_ms = cres.device_ms
+        self.streams_size = cres.streams_size
+        self.streams_off = cres.streams_off
+        self.d_streams = cres.d_streams
+        self.archive = None
+        if keep_archive and cres.archive_size:
+            self.archive = C.string_at(cres.archive, cres.archive_size)
+        self.chroms = []
+        for i in range(cres.n_chroms):
+            c = cres.chroms[i]
+            d = {k: getattr(c, k) for k, _ in CChrom._fields_}
+            if bed_bytes is not None:
+                d["name"] = bytes(bed_bytes[c.name_off:c.name_off + c.name_len])
+            self.chroms.append(d)
+
+    def stream(self, i):
+        """bzip2 stream of chromosome i (bytes), from the archive."""
+        c = self.chroms[i]
+        o = self.streams_off + c["bz_off"]
+        return self.archive[o:o + c["bz_len"]]
+
+
+class Context:
+    """One device context (s3g_ctx).  Single caller, one CUDA stream."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._lib = lib()
+        self._check(self._lib.s3g_init(device, C.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != S3G_OK:
+            raise Starch3Error(rc, self._lib.s3g_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self._h:
+            self._lib.s3g_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.s3g_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    @property
+    def launch_count(self):
+        return self._lib.s3g_launch_count(self._h)
+
+    # ---- whole path ----
+    def compress_bed(self, bed, block_size_100k=9, note=None):
+        a = _u8(bed)
+        r = CResult()
+        rc = self._lib.s3g_compress_bed(self._h, _p(a), len(a), block_size_100k,
+                                        note.encode() if isinstance(note, str) else note, C.byref(r))
+        try:
+            self._check(rc)
+            return Result(r, a)
+        finally:
+            self._lib.s3g_result_free(C.byref(r))
+
+    def compress_bed_device(self, dptr, n, block_size_100k=9, note=None, want_archive=False, bed_bytes=None):
+        r = CResult()
+        rc = self._lib.s3g_compress_bed_device(self._h, C.c_void_p(dptr), n, block_size_100k,
+                                               note.encode() if isinstance(note, str) else note,
+                                               1 if want_archive else 0, C.byref(r))
+        try:
+            self._check(rc)
+            return Result(r, bed_bytes, keep_archive=want_archive)
+        finally:
+            self._lib.s3g_result_free(C.byref(r))
+
+    # ---- stages ----
+    def tokenize(self, bed):
+        a = _u8(bed)
+        cap = int(np.count_nonzero(a == 10)) + 1
+        n = C.c_uint64(0)
+        ls = np.zeros(cap + 1, dtype=np.uint64); st = np.zeros(cap, dtype=np.int64); sp = np.zeros(cap, dtype=np.int64)
+        ro = np.zeros(cap, dtype=np.uint32); cc = np.zeros(cap, dtype=np.uint8)
+        self._check(self._lib.s3g_tokenize(self._h, _p(a), len(a), cap, C.byref(n), _p(ls), _p(st), _p(sp), _p(ro), _p(cc)))
+        m = n.value
+        return dict(n_lines=m, line_start=ls[:m + 1], start=st[:m], stop=sp[:m], rem_off=ro[:m], chrom_change=cc[:m])
+
+    def transform(self, bed):
+        a = _u8(bed)
+        cap = 2 * len(a) + 4096
+        tf = np.empty(cap, dtype=np.uint8)
+        ccap = int(np.count_nonzero(a == 10)) + 1
+        ccap = min(ccap, 1 << 22)
+        chroms = (CChrom * ccap)()
+        tl = C.c_uint64(0); nc = C.c_uint64(0); dr = C.c_uint64(0)
+        self._check(self._lib.s3g_transform(self._h, _p(a), len(a), _p(tf), cap, C.byref(tl), chroms, ccap, C.byref(nc), C.byref(dr)))
+        raw = a.tobytes()
+        out = []
+        for c in chroms[:nc.value]:
+            out.append(dict(name=raw[c.name_off:c.name_off + c.name_len], tf_off=c.tf_off, tf_len=c.tf_len,
+                            line_count=c.line_count, bases_nonunique=c.bases_nonunique, bases_unique=c.bases_unique))
+        return tf[:tl.value].tobytes(), out, dr.value
+
+    def rle1(self, data, block_size_100k=9):
+        a = _u8(data)
+        cap = len(a) // (100000 * block_size_100k - 19 - 260) + 4
+        descs = (CBlockDesc * cap)()
+        rle = np.empty(len(a) + len(a) // 4 + 64, dtype=np.uint8)
+        nb = C.c_uint64(0)
+        self._check(self._lib.s3g_rle1(self._h, _p(a), len(a), block_size_100k, descs, cap, C.byref(nb), _p(rle), len(rle)))
+        out = []
+        for d in descs[:nb.value]:
+            out.append(dict(in_start=d.in_start, in_end=d.in_end, nblock=d.nblock, crc=d.crc,
+                            in_use=np.frombuffer(bytes(d.in_use), dtype=np.uint8).copy()))
+        tot = sum(d["nblock"] for d in out)
+        return out, rle[:tot].copy()
+
+    def bwt(self, blocks):
+        """blocks: list of bytes-like (each <= 900000).  -> list of (ptr ndarray, origPtr)."""
+        arrs = [_u8(b) for b in blocks]
+        off = np.zeros(len(arrs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in arrs])
+        cat = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint8)
+        ptr = np.empty(int(off[-1]), dtype=np.uint32)
+        orig = np.empty(len(arrs), dtype=np.int32)
+        self._check(self._lib.s3g_bwt(self._h, _p(cat), _p(off), len(arrs), _p(ptr), _p(orig)))
+        return [(ptr[int(off[i]):int(off[i + 1])].copy(), int(orig[i])) for i in range(len(arrs))]
+
+    def mtf(self, block, ptr, in_use):
+        a = _u8(block)
+        ptr = np.ascontiguousarray(ptr, dtype=np.uint32)
+        iu = _u8(in_use)
+        mtfv = np.empty(len(a) + 2, dtype=np.uint16)
+        freq = np.zeros(258, dtype=np.int32)
+        n = C.c_uint32(0)
+        self._check(self._lib.s3g_mtf(self._h, _p(a), len(a), _p(ptr), _p(iu), _p(mtfv), C.byref(n), _p(freq)))
+        return mtfv[:n.value].copy(), freq
+
+    def huff(self, mtfv, freq, in_use):
+        m = np.ascontiguousarray(mtfv, dtype=np.uint16)
+        f = np.ascontiguousarray(freq, dtype=np.int32)
+        iu = _u8(in_use)
+        ng = C.c_int32(0); ns = C.c_int32(0); nbits = C.c_uint64(0)
+        sel = np.zeros(18004, dtype=np.uint8)
+        lens = np.zeros((6, 258), dtype=np.uint8)
+        bits = np.zeros(len(m) * 3 + 65536, dtype=np.uint8)
+        self._check(self._lib.s3g_huff(self._h, _p(m), len(m), _p(f), _p(iu), C.byref(ng), C.byref(ns), _p(sel), _p(lens),
+                                       _p(bits), len(bits), C.byref(nbits)))
+        return dict(n_groups=ng.value, n_selectors=ns.value, selector=sel[:ns.value].copy(), len=lens,
+                    bits=bits[:(nbits.value + 7) // 8].copy(), nbits=nbits.value)
+
+    def bz_compress(self, data, block_size_100k=9):
+        a = _u8(data)
+        cap = len(a) + len(a) // 3 + 65536
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_uint64(0)
+        self._check(self._lib.s3g_bz_compress(self._h, _p(a), len(a), block_size_100k, _p(out), cap, C.byref(n)))
+        return out[:n.value].tobytes()

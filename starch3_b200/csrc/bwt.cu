@@ -1,0 +1,450 @@
+// bwt.cu -- kernel (3b): the block sort of bzip2 (BZ2_blockSort,
+// bz/blocksort.c:1031-1089) for a batch of blocks, as a GPU prefix-doubling
+// suffix sort over cyclic rotations.
+//
+// What must match the reference: ptr[0..n) = rotation starts in ascending
+// order of the n cyclic rotations of the block (bz/blocksort.c:347-469 compares
+// with wrap-around) and origPtr = the index of rotation 0 (:1083-1086).  Which
+// algorithm produces the order is free (bz/blocksort.c:1058-1061).
+//
+// Algorithm (per block, all blocks of a batch in the same launches):
+//   init   rank every rotation by its first k symbols, k = max{k : A^k <= 2^20},
+//          A = symbols in use, via a 2-pass LSD radix sort on a 20-bit key.
+//   round  given the order by the first h symbols (SA, grouped; RK[i] = SA
+//          position of the first member of i's group, bit 31 = group is a
+//          singleton), obtain the order by 2h symbols with the Manber-Myers
+//          observation: walking SA in order, j = SA[k]-h arrives in ascending
+//          RK[j+h]; a STABLE counting sort of those j by RK[j] therefore sorts
+//          every group by its second half.  RK[j] < 2^20, so that is again two
+//          10-bit radix passes -- over the still-unsorted rotations only.
+//   Rounds stop when every group is a singleton or h >= n (equal rotations:
+//   a periodic block; flagged in BlockInfo.tie).
+#include "common.cuh"
+
+namespace s3g {
+
+constexpr int ST = 256;                 // threads per sort tile
+constexpr int SI = 16;                  // items per thread
+constexpr int STILE = ST * SI;          // 4096 items per tile
+constexpr int NBINS = 1024;             // 10-bit digits
+constexpr int NT = (BLK_STRIDE + STILE - 1) / STILE;   // tiles per block slot (220)
+constexpr uint32_t FINAL = 0x80000000u;
+
+struct BwtP {
+    const uint8_t *blk;        // block bytes of batch block 0 (slot stride BLK_STRIDE)
+    const uint8_t *seq;        // unseqToSeq maps, 256 per block
+    const BlockInfo *blocks;   // batch block 0
+    uint32_t *sa, *rk;         // [nb][BLK_STRIDE]
+    uint64_t *kv0, *kv1;       // [nb][BLK_STRIDE] (key << 32 | val)
+    uint32_t *hist;            // [nb][NBINS][NT]
+    uint32_t *cnt_n;           // [nb] block sizes
+    uint32_t *cnt_m;           // [nb] active items after pass 1
+    uint32_t *act;             // [2][nb] unsorted rotations per block (ping-pong by round)
+    uint32_t *agg;             // [nb][NT][2] tile aggregates of the boundary scans
+    unsigned long long *g_act; // [2] batch totals
+    uint32_t *init_k;          // [nb] symbols in the initial key
+    uint32_t *init_a;          // [nb] alphabet size
+};
+
+enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2 };
+
+// item p of block lb for the given source mode; returns false if the item does not take part
+template <int MODE>
+__device__ __forceinline__ bool get_item(const BwtP &P, uint32_t lb, uint32_t p, uint32_t n, uint32_t cnt, uint32_t h,
+                                         const uint64_t *kv_in, uint32_t &key, uint32_t &val)
+{
+    if (p >= cnt) return false;
+    if (MODE == MODE_INIT) {
+        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *sq = P.seq + (uint64_t)lb * 256;
+        uint32_t k = P.init_k[lb], a = P.init_a[lb];
+        uint32_t key_ = 0, q = p;
+        for (uint32_t t = 0; t < k; t++) {
+            key_ = key_ * a + sq[b[q]];
+            q++; if (q == n) q = 0;
+        }
+        key = key_; val = p;
+        return true;
+    } else if (MODE == MODE_MM) {
+        uint32_t s = P.sa[(uint64_t)lb * BLK_STRIDE + p];
+        uint32_t j = s >= h ? s - h : s + n - h;          // h < n is guaranteed by the caller
+        uint32_t r = P.rk[(uint64_t)lb * BLK_STRIDE + j];
+        if (r & FINAL) return false;
+        key = r; val = j;
+        return true;
+    } else {
+        uint64_t kv = kv_in[(uint64_t)lb * BLK_STRIDE + p];
+        key = (uint32_t)(kv >> 32); val = (uint32_t)kv;
+        return true;
+    }
+}
+
+// depth (symbols already sorted) of block lb in doubling round `round`
+__device__ __forceinline__ uint32_t depth_of(const BwtP &P, uint32_t lb, uint32_t round)
+{
+    return round >= 25 ? 0x7fffffffu : P.init_k[lb] << round;      // init_k <= 20
+}
+// phase 0 = initial sort (every block), phase 1 = doubling round (unsorted blocks whose depth is below n)
+__device__ __forceinline__ bool block_live(const BwtP &P, uint32_t lb, int phase, uint32_t round, const uint32_t *act_cur)
+{
+    if (phase == 0) return true;
+    return act_cur[lb] != 0 && depth_of(P, lb, round) < P.cnt_n[lb];
+}
+
+// ---- radix pass: per-tile digit histogram ------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(ST) k_hist(BwtP P, int shift, int phase, uint32_t round, const uint32_t *cnt_arr,
+                                             const uint64_t *kv_in, const uint32_t *act_cur)
+{
+    __shared__ uint32_t sh[NBINS];
+    uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    if (!block_live(P, lb, phase, round, act_cur)) return;
+    uint32_t h = depth_of(P, lb, round);
+    uint32_t n = P.cnt_n[lb], cnt = cnt_arr[lb];
+    if ((uint64_t)tile * STILE >= cnt) return;
+    for (int i = threadIdx.x; i < NBINS; i += ST) sh[i] = 0;
+    __syncthreads();
+    uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    uint32_t base = tile * STILE + w * (SI * 32) + l;
+#pragma unroll 4
+    for (int r = 0; r < SI; r++) {
+        uint32_t key, val;
+        bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, key, val);
+        uint32_t d = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (ok && (peers & ((1u << l) - 1)) == 0) atomicAdd(&sh[d], __popc(peers));
+    }
+    __syncthreads();
+    uint32_t *out = P.hist + (uint64_t)lb * NBINS * NT;
+    for (int i = threadIdx.x; i < NBINS; i += ST) out[(uint64_t)i * NT + tile] = sh[i];
+}
+
+// ---- radix pass: exclusive scan of hist[digit][tile] per block ---------------
+__global__ void __launch_bounds__(NBINS) k_hist_scan(BwtP P, int phase, uint32_t round, const uint32_t *cnt_arr, uint32_t *total_out,
+                                                     const uint32_t *act_cur)
+{
+    __shared__ uint32_t sm[33];
+    uint32_t lb = blockIdx.x;
+    if (!block_live(P, lb, phase, round, act_cur)) return;
+    uint32_t cnt = cnt_arr[lb];
+    uint32_t ntiles = (cnt + STILE - 1) / STILE;
+    uint32_t *row = P.hist + (uint64_t)lb * NBINS * NT + (uint64_t)threadIdx.x * NT;
+    uint32_t s = 0;
+    for (uint32_t t = 0; t < ntiles; t++) s += row[t];
+    uint32_t tot;
+    uint32_t ex = block_excl_sum<uint32_t>(s, sm, &tot);
+    for (uint32_t t = 0; t < ntiles; t++) { uint32_t v = row[t]; row[t] = ex; ex += v; }
+    if (threadIdx.x == 0 && total_out) total_out[lb] = tot;
+}
+
+// ---- radix pass: stable scatter ----------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(ST) k_scatter(BwtP P, int shift, int phase, uint32_t round, const uint32_t *cnt_arr,
+                                                const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *act_cur)
+{
+    __shared__ uint16_t wcnt[(ST / 32) * NBINS];   // per-warp digit counters -> exclusive warp offsets
+    __shared__ uint32_t gbase[NBINS];
+    uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    if (!block_live(P, lb, phase, round, act_cur)) return;
+    uint32_t h = depth_of(P, lb, round);
+    uint32_t n = P.cnt_n[lb], cnt = cnt_arr[lb];
+    if ((uint64_t)tile * STILE >= cnt) return;
+    for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) wcnt[i] = 0;
+    const uint32_t *hrow = P.hist + (uint64_t)lb * NBINS * NT;
+    for (int i = threadIdx.x; i < NBINS; i += ST) gbase[i] = hrow[(uint64_t)i * NT + tile];
+    __syncthreads();
+    uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    uint32_t base = tile * STILE + w * (SI * 32) + l;
+    uint16_t *mycnt = wcnt + w * NBINS;
+    uint64_t kv[SI];
+    uint16_t rnk[SI];
+    uint32_t okmask = 0;
+#pragma unroll
+    for (int r = 0; r < SI; r++) {
+        uint32_t key = 0, val = 0;
+        bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, key, val);
+        kv[r] = ((uint64_t)key << 32) | val;
+        uint32_t d = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned lt = peers & ((1u << l) - 1);
+        uint16_t b = ok ? mycnt[d] : (uint16_t)0;
+        __syncwarp();
+        if (ok && lt == 0) mycnt[d] = (uint16_t)(b + __popc(peers));
+        __syncwarp();
+        rnk[r] = (uint16_t)(b + __popc(lt));
+        if (ok) okmask |= 1u << r;
+    }
+    __syncthreads();
+    // exclusive prefix over warps per digit
+    for (int d = threadIdx.x; d < NBINS; d += ST) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < ST / 32; ww++) { uint32_t c = wcnt[ww * NBINS + d]; wcnt[ww * NBINS + d] = (uint16_t)run; run += c; }
+    }
+    __syncthreads();
+    uint64_t *out = kv_out + (uint64_t)lb * BLK_STRIDE;
+#pragma unroll
+    for (int r = 0; r < SI; r++) {
+        if (okmask & (1u << r)) {
+            uint32_t d = ((uint32_t)(kv[r] >> 32) >> shift) & (NBINS - 1);
+            out[gbase[d] + mycnt[d] + rnk[r]] = kv[r];
+        }
+    }
+}
+
+// ---- group boundaries and new ranks -------------------------------------------
+// Sorted items p of block lb: key_p (group = SA position of the group start; in INIT
+// mode the symbol key), val_p.  Thread t of a tile owns SI consecutive items.
+template <bool INIT>
+__device__ __forceinline__ void boundary_flags(const BwtP &P, uint32_t lb, uint32_t n, uint32_t cnt, uint32_t h,
+                                               const uint64_t *kv, uint32_t p0, uint32_t &headmask, uint32_t &bndmask,
+                                               uint64_t *items /*SI+1*/)
+{
+    // flags for items p0 .. p0+SI (one extra for the singleton test of the last own item)
+    const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    uint32_t prev_key = 0, prev_sec = 0;
+    bool have_prev = false;
+    if (p0 > 0 && p0 - 1 < cnt) {
+        uint64_t pv = a[p0 - 1];
+        prev_key = (uint32_t)(pv >> 32);
+        if (!INIT) { uint32_t j = (uint32_t)pv + h; if (j >= n) j -= n; prev_sec = rk[j]; }
+        have_prev = true;
+    }
+    headmask = 0; bndmask = 0;
+#pragma unroll
+    for (int k = 0; k <= SI; k++) {
+        uint32_t p = p0 + k;
+        if (p < cnt) {
+            uint64_t it = a[p];
+            items[k] = it;
+            uint32_t key = (uint32_t)(it >> 32), sec = 0;
+            if (!INIT) { uint32_t j = (uint32_t)it + h; if (j >= n) j -= n; sec = rk[j]; }
+            bool head = !have_prev || (!INIT && key != prev_key);
+            bool bnd = head || (INIT ? key != prev_key : sec != prev_sec);
+            if (INIT) head = !have_prev;
+            if (head) headmask |= 1u << k;
+            if (bnd) bndmask |= 1u << k;
+            prev_key = key; prev_sec = sec; have_prev = true;
+        } else {
+            items[k] = 0;
+            bndmask |= 1u << k;     // past the end counts as a boundary (singleton test)
+            headmask |= 1u << k;
+        }
+    }
+}
+
+template <bool INIT>
+__global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const uint64_t *kv, const uint32_t *act_cur)
+{
+    __shared__ uint32_t sm[33];
+    uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    if (!block_live(P, lb, INIT ? 0 : 1, round, act_cur)) return;
+    uint32_t h = depth_of(P, lb, round);
+    uint32_t n = P.cnt_n[lb], cnt = INIT ? n : P.cnt_m[lb];
+    if ((uint64_t)tile * STILE >= cnt) return;
+    uint32_t p0 = tile * STILE + threadIdx.x * SI;
+    uint32_t hm, bm; uint64_t items[SI + 1];
+    boundary_flags<INIT>(P, lb, n, cnt, h, kv, p0, hm, bm, items);
+    hm &= (1u << SI) - 1; bm &= (1u << SI) - 1;
+    uint32_t valid = p0 < cnt ? (cnt - p0 >= SI ? (1u << SI) - 1 : (1u << (cnt - p0)) - 1) : 0;
+    hm &= valid; bm &= valid;
+    uint32_t lh = hm ? p0 + (31 - __clz(hm)) + 1 : 0;    // position + 1 of my last head
+    uint32_t lbn = bm ? p0 + (31 - __clz(bm)) + 1 : 0;
+    uint32_t th, tb;
+    block_excl_max<uint32_t>(lh, sm, &th);
+    block_excl_max<uint32_t>(lbn, sm, &tb);
+    if (threadIdx.x == 0) {
+        uint32_t *ag = P.agg + ((uint64_t)lb * NT + tile) * 2;
+        ag[0] = th; ag[1] = tb;
+    }
+}
+
+template <bool INIT>
+__global__ void __launch_bounds__(ST) k_bound_apply(BwtP P, uint32_t round, const uint64_t *kv, uint32_t *newrank,
+                                                    const uint32_t *act_cur, uint32_t *act_next, unsigned long long *g_act_next)
+{
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t carry[2];
+    uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    if (!block_live(P, lb, INIT ? 0 : 1, round, act_cur)) return;
+    uint32_t h = depth_of(P, lb, round);
+    uint32_t n = P.cnt_n[lb], cnt = INIT ? n : P.cnt_m[lb];
+    if ((uint64_t)tile * STILE >= cnt) return;
+    // carry-in: max over the aggregates of the earlier tiles
+    {
+        uint32_t ch = 0, cb = 0;
+        const uint32_t *ag = P.agg + (uint64_t)lb * NT * 2;
+        for (uint32_t t = threadIdx.x; t < tile; t += ST) { ch = max(ch, ag[t * 2]); cb = max(cb, ag[t * 2 + 1]); }
+        uint32_t th, tb;
+        block_excl_max<uint32_t>(ch, sm, &th);
+        block_excl_max<uint32_t>(cb, sm, &tb);
+        if (threadIdx.x == 0) { carry[0] = th; carry[1] = tb; }
+        __syncthreads();
+    }
+    uint32_t p0 = tile * STILE + threadIdx.x * SI;
+    uint32_t hm, bm; uint64_t items[SI + 1];
+    boundary_flags<INIT>(P, lb, n, cnt, h, kv, p0, hm, bm, items);
+    uint32_t own = (1u << SI) - 1;
+    uint32_t valid = p0 < cnt ? (cnt - p0 >= SI ? own : (1u << (cnt - p0)) - 1) : 0;
+    uint32_t hmo = hm & valid, bmo = bm & valid;
+    uint32_t lh = hmo ? p0 + (31 - __clz(hmo)) + 1 : 0;
+    uint32_t lbn = bmo ? p0 + (31 - __clz(bmo)) + 1 : 0;
+    uint32_t th, tb;
+    uint32_t eh = block_excl_max<uint32_t>(lh, sm, &th);
+    uint32_t eb = block_excl_max<uint32_t>(lbn, sm, &tb);
+    uint32_t hp = max(eh, carry[0]), bp = max(eb, carry[1]);   // position + 1
+    uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *nr = newrank + (uint64_t)lb * BLK_STRIDE;
+    uint32_t still = 0;
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        if (valid & (1u << k)) {
+            uint32_t p = p0 + k;
+            if (hm & (1u << k)) hp = p + 1;
+            if (bm & (1u << k)) bp = p + 1;
+            uint32_t key = (uint32_t)(items[k] >> 32), val = (uint32_t)items[k];
+            bool single = (bm & (1u << k)) && (bm & (1u << (k + 1)));
+            if (!single) still++;
+            if (INIT) {
+                sa[p] = val;
+                rk[val] = (bp - 1) | (single ? FINAL : 0u);
+            } else {
+                uint32_t q = key + (p - (hp - 1));
+                sa[q] = val;
+                nr[p] = (key + ((bp - 1) - (hp - 1))) | (single ? FINAL : 0u);
+            }
+        }
+    }
+    // count what is still unsorted
+    uint32_t tot;
+    block_excl_sum<uint32_t>(still, sm, &tot);
+    if (threadIdx.x == 0 && tot) { atomicAdd(&act_next[lb], tot); atomicAdd(g_act_next, (unsigned long long)tot); }
+}
+
+__global__ void __launch_bounds__(ST) k_rank_update(BwtP P, uint32_t round, const uint64_t *kv, const uint32_t *newrank,
+                                                    const uint32_t *act_cur)
+{
+    uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    if (!block_live(P, lb, 1, round, act_cur)) return;
+    uint32_t cnt = P.cnt_m[lb];
+    if ((uint64_t)tile * STILE >= cnt) return;
+    const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t *nr = newrank + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    for (int r = 0; r < SI; r++) {
+        uint32_t p = tile * STILE + r * ST + threadIdx.x;
+        if (p < cnt) rk[(uint32_t)a[p]] = nr[p];
+    }
+}
+
+__global__ void k_bwt_setup(BwtP P, uint32_t nb)
+{
+    uint32_t lb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lb >= nb) return;
+    uint32_t n = P.blocks[lb].nblock, a = P.blocks[lb].n_in_use;
+    if (a < 1) a = 1;
+    uint32_t k = 1;
+    if (a >= 2) {
+        uint64_t pw = a;
+        while (pw * a <= (1u << 20)) { pw *= a; k++; }
+    }
+    P.cnt_n[lb] = n; P.init_k[lb] = k; P.init_a[lb] = a;
+    P.act[lb] = 0; P.act[nb + lb] = 0;
+}
+
+// origPtr, tie flag and the BWT last column (bz/compress.c:166-167 reads block[ptr[i]-1])
+__global__ void __launch_bounds__(ST) k_bwt_finish(BwtP P, BlockInfo *blocks, uint8_t *lcol)
+{
+    uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    uint32_t n = P.cnt_n[lb];
+    if ((uint64_t)tile * STILE >= n) return;
+    const uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *sq = P.seq + (uint64_t)lb * 256;
+    uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
+    bool tie = false;
+    for (int r = 0; r < SI; r++) {
+        uint32_t k = tile * STILE + r * ST + threadIdx.x;
+        if (k < n) {
+            uint32_t s = sa[k];
+            if (s == 0) blocks[lb].orig_ptr = (int32_t)k;
+            if (!(rk[s] & FINAL)) tie = true;
+            L[k] = sq[b[s ? s - 1 : n - 1]];
+        }
+    }
+    if (tie) blocks[lb].tie = 1;
+}
+
+int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
+{
+    if (nb == 0) return S3G_OK;
+    size_t slots = (size_t)nb * BLK_STRIDE;
+    S3G_TRY(ctx->sa.ensure(slots * 4));
+    S3G_TRY(ctx->rk.ensure(slots * 4));
+    S3G_TRY(ctx->kv0.ensure(slots * 8));
+    S3G_TRY(ctx->kv1.ensure(slots * 8));
+    S3G_TRY(ctx->hist.ensure((size_t)nb * NBINS * NT * 4));
+    S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (6 * 4 + NT * 2 * 4) + 64));
+    S3G_TRY(ctx->lcol.ensure(slots));
+    BwtP P;
+    P.blk = ctx->blk_bytes.as<uint8_t>() + b0 * (uint64_t)BLK_STRIDE;
+    P.seq = ctx->seq_map.as<uint8_t>() + b0 * 256;
+    P.blocks = ctx->blocks.as<BlockInfo>() + b0;
+    P.sa = ctx->sa.as<uint32_t>(); P.rk = ctx->rk.as<uint32_t>();
+    P.kv0 = ctx->kv0.as<uint64_t>(); P.kv1 = ctx->kv1.as<uint64_t>();
+    P.hist = ctx->hist.as<uint32_t>();
+    uint32_t *misc = ctx->bwt_misc.as<uint32_t>();
+    P.g_act = reinterpret_cast<unsigned long long *>(misc); misc += 4;
+    P.cnt_n = misc; misc += nb;
+    P.cnt_m = misc; misc += nb;
+    P.act = misc; misc += 2 * nb;
+    P.init_k = misc; misc += nb;
+    P.init_a = misc; misc += nb;
+    P.agg = misc;
+    S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 16, ctx->stream));
+    S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
+    dim3 grid(NT, (unsigned)nb);
+    const uint32_t *no_act = nullptr;
+    const uint64_t *no_kv = nullptr;
+    uint32_t *no_out = nullptr;
+    // ---- init: order by the first k symbols ----
+    S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, no_act);
+    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
+    S3G_LAUNCH(ctx, k_scatter<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, P.kv0, no_act);
+    S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, no_act);
+    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
+    S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
+    S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv1, no_act);
+    S3G_LAUNCH(ctx, k_bound_apply<true>, grid, ST, 0, P, 0u, P.kv1, no_out, no_act, P.act, P.g_act);
+    S3G_TRY(check_launch("bwt init"));
+    // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
+    unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
+    for (uint32_t round = 0; round < 32; round++) {
+        uint32_t *act_cur = P.act + (size_t)(round & 1) * nb;
+        uint32_t *act_next = P.act + (size_t)((round + 1) & 1) * nb;
+        unsigned long long *g_cur = P.g_act + (round & 1), *g_next = P.g_act + ((round + 1) & 1);
+        S3G_CUDA(cudaMemcpyAsync(h_act, g_cur, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (*h_act == 0) break;
+        S3G_CUDA(cudaMemsetAsync(act_next, 0, nb * 4, ctx->stream));
+        S3G_CUDA(cudaMemsetAsync(g_next, 0, 8, ctx->stream));
+        uint32_t *newrank = reinterpret_cast<uint32_t *>(P.kv0);
+        S3G_LAUNCH(ctx, k_hist<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, act_cur);
+        S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_n, P.cnt_m, act_cur);
+        S3G_LAUNCH(ctx, k_scatter<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, P.kv0, act_cur);
+        S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, act_cur);
+        S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_m, no_out, act_cur);
+        S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
+        S3G_LAUNCH(ctx, k_bound_agg<false>, grid, ST, 0, P, round, P.kv1, act_cur);
+        S3G_LAUNCH(ctx, k_bound_apply<false>, grid, ST, 0, P, round, P.kv1, newrank, act_cur, act_next, g_next);
+        S3G_LAUNCH(ctx, k_rank_update, grid, ST, 0, P, round, P.kv1, newrank, act_cur);
+        S3G_TRY(check_launch("bwt round"));
+    }
+    S3G_LAUNCH(ctx, k_bwt_finish, grid, ST, 0, P, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>());
+    return check_launch("bwt finish");
+}
+
+}  // namespace s3g

@@ -1,0 +1,214 @@
+// common.cuh -- shared host/device plumbing for the starch3 B200 hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/starch3_b200.h"
+
+namespace s3g {
+
+void set_error(const char *fmt, ...);
+
+#define S3G_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            s3g::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return e_ == cudaErrorMemoryAllocation ? S3G_E_NOMEM : S3G_E_CUDA;           \
+        }                                                                                \
+    } while (0)
+
+#define S3G_TRY(call)                 \
+    do {                              \
+        int rc_ = (call);             \
+        if (rc_ != S3G_OK) return rc_; \
+    } while (0)
+
+// Grow-only device buffer; contexts keep them across calls so steady-state
+// steps do not pay cudaMalloc / cudaFree.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return S3G_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return S3G_E_NOMEM;
+        }
+        cap = want;
+        return S3G_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ---- geometry of one bzip2 block in the batched device layout -------------
+// Every block owns a fixed-stride slot, so block b's arrays start at b*BLK_STRIDE.
+// nblock never exceeds 100000*9-19 + 9 (bz/bzlib.c:194, :284-289 and the final flush).
+constexpr uint32_t BLK_STRIDE = 900096;         // elements per block slot (multiple of 128)
+constexpr uint32_t BITS_WORDS = 491520;         // 32-bit words per block of emitted bits (>= 17 bit * 900001 + header)
+constexpr int      SM_COUNT   = 148;
+
+// Block descriptor shared by stages 3a..3e (device and host).
+struct BlockInfo {
+    uint64_t in_start, in_end;   // byte range of the (concatenated) tf buffer committed to this block
+    uint64_t e_base;             // RLE1 output offset (stream-relative prefix) at in_start
+    uint32_t nblock;             // bytes after RLE1
+    uint32_t chrom;              // owning stream
+    uint32_t crc;                // finalised block CRC
+    uint32_t n_in_use;
+    int32_t  orig_ptr;
+    uint32_t tie;                // 1 if equal rotations remained (periodic block)
+    uint32_t n_mtf;
+    uint32_t pad;
+    uint64_t n_bits;             // bits of this block incl. its 105-bit block header
+    uint64_t bit_off;            // bit offset inside its stream
+};
+
+// ---- per-device context -----------------------------------------------------
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // pinned host scratch for small read-backs
+    uint64_t *h_scalars = nullptr;   // 64 x u64
+    // stage buffers (grow-only)
+    DevBuf bed, tile_cnt, line_start, start, stop, rem_off, flags, line_tf_off, chrom_first;
+    DevBuf scan_a, scan_b, scan_c, scalars;
+    DevBuf tf, chroms, stat_a, stat_b, soff;
+    DevBuf rle_carry, rle_ebase, blocks, blk_prov, blk_bytes, in_use, seq_map, stream_tab;
+    DevBuf sa, rk, kv0, kv1, hist, bwt_misc, lcol;
+    DevBuf mtf0, mtfv16, mtf_freq, bits, pool, pool_woff, streams, stream_meta;
+    DevBuf io_a, io_b, io_c, io_d, io_e;   // staging for the stage entry points
+    // host mirrors
+    std::vector<BlockInfo> h_blocks;
+    std::vector<s3g_chrom> h_chroms;
+    uint64_t pool_words = 0;               // words appended to the pool so far
+};
+
+#define S3G_LAUNCH(ctx, kernel, grid, block, smem, ...)                     \
+    do {                                                                    \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->launches++;                                                  \
+    } while (0)
+
+int check_launch(const char *what);
+
+// ---- device helpers ---------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+template <class T> __device__ __forceinline__ T warp_incl_sum(T v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (unsigned)d) v += o;
+    }
+    return v;
+}
+template <class T> __device__ __forceinline__ T warp_incl_max(T v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (unsigned)d) v = o > v ? o : v;
+    }
+    return v;
+}
+
+// Exclusive block-wide sum over one value per thread.  `sm` needs 33 slots.
+// Returns the exclusive prefix; *total gets the block total.  All threads must call.
+template <class T> __device__ __forceinline__ T block_excl_sum(T v, T *sm, T *total)
+{
+    T inc = warp_incl_sum(v);
+    unsigned w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane_id() == 31) sm[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T x = lane_id() < nw ? sm[lane_id()] : T(0);
+        T xi = warp_incl_sum(x);
+        sm[lane_id()] = xi - x;
+        if (lane_id() == 31) sm[32] = xi;
+    }
+    __syncthreads();
+    *total = sm[32];
+    return sm[w] + inc - v;
+}
+
+// Exclusive block-wide max over one value per thread (identity 0): the max over
+// threads with a smaller index.  `sm` needs 33 slots; *total gets the block max.
+template <class T> __device__ __forceinline__ T block_excl_max(T v, T *sm, T *total)
+{
+    T inc = warp_incl_max(v);
+    unsigned w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane_id() == 31) sm[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T x = lane_id() < nw ? sm[lane_id()] : T(0);
+        T xi = warp_incl_max(x);
+        T ex = __shfl_up_sync(0xffffffffu, xi, 1);
+        if (lane_id() == 0) ex = T(0);
+        sm[lane_id()] = ex;
+        if (lane_id() == 31) sm[32] = xi;
+    }
+    __syncthreads();
+    *total = sm[32];
+    T up = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane_id() == 0) up = T(0);
+    T pre = sm[w];
+    return pre > up ? pre : up;
+}
+
+#endif  // __CUDACC__
+
+// ---- stage drivers (device pointers in, device pointers out) ---------------
+struct TfResult {
+    uint64_t n_lines = 0, n_chroms = 0, tf_len = 0, dropped = 0;
+};
+// kernels (1)+(2); leaves ctx->tf (bytes), ctx->chroms (s3g_chrom[n_chroms]) and the per-line arrays on device
+int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only);
+
+struct CutResult {
+    uint64_t n_blocks = 0;
+};
+// kernel (3a) over a concatenated buffer of `n_streams` streams; stream s covers [d_soff[s], d_soff[s+1]).
+// Leaves ctx->blocks (BlockInfo[n_blocks]), ctx->blk_bytes (slot b at b*BLK_STRIDE), ctx->in_use (256 B per block).
+int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams,
+                int level, CutResult *out);
+
+// kernels (3b..3d) on blocks [b0, b0+nb) of ctx->blocks
+int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb);                 // -> ctx->sa, ctx->lcol, BlockInfo.orig_ptr / tie
+int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb);                 // -> ctx->mtfv16, mtf_freq, BlockInfo.n_mtf
+// -> ctx->bits (BITS_WORDS words per block), BlockInfo.n_bits; optional selector / len dumps for the parity tests
+int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t *d_sel_out, uint8_t *d_len_out);
+// append the bits of blocks [b0, b0+nb) to ctx->pool (word offsets in ctx->pool_woff)
+int run_pool_append(Ctx *ctx, uint64_t b0, uint64_t nb);
+// kernel (3e): bit-level concatenation of the pooled blocks into per-stream byte strings (ctx->streams);
+// fills ctx->stream_meta (StreamMeta[n_streams])
+struct StreamMeta { uint64_t byte_off, byte_len, n_blocks; uint32_t combined_crc, pad; };
+int run_assemble(Ctx *ctx, uint64_t n_blocks, uint64_t n_streams, int level, uint64_t *total_bytes);
+
+}  // namespace s3g
+
+struct s3g_ctx : s3g::Ctx {};

@@ -1,0 +1,464 @@
+// mtf_huff.cu -- kernels (3c) and (3d): move-to-front + RUNA/RUNB zero-run coding
+// (generateMTFValues, bz/compress.c:120-231) and bzip2's iterative Huffman table
+// selection and emission (sendMTFValues, bz/compress.c:239-598; BZ2_hbMakeCodeLengths
+// / BZ2_hbAssignCodes, bz/huffman.c:63-166).  One CTA per bzip2 block.
+#include "common.cuh"
+
+namespace s3g {
+
+// =============================================================================
+// (3c) MTF.  The MTF position of symbol s at index i equals the number of
+// symbols whose most recent occurrence is later than the most recent occurrence
+// of s ("recency rank").  Symbols not seen yet get the virtual position -(c+1),
+// which reproduces the initial list 0,1,2,... (bz/compress.c:161).  With that,
+// a block splits into 32 chunks that only need the last occurrence of every
+// symbol before the chunk start.
+// =============================================================================
+constexpr int MT = 1024;                 // threads per CTA (32 warps = 32 chunks)
+constexpr int UNSET = INT32_MIN;
+
+template <int NS>
+__device__ __forceinline__ void mtf_chunk(const uint8_t *L, uint8_t *M, int beg, int end, const int *init_last, int a)
+{
+    const unsigned l = threadIdx.x & 31;
+    int lastv[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        int c = s * 32 + (int)l;
+        lastv[s] = c < a ? init_last[c] : UNSET;
+    }
+    for (int base = beg; base < end; base += 32) {
+        int pos = base + (int)l;
+        int mysym = pos < end ? L[pos] : 0;
+        int mym = 0;
+        int lim = end - base < 32 ? end - base : 32;
+        for (int t = 0; t < lim; t++) {
+            int s = __shfl_sync(0xffffffffu, mysym, t);
+            int slot = s >> 5, ln = s & 31;
+            int v = lastv[0];
+#pragma unroll
+            for (int q = 1; q < NS; q++) if (slot == q) v = lastv[q];
+            int ls = __shfl_sync(0xffffffffu, v, ln);
+            int cnt = 0;
+#pragma unroll
+            for (int q = 0; q < NS; q++) cnt += __popc(__ballot_sync(0xffffffffu, lastv[q] > ls));
+            if ((int)l == t) mym = cnt;
+            if ((int)l == ln) {
+#pragma unroll
+                for (int q = 0; q < NS; q++) if (slot == q) lastv[q] = base + t;
+            }
+        }
+        if (pos < end) M[pos] = (uint8_t)mym;
+    }
+}
+
+__global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
+                                            BlockInfo *blocks)
+{
+    __shared__ int s_last[32 * 256];
+    __shared__ int s_freq[258];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_carry[2];
+    const uint32_t lb = blockIdx.x;
+    const int n = (int)blocks[lb].nblock;
+    const int a = (int)blocks[lb].n_in_use;
+    const uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
+    uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
+    uint16_t *mtfv = mtfv_all + (uint64_t)lb * BLK_STRIDE;
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 32 * 256; i += MT) s_last[i] = UNSET;
+    for (int i = threadIdx.x; i < 258; i += MT) s_freq[i] = 0;
+    __syncthreads();
+    int chunk = ((n + 31) / 32 + 31) & ~31;
+    int beg = (int)w * chunk, end = beg + chunk;
+    if (beg > n) beg = n;
+    if (end > n) end = n;
+    // phase A: last occurrence of every symbol inside my chunk (scan backwards until all found)
+    {
+        int *mine = s_last + w * 256;
+        int found = 0;
+        for (int top = end; top > beg && found < a; top -= 32) {
+            int pos = top - 32 + (int)l;
+            int sym = pos >= beg ? L[pos] : 256 + (int)l;        // distinct dummies
+            unsigned peers = __match_any_sync(0xffffffffu, sym);
+            bool isnew = false;
+            if (pos >= beg && (int)l == 31 - __clz(peers) && mine[sym] == UNSET) { mine[sym] = pos; isnew = true; }
+            found += __popc(__ballot_sync(0xffffffffu, isnew));
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // phase B: exclusive "latest" over chunks, virtual positions for symbols never seen
+    if (threadIdx.x < 256) {
+        int c = threadIdx.x;
+        int run = -(c + 1);
+        for (int ww = 0; ww < 32; ww++) {
+            int t = s_last[ww * 256 + c];
+            s_last[ww * 256 + c] = run;
+            if (t != UNSET) run = t;
+        }
+    }
+    __syncthreads();
+    // phase C: recency ranks
+    if (beg < end) {
+        const int *il = s_last + w * 256;
+        switch ((a + 31) >> 5) {
+            case 1: mtf_chunk<1>(L, M, beg, end, il, a); break;
+            case 2: mtf_chunk<2>(L, M, beg, end, il, a); break;
+            case 3: mtf_chunk<3>(L, M, beg, end, il, a); break;
+            case 4: mtf_chunk<4>(L, M, beg, end, il, a); break;
+            case 5: mtf_chunk<5>(L, M, beg, end, il, a); break;
+            case 6: mtf_chunk<6>(L, M, beg, end, il, a); break;
+            case 7: mtf_chunk<7>(L, M, beg, end, il, a); break;
+            default: mtf_chunk<8>(L, M, beg, end, il, a); break;
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // phase D: zero runs in bijective base 2 (RUNA/RUNB, bz/compress.c:174-188), others +1, then EOB
+    constexpr int DI = 8;
+    uint32_t out_base = 0;       // symbols written so far
+    uint32_t nz_carry = 0;       // (position + 1) of the last non-zero rank so far
+    int fa = 0, fb = 0;          // private RUNA / RUNB counts
+    for (int tile0 = 0; tile0 < n; tile0 += MT * DI) {
+        int p0 = tile0 + (int)threadIdx.x * DI;
+        uint8_t m[DI + 1];
+#pragma unroll
+        for (int k = 0; k <= DI; k++) m[k] = (p0 + k < n) ? M[p0 + k] : (uint8_t)1;   // past the end acts as non-zero
+        uint32_t lastnz = 0;
+#pragma unroll
+        for (int k = 0; k < DI; k++) if (p0 + k < n && m[k]) lastnz = (uint32_t)(p0 + k + 1);
+        uint32_t tmax;
+        uint32_t ex = block_excl_max<uint32_t>(lastnz, s_scan, &tmax);
+        uint32_t rs = ex > nz_carry ? ex : nz_carry;     // zero run in effect starts at position rs
+        uint32_t emit = 0;
+        uint32_t rs_k = rs;
+#pragma unroll
+        for (int k = 0; k < DI; k++) {
+            if (p0 + k < n) {
+                if (m[k]) { emit++; rs_k = (uint32_t)(p0 + k + 1); }
+                else if (m[k + 1]) { uint32_t r = (uint32_t)(p0 + k + 1) - rs_k; emit += 31 - __clz(r + 1); }
+            }
+        }
+        uint32_t ttot;
+        uint32_t eo = block_excl_sum<uint32_t>(emit, s_scan, &ttot);
+        uint32_t o = out_base + eo;
+        rs_k = rs;
+#pragma unroll
+        for (int k = 0; k < DI; k++) {
+            if (p0 + k < n) {
+                if (m[k]) { mtfv[o++] = (uint16_t)(m[k] + 1); atomicAdd(&s_freq[m[k] + 1], 1); rs_k = (uint32_t)(p0 + k + 1); }
+                else if (m[k + 1]) {
+                    uint32_t zp = (uint32_t)(p0 + k + 1) - rs_k - 1;
+                    for (;;) {
+                        if (zp & 1) { mtfv[o++] = 1; fb++; } else { mtfv[o++] = 0; fa++; }
+                        if (zp < 2) break;
+                        zp = (zp - 2) >> 1;
+                    }
+                }
+            }
+        }
+        out_base += ttot;
+        if (tmax > nz_carry) nz_carry = tmax;
+    }
+    if (fa) atomicAdd(&s_freq[0], fa);
+    if (fb) atomicAdd(&s_freq[1], fb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mtfv[out_base] = (uint16_t)(a + 1);      // EOB
+        s_freq[a + 1] += 1;
+        blocks[lb].n_mtf = out_base + 1;
+    }
+    __syncthreads();
+    int32_t *fq = freq_all + (uint64_t)lb * 258;
+    for (int i = threadIdx.x; i < 258; i += MT) fq[i] = s_freq[i];
+    (void)s_carry;
+}
+
+int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
+{
+    if (nb == 0) return S3G_OK;
+    size_t slots = (size_t)nb * BLK_STRIDE;
+    S3G_TRY(ctx->mtf0.ensure(slots));                 // MTF ranks before zero-run coding
+    S3G_TRY(ctx->mtfv16.ensure(slots * 2));
+    S3G_TRY(ctx->mtf_freq.ensure((size_t)nb * 258 * 4));
+    S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
+               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
+    return check_launch("mtf");
+}
+
+// =============================================================================
+// (3d) Huffman table selection and emission
+// =============================================================================
+constexpr int HT = 1024;
+constexpr int G_SIZE = 50;               // BZ_G_SIZE
+constexpr int N_ITERS = 4;               // BZ_N_ITERS
+constexpr int MAX_SEL = 18002;           // BZ_MAX_SELECTORS
+constexpr int ALPHA_MAX = 258;
+
+// bz/huffman.c:63-148, run verbatim by one thread per table
+__device__ void hb_make_lengths(uint8_t *len, const int32_t *freq, int alpha, int max_len)
+{
+    int32_t heap[ALPHA_MAX + 2], weight[ALPHA_MAX * 2], parent[ALPHA_MAX * 2];
+    for (int i = 0; i < alpha; i++) weight[i + 1] = (freq[i] == 0 ? 1 : freq[i]) << 8;
+    for (;;) {
+        int nnodes = alpha, nheap = 0;
+        heap[0] = 0; weight[0] = 0; parent[0] = -2;
+        for (int i = 1; i <= alpha; i++) {
+            parent[i] = -1;
+            nheap++;
+            int z = nheap, t = i;
+            while (weight[t] < weight[heap[z >> 1]]) { heap[z] = heap[z >> 1]; z >>= 1; }
+            heap[z] = t;
+        }
+        while (nheap > 1) {
+            int n12[2];
+#pragma unroll 1
+            for (int q = 0; q < 2; q++) {
+                n12[q] = heap[1]; heap[1] = heap[nheap]; nheap--;
+                int z = 1, t = heap[1];
+                for (;;) {
+                    int y = z << 1;
+                    if (y > nheap) break;
+                    if (y < nheap && weight[heap[y + 1]] < weight[heap[y]]) y++;
+                    if (weight[t] < weight[heap[y]]) break;
+                    heap[z] = heap[y]; z = y;
+                }
+                heap[z] = t;
+            }
+            nnodes++;
+            parent[n12[0]] = parent[n12[1]] = nnodes;
+            uint32_t w1 = (uint32_t)weight[n12[0]], w2 = (uint32_t)weight[n12[1]];
+            uint32_t d1 = w1 & 0xffu, d2 = w2 & 0xffu;
+            weight[nnodes] = (int32_t)(((w1 & 0xffffff00u) + (w2 & 0xffffff00u)) | (1u + (d1 > d2 ? d1 : d2)));
+            parent[nnodes] = -1;
+            nheap++;
+            int z = nheap, t = nnodes;
+            while (weight[t] < weight[heap[z >> 1]]) { heap[z] = heap[z >> 1]; z >>= 1; }
+            heap[z] = t;
+        }
+        bool too_long = false;
+        for (int i = 1; i <= alpha; i++) {
+            int j = 0, k = i;
+            while (parent[k] >= 0) { k = parent[k]; j++; }
+            len[i - 1] = (uint8_t)j;
+            if (j > max_len) too_long = true;
+        }
+        if (!too_long) break;
+        for (int i = 1; i <= alpha; i++) { int j = weight[i] >> 8; j = 1 + (j / 2); weight[i] = j << 8; }
+    }
+}
+
+// MSB-first bit writer over 32-bit words.  Words wholly inside the writer's bit
+// range are stored; the first and last (possibly shared) words are OR-ed in.
+struct BitW {
+    uint32_t *words;
+    uint64_t widx;       // next word to flush
+    uint64_t acc;        // pending bits, right-aligned
+    int nacc;            // number of pending bits (< 32 after put)
+    bool first;
+    __device__ void begin(uint32_t *w, uint64_t bitpos)
+    {
+        words = w; widx = bitpos >> 5; nacc = (int)(bitpos & 31); acc = 0; first = true;
+    }
+    __device__ __forceinline__ void put(int n, uint32_t v)
+    {
+        acc = (acc << n) | v; nacc += n;
+        if (nacc >= 32) {
+            uint32_t out = (uint32_t)(acc >> (nacc - 32));
+            if (first) { atomicOr(&words[widx], out); first = false; } else words[widx] = out;
+            widx++; nacc -= 32;
+            acc &= (1ull << nacc) - 1;
+        }
+    }
+    __device__ void end()
+    {
+        if (nacc > 0) atomicOr(&words[widx], (uint32_t)(acc << (32 - nacc)));
+    }
+};
+
+struct HuffSmem {
+    uint8_t  len[6][ALPHA_MAX + 2];
+    int32_t  rfreq[6][ALPHA_MAX];
+    int32_t  code[6][ALPHA_MAX];
+    uint8_t  selector[MAX_SEL + 2];
+    uint8_t  sel_mtf[MAX_SEL + 2];
+    uint32_t scan[33];
+    uint32_t tab_bits[8];
+    uint32_t hdr_bits;
+};
+
+// first_block_flags: bit0 set -> this block also carries nothing extra; stream headers are added by the assembler
+__global__ void __launch_bounds__(HT) k_huff(const uint16_t *mtfv_all, const int32_t *freq_all, const uint8_t *in_use_all,
+                                             BlockInfo *blocks, uint32_t *bits_all, uint8_t *sel_out, uint8_t *len_out,
+                                             int with_block_header)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HuffSmem &S = *reinterpret_cast<HuffSmem *>(smem_raw);
+    const uint32_t lb = blockIdx.x;
+    BlockInfo &B = blocks[lb];
+    const int nmtf = (int)B.n_mtf;
+    const int alpha = (int)B.n_in_use + 2;
+    const uint16_t *mtfv = mtfv_all + (uint64_t)lb * BLK_STRIDE;
+    const int32_t *mfreq = freq_all + (uint64_t)lb * 258;
+    const uint8_t *in_use = in_use_all + (uint64_t)lb * 256;
+    uint32_t *words = bits_all + (uint64_t)lb * BITS_WORDS;
+    const int ng = nmtf < 200 ? 2 : nmtf < 600 ? 3 : nmtf < 1200 ? 4 : nmtf < 2400 ? 5 : 6;   // bz/compress.c:273-277
+    const int nsel = (nmtf + G_SIZE - 1) / G_SIZE;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < 6 * (ALPHA_MAX + 2); i += HT) (&S.len[0][0])[i] = 15;   // BZ_GREATER_ICOST
+    __syncthreads();
+    if (tid == 0) {     // initial partition, bz/compress.c:280-317
+        int npart = ng, remf = nmtf, gs = 0;
+        while (npart > 0) {
+            int tfreq = remf / npart, ge = gs - 1, afreq = 0;
+            while (afreq < tfreq && ge < alpha - 1) { ge++; afreq += mfreq[ge]; }
+            if (ge > gs && npart != ng && npart != 1 && ((ng - npart) % 2 == 1)) { afreq -= mfreq[ge]; ge--; }
+            for (int v = 0; v < alpha; v++) S.len[npart - 1][v] = (v >= gs && v <= ge) ? 0 : 15;
+            npart--; gs = ge + 1; remf -= afreq;
+        }
+    }
+    __syncthreads();
+    for (int iter = 0; iter < N_ITERS; iter++) {
+        for (int i = tid; i < 6 * ALPHA_MAX; i += HT) (&S.rfreq[0][0])[i] = 0;
+        __syncthreads();
+        for (int g = tid; g < nsel; g += HT) {
+            int gs = g * G_SIZE, ge = min(gs + G_SIZE, nmtf);
+            uint32_t cost[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = gs; i < ge; i++) {
+                int v = mtfv[i];
+#pragma unroll
+                for (int t = 0; t < 6; t++) cost[t] += S.len[t][v];
+            }
+            int bt = 0; uint32_t bc = cost[0];
+#pragma unroll
+            for (int t = 1; t < 6; t++) if (t < ng && cost[t] < bc) { bc = cost[t]; bt = t; }   // first minimum, :399-401
+            S.selector[g] = (uint8_t)bt;
+            for (int i = gs; i < ge; i++) atomicAdd(&S.rfreq[bt][mtfv[i]], 1);
+        }
+        __syncthreads();
+        if (tid < ng) hb_make_lengths(S.len[tid], S.rfreq[tid], alpha, 17);
+        __syncthreads();
+    }
+    // codes (bz/huffman.c:152-166) and per-table header sizes
+    if (tid < ng) {
+        int mn = 32, mx = 0;
+        for (int i = 0; i < alpha; i++) { int L = S.len[tid][i]; mx = max(mx, L); mn = min(mn, L); }
+        int vec = 0;
+        for (int nlen = mn; nlen <= mx; nlen++) {
+            for (int i = 0; i < alpha; i++) if (S.len[tid][i] == nlen) S.code[tid][i] = vec++;
+            vec <<= 1;
+        }
+        uint32_t bits = 5; int cur = S.len[tid][0];
+        for (int i = 0; i < alpha; i++) { int L = S.len[tid][i]; bits += 2u * (uint32_t)abs(L - cur) + 1; cur = L; }
+        S.tab_bits[tid] = bits;
+    }
+    if (tid == 32) {   // selector MTF (bz/compress.c:462-478)
+        uint8_t pos[6];
+        for (int i = 0; i < ng; i++) pos[i] = (uint8_t)i;
+        for (int i = 0; i < nsel; i++) {
+            uint8_t v = S.selector[i]; int j = 0; uint8_t carry = pos[0];
+            while (carry != v) { j++; uint8_t t = pos[j]; pos[j] = carry; carry = t; }
+            pos[0] = carry;
+            S.sel_mtf[i] = (uint8_t)j;
+        }
+    }
+    if (tid == 64) {   // size of the fixed part
+        uint32_t hb = with_block_header ? 105u : 0u;
+        hb += 16;
+        for (int i = 0; i < 16; i++) { bool u = false; for (int j = 0; j < 16; j++) u |= in_use[i * 16 + j] != 0; if (u) hb += 16; }
+        hb += 3 + 15;
+        S.hdr_bits = hb;
+    }
+    __syncthreads();
+    // ---- layout: [fixed part][selectors][tables][symbols] ----
+    const int spt = (nsel + HT - 1) / HT;          // selectors (= groups) per thread
+    const int g0 = min(tid * spt, nsel), g1 = min(g0 + spt, nsel);
+    uint32_t my_sel_bits = 0, my_sym_bits = 0;
+    for (int g = g0; g < g1; g++) {
+        my_sel_bits += S.sel_mtf[g] + 1u;
+        int gs = g * G_SIZE, ge = min(gs + G_SIZE, nmtf);
+        const uint8_t *ln = S.len[S.selector[g]];
+        for (int i = gs; i < ge; i++) my_sym_bits += ln[mtfv[i]];
+    }
+    uint32_t sel_total, sym_total;
+    uint32_t sel_ex = block_excl_sum<uint32_t>(my_sel_bits, S.scan, &sel_total);
+    uint32_t sym_ex = block_excl_sum<uint32_t>(my_sym_bits, S.scan, &sym_total);
+    uint32_t tab_total = 0, tab_off[6];
+    for (int t = 0; t < ng; t++) { tab_off[t] = tab_total; tab_total += S.tab_bits[t]; }
+    const uint64_t sel_base = S.hdr_bits, tab_base = sel_base + sel_total, sym_base = tab_base + tab_total;
+    const uint64_t total_bits = sym_base + sym_total;
+    const uint32_t total_words = (uint32_t)((total_bits + 31) >> 5) + 1;
+    for (uint32_t i = tid; i < total_words; i += HT) words[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        BitW bw; bw.begin(words, 0);
+        if (with_block_header) {     // bz/compress.c:632-650
+            bw.put(24, 0x314159u); bw.put(24, 0x265359u);
+            bw.put(16, B.crc >> 16); bw.put(16, B.crc & 0xffffu);
+            bw.put(1, 0);
+            bw.put(24, (uint32_t)B.orig_ptr & 0xffffffu);
+        }
+        uint32_t used16 = 0;
+        for (int i = 0; i < 16; i++) { bool u = false; for (int j = 0; j < 16; j++) u |= in_use[i * 16 + j] != 0; if (u) used16 |= 1u << (15 - i); }
+        bw.put(16, used16);
+        for (int i = 0; i < 16; i++) if (used16 & (1u << (15 - i))) {
+            uint32_t m = 0;
+            for (int j = 0; j < 16; j++) if (in_use[i * 16 + j]) m |= 1u << (15 - j);
+            bw.put(16, m);
+        }
+        bw.put(3, (uint32_t)ng); bw.put(15, (uint32_t)nsel);
+        bw.end();
+    }
+    if (g0 < g1) {   // selectors in unary (:519-524)
+        BitW bw; bw.begin(words, sel_base + sel_ex);
+        for (int g = g0; g < g1; g++) { int j = S.sel_mtf[g]; bw.put(j + 1, (1u << (j + 1)) - 2u); }
+        bw.end();
+    }
+    if (tid >= 128 && tid < 128 + ng) {   // delta-coded tables (:531-539)
+        int t = tid - 128;
+        BitW bw; bw.begin(words, tab_base + tab_off[t]);
+        int cur = S.len[t][0];
+        bw.put(5, (uint32_t)cur);
+        for (int i = 0; i < alpha; i++) {
+            int L = S.len[t][i];
+            while (cur < L) { bw.put(2, 2); cur++; }
+            while (cur > L) { bw.put(2, 3); cur--; }
+            bw.put(1, 0);
+        }
+        bw.end();
+    }
+    if (g0 < g1) {   // the symbols (:545-594)
+        BitW bw; bw.begin(words, sym_base + sym_ex);
+        for (int g = g0; g < g1; g++) {
+            int gs = g * G_SIZE, ge = min(gs + G_SIZE, nmtf);
+            const uint8_t *ln = S.len[S.selector[g]];
+            const int32_t *cd = S.code[S.selector[g]];
+            for (int i = gs; i < ge; i++) { int v = mtfv[i]; bw.put(ln[v], (uint32_t)cd[v]); }
+        }
+        bw.end();
+    }
+    if (tid == 0) B.n_bits = total_bits;
+    if (sel_out) {
+        for (int i = tid; i < nsel; i += HT) sel_out[(uint64_t)lb * (MAX_SEL + 2) + i] = S.selector[i];
+        for (int i = tid; i < 6 * ALPHA_MAX; i += HT) len_out[(uint64_t)lb * 6 * ALPHA_MAX + i] = S.len[i / ALPHA_MAX][i % ALPHA_MAX];
+    }
+}
+
+int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t *d_sel_out, uint8_t *d_len_out)
+{
+    if (nb == 0) return S3G_OK;
+    S3G_TRY(ctx->bits.ensure((size_t)nb * BITS_WORDS * 4));
+    static bool attr_done = false;
+    if (!attr_done) {
+        S3G_CUDA(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
+        attr_done = true;
+    }
+    S3G_LAUNCH(ctx, k_huff, (unsigned)nb, HT, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
+               ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
+               d_sel_out, d_len_out, with_block_header);
+    return check_launch("huff");
+}
+
+}  // namespace s3g

@@ -1,0 +1,436 @@
+// rle_crc.cu -- kernel (3a): bzip2's initial run-length coding, block cut and
+// block CRC for a batch of streams (one stream per chromosome).
+//
+// Reference: the byte-serial state machine of ADD_CHAR_TO_BLOCK /
+// add_pair_to_block / copy_input_until_stop / handle_compress in the
+// reference's vendored libbz2 (bz/bzlib.c:225-338, :370-412), for a stream fed
+// with one BZ_FINISH action.  Restated for parallel execution:
+//   * a "chunk" is a maximal run of equal bytes split every 255 bytes; a chunk
+//     of length L emits min(L,4) copies plus, if L >= 4, the byte L-4;
+//   * the emitted length is a prefix sum over input bytes, so output offsets
+//     come from a device-wide scan and every byte is placed independently;
+//   * blocks are whole chunks: a block closes after the first chunk that takes
+//     it to >= nblockMAX bytes -- unless exactly one input byte is left in the
+//     stream, which libbz2 flushes into the same block (bz/bzlib.c:393-396);
+//   * the block CRC (CRC-32/BZIP2, bz/bzlib_private.h:157-172) covers the
+//     pre-RLE bytes of the block's chunks, a contiguous input range.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace s3g {
+
+constexpr int RT = 256;            // threads per tile
+constexpr int RB = 16;             // bytes per thread
+constexpr int RTILE = RT * RB;     // 4096 input bytes per tile
+
+struct StreamMap {
+    const uint64_t *soff;   // [n_streams + 1]
+    uint64_t n_streams;
+    // is position i the first byte of a stream?  (only evaluated where bytes repeat)
+    __device__ __forceinline__ bool is_start(uint64_t i) const
+    {
+        uint64_t lo = 0, hi = n_streams;            // find soff[k] == i
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            uint64_t v = soff[mid];
+            if (v == i) return true;
+            if (v < i) lo = mid + 1; else hi = mid;
+        }
+        return false;
+    }
+};
+
+struct ByteWin {
+    uint8_t b[RB + 2];   // b[0] = byte before, b[1..RB] = the thread's bytes, b[RB+1] = byte after
+    uint64_t pos0;       // absolute index of b[1]
+    int cnt;             // valid bytes (0..RB)
+};
+
+__device__ __forceinline__ void load_win(const uint8_t *in, uint64_t n, uint64_t pos0, ByteWin &w)
+{
+    w.pos0 = pos0;
+    w.cnt = pos0 >= n ? 0 : (n - pos0 >= RB ? RB : (int)(n - pos0));
+    if (w.cnt == RB) {
+        uint4 v = *reinterpret_cast<const uint4 *>(in + pos0);
+        unsigned x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < RB; k++) w.b[1 + k] = (uint8_t)(x[k >> 2] >> (8 * (k & 3)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < RB; k++) w.b[1 + k] = k < w.cnt ? in[pos0 + k] : 0;
+    }
+    w.b[0] = (pos0 > 0 && w.cnt > 0) ? in[pos0 - 1] : 0;
+    w.b[RB + 1] = (w.cnt == RB && pos0 + RB < n) ? in[pos0 + RB] : 0;
+}
+
+// run-start test for byte k (0-based inside the window)
+__device__ __forceinline__ bool run_starts(const ByteWin &w, int k, const StreamMap &sm)
+{
+    uint64_t i = w.pos0 + k;
+    if (i == 0) return true;
+    if (w.b[1 + k] != w.b[k]) return true;
+    return sm.is_start(i);
+}
+
+// ---- pass 1: last run start per tile (max-scan aggregate) --------------------
+__global__ void __launch_bounds__(RT) k_rle_runs(const uint8_t *in, uint64_t n, StreamMap sm, uint64_t *agg)
+{
+    __shared__ uint64_t s[33];
+    ByteWin w;
+    load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
+    uint64_t last = 0;   // position + 1 of the last run start among my bytes
+#pragma unroll
+    for (int k = 0; k < RB; k++)
+        if (k < w.cnt && run_starts(w, k, sm)) last = w.pos0 + k + 1;
+    uint64_t tot;
+    block_excl_max<uint64_t>(last, s, &tot);
+    if (threadIdx.x == 0) agg[blockIdx.x] = tot;
+}
+
+struct MaxU64 {
+    typedef uint64_t T;
+    __host__ __device__ static T identity() { return 0; }
+    __host__ __device__ static T op(T a, T b) { return a > b ? a : b; }
+};
+struct SumU64b {
+    typedef uint64_t T;
+    __host__ __device__ static T identity() { return 0; }
+    __host__ __device__ static T op(T a, T b) { return a + b; }
+};
+
+// Per-thread view of the RLE1 state of its RB bytes: offset inside the run for
+// every byte, chunk-end flags and emitted byte counts.
+struct RleLocal {
+    uint32_t emit_mask;   // bit k: byte k is copied (chunk offset < 4)
+    uint32_t cnt_mask;    // bit k: byte k ends a chunk of length >= 4 (emits the count byte)
+    uint8_t  cnt_val[RB]; // count byte value where cnt_mask is set
+    uint32_t total;       // emitted bytes
+};
+
+// `carry` = position+1 of the last run start before this tile (exclusive max-scan).
+__device__ __forceinline__ void rle_local(const ByteWin &w, const StreamMap &sm, uint64_t carry, uint64_t *s_max,
+                                          RleLocal &r, uint64_t n)
+{
+    uint64_t last = 0;
+    uint32_t startmask = 0;
+#pragma unroll
+    for (int k = 0; k < RB; k++)
+        if (k < w.cnt && run_starts(w, k, sm)) { last = w.pos0 + k + 1; startmask |= 1u << k; }
+    uint64_t tot;
+    uint64_t before = block_excl_max<uint64_t>(last, s_max, &tot);   // run start in effect before my first byte
+    if (carry > before) before = carry;
+    uint64_t rs = before;     // position+1 of current run start
+    r.emit_mask = 0; r.cnt_mask = 0; r.total = 0;
+#pragma unroll
+    for (int k = 0; k < RB; k++) {
+        r.cnt_val[k] = 0;
+        if (k < w.cnt) {
+            uint64_t i = w.pos0 + k;
+            if (startmask & (1u << k)) rs = i + 1;
+            uint32_t c = (uint32_t)((i - (rs - 1)) % 255u);
+            // chunk ends here if the next byte starts a new run, the chunk is full, or the input ends
+            bool last_in_chunk;
+            if (c == 254 || i + 1 >= n) last_in_chunk = true;
+            else if (w.b[2 + k] != w.b[1 + k]) last_in_chunk = true;
+            else last_in_chunk = sm.is_start(i + 1);
+            if (c < 4) { r.emit_mask |= 1u << k; r.total++; }
+            if (last_in_chunk && c >= 3) { r.cnt_mask |= 1u << k; r.cnt_val[k] = (uint8_t)(c - 3); r.total++; }
+        }
+    }
+}
+
+// ---- pass 2: emitted bytes per tile -----------------------------------------
+__global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64_t n, StreamMap sm, const uint64_t *run_carry,
+                                                        uint64_t *agg)
+{
+    __shared__ uint64_t s_max[33];
+    __shared__ uint32_t s_sum[33];
+    ByteWin w;
+    load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
+    RleLocal r;
+    rle_local(w, sm, run_carry[blockIdx.x], s_max, r, n);
+    uint32_t tot;
+    block_excl_sum<uint32_t>(r.total, s_sum, &tot);
+    if (threadIdx.x == 0) agg[blockIdx.x] = tot;
+}
+
+// ---- pass 3: block cut, one thread per stream -------------------------------
+// Serial walk inside one tile; returns through the in/out arguments.
+struct CutWalker {
+    const uint8_t *in; uint64_t n; StreamMap sm;
+    const uint64_t *run_carry; const uint64_t *e_base;   // per tile
+    // E(x) = emitted bytes of input bytes < x (x must be a chunk boundary or any position)
+    // Walk from the start of the tile containing `from_tile` and find the first chunk end x >= lo
+    // with E(x) >= target and x <= s1.  Returns x (or s1 if not reached) and E(x).
+    __device__ void find(uint64_t tile, uint64_t target, uint64_t s1, uint64_t *x_out, uint64_t *e_out) const
+    {
+        uint64_t i = tile * RTILE;
+        uint64_t rs = run_carry[tile];   // position+1
+        uint64_t e = e_base[tile];
+        uint8_t prev = i > 0 ? in[i - 1] : 0;
+        for (; i < s1; i++) {
+            uint8_t c = in[i];
+            if (i == 0 || c != prev || sm.is_start(i)) rs = i + 1;
+            uint32_t o = (uint32_t)((i - (rs - 1)) % 255u);
+            bool last;
+            if (o == 254 || i + 1 >= n) last = true;
+            else if (in[i + 1] != c) last = true;
+            else last = sm.is_start(i + 1);
+            if (o < 4) e++;
+            if (last && o >= 3) e++;
+            prev = c;
+            if (last && e >= target) { *x_out = i + 1; *e_out = e; return; }
+        }
+        *x_out = s1; *e_out = e;
+    }
+};
+
+__device__ __forceinline__ uint64_t e_at(const CutWalker &cw, uint64_t x)
+{
+    // E at an arbitrary position that is a stream boundary (hence a chunk boundary)
+    uint64_t tile = x / RTILE;
+    if (x == tile * RTILE) return cw.e_base[tile];
+    uint64_t i = tile * RTILE, rs = cw.run_carry[tile], e = cw.e_base[tile];
+    uint8_t prev = i > 0 ? cw.in[i - 1] : 0;
+    for (; i < x; i++) {
+        uint8_t c = cw.in[i];
+        if (i == 0 || c != prev || cw.sm.is_start(i)) rs = i + 1;
+        uint32_t o = (uint32_t)((i - (rs - 1)) % 255u);
+        bool last;
+        if (o == 254 || i + 1 >= cw.n) last = true;
+        else if (cw.in[i + 1] != c) last = true;
+        else last = cw.sm.is_start(i + 1);
+        if (o < 4) e++;
+        if (last && o >= 3) e++;
+        prev = c;
+    }
+    return e;
+}
+
+// Blocks of stream s are written at provisional slots prov(s) + k and compacted afterwards.
+__global__ void k_rle_cut(CutWalker cw, uint64_t n_tiles, uint32_t nmax, uint64_t slot_cap,
+                          BlockInfo *prov, uint32_t *blocks_per_stream, uint64_t *prov_base)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cw.sm.n_streams) return;
+    uint64_t s0 = cw.sm.soff[s], s1 = cw.sm.soff[s + 1];
+    uint64_t e0 = e_at(cw, s0), e1 = e_at(cw, s1);
+    uint64_t slot = e0 / nmax + s;     // upper bound on the blocks of earlier streams
+    prov_base[s] = slot;
+    uint32_t nb = 0;
+    uint64_t start = s0, base = e0;
+    while (start < s1) {
+        uint64_t target = base + nmax;
+        uint64_t x = s1, ex = e1;
+        if (e1 >= target) {
+            // tile holding the crossing: last tile with e_base < target
+            uint64_t lo = start / RTILE, hi = (s1 - 1) / RTILE;
+            while (lo < hi) {
+                uint64_t mid = (lo + hi + 1) >> 1;
+                if (cw.e_base[mid] < target) lo = mid; else hi = mid - 1;
+            }
+            cw.find(lo, target, s1, &x, &ex);
+            if (x + 1 >= s1) { x = s1; ex = e1; }   // a single trailing byte is flushed into this block
+        }
+        if (slot + nb < slot_cap) {
+            BlockInfo bi;
+            memset(&bi, 0, sizeof bi);
+            bi.in_start = start; bi.in_end = x; bi.e_base = base; bi.nblock = (uint32_t)(ex - base);
+            bi.chrom = (uint32_t)s; bi.orig_ptr = -1;
+            prov[slot + nb] = bi;
+        }
+        nb++;
+        start = x; base = ex;
+    }
+    blocks_per_stream[s] = nb;
+    (void)n_tiles;
+}
+
+__global__ void k_stream_block_scan(const uint32_t *blocks_per_stream, uint64_t n_streams, uint64_t *first_block,
+                                    uint64_t *total)
+{
+    // tiny serial scan (streams are few); one thread
+    if (blockIdx.x || threadIdx.x) return;
+    uint64_t acc = 0;
+    for (uint64_t s = 0; s < n_streams; s++) { first_block[s] = acc; acc += blocks_per_stream[s]; }
+    first_block[n_streams] = acc;
+    *total = acc;
+}
+
+__global__ void k_compact_blocks(const BlockInfo *prov, const uint64_t *prov_base, const uint64_t *first_block,
+                                 uint64_t n_streams, BlockInfo *blocks, s3g_chrom *chroms)
+{
+    uint64_t s = blockIdx.x;
+    if (s >= n_streams) return;
+    uint64_t nb = first_block[s + 1] - first_block[s];
+    for (uint64_t k = threadIdx.x; k < nb; k += blockDim.x) blocks[first_block[s] + k] = prov[prov_base[s] + k];
+    if (threadIdx.x == 0 && chroms) chroms[s].n_blocks = (uint32_t)nb;
+}
+
+// ---- pass 4: write the RLE1 bytes into the block slots ----------------------
+__global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n, StreamMap sm, const uint64_t *run_carry,
+                                                   const uint64_t *e_base, const BlockInfo *blocks, uint64_t n_blocks,
+                                                   uint8_t *blk_bytes, uint8_t *in_use)
+{
+    __shared__ uint64_t s_max[33];
+    __shared__ uint32_t s_sum[33];
+    ByteWin w;
+    load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
+    RleLocal r;
+    rle_local(w, sm, run_carry[blockIdx.x], s_max, r, n);
+    uint32_t tot;
+    uint32_t ex = block_excl_sum<uint32_t>(r.total, s_sum, &tot);
+    if (w.cnt == 0) return;
+    uint64_t e = e_base[blockIdx.x] + ex;
+    // block containing my first byte: last block with in_start <= pos0
+    uint64_t lo = 0, hi = n_blocks - 1;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi + 1) >> 1;
+        if (blocks[mid].in_start <= w.pos0) lo = mid; else hi = mid - 1;
+    }
+    uint64_t bi = lo;
+    uint64_t b_end = blocks[bi].in_end, b_e0 = blocks[bi].e_base;
+    uint8_t *dst = blk_bytes + bi * (uint64_t)BLK_STRIDE;
+    uint8_t *use = in_use + bi * 256;
+#pragma unroll
+    for (int k = 0; k < RB; k++) {
+        if (k < w.cnt) {
+            uint64_t i = w.pos0 + k;
+            if (i >= b_end) {
+                bi++;
+                b_end = blocks[bi].in_end; b_e0 = blocks[bi].e_base;
+                dst = blk_bytes + bi * (uint64_t)BLK_STRIDE; use = in_use + bi * 256;
+            }
+            if (r.emit_mask & (1u << k)) { dst[e - b_e0] = w.b[1 + k]; use[w.b[1 + k]] = 1; e++; }
+            if (r.cnt_mask & (1u << k)) { dst[e - b_e0] = r.cnt_val[k]; use[r.cnt_val[k]] = 1; e++; }
+        }
+    }
+}
+
+// ---- pass 5: block CRC -------------------------------------------------------
+__device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b)
+{
+    // a*b mod P over GF(2), P = x^32 + 0x04C11DB7, bit 31 = x^31
+    uint32_t r = 0;
+#pragma unroll 1
+    for (int i = 31; i >= 0; i--) {
+        uint32_t msb = r & 0x80000000u;
+        r <<= 1;
+        if (msb) r ^= 0x04C11DB7u;
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+// x^(8*nbytes) mod P
+__device__ uint32_t gf_xpow8(uint64_t nbytes)
+{
+    uint32_t result = 1;           // the polynomial "1"
+    uint32_t sq = 0x100;           // x^8
+    while (nbytes) {
+        if (nbytes & 1) result = gf_mulmod(result, sq);
+        sq = gf_mulmod(sq, sq);
+        nbytes >>= 1;
+    }
+    return result;
+}
+
+constexpr int CRC_T = 512;
+__global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInfo *blocks)
+{
+    __shared__ uint32_t tab[256];
+    __shared__ uint32_t part[CRC_T];
+    for (int i = threadIdx.x; i < 256; i += CRC_T) {
+        uint32_t c = (uint32_t)i << 24;
+        for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
+        tab[i] = c;
+    }
+    __syncthreads();
+    BlockInfo *bi = &blocks[blockIdx.x];
+    uint64_t a = bi->in_start, len = bi->in_end - bi->in_start;
+    uint64_t per = (len + CRC_T - 1) / CRC_T;
+    uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per;
+    if (lo > len) lo = len;
+    if (hi > len) hi = len;
+    uint32_t c = threadIdx.x == 0 ? 0xFFFFFFFFu : 0u;     // only the first segment carries the init state
+    const uint8_t *p = in + a;
+    for (uint64_t i = lo; i < hi; i++) c = (c << 8) ^ tab[(c >> 24) ^ p[i]];
+    // shift by the bytes that follow this segment
+    uint64_t after = len - hi;
+    if (c != 0 && after) c = gf_mulmod(c, gf_xpow8(after));
+    part[threadIdx.x] = c;
+    __syncthreads();
+    for (int d = CRC_T / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) part[threadIdx.x] ^= part[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bi->crc = ~part[0];
+}
+
+// unseqToSeq map + nInUse per block (makeMaps_e, bz/compress.c:106-115)
+__global__ void k_block_maps(const uint8_t *in_use, BlockInfo *blocks, uint8_t *seq_map)
+{
+    __shared__ uint32_t s[33];
+    uint64_t b = blockIdx.x;
+    uint32_t u = in_use[b * 256 + threadIdx.x] ? 1u : 0u;
+    uint32_t tot;
+    uint32_t ex = block_excl_sum<uint32_t>(u, s, &tot);
+    seq_map[b * 256 + threadIdx.x] = (uint8_t)ex;
+    if (threadIdx.x == 0) blocks[b].n_in_use = tot;
+}
+
+int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams, int level,
+                CutResult *out)
+{
+    *out = CutResult();
+    uint32_t nmax = 100000u * (uint32_t)level - 19;     // bz/bzlib.c:194
+    uint64_t ntiles = (n + RTILE - 1) / RTILE;
+    if (ntiles == 0) ntiles = 1;
+    if (ntiles > 0x7fffffffull) { set_error("stream buffer too large"); return S3G_E_LIMIT; }
+    S3G_TRY(ctx->rle_carry.ensure((ntiles + 2) * 8));
+    S3G_TRY(ctx->rle_ebase.ensure((ntiles + 2) * 8));
+    S3G_TRY(ctx->scalars.ensure(64 * 8));
+    uint64_t *d_sc = ctx->scalars.as<uint64_t>();
+    uint64_t *run_carry = ctx->rle_carry.as<uint64_t>(), *e_base = ctx->rle_ebase.as<uint64_t>();
+    StreamMap sm{d_soff, n_streams};
+    S3G_LAUNCH(ctx, k_rle_runs, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry);
+    S3G_LAUNCH(ctx, k_scan_agg<MaxU64>, 1, SCAN_THREADS, 0, run_carry, ntiles, (uint64_t *)nullptr);
+    S3G_LAUNCH(ctx, k_rle_emit_count, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base);
+    S3G_LAUNCH(ctx, k_scan_agg<SumU64b>, 1, SCAN_THREADS, 0, e_base, ntiles, d_sc + 16);
+    // e_base[ntiles] = total, so E() can be evaluated at n
+    S3G_CUDA(cudaMemcpyAsync(e_base + ntiles, d_sc + 16, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 16, d_sc + 16, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    S3G_TRY(check_launch("rle scan"));
+    uint64_t e_total = ctx->h_scalars[16];
+    uint64_t slot_cap = e_total / nmax + n_streams + 2;
+    S3G_TRY(ctx->blk_prov.ensure(slot_cap * sizeof(BlockInfo)));       // provisional slots
+    S3G_TRY(ctx->blocks.ensure(slot_cap * sizeof(BlockInfo)));
+    S3G_TRY(ctx->stream_tab.ensure((n_streams + 2) * 8 * 3));
+    uint64_t *prov_base = ctx->stream_tab.as<uint64_t>();
+    uint64_t *first_block = prov_base + (n_streams + 2);
+    uint32_t *bps = reinterpret_cast<uint32_t *>(first_block + (n_streams + 2));
+    CutWalker cw{d_in, n, sm, run_carry, e_base};
+    S3G_LAUNCH(ctx, k_rle_cut, (unsigned)((n_streams + 31) / 32), 32, 0, cw, ntiles, nmax, slot_cap,
+               ctx->blk_prov.as<BlockInfo>(), bps, prov_base);
+    S3G_LAUNCH(ctx, k_stream_block_scan, 1, 1, 0, bps, n_streams, first_block, d_sc + 17);
+    S3G_LAUNCH(ctx, k_compact_blocks, (unsigned)n_streams, 64, 0, ctx->blk_prov.as<BlockInfo>(), prov_base, first_block,
+               n_streams, ctx->blocks.as<BlockInfo>(), (s3g_chrom *)nullptr);
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 17, d_sc + 17, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    S3G_TRY(check_launch("rle cut"));
+    uint64_t nb = ctx->h_scalars[17];
+    out->n_blocks = nb;
+    if (nb == 0) return S3G_OK;
+    S3G_TRY(ctx->blk_bytes.ensure(nb * (uint64_t)BLK_STRIDE));
+    S3G_TRY(ctx->in_use.ensure(nb * 256));
+    S3G_TRY(ctx->seq_map.ensure(nb * 256));
+    S3G_CUDA(cudaMemsetAsync(ctx->in_use.p, 0, nb * 256, ctx->stream));
+    BlockInfo *blocks = ctx->blocks.as<BlockInfo>();
+    S3G_LAUNCH(ctx, k_rle_write, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base, blocks, nb,
+               ctx->blk_bytes.as<uint8_t>(), ctx->in_use.as<uint8_t>());
+    S3G_LAUNCH(ctx, k_block_crc, (unsigned)nb, CRC_T, 0, d_in, blocks);
+    S3G_LAUNCH(ctx, k_block_maps, (unsigned)nb, 256, 0, ctx->in_use.as<uint8_t>(), blocks, ctx->seq_map.as<uint8_t>());
+    return check_launch("rle write");
+}
+
+}  // namespace s3g

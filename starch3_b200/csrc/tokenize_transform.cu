@@ -1,0 +1,362 @@
+// tokenize_transform.cu -- kernels (1) and (2) of the hot path.
+//
+// (1) newline scan + tab split + integer parse + chromosome-boundary flags:
+//     replaces produce_line / consume_line (hpp:158-199, :201-309) and the
+//     strcmp chromosome test (hpp:325-342).
+// (2) the starch coordinate transform update_transformation_state (hpp:428-504)
+//     with the per-chromosome reset (hpp:523-532) and the statistics the
+//     reference declares but never computes (hpp:61-62).
+// hpp = /root/reference/include/starch3api.hpp.
+//
+// The per-line dependencies are radius-1 (previous stop, previous length,
+// previous chromosome); everything else is scans for output offsets and
+// chromosome ids.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace s3g {
+
+constexpr int NL_THREADS = 256;
+constexpr int NL_SUB = NL_THREADS * 16;     // bytes per sub-iteration (one uint4 per thread)
+constexpr int NL_ITERS = 4;
+constexpr int NL_TILE = NL_SUB * NL_ITERS;  // 16 KiB of input per CTA
+
+__device__ __forceinline__ unsigned nl_mask16(const uint8_t *bed, uint64_t pos, uint64_t n)
+{
+    // bit k set <=> bed[pos+k] == '\n'
+    unsigned m = 0;
+    if (pos + 16 <= n) {
+        uint4 v = *reinterpret_cast<const uint4 *>(bed + pos);
+        unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            unsigned eq = __vcmpeq4(w[q], 0x0a0a0a0au);   // 0xff per matching byte
+            // gather the low bit of each byte into 4 bits
+            unsigned b = eq & 0x01010101u;
+            b = (b | (b >> 7) | (b >> 14) | (b >> 21)) & 0xfu;
+            m |= b << (4 * q);
+        }
+    } else {
+        for (int k = 0; k < 16; k++)
+            if (pos + k < n && bed[pos + k] == '\n') m |= 1u << k;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(NL_THREADS) k_count_newlines(const uint8_t *bed, uint64_t n, uint64_t *tile_cnt)
+{
+    __shared__ uint32_t sm[33];
+    uint64_t tile0 = (uint64_t)blockIdx.x * NL_TILE;
+    uint32_t c = 0;
+#pragma unroll
+    for (int it = 0; it < NL_ITERS; it++) {
+        uint64_t pos = tile0 + (uint64_t)it * NL_SUB + (uint64_t)threadIdx.x * 16;
+        if (pos < n) c += __popc(nl_mask16(bed, pos, n));
+    }
+    uint32_t tot;
+    block_excl_sum<uint32_t>(c, sm, &tot);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+}
+
+struct SumU64 {
+    typedef uint64_t T;
+    __host__ __device__ static T identity() { return 0; }
+    __host__ __device__ static T op(T a, T b) { return a + b; }
+};
+
+__global__ void __launch_bounds__(NL_THREADS) k_line_starts(const uint8_t *bed, uint64_t n, const uint64_t *tile_base,
+                                                            uint64_t *line_start)
+{
+    __shared__ uint32_t sm[33];
+    uint64_t tile0 = (uint64_t)blockIdx.x * NL_TILE;
+    uint64_t run = tile_base[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = 0;
+    for (int it = 0; it < NL_ITERS; it++) {
+        uint64_t pos = tile0 + (uint64_t)it * NL_SUB + (uint64_t)threadIdx.x * 16;
+        unsigned m = pos < n ? nl_mask16(bed, pos, n) : 0;
+        uint32_t tot;
+        uint32_t ex = block_excl_sum<uint32_t>(__popc(m), sm, &tot);
+        uint64_t idx = run + ex + 1;
+        while (m) {
+            int k = __ffs(m) - 1;
+            m &= m - 1;
+            line_start[idx++] = pos + k + 1;
+        }
+        run += tot;
+    }
+}
+
+// flags: bit0 = chromosome differs from the previous line (hpp:331), bit1 = malformed
+__global__ void k_parse_lines(const uint8_t *__restrict__ bed, const uint64_t *__restrict__ line_start, uint64_t n_lines,
+                              int64_t *__restrict__ start, int64_t *__restrict__ stop, uint32_t *__restrict__ rem_off,
+                              uint8_t *__restrict__ flags, unsigned long long *malformed)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    uint64_t p = line_start[i], e = line_start[i + 1] - 1;   // bed[e] == '\n'
+    int field = 0;
+    uint64_t acc = 0;
+    int neg = 0, st = 0;   // st: 0 = expecting sign/digit, 1 = in digits, 2 = number ended
+    int64_t v_start = 0, v_stop = 0;
+    uint64_t q = p, t0 = e;
+    for (; q < e; q++) {
+        uint8_t c = bed[q];
+        if (c == '\t') {
+            if (field == 0) t0 = q;
+            else if (field == 1) v_start = neg ? (int64_t)(0 - acc) : (int64_t)acc;
+            else { break; }
+            field++;
+            acc = 0; neg = 0; st = 0;
+            continue;
+        }
+        if (field >= 1) {
+            // sscanf("%lld") over the documented domain: [sign] digits, stop at the first other byte
+            if (st == 0 && (c == '-' || c == '+')) { neg = (c == '-'); st = 1; }
+            else if (st <= 1 && c >= '0' && c <= '9') { acc = acc * 10 + (uint64_t)(c - '0'); st = 1; }
+            else st = 2;
+        }
+    }
+    uint8_t fl = 0;
+    if (field == 2) v_stop = neg ? (int64_t)(0 - acc) : (int64_t)acc;   // ended by '\n' (BED3) or by the third tab
+    else fl |= 2;
+    // q == e (no fourth field) or q at the third tab
+    uint32_t ro = (uint32_t)((q < e ? q + 1 : e) - p);
+    if (i == 0) fl |= 1;
+    else {
+        // strcmp(chr, previous chr) != 0 (hpp:331); the previous line's field ends at its first tab
+        uint64_t pp = line_start[i - 1], cl = t0 - p;
+        bool diff = false;
+        for (uint64_t k = 0; k < cl; k++)
+            if (bed[p + k] != bed[pp + k]) { diff = true; break; }
+        if (!diff && bed[pp + cl] != '\t') diff = true;
+        if (diff) fl |= 1;
+    }
+    if (fl & 2) atomicAdd(malformed, 1ull);
+    start[i] = v_start; stop[i] = v_stop; rem_off[i] = ro; flags[i] = fl;
+}
+
+__device__ __forceinline__ int dec_len(int64_t v)
+{
+    // printed length of "%lld": n_digits (hpp:559-581) plus the sign it does not count
+    uint64_t a = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    int d = 1;
+    while (a >= 10) { a /= 10; d++; }
+    return d + (v < 0);
+}
+
+struct LineView {
+    const uint64_t *line_start;
+    const int64_t *start, *stop;
+    const uint32_t *rem_off;
+    const uint8_t *flags;
+    __device__ __forceinline__ void prev(uint64_t i, int64_t *p_stop, int64_t *p_len) const
+    {
+        if (flags[i] & 1) { *p_stop = 0; *p_len = 0; }                         // hpp:523-532
+        else { int64_t s0 = start[i - 1], s1 = stop[i - 1]; *p_stop = s1; *p_len = (int64_t)((uint64_t)s1 - (uint64_t)s0); }
+    }
+    __device__ __forceinline__ uint32_t out_len(uint64_t i) const
+    {
+        int64_t ps, pl; prev(i, &ps, &pl);
+        int64_t s = start[i], t = stop[i];
+        int64_t len = (int64_t)((uint64_t)t - (uint64_t)s), d = (int64_t)((uint64_t)s - (uint64_t)ps);
+        uint32_t rem_len = (uint32_t)(line_start[i + 1] - 1 - line_start[i]) - rem_off[i];
+        uint32_t o = (uint32_t)dec_len(d) + 1 + (rem_len ? rem_len + 1 : 0);
+        if (len != pl) o += 2 + (uint32_t)dec_len(len);
+        return o;
+    }
+};
+
+struct OutLenScan : SumU64 {
+    LineView lv;
+    uint64_t *line_tf_off;
+    __device__ T load(uint64_t i) const { return lv.out_len(i); }
+    __device__ void store(uint64_t i, T excl, T) const { line_tf_off[i] = excl; }
+};
+
+// segmented running max of stop (exclusive), producing each line's unique-base contribution
+struct SegMax {
+    int64_t v; int32_t seg; int32_t pad;
+};
+struct UniqScan {
+    typedef SegMax T;
+    const int64_t *start, *stop;
+    const uint8_t *flags;
+    int64_t *uniq;
+    __host__ __device__ static T identity() { T t; t.v = INT64_MIN; t.seg = 0; t.pad = 0; return t; }
+    __host__ __device__ static T op(T a, T b)
+    {
+        if (b.seg) return b;
+        T r; r.v = a.v > b.v ? a.v : b.v; r.seg = a.seg; r.pad = 0; return r;
+    }
+    __device__ T load(uint64_t i) const { T t; t.v = stop[i]; t.seg = flags[i] & 1; t.pad = 0; return t; }
+    __device__ void store(uint64_t i, T excl, T) const
+    {
+        int64_t rm = (flags[i] & 1) ? INT64_MIN : excl.v;
+        int64_t s = start[i], t = stop[i];
+        int64_t lo = s > rm ? s : rm;
+        uniq[i] = t > lo ? t - lo : 0;
+    }
+};
+
+struct Stat3 {
+    int64_t len_sum, uniq_sum; uint64_t chroms;
+};
+struct StatScan {
+    typedef Stat3 T;
+    const int64_t *start, *stop, *uniq;
+    const uint8_t *flags;
+    uint64_t *chrom_first;     // [n_chroms]
+    Stat3 *chrom_pref;         // [n_chroms]
+    __host__ __device__ static T identity() { T t; t.len_sum = 0; t.uniq_sum = 0; t.chroms = 0; return t; }
+    __host__ __device__ static T op(T a, T b) { T r; r.len_sum = a.len_sum + b.len_sum; r.uniq_sum = a.uniq_sum + b.uniq_sum; r.chroms = a.chroms + b.chroms; return r; }
+    __device__ T load(uint64_t i) const
+    {
+        T t; t.len_sum = (int64_t)((uint64_t)stop[i] - (uint64_t)start[i]); t.uniq_sum = uniq[i]; t.chroms = flags[i] & 1; return t;
+    }
+    __device__ void store(uint64_t i, T excl, T) const
+    {
+        if (flags[i] & 1) { chrom_first[excl.chroms] = i; chrom_pref[excl.chroms] = excl; }
+    }
+};
+
+__global__ void k_chrom_table(const uint8_t *bed, const uint64_t *line_start, const uint64_t *line_tf_off,
+                              const uint64_t *chrom_first, const Stat3 *chrom_pref, const Stat3 *stat_total,
+                              uint64_t n_chroms, uint64_t n_lines, uint64_t tf_total, s3g_chrom *out)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chroms) return;
+    uint64_t first = chrom_first[c];
+    uint64_t next = c + 1 < n_chroms ? chrom_first[c + 1] : n_lines;
+    Stat3 a = chrom_pref[c];
+    Stat3 b = c + 1 < n_chroms ? chrom_pref[c + 1] : *stat_total;
+    s3g_chrom r;
+    r.name_off = line_start[first];
+    uint32_t nl = 0;
+    while (bed[r.name_off + nl] != '\t') nl++;
+    r.name_len = nl;
+    r.n_blocks = 0;
+    r.tf_off = line_tf_off[first];
+    r.tf_len = (next < n_lines ? line_tf_off[next] : tf_total) - r.tf_off;
+    r.line_count = (int64_t)(next - first);
+    r.bases_nonunique = b.len_sum - a.len_sum;
+    r.bases_unique = b.uniq_sum - a.uniq_sum;
+    r.bz_off = 0; r.bz_len = 0;
+    out[c] = r;
+}
+
+__device__ __forceinline__ uint64_t put_dec(uint8_t *dst, int64_t v)
+{
+    uint64_t a = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    char buf[20];
+    int nd = 0;
+    do { buf[nd++] = (char)('0' + a % 10); a /= 10; } while (a);
+    uint64_t k = 0;
+    if (v < 0) dst[k++] = '-';
+    for (int j = nd - 1; j >= 0; j--) dst[k++] = (uint8_t)buf[j];
+    return k;
+}
+
+__global__ void k_write_tf(const uint8_t *__restrict__ bed, LineView lv, const uint64_t *__restrict__ line_tf_off,
+                           uint64_t n_lines, uint8_t *__restrict__ tf)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    int64_t ps, pl; lv.prev(i, &ps, &pl);
+    int64_t s = lv.start[i], t = lv.stop[i];
+    int64_t len = (int64_t)((uint64_t)t - (uint64_t)s), d = (int64_t)((uint64_t)s - (uint64_t)ps);
+    uint8_t *o = tf + line_tf_off[i];
+    if (len != pl) { *o++ = 'p'; o += put_dec(o, len); *o++ = '\n'; }     // hpp:438-455
+    o += put_dec(o, d);                                                   // hpp:456-500
+    uint64_t p = lv.line_start[i], e = lv.line_start[i + 1] - 1;
+    uint64_t r = p + lv.rem_off[i];
+    if (r < e) {
+        *o++ = '\t';
+        for (uint64_t q = r; q < e; q++) *o++ = bed[q];
+    }
+    *o = '\n';
+}
+
+int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only)
+{
+    *out = TfResult();
+    uint64_t ntiles = (n + NL_TILE - 1) / NL_TILE;
+    if (ntiles == 0) ntiles = 1;
+    if (ntiles > 0x7fffffffull) { set_error("input too large"); return S3G_E_LIMIT; }
+    S3G_TRY(ctx->tile_cnt.ensure((ntiles + 1) * 8));
+    S3G_TRY(ctx->scalars.ensure(64 * 8));
+    uint64_t *d_sc = ctx->scalars.as<uint64_t>();
+    S3G_CUDA(cudaMemsetAsync(d_sc, 0, 64 * 8, ctx->stream));
+    uint64_t *tile_cnt = ctx->tile_cnt.as<uint64_t>();
+    S3G_LAUNCH(ctx, k_count_newlines, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt);
+    S3G_LAUNCH(ctx, k_scan_agg<SumU64>, 1, SCAN_THREADS, 0, tile_cnt, ntiles, d_sc + 0);
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t n_lines = ctx->h_scalars[0];
+    out->n_lines = n_lines;
+    S3G_TRY(ctx->line_start.ensure((n_lines + 1) * 8));
+    uint64_t *line_start = ctx->line_start.as<uint64_t>();
+    S3G_LAUNCH(ctx, k_line_starts, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt, line_start);
+    if (n_lines == 0) {
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        out->dropped = n;
+        return check_launch("line_starts");
+    }
+    S3G_TRY(ctx->start.ensure(n_lines * 8));
+    S3G_TRY(ctx->stop.ensure(n_lines * 8));
+    S3G_TRY(ctx->rem_off.ensure(n_lines * 4));
+    S3G_TRY(ctx->flags.ensure(n_lines));
+    int64_t *start = ctx->start.as<int64_t>(), *stop = ctx->stop.as<int64_t>();
+    uint32_t *rem_off = ctx->rem_off.as<uint32_t>();
+    uint8_t *flags = ctx->flags.as<uint8_t>();
+    unsigned lgrid = (unsigned)((n_lines + 255) / 256);
+    S3G_LAUNCH(ctx, k_parse_lines, lgrid, 256, 0, d_bed, line_start, n_lines, start, stop, rem_off, flags,
+               (unsigned long long *)(d_sc + 1));
+    // last line start tells how many unterminated tail bytes are dropped (hpp:181-190)
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 2, line_start + n_lines, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tokenize_only) {
+        S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 1, d_sc + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        out->dropped = n - ctx->h_scalars[2];
+        if (ctx->h_scalars[1]) { set_error("%llu malformed BED line(s): fewer than three fields", (unsigned long long)ctx->h_scalars[1]); return S3G_E_MALFORMED; }
+        return check_launch("tokenize");
+    }
+    // ---- sizes: output offsets, unique-base contributions, chromosome count ----
+    uint64_t stiles = (n_lines + SCAN_TILE - 1) / SCAN_TILE + 1;
+    S3G_TRY(ctx->line_tf_off.ensure(n_lines * 8));
+    S3G_TRY(ctx->stat_a.ensure(n_lines * 8));                 // uniq[]
+    S3G_TRY(ctx->scan_a.ensure(stiles * sizeof(uint64_t)));
+    S3G_TRY(ctx->scan_b.ensure(stiles * sizeof(SegMax)));
+    S3G_TRY(ctx->scan_c.ensure(stiles * sizeof(Stat3)));
+    LineView lv{line_start, start, stop, rem_off, flags};
+    OutLenScan f1; f1.lv = lv; f1.line_tf_off = ctx->line_tf_off.as<uint64_t>();
+    S3G_TRY(device_scan(ctx, f1, n_lines, ctx->scan_a.as<uint64_t>(), d_sc + 3));
+    UniqScan f2; f2.start = start; f2.stop = stop; f2.flags = flags; f2.uniq = ctx->stat_a.as<int64_t>();
+    S3G_TRY(device_scan(ctx, f2, n_lines, ctx->scan_b.as<SegMax>(), (SegMax *)nullptr));
+    StatScan f3; f3.start = start; f3.stop = stop; f3.uniq = ctx->stat_a.as<int64_t>(); f3.flags = flags;
+    f3.chrom_first = nullptr; f3.chrom_pref = nullptr;
+    Stat3 *d_stat_total = reinterpret_cast<Stat3 *>(d_sc + 8);
+    unsigned sgrid = (unsigned)(stiles - 1 ? stiles - 1 : 1);
+    S3G_LAUNCH(ctx, k_scan_reduce<StatScan>, sgrid, SCAN_THREADS, 0, f3, n_lines, ctx->scan_c.as<Stat3>());
+    S3G_LAUNCH(ctx, k_scan_agg<StatScan>, 1, SCAN_THREADS, 0, ctx->scan_c.as<Stat3>(), (uint64_t)sgrid, d_stat_total);
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    S3G_TRY(check_launch("transform sizes"));
+    if (ctx->h_scalars[1]) { set_error("%llu malformed BED line(s): fewer than three fields", (unsigned long long)ctx->h_scalars[1]); return S3G_E_MALFORMED; }
+    out->dropped = n - ctx->h_scalars[2];
+    out->tf_len = ctx->h_scalars[3];
+    out->n_chroms = ctx->h_scalars[10];
+    // ---- write ----
+    S3G_TRY(ctx->tf.ensure(out->tf_len + 64));
+    S3G_TRY(ctx->chrom_first.ensure(out->n_chroms * 8));
+    S3G_TRY(ctx->stat_b.ensure(out->n_chroms * sizeof(Stat3)));
+    S3G_TRY(ctx->chroms.ensure((out->n_chroms + 1) * sizeof(s3g_chrom)));
+    f3.chrom_first = ctx->chrom_first.as<uint64_t>(); f3.chrom_pref = ctx->stat_b.as<Stat3>();
+    S3G_LAUNCH(ctx, k_scan_apply<StatScan>, sgrid, SCAN_THREADS, 0, f3, n_lines, ctx->scan_c.as<Stat3>());
+    S3G_LAUNCH(ctx, k_chrom_table, (unsigned)((out->n_chroms + 127) / 128), 128, 0, d_bed, line_start,
+               ctx->line_tf_off.as<uint64_t>(), ctx->chrom_first.as<uint64_t>(), ctx->stat_b.as<Stat3>(), d_stat_total,
+               out->n_chroms, n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>());
+    S3G_LAUNCH(ctx, k_write_tf, lgrid, 256, 0, d_bed, lv, ctx->line_tf_off.as<uint64_t>(), n_lines, ctx->tf.as<uint8_t>());
+    return check_launch("transform write");
+}
+
+}  // namespace s3g

@@ -1,0 +1,193 @@
+"""GPU parity tests, stage by stage, through the C ABI (include/starch3_b200.h) against the
+CPU oracle on the same seeded inputs.  Bit-exact everywhere: this path is integer/byte work."""
+import bz2
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from starch3_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _beds():
+    yield "cfg1", synth.bed(1, 20000).tobytes()
+    yield "cfg2", synth.bed(2, 20000).tobytes()
+    yield "cfg3", synth.bed(3, 20000).tobytes()
+    yield "cfg3const", synth.bed(3, 20000, variant=1).tobytes()
+    yield "cfg4", synth.bed(4, 20000).tobytes()
+    yield "cfg5", synth.bed(5, 20000).tobytes()
+    yield "reappear", b"chr1\t5\t9\nchr2\t10\t20\tx\nchr2\t30\t40\ty\nchr1\t1\t2\n"
+    yield "overlap", golden("transform_overlap.bed")
+    yield "zerolen", golden("transform_zerolen.bed")
+    yield "negative", b"c\t10\t5\nc\t3\t4\tq\t\tr\nc\t-7\t+9\n"
+    yield "emptyrem", b"chr1\t1\t2\t\nchr1\t3\t4\t\t\n"
+    yield "big", f"c\t{9 * 10**18}\t{9 * 10**18 + 7}\nc\t{9 * 10**18 + 1}\t{9 * 10**18 + 8}\n".encode()
+    yield "tail", b"chr1\t1\t2\nchr1\t5\t6"
+    yield "one", b"chrZ\t0\t1\n"
+    yield "manychroms", b"".join(f"s{i}\t{i}\t{i + 3}\tn{i}\n".encode() for i in range(5000))
+    yield "longrem", b"chr1\t1\t2\t" + b"x" * 5000 + b"\nchr1\t2\t3\t" + b"y\tz" * 700 + b"\n"
+
+
+BEDS = list(_beds())
+
+
+@pytest.mark.parametrize("name,bed", BEDS, ids=[n for n, _ in BEDS])
+def test_tokenize(ctx, oracle, name, bed):
+    t = ctx.tokenize(bed)
+    lines = bed.split(b"\n")[:-1]
+    assert t["n_lines"] == len(lines)
+    pos = 0
+    prev_chr = None
+    for i, ln in enumerate(lines):
+        f = ln.split(b"\t", 3)
+        assert t["line_start"][i] == pos
+        assert t["start"][i] == int(f[1]) and t["stop"][i] == int(f[2])
+        assert t["rem_off"][i] == (len(ln) - len(f[3]) if len(f) == 4 else len(ln))
+        assert t["chrom_change"][i] == (1 if f[0] != prev_chr else 0)
+        prev_chr = f[0]
+        pos += len(ln) + 1
+        if i > 300 and i % 97:
+            continue
+    assert t["line_start"][len(lines)] == pos
+
+
+@pytest.mark.parametrize("name,bed", BEDS, ids=[n for n, _ in BEDS])
+def test_transform(ctx, oracle, name, bed):
+    tf, chroms, dropped = ctx.transform(bed)
+    otf, ochroms, odropped = oracle.transform(bed)
+    assert tf == otf
+    assert dropped == odropped
+    assert chroms == ochroms
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg3const", "cfg4", "overlap", "zerolen"])
+def test_transform_vs_reference_binary_golden(ctx, name):
+    tf, chroms, _ = ctx.transform(golden(f"transform_{name}.bed"))
+    assert tf == golden(f"transform_{name}.tf")
+
+
+def test_transform_errors(ctx):
+    import starch3_b200 as s3
+    with pytest.raises(s3.Starch3Error) as e:
+        ctx.transform(b"chr1\t5\t6\nchr1\t7\n")
+    assert e.value.code == -4
+    assert ctx.transform(b"") == (b"", [], 0)
+    assert ctx.transform(b"no newline") == (b"", [], 10)
+
+
+def _streams():
+    rng = np.random.default_rng(7)
+    yield "empty", b"", 9
+    yield "one", b"a", 9
+    yield "run4", b"aaaa", 9
+    yield "run5", b"aaaaab", 9
+    yield "run255", b"b" * 255, 9
+    yield "run256", b"b" * 256 + b"c", 9
+    yield "run1000", b"z" * 1000, 9
+    yield "run_long", b"q" * 70000 + b"r" * 3, 1
+    yield "runs", b"".join(bytes([int(c)]) * int(n) for c, n in zip(rng.integers(48, 52, 30000), rng.integers(1, 12, 30000))), 1
+    yield "digits_l1", bytes(rng.integers(48, 58, 350000, dtype=np.uint8)), 1
+    yield "random", bytes(rng.integers(0, 256, 250000, dtype=np.uint8)), 1
+    yield "allbytes", bytes(range(256)) * 40, 9
+    nmax = 100000 - 19
+    body = bytes(97 + (i * 7 + i // 26) % 26 for i in range(nmax))
+    yield "exactfill1", body + b"\n", 1
+    yield "exactfill2", body + b"\n#", 1
+    yield "exactfill_runs", b"k" * 255 * 4 + body[: nmax - 20] + b"\n", 1
+
+
+STREAMS = list(_streams())
+
+
+@pytest.mark.parametrize("name,data,level", STREAMS, ids=[s[0] for s in STREAMS])
+def test_rle1_cut_crc(ctx, oracle, name, data, level):
+    blocks, rle = ctx.rle1(data, level)
+    oblocks, orle = oracle.rle1_blocks(data, level)
+    oblocks = [b for b in oblocks if b["nblock"]]
+    assert [(b["in_start"], b["in_end"], b["nblock"]) for b in blocks] == [(b["in_start"], b["in_end"], b["nblock"]) for b in oblocks]
+    assert np.array_equal(rle, orle)
+    for b, ob in zip(blocks, oblocks):
+        assert b["crc"] == ob["crc"]
+        assert np.array_equal(b["in_use"], ob["in_use"])
+
+
+def _blocks():
+    rng = np.random.default_rng(5)
+    yield "digits", bytes(rng.integers(48, 58, 20000, dtype=np.uint8))
+    yield "tiny1", b"a"
+    yield "tiny2", b"ba"
+    yield "tiny5", b"hello"
+    yield "binary", bytes(rng.integers(0, 2, 5000, dtype=np.uint8) + 65)
+    yield "random256", bytes(rng.integers(0, 256, 40000, dtype=np.uint8))
+    yield "repeats", (b"abcabd" * 3000)[:17999]
+    yield "deep", bytes(rng.integers(97, 100, 300, dtype=np.uint8)) * 97 + b"!"
+    yield "tf_cfg2", None
+    yield "tf_cfg4", None
+
+
+BLOCKS = list(_blocks())
+
+
+def _resolve_block(oracle, name, blk):
+    if blk is not None:
+        return blk
+    cfg = int(name[-1])
+    tf, _, _ = oracle.transform(synth.bed(cfg, 40000))
+    return tf[:900000]
+
+
+def test_bwt_batch(ctx, oracle):
+    blks = [_resolve_block(oracle, n, b) for n, b in BLOCKS]
+    got = ctx.bwt(blks)
+    for (name, _), blk, (ptr, orig) in zip(BLOCKS, blks, got):
+        optr, oorig = oracle.bwt(blk)
+        assert np.array_equal(ptr, optr), name
+        assert orig == oorig, name
+
+
+def test_bwt_full_block_vs_reference(ctx, oracle):
+    tf, _, _ = oracle.transform(synth.bed(1, 250000))
+    blocks, rle = oracle.rle1_blocks(tf, 9)
+    blk = rle[:blocks[0]["nblock"]]
+    assert len(blk) >= 899981
+    (ptr, orig), = ctx.bwt([blk])
+    optr, oorig = (oracle.ref_bwt if oracle.have_ref() else oracle.bwt)(blk)
+    assert orig == oorig
+    assert np.array_equal(ptr, optr)
+
+
+@pytest.mark.parametrize("name,blk", BLOCKS, ids=[n for n, _ in BLOCKS])
+def test_mtf_and_huffman(ctx, oracle, name, blk):
+    blk = _resolve_block(oracle, name, blk)
+    ptr, _ = oracle.bwt(blk)
+    in_use = np.zeros(256, dtype=np.uint8)
+    in_use[np.frombuffer(blk, dtype=np.uint8)] = 1
+    omtfv, ofreq, nu = oracle.mtf(blk, ptr, in_use)
+    mtfv, freq = ctx.mtf(blk, ptr, in_use)
+    assert np.array_equal(mtfv, omtfv)
+    assert np.array_equal(freq[:nu + 2], ofreq[:nu + 2])
+    oh = oracle.huff_select(omtfv, ofreq, nu)
+    h = ctx.huff(omtfv, ofreq, in_use)
+    assert h["n_groups"] == oh["n_groups"] and h["n_selectors"] == oh["n_selectors"]
+    assert np.array_equal(h["selector"], oh["selector"])
+    assert np.array_equal(h["len"][:oh["n_groups"], :nu + 2], oh["len"][:oh["n_groups"], :nu + 2])
+    if oracle.have_ref():
+        ref = oracle.ref_mtf_huff(blk, ptr, in_use)
+        assert h["nbits"] == ref["nbits"]
+        assert np.array_equal(h["bits"], ref["bits"])
+
+
+@pytest.mark.parametrize("name,data,level", STREAMS, ids=[s[0] for s in STREAMS])
+def test_bz_compress_stream(ctx, oracle, name, data, level):
+    z = ctx.bz_compress(data, level)
+    assert z == oracle.bz_compress(data, level)
+    assert bz2.decompress(z) == data
+
+
+@pytest.mark.parametrize("idx,level", [(1, 1), (2, 2), (3, 3)])
+def test_bz_compress_golden_samples(ctx, idx, level):
+    gold = golden(f"sample{idx}.bz2")
+    data = bz2.decompress(gold)
+    assert ctx.bz_compress(data, level) == gold
