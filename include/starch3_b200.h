@@ -47,6 +47,11 @@ S3G_API const char *s3g_last_error(void);
 S3G_API int  s3g_set_stream(s3g_ctx *ctx, void *cuda_stream);
 /* Number of kernels launched by this context since creation (bench.py `gpu_launches`). */
 S3G_API uint64_t s3g_launch_count(const s3g_ctx *ctx);
+/* Per-kernel timing with CUDA events on the launching stream.  s3g_profile(ctx, 1) starts
+ * recording; s3g_profile_report synchronises and writes one line per kernel name
+ * ("name\tlaunches\ttotal_ms\n") into buf, then clears the records. */
+S3G_API int  s3g_profile(s3g_ctx *ctx, int enable);
+S3G_API int  s3g_profile_report(s3g_ctx *ctx, char *buf, uint64_t cap);
 
 /* One entry per chromosome stream, in input order.  Mirrors what
  * process_tf_buffer (hpp:393-407) is handed: current_chr, line_count, the

@@ -25,6 +25,26 @@ int check_launch(const char *what)
     return S3G_OK;
 }
 
+int prof_begin(Ctx *ctx, const char *name)
+{
+    if (!ctx->prof) return -1;
+    while (ctx->prof_used + 2 > ctx->prof_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return -1; }
+        ctx->prof_pool.push_back(e);
+    }
+    Ctx::ProfRec r;
+    r.name = name; r.e0 = ctx->prof_pool[ctx->prof_used++]; r.e1 = ctx->prof_pool[ctx->prof_used++];
+    cudaEventRecord(r.e0, ctx->stream);
+    ctx->prof_recs.push_back(r);
+    return (int)ctx->prof_recs.size() - 1;
+}
+
+void prof_end(Ctx *ctx, int idx)
+{
+    if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].e1, ctx->stream);
+}
+
 static DevBuf *const *all_bufs(Ctx *c, size_t *n)
 {
     static thread_local DevBuf *list[64];
@@ -278,6 +298,7 @@ void s3g_destroy(s3g_ctx *ctx)
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -290,6 +311,39 @@ int s3g_set_stream(s3g_ctx *ctx, void *cuda_stream)
 }
 
 uint64_t s3g_launch_count(const s3g_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int s3g_profile(s3g_ctx *ctx, int enable)
+{
+    if (!ctx) { set_error("null context"); return S3G_E_PARAM; }
+    ctx->prof = enable != 0;
+    if (!enable) { ctx->prof_recs.clear(); ctx->prof_used = 0; }
+    return S3G_OK;
+}
+
+int s3g_profile_report(s3g_ctx *ctx, char *buf, uint64_t cap)
+{
+    if (!ctx || !buf || cap == 0) { set_error("null argument"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> names; std::vector<double> ms; std::vector<uint64_t> cnt;
+    for (const Ctx::ProfRec &r : ctx->prof_recs) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        size_t k = 0;
+        for (; k < names.size(); k++) if (names[k] == r.name) break;
+        if (k == names.size()) { names.push_back(r.name); ms.push_back(0); cnt.push_back(0); }
+        ms[k] += t; cnt[k]++;
+    }
+    std::string o;
+    for (size_t k = 0; k < names.size(); k++) {
+        char line[256];
+        snprintf(line, sizeof line, "%s\t%llu\t%.6f\n", names[k].c_str(), (unsigned long long)cnt[k], ms[k]);
+        o += line;
+    }
+    ctx->prof_recs.clear(); ctx->prof_used = 0;
+    if (o.size() + 1 > cap) { set_error("profile buffer too small"); return S3G_E_CAPACITY; }
+    memcpy(buf, o.c_str(), o.size() + 1);
+    return S3G_OK;
+}
 
 int s3g_compress_bed_device(s3g_ctx *ctx, const void *d_bed, uint64_t n, int level, const char *note, int want_archive, s3g_result *res)
 {

@@ -378,6 +378,138 @@ __global__ void __launch_bounds__(ST) k_bwt_finish(BwtP P, BlockInfo *blocks, ui
     if (tie) blocks[lb].tie = 1;
 }
 
+
+// ---- periodic blocks: exact origPtr ---------------------------------------------
+// When a block is a power of a shorter string, equal rotations tie and the position of
+// rotation 0 inside its tie group is whatever libbz2's fallbackSort leaves behind
+// (bz/blocksort.c:212-329 with its helper sorts :32-61 and :93-180; SURVEY.md section 7 shows
+// libbz2 always ends in fallbackSort for such blocks).  One thread replays that algorithm
+// step for step on the intact block.  Rare: nblockMAX is prime, so only stream-tail blocks
+// can be periodic.
+struct FbState {
+    uint32_t *fmap, *ec, *bh;
+};
+#define FB_SET(z) (st.bh[(z) >> 5] |= (1u << ((z) & 31)))
+#define FB_CLR(z) (st.bh[(z) >> 5] &= ~(1u << ((z) & 31)))
+#define FB_GET(z) (st.bh[(z) >> 5] & (1u << ((z) & 31)))
+
+__device__ void fb_small_sort(const FbState &st, int lo, int hi)
+{
+    uint32_t *fmap = st.fmap; const uint32_t *ec = st.ec;
+    if (lo == hi) return;
+    if (hi - lo > 3) {
+        for (int i = hi - 4; i >= lo; i--) {
+            uint32_t t = fmap[i], e = ec[t]; int j;
+            for (j = i + 4; j <= hi && e > ec[fmap[j]]; j += 4) fmap[j - 4] = fmap[j];
+            fmap[j - 4] = t;
+        }
+    }
+    for (int i = hi - 1; i >= lo; i--) {
+        uint32_t t = fmap[i], e = ec[t]; int j;
+        for (j = i + 1; j <= hi && e > ec[fmap[j]]; j++) fmap[j - 1] = fmap[j];
+        fmap[j - 1] = t;
+    }
+}
+
+__device__ void fb_qsort3(const FbState &st, int lo0, int hi0)
+{
+    uint32_t *fmap = st.fmap; const uint32_t *ec = st.ec;
+    int slo[100], shi[100], sp = 0;
+    uint32_t r = 0;
+    slo[sp] = lo0; shi[sp] = hi0; sp++;
+    while (sp > 0) {
+        sp--; int lo = slo[sp], hi = shi[sp];
+        if (hi - lo < 10) { fb_small_sort(st, lo, hi); continue; }
+        r = (r * 7621 + 1) % 32768;
+        uint32_t med;
+        uint32_t r3 = r % 3;
+        if (r3 == 0) med = ec[fmap[lo]]; else if (r3 == 1) med = ec[fmap[(lo + hi) >> 1]]; else med = ec[fmap[hi]];
+        int unLo = lo, ltLo = lo, unHi = hi, gtHi = hi;
+        for (;;) {
+            while (unLo <= unHi) {
+                int32_t d = (int32_t)ec[fmap[unLo]] - (int32_t)med;
+                if (d == 0) { uint32_t t = fmap[unLo]; fmap[unLo] = fmap[ltLo]; fmap[ltLo] = t; ltLo++; unLo++; continue; }
+                if (d > 0) break;
+                unLo++;
+            }
+            while (unLo <= unHi) {
+                int32_t d = (int32_t)ec[fmap[unHi]] - (int32_t)med;
+                if (d == 0) { uint32_t t = fmap[unHi]; fmap[unHi] = fmap[gtHi]; fmap[gtHi] = t; gtHi--; unHi--; continue; }
+                if (d < 0) break;
+                unHi--;
+            }
+            if (unLo > unHi) break;
+            { uint32_t t = fmap[unLo]; fmap[unLo] = fmap[unHi]; fmap[unHi] = t; }
+            unLo++; unHi--;
+        }
+        if (gtHi < ltLo) continue;
+        int a = ltLo - lo, b = unLo - ltLo, n = a < b ? a : b;
+        for (int p1 = lo, p2 = unLo - n; n > 0; n--, p1++, p2++) { uint32_t t = fmap[p1]; fmap[p1] = fmap[p2]; fmap[p2] = t; }
+        a = hi - gtHi; b = gtHi - unHi; int m = a < b ? a : b;
+        for (int p1 = unLo, p2 = hi - m + 1; m > 0; m--, p1++, p2++) { uint32_t t = fmap[p1]; fmap[p1] = fmap[p2]; fmap[p2] = t; }
+        n = lo + unLo - ltLo - 1;
+        m = hi - (gtHi - unHi) + 1;
+        if (n - lo > hi - m) { slo[sp] = lo; shi[sp] = n; sp++; slo[sp] = m; shi[sp] = hi; sp++; }
+        else                 { slo[sp] = m; shi[sp] = hi; sp++; slo[sp] = lo; shi[sp] = n; sp++; }
+    }
+}
+
+__global__ void k_fallback_exact(BwtP P, BlockInfo *blocks)
+{
+    uint32_t lb = blockIdx.x;
+    if (threadIdx.x != 0 || !blocks[lb].tie) return;
+    const int n = (int)P.cnt_n[lb];
+    const uint8_t *blk = P.blk + (uint64_t)lb * BLK_STRIDE;
+    FbState st;
+    st.fmap = P.sa + (uint64_t)lb * BLK_STRIDE;
+    st.ec = P.rk + (uint64_t)lb * BLK_STRIDE;
+    st.bh = reinterpret_cast<uint32_t *>(P.kv0 + (uint64_t)lb * BLK_STRIDE);
+    int32_t ftab[257];
+    for (int i = 0; i < 257; i++) ftab[i] = 0;
+    for (int i = 0; i < n; i++) ftab[blk[i]]++;
+    { int32_t acc = 0; for (int i = 0; i < 256; i++) { acc += ftab[i]; ftab[i] = acc; } }
+    for (int i = 0; i < n; i++) { int k = --ftab[blk[i]]; st.fmap[k] = (uint32_t)i; }
+    int nbh = n / 32 + 8;
+    for (int i = 0; i < nbh; i++) st.bh[i] = 0;
+    for (int i = 0; i < 256; i++) FB_SET(ftab[i]);
+    for (int i = 0; i < 32; i++) { FB_SET(n + 2 * i); FB_CLR(n + 2 * i + 1); }
+    for (long long H = 1;;) {
+        int j = 0;
+        for (int i = 0; i < n; i++) {
+            if (FB_GET(i)) j = i;
+            int k = (int)st.fmap[i] - (int)H; if (k < 0) k += n;
+            st.ec[k] = (uint32_t)j;
+        }
+        int notdone = 0, r = -1;
+        for (;;) {
+            int k = r + 1;
+            while (FB_GET(k)) k++;
+            int l = k - 1;
+            if (l >= n) break;
+            while (!FB_GET(k)) k++;
+            r = k - 1;
+            if (r >= n) break;
+            if (r > l) {
+                notdone += r - l + 1;
+                fb_qsort3(st, l, r);
+                int32_t cc = -1;
+                for (int i = l; i <= r; i++) {
+                    int32_t c1 = (int32_t)st.ec[st.fmap[i]];
+                    if (cc != c1) { FB_SET(i); cc = c1; }
+                }
+            }
+        }
+        H *= 2;
+        if (H > n || notdone == 0) break;
+    }
+    int32_t orig = -1;
+    for (int i = 0; i < n; i++) if (st.fmap[i] == 0) { orig = i; break; }
+    blocks[lb].orig_ptr = orig;
+}
+#undef FB_SET
+#undef FB_CLR
+#undef FB_GET
+
 int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
 {
     if (nb == 0) return S3G_OK;
@@ -444,6 +576,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_TRY(check_launch("bwt round"));
     }
     S3G_LAUNCH(ctx, k_bwt_finish, grid, ST, 0, P, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>());
+    S3G_LAUNCH(ctx, k_fallback_exact, (unsigned)nb, 32, 0, P, ctx->blocks.as<BlockInfo>() + b0);
     return check_launch("bwt finish");
 }
 

@@ -101,15 +101,28 @@ struct Ctx {
     std::vector<BlockInfo> h_blocks;
     std::vector<s3g_chrom> h_chroms;
     uint64_t pool_words = 0;               // words appended to the pool so far
+    // per-kernel profiling (off by default)
+    bool prof = false;
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
 };
 
+// Every kernel launch goes through this macro: it counts launches and, when
+// per-kernel profiling is on (s3g_profile), brackets the launch with CUDA events
+// on the launching stream.
 #define S3G_LAUNCH(ctx, kernel, grid, block, smem, ...)                     \
     do {                                                                    \
+        int pi_ = s3g::prof_begin((ctx), #kernel);                          \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+        s3g::prof_end((ctx), pi_);                                          \
         (ctx)->launches++;                                                  \
     } while (0)
 
 int check_launch(const char *what);
+int prof_begin(Ctx *ctx, const char *name);
+void prof_end(Ctx *ctx, int idx);
 
 // ---- device helpers ---------------------------------------------------------
 #ifdef __CUDACC__

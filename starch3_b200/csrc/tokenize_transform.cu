@@ -312,11 +312,11 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_LAUNCH(ctx, k_parse_lines, lgrid, 256, 0, d_bed, line_start, n_lines, start, stop, rem_off, flags,
                (unsigned long long *)(d_sc + 1));
     // last line start tells how many unterminated tail bytes are dropped (hpp:181-190)
-    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 2, line_start + n_lines, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 40, line_start + n_lines, 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (tokenize_only) {
         S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 1, d_sc + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-        out->dropped = n - ctx->h_scalars[2];
+        out->dropped = n - ctx->h_scalars[40];
         if (ctx->h_scalars[1]) { set_error("%llu malformed BED line(s): fewer than three fields", (unsigned long long)ctx->h_scalars[1]); return S3G_E_MALFORMED; }
         return check_launch("tokenize");
     }
@@ -342,7 +342,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     S3G_TRY(check_launch("transform sizes"));
     if (ctx->h_scalars[1]) { set_error("%llu malformed BED line(s): fewer than three fields", (unsigned long long)ctx->h_scalars[1]); return S3G_E_MALFORMED; }
-    out->dropped = n - ctx->h_scalars[2];
+    out->dropped = n - ctx->h_scalars[40];
     out->tf_len = ctx->h_scalars[3];
     out->n_chroms = ctx->h_scalars[10];
     // ---- write ----
