@@ -247,7 +247,7 @@ def run_b200(args, rank, world, local_rank):
                          "model": alg["model"],
                          "pipeline": {"algorithmic_bytes_per_step": a_total, "achieved": a_total / (ms_per_step / 1000.0) / 1e9,
                                       "frac": a_total / (ms_per_step / 1000.0) / 1e9 / peak}},
-            "kernels": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
+            "kernels": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

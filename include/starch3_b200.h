@@ -99,6 +99,8 @@ S3G_API int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int b
 S3G_API int s3g_compress_bed_device(s3g_ctx *ctx, const void *d_bed, uint64_t n, int block_size_100k,
                             const char *note, int want_archive, s3g_result *res);
 S3G_API void s3g_result_free(s3g_result *res);
+/* Copy the device-resident streams of the last compress call (s3g_result.d_streams) to the host. */
+S3G_API int s3g_read_streams(s3g_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
 
 /* ---- stage entry points (host buffers in / out), for the parity tests ---- */
 

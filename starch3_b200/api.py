@@ -19,7 +19,7 @@ S3G_OK, S3G_E_CUDA, S3G_E_PARAM, S3G_E_NOMEM, S3G_E_MALFORMED, S3G_E_CAPACITY, S
 
 C_ABI_SYMBOLS = [
     "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_profile", "s3g_profile_report",
-    "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free",
+    "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
 ]
 
@@ -81,6 +81,7 @@ def lib():
         L.s3g_compress_bed.argtypes = [vp, vp, u64, i32, C.c_char_p, C.POINTER(CResult)]
         L.s3g_compress_bed_device.argtypes = [vp, vp, u64, i32, C.c_char_p, i32, C.POINTER(CResult)]
         L.s3g_result_free.argtypes = [C.POINTER(CResult)]; L.s3g_result_free.restype = None
+        L.s3g_read_streams.argtypes = [vp, vp, u64, C.POINTER(u64)]
         L.s3g_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(u64), vp, vp, vp, vp, vp]
         L.s3g_transform.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.s3g_rle1.argtypes = [vp, vp, u64, i32, vp, u64, C.POINTER(u64), vp, u64]
@@ -204,6 +205,13 @@ class Context:
             return Result(r, bed_bytes, keep_archive=want_archive)
         finally:
             self._lib.s3g_result_free(C.byref(r))
+
+    def read_streams(self, size):
+        """Host copy of the device-resident bzip2 streams left by the last compress call."""
+        out = np.empty(max(1, size), dtype=np.uint8)
+        n = C.c_uint64(0)
+        self._check(self._lib.s3g_read_streams(self._h, _p(out), size, C.byref(n)))
+        return out[:n.value].tobytes()
 
     # ---- stages ----
     def tokenize(self, bed):

@@ -197,6 +197,7 @@ static int compress_bed_impl(Ctx *ctx, const uint8_t *d_bed, uint64_t n, int lev
     res->n_blocks = n_blocks;
     res->d_streams = ctx->streams.p;
     res->streams_size = total_bytes;
+    ctx->last_streams_size = total_bytes;
     // ---- metadata back to the host ----
     ctx->h_chroms.resize(tr.n_chroms);
     std::vector<StreamMeta> meta(tr.n_chroms);
@@ -358,6 +359,17 @@ int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int level, co
     S3G_CUDA(cudaSetDevice(ctx->device));
     S3G_TRY(stage_in(ctx, ctx->bed, bed, n));
     return compress_bed_impl(ctx, ctx->bed.as<uint8_t>(), n, level, note, 1, res);
+}
+
+int s3g_read_streams(s3g_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n)
+{
+    if (!ctx || !dst || !n) { set_error("null argument"); return S3G_E_PARAM; }
+    *n = ctx->last_streams_size;
+    if (*n > cap) { set_error("cap too small: need %llu", (unsigned long long)*n); return S3G_E_CAPACITY; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    if (*n) S3G_CUDA(cudaMemcpyAsync(dst, ctx->streams.p, *n, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    return S3G_OK;
 }
 
 void s3g_result_free(s3g_result *res)

@@ -101,6 +101,7 @@ struct Ctx {
     std::vector<BlockInfo> h_blocks;
     std::vector<s3g_chrom> h_chroms;
     uint64_t pool_words = 0;               // words appended to the pool so far
+    uint64_t last_streams_size = 0;
     // per-kernel profiling (off by default)
     bool prof = false;
     struct ProfRec { const char *name; cudaEvent_t e0, e1; };

@@ -154,85 +154,131 @@ __global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64
     if (threadIdx.x == 0) agg[blockIdx.x] = tot;
 }
 
-// ---- pass 3: block cut, one thread per stream -------------------------------
-// Serial walk inside one tile; returns through the in/out arguments.
+// ---- pass 3: block cut, one warp per stream -----------------------------------
+// The cut is a sequential chain over the blocks of a stream (each block starts where the
+// previous one ended), so a stream is walked by one warp; the search for each block end is
+// what the 32 lanes share: a 32-ary search over the per-tile prefix e_base and a cooperative
+// scan of the one tile that holds the crossing.
 struct CutWalker {
     const uint8_t *in; uint64_t n; StreamMap sm;
-    const uint64_t *run_carry; const uint64_t *e_base;   // per tile
-    // E(x) = emitted bytes of input bytes < x (x must be a chunk boundary or any position)
-    // Walk from the start of the tile containing `from_tile` and find the first chunk end x >= lo
-    // with E(x) >= target and x <= s1.  Returns x (or s1 if not reached) and E(x).
+    const uint64_t *run_carry; const uint64_t *e_base;   // per tile (exclusive scans)
+
+    // RLE1 state of one byte given the run start in effect (rs = position + 1)
+    __device__ __forceinline__ void step(uint64_t i, uint8_t prev, uint8_t c, uint64_t &rs, uint32_t &emit, bool &last) const
+    {
+        if (i == 0 || c != prev || sm.is_start(i)) rs = i + 1;
+        uint32_t o = (uint32_t)((i - (rs - 1)) % 255u);
+        if (o == 254 || i + 1 >= n) last = true;
+        else if (in[i + 1] != c) last = true;
+        else last = sm.is_start(i + 1);
+        emit = (o < 4 ? 1u : 0u) + ((last && o >= 3) ? 1u : 0u);
+    }
+
+    // Lane-parallel pass over tile `tile`: returns for this lane the run start and the E value in
+    // effect at the first byte of its 128-byte slice, and the emitted bytes of the slice limited to
+    // positions < limit.
+    __device__ void lane_state(uint64_t tile, uint64_t limit, uint64_t &rs_in, uint64_t &e_in, uint32_t &emits) const
+    {
+        const unsigned l = threadIdx.x & 31;
+        uint64_t i0 = tile * RTILE + (uint64_t)l * (RTILE / 32), i1 = i0 + RTILE / 32;
+        if (i1 > n) i1 = n;
+        uint64_t last_rs = 0;
+        uint8_t prev = (i0 > 0 && i0 < n) ? in[i0 - 1] : 0;
+        for (uint64_t i = i0; i < i1; i++) {
+            uint8_t c = in[i];
+            if (i == 0 || c != prev || sm.is_start(i)) last_rs = i + 1;
+            prev = c;
+        }
+        uint64_t inc = warp_incl_max<uint64_t>(last_rs);
+        uint64_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (l == 0) ex = 0;
+        uint64_t carry = run_carry[tile];
+        rs_in = ex > carry ? ex : carry;
+        uint64_t rs = rs_in;
+        uint32_t tot = 0;
+        prev = (i0 > 0 && i0 < n) ? in[i0 - 1] : 0;
+        for (uint64_t i = i0; i < i1 && i < limit; i++) {
+            uint8_t c = in[i]; uint32_t em; bool last;
+            step(i, prev, c, rs, em, last);
+            tot += em; prev = c;
+        }
+        emits = tot;
+        uint32_t inc2 = warp_incl_sum<uint32_t>(tot);
+        e_in = e_base[tile] + (inc2 - tot);
+    }
+
+    // E(x): emitted bytes of all input bytes < x
+    __device__ uint64_t e_at(uint64_t x) const
+    {
+        uint64_t tile = x / RTILE;
+        if (x == tile * RTILE) return e_base[tile];
+        uint64_t rs_in, e_in; uint32_t em;
+        lane_state(tile, x, rs_in, e_in, em);
+        uint64_t tot = e_in + em;                         // inclusive prefix of my lane
+        return __shfl_sync(0xffffffffu, tot, 31);
+    }
+
+    // first chunk end x (<= s1) with E(x) >= target, searching from tile `tile` (e_base[tile] < target)
     __device__ void find(uint64_t tile, uint64_t target, uint64_t s1, uint64_t *x_out, uint64_t *e_out) const
     {
-        uint64_t i = tile * RTILE;
-        uint64_t rs = run_carry[tile];   // position+1
-        uint64_t e = e_base[tile];
-        uint8_t prev = i > 0 ? in[i - 1] : 0;
-        for (; i < s1; i++) {
-            uint8_t c = in[i];
-            if (i == 0 || c != prev || sm.is_start(i)) rs = i + 1;
-            uint32_t o = (uint32_t)((i - (rs - 1)) % 255u);
-            bool last;
-            if (o == 254 || i + 1 >= n) last = true;
-            else if (in[i + 1] != c) last = true;
-            else last = sm.is_start(i + 1);
-            if (o < 4) e++;
-            if (last && o >= 3) e++;
-            prev = c;
-            if (last && e >= target) { *x_out = i + 1; *e_out = e; return; }
+        const unsigned l = threadIdx.x & 31;
+        uint64_t rs_in, e_in; uint32_t em;
+        lane_state(tile, ~0ull, rs_in, e_in, em);
+        unsigned cross = __ballot_sync(0xffffffffu, e_in + em >= target);
+        // the crossing lane walks from its slice start to the chunk end that reaches the target; if the
+        // target is only met by a chunk that ends in a later tile, the last lane keeps walking
+        unsigned who = cross ? (unsigned)(__ffs(cross) - 1) : 31u;
+        uint64_t x = s1, e = 0;
+        if (l == who) {
+            uint64_t i = tile * RTILE + (uint64_t)l * (RTILE / 32);
+            uint64_t rs = rs_in; e = e_in;
+            uint8_t prev = (i > 0) ? in[i - 1] : 0;
+            for (; i < s1; i++) {
+                uint8_t c = in[i]; uint32_t emv; bool last;
+                step(i, prev, c, rs, emv, last);
+                e += emv; prev = c;
+                if (last && e >= target) { x = i + 1; break; }
+            }
         }
-        *x_out = s1; *e_out = e;
+        *x_out = __shfl_sync(0xffffffffu, x, who);
+        *e_out = __shfl_sync(0xffffffffu, e, who);
     }
 };
 
-__device__ __forceinline__ uint64_t e_at(const CutWalker &cw, uint64_t x)
-{
-    // E at an arbitrary position that is a stream boundary (hence a chunk boundary)
-    uint64_t tile = x / RTILE;
-    if (x == tile * RTILE) return cw.e_base[tile];
-    uint64_t i = tile * RTILE, rs = cw.run_carry[tile], e = cw.e_base[tile];
-    uint8_t prev = i > 0 ? cw.in[i - 1] : 0;
-    for (; i < x; i++) {
-        uint8_t c = cw.in[i];
-        if (i == 0 || c != prev || cw.sm.is_start(i)) rs = i + 1;
-        uint32_t o = (uint32_t)((i - (rs - 1)) % 255u);
-        bool last;
-        if (o == 254 || i + 1 >= cw.n) last = true;
-        else if (cw.in[i + 1] != c) last = true;
-        else last = cw.sm.is_start(i + 1);
-        if (o < 4) e++;
-        if (last && o >= 3) e++;
-        prev = c;
-    }
-    return e;
-}
-
 // Blocks of stream s are written at provisional slots prov(s) + k and compacted afterwards.
-__global__ void k_rle_cut(CutWalker cw, uint64_t n_tiles, uint32_t nmax, uint64_t slot_cap,
-                          BlockInfo *prov, uint32_t *blocks_per_stream, uint64_t *prov_base)
+__global__ void __launch_bounds__(32) k_rle_cut(CutWalker cw, uint32_t nmax, uint64_t slot_cap, BlockInfo *prov,
+                                                uint32_t *blocks_per_stream, uint64_t *prov_base)
 {
-    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t s = blockIdx.x;
+    const unsigned l = threadIdx.x & 31;
     if (s >= cw.sm.n_streams) return;
     uint64_t s0 = cw.sm.soff[s], s1 = cw.sm.soff[s + 1];
-    uint64_t e0 = e_at(cw, s0), e1 = e_at(cw, s1);
+    uint64_t e0 = cw.e_at(s0), e1 = cw.e_at(s1);
     uint64_t slot = e0 / nmax + s;     // upper bound on the blocks of earlier streams
-    prov_base[s] = slot;
+    if (l == 0) prov_base[s] = slot;
     uint32_t nb = 0;
     uint64_t start = s0, base = e0;
     while (start < s1) {
         uint64_t target = base + nmax;
         uint64_t x = s1, ex = e1;
         if (e1 >= target) {
-            // tile holding the crossing: last tile with e_base < target
+            // 32-ary search for the last tile whose prefix is still below the target
             uint64_t lo = start / RTILE, hi = (s1 - 1) / RTILE;
             while (lo < hi) {
-                uint64_t mid = (lo + hi + 1) >> 1;
-                if (cw.e_base[mid] < target) lo = mid; else hi = mid - 1;
+                uint64_t span = hi - lo, stepw = (span + 31) / 32;
+                uint64_t probe = lo + (uint64_t)(l + 1) * stepw;
+                bool below = probe <= hi && cw.e_base[probe] < target;
+                unsigned m = __ballot_sync(0xffffffffu, below);
+                unsigned cnt = __popc(m);               // monotone: the first cnt probes are below
+                uint64_t nlo = lo + (uint64_t)cnt * stepw;
+                uint64_t nhi = lo + (uint64_t)(cnt + 1) * stepw - 1;
+                lo = nlo; if (nhi < hi) hi = nhi;
+                if (lo > hi) hi = lo;
             }
             cw.find(lo, target, s1, &x, &ex);
             if (x + 1 >= s1) { x = s1; ex = e1; }   // a single trailing byte is flushed into this block
         }
-        if (slot + nb < slot_cap) {
+        if (l == 0 && slot + nb < slot_cap) {
             BlockInfo bi;
             memset(&bi, 0, sizeof bi);
             bi.in_start = start; bi.in_end = x; bi.e_base = base; bi.nblock = (uint32_t)(ex - base);
@@ -242,8 +288,7 @@ __global__ void k_rle_cut(CutWalker cw, uint64_t n_tiles, uint32_t nmax, uint64_
         nb++;
         start = x; base = ex;
     }
-    blocks_per_stream[s] = nb;
-    (void)n_tiles;
+    if (l == 0) blocks_per_stream[s] = nb;
 }
 
 __global__ void k_stream_block_scan(const uint32_t *blocks_per_stream, uint64_t n_streams, uint64_t *first_block,
@@ -410,8 +455,7 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     uint64_t *first_block = prov_base + (n_streams + 2);
     uint32_t *bps = reinterpret_cast<uint32_t *>(first_block + (n_streams + 2));
     CutWalker cw{d_in, n, sm, run_carry, e_base};
-    S3G_LAUNCH(ctx, k_rle_cut, (unsigned)((n_streams + 31) / 32), 32, 0, cw, ntiles, nmax, slot_cap,
-               ctx->blk_prov.as<BlockInfo>(), bps, prov_base);
+    S3G_LAUNCH(ctx, k_rle_cut, (unsigned)n_streams, 32, 0, cw, nmax, slot_cap, ctx->blk_prov.as<BlockInfo>(), bps, prov_base);
     S3G_LAUNCH(ctx, k_stream_block_scan, 1, 1, 0, bps, n_streams, first_block, d_sc + 17);
     S3G_LAUNCH(ctx, k_compact_blocks, (unsigned)n_streams, 64, 0, ctx->blk_prov.as<BlockInfo>(), prov_base, first_block,
                n_streams, ctx->blocks.as<BlockInfo>(), (s3g_chrom *)nullptr);
