@@ -189,6 +189,16 @@ def run_b200(args, rank, world, local_rank):
     dev_ms = e0.elapsed_time(e1)
     prof = ctx.profile_report()
     ctx.profile(False)
+    lib_ms = res.device_ms
+    # the same K steps once more without the per-kernel events, to show what they cost
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        res = ctx.compress_bed_device(d_bed.data_ptr(), nbytes, 9, want_archive=False)
+    f1.record(stream)
+    barrier()
+    noprof_ms = f0.elapsed_time(f1) / args.steps
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count - launches0
 
@@ -240,6 +250,7 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": archive_bytes,
                     "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
+            "ms_per_step_without_kernel_events": noprof_ms, "library_first_to_last_kernel_ms": lib_ms,
             "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_share_of_step": top_ms / tot_kernel_ms, "launches": top_n,

@@ -36,7 +36,7 @@ struct BwtP {
     const BlockInfo *blocks;   // batch block 0
     uint32_t *sa, *rk;         // [nb][BLK_STRIDE]
     uint64_t *kv0, *kv1;       // [nb][BLK_STRIDE] (key << 32 | val)
-    uint32_t *hist;            // [nb][NBINS][NT]
+    uint32_t *hist;            // [nb][NT][NBINS] (tile-major: every access below is coalesced over digits)
     uint32_t *cnt_n;           // [nb] block sizes
     uint32_t *cnt_m;           // [nb] active items after pass 1
     uint32_t *act;             // [2][nb] unsorted rotations per block (ping-pong by round)
@@ -106,17 +106,21 @@ __global__ void __launch_bounds__(ST) k_hist(BwtP P, int shift, int phase, uint3
     __syncthreads();
     uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
     uint32_t base = tile * STILE + w * (SI * 32) + l;
-#pragma unroll 4
+    uint32_t dg[SI];
+#pragma unroll
     for (int r = 0; r < SI; r++) {
         uint32_t key, val;
         bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, key, val);
-        uint32_t d = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (ok && (peers & ((1u << l) - 1)) == 0) atomicAdd(&sh[d], __popc(peers));
+        dg[r] = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < SI; r++) {
+        unsigned peers = __match_any_sync(0xffffffffu, dg[r]);
+        if (dg[r] != 0xffffffffu && (peers & ((1u << l) - 1)) == 0) atomicAdd(&sh[dg[r]], __popc(peers));
     }
     __syncthreads();
-    uint32_t *out = P.hist + (uint64_t)lb * NBINS * NT;
-    for (int i = threadIdx.x; i < NBINS; i += ST) out[(uint64_t)i * NT + tile] = sh[i];
+    uint32_t *out = P.hist + ((uint64_t)lb * NT + tile) * NBINS;
+    for (int i = threadIdx.x; i < NBINS; i += ST) out[i] = sh[i];
 }
 
 // ---- radix pass: exclusive scan of hist[digit][tile] per block ---------------
@@ -128,42 +132,63 @@ __global__ void __launch_bounds__(NBINS) k_hist_scan(BwtP P, int phase, uint32_t
     if (!block_live(P, lb, phase, round, act_cur)) return;
     uint32_t cnt = cnt_arr[lb];
     uint32_t ntiles = (cnt + STILE - 1) / STILE;
-    uint32_t *row = P.hist + (uint64_t)lb * NBINS * NT + (uint64_t)threadIdx.x * NT;
+    // thread d owns digit d: column d of the [tile][digit] matrix
+    uint32_t *col = P.hist + (uint64_t)lb * NT * NBINS + threadIdx.x;
     uint32_t s = 0;
-    for (uint32_t t = 0; t < ntiles; t++) s += row[t];
+#pragma unroll 4
+    for (uint32_t t = 0; t < ntiles; t++) s += col[(uint64_t)t * NBINS];
     uint32_t tot;
     uint32_t ex = block_excl_sum<uint32_t>(s, sm, &tot);
-    for (uint32_t t = 0; t < ntiles; t++) { uint32_t v = row[t]; row[t] = ex; ex += v; }
+#pragma unroll 4
+    for (uint32_t t = 0; t < ntiles; t++) { uint32_t v = col[(uint64_t)t * NBINS]; col[(uint64_t)t * NBINS] = ex; ex += v; }
     if (threadIdx.x == 0 && total_out) total_out[lb] = tot;
 }
 
 // ---- radix pass: stable scatter ----------------------------------------------
+// Ranks are computed warp-synchronously (match.any on the digit), items are first
+// placed in digit order inside shared memory, then written out so that neighbouring
+// threads store to neighbouring addresses (runs of equal digits are contiguous in HBM).
+struct ScatterSmem {
+    uint64_t stage[STILE];                 // tile in digit order
+    uint32_t gbase[NBINS];                 // global offset of (digit, this tile)
+    uint32_t tbase[NBINS];                 // offset of the digit inside the tile
+    uint16_t wcnt[(ST / 32) * NBINS];      // per-warp digit counters -> exclusive warp offsets
+    uint32_t scan[33];
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(ST) k_scatter(BwtP P, int shift, int phase, uint32_t round, const uint32_t *cnt_arr,
+__global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int shift, int phase, uint32_t round, const uint32_t *cnt_arr,
                                                 const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *act_cur)
 {
-    __shared__ uint16_t wcnt[(ST / 32) * NBINS];   // per-warp digit counters -> exclusive warp offsets
-    __shared__ uint32_t gbase[NBINS];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
     uint32_t lb = blockIdx.y, tile = blockIdx.x;
     if (!block_live(P, lb, phase, round, act_cur)) return;
     uint32_t h = depth_of(P, lb, round);
     uint32_t n = P.cnt_n[lb], cnt = cnt_arr[lb];
     if ((uint64_t)tile * STILE >= cnt) return;
-    for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) wcnt[i] = 0;
-    const uint32_t *hrow = P.hist + (uint64_t)lb * NBINS * NT;
-    for (int i = threadIdx.x; i < NBINS; i += ST) gbase[i] = hrow[(uint64_t)i * NT + tile];
-    __syncthreads();
+    for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) S.wcnt[i] = 0;
+    const uint32_t *hrow = P.hist + ((uint64_t)lb * NT + tile) * NBINS;
+    for (int i = threadIdx.x; i < NBINS; i += ST) S.gbase[i] = hrow[i];
     uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
     uint32_t base = tile * STILE + w * (SI * 32) + l;
-    uint16_t *mycnt = wcnt + w * NBINS;
+    uint16_t *mycnt = S.wcnt + w * NBINS;
     uint64_t kv[SI];
     uint16_t rnk[SI];
     uint32_t okmask = 0;
+    // all loads first (independent, 16 in flight per thread); the ranking below is warp-synchronous
 #pragma unroll
     for (int r = 0; r < SI; r++) {
         uint32_t key = 0, val = 0;
         bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, key, val);
         kv[r] = ((uint64_t)key << 32) | val;
+        if (ok) okmask |= 1u << r;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SI; r++) {
+        bool ok = (okmask >> r) & 1u;
+        uint32_t key = (uint32_t)(kv[r] >> 32);
         uint32_t d = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
         unsigned peers = __match_any_sync(0xffffffffu, d);
         unsigned lt = peers & ((1u << l) - 1);
@@ -172,23 +197,37 @@ __global__ void __launch_bounds__(ST) k_scatter(BwtP P, int shift, int phase, ui
         if (ok && lt == 0) mycnt[d] = (uint16_t)(b + __popc(peers));
         __syncwarp();
         rnk[r] = (uint16_t)(b + __popc(lt));
-        if (ok) okmask |= 1u << r;
     }
     __syncthreads();
-    // exclusive prefix over warps per digit
-    for (int d = threadIdx.x; d < NBINS; d += ST) {
+    // per digit: exclusive prefix over warps, tile total; then exclusive scan of the totals over digits
+    uint32_t tot4[NBINS / ST];
+    uint32_t mysum = 0;
+#pragma unroll
+    for (int q = 0; q < NBINS / ST; q++) {
+        int d = threadIdx.x * (NBINS / ST) + q;
         uint32_t run = 0;
 #pragma unroll
-        for (int ww = 0; ww < ST / 32; ww++) { uint32_t c = wcnt[ww * NBINS + d]; wcnt[ww * NBINS + d] = (uint16_t)run; run += c; }
+        for (int ww = 0; ww < ST / 32; ww++) { uint32_t c = S.wcnt[ww * NBINS + d]; S.wcnt[ww * NBINS + d] = (uint16_t)run; run += c; }
+        tot4[q] = run; mysum += run;
     }
+    uint32_t tile_total;
+    uint32_t ex = block_excl_sum<uint32_t>(mysum, S.scan, &tile_total);
+#pragma unroll
+    for (int q = 0; q < NBINS / ST; q++) { S.tbase[threadIdx.x * (NBINS / ST) + q] = ex; ex += tot4[q]; }
     __syncthreads();
-    uint64_t *out = kv_out + (uint64_t)lb * BLK_STRIDE;
 #pragma unroll
     for (int r = 0; r < SI; r++) {
         if (okmask & (1u << r)) {
             uint32_t d = ((uint32_t)(kv[r] >> 32) >> shift) & (NBINS - 1);
-            out[gbase[d] + mycnt[d] + rnk[r]] = kv[r];
+            S.stage[S.tbase[d] + mycnt[d] + rnk[r]] = kv[r];
         }
+    }
+    __syncthreads();
+    uint64_t *out = kv_out + (uint64_t)lb * BLK_STRIDE;
+    for (uint32_t i = threadIdx.x; i < tile_total; i += ST) {
+        uint64_t it = S.stage[i];
+        uint32_t d = ((uint32_t)(it >> 32) >> shift) & (NBINS - 1);
+        out[S.gbase[d] + (i - S.tbase[d])] = it;
     }
 }
 
@@ -234,6 +273,9 @@ __device__ __forceinline__ void boundary_flags(const BwtP &P, uint32_t lb, uint3
     }
 }
 
+// Tile aggregates for the two max-scans: (position + 1) of the last group head and of the last
+// sub-group boundary inside the tile.  Heads need only the keys (coalesced); the last boundary is
+// searched backwards from the tile end in chunks of ST items and almost always sits in the first one.
 template <bool INIT>
 __global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const uint64_t *kv, const uint32_t *act_cur)
 {
@@ -242,18 +284,44 @@ __global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const 
     if (!block_live(P, lb, INIT ? 0 : 1, round, act_cur)) return;
     uint32_t h = depth_of(P, lb, round);
     uint32_t n = P.cnt_n[lb], cnt = INIT ? n : P.cnt_m[lb];
-    if ((uint64_t)tile * STILE >= cnt) return;
-    uint32_t p0 = tile * STILE + threadIdx.x * SI;
-    uint32_t hm, bm; uint64_t items[SI + 1];
-    boundary_flags<INIT>(P, lb, n, cnt, h, kv, p0, hm, bm, items);
-    hm &= (1u << SI) - 1; bm &= (1u << SI) - 1;
-    uint32_t valid = p0 < cnt ? (cnt - p0 >= SI ? (1u << SI) - 1 : (1u << (cnt - p0)) - 1) : 0;
-    hm &= valid; bm &= valid;
-    uint32_t lh = hm ? p0 + (31 - __clz(hm)) + 1 : 0;    // position + 1 of my last head
-    uint32_t lbn = bm ? p0 + (31 - __clz(bm)) + 1 : 0;
-    uint32_t th, tb;
+    uint32_t t0 = tile * STILE;
+    if (t0 >= cnt) return;
+    uint32_t t1 = min(t0 + (uint32_t)STILE, cnt);
+    const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    uint32_t lh = 0;
+    if (INIT) { if (t0 == 0 && threadIdx.x == 0) lh = 1; }
+    else {
+#pragma unroll 4
+        for (uint32_t p = t0 + threadIdx.x; p < t1; p += ST) {
+            bool head = p == 0 || (uint32_t)(a[p] >> 32) != (uint32_t)(a[p - 1] >> 32);
+            if (head) lh = p + 1;
+        }
+    }
+    uint32_t th, tb = 0;
     block_excl_max<uint32_t>(lh, sm, &th);
-    block_excl_max<uint32_t>(lbn, sm, &tb);
+    for (uint32_t top = t1; top > t0; top = top > t0 + ST ? top - ST : t0) {
+        uint32_t lo = top > t0 + ST ? top - ST : t0;
+        uint32_t p = lo + threadIdx.x;
+        uint32_t v = 0;
+        if (p < top) {
+            bool bnd;
+            if (p == 0) bnd = true;
+            else {
+                uint64_t x = a[p], y = a[p - 1];
+                if ((uint32_t)(x >> 32) != (uint32_t)(y >> 32)) bnd = true;
+                else if (INIT) bnd = false;
+                else {
+                    uint32_t jx = (uint32_t)x + h; if (jx >= n) jx -= n;
+                    uint32_t jy = (uint32_t)y + h; if (jy >= n) jy -= n;
+                    bnd = rk[jx] != rk[jy];
+                }
+            }
+            if (bnd) v = p + 1;
+        }
+        block_excl_max<uint32_t>(v, sm, &tb);
+        if (tb) break;                     // uniform: tb comes from shared memory
+    }
     if (threadIdx.x == 0) {
         uint32_t *ag = P.agg + ((uint64_t)lb * NT + tile) * 2;
         ag[0] = th; ag[1] = tb;
@@ -539,16 +607,23 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 16, ctx->stream));
     S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
     dim3 grid(NT, (unsigned)nb);
+    static bool attr_done = false;
+    if (!attr_done) {
+        S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        attr_done = true;
+    }
     const uint32_t *no_act = nullptr;
     const uint64_t *no_kv = nullptr;
     uint32_t *no_out = nullptr;
     // ---- init: order by the first k symbols ----
     S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, no_act);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
-    S3G_LAUNCH(ctx, k_scatter<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, P.kv0, no_act);
+    S3G_LAUNCH(ctx, k_scatter<MODE_INIT>, grid, ST, sizeof(ScatterSmem), P, 0, 0, 0u, P.cnt_n, no_kv, P.kv0, no_act);
     S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, no_act);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
-    S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
+    S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
     S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv1, no_act);
     S3G_LAUNCH(ctx, k_bound_apply<true>, grid, ST, 0, P, 0u, P.kv1, no_out, no_act, P.act, P.g_act);
     S3G_TRY(check_launch("bwt init"));
@@ -560,16 +635,17 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         unsigned long long *g_cur = P.g_act + (round & 1), *g_next = P.g_act + ((round + 1) & 1);
         S3G_CUDA(cudaMemcpyAsync(h_act, g_cur, 8, cudaMemcpyDeviceToHost, ctx->stream));
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (getenv("S3G_DEBUG")) fprintf(stderr, "[s3g] bwt round %u: %llu of %llu rotations unsorted\n", round, *h_act, (unsigned long long)nb * BLK_STRIDE);
         if (*h_act == 0) break;
         S3G_CUDA(cudaMemsetAsync(act_next, 0, nb * 4, ctx->stream));
         S3G_CUDA(cudaMemsetAsync(g_next, 0, 8, ctx->stream));
         uint32_t *newrank = reinterpret_cast<uint32_t *>(P.kv0);
         S3G_LAUNCH(ctx, k_hist<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, act_cur);
         S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_n, P.cnt_m, act_cur);
-        S3G_LAUNCH(ctx, k_scatter<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, P.kv0, act_cur);
+        S3G_LAUNCH(ctx, k_scatter<MODE_MM>, grid, ST, sizeof(ScatterSmem), P, 0, 1, round, P.cnt_n, no_kv, P.kv0, act_cur);
         S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, act_cur);
         S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_m, no_out, act_cur);
-        S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
+        S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
         S3G_LAUNCH(ctx, k_bound_agg<false>, grid, ST, 0, P, round, P.kv1, act_cur);
         S3G_LAUNCH(ctx, k_bound_apply<false>, grid, ST, 0, P, round, P.kv1, newrank, act_cur, act_next, g_next);
         S3G_LAUNCH(ctx, k_rank_update, grid, ST, 0, P, round, P.kv1, newrank, act_cur);

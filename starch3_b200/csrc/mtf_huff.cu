@@ -278,6 +278,7 @@ struct BitW {
 };
 
 struct HuffSmem {
+    uint64_t len_pack[ALPHA_MAX + 2];
     uint8_t  len[6][ALPHA_MAX + 2];
     int32_t  rfreq[6][ALPHA_MAX];
     int32_t  code[6][ALPHA_MAX];
@@ -322,20 +323,58 @@ __global__ void __launch_bounds__(HT) k_huff(const uint16_t *mtfv_all, const int
     __syncthreads();
     for (int iter = 0; iter < N_ITERS; iter++) {
         for (int i = tid; i < 6 * ALPHA_MAX; i += HT) (&S.rfreq[0][0])[i] = 0;
+        // six 10-bit cost lanes per symbol (50 symbols x length <= 20 stays below 1024): the same
+        // arithmetic as the reference's len_pack fast path (bz/compress.c:334-393), one add per symbol
+        for (int v = tid; v < alpha; v += HT) {
+            uint64_t pk = 0;
+#pragma unroll
+            for (int t = 0; t < 6; t++) pk |= (uint64_t)S.len[t][v] << (10 * t);
+            S.len_pack[v] = pk;
+        }
         __syncthreads();
         for (int g = tid; g < nsel; g += HT) {
-            int gs = g * G_SIZE, ge = min(gs + G_SIZE, nmtf);
-            uint32_t cost[6] = {0, 0, 0, 0, 0, 0};
-            for (int i = gs; i < ge; i++) {
-                int v = mtfv[i];
+            const int gs = g * G_SIZE, cnt = min(G_SIZE, nmtf - gs);
+            uint32_t w[G_SIZE / 2];
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(mtfv + gs);     // gs * 2 bytes is 4-byte aligned
+            uint64_t acc = 0;
+            if (cnt == G_SIZE) {
 #pragma unroll
-                for (int t = 0; t < 6; t++) cost[t] += S.len[t][v];
+                for (int k = 0; k < G_SIZE / 2; k++) {
+                    w[k] = src[k];
+                    acc += S.len_pack[w[k] & 0xffffu] + S.len_pack[w[k] >> 16];
+                }
+            } else {
+                for (int i = 0; i < cnt; i++) acc += S.len_pack[mtfv[gs + i]];
             }
-            int bt = 0; uint32_t bc = cost[0];
+            int bt = 0; uint32_t bc = (uint32_t)(acc & 1023u);
 #pragma unroll
-            for (int t = 1; t < 6; t++) if (t < ng && cost[t] < bc) { bc = cost[t]; bt = t; }   // first minimum, :399-401
+            for (int t = 1; t < 6; t++) {
+                uint32_t c = (uint32_t)(acc >> (10 * t)) & 1023u;
+                if (t < ng && c < bc) { bc = c; bt = t; }          // first minimum, :399-401
+            }
             S.selector[g] = (uint8_t)bt;
-            for (int i = gs; i < ge; i++) atomicAdd(&S.rfreq[bt][mtfv[i]], 1);
+            // symbol frequencies of the chosen table (:410-432); the eight smallest symbol values
+            // (RUNA, RUNB and the nearest MTF ranks -- most of the mass) are counted in a register first
+            int32_t *rf = S.rfreq[bt];
+            uint64_t small = 0;
+            if (cnt == G_SIZE) {
+#pragma unroll
+                for (int k = 0; k < G_SIZE / 2; k++) {
+                    uint32_t v0 = w[k] & 0xffffu, v1 = w[k] >> 16;
+                    if (v0 < 8) small += 1ull << (8 * v0); else atomicAdd(&rf[v0], 1);
+                    if (v1 < 8) small += 1ull << (8 * v1); else atomicAdd(&rf[v1], 1);
+                }
+            } else {
+                for (int i = 0; i < cnt; i++) {
+                    uint32_t v0 = mtfv[gs + i];
+                    if (v0 < 8) small += 1ull << (8 * v0); else atomicAdd(&rf[v0], 1);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int c = (int)((small >> (8 * k)) & 255u);
+                if (c) atomicAdd(&rf[k], c);
+            }
         }
         __syncthreads();
         if (tid < ng) hb_make_lengths(S.len[tid], S.rfreq[tid], alpha, 17);

@@ -127,7 +127,8 @@ __device__ __forceinline__ void rle_local(const ByteWin &w, const StreamMap &sm,
         if (k < w.cnt) {
             uint64_t i = w.pos0 + k;
             if (startmask & (1u << k)) rs = i + 1;
-            uint32_t c = (uint32_t)((i - (rs - 1)) % 255u);
+            uint64_t o64 = i - (rs - 1);
+            uint32_t c = o64 < 0xffffffffull ? (uint32_t)o64 % 255u : (uint32_t)(o64 % 255u);
             // chunk ends here if the next byte starts a new run, the chunk is full, or the input ends
             bool last_in_chunk;
             if (c == 254 || i + 1 >= n) last_in_chunk = true;
@@ -167,7 +168,8 @@ struct CutWalker {
     __device__ __forceinline__ void step(uint64_t i, uint8_t prev, uint8_t c, uint64_t &rs, uint32_t &emit, bool &last) const
     {
         if (i == 0 || c != prev || sm.is_start(i)) rs = i + 1;
-        uint32_t o = (uint32_t)((i - (rs - 1)) % 255u);
+        uint64_t o64 = i - (rs - 1);
+        uint32_t o = o64 < 0xffffffffull ? (uint32_t)o64 % 255u : (uint32_t)(o64 % 255u);
         if (o == 254 || i + 1 >= n) last = true;
         else if (in[i + 1] != c) last = true;
         else last = sm.is_start(i + 1);
