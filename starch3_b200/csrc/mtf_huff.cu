@@ -197,9 +197,12 @@ constexpr int MAX_SEL = 18002;           // BZ_MAX_SELECTORS
 constexpr int ALPHA_MAX = 258;
 
 // bz/huffman.c:63-148, run verbatim by one thread per table
-__device__ void hb_make_lengths(uint8_t *len, const int32_t *freq, int alpha, int max_len)
-{
+struct HeapScratch {
     int32_t heap[ALPHA_MAX + 2], weight[ALPHA_MAX * 2], parent[ALPHA_MAX * 2];
+};
+__device__ void hb_make_lengths(uint8_t *len, const int32_t *freq, int alpha, int max_len, HeapScratch &hs)
+{
+    int32_t *heap = hs.heap, *weight = hs.weight, *parent = hs.parent;
     for (int i = 0; i < alpha; i++) weight[i + 1] = (freq[i] == 0 ? 1 : freq[i]) << 8;
     for (;;) {
         int nnodes = alpha, nheap = 0;
@@ -279,6 +282,7 @@ struct BitW {
 
 struct HuffSmem {
     uint64_t len_pack[ALPHA_MAX + 2];
+    HeapScratch heaps[6];
     uint8_t  len[6][ALPHA_MAX + 2];
     int32_t  rfreq[6][ALPHA_MAX];
     int32_t  code[6][ALPHA_MAX];
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(HT) k_huff(const uint16_t *mtfv_all, const int
             }
         }
         __syncthreads();
-        if (tid < ng) hb_make_lengths(S.len[tid], S.rfreq[tid], alpha, 17);
+        if (tid < ng) hb_make_lengths(S.len[tid], S.rfreq[tid], alpha, 17, S.heaps[tid]);
         __syncthreads();
     }
     // codes (bz/huffman.c:152-166) and per-table header sizes
@@ -393,22 +397,48 @@ __global__ void __launch_bounds__(HT) k_huff(const uint16_t *mtfv_all, const int
         for (int i = 0; i < alpha; i++) { int L = S.len[tid][i]; bits += 2u * (uint32_t)abs(L - cur) + 1; cur = L; }
         S.tab_bits[tid] = bits;
     }
-    if (tid == 32) {   // selector MTF (bz/compress.c:462-478)
-        uint8_t pos[6];
-        for (int i = 0; i < ng; i++) pos[i] = (uint8_t)i;
-        for (int i = 0; i < nsel; i++) {
-            uint8_t v = S.selector[i]; int j = 0; uint8_t carry = pos[0];
-            while (carry != v) { j++; uint8_t t = pos[j]; pos[j] = carry; carry = t; }
-            pos[0] = carry;
-            S.sel_mtf[i] = (uint8_t)j;
-        }
-    }
     if (tid == 64) {   // size of the fixed part
         uint32_t hb = with_block_header ? 105u : 0u;
         hb += 16;
         for (int i = 0; i < 16; i++) { bool u = false; for (int j = 0; j < 16; j++) u |= in_use[i * 16 + j] != 0; if (u) hb += 16; }
         hb += 3 + 15;
         S.hdr_bits = hb;
+    }
+    __syncthreads();
+    // ---- selector MTF (bz/compress.c:462-478) in parallel: the MTF position of table v at selector i
+    // is the number of tables used more recently than v; a table never used yet sits at its initial
+    // index (virtual last use -(t+1)).  Each thread owns a run of selectors and needs, per table,
+    // the last use before its run: six exclusive block-wide max-scans.
+    {
+        const int spt0 = (nsel + HT - 1) / HT;
+        const int a0 = min(tid * spt0, nsel), a1 = min(a0 + spt0, nsel);
+        int last[6];
+#pragma unroll
+        for (int t = 0; t < 6; t++) last[t] = 0;                 // (position + 1), 0 = not used in my run
+        for (int i = a0; i < a1; i++) {
+            int v = S.selector[i];
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (v == t) last[t] = i + 1;
+        }
+        int before[6];
+#pragma unroll
+        for (int t = 0; t < 6; t++) {
+            uint32_t tot;
+            uint32_t ex = block_excl_max<uint32_t>((uint32_t)last[t], S.scan, &tot);
+            before[t] = ex ? (int)ex : -t;                         // -t orders never-used tables 0,1,2,... (ties impossible)
+        }
+        for (int i = a0; i < a1; i++) {
+            int v = S.selector[i];
+            int lv = 0;
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (v == t) lv = before[t];
+            int j = 0;
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (t < ng && before[t] > lv) j++;
+            S.sel_mtf[i] = (uint8_t)j;
+#pragma unroll
+            for (int t = 0; t < 6; t++) if (v == t) before[t] = i + 1;
+        }
     }
     __syncthreads();
     // ---- layout: [fixed part][selectors][tables][symbols] ----
