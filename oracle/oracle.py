@@ -230,3 +230,40 @@ def transform(bed):
                         line_count=c.line_count, bases_nonunique=c.bases_nonunique,
                         bases_unique=c.bases_unique))
     return tf[:tf_len.value].tobytes(), out, dropped.value
+
+
+# ---- archive container (ARCHIVE_FORMAT.md; parity unpinned by the reference) -----------------
+def _json_string(b: bytes) -> bytes:
+    """jansson 2.9 dump_string without JSON_ESCAPE_SLASH / JSON_ENSURE_ASCII (src/dump.c:70-160)."""
+    out = bytearray(b'"')
+    short = {0x5c: b"\\\\", 0x22: b'\\"', 0x08: b"\\b", 0x0c: b"\\f", 0x0a: b"\\n", 0x0d: b"\\r", 0x09: b"\\t"}
+    for c in b:
+        if c in short:
+            out += short[c]
+        elif c < 0x20:
+            out += b"\\u%04X" % c
+        else:
+            out.append(c)
+    out += b'"'
+    return bytes(out)
+
+
+def archive(bed, level=9, note=""):
+    """The whole path on the CPU: restated transform, one bzip2 stream per chromosome
+    (reference libbz2 when oracle/_ref is built, else the restatement), container."""
+    tf, chroms, _ = transform(bed)
+    comp = ref_bz_compress if have_ref() else bz_compress
+    streams, metas, off = [], [], 0
+    for c in chroms:
+        s = tf[c["tf_off"]:c["tf_off"] + c["tf_len"]]
+        z = comp(s, level)
+        nblk = len([b for b in rle1_blocks(s, level)[0] if b["nblock"]])
+        metas.append(b'{"chromosome":' + _json_string(c["name"]) +
+                     b',"offset":%d,"size":%d,"lines":%d,"blocks":%d,"transformedBytes":%d,"nonUniqueBases":%d,"uniqueBases":%d}'
+                     % (off, len(z), c["line_count"], nblk, c["tf_len"], c["bases_nonunique"], c["bases_unique"]))
+        streams.append(z)
+        off += len(z)
+    note_b = note.encode() if isinstance(note, str) else (note or b"")
+    hdr = (b'{"archive":{"type":"starch","version":{"major":3,"minor":0,"revision":0},"creator":"starch3_b200",'
+           b'"compression":"bzip2","blockSize100k":%d,"note":' % level) + _json_string(note_b) + b'},"streams":[' + b",".join(metas) + b"]}"
+    return bytes([0xca, 0x5c, 0xad, 0x1a]) + hdr + b"\n" + b"".join(streams)

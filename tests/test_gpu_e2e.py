@@ -60,6 +60,24 @@ def test_archive_parity_and_roundtrip(ctx, oracle, cfg, lines):
     assert sum(m["size"] for m in meta["streams"]) == len(payload)
 
 
+@pytest.mark.parametrize("cfg,lines,level,note", [(2, 30000, 9, ""), (5, 40000, 3, 'note with "quotes"\tand\\slashes/\x01'), (1, 20000, 1, "x")])
+def test_whole_archive_bytes_equal_oracle(ctx, oracle, cfg, lines, level, note):
+    bed = synth.bed(cfg, lines).tobytes()
+    res = ctx.compress_bed(bed, level, note=note)
+    assert res.archive == oracle.archive(bed, level, note)
+    json.loads(res.archive[4:res.archive.index(b"\n", 4)])
+
+
+def test_archive_odd_chromosome_names_and_empty_input(ctx, oracle):
+    bed = b'we"ird\\n\x07me\t1\t5\n' + "chr\u00e9\t2\t9\tz\n".encode()
+    res = ctx.compress_bed(bed, 9)
+    assert res.archive == oracle.archive(bed, 9, "")
+    meta, _ = parse_archive(res.archive)
+    assert [s["chromosome"] for s in meta["streams"]] == ['we"ird\\n\x07me', "chr\u00e9"]
+    empty = ctx.compress_bed(b"", 9)
+    assert empty.archive == oracle.archive(b"", 9, "") and empty.n_blocks == 0
+
+
 def test_multiblock_chromosomes_level1(ctx, oracle):
     """Small block size so every chromosome has several blocks and unaligned bit joins."""
     bed = synth.bed(2, 120000).tobytes()
@@ -95,3 +113,24 @@ def test_full_size_blocks_properties(ctx, oracle):
     tf = bz2.decompress(z)
     assert inverse_transform(b"chr1", tf) == bed
     assert z == (oracle.ref_bz_compress if oracle.have_ref() else oracle.bz_compress)(tf, 9)
+
+
+def test_cli_client_matches_library(ctx, tmp_path):
+    """The C++ client (include/starch3api.hpp + csrc/host/starch3.cpp, the reference's main() sequence)
+    writes the same archive as the C ABI called directly."""
+    import os
+    import subprocess
+    import starch3_b200 as s3
+    exe = os.path.join(os.path.dirname(s3.lib_path), "starch3")
+    bed = synth.bed(2, 30000).tobytes()
+    f = tmp_path / "in.bed"
+    f.write_bytes(bed)
+    p = subprocess.run([exe, "--note", "cli", str(f)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert p.returncode == 0, p.stderr[-500:]
+    assert p.stdout == ctx.compress_bed(bed, 9, note="cli").archive
+    p2 = subprocess.run([exe, "--block-size", "2"], input=bed, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert p2.returncode == 0 and p2.stdout == ctx.compress_bed(bed, 2).archive
+    bad = subprocess.run([exe], input=b"chr1\t5\n", stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert bad.returncode != 0 and b"Error:" in bad.stderr
+    gz = subprocess.run([exe, "--gzip"], input=bed, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert gz.returncode != 0 and b"unsupported" in gz.stderr          # starch3api.hpp:777-779

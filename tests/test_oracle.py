@@ -167,3 +167,19 @@ def test_transform_then_bzip2_roundtrip(oracle):
         s = tf[c["tf_off"]:c["tf_off"] + c["tf_len"]]
         z = oracle.bz_compress(s, 9)
         assert bz2.decompress(z) == s
+
+
+def test_archive_container(oracle):
+    import json
+    bed = b"chr1\t5\t9\nchr2\t10\t20\tx\nchr2\t30\t40\ty\n"
+    arc = oracle.archive(bed, 9, 'a "note"')
+    assert arc[:4] == bytes([0xca, 0x5c, 0xad, 0x1a])                   # starch3api.hpp:907-910
+    nl = arc.index(b"\n", 4)
+    meta = json.loads(arc[4:nl])
+    assert meta["archive"]["note"] == 'a "note"' and meta["archive"]["compression"] == "bzip2"
+    payload = arc[nl + 1:]
+    texts = [bz2.decompress(payload[s["offset"]:s["offset"] + s["size"]]) for s in meta["streams"]]
+    assert texts == [b"p4\n5\n", b"p10\n10\tx\n10\ty\n"]
+    assert [s["lines"] for s in meta["streams"]] == [1, 2]
+    # compact jansson-style text: no spaces, insertion order
+    assert arc[4:nl].startswith(b'{"archive":{"type":"starch","version":{"major":3,"minor":0,"revision":0},')
