@@ -134,3 +134,11 @@ def test_cli_client_matches_library(ctx, tmp_path):
     assert bad.returncode != 0 and b"Error:" in bad.stderr
     gz = subprocess.run([exe, "--gzip"], input=bed, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert gz.returncode != 0 and b"unsupported" in gz.stderr          # starch3api.hpp:777-779
+
+
+def test_sharded_single_rank_gpu(ctx, oracle):
+    """The multi-GPU host logic (starch3_b200/shard.py) with the real per-rank compressor."""
+    from starch3_b200 import shard
+    bed = synth.bed(5, 30000).tobytes() + b"chr1\t5\t9\n"
+    arc = shard.compress_sharded(bed, shard.gpu_compress_fn(ctx), 9, "s")
+    assert arc == ctx.compress_bed(bed, 9, note="s").archive == oracle.archive(bed, 9, "s")
