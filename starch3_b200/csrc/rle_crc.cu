@@ -40,48 +40,87 @@ struct StreamMap {
     }
 };
 
-struct ByteWin {
-    uint8_t b[RB + 2];   // b[0] = byte before, b[1..RB] = the thread's bytes, b[RB+1] = byte after
-    uint64_t pos0;       // absolute index of b[1]
+// One thread's 16 input bytes plus the byte before and after, kept as words so that the
+// run structure comes from SIMD-in-register byte compares instead of per-byte branches.
+struct Win {
+    uint32_t x[4];       // bytes pos0 .. pos0+15, little endian
+    uint32_t prevb;      // byte pos0-1 (0 if none)
+    uint32_t nextb;      // byte pos0+16 (0 if none)
+    uint64_t pos0;
     int cnt;             // valid bytes (0..RB)
 };
 
-__device__ __forceinline__ void load_win(const uint8_t *in, uint64_t n, uint64_t pos0, ByteWin &w)
+__device__ __forceinline__ void load_win(const uint8_t *in, uint64_t n, uint64_t pos0, Win &w)
 {
     w.pos0 = pos0;
     w.cnt = pos0 >= n ? 0 : (n - pos0 >= RB ? RB : (int)(n - pos0));
     if (w.cnt == RB) {
         uint4 v = *reinterpret_cast<const uint4 *>(in + pos0);
-        unsigned x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < RB; k++) w.b[1 + k] = (uint8_t)(x[k >> 2] >> (8 * (k & 3)));
+        w.x[0] = v.x; w.x[1] = v.y; w.x[2] = v.z; w.x[3] = v.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < RB; k++) w.b[1 + k] = k < w.cnt ? in[pos0 + k] : 0;
+        for (int q = 0; q < 4; q++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (q * 4 + k < w.cnt) v |= (uint32_t)in[pos0 + q * 4 + k] << (8 * k);
+            w.x[q] = v;
+        }
     }
-    w.b[0] = (pos0 > 0 && w.cnt > 0) ? in[pos0 - 1] : 0;
-    w.b[RB + 1] = (w.cnt == RB && pos0 + RB < n) ? in[pos0 + RB] : 0;
+    w.prevb = (pos0 > 0 && w.cnt > 0) ? in[pos0 - 1] : 0;
+    w.nextb = (w.cnt == RB && pos0 + RB < n) ? in[pos0 + RB] : 0;
 }
 
-// run-start test for byte k (0-based inside the window)
-__device__ __forceinline__ bool run_starts(const ByteWin &w, int k, const StreamMap &sm)
+__device__ __forceinline__ uint32_t byte_of(const Win &w, int k) { return (w.x[k >> 2] >> (8 * (k & 3))) & 0xffu; }
+
+// Stream starts inside the current tile, found once per CTA (streams are few and sorted).
+struct TileStarts {
+    uint64_t k0;        // index of the first stream start >= tile begin
+    uint32_t count;     // stream starts in [tile begin, tile end]   (tile end = first byte of the next tile)
+};
+__device__ __forceinline__ void find_tile_starts(const StreamMap &sm, uint64_t tile_begin, TileStarts *ts)
 {
-    uint64_t i = w.pos0 + k;
-    if (i == 0) return true;
-    if (w.b[1 + k] != w.b[k]) return true;
-    return sm.is_start(i);
+    uint64_t lo = 0, hi = sm.n_streams + 1;          // soff has n_streams + 1 entries (the last is the end)
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sm.soff[mid] < tile_begin) lo = mid + 1; else hi = mid; }
+    uint64_t k = lo; uint32_t c = 0;
+    while (k + c < sm.n_streams + 1 && sm.soff[k + c] <= tile_begin + RTILE) c++;
+    ts->k0 = k; ts->count = c;
+}
+
+// bit k (0..16) set <=> a run starts at window byte k (bit 16: at the byte after the window).
+// Bits at or beyond the end of the input are set: the input end closes the last chunk.
+__device__ __forceinline__ uint32_t run_start_mask(const Win &w, const StreamMap &sm, const TileStarts &ts, uint64_t n)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t prevw = q == 0 ? w.prevb : (w.x[q - 1] >> 24);
+        uint32_t sh = (w.x[q] << 8) | prevw;                      // every byte's predecessor
+        uint32_t ne = __vcmpne4(w.x[q], sh) & 0x01010101u;
+        m |= ((ne * 0x01020408u) >> 24) << (4 * q);
+    }
+    if ((w.x[3] >> 24) != w.nextb) m |= 1u << 16;
+    if (w.pos0 == 0) m |= 1u;
+    for (uint32_t q = 0; q < ts.count; q++) {                     // almost always zero iterations
+        uint64_t st = sm.soff[ts.k0 + q];
+        if (st >= w.pos0 && st <= w.pos0 + RB) m |= 1u << (uint32_t)(st - w.pos0);
+    }
+    // positions >= n count as starts
+    uint64_t left = n > w.pos0 ? n - w.pos0 : 0;
+    if (left <= RB) m |= ~0u << (uint32_t)left;
+    return m & 0x1ffffu;
 }
 
 // ---- pass 1: last run start per tile (max-scan aggregate) --------------------
 __global__ void __launch_bounds__(RT) k_rle_runs(const uint8_t *in, uint64_t n, StreamMap sm, uint64_t *agg)
 {
     __shared__ uint64_t s[33];
-    ByteWin w;
+    __shared__ TileStarts ts;
+    if (threadIdx.x == 0) find_tile_starts(sm, (uint64_t)blockIdx.x * RTILE, &ts);
+    __syncthreads();
+    Win w;
     load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
-    uint64_t last = 0;   // position + 1 of the last run start among my bytes
-#pragma unroll
-    for (int k = 0; k < RB; k++)
-        if (k < w.cnt && run_starts(w, k, sm)) last = w.pos0 + k + 1;
+    uint32_t m = w.cnt ? run_start_mask(w, sm, ts, n) & ((1u << w.cnt) - 1) : 0;
+    uint64_t last = m ? w.pos0 + (31 - __clz(m)) + 1 : 0;   // position + 1 of the last run start among my bytes
     uint64_t tot;
     block_excl_max<uint64_t>(last, s, &tot);
     if (threadIdx.x == 0) agg[blockIdx.x] = tot;
@@ -98,44 +137,51 @@ struct SumU64b {
     __host__ __device__ static T op(T a, T b) { return a + b; }
 };
 
-// Per-thread view of the RLE1 state of its RB bytes: offset inside the run for
-// every byte, chunk-end flags and emitted byte counts.
+// Per-thread RLE1 result for its RB bytes.
 struct RleLocal {
     uint32_t emit_mask;   // bit k: byte k is copied (chunk offset < 4)
     uint32_t cnt_mask;    // bit k: byte k ends a chunk of length >= 4 (emits the count byte)
-    uint8_t  cnt_val[RB]; // count byte value where cnt_mask is set
+    uint32_t cnt_val[RB / 4];   // count bytes, packed like the input words
     uint32_t total;       // emitted bytes
 };
 
 // `carry` = position+1 of the last run start before this tile (exclusive max-scan).
-__device__ __forceinline__ void rle_local(const ByteWin &w, const StreamMap &sm, uint64_t carry, uint64_t *s_max,
-                                          RleLocal &r, uint64_t n)
+__device__ __forceinline__ void rle_local(const Win &w, uint32_t startmask, uint64_t carry, uint64_t *s_max, RleLocal &r)
 {
-    uint64_t last = 0;
-    uint32_t startmask = 0;
-#pragma unroll
-    for (int k = 0; k < RB; k++)
-        if (k < w.cnt && run_starts(w, k, sm)) { last = w.pos0 + k + 1; startmask |= 1u << k; }
+    uint32_t own = w.cnt ? startmask & ((1u << w.cnt) - 1) : 0;
+    uint64_t last = own ? w.pos0 + (31 - __clz(own)) + 1 : 0;
     uint64_t tot;
     uint64_t before = block_excl_max<uint64_t>(last, s_max, &tot);   // run start in effect before my first byte
     if (carry > before) before = carry;
-    uint64_t rs = before;     // position+1 of current run start
     r.emit_mask = 0; r.cnt_mask = 0; r.total = 0;
 #pragma unroll
+    for (int q = 0; q < RB / 4; q++) r.cnt_val[q] = 0;
+    if (w.cnt == 0) return;
+    // chunk offset of my first byte
+    uint32_t c;
+    if (startmask & 1u) c = 0;
+    else {
+        uint64_t o64 = w.pos0 - (before - 1);
+        c = o64 < 0xffffffffull ? (uint32_t)o64 % 255u : (uint32_t)(o64 % 255u);
+    }
+    // fast path: every chunk offset in this window stays <= 2 -> every byte is copied, no count bytes.
+    // Offsets grow by one per continuing byte, so that holds iff no three continue-bits are adjacent
+    // and the run entering the window (offset c) does not reach 3 either.
+    {
+        uint32_t eqv = ~startmask & ((1u << w.cnt) - 1);      // bit k: byte k continues the run of byte k-1
+        uint32_t lead = (uint32_t)__ffs((int)~(eqv >> 1)) - 1;  // continuing bytes right after byte 0
+        if ((eqv & (eqv >> 1) & (eqv >> 2)) == 0 && c + lead <= 2) {
+            r.emit_mask = (1u << w.cnt) - 1; r.total = (uint32_t)w.cnt;
+            return;
+        }
+    }
+#pragma unroll
     for (int k = 0; k < RB; k++) {
-        r.cnt_val[k] = 0;
         if (k < w.cnt) {
-            uint64_t i = w.pos0 + k;
-            if (startmask & (1u << k)) rs = i + 1;
-            uint64_t o64 = i - (rs - 1);
-            uint32_t c = o64 < 0xffffffffull ? (uint32_t)o64 % 255u : (uint32_t)(o64 % 255u);
-            // chunk ends here if the next byte starts a new run, the chunk is full, or the input ends
-            bool last_in_chunk;
-            if (c == 254 || i + 1 >= n) last_in_chunk = true;
-            else if (w.b[2 + k] != w.b[1 + k]) last_in_chunk = true;
-            else last_in_chunk = sm.is_start(i + 1);
+            if (k > 0) { c = (startmask >> k) & 1u ? 0u : (c == 254u ? 0u : c + 1u); }
+            bool last_in_chunk = c == 254u || ((startmask >> (k + 1)) & 1u);
             if (c < 4) { r.emit_mask |= 1u << k; r.total++; }
-            if (last_in_chunk && c >= 3) { r.cnt_mask |= 1u << k; r.cnt_val[k] = (uint8_t)(c - 3); r.total++; }
+            if (last_in_chunk && c >= 3) { r.cnt_mask |= 1u << k; r.cnt_val[k >> 2] |= (c - 3) << (8 * (k & 3)); r.total++; }
         }
     }
 }
@@ -146,10 +192,14 @@ __global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64
 {
     __shared__ uint64_t s_max[33];
     __shared__ uint32_t s_sum[33];
-    ByteWin w;
+    __shared__ TileStarts ts;
+    if (threadIdx.x == 0) find_tile_starts(sm, (uint64_t)blockIdx.x * RTILE, &ts);
+    __syncthreads();
+    Win w;
     load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
+    uint32_t sm_mask = run_start_mask(w, sm, ts, n);
     RleLocal r;
-    rle_local(w, sm, run_carry[blockIdx.x], s_max, r, n);
+    rle_local(w, sm_mask, run_carry[blockIdx.x], s_max, r);
     uint32_t tot;
     block_excl_sum<uint32_t>(r.total, s_sum, &tot);
     if (threadIdx.x == 0) agg[blockIdx.x] = tot;
@@ -321,10 +371,14 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
 {
     __shared__ uint64_t s_max[33];
     __shared__ uint32_t s_sum[33];
-    ByteWin w;
+    __shared__ TileStarts ts;
+    if (threadIdx.x == 0) find_tile_starts(sm, (uint64_t)blockIdx.x * RTILE, &ts);
+    __syncthreads();
+    Win w;
     load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
+    uint32_t sm_mask = run_start_mask(w, sm, ts, n);
     RleLocal r;
-    rle_local(w, sm, run_carry[blockIdx.x], s_max, r, n);
+    rle_local(w, sm_mask, run_carry[blockIdx.x], s_max, r);
     uint32_t tot;
     uint32_t ex = block_excl_sum<uint32_t>(r.total, s_sum, &tot);
     if (w.cnt == 0) return;
@@ -339,6 +393,8 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
     uint64_t b_end = blocks[bi].in_end, b_e0 = blocks[bi].e_base;
     uint8_t *dst = blk_bytes + bi * (uint64_t)BLK_STRIDE;
     uint8_t *use = in_use + bi * 256;
+    // common case: the 16 bytes are copied unchanged into one block at a 16-byte-aligned... (alignment is arbitrary,
+    // so bytes are stored one by one; the L2 merges them into full sectors)
 #pragma unroll
     for (int k = 0; k < RB; k++) {
         if (k < w.cnt) {
@@ -348,8 +404,9 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
                 b_end = blocks[bi].in_end; b_e0 = blocks[bi].e_base;
                 dst = blk_bytes + bi * (uint64_t)BLK_STRIDE; use = in_use + bi * 256;
             }
-            if (r.emit_mask & (1u << k)) { dst[e - b_e0] = w.b[1 + k]; use[w.b[1 + k]] = 1; e++; }
-            if (r.cnt_mask & (1u << k)) { dst[e - b_e0] = r.cnt_val[k]; use[r.cnt_val[k]] = 1; e++; }
+            uint8_t by = (uint8_t)byte_of(w, k);
+            if (r.emit_mask & (1u << k)) { dst[e - b_e0] = by; use[by] = 1; e++; }
+            if (r.cnt_mask & (1u << k)) { uint8_t cv = (uint8_t)((r.cnt_val[k >> 2] >> (8 * (k & 3))) & 0xffu); dst[e - b_e0] = cv; use[cv] = 1; e++; }
         }
     }
 }
