@@ -46,7 +46,7 @@ struct BwtP {
     uint32_t *init_a;          // [nb] alphabet size
 };
 
-enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2 };
+enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2, MODE_KVX = 3 };   // KVX: key/value pairs saved by the histogram pass, ~0 = not taking part
 
 // item p of block lb for the given source mode; returns false if the item does not take part
 template <int MODE>
@@ -75,7 +75,7 @@ __device__ __forceinline__ bool get_item(const BwtP &P, uint32_t lb, uint32_t p,
     } else {
         uint64_t kv = kv_in[(uint64_t)lb * BLK_STRIDE + p];
         key = (uint32_t)(kv >> 32); val = (uint32_t)kv;
-        return true;
+        return MODE == MODE_KVX ? kv != ~0ull : true;
     }
 }
 
@@ -94,7 +94,7 @@ __device__ __forceinline__ bool block_live(const BwtP &P, uint32_t lb, int phase
 // ---- radix pass: per-tile digit histogram ------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(ST) k_hist(BwtP P, int shift, int phase, uint32_t round, const uint32_t *cnt_arr,
-                                             const uint64_t *kv_in, const uint32_t *act_cur)
+                                             const uint64_t *kv_in, const uint32_t *act_cur, uint64_t *kv_save)
 {
     __shared__ uint32_t sh[NBINS];
     uint32_t lb = blockIdx.y, tile = blockIdx.x;
@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(ST) k_hist(BwtP P, int shift, int phase, uint3
         uint32_t key, val;
         bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, key, val);
         dg[r] = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
+        // the gathered pairs are kept so that the scatter of this pass reads them back coalesced
+        if (kv_save && base + r * 32 < cnt) kv_save[(uint64_t)lb * BLK_STRIDE + base + r * 32] = ok ? (((uint64_t)key << 32) | val) : ~0ull;
     }
 #pragma unroll
     for (int r = 0; r < SI; r++) {
@@ -609,19 +611,19 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     dim3 grid(NT, (unsigned)nb);
     static bool attr_done = false;
     if (!attr_done) {
-        S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         attr_done = true;
     }
     const uint32_t *no_act = nullptr;
     const uint64_t *no_kv = nullptr;
     uint32_t *no_out = nullptr;
+    uint64_t *no_save = nullptr;
     // ---- init: order by the first k symbols ----
-    S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, no_act);
+    S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, no_act, P.kv1);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
-    S3G_LAUNCH(ctx, k_scatter<MODE_INIT>, grid, ST, sizeof(ScatterSmem), P, 0, 0, 0u, P.cnt_n, no_kv, P.kv0, no_act);
-    S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, no_act);
+    S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, 0, 0, 0u, P.cnt_n, P.kv1, P.kv0, no_act);
+    S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, no_act, no_save);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
     S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
     S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv1, no_act);
@@ -640,10 +642,10 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaMemsetAsync(act_next, 0, nb * 4, ctx->stream));
         S3G_CUDA(cudaMemsetAsync(g_next, 0, 8, ctx->stream));
         uint32_t *newrank = reinterpret_cast<uint32_t *>(P.kv0);
-        S3G_LAUNCH(ctx, k_hist<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, act_cur);
+        S3G_LAUNCH(ctx, k_hist<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, act_cur, P.kv1);
         S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_n, P.cnt_m, act_cur);
-        S3G_LAUNCH(ctx, k_scatter<MODE_MM>, grid, ST, sizeof(ScatterSmem), P, 0, 1, round, P.cnt_n, no_kv, P.kv0, act_cur);
-        S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, act_cur);
+        S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, 0, 1, round, P.cnt_n, P.kv1, P.kv0, act_cur);
+        S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, act_cur, no_save);
         S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_m, no_out, act_cur);
         S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
         S3G_LAUNCH(ctx, k_bound_agg<false>, grid, ST, 0, P, round, P.kv1, act_cur);
