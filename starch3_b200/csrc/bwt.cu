@@ -236,10 +236,10 @@ __global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int shift, int phase,
 // ---- group boundaries and new ranks -------------------------------------------
 // Sorted items p of block lb: key_p (group = SA position of the group start; in INIT
 // mode the symbol key), val_p.  Thread t of a tile owns SI consecutive items.
-template <bool INIT>
+template <bool INIT, int ITEMS>
 __device__ __forceinline__ void boundary_flags(const BwtP &P, uint32_t lb, uint32_t n, uint32_t cnt, uint32_t h,
                                                const uint64_t *kv, uint32_t p0, uint32_t &headmask, uint32_t &bndmask,
-                                               uint64_t *items /*SI+1*/)
+                                               uint64_t *items /*ITEMS+1*/)
 {
     // flags for items p0 .. p0+SI (one extra for the singleton test of the last own item)
     const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
@@ -254,7 +254,7 @@ __device__ __forceinline__ void boundary_flags(const BwtP &P, uint32_t lb, uint3
     }
     headmask = 0; bndmask = 0;
 #pragma unroll
-    for (int k = 0; k <= SI; k++) {
+    for (int k = 0; k <= ITEMS; k++) {
         uint32_t p = p0 + k;
         if (p < cnt) {
             uint64_t it = a[p];
@@ -330,8 +330,11 @@ __global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const 
     }
 }
 
+constexpr int BT = 512;                 // boundary kernels: 512 threads x 8 items per tile (same 4096-item tiles)
+constexpr int BI = STILE / BT;
+
 template <bool INIT>
-__global__ void __launch_bounds__(ST) k_bound_apply(BwtP P, uint32_t round, const uint64_t *kv, uint32_t *newrank,
+__global__ void __launch_bounds__(BT, 2) k_bound_apply(BwtP P, uint32_t round, const uint64_t *kv, uint32_t *newrank,
                                                     const uint32_t *act_cur, uint32_t *act_next, unsigned long long *g_act_next)
 {
     __shared__ uint32_t sm[33];
@@ -345,18 +348,18 @@ __global__ void __launch_bounds__(ST) k_bound_apply(BwtP P, uint32_t round, cons
     {
         uint32_t ch = 0, cb = 0;
         const uint32_t *ag = P.agg + (uint64_t)lb * NT * 2;
-        for (uint32_t t = threadIdx.x; t < tile; t += ST) { ch = max(ch, ag[t * 2]); cb = max(cb, ag[t * 2 + 1]); }
+        for (uint32_t t = threadIdx.x; t < tile; t += BT) { ch = max(ch, ag[t * 2]); cb = max(cb, ag[t * 2 + 1]); }
         uint32_t th, tb;
         block_excl_max<uint32_t>(ch, sm, &th);
         block_excl_max<uint32_t>(cb, sm, &tb);
         if (threadIdx.x == 0) { carry[0] = th; carry[1] = tb; }
         __syncthreads();
     }
-    uint32_t p0 = tile * STILE + threadIdx.x * SI;
-    uint32_t hm, bm; uint64_t items[SI + 1];
-    boundary_flags<INIT>(P, lb, n, cnt, h, kv, p0, hm, bm, items);
-    uint32_t own = (1u << SI) - 1;
-    uint32_t valid = p0 < cnt ? (cnt - p0 >= SI ? own : (1u << (cnt - p0)) - 1) : 0;
+    uint32_t p0 = tile * STILE + threadIdx.x * BI;
+    uint32_t hm, bm; uint64_t items[BI + 1];
+    boundary_flags<INIT, BI>(P, lb, n, cnt, h, kv, p0, hm, bm, items);
+    uint32_t own = (1u << BI) - 1;
+    uint32_t valid = p0 < cnt ? (cnt - p0 >= BI ? own : (1u << (cnt - p0)) - 1) : 0;
     uint32_t hmo = hm & valid, bmo = bm & valid;
     uint32_t lh = hmo ? p0 + (31 - __clz(hmo)) + 1 : 0;
     uint32_t lbn = bmo ? p0 + (31 - __clz(bmo)) + 1 : 0;
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(ST) k_bound_apply(BwtP P, uint32_t round, cons
     uint32_t *nr = newrank + (uint64_t)lb * BLK_STRIDE;
     uint32_t still = 0;
 #pragma unroll
-    for (int k = 0; k < SI; k++) {
+    for (int k = 0; k < BI; k++) {
         if (valid & (1u << k)) {
             uint32_t p = p0 + k;
             if (hm & (1u << k)) hp = p + 1;
@@ -627,7 +630,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
     S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
     S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv1, no_act);
-    S3G_LAUNCH(ctx, k_bound_apply<true>, grid, ST, 0, P, 0u, P.kv1, no_out, no_act, P.act, P.g_act);
+    S3G_LAUNCH(ctx, k_bound_apply<true>, grid, BT, 0, P, 0u, P.kv1, no_out, no_act, P.act, P.g_act);
     S3G_TRY(check_launch("bwt init"));
     // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
     unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
@@ -649,7 +652,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_m, no_out, act_cur);
         S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
         S3G_LAUNCH(ctx, k_bound_agg<false>, grid, ST, 0, P, round, P.kv1, act_cur);
-        S3G_LAUNCH(ctx, k_bound_apply<false>, grid, ST, 0, P, round, P.kv1, newrank, act_cur, act_next, g_next);
+        S3G_LAUNCH(ctx, k_bound_apply<false>, grid, BT, 0, P, round, P.kv1, newrank, act_cur, act_next, g_next);
         S3G_LAUNCH(ctx, k_rank_update, grid, ST, 0, P, round, P.kv1, newrank, act_cur);
         S3G_TRY(check_launch("bwt round"));
     }

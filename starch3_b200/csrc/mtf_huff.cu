@@ -52,6 +52,196 @@ __device__ __forceinline__ void mtf_chunk(const uint8_t *L, uint8_t *M, int beg,
     }
 }
 
+// zero runs in bijective base 2 (RUNA/RUNB, bz/compress.c:174-188), other ranks +1, then EOB; mtfFreq.
+// Called by all THREADS threads of the CTA after the ranks M[0..n) are visible.
+template <int THREADS>
+__device__ __forceinline__ void mtf_zero_runs(const uint8_t *M, uint16_t *mtfv, int n, int a, int *s_freq, uint32_t *s_scan,
+                                              BlockInfo *blocks, uint32_t lb, int32_t *freq_all)
+{
+    constexpr int DI = 8;
+    uint32_t out_base = 0;       // symbols written so far
+    uint32_t nz_carry = 0;       // (position + 1) of the last non-zero rank so far
+    int fa = 0, fb = 0;          // private RUNA / RUNB counts
+    for (int tile0 = 0; tile0 < n; tile0 += THREADS * DI) {
+        int p0 = tile0 + (int)threadIdx.x * DI;
+        uint8_t m[DI + 1];
+        if (p0 + DI < n) {
+            uint64_t v = *reinterpret_cast<const uint64_t *>(M + p0);      // slots are 128-byte aligned, p0 % 8 == 0
+#pragma unroll
+            for (int k = 0; k < DI; k++) m[k] = (uint8_t)(v >> (8 * k));
+            m[DI] = M[p0 + DI];
+        } else {
+#pragma unroll
+            for (int k = 0; k <= DI; k++) m[k] = (p0 + k < n) ? M[p0 + k] : (uint8_t)1;   // past the end acts as non-zero
+        }
+        uint32_t lastnz = 0;
+#pragma unroll
+        for (int k = 0; k < DI; k++) if (p0 + k < n && m[k]) lastnz = (uint32_t)(p0 + k + 1);
+        uint32_t tmax;
+        uint32_t ex = block_excl_max<uint32_t>(lastnz, s_scan, &tmax);
+        uint32_t rs = ex > nz_carry ? ex : nz_carry;     // the zero run in effect starts at position rs
+        uint32_t emit = 0;
+        uint32_t rs_k = rs;
+#pragma unroll
+        for (int k = 0; k < DI; k++) {
+            if (p0 + k < n) {
+                if (m[k]) { emit++; rs_k = (uint32_t)(p0 + k + 1); }
+                else if (m[k + 1]) { uint32_t r = (uint32_t)(p0 + k + 1) - rs_k; emit += 31 - __clz(r + 1); }
+            }
+        }
+        uint32_t ttot;
+        uint32_t eo = block_excl_sum<uint32_t>(emit, s_scan, &ttot);
+        uint32_t o = out_base + eo;
+        rs_k = rs;
+#pragma unroll
+        for (int k = 0; k < DI; k++) {
+            if (p0 + k < n) {
+                if (m[k]) { mtfv[o++] = (uint16_t)(m[k] + 1); atomicAdd(&s_freq[m[k] + 1], 1); rs_k = (uint32_t)(p0 + k + 1); }
+                else if (m[k + 1]) {
+                    uint32_t zp = (uint32_t)(p0 + k + 1) - rs_k - 1;
+                    for (;;) {
+                        if (zp & 1) { mtfv[o++] = 1; fb++; } else { mtfv[o++] = 0; fa++; }
+                        if (zp < 2) break;
+                        zp = (zp - 2) >> 1;
+                    }
+                }
+            }
+        }
+        out_base += ttot;
+        if (tmax > nz_carry) nz_carry = tmax;
+    }
+    if (fa) atomicAdd(&s_freq[0], fa);
+    if (fb) atomicAdd(&s_freq[1], fb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mtfv[out_base] = (uint16_t)(a + 1);      // EOB
+        s_freq[a + 1] += 1;
+        blocks[lb].n_mtf = out_base + 1;
+    }
+    __syncthreads();
+    int32_t *fq = freq_all + (uint64_t)lb * 258;
+    for (int i = threadIdx.x; i < 258; i += THREADS) fq[i] = s_freq[i];
+}
+
+// =============================================================================
+// (3c, alphabets of at most 32 symbols -- every BED-derived stream) MTF with the list held in
+// registers: 8 entries per 64-bit word, position found with a zero-byte test, move-to-front as a
+// masked one-byte shift.  A block is cut into 512 chunks, one per thread; the list a chunk
+// starts with is the symbols ordered by their last occurrence before the chunk.
+// =============================================================================
+constexpr int MS = 512;
+
+template <int NW>
+__device__ __forceinline__ uint32_t mtf_step(uint64_t (&lst)[NW], uint32_t s)
+{
+    const uint64_t K1 = 0x0101010101010101ull, K80 = 0x8080808080808080ull;
+    uint64_t pat = (uint64_t)s * K1;
+    int qh = 0; uint64_t zh = 0;
+#pragma unroll
+    for (int q = NW - 1; q >= 0; q--) {
+        uint64_t x = lst[q] ^ pat;
+        uint64_t z = (x - K1) & ~x & K80;        // lowest set bit marks the first zero byte of x
+        if (z) { qh = q; zh = z; }
+    }
+    uint32_t bpos = (uint32_t)(__ffsll((long long)zh) - 1) >> 3;
+    uint64_t inmask = bpos == 7 ? ~0ull : ((1ull << (8 * (bpos + 1))) - 1);
+    uint64_t carry = s;
+#pragma unroll
+    for (int q = 0; q < NW; q++) {
+        uint64_t old = lst[q];
+        uint64_t sh = (old << 8) | carry;
+        carry = old >> 56;
+        uint64_t m = q < qh ? ~0ull : (q == qh ? inmask : 0ull);
+        lst[q] = (old & ~m) | (sh & m);
+    }
+    return (uint32_t)qh * 8 + bpos;
+}
+
+template <int NW>
+__device__ __forceinline__ void mtf_thread_chunk(const uint8_t *L, uint8_t *M, int beg, int end, const int *s_last, int a)
+{
+    // initial list: symbols by decreasing last occurrence (virtual negative positions keep 0,1,2,.. for unseen ones)
+    uint64_t lst[NW];
+#pragma unroll
+    for (int q = 0; q < NW; q++) lst[q] = ~0ull;
+    for (int c = 0; c < a; c++) {
+        int v = s_last[c * MS + threadIdx.x];
+        int rank = 0;
+        for (int c2 = 0; c2 < a; c2++) rank += s_last[c2 * MS + threadIdx.x] > v ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < NW; q++)
+            if ((rank >> 3) == q) lst[q] = (lst[q] & ~(0xffull << (8 * (rank & 7)))) | ((uint64_t)c << (8 * (rank & 7)));
+    }
+    for (int p = beg; p < end; p += 8) {
+        uint64_t in8 = *reinterpret_cast<const uint64_t *>(L + p);          // beg % 8 == 0, slots padded
+        uint64_t out8 = 0;
+        int lim = end - p < 8 ? end - p : 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k < lim) {
+                uint32_t pos = mtf_step<NW>(lst, (uint32_t)(in8 >> (8 * k)) & 0xffu);
+                out8 |= (uint64_t)pos << (8 * k);
+            }
+        }
+        *reinterpret_cast<uint64_t *>(M + p) = out8;
+    }
+}
+
+__global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
+                                                  BlockInfo *blocks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *s_last = reinterpret_cast<int *>(smem_raw);            // [32][MS]
+    int *s_freq = s_last + 32 * MS;                             // [258]
+    uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_freq + 260);
+    const uint32_t lb = blockIdx.x;
+    const int n = (int)blocks[lb].nblock;
+    const int a = (int)blocks[lb].n_in_use;
+    if (a > 32) return;                                         // handled by k_mtf
+    const uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
+    uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
+    uint16_t *mtfv = mtfv_all + (uint64_t)lb * BLK_STRIDE;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 32 * MS; i += MS) s_last[i] = 0;
+    for (int i = tid; i < 258; i += MS) s_freq[i] = 0;
+    __syncthreads();
+    int chunk = (((n + MS - 1) / MS) + 7) & ~7;
+    int beg = tid * chunk, end = beg + chunk;
+    if (beg > n) beg = n;
+    if (end > n) end = n;
+    // phase A: last occurrence (position + 1) of every symbol inside my chunk, scanning backwards
+    {
+        uint32_t seen = 0, full = a >= 32 ? ~0u : ((1u << a) - 1);
+        for (int p = end - 1; p >= beg && seen != full; p--) {
+            uint32_t sy = L[p];
+            if (!((seen >> sy) & 1u)) { seen |= 1u << sy; s_last[sy * MS + tid] = p + 1; }
+        }
+    }
+    __syncthreads();
+    // phase B: exclusive "latest occurrence" over the chunks
+    if (tid < a) {
+        int run = -(tid + 1);
+        for (int ch = 0; ch < MS; ch++) {
+            int t = s_last[tid * MS + ch];
+            s_last[tid * MS + ch] = run;
+            if (t) run = t;
+        }
+    }
+    __syncthreads();
+    // phase C: ranks
+    if (beg < end) {
+        switch ((a + 7) >> 3) {
+            case 1: mtf_thread_chunk<1>(L, M, beg, end, s_last, a); break;
+            case 2: mtf_thread_chunk<2>(L, M, beg, end, s_last, a); break;
+            case 3: mtf_thread_chunk<3>(L, M, beg, end, s_last, a); break;
+            default: mtf_thread_chunk<4>(L, M, beg, end, s_last, a); break;
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    mtf_zero_runs<MS>(M, mtfv, n, a, s_freq, s_scan, blocks, lb, freq_all);
+}
+
 __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
                                             BlockInfo *blocks)
 {
@@ -62,6 +252,7 @@ __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, 
     const uint32_t lb = blockIdx.x;
     const int n = (int)blocks[lb].nblock;
     const int a = (int)blocks[lb].n_in_use;
+    if (a <= 32) return;                                        // handled by k_mtf_small
     const uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
     uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
     uint16_t *mtfv = mtfv_all + (uint64_t)lb * BLK_STRIDE;
@@ -115,64 +306,7 @@ __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, 
     }
     __threadfence_block();
     __syncthreads();
-    // phase D: zero runs in bijective base 2 (RUNA/RUNB, bz/compress.c:174-188), others +1, then EOB
-    constexpr int DI = 8;
-    uint32_t out_base = 0;       // symbols written so far
-    uint32_t nz_carry = 0;       // (position + 1) of the last non-zero rank so far
-    int fa = 0, fb = 0;          // private RUNA / RUNB counts
-    for (int tile0 = 0; tile0 < n; tile0 += MT * DI) {
-        int p0 = tile0 + (int)threadIdx.x * DI;
-        uint8_t m[DI + 1];
-#pragma unroll
-        for (int k = 0; k <= DI; k++) m[k] = (p0 + k < n) ? M[p0 + k] : (uint8_t)1;   // past the end acts as non-zero
-        uint32_t lastnz = 0;
-#pragma unroll
-        for (int k = 0; k < DI; k++) if (p0 + k < n && m[k]) lastnz = (uint32_t)(p0 + k + 1);
-        uint32_t tmax;
-        uint32_t ex = block_excl_max<uint32_t>(lastnz, s_scan, &tmax);
-        uint32_t rs = ex > nz_carry ? ex : nz_carry;     // zero run in effect starts at position rs
-        uint32_t emit = 0;
-        uint32_t rs_k = rs;
-#pragma unroll
-        for (int k = 0; k < DI; k++) {
-            if (p0 + k < n) {
-                if (m[k]) { emit++; rs_k = (uint32_t)(p0 + k + 1); }
-                else if (m[k + 1]) { uint32_t r = (uint32_t)(p0 + k + 1) - rs_k; emit += 31 - __clz(r + 1); }
-            }
-        }
-        uint32_t ttot;
-        uint32_t eo = block_excl_sum<uint32_t>(emit, s_scan, &ttot);
-        uint32_t o = out_base + eo;
-        rs_k = rs;
-#pragma unroll
-        for (int k = 0; k < DI; k++) {
-            if (p0 + k < n) {
-                if (m[k]) { mtfv[o++] = (uint16_t)(m[k] + 1); atomicAdd(&s_freq[m[k] + 1], 1); rs_k = (uint32_t)(p0 + k + 1); }
-                else if (m[k + 1]) {
-                    uint32_t zp = (uint32_t)(p0 + k + 1) - rs_k - 1;
-                    for (;;) {
-                        if (zp & 1) { mtfv[o++] = 1; fb++; } else { mtfv[o++] = 0; fa++; }
-                        if (zp < 2) break;
-                        zp = (zp - 2) >> 1;
-                    }
-                }
-            }
-        }
-        out_base += ttot;
-        if (tmax > nz_carry) nz_carry = tmax;
-    }
-    if (fa) atomicAdd(&s_freq[0], fa);
-    if (fb) atomicAdd(&s_freq[1], fb);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mtfv[out_base] = (uint16_t)(a + 1);      // EOB
-        s_freq[a + 1] += 1;
-        blocks[lb].n_mtf = out_base + 1;
-    }
-    __syncthreads();
-    int32_t *fq = freq_all + (uint64_t)lb * 258;
-    for (int i = threadIdx.x; i < 258; i += MT) fq[i] = s_freq[i];
-    (void)s_carry;
+    mtf_zero_runs<MT>(M, mtfv, n, a, s_freq, s_scan, blocks, lb, freq_all);
 }
 
 int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
@@ -182,6 +316,15 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->mtf0.ensure(slots));                 // MTF ranks before zero-run coding
     S3G_TRY(ctx->mtfv16.ensure(slots * 2));
     S3G_TRY(ctx->mtf_freq.ensure((size_t)nb * 258 * 4));
+    const size_t small_smem = (size_t)32 * MS * 4 + 260 * 4 + 40 * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        S3G_CUDA(cudaFuncSetAttribute(k_mtf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+        attr_done = true;
+    }
+    // alphabets of <= 32 symbols take the register-list kernel, larger ones the warp-cooperative one
+    S3G_LAUNCH(ctx, k_mtf_small, (unsigned)nb, MS, small_smem, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
+               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
     S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
                ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
     return check_launch("mtf");

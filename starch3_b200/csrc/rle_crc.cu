@@ -146,7 +146,8 @@ struct RleLocal {
 };
 
 // `carry` = position+1 of the last run start before this tile (exclusive max-scan).
-__device__ __forceinline__ void rle_local(const Win &w, uint32_t startmask, uint64_t carry, uint64_t *s_max, RleLocal &r)
+__device__ __forceinline__ void rle_local(const Win &w, uint32_t startmask, uint64_t carry, uint64_t *s_max, RleLocal &r,
+                                          uint32_t *c_first = nullptr)
 {
     uint32_t own = w.cnt ? startmask & ((1u << w.cnt) - 1) : 0;
     uint64_t last = own ? w.pos0 + (31 - __clz(own)) + 1 : 0;
@@ -164,6 +165,7 @@ __device__ __forceinline__ void rle_local(const Win &w, uint32_t startmask, uint
         uint64_t o64 = w.pos0 - (before - 1);
         c = o64 < 0xffffffffull ? (uint32_t)o64 % 255u : (uint32_t)(o64 % 255u);
     }
+    if (c_first) *c_first = c;
     // fast path: every chunk offset in this window stays <= 2 -> every byte is copied, no count bytes.
     // Offsets grow by one per continuing byte, so that holds iff no three continue-bits are adjacent
     // and the run entering the window (offset c) does not reach 3 either.
@@ -188,7 +190,7 @@ __device__ __forceinline__ void rle_local(const Win &w, uint32_t startmask, uint
 
 // ---- pass 2: emitted bytes per tile -----------------------------------------
 __global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64_t n, StreamMap sm, const uint64_t *run_carry,
-                                                        uint64_t *agg)
+                                                        uint64_t *agg, uint16_t *win_e, uint8_t *win_c)
 {
     __shared__ uint64_t s_max[33];
     __shared__ uint32_t s_sum[33];
@@ -199,10 +201,15 @@ __global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64
     load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
     uint32_t sm_mask = run_start_mask(w, sm, ts, n);
     RleLocal r;
-    rle_local(w, sm_mask, run_carry[blockIdx.x], s_max, r);
+    uint32_t c0 = 0;
+    rle_local(w, sm_mask, run_carry[blockIdx.x], s_max, r, &c0);
     uint32_t tot;
-    block_excl_sum<uint32_t>(r.total, s_sum, &tot);
+    uint32_t ex = block_excl_sum<uint32_t>(r.total, s_sum, &tot);
     if (threadIdx.x == 0) agg[blockIdx.x] = tot;
+    // per-window prefix (relative to the tile) and chunk offset of the window's first byte: the block
+    // cut walks from a window start instead of re-deriving the state of a whole tile
+    win_e[(uint64_t)blockIdx.x * RT + threadIdx.x] = (uint16_t)ex;
+    win_c[(uint64_t)blockIdx.x * RT + threadIdx.x] = (uint8_t)c0;
 }
 
 // ---- pass 3: block cut, one warp per stream -----------------------------------
@@ -212,88 +219,67 @@ __global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64
 // scan of the one tile that holds the crossing.
 struct CutWalker {
     const uint8_t *in; uint64_t n; StreamMap sm;
-    const uint64_t *run_carry; const uint64_t *e_base;   // per tile (exclusive scans)
+    const uint64_t *e_base;      // per tile: emitted bytes before the tile (exclusive scan), [ntiles] = total
+    const uint16_t *win_e;       // per 16-byte window: emitted bytes before the window, relative to its tile
+    const uint8_t *win_c;        // per window: chunk offset (0..254) of its first byte
 
-    // RLE1 state of one byte given the run start in effect (rs = position + 1)
-    __device__ __forceinline__ void step(uint64_t i, uint8_t prev, uint8_t c, uint64_t &rs, uint32_t &emit, bool &last) const
+    // serial walk from the start of window `win`; stops at the first chunk end x <= s1 with E(x) >= target
+    // (or, when stop_at != ~0, exactly at position stop_at) and returns x and E(x)
+    __device__ void walk(uint64_t win, uint64_t target, uint64_t s1, uint64_t stop_at, uint64_t *x_out, uint64_t *e_out) const
     {
-        if (i == 0 || c != prev || sm.is_start(i)) rs = i + 1;
-        uint64_t o64 = i - (rs - 1);
-        uint32_t o = o64 < 0xffffffffull ? (uint32_t)o64 % 255u : (uint32_t)(o64 % 255u);
-        if (o == 254 || i + 1 >= n) last = true;
-        else if (in[i + 1] != c) last = true;
-        else last = sm.is_start(i + 1);
-        emit = (o < 4 ? 1u : 0u) + ((last && o >= 3) ? 1u : 0u);
+        uint64_t i = win * RB;
+        uint64_t e = e_base[win / RT] + win_e[win];
+        uint32_t c = win_c[win];
+        bool first = true;
+        uint64_t x = s1;
+        for (; i < s1; i++) {
+            if (i == stop_at) { x = i; break; }
+            uint8_t ch = in[i];
+            if (!first) {
+                bool st = ch != in[i - 1] || sm.is_start(i);
+                c = st ? 0u : (c == 254u ? 0u : c + 1u);
+            }
+            first = false;
+            bool last;
+            if (c == 254u || i + 1 >= n) last = true;
+            else if (in[i + 1] != ch) last = true;
+            else last = sm.is_start(i + 1);
+            if (c < 4) e++;
+            if (last && c >= 3) e++;
+            if (stop_at == ~0ull && last && e >= target) { x = i + 1; break; }
+        }
+        *x_out = x; *e_out = e;
     }
 
-    // Lane-parallel pass over tile `tile`: returns for this lane the run start and the E value in
-    // effect at the first byte of its 128-byte slice, and the emitted bytes of the slice limited to
-    // positions < limit.
-    __device__ void lane_state(uint64_t tile, uint64_t limit, uint64_t &rs_in, uint64_t &e_in, uint32_t &emits) const
-    {
-        const unsigned l = threadIdx.x & 31;
-        uint64_t i0 = tile * RTILE + (uint64_t)l * (RTILE / 32), i1 = i0 + RTILE / 32;
-        if (i1 > n) i1 = n;
-        uint64_t last_rs = 0;
-        uint8_t prev = (i0 > 0 && i0 < n) ? in[i0 - 1] : 0;
-        for (uint64_t i = i0; i < i1; i++) {
-            uint8_t c = in[i];
-            if (i == 0 || c != prev || sm.is_start(i)) last_rs = i + 1;
-            prev = c;
-        }
-        uint64_t inc = warp_incl_max<uint64_t>(last_rs);
-        uint64_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (l == 0) ex = 0;
-        uint64_t carry = run_carry[tile];
-        rs_in = ex > carry ? ex : carry;
-        uint64_t rs = rs_in;
-        uint32_t tot = 0;
-        prev = (i0 > 0 && i0 < n) ? in[i0 - 1] : 0;
-        for (uint64_t i = i0; i < i1 && i < limit; i++) {
-            uint8_t c = in[i]; uint32_t em; bool last;
-            step(i, prev, c, rs, em, last);
-            tot += em; prev = c;
-        }
-        emits = tot;
-        uint32_t inc2 = warp_incl_sum<uint32_t>(tot);
-        e_in = e_base[tile] + (inc2 - tot);
-    }
-
-    // E(x): emitted bytes of all input bytes < x
+    // E(x): emitted bytes of all input bytes < x   (x is a stream boundary, hence a chunk boundary)
     __device__ uint64_t e_at(uint64_t x) const
     {
         uint64_t tile = x / RTILE;
         if (x == tile * RTILE) return e_base[tile];
-        uint64_t rs_in, e_in; uint32_t em;
-        lane_state(tile, x, rs_in, e_in, em);
-        uint64_t tot = e_in + em;                         // inclusive prefix of my lane
-        return __shfl_sync(0xffffffffu, tot, 31);
+        uint64_t xo, eo;
+        walk(x / RB, 0, x, x, &xo, &eo);
+        return eo;
     }
 
-    // first chunk end x (<= s1) with E(x) >= target, searching from tile `tile` (e_base[tile] < target)
+    // first chunk end x (<= s1) with E(x) >= target, given the last tile whose prefix is below the target
     __device__ void find(uint64_t tile, uint64_t target, uint64_t s1, uint64_t *x_out, uint64_t *e_out) const
     {
         const unsigned l = threadIdx.x & 31;
-        uint64_t rs_in, e_in; uint32_t em;
-        lane_state(tile, ~0ull, rs_in, e_in, em);
-        unsigned cross = __ballot_sync(0xffffffffu, e_in + em >= target);
-        // the crossing lane walks from its slice start to the chunk end that reaches the target; if the
-        // target is only met by a chunk that ends in a later tile, the last lane keeps walking
-        unsigned who = cross ? (unsigned)(__ffs(cross) - 1) : 31u;
-        uint64_t x = s1, e = 0;
-        if (l == who) {
-            uint64_t i = tile * RTILE + (uint64_t)l * (RTILE / 32);
-            uint64_t rs = rs_in; e = e_in;
-            uint8_t prev = (i > 0) ? in[i - 1] : 0;
-            for (; i < s1; i++) {
-                uint8_t c = in[i]; uint32_t emv; bool last;
-                step(i, prev, c, rs, emv, last);
-                e += emv; prev = c;
-                if (last && e >= target) { x = i + 1; break; }
-            }
+        // the crossing byte lies in the last window whose prefix is still below the target
+        uint64_t eb = e_base[tile];
+        uint32_t below = 0;
+#pragma unroll
+        for (int q = 0; q < RT / 32; q++) {
+            uint64_t wi = tile * RT + (uint64_t)l * (RT / 32) + q;
+            if (wi * RB < n && eb + win_e[wi] < target) below++;
         }
-        *x_out = __shfl_sync(0xffffffffu, x, who);
-        *e_out = __shfl_sync(0xffffffffu, e, who);
+        uint32_t total = warp_incl_sum<uint32_t>(below);
+        total = __shfl_sync(0xffffffffu, total, 31);
+        uint64_t win = tile * RT + (total ? total - 1 : 0);
+        uint64_t x = 0, e = 0;
+        if (l == 0) walk(win, target, s1, ~0ull, &x, &e);
+        *x_out = __shfl_sync(0xffffffffu, x, 0);
+        *e_out = __shfl_sync(0xffffffffu, e, 0);
     }
 };
 
@@ -305,7 +291,9 @@ __global__ void __launch_bounds__(32) k_rle_cut(CutWalker cw, uint32_t nmax, uin
     const unsigned l = threadIdx.x & 31;
     if (s >= cw.sm.n_streams) return;
     uint64_t s0 = cw.sm.soff[s], s1 = cw.sm.soff[s + 1];
-    uint64_t e0 = cw.e_at(s0), e1 = cw.e_at(s1);
+    uint64_t e0 = 0, e1 = 0;
+    if (l == 0) { e0 = cw.e_at(s0); e1 = cw.e_at(s1); }
+    e0 = __shfl_sync(0xffffffffu, e0, 0); e1 = __shfl_sync(0xffffffffu, e1, 0);
     uint64_t slot = e0 / nmax + s;     // upper bound on the blocks of earlier streams
     if (l == 0) prov_base[s] = slot;
     uint32_t nb = 0;
@@ -498,7 +486,9 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     StreamMap sm{d_soff, n_streams};
     S3G_LAUNCH(ctx, k_rle_runs, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry);
     S3G_LAUNCH(ctx, k_scan_agg<MaxU64>, 1, SCAN_THREADS, 0, run_carry, ntiles, (uint64_t *)nullptr);
-    S3G_LAUNCH(ctx, k_rle_emit_count, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base);
+    S3G_TRY(ctx->io_c.ensure((ntiles + 1) * RT * 2));
+    S3G_TRY(ctx->io_e.ensure((ntiles + 1) * RT));
+    S3G_LAUNCH(ctx, k_rle_emit_count, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base, ctx->io_c.as<uint16_t>(), ctx->io_e.as<uint8_t>());
     S3G_LAUNCH(ctx, k_scan_agg<SumU64b>, 1, SCAN_THREADS, 0, e_base, ntiles, d_sc + 16);
     // e_base[ntiles] = total, so E() can be evaluated at n
     S3G_CUDA(cudaMemcpyAsync(e_base + ntiles, d_sc + 16, 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -513,7 +503,7 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     uint64_t *prov_base = ctx->stream_tab.as<uint64_t>();
     uint64_t *first_block = prov_base + (n_streams + 2);
     uint32_t *bps = reinterpret_cast<uint32_t *>(first_block + (n_streams + 2));
-    CutWalker cw{d_in, n, sm, run_carry, e_base};
+    CutWalker cw{d_in, n, sm, e_base, ctx->io_c.as<uint16_t>(), ctx->io_e.as<uint8_t>()};
     S3G_LAUNCH(ctx, k_rle_cut, (unsigned)n_streams, 32, 0, cw, nmax, slot_cap, ctx->blk_prov.as<BlockInfo>(), bps, prov_base);
     S3G_LAUNCH(ctx, k_stream_block_scan, 1, 1, 0, bps, n_streams, first_block, d_sc + 17);
     S3G_LAUNCH(ctx, k_compact_blocks, (unsigned)n_streams, 64, 0, ctx->blk_prov.as<BlockInfo>(), prov_base, first_block,
