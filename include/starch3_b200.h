@@ -49,7 +49,7 @@ S3G_API int  s3g_set_stream(s3g_ctx *ctx, void *cuda_stream);
 S3G_API uint64_t s3g_launch_count(const s3g_ctx *ctx);
 /* Per-kernel timing with CUDA events on the launching stream.  s3g_profile(ctx, 1) starts
  * recording; s3g_profile_report synchronises and writes one line per kernel name
- * ("name\tlaunches\ttotal_ms\n") into buf, then clears the records. */
+ * ("name\tlaunches\ttotal_ms\talgorithmic_bytes\n") into buf, then clears the records. */
 S3G_API int  s3g_profile(s3g_ctx *ctx, int enable);
 S3G_API int  s3g_profile_report(s3g_ctx *ctx, char *buf, uint64_t cap);
 
@@ -69,7 +69,8 @@ typedef struct s3g_chrom {
 } s3g_chrom;
 
 typedef struct s3g_result {
-    uint8_t   *archive;        /* host: complete archive (ARCHIVE_FORMAT.md); owned by the library */
+    uint8_t   *archive;        /* host (pinned, owned by the context): complete archive (ARCHIVE_FORMAT.md);
+                                  valid until the next compress call on ctx or s3g_destroy */
     uint64_t   archive_size;
     uint64_t   streams_off;    /* where the concatenated bzip2 streams start inside archive */
     s3g_chrom *chroms;         /* host */

@@ -116,9 +116,13 @@ class Result:
         self.streams_size = cres.streams_size
         self.streams_off = cres.streams_off
         self.d_streams = cres.d_streams
-        self.archive = None
+        # zero-copy view of the context-owned archive buffer (valid until the next compress call);
+        # `.archive` materialises an independent bytes object on first use
+        self.archive_size = cres.archive_size if keep_archive else 0
+        self._archive_bytes = None
+        self.archive_view = None
         if keep_archive and cres.archive_size:
-            self.archive = C.string_at(cres.archive, cres.archive_size)
+            self.archive_view = memoryview((C.c_uint8 * cres.archive_size).from_address(C.addressof(cres.archive.contents))).cast("B")
         self.chroms = []
         for i in range(cres.n_chroms):
             c = cres.chroms[i]
@@ -126,6 +130,12 @@ class Result:
             if bed_bytes is not None:
                 d["name"] = bytes(bed_bytes[c.name_off:c.name_off + c.name_len])
             self.chroms.append(d)
+
+    @property
+    def archive(self):
+        if self._archive_bytes is None and self.archive_view is not None:
+            self._archive_bytes = bytes(self.archive_view)
+        return self._archive_bytes
 
     def stream(self, i):
         """bzip2 stream of chromosome i (bytes), from the archive."""
@@ -174,24 +184,27 @@ class Context:
         self._check(self._lib.s3g_profile(self._h, 1 if enable else 0))
 
     def profile_report(self):
-        """-> {kernel name: (launches, total_ms)} since profiling was enabled / last report."""
+        """-> {kernel name: (launches, total_ms, algorithmic_bytes)} since profiling was enabled / last report."""
         buf = C.create_string_buffer(1 << 16)
         self._check(self._lib.s3g_profile_report(self._h, buf, len(buf)))
         out = {}
         for ln in buf.value.decode().splitlines():
-            name, cnt, ms = ln.split("\t")
-            out[name] = (int(cnt), float(ms))
+            name, cnt, ms, by = ln.split("\t")
+            out[name] = (int(cnt), float(ms), float(by))
         return out
 
     # ---- whole path ----
-    def compress_bed(self, bed, block_size_100k=9, note=None):
+    def compress_bed(self, bed, block_size_100k=9, note=None, lazy=False):
         a = _u8(bed)
         r = CResult()
         rc = self._lib.s3g_compress_bed(self._h, _p(a), len(a), block_size_100k,
                                         note.encode() if isinstance(note, str) else note, C.byref(r))
         try:
             self._check(rc)
-            return Result(r, a)
+            res = Result(r, a)
+            if not lazy:
+                res.archive          # copy out now: the view dies with the next call
+            return res
         finally:
             self._lib.s3g_result_free(C.byref(r))
 
@@ -202,7 +215,9 @@ class Context:
                                                1 if want_archive else 0, C.byref(r))
         try:
             self._check(rc)
-            return Result(r, bed_bytes, keep_archive=want_archive)
+            res = Result(r, bed_bytes, keep_archive=want_archive)
+            res.archive
+            return res
         finally:
             self._lib.s3g_result_free(C.byref(r))
 

@@ -27,6 +27,8 @@ int check_launch(const char *what)
 
 int prof_begin(Ctx *ctx, const char *name)
 {
+    double bytes = ctx->prof_next_bytes;
+    ctx->prof_next_bytes = 0;
     if (!ctx->prof) return -1;
     while (ctx->prof_used + 2 > ctx->prof_pool.size()) {
         cudaEvent_t e;
@@ -34,7 +36,7 @@ int prof_begin(Ctx *ctx, const char *name)
         ctx->prof_pool.push_back(e);
     }
     Ctx::ProfRec r;
-    r.name = name; r.e0 = ctx->prof_pool[ctx->prof_used++]; r.e1 = ctx->prof_pool[ctx->prof_used++];
+    r.name = name; r.e0 = ctx->prof_pool[ctx->prof_used++]; r.e1 = ctx->prof_pool[ctx->prof_used++]; r.bytes = bytes;
     cudaEventRecord(r.e0, ctx->stream);
     ctx->prof_recs.push_back(r);
     return (int)ctx->prof_recs.size() - 1;
@@ -233,8 +235,16 @@ static int compress_bed_impl(Ctx *ctx, const uint8_t *d_bed, uint64_t n, int lev
     std::string hdr = build_header(names.data(), name_off, ctx->h_chroms, level, note);
     uint64_t streams_off = 4 + hdr.size() + 1;
     res->archive_size = streams_off + total_bytes;
-    res->archive = (uint8_t *)malloc(res->archive_size);
-    if (!res->archive) { set_error("out of host memory"); return S3G_E_NOMEM; }
+    // the archive is assembled in context-owned pinned memory: the device-to-host copy of the
+    // streams lands directly in its final place
+    if (res->archive_size > ctx->h_archive_cap) {
+        if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
+        ctx->h_archive = nullptr; ctx->h_archive_cap = 0;
+        size_t want = res->archive_size + res->archive_size / 8 + 4096;
+        if (cudaMallocHost(&ctx->h_archive, want) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+        ctx->h_archive_cap = want;
+    }
+    res->archive = ctx->h_archive;
     static const uint8_t magic[4] = {0xca, 0x5c, 0xad, 0x1a};      // hpp:907-910
     memcpy(res->archive, magic, 4);
     memcpy(res->archive + 4, hdr.data(), hdr.size());
@@ -297,6 +307,7 @@ void s3g_destroy(s3g_ctx *ctx)
     size_t k; DevBuf *const *bl = all_bufs(ctx, &k);
     for (size_t i = 0; i < k; i++) bl[i]->release();
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
@@ -325,19 +336,19 @@ int s3g_profile_report(s3g_ctx *ctx, char *buf, uint64_t cap)
 {
     if (!ctx || !buf || cap == 0) { set_error("null argument"); return S3G_E_PARAM; }
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<std::string> names; std::vector<double> ms; std::vector<uint64_t> cnt;
+    std::vector<std::string> names; std::vector<double> ms, by; std::vector<uint64_t> cnt;
     for (const Ctx::ProfRec &r : ctx->prof_recs) {
         float t = 0;
         if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
         size_t k = 0;
         for (; k < names.size(); k++) if (names[k] == r.name) break;
-        if (k == names.size()) { names.push_back(r.name); ms.push_back(0); cnt.push_back(0); }
-        ms[k] += t; cnt[k]++;
+        if (k == names.size()) { names.push_back(r.name); ms.push_back(0); by.push_back(0); cnt.push_back(0); }
+        ms[k] += t; by[k] += r.bytes; cnt[k]++;
     }
     std::string o;
     for (size_t k = 0; k < names.size(); k++) {
         char line[256];
-        snprintf(line, sizeof line, "%s\t%llu\t%.6f\n", names[k].c_str(), (unsigned long long)cnt[k], ms[k]);
+        snprintf(line, sizeof line, "%s\t%llu\t%.6f\t%.0f\n", names[k].c_str(), (unsigned long long)cnt[k], ms[k], by[k]);
         o += line;
     }
     ctx->prof_recs.clear(); ctx->prof_used = 0;
@@ -375,7 +386,7 @@ int s3g_read_streams(s3g_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n)
 void s3g_result_free(s3g_result *res)
 {
     if (!res) return;
-    free(res->archive); free(res->chroms);
+    free(res->chroms);                  // the archive buffer belongs to the context
     memset(res, 0, sizeof *res);
 }
 

@@ -612,6 +612,9 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 16, ctx->stream));
     S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
     dim3 grid(NT, (unsigned)nb);
+    double N = 0;                       // rotations in this batch
+    for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
+    const double HS = (double)nb * NT * NBINS * 4 * 2;
     static bool attr_done = false;
     if (!attr_done) {
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
@@ -623,13 +626,21 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     uint32_t *no_out = nullptr;
     uint64_t *no_save = nullptr;
     // ---- init: order by the first k symbols ----
+    S3G_BYTES(ctx, 9 * N);
     S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, no_act, P.kv1);
+    S3G_BYTES(ctx, HS);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
+    S3G_BYTES(ctx, 16 * N);
     S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, 0, 0, 0u, P.cnt_n, P.kv1, P.kv0, no_act);
+    S3G_BYTES(ctx, 8 * N);
     S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, no_act, no_save);
+    S3G_BYTES(ctx, HS);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
+    S3G_BYTES(ctx, 16 * N);
     S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
+    S3G_BYTES(ctx, 8 * N);
     S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv1, no_act);
+    S3G_BYTES(ctx, 16 * N);
     S3G_LAUNCH(ctx, k_bound_apply<true>, grid, BT, 0, P, 0u, P.kv1, no_out, no_act, P.act, P.g_act);
     S3G_TRY(check_launch("bwt init"));
     // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
@@ -645,17 +656,28 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaMemsetAsync(act_next, 0, nb * 4, ctx->stream));
         S3G_CUDA(cudaMemsetAsync(g_next, 0, 8, ctx->stream));
         uint32_t *newrank = reinterpret_cast<uint32_t *>(P.kv0);
+        const double M = (double)*h_act;          // unsorted rotations entering this round
+        S3G_BYTES(ctx, 16 * N);
         S3G_LAUNCH(ctx, k_hist<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, act_cur, P.kv1);
-        S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_n, P.cnt_m, act_cur);
+        S3G_BYTES(ctx, HS);
+    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_n, P.cnt_m, act_cur);
+        S3G_BYTES(ctx, 8 * N + 8 * M);
         S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, 0, 1, round, P.cnt_n, P.kv1, P.kv0, act_cur);
+        S3G_BYTES(ctx, 8 * M);
         S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, act_cur, no_save);
-        S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_m, no_out, act_cur);
+        S3G_BYTES(ctx, HS);
+    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_m, no_out, act_cur);
+        S3G_BYTES(ctx, 16 * M);
         S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
+        S3G_BYTES(ctx, 8 * M);
         S3G_LAUNCH(ctx, k_bound_agg<false>, grid, ST, 0, P, round, P.kv1, act_cur);
+        S3G_BYTES(ctx, 20 * M);
         S3G_LAUNCH(ctx, k_bound_apply<false>, grid, BT, 0, P, round, P.kv1, newrank, act_cur, act_next, g_next);
+        S3G_BYTES(ctx, 16 * M);
         S3G_LAUNCH(ctx, k_rank_update, grid, ST, 0, P, round, P.kv1, newrank, act_cur);
         S3G_TRY(check_launch("bwt round"));
     }
+    S3G_BYTES(ctx, 10 * N);
     S3G_LAUNCH(ctx, k_bwt_finish, grid, ST, 0, P, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>());
     S3G_LAUNCH(ctx, k_fallback_exact, (unsigned)nb, 32, 0, P, ctx->blocks.as<BlockInfo>() + b0);
     return check_launch("bwt finish");

@@ -102,9 +102,12 @@ struct Ctx {
     std::vector<s3g_chrom> h_chroms;
     uint64_t pool_words = 0;               // words appended to the pool so far
     uint64_t last_streams_size = 0;
+    uint8_t *h_archive = nullptr;          // pinned; holds the archive of the last compress call
+    size_t h_archive_cap = 0;
     // per-kernel profiling (off by default)
     bool prof = false;
-    struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; double bytes; };
+    double prof_next_bytes = 0;
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
     size_t prof_used = 0;
@@ -113,6 +116,9 @@ struct Ctx {
 // Every kernel launch goes through this macro: it counts launches and, when
 // per-kernel profiling is on (s3g_profile), brackets the launch with CUDA events
 // on the launching stream.
+// S3G_BYTES(ctx, b) before a launch records its algorithmic bytes for the
+// roofline figure of bench.py.
+#define S3G_BYTES(ctx, b) ((ctx)->prof_next_bytes = (double)(b))
 #define S3G_LAUNCH(ctx, kernel, grid, block, smem, ...)                     \
     do {                                                                    \
         int pi_ = s3g::prof_begin((ctx), #kernel);                          \

@@ -323,6 +323,9 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
         attr_done = true;
     }
     // alphabets of <= 32 symbols take the register-list kernel, larger ones the warp-cooperative one
+    double N = 0;
+    for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
+    S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
     S3G_LAUNCH(ctx, k_mtf_small, (unsigned)nb, MS, small_smem, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
                ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
     S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
@@ -667,6 +670,9 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
         S3G_CUDA(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
         attr_done = true;
     }
+    double N = 0;
+    for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
+    S3G_BYTES(ctx, 6 * 2 * 0.67 * N + 0.25 * N);      // 4 selection passes + size + emit over uint16 symbols, bits out
     S3G_LAUNCH(ctx, k_huff, (unsigned)nb, HT, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
                ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
                d_sel_out, d_len_out, with_block_header);

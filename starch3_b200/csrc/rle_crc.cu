@@ -484,10 +484,12 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     uint64_t *d_sc = ctx->scalars.as<uint64_t>();
     uint64_t *run_carry = ctx->rle_carry.as<uint64_t>(), *e_base = ctx->rle_ebase.as<uint64_t>();
     StreamMap sm{d_soff, n_streams};
+    S3G_BYTES(ctx, n);
     S3G_LAUNCH(ctx, k_rle_runs, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry);
     S3G_LAUNCH(ctx, k_scan_agg<MaxU64>, 1, SCAN_THREADS, 0, run_carry, ntiles, (uint64_t *)nullptr);
     S3G_TRY(ctx->io_c.ensure((ntiles + 1) * RT * 2));
     S3G_TRY(ctx->io_e.ensure((ntiles + 1) * RT));
+    S3G_BYTES(ctx, n + n * 3 / 16);
     S3G_LAUNCH(ctx, k_rle_emit_count, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base, ctx->io_c.as<uint16_t>(), ctx->io_e.as<uint8_t>());
     S3G_LAUNCH(ctx, k_scan_agg<SumU64b>, 1, SCAN_THREADS, 0, e_base, ntiles, d_sc + 16);
     // e_base[ntiles] = total, so E() can be evaluated at n
@@ -519,10 +521,16 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     S3G_TRY(ctx->seq_map.ensure(nb * 256));
     S3G_CUDA(cudaMemsetAsync(ctx->in_use.p, 0, nb * 256, ctx->stream));
     BlockInfo *blocks = ctx->blocks.as<BlockInfo>();
+    S3G_BYTES(ctx, n + e_total);
     S3G_LAUNCH(ctx, k_rle_write, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base, blocks, nb,
                ctx->blk_bytes.as<uint8_t>(), ctx->in_use.as<uint8_t>());
+    S3G_BYTES(ctx, n);
     S3G_LAUNCH(ctx, k_block_crc, (unsigned)nb, CRC_T, 0, d_in, blocks);
     S3G_LAUNCH(ctx, k_block_maps, (unsigned)nb, 256, 0, ctx->in_use.as<uint8_t>(), blocks, ctx->seq_map.as<uint8_t>());
+    // host mirror of the block table (sizes drive batching and the byte accounting of the later stages)
+    ctx->h_blocks.resize(nb);
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_blocks.data(), blocks, nb * sizeof(BlockInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     return check_launch("rle write");
 }
 

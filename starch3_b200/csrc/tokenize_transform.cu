@@ -287,6 +287,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     uint64_t *d_sc = ctx->scalars.as<uint64_t>();
     S3G_CUDA(cudaMemsetAsync(d_sc, 0, 64 * 8, ctx->stream));
     uint64_t *tile_cnt = ctx->tile_cnt.as<uint64_t>();
+    S3G_BYTES(ctx, n);
     S3G_LAUNCH(ctx, k_count_newlines, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt);
     S3G_LAUNCH(ctx, k_scan_agg<SumU64>, 1, SCAN_THREADS, 0, tile_cnt, ntiles, d_sc + 0);
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -295,6 +296,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     out->n_lines = n_lines;
     S3G_TRY(ctx->line_start.ensure((n_lines + 1) * 8));
     uint64_t *line_start = ctx->line_start.as<uint64_t>();
+    S3G_BYTES(ctx, n + 8 * n_lines);
     S3G_LAUNCH(ctx, k_line_starts, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt, line_start);
     if (n_lines == 0) {
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -309,6 +311,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     uint32_t *rem_off = ctx->rem_off.as<uint32_t>();
     uint8_t *flags = ctx->flags.as<uint8_t>();
     unsigned lgrid = (unsigned)((n_lines + 255) / 256);
+    S3G_BYTES(ctx, n + 29 * n_lines);
     S3G_LAUNCH(ctx, k_parse_lines, lgrid, 256, 0, d_bed, line_start, n_lines, start, stop, rem_off, flags,
                (unsigned long long *)(d_sc + 1));
     // last line start tells how many unterminated tail bytes are dropped (hpp:181-190)
@@ -355,6 +358,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_LAUNCH(ctx, k_chrom_table, (unsigned)((out->n_chroms + 127) / 128), 128, 0, d_bed, line_start,
                ctx->line_tf_off.as<uint64_t>(), ctx->chrom_first.as<uint64_t>(), ctx->stat_b.as<Stat3>(), d_stat_total,
                out->n_chroms, n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>());
+    S3G_BYTES(ctx, n + out->tf_len + 37 * n_lines);
     S3G_LAUNCH(ctx, k_write_tf, lgrid, 256, 0, d_bed, lv, ctx->line_tf_off.as<uint64_t>(), n_lines, ctx->tf.as<uint8_t>());
     return check_launch("transform write");
 }
