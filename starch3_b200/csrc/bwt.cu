@@ -8,8 +8,8 @@
 // algorithm produces the order is free (bz/blocksort.c:1058-1061).
 //
 // Algorithm (per block, all blocks of a batch in the same launches):
-//   init   rank every rotation by its first k symbols, k = max{k : A^k <= 2^20},
-//          A = symbols in use, via a 2-pass LSD radix sort on a 20-bit key.
+//   init   rank every rotation by its first k symbols, k = max{k : A^k <= 2^30},
+//          A = symbols in use, via a 3-pass LSD radix sort on a 30-bit key.
 //   round  given the order by the first h symbols (SA, grouped; RK[i] = SA
 //          position of the first member of i's group, bit 31 = group is a
 //          singleton), obtain the order by 2h symbols with the Manber-Myers
@@ -82,7 +82,7 @@ __device__ __forceinline__ bool get_item(const BwtP &P, uint32_t lb, uint32_t p,
 // depth (symbols already sorted) of block lb in doubling round `round`
 __device__ __forceinline__ uint32_t depth_of(const BwtP &P, uint32_t lb, uint32_t round)
 {
-    return round >= 25 ? 0x7fffffffu : P.init_k[lb] << round;      // init_k <= 20
+    return round >= 25 ? 0x7fffffffu : P.init_k[lb] << round;      // init_k <= 30
 }
 // phase 0 = initial sort (every block), phase 1 = doubling round (unsorted blocks whose depth is below n)
 __device__ __forceinline__ bool block_live(const BwtP &P, uint32_t lb, int phase, uint32_t round, const uint32_t *act_cur)
@@ -137,11 +137,11 @@ __global__ void __launch_bounds__(NBINS) k_hist_scan(BwtP P, int phase, uint32_t
     // thread d owns digit d: column d of the [tile][digit] matrix
     uint32_t *col = P.hist + (uint64_t)lb * NT * NBINS + threadIdx.x;
     uint32_t s = 0;
-#pragma unroll 4
+#pragma unroll 16
     for (uint32_t t = 0; t < ntiles; t++) s += col[(uint64_t)t * NBINS];
     uint32_t tot;
     uint32_t ex = block_excl_sum<uint32_t>(s, sm, &tot);
-#pragma unroll 4
+#pragma unroll 16
     for (uint32_t t = 0; t < ntiles; t++) { uint32_t v = col[(uint64_t)t * NBINS]; col[(uint64_t)t * NBINS] = ex; ex += v; }
     if (threadIdx.x == 0 && total_out) total_out[lb] = tot;
 }
@@ -421,7 +421,7 @@ __global__ void k_bwt_setup(BwtP P, uint32_t nb)
     uint32_t k = 1;
     if (a >= 2) {
         uint64_t pw = a;
-        while (pw * a <= (1u << 20)) { pw *= a; k++; }
+        while (pw * a <= (1u << 30)) { pw *= a; k++; }       // 30-bit initial key: three 10-bit passes
     }
     P.cnt_n[lb] = n; P.init_k[lb] = k; P.init_a[lb] = a;
     P.act[lb] = 0; P.act[nb + lb] = 0;
@@ -639,9 +639,15 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_BYTES(ctx, 16 * N);
     S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
     S3G_BYTES(ctx, 8 * N);
-    S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv1, no_act);
+    S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 20, 0, 0u, P.cnt_n, P.kv1, no_act, no_save);
+    S3G_BYTES(ctx, HS);
+    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
     S3G_BYTES(ctx, 16 * N);
-    S3G_LAUNCH(ctx, k_bound_apply<true>, grid, BT, 0, P, 0u, P.kv1, no_out, no_act, P.act, P.g_act);
+    S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 20, 0, 0u, P.cnt_n, P.kv1, P.kv0, no_act);
+    S3G_BYTES(ctx, 8 * N);
+    S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv0, no_act);
+    S3G_BYTES(ctx, 16 * N);
+    S3G_LAUNCH(ctx, k_bound_apply<true>, grid, BT, 0, P, 0u, P.kv0, no_out, no_act, P.act, P.g_act);
     S3G_TRY(check_launch("bwt init"));
     // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
     unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
