@@ -43,46 +43,55 @@ struct BwtP {
     uint32_t *agg;             // [nb][NT][2] tile aggregates of the boundary scans
     unsigned long long *g_act; // [2] batch totals
     uint32_t *init_k;          // [nb] symbols in the initial key
+    uint32_t *init_k32;        // [nb] symbols in the 32-bit per-position key the group finisher compares (<= init_k)
     uint32_t *init_a;          // [nb] alphabet size
+    uint32_t *left;            // [nb] rotations the group finisher left unsorted (blocks that need doubling rounds)
 };
 
 enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2, MODE_KVX = 3 };   // KVX: key/value pairs saved by the histogram pass, ~0 = not taking part
 
-// item p of block lb for the given source mode; returns false if the item does not take part
+// Records are 64 bits.  Initial sort: (40-bit symbol key << 20) | rotation start.  Doubling rounds:
+// (rank << 32) | rotation start.  A radix pass takes its 10-bit digit at bit `rshift` of the record.
+constexpr int KEY_BITS = 40;             // initial key: four 10-bit passes
+constexpr int VAL_BITS = 20;             // rotation starts are < 2^20 (BLK_STRIDE)
+
+// record p of block lb for the given source mode; returns false if the item does not take part
 template <int MODE>
 __device__ __forceinline__ bool get_item(const BwtP &P, uint32_t lb, uint32_t p, uint32_t n, uint32_t cnt, uint32_t h,
-                                         const uint64_t *kv_in, uint32_t &key, uint32_t &val)
+                                         const uint64_t *kv_in, uint64_t &rec)
 {
     if (p >= cnt) return false;
     if (MODE == MODE_INIT) {
         const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
         const uint8_t *sq = P.seq + (uint64_t)lb * 256;
-        uint32_t k = P.init_k[lb], a = P.init_a[lb];
-        uint32_t key_ = 0, q = p;
+        uint32_t k = P.init_k[lb], k32 = P.init_k32[lb], a = P.init_a[lb];
+        uint64_t key_ = 0;
+        uint32_t q = p;
         for (uint32_t t = 0; t < k; t++) {
             key_ = key_ * a + sq[b[q]];
             q++; if (q == n) q = 0;
+            // the key of the first k32 symbols stays behind in rk: the group finisher reads deeper symbols from it
+            if (t + 1 == k32) P.rk[(uint64_t)lb * BLK_STRIDE + p] = (uint32_t)key_;
         }
-        key = key_; val = p;
+        rec = (key_ << VAL_BITS) | p;
         return true;
     } else if (MODE == MODE_MM) {
         uint32_t s = P.sa[(uint64_t)lb * BLK_STRIDE + p];
         uint32_t j = s >= h ? s - h : s + n - h;          // h < n is guaranteed by the caller
         uint32_t r = P.rk[(uint64_t)lb * BLK_STRIDE + j];
         if (r & FINAL) return false;
-        key = r; val = j;
+        rec = ((uint64_t)r << 32) | j;
         return true;
     } else {
-        uint64_t kv = kv_in[(uint64_t)lb * BLK_STRIDE + p];
-        key = (uint32_t)(kv >> 32); val = (uint32_t)kv;
-        return MODE == MODE_KVX ? kv != ~0ull : true;
+        rec = kv_in[(uint64_t)lb * BLK_STRIDE + p];
+        return MODE == MODE_KVX ? rec != ~0ull : true;
     }
 }
 
 // depth (symbols already sorted) of block lb in doubling round `round`
 __device__ __forceinline__ uint32_t depth_of(const BwtP &P, uint32_t lb, uint32_t round)
 {
-    return round >= 25 ? 0x7fffffffu : P.init_k[lb] << round;      // init_k <= 30
+    return round >= 25 ? 0x7fffffffu : P.init_k[lb] << round;      // init_k <= 40
 }
 // phase 0 = initial sort (every block), phase 1 = doubling round (unsorted blocks whose depth is below n)
 __device__ __forceinline__ bool block_live(const BwtP &P, uint32_t lb, int phase, uint32_t round, const uint32_t *act_cur)
@@ -93,7 +102,7 @@ __device__ __forceinline__ bool block_live(const BwtP &P, uint32_t lb, int phase
 
 // ---- radix pass: per-tile digit histogram ------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(ST) k_hist(BwtP P, int shift, int phase, uint32_t round, const uint32_t *cnt_arr,
+__global__ void __launch_bounds__(ST) k_hist(BwtP P, int rshift, int phase, uint32_t round, const uint32_t *cnt_arr,
                                              const uint64_t *kv_in, const uint32_t *act_cur, uint64_t *kv_save)
 {
     __shared__ uint32_t sh[NBINS];
@@ -109,11 +118,11 @@ __global__ void __launch_bounds__(ST) k_hist(BwtP P, int shift, int phase, uint3
     uint32_t dg[SI];
 #pragma unroll
     for (int r = 0; r < SI; r++) {
-        uint32_t key, val;
-        bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, key, val);
-        dg[r] = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
-        // the gathered pairs are kept so that the scatter of this pass reads them back coalesced
-        if (kv_save && base + r * 32 < cnt) kv_save[(uint64_t)lb * BLK_STRIDE + base + r * 32] = ok ? (((uint64_t)key << 32) | val) : ~0ull;
+        uint64_t rec = 0;
+        bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, rec);
+        dg[r] = ok ? ((uint32_t)(rec >> rshift) & (NBINS - 1)) : 0xffffffffu;
+        // the gathered records are kept so that the scatter of this pass reads them back coalesced
+        if (kv_save && base + r * 32 < cnt) kv_save[(uint64_t)lb * BLK_STRIDE + base + r * 32] = ok ? rec : ~0ull;
     }
 #pragma unroll
     for (int r = 0; r < SI; r++) {
@@ -159,7 +168,7 @@ struct ScatterSmem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int shift, int phase, uint32_t round, const uint32_t *cnt_arr,
+__global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int rshift, int phase, uint32_t round, const uint32_t *cnt_arr,
                                                 const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *act_cur)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -181,17 +190,16 @@ __global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int shift, int phase,
     // all loads first (independent, 16 in flight per thread); the ranking below is warp-synchronous
 #pragma unroll
     for (int r = 0; r < SI; r++) {
-        uint32_t key = 0, val = 0;
-        bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, key, val);
-        kv[r] = ((uint64_t)key << 32) | val;
+        uint64_t rec = 0;
+        bool ok = get_item<MODE>(P, lb, base + r * 32, n, cnt, h, kv_in, rec);
+        kv[r] = rec;
         if (ok) okmask |= 1u << r;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < SI; r++) {
         bool ok = (okmask >> r) & 1u;
-        uint32_t key = (uint32_t)(kv[r] >> 32);
-        uint32_t d = ok ? ((key >> shift) & (NBINS - 1)) : 0xffffffffu;
+        uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (NBINS - 1)) : 0xffffffffu;
         unsigned peers = __match_any_sync(0xffffffffu, d);
         unsigned lt = peers & ((1u << l) - 1);
         uint16_t b = ok ? mycnt[d] : (uint16_t)0;
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int shift, int phase,
 #pragma unroll
     for (int r = 0; r < SI; r++) {
         if (okmask & (1u << r)) {
-            uint32_t d = ((uint32_t)(kv[r] >> 32) >> shift) & (NBINS - 1);
+            uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
             S.stage[S.tbase[d] + mycnt[d] + rnk[r]] = kv[r];
         }
     }
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int shift, int phase,
     uint64_t *out = kv_out + (uint64_t)lb * BLK_STRIDE;
     for (uint32_t i = threadIdx.x; i < tile_total; i += ST) {
         uint64_t it = S.stage[i];
-        uint32_t d = ((uint32_t)(it >> 32) >> shift) & (NBINS - 1);
+        uint32_t d = (uint32_t)(it >> rshift) & (NBINS - 1);
         out[S.gbase[d] + (i - S.tbase[d])] = it;
     }
 }
@@ -330,6 +338,308 @@ __global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const 
     }
 }
 
+// ---- group finisher ---------------------------------------------------------------
+// After the initial sort every group (rotations with equal first k symbols) is contiguous in SA
+// order.  bzip2's own mainSort finishes such buckets with direct string comparisons
+// (bz/blocksort.c:347-469, :621-717) because real blocks have short common prefixes; the same holds
+// here, so one kernel finishes every group of up to FX rotations inside shared memory instead of
+// paying global radix passes per doubling round:
+//   level 0   key = the 32-bit key (k32 symbols) saved for position val+k, i.e. the NEXT symbols in one
+//             4-byte gather; rank inside the group by counting smaller/equal keys; unique keys are final
+//   level >=1 the few still-tied rotations move to a small list and repeat k32 symbols further on
+// Groups larger than FX and ties that survive FLEVELS levels (long repeats, periodic blocks) are
+// written out unsorted with a NONHEAD flag on every member but the first; only blocks that have
+// such leftovers go through the prefix-doubling rounds below.
+// A tile owns the groups that START inside it and reads past its end to the end of the last one;
+// whether a group is sorted here depends only on its size (<= FX), so the tile a group spills into
+// can tell without communication that the owner took care of it.
+constexpr int FTH = 512;                         // threads per finisher tile
+constexpr int FT = 2048;                         // SA positions owned by a tile
+constexpr int FX = 2048;                         // largest group sorted in shared memory (FX <= FT)
+constexpr int FWA = FT + FX + 64;                // window entries
+constexpr int FEPT = (FWA + FTH - 1) / FTH;      // consecutive entries per thread in the grouping phase
+constexpr int FNT = (BLK_STRIDE + FT - 1) / FT;  // finisher tiles per block slot
+constexpr int TCAP = 1024;                       // tied rotations a tile carries to deeper levels
+constexpr int FLEVELS = 12;                      // levels of k symbols before a tie is left to the doubling rounds
+constexpr uint32_t NONHEAD = 0x80000000u;        // SA flag: same (unsorted) group as the previous position
+constexpr uint32_t VMASK = 0x000fffffu;          // rotation start (< 2^20)
+
+struct FinSmem {
+    uint32_t key[FWA];        // low 32 bits of the initial key while grouping, level-0 key afterwards
+    uint32_t idx[FWA];        // rotation start (low 20 bits); the key's high bits above them while grouping
+    uint32_t gb[FWA];         // group start | group end << 16 (window-relative); start 0xffff = continuation from an earlier tile
+    uint32_t out[FWA];        // final SA value per window position (scratch for group ends while grouping)
+    uint16_t list[FWA];       // entries that take part in level 0, in window order
+    uint32_t t_idx[TCAP], t_key[TCAP];
+    uint16_t t_cs[TCAP], t_rank[TCAP];
+    uint32_t scan[33];
+    uint32_t first_head, c, ntied, lo, hi, handled;
+};
+
+__device__ __forceinline__ uint32_t deeper_key(const uint32_t *k30, uint32_t pos, uint32_t off, uint32_t n)
+{
+    uint32_t p = pos + off;
+    if (p >= n) { p -= n; if (p >= n) p %= n; }
+    return k30[p];
+}
+
+__global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
+                                                         uint8_t *lcol)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FinSmem &S = *reinterpret_cast<FinSmem *>(smem_raw);
+    const uint32_t lb = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const uint32_t n = P.cnt_n[lb];
+    const uint32_t base = tile * FT;
+    if (base >= n) return;
+    const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
+    const uint32_t avail = n - base;
+    // ---- 1. load the tile, then extend to the end of the group that crosses its end ----
+    uint32_t W = min(avail, (uint32_t)FT);
+    // record = key << 20 | start: key[] gets key bits 0..31, idx[] gets start | key bits 32.. << 20
+    for (uint32_t e = tid; e < W; e += FTH) { uint64_t x = a[base + e]; S.key[e] = (uint32_t)(x >> VAL_BITS); S.idx[e] = (uint32_t)x & VMASK | (uint32_t)(x >> 52) << VAL_BITS; }
+    if (tid == 0) {
+        S.first_head = (base == 0) || (a[base - 1] >> VAL_BITS) != (a[base] >> VAL_BITS);
+        S.c = 0xffffffffu; S.ntied = 0; S.lo = 0; S.hi = 0; S.handled = 0;
+    }
+    __syncthreads();
+    if (avail > FT) {
+        const uint64_t lastkey = a[base + FT - 1] >> VAL_BITS;
+        while (W < FWA && W < avail) {
+            uint32_t e = W + tid;
+            bool found = false;
+            if (e < FWA && e < avail) {
+                uint64_t x = a[base + e];
+                S.key[e] = (uint32_t)(x >> VAL_BITS); S.idx[e] = (uint32_t)x & VMASK | (uint32_t)(x >> 52) << VAL_BITS;
+                found = (x >> VAL_BITS) != lastkey;
+            }
+            W = min(min(W + (uint32_t)FTH, (uint32_t)FWA), avail);
+            if (__syncthreads_or(found)) break;
+        }
+    }
+    const bool open_end = W < avail;              // the group holding entry W-1 continues past the window
+    // ---- 2. group starts (max-scan of head positions), group ends, classification ----
+    const uint32_t e0 = tid * FEPT;
+    uint32_t hm = 0, lh = 0;
+#pragma unroll
+    for (int k = 0; k < FEPT; k++) {
+        uint32_t e = e0 + k;
+        if (e < W) {
+            bool head = e == 0 ? S.first_head != 0 : (S.key[e] != S.key[e - 1] || (S.idx[e] ^ S.idx[e - 1]) >> VAL_BITS);
+            if (head) { hm |= 1u << k; lh = e + 1; }
+        }
+    }
+    if (hm) atomicMin(&S.c, e0 + (uint32_t)__ffs(hm) - 1);
+    uint32_t tot;
+    uint32_t cur = block_excl_max<uint32_t>(lh, S.scan, &tot);    // (entry + 1) of the last head before my range
+    uint32_t gs_[FEPT];
+#pragma unroll
+    for (int k = 0; k < FEPT; k++) {
+        uint32_t e = e0 + k;
+        gs_[k] = 0xffffu;
+        if (e < W) {
+            if (hm & (1u << k)) cur = e + 1;
+            if (cur) {
+                gs_[k] = cur - 1;
+                bool last = e + 1 == W || S.key[e + 1] != S.key[e] || (S.idx[e + 1] ^ S.idx[e]) >> VAL_BITS;
+                if (last) S.out[cur - 1] = e + 1;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t c = min(S.c, W);               // entries [0, c) continue a group that started in an earlier tile
+    if (tid == 0 && c > 0) {
+        // the owner sorted that group iff its size is <= FX; it ends at base + c
+        bool handled = false;
+        if (c < FT && !(c == W && open_end)) {
+            uint32_t end = base + c;
+            handled = end <= FX || (a[end - FX - 1] >> VAL_BITS) != (a[base] >> VAL_BITS);
+        }
+        S.handled = handled;
+    }
+    uint32_t myuns = 0;
+    uint32_t ge_[FEPT];
+#pragma unroll
+    for (int k = 0; k < FEPT; k++) {
+        ge_[k] = 0;
+        if (gs_[k] != 0xffffu) {
+            ge_[k] = S.out[gs_[k]];
+            uint32_t size = ge_[k] - gs_[k];
+            bool sortable = gs_[k] < FT && size <= FX && !(open_end && ge_[k] == W);
+            if (sortable && size > 1) myuns++;
+        }
+    }
+    uint32_t nuns;
+    uint32_t lpos = block_excl_sum<uint32_t>(myuns, S.scan, &nuns);   // (syncs: every read of the group ends in S.out is done)
+    uint32_t leftover = 0;
+    const uint32_t tile_w = min(W, (uint32_t)FT);
+    const uint32_t handled = S.handled;
+#pragma unroll
+    for (int k = 0; k < FEPT; k++) {
+        uint32_t e = e0 + k;
+        if (e >= W) continue;
+        uint32_t gs = gs_[k], ge = ge_[k];
+        S.gb[e] = gs | (ge << 16);
+        S.idx[e] &= VMASK;                        // the key's high bits are no longer needed
+        if (gs == 0xffffu) {
+            // continuation of a group from an earlier tile: written here only when its owner could not sort it
+            if (!handled && e < tile_w) { S.out[e] = S.idx[e] | NONHEAD; leftover++; }
+            continue;
+        }
+        if (gs >= FT) continue;
+        uint32_t size = ge - gs;
+        bool sortable = size <= FX && !(open_end && ge == W);
+        if (!sortable) {
+            if (e < tile_w) { S.out[e] = S.idx[e] | (e > gs ? NONHEAD : 0u); leftover++; }
+        } else if (size == 1) {
+            S.out[e] = S.idx[e];
+        } else {
+            S.list[lpos++] = (uint16_t)e;
+        }
+        if (e + 1 == tile_w) S.hi = sortable ? ge : tile_w;     // the group holding the tile's last entry decides the written range
+    }
+    if (tid == 0) {
+        if (c >= tile_w) { S.lo = handled ? tile_w : 0; S.hi = tile_w; }   // no group starts in this tile
+        else S.lo = handled ? c : 0;
+    }
+    __syncthreads();
+    // ---- 3. level 0: the next k symbols of every unsorted rotation ----
+    for (uint32_t u = tid; u < nuns; u += FTH) { uint32_t e = S.list[u]; S.key[e] = deeper_key(k30, S.idx[e], k0, n); }
+    __syncthreads();
+    for (uint32_t u = tid; u < nuns; u += FTH) {
+        uint32_t e = S.list[u];
+        uint32_t g = S.gb[e], gs = g & 0xffffu, ge = g >> 16;
+        uint32_t my = S.key[e], lt = 0, eq = 0, eqb = 0;
+        for (uint32_t k = gs; k < ge; k++) {
+            uint32_t x = S.key[k];
+            lt += x < my;
+            uint32_t is = x == my;
+            eq += is;
+            eqb += is & (uint32_t)(k < e);
+        }
+        if (eq == 1) S.out[gs + lt] = S.idx[e];
+        else {
+            uint32_t slot = atomicAdd(&S.ntied, 1u);
+            if (slot < TCAP) { S.t_idx[slot] = S.idx[e]; S.t_cs[slot] = (uint16_t)(gs + lt); S.t_rank[slot] = (uint16_t)eqb; }
+            else { S.out[gs + lt + eqb] = S.idx[e] | (eqb ? NONHEAD : 0u); leftover++; }
+        }
+    }
+    __syncthreads();
+    // ---- 4. deeper levels on the tied list ----
+    const uint32_t nt_all = S.ntied;
+    const uint32_t nt = min(nt_all, (uint32_t)TCAP);
+    constexpr int TPT = TCAP / FTH;
+    if (nt_all <= TCAP) {
+        for (uint32_t level = 1; level < FLEVELS && nt; level++) {
+#pragma unroll
+            for (int r = 0; r < TPT; r++) {
+                uint32_t u = tid + r * FTH;
+                if (u < nt && S.t_cs[u] != 0xffffu) S.t_key[u] = deeper_key(k30, S.t_idx[u], k0 + level * k32, n);
+            }
+            __syncthreads();
+            uint32_t lt_[TPT], eq_[TPT], eqb_[TPT];
+#pragma unroll
+            for (int r = 0; r < TPT; r++) {
+                uint32_t u = tid + r * FTH;
+                lt_[r] = eq_[r] = eqb_[r] = 0;
+                if (u < nt && S.t_cs[u] != 0xffffu) {
+                    uint32_t cs = S.t_cs[u], my = S.t_key[u];
+                    for (uint32_t v = 0; v < nt; v++) {
+                        if (S.t_cs[v] != cs) continue;
+                        uint32_t x = S.t_key[v];
+                        lt_[r] += x < my;
+                        uint32_t is = x == my;
+                        eq_[r] += is;
+                        eqb_[r] += is & (uint32_t)(v < u);
+                    }
+                }
+            }
+            __syncthreads();
+            bool live = false;
+#pragma unroll
+            for (int r = 0; r < TPT; r++) {
+                uint32_t u = tid + r * FTH;
+                if (u < nt && S.t_cs[u] != 0xffffu) {
+                    uint32_t cs = S.t_cs[u];
+                    if (eq_[r] == 1) { S.out[cs + lt_[r]] = S.t_idx[u]; S.t_cs[u] = 0xffffu; }
+                    else { S.t_cs[u] = (uint16_t)(cs + lt_[r]); S.t_rank[u] = (uint16_t)eqb_[r]; live = true; }
+                }
+            }
+            if (!__syncthreads_or(live)) break;
+        }
+    }
+    // whatever is still tied goes out as an unsorted group
+#pragma unroll
+    for (int r = 0; r < TPT; r++) {
+        uint32_t u = tid + r * FTH;
+        if (u < nt && S.t_cs[u] != 0xffffu) {
+            uint32_t rk_ = S.t_rank[u];
+            S.out[(uint32_t)S.t_cs[u] + rk_] = S.t_idx[u] | (rk_ ? NONHEAD : 0u);
+            leftover++;
+        }
+    }
+    __syncthreads();
+    // ---- 5. write SA, the BWT last column (bz/compress.c:166-167) and origPtr (bz/blocksort.c:1083-1086) ----
+    const uint32_t lo = S.lo, hi = S.hi;
+    uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *sq = P.seq + (uint64_t)lb * 256;
+    uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
+    for (uint32_t pos = lo + tid; pos < hi; pos += FTH) {
+        uint32_t v = S.out[pos], s = v & VMASK;
+        sa[base + pos] = v;
+        L[base + pos] = sq[b[s ? s - 1 : n - 1]];
+        if (s == 0) blocks[lb].orig_ptr = (int32_t)(base + pos);
+    }
+    uint32_t ltot;
+    block_excl_sum<uint32_t>(leftover, S.scan, &ltot);
+    if (tid == 0 && ltot) { atomicAdd(&P.left[lb], ltot); atomicAdd(g_left, (unsigned long long)ltot); }
+}
+
+// Blocks with leftovers: ranks (SA position of the group head, FINAL on singletons) from the NONHEAD
+// flags, flags cleared, so that the doubling rounds can take over at depth k.
+__global__ void __launch_bounds__(1024) k_rank_rebuild(BwtP P)
+{
+    __shared__ uint32_t sm[33];
+    const uint32_t lb = blockIdx.x, tid = threadIdx.x;
+    const uint32_t left = P.left[lb];
+    if (tid == 0) P.act[lb] = left;
+    if (!left) return;
+    const uint32_t n = P.cnt_n[lb];
+    uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    uint32_t carry = 0;
+    for (uint32_t chunk = 0; chunk < n; chunk += 1024 * 4) {
+        uint32_t p0 = chunk + tid * 4;
+        uint32_t v[5];
+        uint32_t lh = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            uint32_t p = p0 + k;
+            v[k] = p < n ? sa[p] : 0u;                    // past the end counts as a head
+            if (k < 4 && p < n && !(v[k] & NONHEAD)) lh = p + 1;
+        }
+        uint32_t tot;
+        uint32_t hp = max(block_excl_max<uint32_t>(lh, sm, &tot), carry);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t p = p0 + k;
+            if (p < n) {
+                bool head = !(v[k] & NONHEAD);
+                if (head) hp = p + 1;
+                bool single = head && !(v[k + 1] & NONHEAD);
+                uint32_t val = v[k] & VMASK;
+                rk[val] = (hp - 1) | (single ? FINAL : 0u);
+                sa[p] = val;
+            }
+        }
+        carry = max(carry, tot);
+        __syncthreads();
+    }
+}
+
 constexpr int BT = 512;                 // boundary kernels: 512 threads x 8 items per tile (same 4096-item tiles)
 constexpr int BI = STILE / BT;
 
@@ -418,19 +728,20 @@ __global__ void k_bwt_setup(BwtP P, uint32_t nb)
     if (lb >= nb) return;
     uint32_t n = P.blocks[lb].nblock, a = P.blocks[lb].n_in_use;
     if (a < 1) a = 1;
-    uint32_t k = 1;
+    uint32_t k = 1, k32 = 1;
     if (a >= 2) {
         uint64_t pw = a;
-        while (pw * a <= (1u << 30)) { pw *= a; k++; }       // 30-bit initial key: three 10-bit passes
+        while (pw * a <= (1ull << KEY_BITS)) { pw *= a; k++; if (pw <= 0xffffffffull) k32 = k; }
     }
-    P.cnt_n[lb] = n; P.init_k[lb] = k; P.init_a[lb] = a;
-    P.act[lb] = 0; P.act[nb + lb] = 0;
+    P.cnt_n[lb] = n; P.init_k[lb] = k; P.init_k32[lb] = k32; P.init_a[lb] = a;
+    P.act[lb] = 0; P.act[nb + lb] = 0; P.left[lb] = 0;
 }
 
 // origPtr, tie flag and the BWT last column (bz/compress.c:166-167 reads block[ptr[i]-1])
 __global__ void __launch_bounds__(ST) k_bwt_finish(BwtP P, BlockInfo *blocks, uint8_t *lcol)
 {
     uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    if (!P.left[lb]) return;            // finished by k_group_finish
     uint32_t n = P.cnt_n[lb];
     if ((uint64_t)tile * STILE >= n) return;
     const uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
@@ -592,7 +903,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->kv0.ensure(slots * 8));
     S3G_TRY(ctx->kv1.ensure(slots * 8));
     S3G_TRY(ctx->hist.ensure((size_t)nb * NBINS * NT * 4));
-    S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (6 * 4 + NT * 2 * 4) + 64));
+    S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (8 * 4 + NT * 2 * 4) + 64));
     S3G_TRY(ctx->lcol.ensure(slots));
     BwtP P;
     P.blk = ctx->blk_bytes.as<uint8_t>() + b0 * (uint64_t)BLK_STRIDE;
@@ -608,6 +919,8 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.act = misc; misc += 2 * nb;
     P.init_k = misc; misc += nb;
     P.init_a = misc; misc += nb;
+    P.left = misc; misc += nb;
+    P.init_k32 = misc; misc += nb;
     P.agg = misc;
     S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 16, ctx->stream));
     S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
@@ -619,38 +932,45 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     if (!attr_done) {
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_group_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
         attr_done = true;
     }
     const uint32_t *no_act = nullptr;
     const uint64_t *no_kv = nullptr;
     uint32_t *no_out = nullptr;
     uint64_t *no_save = nullptr;
-    // ---- init: order by the first k symbols ----
-    S3G_BYTES(ctx, 9 * N);
-    S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, 0, 0, 0u, P.cnt_n, no_kv, no_act, P.kv1);
+    // ---- init: order by the first k symbols (40-bit key, four 10-bit passes; records end up in kv1) ----
+    S3G_BYTES(ctx, 13 * N);
+    S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, VAL_BITS, 0, 0u, P.cnt_n, no_kv, no_act, P.kv1);
     S3G_BYTES(ctx, HS);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
     S3G_BYTES(ctx, 16 * N);
-    S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, 0, 0, 0u, P.cnt_n, P.kv1, P.kv0, no_act);
-    S3G_BYTES(ctx, 8 * N);
-    S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 0, 0u, P.cnt_n, P.kv0, no_act, no_save);
-    S3G_BYTES(ctx, HS);
-    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
-    S3G_BYTES(ctx, 16 * N);
-    S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 0, 0u, P.cnt_n, P.kv0, P.kv1, no_act);
-    S3G_BYTES(ctx, 8 * N);
-    S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 20, 0, 0u, P.cnt_n, P.kv1, no_act, no_save);
-    S3G_BYTES(ctx, HS);
-    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
-    S3G_BYTES(ctx, 16 * N);
-    S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 20, 0, 0u, P.cnt_n, P.kv1, P.kv0, no_act);
-    S3G_BYTES(ctx, 8 * N);
-    S3G_LAUNCH(ctx, k_bound_agg<true>, grid, ST, 0, P, 0u, P.kv0, no_act);
-    S3G_BYTES(ctx, 16 * N);
-    S3G_LAUNCH(ctx, k_bound_apply<true>, grid, BT, 0, P, 0u, P.kv0, no_out, no_act, P.act, P.g_act);
+    S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, VAL_BITS, 0, 0u, P.cnt_n, P.kv1, P.kv0, no_act);
+    {
+        uint64_t *src = P.kv0, *dst = P.kv1;
+        for (int pass = 1; pass < KEY_BITS / 10; pass++) {
+            int rshift = VAL_BITS + 10 * pass;
+            S3G_BYTES(ctx, 8 * N);
+            S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, rshift, 0, 0u, P.cnt_n, src, no_act, no_save);
+            S3G_BYTES(ctx, HS);
+            S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
+            S3G_BYTES(ctx, 16 * N);
+            S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, rshift, 0, 0u, P.cnt_n, src, dst, no_act);
+            std::swap(src, dst);
+        }
+    }
+    // ---- every group of up to FX rotations is finished in shared memory; SA, last column, origPtr ----
+    S3G_BYTES(ctx, 18 * N);
+    S3G_LAUNCH(ctx, k_group_finish, dim3(FNT, (unsigned)nb), FTH, sizeof(FinSmem), P, P.kv1, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
+               ctx->lcol.as<uint8_t>());
     S3G_TRY(check_launch("bwt init"));
-    // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
     unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
+    S3G_CUDA(cudaMemcpyAsync(h_act, P.g_act, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (getenv("S3G_DEBUG")) fprintf(stderr, "[s3g] bwt: %llu of %.0f rotations left to the doubling rounds\n", *h_act, N);
+    if (*h_act == 0) return S3G_OK;
+    S3G_LAUNCH(ctx, k_rank_rebuild, (unsigned)nb, 1024, 0, P);
+    // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
     for (uint32_t round = 0; round < 32; round++) {
         uint32_t *act_cur = P.act + (size_t)(round & 1) * nb;
         uint32_t *act_next = P.act + (size_t)((round + 1) & 1) * nb;
@@ -664,17 +984,17 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         uint32_t *newrank = reinterpret_cast<uint32_t *>(P.kv0);
         const double M = (double)*h_act;          // unsorted rotations entering this round
         S3G_BYTES(ctx, 16 * N);
-        S3G_LAUNCH(ctx, k_hist<MODE_MM>, grid, ST, 0, P, 0, 1, round, P.cnt_n, no_kv, act_cur, P.kv1);
+        S3G_LAUNCH(ctx, k_hist<MODE_MM>, grid, ST, 0, P, 32, 1, round, P.cnt_n, no_kv, act_cur, P.kv1);
         S3G_BYTES(ctx, HS);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_n, P.cnt_m, act_cur);
         S3G_BYTES(ctx, 8 * N + 8 * M);
-        S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, 0, 1, round, P.cnt_n, P.kv1, P.kv0, act_cur);
+        S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, 32, 1, round, P.cnt_n, P.kv1, P.kv0, act_cur);
         S3G_BYTES(ctx, 8 * M);
-        S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 10, 1, round, P.cnt_m, P.kv0, act_cur, no_save);
+        S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, 42, 1, round, P.cnt_m, P.kv0, act_cur, no_save);
         S3G_BYTES(ctx, HS);
     S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 1, round, P.cnt_m, no_out, act_cur);
         S3G_BYTES(ctx, 16 * M);
-        S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 10, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
+        S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, 42, 1, round, P.cnt_m, P.kv0, P.kv1, act_cur);
         S3G_BYTES(ctx, 8 * M);
         S3G_LAUNCH(ctx, k_bound_agg<false>, grid, ST, 0, P, round, P.kv1, act_cur);
         S3G_BYTES(ctx, 20 * M);
