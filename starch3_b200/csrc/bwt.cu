@@ -241,6 +241,204 @@ __global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int rshift, int phase
     }
 }
 
+// ---- initial sort, onesweep style -------------------------------------------------
+// k_keys      builds the 64-bit record of every rotation (rolling mixed-radix key over consecutive
+//             positions), the 32-bit per-position key for the group finisher (rk), and the digit
+//             histograms of ALL four passes of every block in one read of the block bytes.
+// k_digit_scan turns each histogram into the digit base offsets of its pass.
+// k_sweep     one radix pass in ONE kernel: the tile ranks its records, publishes its per-digit
+//             counts, and obtains its global offsets by a decoupled look-back over the earlier tiles
+//             of the same block (status word = generation | flag | count, so nothing is zeroed
+//             between passes).  Tiles are handed out by an atomic ticket, block index fastest:
+//             a tile's predecessors always hold earlier tickets (forward progress), and with many
+//             blocks in a batch the predecessor has normally published its inclusive prefix already.
+constexpr int KT = 8;                        // tiles per CTA in k_keys
+constexpr int NPASS = KEY_BITS / 10;
+constexpr uint32_t ST_INCL = 1u << 23, ST_AGG = 1u << 22, ST_VAL = 0x000fffffu;
+
+struct KeysSmem {
+    uint64_t stage[STILE + STILE / 16];      // records, skewed so that 16-consecutive-per-thread writes are conflict-free
+    uint32_t stage32[STILE + STILE / 16];
+    uint32_t hist[NPASS][NBINS];
+    uint8_t sym[STILE + 64];
+    uint8_t seq[256];
+};
+
+__global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t *ghist)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KeysSmem &S = *reinterpret_cast<KeysSmem *>(smem_raw);
+    const uint32_t lb = blockIdx.y, tid = threadIdx.x;
+    const uint32_t n = P.cnt_n[lb];
+    const uint32_t t0 = blockIdx.x * KT;
+    if ((uint64_t)t0 * STILE >= n) return;
+    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t k = P.init_k[lb], k32 = P.init_k32[lb], a = P.init_a[lb];
+    for (int i = tid; i < NPASS * NBINS; i += ST) (&S.hist[0][0])[i] = 0;
+    S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
+    uint64_t pw = 1; uint32_t pw32 = 1;                      // a^(k-1), a^(k32-1)
+    for (uint32_t i = 1; i < k; i++) pw *= a;
+    for (uint32_t i = 1; i < k32; i++) pw32 *= a;
+    uint64_t *out = rec_out + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    for (uint32_t t = t0; t < t0 + KT && (uint64_t)t * STILE < n; t++) {
+        const uint32_t base = t * STILE, cntT = min((uint32_t)STILE, n - base);
+        __syncthreads();
+        for (uint32_t i = tid; i < cntT + k; i += ST) {
+            uint32_t q = base + i;
+            if (q >= n) { q -= n; if (q >= n) q %= n; }
+            S.sym[i] = S.seq[b[q]];
+        }
+        __syncthreads();
+        const uint32_t p0 = tid * SI;
+        if (p0 < cntT) {
+            uint64_t key = 0; uint32_t key32 = 0;
+            for (uint32_t j = 0; j < k; j++) { key = key * a + S.sym[p0 + j]; if (j + 1 == k32) key32 = (uint32_t)key; }
+#pragma unroll
+            for (int r = 0; r < SI; r++) {
+                uint32_t p = p0 + r;
+                if (p < cntT) {
+                    uint64_t rec = (key << VAL_BITS) | (base + p);
+                    S.stage[p + (p >> 4)] = rec;
+                    S.stage32[p + (p >> 4)] = key32;
+#pragma unroll
+                    for (int ps = 0; ps < NPASS; ps++) atomicAdd(&S.hist[ps][(uint32_t)(rec >> (VAL_BITS + 10 * ps)) & (NBINS - 1)], 1u);
+                    uint32_t so = S.sym[p];
+                    key = (key - so * pw) * a + S.sym[p + k];
+                    key32 = (key32 - so * pw32) * a + S.sym[p + k32];
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t p = tid; p < cntT; p += ST) { out[base + p] = S.stage[p + (p >> 4)]; rk[base + p] = S.stage32[p + (p >> 4)]; }
+    }
+    __syncthreads();
+    uint32_t *gh = ghist + (uint64_t)lb * NPASS * NBINS;
+    for (int i = tid; i < NPASS * NBINS; i += ST) { uint32_t v = (&S.hist[0][0])[i]; if (v) atomicAdd(&gh[i], v); }
+}
+
+__global__ void __launch_bounds__(NBINS) k_digit_scan(uint32_t *ghist)
+{
+    __shared__ uint32_t sm[33];
+    uint32_t *g = ghist + ((uint64_t)blockIdx.y * NPASS + blockIdx.x) * NBINS;
+    uint32_t v = g[threadIdx.x], tot;
+    g[threadIdx.x] = block_excl_sum<uint32_t>(v, sm, &tot);
+}
+
+__global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *dbase_all,
+                                                 int pass, uint32_t *ticket_ctr, uint32_t nb, uint32_t gen)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    if (threadIdx.x == 0) S.scan[0] = atomicAdd(ticket_ctr, 1u);
+    for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) S.wcnt[i] = 0;
+    __syncthreads();
+    const uint32_t ticket = S.scan[0];
+    const uint32_t tile = ticket / nb, lb = ticket - tile * nb;
+    const uint32_t cnt = P.cnt_n[lb];
+    if ((uint64_t)tile * STILE >= cnt) return;
+    uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    uint32_t base = tile * STILE + w * (SI * 32) + l;
+    uint16_t *mycnt = S.wcnt + w * NBINS;
+    const uint64_t *in = kv_in + (uint64_t)lb * BLK_STRIDE;
+    uint64_t kv[SI];
+    uint16_t rnk[SI];
+    uint32_t okmask = 0;
+#pragma unroll
+    for (int r = 0; r < SI; r++) {
+        uint32_t p = base + r * 32;
+        kv[r] = 0;
+        if (p < cnt) { kv[r] = in[p]; okmask |= 1u << r; }
+    }
+#pragma unroll
+    for (int r = 0; r < SI; r++) {
+        bool ok = (okmask >> r) & 1u;
+        uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (NBINS - 1)) : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned lt = peers & ((1u << l) - 1);
+        uint16_t bb = ok ? mycnt[d] : (uint16_t)0;
+        __syncwarp();
+        if (ok && lt == 0) mycnt[d] = (uint16_t)(bb + __popc(peers));
+        __syncwarp();
+        rnk[r] = (uint16_t)(bb + __popc(lt));
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, tile total
+    constexpr int DPT = NBINS / ST;
+    uint32_t tot4[DPT];
+    uint32_t mysum = 0;
+#pragma unroll
+    for (int q = 0; q < DPT; q++) {
+        int d = threadIdx.x * DPT + q;
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < ST / 32; ww++) { uint32_t c = S.wcnt[ww * NBINS + d]; S.wcnt[ww * NBINS + d] = (uint16_t)run; run += c; }
+        tot4[q] = run; mysum += run;
+    }
+    // publish the tile's counts, look back for the exclusive prefix over earlier tiles, publish the inclusive prefix
+    static_assert(DPT == 4, "status words are moved as uint4");
+    const uint32_t gtag = gen << 24;
+    volatile uint4 *status = reinterpret_cast<volatile uint4 *>(P.hist + (uint64_t)lb * NT * NBINS) + threadIdx.x;   // + tile * (NBINS / 4)
+    uint32_t ex4[DPT] = {0, 0, 0, 0};
+    if (tile > 0) {
+        {
+            uint4 v = make_uint4(gtag | ST_AGG | tot4[0], gtag | ST_AGG | tot4[1], gtag | ST_AGG | tot4[2], gtag | ST_AGG | tot4[3]);
+            volatile uint4 *dst = status + (uint64_t)tile * (NBINS / 4);
+            dst->x = v.x; dst->y = v.y; dst->z = v.z; dst->w = v.w;
+        }
+        uint32_t done = 0;                 // bit q: digit q has met an inclusive prefix
+        uint32_t spins = 0;
+        for (int32_t t = (int32_t)tile - 1; t >= 0 && done != 0xfu;) {
+            const volatile uint4 *src = status + (uint64_t)t * (NBINS / 4);
+            uint32_t x[DPT] = {src->x, src->y, src->z, src->w};
+            bool ready = true;
+#pragma unroll
+            for (int q = 0; q < DPT; q++) if (!(done & (1u << q)) && (x[q] >> 24) != gen) ready = false;
+            if (!ready) {
+                if (++spins > (1u << 24)) __trap();          // a predecessor never published: fail loudly instead of hanging
+                __nanosleep(20);
+                continue;
+            }
+#pragma unroll
+            for (int q = 0; q < DPT; q++) {
+                if (done & (1u << q)) continue;
+                ex4[q] += x[q] & ST_VAL;
+                if (x[q] & ST_INCL) done |= 1u << q;
+            }
+            t--;
+        }
+    }
+    {
+        volatile uint4 *dst = status + (uint64_t)tile * (NBINS / 4);
+        dst->x = gtag | ST_INCL | (ex4[0] + tot4[0]); dst->y = gtag | ST_INCL | (ex4[1] + tot4[1]);
+        dst->z = gtag | ST_INCL | (ex4[2] + tot4[2]); dst->w = gtag | ST_INCL | (ex4[3] + tot4[3]);
+    }
+    const uint32_t *dbase = dbase_all + ((uint64_t)lb * NPASS + pass) * NBINS;
+    uint32_t tile_total;
+    uint32_t ex = block_excl_sum<uint32_t>(mysum, S.scan, &tile_total);
+#pragma unroll
+    for (int q = 0; q < DPT; q++) {
+        int d = threadIdx.x * DPT + q;
+        S.tbase[d] = ex; ex += tot4[q];
+        S.gbase[d] = dbase[d] + ex4[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SI; r++) {
+        if (okmask & (1u << r)) {
+            uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
+            S.stage[S.tbase[d] + mycnt[d] + rnk[r]] = kv[r];
+        }
+    }
+    __syncthreads();
+    uint64_t *out = kv_out + (uint64_t)lb * BLK_STRIDE;
+    for (uint32_t i = threadIdx.x; i < tile_total; i += ST) {
+        uint64_t it = S.stage[i];
+        uint32_t d = (uint32_t)(it >> rshift) & (NBINS - 1);
+        out[S.gbase[d] + (i - S.tbase[d])] = it;
+    }
+}
+
 // ---- group boundaries and new ranks -------------------------------------------
 // Sorted items p of block lb: key_p (group = SA position of the group start; in INIT
 // mode the symbol key), val_p.  Thread t of a tile owns SI consecutive items.
@@ -933,35 +1131,41 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_group_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KeysSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         attr_done = true;
     }
     const uint32_t *no_act = nullptr;
     const uint64_t *no_kv = nullptr;
     uint32_t *no_out = nullptr;
     uint64_t *no_save = nullptr;
-    // ---- init: order by the first k symbols (40-bit key, four 10-bit passes; records end up in kv1) ----
+    // ---- init: order by the first k symbols (40-bit key, four 10-bit onesweep passes; records end up in kv0) ----
+    S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * NPASS * NBINS * 4 + 64));
+    uint32_t *ghist = ctx->bwt_ghist.as<uint32_t>();
+    uint32_t *tickets = ghist + (size_t)nb * NPASS * NBINS;
+    S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * NPASS * NBINS * 4 + 64, ctx->stream));
+    // look-back status words carry a generation tag; the table is cleared only when it is new, was used
+    // by the doubling rounds (as a histogram table) or the tag wraps
+    if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS > 255) {
+        S3G_CUDA(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->stream));
+        ctx->sweep_cap = ctx->hist.cap; ctx->sweep_gen = 0;
+    }
     S3G_BYTES(ctx, 13 * N);
-    S3G_LAUNCH(ctx, k_hist<MODE_INIT>, grid, ST, 0, P, VAL_BITS, 0, 0u, P.cnt_n, no_kv, no_act, P.kv1);
-    S3G_BYTES(ctx, HS);
-    S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
-    S3G_BYTES(ctx, 16 * N);
-    S3G_LAUNCH(ctx, k_scatter<MODE_KVX>, grid, ST, sizeof(ScatterSmem), P, VAL_BITS, 0, 0u, P.cnt_n, P.kv1, P.kv0, no_act);
+    S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, P.kv0, ghist);
+    S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), NBINS, 0, ghist);
     {
         uint64_t *src = P.kv0, *dst = P.kv1;
-        for (int pass = 1; pass < KEY_BITS / 10; pass++) {
-            int rshift = VAL_BITS + 10 * pass;
-            S3G_BYTES(ctx, 8 * N);
-            S3G_LAUNCH(ctx, k_hist<MODE_KV>, grid, ST, 0, P, rshift, 0, 0u, P.cnt_n, src, no_act, no_save);
-            S3G_BYTES(ctx, HS);
-            S3G_LAUNCH(ctx, k_hist_scan, (unsigned)nb, NBINS, 0, P, 0, 0u, P.cnt_n, no_out, no_act);
+        for (int pass = 0; pass < NPASS; pass++) {
             S3G_BYTES(ctx, 16 * N);
-            S3G_LAUNCH(ctx, k_scatter<MODE_KV>, grid, ST, sizeof(ScatterSmem), P, rshift, 0, 0u, P.cnt_n, src, dst, no_act);
+            S3G_LAUNCH(ctx, k_sweep, NT * (unsigned)nb, ST, sizeof(ScatterSmem), P, VAL_BITS + 10 * pass, src, dst, ghist, pass, tickets + pass,
+                       (uint32_t)nb, ++ctx->sweep_gen);
             std::swap(src, dst);
         }
+        static_assert(NPASS % 2 == 0, "an even number of passes leaves the sorted records in kv0");
     }
     // ---- every group of up to FX rotations is finished in shared memory; SA, last column, origPtr ----
     S3G_BYTES(ctx, 18 * N);
-    S3G_LAUNCH(ctx, k_group_finish, dim3(FNT, (unsigned)nb), FTH, sizeof(FinSmem), P, P.kv1, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
+    S3G_LAUNCH(ctx, k_group_finish, dim3(FNT, (unsigned)nb), FTH, sizeof(FinSmem), P, P.kv0, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
                ctx->lcol.as<uint8_t>());
     S3G_TRY(check_launch("bwt init"));
     unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
@@ -970,6 +1174,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     if (getenv("S3G_DEBUG")) fprintf(stderr, "[s3g] bwt: %llu of %.0f rotations left to the doubling rounds\n", *h_act, N);
     if (*h_act == 0) return S3G_OK;
     S3G_LAUNCH(ctx, k_rank_rebuild, (unsigned)nb, 1024, 0, P);
+    ctx->sweep_cap = 0;                  // the rounds below reuse the status table as per-tile histograms
     // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
     for (uint32_t round = 0; round < 32; round++) {
         uint32_t *act_cur = P.act + (size_t)(round & 1) * nb;
