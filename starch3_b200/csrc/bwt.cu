@@ -260,7 +260,7 @@ struct KeysSmem {
     uint64_t stage[STILE + STILE / 16];      // records, skewed so that 16-consecutive-per-thread writes are conflict-free
     uint32_t stage32[STILE + STILE / 16];
     uint32_t hist[NPASS][NBINS];
-    uint8_t sym[STILE + 64];
+    __align__(16) uint8_t sym[STILE + 64];
     uint8_t seq[256];
 };
 
@@ -284,10 +284,30 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t
     for (uint32_t t = t0; t < t0 + KT && (uint64_t)t * STILE < n; t++) {
         const uint32_t base = t * STILE, cntT = min((uint32_t)STILE, n - base);
         __syncthreads();
-        for (uint32_t i = tid; i < cntT + k; i += ST) {
-            uint32_t q = base + i;
-            if (q >= n) { q -= n; if (q >= n) q %= n; }
-            S.sym[i] = S.seq[b[q]];
+        {
+            // 16 block bytes per thread in one vector load, mapped to symbol ranks (unseqToSeq, bz/compress.c:106-115)
+            const uint32_t i0 = tid * 16;
+            if (base + i0 + 16 <= n) {
+                uint4 v = *reinterpret_cast<const uint4 *>(b + base + i0);
+                uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    wv[j] = (uint32_t)S.seq[wv[j] & 255] | (uint32_t)S.seq[(wv[j] >> 8) & 255] << 8 | (uint32_t)S.seq[(wv[j] >> 16) & 255] << 16 |
+                            (uint32_t)S.seq[wv[j] >> 24] << 24;
+                *reinterpret_cast<uint4 *>(S.sym + i0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            } else {
+                for (uint32_t i = i0; i < i0 + 16 && i < cntT + k; i++) {
+                    uint32_t q = base + i;
+                    if (q >= n) { q -= n; if (q >= n) q %= n; }
+                    S.sym[i] = S.seq[b[q]];
+                }
+            }
+            // the k symbols past the tile (cyclic)
+            for (uint32_t i = STILE + tid; i < cntT + k; i += ST) {
+                uint32_t q = base + i;
+                if (q >= n) { q -= n; if (q >= n) q %= n; }
+                S.sym[i] = S.seq[b[q]];
+            }
         }
         __syncthreads();
         const uint32_t p0 = tid * SI;
@@ -331,7 +351,13 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
     if (threadIdx.x == 0) S.scan[0] = atomicAdd(ticket_ctr, 1u);
-    for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) S.wcnt[i] = 0;
+    // Intra-warp matching through shared memory instead of match.any (measured on B200: match.any costs
+    // ~8 cycles per DISTINCT value in the warp, 170-250 cycles per call on these digits; an atomicOr of
+    // the lane bit into a per-warp, per-digit mask word plus a read-back gives the same peer mask for
+    // ~20).  The mask table aliases the staging buffer, which is not live until ranking is over.
+    static_assert(sizeof(S.stage) >= (ST / 32) * NBINS * 4, "mask table must fit in the staging buffer");
+    uint32_t *Mall = reinterpret_cast<uint32_t *>(S.stage);
+    for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) { S.wcnt[i] = 0; Mall[i] = 0; }
     __syncthreads();
     const uint32_t ticket = S.scan[0];
     const uint32_t tile = ticket / nb, lb = ticket - tile * nb;
@@ -340,6 +366,7 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
     uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
     uint32_t base = tile * STILE + w * (SI * 32) + l;
     uint16_t *mycnt = S.wcnt + w * NBINS;
+    uint32_t *M = Mall + w * NBINS;
     const uint64_t *in = kv_in + (uint64_t)lb * BLK_STRIDE;
     uint64_t kv[SI];
     uint16_t rnk[SI];
@@ -350,17 +377,44 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
         kv[r] = 0;
         if (p < cnt) { kv[r] = in[p]; okmask |= 1u << r; }
     }
+    const uint32_t lbit = 1u << l, ltmask = lbit - 1;
+    // match.any is cheap when the warp holds few distinct digits (the upper passes of text: the records
+    // arrive sorted by the lower digits and neighbours share their context), the mask table when it holds
+    // many.  One probe per warp and tile: equal neighbours among the first 32 records.
+    bool use_match;
+    {
+        uint32_t d0 = (okmask & 1u) ? ((uint32_t)(kv[0] >> rshift) & (NBINS - 1)) : 0x10000u + l;
+        uint32_t dn = __shfl_down_sync(0xffffffffu, d0, 1);
+        use_match = __popc(__ballot_sync(0xffffffffu, l < 31 && d0 == dn)) >= 16;
+    }
+    if (use_match) {
 #pragma unroll
-    for (int r = 0; r < SI; r++) {
-        bool ok = (okmask >> r) & 1u;
-        uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (NBINS - 1)) : 0xffffffffu;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        unsigned lt = peers & ((1u << l) - 1);
-        uint16_t bb = ok ? mycnt[d] : (uint16_t)0;
-        __syncwarp();
-        if (ok && lt == 0) mycnt[d] = (uint16_t)(bb + __popc(peers));
-        __syncwarp();
-        rnk[r] = (uint16_t)(bb + __popc(lt));
+        for (int r = 0; r < SI; r++) {
+            bool ok = (okmask >> r) & 1u;
+            uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (NBINS - 1)) : 0xffffffffu;
+            unsigned peers = __match_any_sync(0xffffffffu, d);
+            unsigned lt = peers & ltmask;
+            uint32_t bb = ok ? mycnt[d] : 0u;
+            __syncwarp();
+            if (ok && lt == 0) mycnt[d] = (uint16_t)(bb + __popc(peers));
+            __syncwarp();
+            rnk[r] = (uint16_t)(bb + __popc(lt));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < SI; r++) {
+            bool ok = (okmask >> r) & 1u;
+            uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
+            if (ok) atomicOr(&M[d], lbit);
+            __syncwarp();
+            uint32_t peers = ok ? M[d] : 0u;
+            uint32_t bb = ok ? mycnt[d] : 0u;
+            __syncwarp();
+            uint32_t lt = peers & ltmask;
+            if (ok && lt == 0) { mycnt[d] = (uint16_t)(bb + __popc(peers)); M[d] = 0; }
+            __syncwarp();
+            rnk[r] = (uint16_t)(bb + __popc(lt));
+        }
     }
     __syncthreads();
     // per digit: exclusive prefix over warps, tile total
@@ -572,6 +626,7 @@ struct FinSmem {
     uint16_t t_cs[TCAP], t_rank[TCAP];
     uint32_t scan[33];
     uint32_t first_head, c, ntied, lo, hi, handled;
+    uint8_t seq[256];         // unseqToSeq of the block
 };
 
 __device__ __forceinline__ uint32_t deeper_key(const uint32_t *k30, uint32_t pos, uint32_t off, uint32_t n)
@@ -598,6 +653,7 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
     uint32_t W = min(avail, (uint32_t)FT);
     // record = key << 20 | start: key[] gets key bits 0..31, idx[] gets start | key bits 32.. << 20
     for (uint32_t e = tid; e < W; e += FTH) { uint64_t x = a[base + e]; S.key[e] = (uint32_t)(x >> VAL_BITS); S.idx[e] = (uint32_t)x & VMASK | (uint32_t)(x >> 52) << VAL_BITS; }
+    if (tid < 256) S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
     if (tid == 0) {
         S.first_head = (base == 0) || (a[base - 1] >> VAL_BITS) != (a[base] >> VAL_BITS);
         S.c = 0xffffffffu; S.ntied = 0; S.lo = 0; S.hi = 0; S.handled = 0;
@@ -703,22 +759,38 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
         else S.lo = handled ? c : 0;
     }
     __syncthreads();
-    // ---- 3. level 0: the next k symbols of every unsorted rotation ----
-    for (uint32_t u = tid; u < nuns; u += FTH) { uint32_t e = S.list[u]; S.key[e] = deeper_key(k30, S.idx[e], k0, n); }
+    // ---- 3. level 0: the next k32 symbols of every unsorted rotation ----
+    {
+        constexpr int GU = 4;                       // gathers in flight per thread
+        for (uint32_t u0 = tid; u0 < nuns; u0 += FTH * GU) {
+            uint32_t e_[GU], kk[GU];
+#pragma unroll
+            for (int g = 0; g < GU; g++) {
+                uint32_t u = u0 + g * FTH;
+                e_[g] = u < nuns ? S.list[u] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int g = 0; g < GU; g++) kk[g] = e_[g] != 0xffffffffu ? deeper_key(k30, S.idx[e_[g]], k0, n) : 0u;
+#pragma unroll
+            for (int g = 0; g < GU; g++) if (e_[g] != 0xffffffffu) S.key[e_[g]] = kk[g];
+        }
+    }
     __syncthreads();
     for (uint32_t u = tid; u < nuns; u += FTH) {
         uint32_t e = S.list[u];
         uint32_t g = S.gb[e], gs = g & 0xffffu, ge = g >> 16;
-        uint32_t my = S.key[e], lt = 0, eq = 0, eqb = 0;
+        uint32_t my = S.key[e], lt = 0, le = 0;
+#pragma unroll 4
         for (uint32_t k = gs; k < ge; k++) {
             uint32_t x = S.key[k];
             lt += x < my;
-            uint32_t is = x == my;
-            eq += is;
-            eqb += is & (uint32_t)(k < e);
+            le += x <= my;
         }
+        uint32_t eq = le - lt;
         if (eq == 1) S.out[gs + lt] = S.idx[e];
         else {
+            uint32_t eqb = 0;                      // ties are rare: their order among equals is counted separately
+            for (uint32_t k = gs; k < e; k++) eqb += S.key[k] == my;
             uint32_t slot = atomicAdd(&S.ntied, 1u);
             if (slot < TCAP) { S.t_idx[slot] = S.idx[e]; S.t_cs[slot] = (uint16_t)(gs + lt); S.t_rank[slot] = (uint16_t)eqb; }
             else { S.out[gs + lt + eqb] = S.idx[e] | (eqb ? NONHEAD : 0u); leftover++; }
@@ -783,13 +855,25 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
     const uint32_t lo = S.lo, hi = S.hi;
     uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
     const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
-    const uint8_t *sq = P.seq + (uint64_t)lb * 256;
     uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
-    for (uint32_t pos = lo + tid; pos < hi; pos += FTH) {
-        uint32_t v = S.out[pos], s = v & VMASK;
-        sa[base + pos] = v;
-        L[base + pos] = sq[b[s ? s - 1 : n - 1]];
-        if (s == 0) blocks[lb].orig_ptr = (int32_t)(base + pos);
+    {
+        constexpr int OU = 4;
+        for (uint32_t pos0 = lo + tid; pos0 < hi; pos0 += FTH * OU) {
+            uint32_t v[OU]; uint8_t by[OU];
+#pragma unroll
+            for (int g = 0; g < OU; g++) { uint32_t pos = pos0 + g * FTH; v[g] = pos < hi ? S.out[pos] : 1u; }
+#pragma unroll
+            for (int g = 0; g < OU; g++) { uint32_t s_ = v[g] & VMASK; by[g] = b[s_ ? s_ - 1 : n - 1]; }
+#pragma unroll
+            for (int g = 0; g < OU; g++) {
+                uint32_t pos = pos0 + g * FTH;
+                if (pos < hi) {
+                    sa[base + pos] = v[g];
+                    L[base + pos] = S.seq[by[g]];
+                    if ((v[g] & VMASK) == 0) blocks[lb].orig_ptr = (int32_t)(base + pos);
+                }
+            }
+        }
     }
     uint32_t ltot;
     block_excl_sum<uint32_t>(leftover, S.scan, &ltot);

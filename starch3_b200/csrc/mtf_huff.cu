@@ -209,13 +209,14 @@ __global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *
     int beg = tid * chunk, end = beg + chunk;
     if (beg > n) beg = n;
     if (end > n) end = n;
-    // phase A: last occurrence (position + 1) of every symbol inside my chunk, scanning backwards
-    {
-        uint32_t seen = 0, full = a >= 32 ? ~0u : ((1u << a) - 1);
-        for (int p = end - 1; p >= beg && seen != full; p--) {
-            uint32_t sy = L[p];
-            if (!((seen >> sy) & 1u)) { seen |= 1u << sy; s_last[sy * MS + tid] = p + 1; }
-        }
+    // phase A: last occurrence (position + 1) of every symbol inside my chunk: a forward sweep of
+    // fire-and-forget shared-memory stores (bank = tid, conflict-free), 8 bytes per load
+    for (int p = beg; p < end; p += 8) {
+        uint64_t in8 = *reinterpret_cast<const uint64_t *>(L + p);          // beg % 8 == 0, slots padded
+        int lim = end - p < 8 ? end - p : 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < lim) s_last[((uint32_t)(in8 >> (8 * k)) & 0xffu) * MS + tid] = p + k + 1;
     }
     __syncthreads();
     // phase B: exclusive "latest occurrence" over the chunks

@@ -353,6 +353,12 @@ __global__ void k_compact_blocks(const BlockInfo *prov, const uint64_t *prov_bas
 }
 
 // ---- pass 4: write the RLE1 bytes into the block slots ----------------------
+// A tile that lies inside one block (all but one tile in ~220) stages its output in shared memory at
+// the same 16-byte phase as its destination and writes it out with aligned vector stores; the bytes
+// in use are collected in a per-CTA flag table.  Tiles that touch a block boundary take the
+// byte-by-byte path.
+constexpr int RW_BUF = RTILE + RTILE / 4 + 32;        // a tile emits at most 5/4 of its bytes, plus the phase
+
 __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n, StreamMap sm, const uint64_t *run_carry,
                                                    const uint64_t *e_base, const BlockInfo *blocks, uint64_t n_blocks,
                                                    uint8_t *blk_bytes, uint8_t *in_use)
@@ -360,15 +366,57 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
     __shared__ uint64_t s_max[33];
     __shared__ uint32_t s_sum[33];
     __shared__ TileStarts ts;
-    if (threadIdx.x == 0) find_tile_starts(sm, (uint64_t)blockIdx.x * RTILE, &ts);
+    __shared__ uint64_t s_bi;
+    __shared__ int s_fast;
+    __shared__ __align__(16) uint8_t s_buf[RW_BUF];
+    __shared__ uint8_t s_used[256];
+    const uint64_t tile_begin = (uint64_t)blockIdx.x * RTILE;
+    if (threadIdx.x == 0) {
+        find_tile_starts(sm, tile_begin, &ts);
+        // block containing the tile's first byte: last block with in_start <= tile_begin
+        uint64_t lo = 0, hi = n_blocks - 1;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi + 1) >> 1;
+            if (blocks[mid].in_start <= tile_begin) lo = mid; else hi = mid - 1;
+        }
+        uint64_t tile_end = tile_begin + RTILE < n ? tile_begin + RTILE : n;
+        s_bi = lo;
+        s_fast = blocks[lo].in_start <= tile_begin && tile_end <= blocks[lo].in_end;
+    }
+    s_used[threadIdx.x] = 0;
     __syncthreads();
     Win w;
-    load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
+    load_win(in, n, tile_begin + (uint64_t)threadIdx.x * RB, w);
     uint32_t sm_mask = run_start_mask(w, sm, ts, n);
     RleLocal r;
     rle_local(w, sm_mask, run_carry[blockIdx.x], s_max, r);
     uint32_t tot;
     uint32_t ex = block_excl_sum<uint32_t>(r.total, s_sum, &tot);
+    if (s_fast) {
+        const uint64_t bi = s_bi;
+        const uint64_t d0 = e_base[blockIdx.x] - blocks[bi].e_base;     // offset of the tile's output inside the block slot
+        const uint32_t ph = (uint32_t)d0 & 15u;
+        if (w.cnt) {
+            uint32_t o = ph + ex;
+#pragma unroll
+            for (int k = 0; k < RB; k++) {
+                if (k < w.cnt) {
+                    uint8_t by = (uint8_t)byte_of(w, k);
+                    if (r.emit_mask & (1u << k)) { s_buf[o++] = by; s_used[by] = 1; }
+                    if (r.cnt_mask & (1u << k)) { uint8_t cv = (uint8_t)((r.cnt_val[k >> 2] >> (8 * (k & 3))) & 0xffu); s_buf[o++] = cv; s_used[cv] = 1; }
+                }
+            }
+        }
+        __syncthreads();
+        uint8_t *dst = blk_bytes + bi * (uint64_t)BLK_STRIDE + (d0 - ph);        // 16-byte aligned
+        const uint32_t lo_b = ph, hi_b = ph + tot;                                // valid bytes of s_buf
+        for (uint32_t c = threadIdx.x * 16; c < hi_b; c += RT * 16) {
+            if (c >= lo_b && c + 16 <= hi_b) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(s_buf + c);
+            else for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = s_buf[j];
+        }
+        if (s_used[threadIdx.x]) in_use[bi * 256 + threadIdx.x] = 1;
+        return;
+    }
     if (w.cnt == 0) return;
     uint64_t e = e_base[blockIdx.x] + ex;
     // block containing my first byte: last block with in_start <= pos0
@@ -381,8 +429,6 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
     uint64_t b_end = blocks[bi].in_end, b_e0 = blocks[bi].e_base;
     uint8_t *dst = blk_bytes + bi * (uint64_t)BLK_STRIDE;
     uint8_t *use = in_use + bi * 256;
-    // common case: the 16 bytes are copied unchanged into one block at a 16-byte-aligned... (alignment is arbitrary,
-    // so bytes are stored one by one; the L2 merges them into full sectors)
 #pragma unroll
     for (int k = 0; k < RB; k++) {
         if (k < w.cnt) {
