@@ -164,7 +164,8 @@ def run_b200(args, rank, world, local_rank):
     pinned.numpy()[:] = bed
     d_bed = pinned.cuda(non_blocking=False)
     ctx = s3.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                      # the launching stream: library kernels and the timing events share it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     def barrier():
@@ -174,12 +175,23 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident: input already in HBM, output left in HBM ----
-    for _ in range(args.warmup):
+    # warm-up; the last warm-up step is timed kernel by kernel (two events around every launch) to get the
+    # per-kernel table and to find the dominant kernel
+    for i in range(args.warmup):
+        if i == args.warmup - 1:
+            ctx.profile(True)
         res = ctx.compress_bed_device(d_bed.data_ptr(), nbytes, 9, want_archive=False)
+    table = ctx.profile_report() if args.warmup else {}
+    if not table:
+        ctx.profile(True)
+        res = ctx.compress_bed_device(d_bed.data_ptr(), nbytes, 9, want_archive=False)
+        table = ctx.profile_report()
+    top_name = max(table.items(), key=lambda kv: kv[1][1])[0]
+    # timed region: K steps; only the dominant kernel keeps its events (its duration is measured live, here)
+    ctx.profile_filter(top_name)
     barrier()
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ctx.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -189,8 +201,10 @@ def run_b200(args, rank, world, local_rank):
     dev_ms = e0.elapsed_time(e1)
     prof = ctx.profile_report()
     ctx.profile(False)
+    ctx.profile_filter(None)
     lib_ms = res.device_ms
-    # the same K steps once more without the per-kernel events, to show what they cost
+    launches = ctx.launch_count - launches0
+    # the same K steps once more without any events
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
@@ -200,7 +214,6 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     noprof_ms = f0.elapsed_time(f1) / args.steps
     clocks = sampler.stop() if sampler else None
-    launches = ctx.launch_count - launches0
 
     # ---- end to end: host buffer in, archive in host memory out, through the C ABI ----
     host_view = pinned.numpy()
@@ -230,8 +243,8 @@ def run_b200(args, rank, world, local_rank):
         peak, peak_src = measured_peak_hbm()
         # dominant kernel: largest share of the per-kernel CUDA-event time in the timed region; its
         # algorithmic bytes are accounted per launch inside the library (S3G_BYTES)
-        tot_kernel_ms = sum(v[1] for v in prof.values()) or 1.0
-        top_name, (top_n, top_ms, top_bytes) = max(prof.items(), key=lambda kv: kv[1][1])
+        tot_kernel_ms = sum(v[1] for v in table.values()) or 1.0       # one step, every kernel (last warm-up step)
+        top_n, top_ms, top_bytes = prof[top_name]                        # the timed region, dominant kernel only
         n_blocks, tf_bytes = res.n_blocks, res.tf_bytes
         bytes_per_launch = top_bytes / top_n if top_n else 0.0
         achieved = bytes_per_launch / (top_ms / top_n / 1000.0) / 1e9 if top_n and top_ms else 0.0
@@ -251,18 +264,19 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": archive_bytes,
                     "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
-            "ms_per_step_without_kernel_events": noprof_ms, "library_first_to_last_kernel_ms": lib_ms,
+            "ms_per_step_without_any_events": noprof_ms, "library_first_to_last_kernel_ms": lib_ms,
             "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_share_of_step": top_ms / tot_kernel_ms, "launches": top_n,
+                         "kernel_share_of_step": table[top_name][1] / tot_kernel_ms, "launches": top_n,
                          "avg_launch_ms": top_ms / top_n if top_n else None, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "note": "radix passes of the block sort keep each block's 7 MB working set in the 126 MB L2, so DRAM traffic can be below the algorithmic bytes",
                          "pipeline": {"algorithmic_bytes_per_step": a_total, "achieved": a_total / (ms_per_step / 1000.0) / 1e9,
                                       "frac": a_total / (ms_per_step / 1000.0) / 1e9 / peak}},
+            "kernels_note": "one step (the last warm-up step) with events around every launch",
             "kernels": {k: {"launches": v[0], "ms": round(v[1], 3),
                             "GBps": round(v[2] / (v[1] / 1000.0) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None,
                             "frac": round(v[2] / (v[1] / 1000.0) / 1e9 / peak, 4) if v[1] > 0 and v[2] > 0 else None}
-                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+                        for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

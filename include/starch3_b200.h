@@ -52,6 +52,10 @@ S3G_API uint64_t s3g_launch_count(const s3g_ctx *ctx);
  * ("name\tlaunches\ttotal_ms\talgorithmic_bytes\n") into buf, then clears the records. */
 S3G_API int  s3g_profile(s3g_ctx *ctx, int enable);
 S3G_API int  s3g_profile_report(s3g_ctx *ctx, char *buf, uint64_t cap);
+/* Restrict the events to launches of one kernel (name as printed by s3g_profile_report);
+ * NULL or "" = every kernel.  Lets a caller time the dominant kernel inside a timed region
+ * without paying two event records around each of the ~90 other launches. */
+S3G_API int  s3g_profile_filter(s3g_ctx *ctx, const char *kernel_name);
 
 /* One entry per chromosome stream, in input order.  Mirrors what
  * process_tf_buffer (hpp:393-407) is handed: current_chr, line_count, the

@@ -18,7 +18,7 @@ lib_path = os.path.join(HERE, "libstarch3_b200.so")
 S3G_OK, S3G_E_CUDA, S3G_E_PARAM, S3G_E_NOMEM, S3G_E_MALFORMED, S3G_E_CAPACITY, S3G_E_LIMIT = 0, -1, -2, -3, -4, -5, -6
 
 C_ABI_SYMBOLS = [
-    "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_profile", "s3g_profile_report",
+    "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
 ]
@@ -78,6 +78,7 @@ def lib():
         L.s3g_launch_count.argtypes = [vp]; L.s3g_launch_count.restype = u64
         L.s3g_profile.argtypes = [vp, i32]
         L.s3g_profile_report.argtypes = [vp, C.c_char_p, u64]
+        L.s3g_profile_filter.argtypes = [vp, C.c_char_p]
         L.s3g_compress_bed.argtypes = [vp, vp, u64, i32, C.c_char_p, C.POINTER(CResult)]
         L.s3g_compress_bed_device.argtypes = [vp, vp, u64, i32, C.c_char_p, i32, C.POINTER(CResult)]
         L.s3g_result_free.argtypes = [C.POINTER(CResult)]; L.s3g_result_free.restype = None
@@ -182,6 +183,10 @@ class Context:
 
     def profile(self, enable=True):
         self._check(self._lib.s3g_profile(self._h, 1 if enable else 0))
+
+    def profile_filter(self, kernel_name=None):
+        """Time only launches of `kernel_name` (None = all kernels)."""
+        self._check(self._lib.s3g_profile_filter(self._h, kernel_name.encode() if kernel_name else None))
 
     def profile_report(self):
         """-> {kernel name: (launches, total_ms, algorithmic_bytes)} since profiling was enabled / last report."""

@@ -2,6 +2,7 @@
 // GPU pipeline.  Host code is plain C++; nothing here computes on the CPU except the
 // few-hundred-byte archive header (ARCHIVE_FORMAT.md).
 #include <cstdarg>
+#include <ctime>
 #include <algorithm>
 #include <new>
 #include "common.cuh"
@@ -30,6 +31,7 @@ int prof_begin(Ctx *ctx, const char *name)
     double bytes = ctx->prof_next_bytes;
     ctx->prof_next_bytes = 0;
     if (!ctx->prof) return -1;
+    if (!ctx->prof_filter.empty() && ctx->prof_filter != name) return -1;
     while (ctx->prof_used + 2 > ctx->prof_pool.size()) {
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -88,11 +90,21 @@ __global__ void k_soff_from_chroms(const s3g_chrom *chroms, uint64_t n_chroms, u
 }
 
 // stages 3a..3e over `n_streams` streams laid out back to back in d_in
+static double host_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int compress_streams(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams, int level,
                             uint64_t *n_blocks_out, uint64_t *total_bytes)
 {
+    const bool timing = getenv("S3G_TIMING") != nullptr;
+    double t0 = timing ? host_ms() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
     CutResult cut;
     S3G_TRY(run_rle_cut(ctx, d_in, n, d_soff, n_streams, level, &cut));
+    if (timing) t1 = host_ms();
     uint64_t nb = cut.n_blocks;
     *n_blocks_out = nb;
     ctx->pool_words = 0;
@@ -102,18 +114,28 @@ static int compress_streams(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uin
         uint64_t held = 0;
         DevBuf *batch_bufs[] = {&ctx->sa, &ctx->rk, &ctx->kv0, &ctx->kv1, &ctx->hist, &ctx->lcol, &ctx->mtf0, &ctx->mtfv16, &ctx->bits};
         for (DevBuf *b : batch_bufs) held += b->cap;
-        uint64_t batch = pick_batch(nb);
+        // steady state: the buffers already hold this many blocks; cudaMemGetInfo is only asked when they must grow
+        // (it takes anywhere from 0.1 to 20 ms on a shared host)
         uint64_t have = held / batch_bytes_per_block();
+        uint64_t batch = have >= nb && !getenv("S3G_BATCH") ? nb : pick_batch(nb);
         if (have > batch) batch = std::min<uint64_t>(nb, have);
         for (uint64_t b0 = 0; b0 < nb; b0 += batch) {
             uint64_t cnt = std::min<uint64_t>(batch, nb - b0);
+            if (timing) t2 = host_ms();
             S3G_TRY(run_bwt(ctx, b0, cnt));
+            if (timing) t3 = host_ms();
             S3G_TRY(run_mtf(ctx, b0, cnt));
             S3G_TRY(run_huff(ctx, b0, cnt, 1, nullptr, nullptr));
             S3G_TRY(run_pool_append(ctx, b0, cnt));
+            if (timing) t4 = host_ms();
         }
     }
     S3G_TRY(run_assemble(ctx, nb, n_streams, level, total_bytes));
+    if (timing) {
+        t5 = host_ms();
+        fprintf(stderr, "[s3g timing] rle+cut %.2f  batch setup %.2f  bwt %.2f  mtf+huff+pool (enqueue) %.2f  assemble %.2f  total %.2f ms (host clock)\n",
+                t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0);
+    }
     return S3G_OK;
 }
 
@@ -185,7 +207,9 @@ static int compress_bed_impl(Ctx *ctx, const uint8_t *d_bed, uint64_t n, int lev
     S3G_CUDA(cudaSetDevice(ctx->device));
     S3G_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     TfResult tr;
+    double tt0 = getenv("S3G_TIMING") ? host_ms() : 0;
     S3G_TRY(run_transform(ctx, d_bed, n, &tr, false));
+    if (getenv("S3G_TIMING")) fprintf(stderr, "[s3g timing] transform %.2f ms (host clock)\n", host_ms() - tt0);
     res->n_lines = tr.n_lines; res->n_chroms = tr.n_chroms; res->tf_bytes = tr.tf_len; res->dropped_tail_bytes = tr.dropped;
     uint64_t total_bytes = 0, n_blocks = 0;
     if (tr.n_chroms) {
@@ -329,6 +353,13 @@ int s3g_profile(s3g_ctx *ctx, int enable)
     if (!ctx) { set_error("null context"); return S3G_E_PARAM; }
     ctx->prof = enable != 0;
     if (!enable) { ctx->prof_recs.clear(); ctx->prof_used = 0; }
+    return S3G_OK;
+}
+
+int s3g_profile_filter(s3g_ctx *ctx, const char *kernel_name)
+{
+    if (!ctx) { set_error("null context"); return S3G_E_PARAM; }
+    ctx->prof_filter = kernel_name ? kernel_name : "";
     return S3G_OK;
 }
 

@@ -108,6 +108,7 @@ struct Ctx {
     size_t h_archive_cap = 0;
     // per-kernel profiling (off by default)
     bool prof = false;
+    std::string prof_filter;               // non-empty: only this kernel is timed
     struct ProfRec { const char *name; cudaEvent_t e0, e1; double bytes; };
     double prof_next_bytes = 0;
     std::vector<ProfRec> prof_recs;
