@@ -616,16 +616,18 @@ constexpr int FLEVELS = 12;                      // levels of k symbols before a
 constexpr uint32_t NONHEAD = 0x80000000u;        // SA flag: same (unsorted) group as the previous position
 constexpr uint32_t VMASK = 0x000fffffu;          // rotation start (< 2^20)
 
+constexpr int FROWS = (FWA + 31) / 32;           // 32-entry rows of the window
+
 struct FinSmem {
     uint32_t key[FWA];        // low 32 bits of the initial key while grouping, level-0 key afterwards
     uint32_t idx[FWA];        // rotation start (low 20 bits); the key's high bits above them while grouping
-    uint32_t gb[FWA];         // group start | group end << 16 (window-relative); start 0xffff = continuation from an earlier tile
-    uint32_t out[FWA];        // final SA value per window position (scratch for group ends while grouping)
-    uint16_t list[FWA];       // entries that take part in level 0, in window order
+    uint32_t gb[FWA];         // group start | group end << 16 (window-relative) of entries that take part in level 0
+    uint32_t out[FWA];        // final SA value per window position
+    uint32_t hbits[FROWS + 1];// bit l of word r: entry 32 r + l starts a group
     uint32_t t_idx[TCAP], t_key[TCAP];
     uint16_t t_cs[TCAP], t_rank[TCAP];
     uint32_t scan[33];
-    uint32_t first_head, c, ntied, lo, hi, handled;
+    uint32_t first_head, ntied, lo, hi, handled;
     uint8_t seq[256];         // unseqToSeq of the block
 };
 
@@ -634,6 +636,24 @@ __device__ __forceinline__ uint32_t deeper_key(const uint32_t *k30, uint32_t pos
     uint32_t p = pos + off;
     if (p >= n) { p -= n; if (p >= n) p %= n; }
     return k30[p];
+}
+
+// group start of entry e from the head bitmap: last head at or before e (0xffffffff if none in the window)
+__device__ __forceinline__ uint32_t fin_group_start(const uint32_t *hbits, uint32_t e)
+{
+    int w = (int)(e >> 5);
+    uint32_t m = hbits[w] & (0xffffffffu >> (31 - (e & 31)));
+    while (!m && w > 0) m = hbits[--w];
+    return m ? (uint32_t)w * 32 + (31 - __clz(m)) : 0xffffffffu;
+}
+// first head after e, or W if there is none
+__device__ __forceinline__ uint32_t fin_group_end(const uint32_t *hbits, uint32_t e, uint32_t W)
+{
+    uint32_t w = e >> 5, nw = (W + 31) >> 5;
+    uint32_t m = (e & 31) == 31 ? 0u : hbits[w] & (0xffffffffu << ((e & 31) + 1));
+    while (!m && ++w < nw) m = hbits[w];
+    uint32_t ge = m ? w * 32 + (uint32_t)__ffs(m) - 1 : W;
+    return ge < W ? ge : W;
 }
 
 __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
@@ -649,14 +669,15 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
     const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
     const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
     const uint32_t avail = n - base;
+    constexpr int EPT = (FWA + FTH - 1) / FTH;       // entries per thread, entry = tid + j * FTH (row = warp + 16 j, bit = lane)
     // ---- 1. load the tile, then extend to the end of the group that crosses its end ----
-    uint32_t W = min(avail, (uint32_t)FT);
     // record = key << 20 | start: key[] gets key bits 0..31, idx[] gets start | key bits 32.. << 20
+    uint32_t W = min(avail, (uint32_t)FT);
     for (uint32_t e = tid; e < W; e += FTH) { uint64_t x = a[base + e]; S.key[e] = (uint32_t)(x >> VAL_BITS); S.idx[e] = (uint32_t)x & VMASK | (uint32_t)(x >> 52) << VAL_BITS; }
     if (tid < 256) S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
     if (tid == 0) {
         S.first_head = (base == 0) || (a[base - 1] >> VAL_BITS) != (a[base] >> VAL_BITS);
-        S.c = 0xffffffffu; S.ntied = 0; S.lo = 0; S.hi = 0; S.handled = 0;
+        S.ntied = 0; S.lo = 0; S.hi = 0; S.handled = 0;
     }
     __syncthreads();
     if (avail > FT) {
@@ -674,112 +695,81 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
         }
     }
     const bool open_end = W < avail;              // the group holding entry W-1 continues past the window
-    // ---- 2. group starts (max-scan of head positions), group ends, classification ----
-    const uint32_t e0 = tid * FEPT;
-    uint32_t hm = 0, lh = 0;
+    const uint32_t tile_w = min(W, (uint32_t)FT);
+    // ---- 2. head bitmap: one ballot per 32-entry row ----
 #pragma unroll
-    for (int k = 0; k < FEPT; k++) {
-        uint32_t e = e0 + k;
-        if (e < W) {
-            bool head = e == 0 ? S.first_head != 0 : (S.key[e] != S.key[e - 1] || (S.idx[e] ^ S.idx[e - 1]) >> VAL_BITS);
-            if (head) { hm |= 1u << k; lh = e + 1; }
-        }
-    }
-    if (hm) atomicMin(&S.c, e0 + (uint32_t)__ffs(hm) - 1);
-    uint32_t tot;
-    uint32_t cur = block_excl_max<uint32_t>(lh, S.scan, &tot);    // (entry + 1) of the last head before my range
-    uint32_t gs_[FEPT];
-#pragma unroll
-    for (int k = 0; k < FEPT; k++) {
-        uint32_t e = e0 + k;
-        gs_[k] = 0xffffu;
-        if (e < W) {
-            if (hm & (1u << k)) cur = e + 1;
-            if (cur) {
-                gs_[k] = cur - 1;
-                bool last = e + 1 == W || S.key[e + 1] != S.key[e] || (S.idx[e + 1] ^ S.idx[e]) >> VAL_BITS;
-                if (last) S.out[cur - 1] = e + 1;
-            }
+    for (int j = 0; j < EPT; j++) {
+        uint32_t e = tid + j * FTH;
+        if ((e & ~31u) < W) {                     // whole rows only: the ballot needs every lane of the warp
+            bool head = e >= W ? false
+                      : e == 0 ? S.first_head != 0 : (S.key[e] != S.key[e - 1] || (S.idx[e] ^ S.idx[e - 1]) >> VAL_BITS);
+            uint32_t hb = __ballot_sync(0xffffffffu, head);
+            if ((tid & 31) == 0) S.hbits[e >> 5] = hb;
         }
     }
     __syncthreads();
-    const uint32_t c = min(S.c, W);               // entries [0, c) continue a group that started in an earlier tile
-    if (tid == 0 && c > 0) {
+    // entries [0, c) continue a group that started in an earlier tile
+    if (tid == 0) {
+        uint32_t c = W;
+        for (uint32_t w = 0; w < (W + 31) / 32; w++) if (S.hbits[w]) { c = w * 32 + (uint32_t)__ffs(S.hbits[w]) - 1; break; }
         // the owner sorted that group iff its size is <= FX; it ends at base + c
         bool handled = false;
-        if (c < FT && !(c == W && open_end)) {
+        if (c > 0 && c < FT && !(c == W && open_end)) {
             uint32_t end = base + c;
             handled = end <= FX || (a[end - FX - 1] >> VAL_BITS) != (a[base] >> VAL_BITS);
         }
         S.handled = handled;
-    }
-    uint32_t myuns = 0;
-    uint32_t ge_[FEPT];
-#pragma unroll
-    for (int k = 0; k < FEPT; k++) {
-        ge_[k] = 0;
-        if (gs_[k] != 0xffffu) {
-            ge_[k] = S.out[gs_[k]];
-            uint32_t size = ge_[k] - gs_[k];
-            bool sortable = gs_[k] < FT && size <= FX && !(open_end && ge_[k] == W);
-            if (sortable && size > 1) myuns++;
-        }
-    }
-    uint32_t nuns;
-    uint32_t lpos = block_excl_sum<uint32_t>(myuns, S.scan, &nuns);   // (syncs: every read of the group ends in S.out is done)
-    uint32_t leftover = 0;
-    const uint32_t tile_w = min(W, (uint32_t)FT);
-    const uint32_t handled = S.handled;
-#pragma unroll
-    for (int k = 0; k < FEPT; k++) {
-        uint32_t e = e0 + k;
-        if (e >= W) continue;
-        uint32_t gs = gs_[k], ge = ge_[k];
-        S.gb[e] = gs | (ge << 16);
-        S.idx[e] &= VMASK;                        // the key's high bits are no longer needed
-        if (gs == 0xffffu) {
-            // continuation of a group from an earlier tile: written here only when its owner could not sort it
-            if (!handled && e < tile_w) { S.out[e] = S.idx[e] | NONHEAD; leftover++; }
-            continue;
-        }
-        if (gs >= FT) continue;
-        uint32_t size = ge - gs;
-        bool sortable = size <= FX && !(open_end && ge == W);
-        if (!sortable) {
-            if (e < tile_w) { S.out[e] = S.idx[e] | (e > gs ? NONHEAD : 0u); leftover++; }
-        } else if (size == 1) {
-            S.out[e] = S.idx[e];
-        } else {
-            S.list[lpos++] = (uint16_t)e;
-        }
-        if (e + 1 == tile_w) S.hi = sortable ? ge : tile_w;     // the group holding the tile's last entry decides the written range
-    }
-    if (tid == 0) {
         if (c >= tile_w) { S.lo = handled ? tile_w : 0; S.hi = tile_w; }   // no group starts in this tile
         else S.lo = handled ? c : 0;
     }
     __syncthreads();
-    // ---- 3. level 0: the next k32 symbols of every unsorted rotation ----
-    {
-        constexpr int GU = 4;                       // gathers in flight per thread
-        for (uint32_t u0 = tid; u0 < nuns; u0 += FTH * GU) {
-            uint32_t e_[GU], kk[GU];
+    // ---- 3. classify every entry; unsorted ones fetch their level-0 key (the next k32 symbols) ----
+    const uint32_t handled = S.handled;
+    uint32_t leftover = 0;
+    uint32_t unsorted = 0;                        // bit j: entry tid + j * FTH takes part in level 0
+    uint32_t l0key[EPT];
 #pragma unroll
-            for (int g = 0; g < GU; g++) {
-                uint32_t u = u0 + g * FTH;
-                e_[g] = u < nuns ? S.list[u] : 0xffffffffu;
-            }
-#pragma unroll
-            for (int g = 0; g < GU; g++) kk[g] = e_[g] != 0xffffffffu ? deeper_key(k30, S.idx[e_[g]], k0, n) : 0u;
-#pragma unroll
-            for (int g = 0; g < GU; g++) if (e_[g] != 0xffffffffu) S.key[e_[g]] = kk[g];
+    for (int j = 0; j < EPT; j++) {
+        uint32_t e = tid + j * FTH;
+        l0key[j] = 0;
+        if (e >= W) continue;
+        uint32_t v = S.idx[e] & VMASK;
+        uint32_t gs = fin_group_start(S.hbits, e);
+        if (gs == 0xffffffffu) {
+            // continuation of a group from an earlier tile: written here only when its owner could not sort it
+            if (!handled && e < tile_w) { S.out[e] = v | NONHEAD; leftover++; }
+            continue;
+        }
+        if (gs >= FT) continue;                   // belongs to the next tile
+        uint32_t ge = fin_group_end(S.hbits, e, W);
+        uint32_t size = ge - gs;
+        bool sortable = size <= FX && !(open_end && ge == W);
+        if (e + 1 == tile_w) S.hi = sortable ? ge : tile_w;     // the group holding the tile's last entry decides the written range
+        if (!sortable) {
+            if (e < tile_w) { S.out[e] = v | (e > gs ? NONHEAD : 0u); leftover++; }
+        } else if (size == 1) {
+            S.out[e] = v;
+        } else {
+            unsorted |= 1u << j;
+            S.gb[e] = gs | (ge << 16);
+            l0key[j] = deeper_key(k30, v, k0, n);
         }
     }
+    __syncthreads();                              // every read of the grouping keys is done
+#pragma unroll
+    for (int j = 0; j < EPT; j++) {
+        uint32_t e = tid + j * FTH;
+        if (e < W) S.idx[e] &= VMASK;
+        if (unsorted & (1u << j)) S.key[e] = l0key[j];
+    }
     __syncthreads();
-    for (uint32_t u = tid; u < nuns; u += FTH) {
-        uint32_t e = S.list[u];
+    // ---- 4. level 0: rank inside the group by counting smaller / not larger keys ----
+#pragma unroll
+    for (int j = 0; j < EPT; j++) {
+        if (!(unsorted & (1u << j))) continue;
+        uint32_t e = tid + j * FTH;
         uint32_t g = S.gb[e], gs = g & 0xffffu, ge = g >> 16;
-        uint32_t my = S.key[e], lt = 0, le = 0;
+        uint32_t my = l0key[j], lt = 0, le = 0;
 #pragma unroll 4
         for (uint32_t k = gs; k < ge; k++) {
             uint32_t x = S.key[k];
@@ -797,7 +787,7 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
         }
     }
     __syncthreads();
-    // ---- 4. deeper levels on the tied list ----
+    // ---- 5. deeper levels on the tied list ----
     const uint32_t nt_all = S.ntied;
     const uint32_t nt = min(nt_all, (uint32_t)TCAP);
     constexpr int TPT = TCAP / FTH;
@@ -851,7 +841,7 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
         }
     }
     __syncthreads();
-    // ---- 5. write SA, the BWT last column (bz/compress.c:166-167) and origPtr (bz/blocksort.c:1083-1086) ----
+    // ---- 6. write SA, the BWT last column (bz/compress.c:166-167) and origPtr (bz/blocksort.c:1083-1086) ----
     const uint32_t lo = S.lo, hi = S.hi;
     uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
     const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
