@@ -558,6 +558,8 @@ static int load_blocks(Ctx *ctx, const uint8_t *blocks, const uint64_t *off, uin
         S3G_LAUNCH(ctx, k_in_use_from_bytes, g, 256, 0, ctx->blk_bytes.as<uint8_t>(), ctx->blocks.as<BlockInfo>(), ctx->in_use.as<uint8_t>());
     }
     S3G_LAUNCH(ctx, k_block_maps_api, (unsigned)nb, 256, 0, ctx->in_use.as<uint8_t>(), ctx->blocks.as<BlockInfo>(), ctx->seq_map.as<uint8_t>());
+    // host mirror with the alphabet sizes (the later stages size their launches from it)
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_blocks.data(), ctx->blocks.p, nb * sizeof(BlockInfo), cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     return check_launch("load blocks");
 }

@@ -357,7 +357,12 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
     // ~20).  The mask table aliases the staging buffer, which is not live until ranking is over.
     static_assert(sizeof(S.stage) >= (ST / 32) * NBINS * 4, "mask table must fit in the staging buffer");
     uint32_t *Mall = reinterpret_cast<uint32_t *>(S.stage);
-    for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) { S.wcnt[i] = 0; Mall[i] = 0; }
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 *zm = reinterpret_cast<uint4 *>(S.stage), *zc = reinterpret_cast<uint4 *>(S.wcnt);
+        for (int i = threadIdx.x; i < (ST / 32) * NBINS / 4; i += ST) zm[i] = z;      // mask table: 8 warps x 1024 words
+        for (int i = threadIdx.x; i < (ST / 32) * NBINS / 8; i += ST) zc[i] = z;      // counters: 8 warps x 1024 halfwords
+    }
     __syncthreads();
     const uint32_t ticket = S.scan[0];
     const uint32_t tile = ticket / nb, lb = ticket - tile * nb;
@@ -376,6 +381,15 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
         uint32_t p = base + r * 32;
         kv[r] = 0;
         if (p < cnt) { kv[r] = in[p]; okmask |= 1u << r; }
+    }
+    {
+        // the tile that will be handed out about two waves from now: pull it into L2 (one 128-byte line per thread)
+        uint32_t t2 = ticket + 2 * SM_COUNT * 3;
+        uint32_t tile2 = t2 / nb, lb2 = t2 - tile2 * nb;
+        if (tile2 < NT) {
+            const uint8_t *pf = reinterpret_cast<const uint8_t *>(kv_in + (uint64_t)lb2 * BLK_STRIDE + (uint64_t)tile2 * STILE) + threadIdx.x * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
     }
     const uint32_t lbit = 1u << l, ltmask = lbit - 1;
     // match.any is cheap when the warp holds few distinct digits (the upper passes of text: the records
@@ -473,8 +487,9 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
 #pragma unroll
     for (int q = 0; q < DPT; q++) {
         int d = threadIdx.x * DPT + q;
-        S.tbase[d] = ex; ex += tot4[q];
-        S.gbase[d] = dbase[d] + ex4[q];
+        S.tbase[d] = ex;
+        S.gbase[d] = dbase[d] + ex4[q] - ex;          // (global offset - tile offset) of the digit
+        ex += tot4[q];
     }
     __syncthreads();
 #pragma unroll
@@ -489,7 +504,7 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
     for (uint32_t i = threadIdx.x; i < tile_total; i += ST) {
         uint64_t it = S.stage[i];
         uint32_t d = (uint32_t)(it >> rshift) & (NBINS - 1);
-        out[S.gbase[d] + (i - S.tbase[d])] = it;
+        out[S.gbase[d] + i] = it;
     }
 }
 

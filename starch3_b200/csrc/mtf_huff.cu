@@ -129,7 +129,7 @@ __device__ __forceinline__ void mtf_zero_runs(const uint8_t *M, uint16_t *mtfv, 
 // masked one-byte shift.  A block is cut into 512 chunks, one per thread; the list a chunk
 // starts with is the symbols ordered by their last occurrence before the chunk.
 // =============================================================================
-constexpr int MS = 512;
+constexpr int MS = 512;                 // chunks (threads) per block
 
 template <int NW>
 __device__ __forceinline__ uint32_t mtf_step(uint64_t (&lst)[NW], uint32_t s)
@@ -188,21 +188,22 @@ __device__ __forceinline__ void mtf_thread_chunk(const uint8_t *L, uint8_t *M, i
 }
 
 __global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
-                                                  BlockInfo *blocks)
+                                                  BlockInfo *blocks, int rows)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *s_last = reinterpret_cast<int *>(smem_raw);            // [32][MS]
-    int *s_freq = s_last + 32 * MS;                             // [258]
+    int *s_last = reinterpret_cast<int *>(smem_raw);            // [rows][MS], rows = largest alphabet (<= 32) in the batch
+    int *s_freq = s_last + rows * MS;                           // [258]
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_freq + 260);
     const uint32_t lb = blockIdx.x;
     const int n = (int)blocks[lb].nblock;
     const int a = (int)blocks[lb].n_in_use;
     if (a > 32) return;                                         // handled by k_mtf
+    if (a > rows) __trap();                                     // host mirror out of date: fail loudly
     const uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
     uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
     uint16_t *mtfv = mtfv_all + (uint64_t)lb * BLK_STRIDE;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 32 * MS; i += MS) s_last[i] = 0;
+    for (int i = tid; i < a * MS; i += MS) s_last[i] = 0;
     for (int i = tid; i < 258; i += MS) s_freq[i] = 0;
     __syncthreads();
     int chunk = (((n + MS - 1) / MS) + 7) & ~7;
@@ -317,18 +318,25 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->mtf0.ensure(slots));                 // MTF ranks before zero-run coding
     S3G_TRY(ctx->mtfv16.ensure(slots * 2));
     S3G_TRY(ctx->mtf_freq.ensure((size_t)nb * 258 * 4));
-    const size_t small_smem = (size_t)32 * MS * 4 + 260 * 4 + 40 * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-        S3G_CUDA(cudaFuncSetAttribute(k_mtf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
-        attr_done = true;
-    }
     // alphabets of <= 32 symbols take the register-list kernel, larger ones the warp-cooperative one
     double N = 0;
-    for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
+    int rows = 1;
+    for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) {
+        N += ctx->h_blocks[b0 + b].nblock;
+        int a = (int)ctx->h_blocks[b0 + b].n_in_use;
+        if (a <= 32 && a > rows) rows = a;
+        if (a == 0) rows = 32;                        // alphabet not mirrored on the host: size for the worst case
+    }
+    if (ctx->h_blocks.size() < b0 + nb) rows = 32;
+    const size_t small_smem = (size_t)rows * MS * 4 + 260 * 4 + 40 * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        S3G_CUDA(cudaFuncSetAttribute(k_mtf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)32 * MS * 4 + 260 * 4 + 40 * 4)));
+        attr_done = true;
+    }
     S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
     S3G_LAUNCH(ctx, k_mtf_small, (unsigned)nb, MS, small_smem, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
-               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
+               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, rows);
     S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
                ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
     return check_launch("mtf");

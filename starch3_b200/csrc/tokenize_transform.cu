@@ -256,24 +256,45 @@ __device__ __forceinline__ uint64_t put_dec(uint8_t *dst, int64_t v)
     return k;
 }
 
-__global__ void k_write_tf(const uint8_t *__restrict__ bed, LineView lv, const uint64_t *__restrict__ line_tf_off,
-                           uint64_t n_lines, uint8_t *__restrict__ tf)
+// One thread formats one line.  The 256 lines of a CTA produce one contiguous piece of the transformed
+// buffer, so they are staged in shared memory at the destination's 16-byte phase and written out with
+// aligned vector stores (per-thread byte stores to HBM kept the load/store queues full).
+constexpr int WT_LINES = 256;
+constexpr int WT_BUF = 16384;
+
+__global__ void __launch_bounds__(WT_LINES) k_write_tf(const uint8_t *__restrict__ bed, LineView lv, const uint64_t *__restrict__ line_tf_off,
+                                                       uint64_t n_lines, uint64_t tf_total, uint8_t *__restrict__ tf)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_lines) return;
-    int64_t ps, pl; lv.prev(i, &ps, &pl);
-    int64_t s = lv.start[i], t = lv.stop[i];
-    int64_t len = (int64_t)((uint64_t)t - (uint64_t)s), d = (int64_t)((uint64_t)s - (uint64_t)ps);
-    uint8_t *o = tf + line_tf_off[i];
-    if (len != pl) { *o++ = 'p'; o += put_dec(o, len); *o++ = '\n'; }     // hpp:438-455
-    o += put_dec(o, d);                                                   // hpp:456-500
-    uint64_t p = lv.line_start[i], e = lv.line_start[i + 1] - 1;
-    uint64_t r = p + lv.rem_off[i];
-    if (r < e) {
-        *o++ = '\t';
-        for (uint64_t q = r; q < e; q++) *o++ = bed[q];
+    __shared__ __align__(16) uint8_t s_buf[WT_BUF + 16];
+    const uint64_t i0 = (uint64_t)blockIdx.x * WT_LINES;
+    const uint64_t i1 = i0 + WT_LINES < n_lines ? i0 + WT_LINES : n_lines;
+    const uint64_t o_begin = line_tf_off[i0], o_end = i1 < n_lines ? line_tf_off[i1] : tf_total;
+    const bool staged = o_end - o_begin <= WT_BUF;
+    const uint32_t ph = (uint32_t)o_begin & 15u;
+    uint64_t i = i0 + threadIdx.x;
+    if (i < n_lines) {
+        int64_t ps, pl; lv.prev(i, &ps, &pl);
+        int64_t s = lv.start[i], t = lv.stop[i];
+        int64_t len = (int64_t)((uint64_t)t - (uint64_t)s), d = (int64_t)((uint64_t)s - (uint64_t)ps);
+        uint8_t *o = staged ? s_buf + ph + (line_tf_off[i] - o_begin) : tf + line_tf_off[i];
+        if (len != pl) { *o++ = 'p'; o += put_dec(o, len); *o++ = '\n'; }     // hpp:438-455
+        o += put_dec(o, d);                                                   // hpp:456-500
+        uint64_t p = lv.line_start[i], e = lv.line_start[i + 1] - 1;
+        uint64_t r = p + lv.rem_off[i];
+        if (r < e) {
+            *o++ = '\t';
+            for (uint64_t q = r; q < e; q++) *o++ = bed[q];
+        }
+        *o = '\n';
     }
-    *o = '\n';
+    if (!staged) return;
+    __syncthreads();
+    uint8_t *dst = tf + (o_begin - ph);                                       // 16-byte aligned (tf comes from cudaMalloc)
+    const uint32_t lo_b = ph, hi_b = ph + (uint32_t)(o_end - o_begin);
+    for (uint32_t c = threadIdx.x * 16; c < hi_b; c += WT_LINES * 16) {
+        if (c >= lo_b && c + 16 <= hi_b) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(s_buf + c);
+        else for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = s_buf[j];
+    }
 }
 
 int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only)
@@ -359,7 +380,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
                ctx->line_tf_off.as<uint64_t>(), ctx->chrom_first.as<uint64_t>(), ctx->stat_b.as<Stat3>(), d_stat_total,
                out->n_chroms, n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>());
     S3G_BYTES(ctx, n + out->tf_len + 37 * n_lines);
-    S3G_LAUNCH(ctx, k_write_tf, lgrid, 256, 0, d_bed, lv, ctx->line_tf_off.as<uint64_t>(), n_lines, ctx->tf.as<uint8_t>());
+    S3G_LAUNCH(ctx, k_write_tf, lgrid, WT_LINES, 0, d_bed, lv, ctx->line_tf_off.as<uint64_t>(), n_lines, out->tf_len, ctx->tf.as<uint8_t>());
     return check_launch("transform write");
 }
 
