@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int rshift, int phase
 //             a tile's predecessors always hold earlier tickets (forward progress), and with many
 //             blocks in a batch the predecessor has normally published its inclusive prefix already.
 constexpr int KT = 8;                        // tiles per CTA in k_keys
+constexpr int SWEEP_G = 64;                  // blocks whose tiles are interleaved in a radix pass
 constexpr int NPASS = KEY_BITS / 10;
 constexpr uint32_t ST_INCL = 1u << 23, ST_AGG = 1u << 22, ST_VAL = 0x000fffffu;
 
@@ -345,27 +346,44 @@ __global__ void __launch_bounds__(NBINS) k_digit_scan(uint32_t *ghist)
     g[threadIdx.x] = block_excl_sum<uint32_t>(v, sm, &tot);
 }
 
+// STABLE = false (the first pass only: the records arrive in position order, which carries no
+// meaning yet): ranks come straight from an atomicAdd on one per-tile counter per digit -- no
+// per-warp tables, no peer matching, and the 16 records of a thread rank independently.
+template <bool STABLE>
 __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *dbase_all,
-                                                 int pass, uint32_t *ticket_ctr, uint32_t nb, uint32_t gen)
+                                                 int pass, uint32_t *ticket_ctr, uint32_t nb, uint32_t gen, uint32_t G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
-    if (threadIdx.x == 0) S.scan[0] = atomicAdd(ticket_ctr, 1u);
+    // one ticket counter per bzip2 block (a single counter for the whole grid serialises ~65 k atomics on one
+    // L2 address per pass, ~35 cycles each: that alone is 1.2 ms): the CTA is bound to block blockIdx.x % nb and
+    // draws the next tile of that block
+    // CTAs are dealt to the blocks in groups of SWEEP_G: the tiles of one block run close together in time, so the
+    // 32-byte pieces a digit receives from consecutive tiles meet in L2 and leave as full lines (with the whole
+    // batch interleaved they were evicted one sector at a time and the pass ran at a third of the DRAM rate),
+    // while the look-back still finds its predecessors finished after about 444 / SWEEP_G tiles.
+    const uint32_t lb = blockIdx.x / (NT * G) * G + blockIdx.x % G;
+    if (lb >= nb) return;
+    if (threadIdx.x == 0) S.scan[0] = atomicAdd(ticket_ctr + lb, 1u);
     // Intra-warp matching through shared memory instead of match.any (measured on B200: match.any costs
     // ~8 cycles per DISTINCT value in the warp, 170-250 cycles per call on these digits; an atomicOr of
     // the lane bit into a per-warp, per-digit mask word plus a read-back gives the same peer mask for
     // ~20).  The mask table aliases the staging buffer, which is not live until ranking is over.
     static_assert(sizeof(S.stage) >= (ST / 32) * NBINS * 4, "mask table must fit in the staging buffer");
     uint32_t *Mall = reinterpret_cast<uint32_t *>(S.stage);
+    uint32_t *tcnt = reinterpret_cast<uint32_t *>(S.wcnt);       // !STABLE: one counter per digit
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *zm = reinterpret_cast<uint4 *>(S.stage), *zc = reinterpret_cast<uint4 *>(S.wcnt);
-        for (int i = threadIdx.x; i < (ST / 32) * NBINS / 4; i += ST) zm[i] = z;      // mask table: 8 warps x 1024 words
-        for (int i = threadIdx.x; i < (ST / 32) * NBINS / 8; i += ST) zc[i] = z;      // counters: 8 warps x 1024 halfwords
+        if (STABLE) {
+            for (int i = threadIdx.x; i < (ST / 32) * NBINS / 4; i += ST) zm[i] = z;      // mask table: 8 warps x 1024 words
+            for (int i = threadIdx.x; i < (ST / 32) * NBINS / 8; i += ST) zc[i] = z;      // counters: 8 warps x 1024 halfwords
+        } else {
+            for (int i = threadIdx.x; i < NBINS / 4; i += ST) zc[i] = z;
+        }
     }
     __syncthreads();
-    const uint32_t ticket = S.scan[0];
-    const uint32_t tile = ticket / nb, lb = ticket - tile * nb;
+    const uint32_t tile = S.scan[0];
     const uint32_t cnt = P.cnt_n[lb];
     if ((uint64_t)tile * STILE >= cnt) return;
     uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -384,64 +402,72 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
     }
     {
         // the tile that will be handed out about two waves from now: pull it into L2 (one 128-byte line per thread)
-        uint32_t t2 = ticket + 2 * SM_COUNT * 3;
-        uint32_t tile2 = t2 / nb, lb2 = t2 - tile2 * nb;
+        uint32_t tile2 = tile + 2 * SM_COUNT * 3 / G + 1;
         if (tile2 < NT) {
-            const uint8_t *pf = reinterpret_cast<const uint8_t *>(kv_in + (uint64_t)lb2 * BLK_STRIDE + (uint64_t)tile2 * STILE) + threadIdx.x * 128;
+            const uint8_t *pf = reinterpret_cast<const uint8_t *>(kv_in + (uint64_t)lb * BLK_STRIDE + (uint64_t)tile2 * STILE) + threadIdx.x * 128;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
         }
     }
-    const uint32_t lbit = 1u << l, ltmask = lbit - 1;
-    // match.any is cheap when the warp holds few distinct digits (the upper passes of text: the records
-    // arrive sorted by the lower digits and neighbours share their context), the mask table when it holds
-    // many.  One probe per warp and tile: equal neighbours among the first 32 records.
-    bool use_match;
-    {
-        uint32_t d0 = (okmask & 1u) ? ((uint32_t)(kv[0] >> rshift) & (NBINS - 1)) : 0x10000u + l;
-        uint32_t dn = __shfl_down_sync(0xffffffffu, d0, 1);
-        use_match = __popc(__ballot_sync(0xffffffffu, l < 31 && d0 == dn)) >= 16;
-    }
-    if (use_match) {
-#pragma unroll
-        for (int r = 0; r < SI; r++) {
-            bool ok = (okmask >> r) & 1u;
-            uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (NBINS - 1)) : 0xffffffffu;
-            unsigned peers = __match_any_sync(0xffffffffu, d);
-            unsigned lt = peers & ltmask;
-            uint32_t bb = ok ? mycnt[d] : 0u;
-            __syncwarp();
-            if (ok && lt == 0) mycnt[d] = (uint16_t)(bb + __popc(peers));
-            __syncwarp();
-            rnk[r] = (uint16_t)(bb + __popc(lt));
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < SI; r++) {
-            bool ok = (okmask >> r) & 1u;
-            uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
-            if (ok) atomicOr(&M[d], lbit);
-            __syncwarp();
-            uint32_t peers = ok ? M[d] : 0u;
-            uint32_t bb = ok ? mycnt[d] : 0u;
-            __syncwarp();
-            uint32_t lt = peers & ltmask;
-            if (ok && lt == 0) { mycnt[d] = (uint16_t)(bb + __popc(peers)); M[d] = 0; }
-            __syncwarp();
-            rnk[r] = (uint16_t)(bb + __popc(lt));
-        }
-    }
-    __syncthreads();
-    // per digit: exclusive prefix over warps, tile total
     constexpr int DPT = NBINS / ST;
     uint32_t tot4[DPT];
     uint32_t mysum = 0;
+    if (!STABLE) {
 #pragma unroll
-    for (int q = 0; q < DPT; q++) {
-        int d = threadIdx.x * DPT + q;
-        uint32_t run = 0;
+        for (int r = 0; r < SI; r++)
+            if (okmask & (1u << r)) rnk[r] = (uint16_t)atomicAdd(&tcnt[(uint32_t)(kv[r] >> rshift) & (NBINS - 1)], 1u);
+        __syncthreads();
 #pragma unroll
-        for (int ww = 0; ww < ST / 32; ww++) { uint32_t c = S.wcnt[ww * NBINS + d]; S.wcnt[ww * NBINS + d] = (uint16_t)run; run += c; }
-        tot4[q] = run; mysum += run;
+        for (int q = 0; q < DPT; q++) { tot4[q] = tcnt[threadIdx.x * DPT + q]; mysum += tot4[q]; }
+    } else {
+        const uint32_t lbit = 1u << l, ltmask = lbit - 1;
+        // match.any is cheap when the warp holds few distinct digits (the upper passes of text: the records
+        // arrive sorted by the lower digits and neighbours share their context), the mask table when it holds
+        // many.  One probe per warp and tile: equal neighbours among the first 32 records.
+        bool use_match;
+        {
+            uint32_t d0 = (okmask & 1u) ? ((uint32_t)(kv[0] >> rshift) & (NBINS - 1)) : 0x10000u + l;
+            uint32_t dn = __shfl_down_sync(0xffffffffu, d0, 1);
+            use_match = __popc(__ballot_sync(0xffffffffu, l < 31 && d0 == dn)) >= 16;
+        }
+        if (use_match) {
+#pragma unroll
+            for (int r = 0; r < SI; r++) {
+                bool ok = (okmask >> r) & 1u;
+                uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (NBINS - 1)) : 0xffffffffu;
+                unsigned peers = __match_any_sync(0xffffffffu, d);
+                unsigned lt = peers & ltmask;
+                uint32_t bb = ok ? mycnt[d] : 0u;
+                __syncwarp();
+                if (ok && lt == 0) mycnt[d] = (uint16_t)(bb + __popc(peers));
+                __syncwarp();
+                rnk[r] = (uint16_t)(bb + __popc(lt));
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < SI; r++) {
+                bool ok = (okmask >> r) & 1u;
+                uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
+                if (ok) atomicOr(&M[d], lbit);
+                __syncwarp();
+                uint32_t peers = ok ? M[d] : 0u;
+                uint32_t bb = ok ? mycnt[d] : 0u;
+                __syncwarp();
+                uint32_t lt = peers & ltmask;
+                if (ok && lt == 0) { mycnt[d] = (uint16_t)(bb + __popc(peers)); M[d] = 0; }
+                __syncwarp();
+                rnk[r] = (uint16_t)(bb + __popc(lt));
+            }
+        }
+        __syncthreads();
+        // per digit: exclusive prefix over warps, tile total
+#pragma unroll
+        for (int q = 0; q < DPT; q++) {
+            int d = threadIdx.x * DPT + q;
+            uint32_t run = 0;
+#pragma unroll
+            for (int ww = 0; ww < ST / 32; ww++) { uint32_t c = S.wcnt[ww * NBINS + d]; S.wcnt[ww * NBINS + d] = (uint16_t)run; run += c; }
+            tot4[q] = run; mysum += run;
+        }
     }
     // publish the tile's counts, look back for the exclusive prefix over earlier tiles, publish the inclusive prefix
     static_assert(DPT == 4, "status words are moved as uint4");
@@ -496,7 +522,7 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
     for (int r = 0; r < SI; r++) {
         if (okmask & (1u << r)) {
             uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
-            S.stage[S.tbase[d] + mycnt[d] + rnk[r]] = kv[r];
+            S.stage[S.tbase[d] + (STABLE ? (uint32_t)mycnt[d] : 0u) + rnk[r]] = kv[r];
         }
     }
     __syncthreads();
@@ -1221,7 +1247,8 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_group_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KeysSmem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         attr_done = true;
     }
     const uint32_t *no_act = nullptr;
@@ -1229,10 +1256,10 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     uint32_t *no_out = nullptr;
     uint64_t *no_save = nullptr;
     // ---- init: order by the first k symbols (40-bit key, four 10-bit onesweep passes; records end up in kv0) ----
-    S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * NPASS * NBINS * 4 + 64));
+    S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * NPASS * (NBINS + 1) * 4));
     uint32_t *ghist = ctx->bwt_ghist.as<uint32_t>();
-    uint32_t *tickets = ghist + (size_t)nb * NPASS * NBINS;
-    S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * NPASS * NBINS * 4 + 64, ctx->stream));
+    uint32_t *tickets = ghist + (size_t)nb * NPASS * NBINS;      // [NPASS][nb]
+    S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * NPASS * (NBINS + 1) * 4, ctx->stream));
     // look-back status words carry a generation tag; the table is cleared only when it is new, was used
     // by the doubling rounds (as a histogram table) or the tag wraps
     if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS > 255) {
@@ -1244,10 +1271,17 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), NBINS, 0, ghist);
     {
         uint64_t *src = P.kv0, *dst = P.kv1;
+        uint32_t G = SWEEP_G;
+        if (const char *e = getenv("S3G_SWEEP_G")) { int v = atoi(e); if (v > 0) G = (uint32_t)v; }
+        const unsigned sweep_grid = (unsigned)((nb + G - 1) / G) * G * NT;
         for (int pass = 0; pass < NPASS; pass++) {
             S3G_BYTES(ctx, 16 * N);
-            S3G_LAUNCH(ctx, k_sweep, NT * (unsigned)nb, ST, sizeof(ScatterSmem), P, VAL_BITS + 10 * pass, src, dst, ghist, pass, tickets + pass,
-                       (uint32_t)nb, ++ctx->sweep_gen);
+            if (pass == 0)
+                S3G_LAUNCH(ctx, k_sweep<false>, sweep_grid, ST, sizeof(ScatterSmem), P, VAL_BITS, src, dst, ghist, pass, tickets + (size_t)pass * nb,
+                           (uint32_t)nb, ++ctx->sweep_gen, G);
+            else
+                S3G_LAUNCH(ctx, k_sweep<true>, sweep_grid, ST, sizeof(ScatterSmem), P, VAL_BITS + 10 * pass, src, dst, ghist, pass, tickets + (size_t)pass * nb,
+                           (uint32_t)nb, ++ctx->sweep_gen, G);
             std::swap(src, dst);
         }
         static_assert(NPASS % 2 == 0, "an even number of passes leaves the sorted records in kv0");
