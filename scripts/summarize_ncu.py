@@ -21,6 +21,9 @@ def short(name):
     m = re.match(r"(k_hist|k_scatter)<(\d)>$", name)
     if m:
         return f"{m.group(1)}<{MODES[m.group(2)]}>"
+    m = re.match(r"(k_sweep)<\(bool\)([01])>$", name) or re.match(r"(k_sweep)<([01])>$", name)
+    if m:
+        return f"{m.group(1)}<{'true' if m.group(2) == '1' else 'false'}>"
     m = re.match(r"(k_bound_\w+)<([01])>$", name)
     if m:
         return f"{m.group(1)}<{'true' if m.group(2) == '1' else 'false'}>"

@@ -44,6 +44,7 @@ struct BwtP {
     unsigned long long *g_act; // [2] batch totals
     uint32_t *init_k;          // [nb] symbols in the initial key
     uint32_t *init_k32;        // [nb] symbols in the 32-bit per-position key the group finisher compares (<= init_k)
+    uint32_t *init_f;          // [nb] classes of the symbol after the k-th that still fit below 2^40 (floor(2^40 / a^k) >= 1)
     uint32_t *init_a;          // [nb] alphabet size
     uint32_t *left;            // [nb] rotations the group finisher left unsorted (blocks that need doubling rounds)
 };
@@ -263,6 +264,7 @@ struct KeysSmem {
     uint32_t hist[NPASS][NBINS];
     __align__(16) uint8_t sym[STILE + 64];
     uint8_t seq[256];
+    uint8_t frac[256];
 };
 
 __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t *ghist)
@@ -274,9 +276,10 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t
     const uint32_t t0 = blockIdx.x * KT;
     if ((uint64_t)t0 * STILE >= n) return;
     const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
-    const uint32_t k = P.init_k[lb], k32 = P.init_k32[lb], a = P.init_a[lb];
+    const uint32_t k = P.init_k[lb], k32 = P.init_k32[lb], a = P.init_a[lb], f = P.init_f[lb];
     for (int i = tid; i < NPASS * NBINS; i += ST) (&S.hist[0][0])[i] = 0;
     S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
+    S.frac[tid] = (uint8_t)(tid < a ? tid * f / a : 0);      // class of a symbol rank, monotone
     uint64_t pw = 1; uint32_t pw32 = 1;                      // a^(k-1), a^(k32-1)
     for (uint32_t i = 1; i < k; i++) pw *= a;
     for (uint32_t i = 1; i < k32; i++) pw32 *= a;
@@ -297,14 +300,14 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t
                             (uint32_t)S.seq[wv[j] >> 24] << 24;
                 *reinterpret_cast<uint4 *>(S.sym + i0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             } else {
-                for (uint32_t i = i0; i < i0 + 16 && i < cntT + k; i++) {
+                for (uint32_t i = i0; i < i0 + 16 && i < cntT + k + 1; i++) {
                     uint32_t q = base + i;
                     if (q >= n) { q -= n; if (q >= n) q %= n; }
                     S.sym[i] = S.seq[b[q]];
                 }
             }
             // the k symbols past the tile (cyclic)
-            for (uint32_t i = STILE + tid; i < cntT + k; i += ST) {
+            for (uint32_t i = STILE + tid; i < cntT + k + 1; i += ST) {
                 uint32_t q = base + i;
                 if (q >= n) { q -= n; if (q >= n) q %= n; }
                 S.sym[i] = S.seq[b[q]];
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t
             for (int r = 0; r < SI; r++) {
                 uint32_t p = p0 + r;
                 if (p < cntT) {
-                    uint64_t rec = (key << VAL_BITS) | (base + p);
+                    uint64_t rec = ((key * f + S.frac[S.sym[p + k]]) << VAL_BITS) | (base + p);
                     S.stage[p + (p >> 4)] = rec;
                     S.stage32[p + (p >> 4)] = key32;
 #pragma unroll
@@ -1046,7 +1049,13 @@ __global__ void k_bwt_setup(BwtP P, uint32_t nb)
         uint64_t pw = a;
         while (pw * a <= (1ull << KEY_BITS)) { pw *= a; k++; if (pw <= 0xffffffffull) k32 = k; }
     }
-    P.cnt_n[lb] = n; P.init_k[lb] = k; P.init_k32[lb] = k32; P.init_a[lb] = a;
+    // the room left above a^k is given to a coarse, order-preserving class of the NEXT symbol: key = key_k * f + floor(s_k * f / a)
+    uint64_t pwk = 1;
+    for (uint32_t i = 0; i < k; i++) pwk *= a;
+    uint64_t f = (1ull << KEY_BITS) / pwk;
+    if (f > a) f = a;
+    if (f < 1) f = 1;
+    P.cnt_n[lb] = n; P.init_k[lb] = k; P.init_k32[lb] = k32; P.init_a[lb] = a; P.init_f[lb] = (uint32_t)f;
     P.act[lb] = 0; P.act[nb + lb] = 0; P.left[lb] = 0;
 }
 
@@ -1216,7 +1225,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->kv0.ensure(slots * 8));
     S3G_TRY(ctx->kv1.ensure(slots * 8));
     S3G_TRY(ctx->hist.ensure((size_t)nb * NBINS * NT * 4));
-    S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (8 * 4 + NT * 2 * 4) + 64));
+    S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (9 * 4 + NT * 2 * 4) + 64));
     S3G_TRY(ctx->lcol.ensure(slots));
     BwtP P;
     P.blk = ctx->blk_bytes.as<uint8_t>() + b0 * (uint64_t)BLK_STRIDE;
@@ -1234,6 +1243,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.init_a = misc; misc += nb;
     P.left = misc; misc += nb;
     P.init_k32 = misc; misc += nb;
+    P.init_f = misc; misc += nb;
     P.agg = misc;
     S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 16, ctx->stream));
     S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);

@@ -147,6 +147,40 @@ def test_bwt_batch(ctx, oracle):
         assert orig == oorig, name
 
 
+def _finisher_blocks():
+    """Blocks aimed at the group finisher (bwt.cu): groups at and just past the size it sorts in shared
+    memory (2048), ties that need several deeper levels, ties that outlast them (doubling rounds), a
+    group spilling over tile boundaries, and a large block of long repeated fields."""
+    rng = np.random.default_rng(11)
+    ctx9 = b"ABCDEFGHIJKL"                                    # longer than any initial key of a 30-symbol alphabet
+    def tagged(count, width, filler=3000):
+        # `count` occurrences of the same context, each followed by a distinct number, in random filler
+        parts = [bytes(rng.integers(97, 123, filler, dtype=np.uint8))]
+        for i in rng.permutation(count):
+            parts.append(ctx9 + (b"%0*d" % (width, int(i))) + bytes(rng.integers(97, 123, 5, dtype=np.uint8)))
+        return b"".join(parts)
+    yield "group2048", tagged(2048, 6)
+    yield "group2049", tagged(2049, 6)
+    yield "group5000", tagged(5000, 6)
+    # equal for 40 symbols after the context: level 0 ties, deeper levels resolve
+    yield "deep_ties", b"".join(ctx9 + b"x" * 40 + (b"%05d" % int(i)) + b"\n" for i in rng.permutation(700))
+    # equal for 300 symbols: the levels give up, the doubling rounds finish
+    yield "very_deep_ties", b"".join(ctx9 + b"y" * 300 + (b"%04d" % int(i)) + b"\n" for i in rng.permutation(60))
+    # long constant fields on every line of a big block (a BED file with a repeated annotation)
+    lines = [b"%d\tENSG%011d\tprotein_coding\tKNOWN\t+\n" % (int(rng.integers(1, 500)), int(rng.integers(0, 10**9))) for _ in range(16000)]
+    yield "annotated", b"".join(lines)[:899000]
+    yield "two_symbols", bytes(rng.integers(0, 2, 120000, dtype=np.uint8) + 48)
+    yield "all_bytes_big", bytes(rng.integers(0, 256, 300000, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("name,blk", list(_finisher_blocks()), ids=[n for n, _ in _finisher_blocks()])
+def test_bwt_finisher_limits_and_fallback(ctx, oracle, name, blk):
+    (ptr, orig), = ctx.bwt([blk])
+    optr, oorig = oracle.bwt(blk)
+    assert orig == oorig, name
+    assert np.array_equal(ptr, optr), name
+
+
 def test_bwt_full_block_vs_reference(ctx, oracle):
     tf, _, _ = oracle.transform(synth.bed(1, 250000))
     blocks, rle = oracle.rle1_blocks(tf, 9)
