@@ -51,7 +51,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -269,7 +269,7 @@ def run_b200(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_share_of_step": table[top_name][1] / tot_kernel_ms, "launches": top_n,
                          "avg_launch_ms": top_ms / top_n if top_n else None, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "note": "radix passes of the block sort keep each block's 7 MB working set in the 126 MB L2, so DRAM traffic can be below the algorithmic bytes",
+                         "note": "algorithmic bytes per launch are accounted inside the library (S3G_BYTES, DESIGN.md section 4); traffic = ncu dram bytes per launch from profiles/ncu_traffic.json",
                          "pipeline": {"algorithmic_bytes_per_step": a_total, "achieved": a_total / (ms_per_step / 1000.0) / 1e9,
                                       "frac": a_total / (ms_per_step / 1000.0) / 1e9 / peak}},
             "kernels_note": "one step (the last warm-up step) with events around every launch",
