@@ -18,22 +18,24 @@ for spec in sys.argv[1:]:
     for _ in range(2):
         res = ctx.compress_bed_device(d.data_ptr(), d.numel(), 9, want_archive=False)
     torch.cuda.synchronize()
-    ctx.profile(True)
     t0 = time.perf_counter()
     res = ctx.compress_bed_device(d.data_ptr(), d.numel(), 9, want_archive=False)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
+    dev_ms = res.device_ms
+    ctx.profile(True)
+    res = ctx.compress_bed_device(d.data_ptr(), d.numel(), 9, want_archive=False)
     prof = ctx.profile_report(); ctx.profile(False)
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]
     # check: every stream decodes; total decoded size equals the transformed size
     z = ctx.read_streams(res.streams_size)
     tot = 0
     for c in res.chroms:
-        tot += len(bz2.decompress(z[c["bz_off"]:c["bz_off"] + c["bz_len"]])) if lines <= 20_000_000 else c["tf_len"]
+        tot += len(bz2.decompress(z[c["bz_off"]:c["bz_off"] + c["bz_len"]])) if lines <= 120_000_000 else c["tf_len"]
     ok = tot == res.tf_bytes
     print(json.dumps({"cfg": cfg, "variant": variant, "lines": lines, "in_mb": round(bed.nbytes / 1e6, 1), "tf_mb": round(res.tf_bytes / 1e6, 1),
-                      "blocks": res.n_blocks, "out_mb": round(res.streams_size / 1e6, 1), "device_ms": round(res.device_ms, 2),
-                      "wall_ms": round(wall, 2), "GBps_in": round(bed.nbytes / 1e6 / res.device_ms, 2), "decodes": ok,
+                      "blocks": res.n_blocks, "out_mb": round(res.streams_size / 1e6, 1), "device_ms": round(dev_ms, 2),
+                      "wall_ms": round(wall, 2), "GBps_in": round(bed.nbytes / 1e6 / dev_ms, 2), "decodes": ok,
                       "top": {k: round(v[1], 2) for k, v in top}}), flush=True)
     del d
 ctx.close()

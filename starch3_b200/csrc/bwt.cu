@@ -1187,6 +1187,7 @@ __global__ void k_fallback_exact(BwtP P, BlockInfo *blocks)
             st.ec[k] = (uint32_t)j;
         }
         int notdone = 0, r = -1;
+        bool refined = false;
         for (;;) {
             int k = r + 1;
             while (FB_GET(k)) k++;
@@ -1201,12 +1202,16 @@ __global__ void k_fallback_exact(BwtP P, BlockInfo *blocks)
                 int32_t cc = -1;
                 for (int i = l; i <= r; i++) {
                     int32_t c1 = (int32_t)st.ec[st.fmap[i]];
-                    if (cc != c1) { FB_SET(i); cc = c1; }
+                    if (cc != c1) { if (i > l) refined = true; FB_SET(i); cc = c1; }
                 }
             }
         }
         H *= 2;
         if (H > n || notdone == 0) break;
+        // A round that splits no bucket is a fixed point of the doubling (every bucket's keys are equal, and
+        // fallbackQSort3 / fallbackSimpleSort leave all-equal ranges untouched: bz/blocksort.c:32-61, :93-180),
+        // so the remaining rounds of the reference change nothing.  Periodic blocks get here after few rounds.
+        if (!refined) break;
     }
     int32_t orig = -1;
     for (int i = 0; i < n; i++) if (st.fmap[i] == 0) { orig = i; break; }

@@ -130,6 +130,7 @@ __device__ __forceinline__ void mtf_zero_runs(const uint8_t *M, uint16_t *mtfv, 
 // starts with is the symbols ordered by their last occurrence before the chunk.
 // =============================================================================
 constexpr int MS = 512;                 // chunks (threads) per block
+constexpr int MTF_REG_MAX = 96;         // largest alphabet of the register-list kernel (12 list words; 96 x 512 x 4 B of shared memory)
 
 template <int NW>
 __device__ __forceinline__ uint32_t mtf_step(uint64_t (&lst)[NW], uint32_t s)
@@ -191,13 +192,13 @@ __global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *
                                                   BlockInfo *blocks, int rows)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *s_last = reinterpret_cast<int *>(smem_raw);            // [rows][MS], rows = largest alphabet (<= 32) in the batch
+    int *s_last = reinterpret_cast<int *>(smem_raw);            // [rows][MS], rows = largest alphabet (<= MTF_REG_MAX) in the batch
     int *s_freq = s_last + rows * MS;                           // [258]
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_freq + 260);
     const uint32_t lb = blockIdx.x;
     const int n = (int)blocks[lb].nblock;
     const int a = (int)blocks[lb].n_in_use;
-    if (a > 32) return;                                         // handled by k_mtf
+    if (a > MTF_REG_MAX) return;                                // handled by k_mtf
     if (a > rows) __trap();                                     // host mirror out of date: fail loudly
     const uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
     uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
@@ -236,7 +237,15 @@ __global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *
             case 1: mtf_thread_chunk<1>(L, M, beg, end, s_last, a); break;
             case 2: mtf_thread_chunk<2>(L, M, beg, end, s_last, a); break;
             case 3: mtf_thread_chunk<3>(L, M, beg, end, s_last, a); break;
-            default: mtf_thread_chunk<4>(L, M, beg, end, s_last, a); break;
+            case 4: mtf_thread_chunk<4>(L, M, beg, end, s_last, a); break;
+            case 5: mtf_thread_chunk<5>(L, M, beg, end, s_last, a); break;
+            case 6: mtf_thread_chunk<6>(L, M, beg, end, s_last, a); break;
+            case 7: mtf_thread_chunk<7>(L, M, beg, end, s_last, a); break;
+            case 8: mtf_thread_chunk<8>(L, M, beg, end, s_last, a); break;
+            case 9: mtf_thread_chunk<9>(L, M, beg, end, s_last, a); break;
+            case 10: mtf_thread_chunk<10>(L, M, beg, end, s_last, a); break;
+            case 11: mtf_thread_chunk<11>(L, M, beg, end, s_last, a); break;
+            default: mtf_thread_chunk<12>(L, M, beg, end, s_last, a); break;
         }
     }
     __threadfence_block();
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, 
     const uint32_t lb = blockIdx.x;
     const int n = (int)blocks[lb].nblock;
     const int a = (int)blocks[lb].n_in_use;
-    if (a <= 32) return;                                        // handled by k_mtf_small
+    if (a <= MTF_REG_MAX) return;                               // handled by k_mtf_small
     const uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
     uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
     uint16_t *mtfv = mtfv_all + (uint64_t)lb * BLK_STRIDE;
@@ -318,20 +327,20 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->mtf0.ensure(slots));                 // MTF ranks before zero-run coding
     S3G_TRY(ctx->mtfv16.ensure(slots * 2));
     S3G_TRY(ctx->mtf_freq.ensure((size_t)nb * 258 * 4));
-    // alphabets of <= 32 symbols take the register-list kernel, larger ones the warp-cooperative one
+    // alphabets of <= MTF_REG_MAX symbols take the register-list kernel, larger ones the warp-cooperative one
     double N = 0;
     int rows = 1;
     for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) {
         N += ctx->h_blocks[b0 + b].nblock;
         int a = (int)ctx->h_blocks[b0 + b].n_in_use;
-        if (a <= 32 && a > rows) rows = a;
-        if (a == 0) rows = 32;                        // alphabet not mirrored on the host: size for the worst case
+        if (a <= MTF_REG_MAX && a > rows) rows = a;
+        if (a == 0) rows = MTF_REG_MAX;                        // alphabet not mirrored on the host: size for the worst case
     }
-    if (ctx->h_blocks.size() < b0 + nb) rows = 32;
+    if (ctx->h_blocks.size() < b0 + nb) rows = MTF_REG_MAX;
     const size_t small_smem = (size_t)rows * MS * 4 + 260 * 4 + 40 * 4;
     static bool attr_done = false;
     if (!attr_done) {
-        S3G_CUDA(cudaFuncSetAttribute(k_mtf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)32 * MS * 4 + 260 * 4 + 40 * 4)));
+        S3G_CUDA(cudaFuncSetAttribute(k_mtf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MTF_REG_MAX * MS * 4 + 260 * 4 + 40 * 4)));
         attr_done = true;
     }
     S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
