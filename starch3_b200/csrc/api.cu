@@ -3,6 +3,9 @@
 // few-hundred-byte archive header (ARCHIVE_FORMAT.md).
 #include <cstdarg>
 #include <ctime>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <algorithm>
 #include <new>
 #include "common.cuh"
@@ -199,6 +202,102 @@ __global__ void k_gather_names(const uint8_t *bed, const s3g_chrom *chroms, uint
     for (uint32_t i = threadIdx.x; i < chroms[c].name_len; i += blockDim.x) dst[dst_off[c] + i] = bed[chroms[c].name_off + i];
 }
 
+// ---- one range of the input: [off, off + len) of the device buffer d_bed --------------------------
+// A range starts at the first line of a chromosome.  Unless it is the last range of the input, its
+// last chromosome may continue in the bytes that follow, so it is left to the next range
+// (PartOut.cs_next = where it starts).
+struct PartOut {
+    std::vector<s3g_chrom> chroms;     // the chromosomes compressed here; name_off absolute, bz_off relative to this part's streams
+    std::vector<uint8_t> names;        // their names, back to back
+    uint64_t n_seen = 0;               // chromosomes found in the range
+    uint64_t cs_next = 0;              // absolute offset of the chromosome left for the next range
+    uint64_t streams_size = 0, n_blocks = 0, dropped = 0, tf_kept = 0;
+};
+
+// tokenise + transform the range; decides how many chromosomes are compressed here
+static int part_front(Ctx *ctx, const uint8_t *d_bed, uint64_t off, uint64_t len, bool last_part, PartOut &po, TfResult &tr)
+{
+    const uint64_t base = off & ~(uint64_t)15;                 // the tokenizer loads 16-byte vectors
+    const bool timing = getenv("S3G_TIMING") != nullptr;
+    double tt0 = timing ? host_ms() : 0;
+    S3G_TRY(run_transform(ctx, d_bed + base, len + (off - base), &tr, false, (uint32_t)(off - base)));
+    if (timing) fprintf(stderr, "[s3g timing] transform %.2f ms (host clock)\n", host_ms() - tt0);
+    po.n_seen = tr.n_chroms;
+    po.dropped = tr.dropped;
+    ctx->h_chroms.resize(tr.n_chroms);
+    if (tr.n_chroms) {
+        S3G_CUDA(cudaMemcpyAsync(ctx->h_chroms.data(), ctx->chroms.p, tr.n_chroms * sizeof(s3g_chrom), cudaMemcpyDeviceToHost, ctx->stream));
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    const uint64_t kept = last_part ? tr.n_chroms : (tr.n_chroms ? tr.n_chroms - 1 : 0);
+    po.cs_next = (!last_part && tr.n_chroms) ? base + ctx->h_chroms[tr.n_chroms - 1].name_off : off + len;
+    po.tf_kept = kept == tr.n_chroms ? tr.tf_len : ctx->h_chroms[kept].tf_off;
+    po.chroms.assign(ctx->h_chroms.begin(), ctx->h_chroms.begin() + kept);
+    return S3G_OK;
+}
+
+// RLE1 .. bit assembly for the chromosomes kept by part_front; stream table and names back to the host
+static int part_back(Ctx *ctx, const uint8_t *d_bed, uint64_t off, int level, bool want_names, PartOut &po)
+{
+    const uint64_t base = off & ~(uint64_t)15;
+    const uint64_t kept = po.chroms.size();
+    uint64_t total_bytes = 0, n_blocks = 0;
+    if (kept) {
+        S3G_TRY(ctx->soff.ensure((kept + 2) * 8));
+        S3G_LAUNCH(ctx, k_soff_from_chroms, (unsigned)((kept + 1 + 127) / 128), 128, 0, ctx->chroms.as<s3g_chrom>(),
+                   kept, po.tf_kept, ctx->soff.as<uint64_t>());
+        S3G_TRY(compress_streams(ctx, ctx->tf.as<uint8_t>(), po.tf_kept, ctx->soff.as<uint64_t>(), kept, level, &n_blocks,
+                                 &total_bytes));
+    }
+    S3G_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    po.n_blocks = n_blocks;
+    po.streams_size = total_bytes;
+    ctx->last_streams_size = total_bytes;
+    std::vector<StreamMeta> meta(kept);
+    std::vector<uint64_t> name_off(kept + 1, 0);
+    for (uint64_t c = 0; c < kept; c++) name_off[c + 1] = name_off[c] + po.chroms[c].name_len;
+    po.names.assign(name_off[kept] + 1, 0);
+    if (kept) {
+        S3G_CUDA(cudaMemcpyAsync(meta.data(), ctx->stream_meta.p, kept * sizeof(StreamMeta), cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_names) {
+            // chromosome names (a few bytes each) come back through one gather
+            S3G_TRY(ctx->io_a.ensure((kept + 1) * 8));
+            S3G_TRY(ctx->io_b.ensure(name_off[kept] + 16));
+            S3G_CUDA(cudaMemcpyAsync(ctx->io_a.p, name_off.data(), (kept + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            S3G_LAUNCH(ctx, k_gather_names, (unsigned)kept, 32, 0, d_bed + base, ctx->chroms.as<s3g_chrom>(), kept,
+                       ctx->io_a.as<uint64_t>(), ctx->io_b.as<uint8_t>());
+            S3G_CUDA(cudaMemcpyAsync(po.names.data(), ctx->io_b.p, name_off[kept], cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t c = 0; c < kept; c++) {
+        po.chroms[c].bz_off = meta[c].byte_off; po.chroms[c].bz_len = meta[c].byte_len;
+        po.chroms[c].n_blocks = (uint32_t)meta[c].n_blocks;
+        po.chroms[c].name_off += base;
+    }
+    return S3G_OK;
+}
+
+static int ensure_archive(Ctx *ctx, uint64_t bytes)
+{
+    if (bytes <= ctx->h_archive_cap) return S3G_OK;
+    uint8_t *p = nullptr;
+    size_t want = bytes + bytes / 8 + 4096;
+    if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+    if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
+    ctx->h_archive = p; ctx->h_archive_cap = want;
+    return S3G_OK;
+}
+
+static void fill_result(s3g_result *res, const std::vector<s3g_chrom> &chroms)
+{
+    res->n_chroms = chroms.size();
+    res->n_lines = 0; res->tf_bytes = 0;
+    for (const s3g_chrom &c : chroms) { res->n_lines += (uint64_t)c.line_count; res->tf_bytes += c.tf_len; }
+    res->chroms = (s3g_chrom *)malloc(std::max<size_t>(1, chroms.size()) * sizeof(s3g_chrom));
+    if (res->chroms && !chroms.empty()) memcpy(res->chroms, chroms.data(), chroms.size() * sizeof(s3g_chrom));
+}
+
 static int compress_bed_impl(Ctx *ctx, const uint8_t *d_bed, uint64_t n, int level, const char *note, int want_archive,
                              s3g_result *res)
 {
@@ -206,78 +305,211 @@ static int compress_bed_impl(Ctx *ctx, const uint8_t *d_bed, uint64_t n, int lev
     if (level < 1 || level > 9) { set_error("block_size_100k must be 1..9"); return S3G_E_PARAM; }
     S3G_CUDA(cudaSetDevice(ctx->device));
     S3G_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    PartOut po;
     TfResult tr;
-    double tt0 = getenv("S3G_TIMING") ? host_ms() : 0;
-    S3G_TRY(run_transform(ctx, d_bed, n, &tr, false));
-    if (getenv("S3G_TIMING")) fprintf(stderr, "[s3g timing] transform %.2f ms (host clock)\n", host_ms() - tt0);
-    res->n_lines = tr.n_lines; res->n_chroms = tr.n_chroms; res->tf_bytes = tr.tf_len; res->dropped_tail_bytes = tr.dropped;
-    uint64_t total_bytes = 0, n_blocks = 0;
-    if (tr.n_chroms) {
-        S3G_TRY(ctx->soff.ensure((tr.n_chroms + 2) * 8));
-        S3G_LAUNCH(ctx, k_soff_from_chroms, (unsigned)((tr.n_chroms + 1 + 127) / 128), 128, 0, ctx->chroms.as<s3g_chrom>(),
-                   tr.n_chroms, tr.tf_len, ctx->soff.as<uint64_t>());
-        S3G_TRY(compress_streams(ctx, ctx->tf.as<uint8_t>(), tr.tf_len, ctx->soff.as<uint64_t>(), tr.n_chroms, level, &n_blocks,
-                                 &total_bytes));
-    }
-    S3G_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    res->n_blocks = n_blocks;
-    res->d_streams = ctx->streams.p;
-    res->streams_size = total_bytes;
-    ctx->last_streams_size = total_bytes;
-    // ---- metadata back to the host ----
-    ctx->h_chroms.resize(tr.n_chroms);
-    std::vector<StreamMeta> meta(tr.n_chroms);
-    if (tr.n_chroms) {
-        S3G_CUDA(cudaMemcpyAsync(ctx->h_chroms.data(), ctx->chroms.p, tr.n_chroms * sizeof(s3g_chrom), cudaMemcpyDeviceToHost, ctx->stream));
-        S3G_CUDA(cudaMemcpyAsync(meta.data(), ctx->stream_meta.p, tr.n_chroms * sizeof(StreamMeta), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    S3G_TRY(part_front(ctx, d_bed, 0, n, true, po, tr));
+    S3G_TRY(part_back(ctx, d_bed, 0, level, want_archive != 0, po));
     float ms = 0;
     S3G_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     res->device_ms = ms;
-    for (uint64_t c = 0; c < tr.n_chroms; c++) {
-        ctx->h_chroms[c].bz_off = meta[c].byte_off; ctx->h_chroms[c].bz_len = meta[c].byte_len;
-        ctx->h_chroms[c].n_blocks = (uint32_t)meta[c].n_blocks;
-    }
-    res->chroms = (s3g_chrom *)malloc(std::max<size_t>(1, tr.n_chroms) * sizeof(s3g_chrom));
+    res->n_blocks = po.n_blocks;
+    res->d_streams = ctx->streams.p;
+    res->streams_size = po.streams_size;
+    res->dropped_tail_bytes = po.dropped;
+    ctx->h_chroms = po.chroms;
+    fill_result(res, po.chroms);
     if (!res->chroms) { set_error("out of host memory"); return S3G_E_NOMEM; }
-    if (tr.n_chroms) memcpy(res->chroms, ctx->h_chroms.data(), tr.n_chroms * sizeof(s3g_chrom));
+    res->n_lines = tr.n_lines; res->tf_bytes = tr.tf_len;
     if (!want_archive) return S3G_OK;
-    // chromosome names (a few bytes each) come back through one gather
-    std::vector<uint64_t> name_off(tr.n_chroms + 1, 0);
-    for (uint64_t c = 0; c < tr.n_chroms; c++) name_off[c + 1] = name_off[c] + ctx->h_chroms[c].name_len;
-    std::vector<uint8_t> names(name_off[tr.n_chroms] + 1);
-    if (tr.n_chroms) {
-        S3G_TRY(ctx->io_a.ensure((tr.n_chroms + 1) * 8));
-        S3G_TRY(ctx->io_b.ensure(name_off[tr.n_chroms] + 16));
-        S3G_CUDA(cudaMemcpyAsync(ctx->io_a.p, name_off.data(), (tr.n_chroms + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        S3G_LAUNCH(ctx, k_gather_names, (unsigned)tr.n_chroms, 32, 0, d_bed, ctx->chroms.as<s3g_chrom>(), tr.n_chroms,
-                   ctx->io_a.as<uint64_t>(), ctx->io_b.as<uint8_t>());
-        S3G_CUDA(cudaMemcpyAsync(names.data(), ctx->io_b.p, name_off[tr.n_chroms], cudaMemcpyDeviceToHost, ctx->stream));
-        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    std::string hdr = build_header(names.data(), name_off, ctx->h_chroms, level, note);
+    std::vector<uint64_t> name_off(po.chroms.size() + 1, 0);
+    for (size_t c = 0; c < po.chroms.size(); c++) name_off[c + 1] = name_off[c] + po.chroms[c].name_len;
+    std::string hdr = build_header(po.names.data(), name_off, po.chroms, level, note);
     uint64_t streams_off = 4 + hdr.size() + 1;
-    res->archive_size = streams_off + total_bytes;
+    res->archive_size = streams_off + po.streams_size;
     // the archive is assembled in context-owned pinned memory: the device-to-host copy of the
     // streams lands directly in its final place
-    if (res->archive_size > ctx->h_archive_cap) {
-        if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
-        ctx->h_archive = nullptr; ctx->h_archive_cap = 0;
-        size_t want = res->archive_size + res->archive_size / 8 + 4096;
-        if (cudaMallocHost(&ctx->h_archive, want) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
-        ctx->h_archive_cap = want;
-    }
+    S3G_TRY(ensure_archive(ctx, res->archive_size));
     res->archive = ctx->h_archive;
     static const uint8_t magic[4] = {0xca, 0x5c, 0xad, 0x1a};      // hpp:907-910
     memcpy(res->archive, magic, 4);
     memcpy(res->archive + 4, hdr.data(), hdr.size());
     res->archive[4 + hdr.size()] = '\n';
     res->streams_off = streams_off;
-    if (total_bytes) {
-        S3G_CUDA(cudaMemcpyAsync(res->archive + streams_off, ctx->streams.p, total_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (po.streams_size) {
+        S3G_CUDA(cudaMemcpyAsync(res->archive + streams_off, ctx->streams.p, po.streams_size, cudaMemcpyDeviceToHost, ctx->stream));
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    return S3G_OK;
+}
+
+// ---- pipelined host entry --------------------------------------------------------------------------
+// The upload of a large input takes a third as long as compressing it, so s3g_compress_bed cuts the input
+// into ranges at line starts, queues all uploads on a copy stream, and lets two worker contexts (own
+// stream, own buffers, own host thread) compress range after range as their bytes arrive.  A range
+// compresses the chromosomes that END inside it; the chromosome still open at its end is handed to the next
+// range, which starts over at that chromosome's first line (already on the device).  Chromosomes are
+// independent bzip2 streams, so the archive is the header plus the streams of the ranges in order -- the
+// same bytes as the one-shot path.  Transforms are serialised (each range needs the previous hand-over),
+// everything after the transform overlaps.
+constexpr uint64_t PIPE_MIN_BYTES = 48ull << 20;      // smaller inputs go through in one piece
+constexpr uint64_t HDR_RESERVE = 1ull << 20;          // the header is right-aligned in front of the streams
+
+struct PipeShared {
+    std::mutex mu;
+    std::condition_variable cv;
+    int next_front = 0;            // range whose transform may start
+    uint64_t cs = 0;               // where it starts
+    bool single_chrom = false;     // a range ended inside the chromosome it began with: stop cutting, the last range takes all
+    int next_copy = 0;             // range whose streams are copied out next
+    uint64_t streams_so_far = 0, archive_cap = 0;
+    int rc = S3G_OK;
+    std::string err;
+};
+
+static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::vector<uint64_t> &cut, int level,
+                        std::vector<PartOut> &parts, PipeShared &sh)
+{
+    cudaSetDevice(w->device);
+    const uint8_t *d_bed = main_ctx->bed.as<uint8_t>();
+    for (int i = wid; i < nparts; i += 2) {
+        const bool last = i == nparts - 1;
+        uint64_t off;
+        {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            sh.cv.wait(lk, [&] { return sh.next_front == i || sh.rc != S3G_OK; });
+            if (sh.rc != S3G_OK) return;
+            off = sh.cs;
+            if (sh.single_chrom && !last) {
+                // nothing to do for this range: pass both turns on
+                sh.next_front = i + 1;
+                sh.cv.notify_all();
+                sh.cv.wait(lk, [&] { return sh.next_copy == i || sh.rc != S3G_OK; });
+                if (sh.rc != S3G_OK) return;
+                sh.next_copy = i + 1;
+                sh.cv.notify_all();
+                continue;
+            }
+        }
+        int rc = S3G_OK;
+        TfResult tr;
+        PartOut &po = parts[i];
+        if (cudaStreamWaitEvent(w->stream, main_ctx->part_ev[i], 0) != cudaSuccess) rc = S3G_E_CUDA;
+        if (rc == S3G_OK) rc = part_front(w, d_bed, off, cut[i + 1] - off, last, po, tr);
+        {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            if (rc != S3G_OK) { sh.rc = rc; sh.err = g_err; sh.cv.notify_all(); return; }
+            if (!last && po.chroms.empty()) sh.single_chrom = true;
+            sh.cs = po.cs_next;
+            sh.next_front = i + 1;
+            sh.cv.notify_all();
+        }
+        rc = part_back(w, d_bed, off, level, true, po);
+        // streams of the ranges go out in order, straight into their place in the pinned archive
+        {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            if (rc != S3G_OK) { sh.rc = rc; sh.err = g_err; sh.cv.notify_all(); return; }
+            sh.cv.wait(lk, [&] { return sh.next_copy == i || sh.rc != S3G_OK; });
+            if (sh.rc != S3G_OK) return;
+            uint64_t at = HDR_RESERVE + sh.streams_so_far;
+            if (at + po.streams_size > sh.archive_cap) { sh.rc = S3G_E_CAPACITY; sh.err = "pinned archive buffer too small"; sh.cv.notify_all(); return; }
+            for (s3g_chrom &c : po.chroms) c.bz_off += sh.streams_so_far;
+            sh.streams_so_far += po.streams_size;
+            sh.next_copy = i + 1;
+            sh.cv.notify_all();
+            lk.unlock();
+            if (po.streams_size) {
+                if (cudaMemcpyAsync(main_ctx->h_archive + at, w->streams.p, po.streams_size, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(w->stream) != cudaSuccess) {
+                    std::unique_lock<std::mutex> lk2(sh.mu);
+                    sh.rc = S3G_E_CUDA; sh.err = "device-to-host copy of the streams failed"; sh.cv.notify_all();
+                    return;
+                }
+            }
+        }
+    }
+}
+
+static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int level, const char *note, int nparts, s3g_result *res)
+{
+    memset(res, 0, sizeof *res);
+    if (level < 1 || level > 9) { set_error("block_size_100k must be 1..9"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) S3G_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while ((int)ctx->part_ev.size() < nparts) {
+        cudaEvent_t e;
+        S3G_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->part_ev.push_back(e);
+    }
+    for (int k = 0; k < 2; k++)
+        if (!ctx->sub[k]) {
+            s3g_ctx *c = nullptr;
+            S3G_TRY(s3g_init(ctx->device, &c));
+            ctx->sub[k] = c;
+        }
+    // cut points: the line start at or after i * n / nparts
+    std::vector<uint64_t> cut(nparts + 1, n);
+    cut[0] = 0;
+    for (int i = 1; i < nparts; i++) {
+        uint64_t p = std::max<uint64_t>(cut[i - 1], n / nparts * i);
+        const void *nl = p < n ? memchr(bed + p, '\n', n - p) : nullptr;
+        cut[i] = nl ? (uint64_t)((const uint8_t *)nl - bed) + 1 : n;
+    }
+    S3G_TRY(ctx->bed.ensure(n + 64));
+    // the archive buffer must exist before the workers copy into it: the compressed size is not known yet,
+    // half of the input is generous for BED (the one-shot path takes over if it ever is not)
+    S3G_TRY(ensure_archive(ctx, HDR_RESERVE + std::max<uint64_t>(n / 2, ctx->last_streams_size + (ctx->last_streams_size >> 3)) + 4096));
+    cudaEvent_t t0 = ctx->ev0, t1 = ctx->ev1;
+    S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));
+    for (int i = 0; i < nparts; i++) {
+        if (cut[i + 1] > cut[i])
+            S3G_CUDA(cudaMemcpyAsync(ctx->bed.as<uint8_t>() + cut[i], bed + cut[i], cut[i + 1] - cut[i], cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (i == nparts - 1) S3G_CUDA(cudaMemsetAsync(ctx->bed.as<uint8_t>() + n, 0, 64, ctx->copy_stream));
+        S3G_CUDA(cudaEventRecord(ctx->part_ev[i], ctx->copy_stream));
+    }
+    std::vector<PartOut> parts(nparts);
+    PipeShared sh;
+    sh.archive_cap = ctx->h_archive_cap;
+    std::thread th0(pipe_worker, ctx, ctx->sub[0], 0, nparts, std::cref(cut), level, std::ref(parts), std::ref(sh));
+    std::thread th1(pipe_worker, ctx, ctx->sub[1], 1, nparts, std::cref(cut), level, std::ref(parts), std::ref(sh));
+    th0.join(); th1.join();
+    if (sh.rc == S3G_E_CAPACITY) return S3G_E_CAPACITY;       // caller falls back to the one-shot path
+    if (sh.rc != S3G_OK) { set_error("%s", sh.err.c_str()); return sh.rc; }
+    S3G_CUDA(cudaEventRecord(t1, ctx->sub[(nparts - 1) & 1]->stream));
+    S3G_CUDA(cudaEventSynchronize(t1));
+    float ms = 0;
+    S3G_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    res->device_ms = ms;                                       // first upload to last kernel
+    // merge
+    std::vector<s3g_chrom> chroms;
+    std::vector<uint8_t> names;
+    for (PartOut &po : parts) {
+        chroms.insert(chroms.end(), po.chroms.begin(), po.chroms.end());
+        if (!po.chroms.empty()) names.insert(names.end(), po.names.begin(), po.names.end() - 1);
+        res->n_blocks += po.n_blocks;
+    }
+    names.push_back(0);
+    { uint64_t t = 0; for (s3g_chrom &c : chroms) { c.tf_off = t; t += c.tf_len; } }    // as in one transformed buffer
+    res->dropped_tail_bytes = parts[nparts - 1].dropped;
+    for (int k = 0; k < 2; k++) { ctx->launches += ctx->sub[k]->launches; ctx->sub[k]->launches = 0; }
+    ctx->h_chroms = chroms;
+    fill_result(res, chroms);
+    if (!res->chroms) { set_error("out of host memory"); return S3G_E_NOMEM; }
+    std::vector<uint64_t> name_off(chroms.size() + 1, 0);
+    for (size_t c = 0; c < chroms.size(); c++) name_off[c + 1] = name_off[c] + chroms[c].name_len;
+    std::string hdr = build_header(names.data(), name_off, chroms, level, note);
+    const uint64_t streams_off = 4 + hdr.size() + 1;
+    if (streams_off > HDR_RESERVE) return S3G_E_CAPACITY;      // enormous chromosome table: one-shot path
+    uint8_t *arc = ctx->h_archive + HDR_RESERVE - streams_off;
+    static const uint8_t magic[4] = {0xca, 0x5c, 0xad, 0x1a};      // hpp:907-910
+    memcpy(arc, magic, 4);
+    memcpy(arc + 4, hdr.data(), hdr.size());
+    arc[4 + hdr.size()] = '\n';
+    res->archive = arc;
+    res->streams_off = streams_off;
+    res->streams_size = sh.streams_so_far;
+    res->archive_size = streams_off + sh.streams_so_far;
+    res->d_streams = nullptr;                                  // the streams of the ranges live in the worker contexts
+    ctx->last_streams_size = sh.streams_so_far;
     return S3G_OK;
 }
 
@@ -330,6 +562,9 @@ void s3g_destroy(s3g_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     size_t k; DevBuf *const *bl = all_bufs(ctx, &k);
     for (size_t i = 0; i < k; i++) bl[i]->release();
+    for (int k2 = 0; k2 < 2; k2++) if (ctx->sub[k2]) { s3g_destroy(static_cast<s3g_ctx *>(ctx->sub[k2])); ctx->sub[k2] = nullptr; }
+    for (cudaEvent_t e : ctx->part_ev) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -399,6 +634,13 @@ int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int level, co
 {
     if (!ctx || !res || (!bed && n)) { set_error("null argument"); return S3G_E_PARAM; }
     S3G_CUDA(cudaSetDevice(ctx->device));
+    int nparts = n >= PIPE_MIN_BYTES ? 4 : 1;
+    if (const char *e = getenv("S3G_PARTS")) { int v = atoi(e); if (v >= 1 && v <= 64) nparts = v; }
+    if (nparts > 1 && !ctx->prof) {
+        int rc = compress_bed_pipelined(ctx, bed, n, level, note, nparts, res);
+        if (rc != S3G_E_CAPACITY) return rc;
+        s3g_result_free(res);                                  // does not fit the pipelined buffers: one piece
+    }
     S3G_TRY(stage_in(ctx, ctx->bed, bed, n));
     return compress_bed_impl(ctx, ctx->bed.as<uint8_t>(), n, level, note, 1, res);
 }

@@ -106,6 +106,11 @@ struct Ctx {
     uint64_t last_streams_size = 0;
     uint8_t *h_archive = nullptr;          // pinned; holds the archive of the last compress call
     size_t h_archive_cap = 0;
+    // pipelined host entry (s3g_compress_bed on large inputs): upload stream, one event per input range,
+    // and two worker contexts that compress ranges while later ranges are still on their way
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> part_ev;
+    Ctx *sub[2] = {nullptr, nullptr};
     // per-kernel profiling (off by default)
     bool prof = false;
     std::string prof_filter;               // non-empty: only this kernel is timed
@@ -210,7 +215,8 @@ struct TfResult {
     uint64_t n_lines = 0, n_chroms = 0, tf_len = 0, dropped = 0;
 };
 // kernels (1)+(2); leaves ctx->tf (bytes), ctx->chroms (s3g_chrom[n_chroms]) and the per-line arrays on device
-int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only);
+// `skip` (< 16): leading bytes of d_bed that belong to the line before the range (see k_count_newlines)
+int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip = 0);
 
 struct CutResult {
     uint64_t n_blocks = 0;

@@ -43,7 +43,9 @@ __device__ __forceinline__ unsigned nl_mask16(const uint8_t *bed, uint64_t pos, 
     return m;
 }
 
-__global__ void __launch_bounds__(NL_THREADS) k_count_newlines(const uint8_t *bed, uint64_t n, uint64_t *tile_cnt)
+// `skip` (< 16): the first bytes of the buffer belong to the line before the range being processed (a range that
+// starts at an arbitrary line start is handed over with its base rounded down to 16 bytes); their newline is ignored.
+__global__ void __launch_bounds__(NL_THREADS) k_count_newlines(const uint8_t *bed, uint64_t n, uint64_t *tile_cnt, uint32_t skip)
 {
     __shared__ uint32_t sm[33];
     uint64_t tile0 = (uint64_t)blockIdx.x * NL_TILE;
@@ -51,7 +53,11 @@ __global__ void __launch_bounds__(NL_THREADS) k_count_newlines(const uint8_t *be
 #pragma unroll
     for (int it = 0; it < NL_ITERS; it++) {
         uint64_t pos = tile0 + (uint64_t)it * NL_SUB + (uint64_t)threadIdx.x * 16;
-        if (pos < n) c += __popc(nl_mask16(bed, pos, n));
+        if (pos < n) {
+            unsigned m = nl_mask16(bed, pos, n);
+            if (pos == 0) m &= 0xffffffffu << skip;
+            c += __popc(m);
+        }
     }
     uint32_t tot;
     block_excl_sum<uint32_t>(c, sm, &tot);
@@ -65,15 +71,16 @@ struct SumU64 {
 };
 
 __global__ void __launch_bounds__(NL_THREADS) k_line_starts(const uint8_t *bed, uint64_t n, const uint64_t *tile_base,
-                                                            uint64_t *line_start)
+                                                            uint64_t *line_start, uint32_t skip)
 {
     __shared__ uint32_t sm[33];
     uint64_t tile0 = (uint64_t)blockIdx.x * NL_TILE;
     uint64_t run = tile_base[blockIdx.x];
-    if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = skip;
     for (int it = 0; it < NL_ITERS; it++) {
         uint64_t pos = tile0 + (uint64_t)it * NL_SUB + (uint64_t)threadIdx.x * 16;
         unsigned m = pos < n ? nl_mask16(bed, pos, n) : 0;
+        if (pos == 0) m &= 0xffffffffu << skip;
         uint32_t tot;
         uint32_t ex = block_excl_sum<uint32_t>(__popc(m), sm, &tot);
         uint64_t idx = run + ex + 1;
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(WT_LINES) k_write_tf(const uint8_t *__restrict
     }
 }
 
-int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only)
+int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip)
 {
     *out = TfResult();
     uint64_t ntiles = (n + NL_TILE - 1) / NL_TILE;
@@ -309,7 +316,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_CUDA(cudaMemsetAsync(d_sc, 0, 64 * 8, ctx->stream));
     uint64_t *tile_cnt = ctx->tile_cnt.as<uint64_t>();
     S3G_BYTES(ctx, n);
-    S3G_LAUNCH(ctx, k_count_newlines, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt);
+    S3G_LAUNCH(ctx, k_count_newlines, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt, skip);
     S3G_LAUNCH(ctx, k_scan_agg<SumU64>, 1, SCAN_THREADS, 0, tile_cnt, ntiles, d_sc + 0);
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 8, cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -318,7 +325,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_TRY(ctx->line_start.ensure((n_lines + 1) * 8));
     uint64_t *line_start = ctx->line_start.as<uint64_t>();
     S3G_BYTES(ctx, n + 8 * n_lines);
-    S3G_LAUNCH(ctx, k_line_starts, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt, line_start);
+    S3G_LAUNCH(ctx, k_line_starts, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt, line_start, skip);
     if (n_lines == 0) {
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
         out->dropped = n;

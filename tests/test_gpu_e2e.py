@@ -142,3 +142,31 @@ def test_sharded_single_rank_gpu(ctx, oracle):
     bed = synth.bed(5, 30000).tobytes() + b"chr1\t5\t9\n"
     arc = shard.compress_sharded(bed, shard.gpu_compress_fn(ctx), 9, "s")
     assert arc == ctx.compress_bed(bed, 9, note="s").archive == oracle.archive(bed, 9, "s")
+
+
+@pytest.mark.parametrize("cfg,lines,parts", [(2, 60000, 2), (2, 60000, 4), (2, 60000, 7), (5, 50000, 3), (1, 40000, 4), (2, 30, 5), (4, 20000, 2)])
+def test_pipelined_host_entry_matches_one_shot(ctx, oracle, cfg, lines, parts, monkeypatch):
+    """s3g_compress_bed cuts large inputs into ranges that are uploaded and compressed in a pipeline
+    (api.cu, compress_bed_pipelined).  Forced here on small inputs: the archive must be the same bytes as
+    the one-shot path and as the oracle's, whether a chromosome spans several ranges (cfg 1, 4: all of
+    them) or ends inside one."""
+    bed = synth.bed(cfg, lines).tobytes()
+    monkeypatch.setenv("S3G_PARTS", "1")
+    one = ctx.compress_bed(bed, 9, note="p")
+    monkeypatch.setenv("S3G_PARTS", str(parts))
+    piped = ctx.compress_bed(bed, 9, note="p")
+    assert piped.archive == one.archive == oracle.archive(bed, 9, "p")
+    assert piped.n_lines == one.n_lines == lines and piped.n_blocks == one.n_blocks and piped.tf_bytes == one.tf_bytes
+    assert [(c["name"], c["line_count"], c["bz_off"], c["bz_len"], c["tf_off"], c["tf_len"]) for c in piped.chroms] == \
+           [(c["name"], c["line_count"], c["bz_off"], c["bz_len"], c["tf_off"], c["tf_len"]) for c in one.chroms]
+
+
+def test_pipelined_host_entry_edge_inputs(ctx, oracle, monkeypatch):
+    monkeypatch.setenv("S3G_PARTS", "3")
+    for bed in (b"", b"chr1\t1\t2\n", b"chr1\t1\t2\nchr2\t5\t9\tx\n", b"chr1\t1\t2\nchr1\t5\t9\nchr1\t7\t1",
+                b"chrA\t10\t20\n" * 3 + b"chrB\t1\t2\n" * 2 + b"chrA\t5\t6\n"):
+        res = ctx.compress_bed(bed, 9)
+        assert res.archive == oracle.archive(bed, 9, ""), bed
+    monkeypatch.setenv("S3G_PARTS", "2")
+    with pytest.raises(Exception):
+        ctx.compress_bed(b"chr1\t1\t2\n" * 50 + b"chr1\t5\n" + b"chr2\t1\t2\n" * 50, 9)
