@@ -446,11 +446,14 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
             S3G_TRY(s3g_init(ctx->device, &c));
             ctx->sub[k] = c;
         }
-    // cut points: the line start at or after i * n / nparts
+    // cut points at line starts; the first range is shorter than the others (nothing can run until it has arrived)
     std::vector<uint64_t> cut(nparts + 1, n);
     cut[0] = 0;
+    double first = 0.75 / nparts;
+    if (const char *e = getenv("S3G_FIRST")) { double v = atof(e); if (v > 0 && v < 1) first = v; }
     for (int i = 1; i < nparts; i++) {
-        uint64_t p = std::max<uint64_t>(cut[i - 1], n / nparts * i);
+        double frac = first + (1.0 - first) * (i - 1) / (nparts - 1);
+        uint64_t p = std::max<uint64_t>(cut[i - 1], (uint64_t)(frac * (double)n));
         const void *nl = p < n ? memchr(bed + p, '\n', n - p) : nullptr;
         cut[i] = nl ? (uint64_t)((const uint8_t *)nl - bed) + 1 : n;
     }
@@ -634,7 +637,7 @@ int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int level, co
 {
     if (!ctx || !res || (!bed && n)) { set_error("null argument"); return S3G_E_PARAM; }
     S3G_CUDA(cudaSetDevice(ctx->device));
-    int nparts = n >= PIPE_MIN_BYTES ? 4 : 1;
+    int nparts = n >= PIPE_MIN_BYTES ? 3 : 1;
     if (const char *e = getenv("S3G_PARTS")) { int v = atoi(e); if (v >= 1 && v <= 64) nparts = v; }
     if (nparts > 1 && !ctx->prof) {
         int rc = compress_bed_pipelined(ctx, bed, n, level, note, nparts, res);
