@@ -74,13 +74,13 @@ static size_t batch_bytes_per_block()
     return (size_t)BLK_STRIDE * (4 + 4 + 8 + 8 + 1 + 1 + 2) + (size_t)1024 * 220 * 4 + (size_t)BITS_WORDS * 4 + 258 * 4 + 4096;
 }
 
-static uint64_t pick_batch(uint64_t n_blocks)
+static uint64_t pick_batch(uint64_t n_blocks, double mem_frac = 0.85)
 {
     const char *env = getenv("S3G_BATCH");
     if (env && atoll(env) > 0) return std::min<uint64_t>(n_blocks, (uint64_t)atoll(env));
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = (size_t)8 << 30; }
-    uint64_t fit = (uint64_t)((double)fr * 0.85 / (double)batch_bytes_per_block());
+    uint64_t fit = (uint64_t)((double)fr * mem_frac / (double)batch_bytes_per_block());
     if (fit < 1) fit = 1;
     return std::min<uint64_t>(n_blocks, std::min<uint64_t>(fit, 1024));
 }
@@ -120,7 +120,7 @@ static int compress_streams(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uin
         // steady state: the buffers already hold this many blocks; cudaMemGetInfo is only asked when they must grow
         // (it takes anywhere from 0.1 to 20 ms on a shared host)
         uint64_t have = held / batch_bytes_per_block();
-        uint64_t batch = have >= nb && !getenv("S3G_BATCH") ? nb : pick_batch(nb);
+        uint64_t batch = have >= nb && !getenv("S3G_BATCH") ? nb : pick_batch(nb, ctx->mem_frac);
         if (have > batch) batch = std::min<uint64_t>(nb, have);
         for (uint64_t b0 = 0; b0 < nb; b0 += batch) {
             uint64_t cnt = std::min<uint64_t>(batch, nb - b0);
@@ -444,6 +444,7 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
         if (!ctx->sub[k]) {
             s3g_ctx *c = nullptr;
             S3G_TRY(s3g_init(ctx->device, &c));
+            c->mem_frac = 0.4;                      // two workers size their batches at the same time
             ctx->sub[k] = c;
         }
     // cut points at line starts; the first range is shorter than the others (nothing can run until it has arrived)

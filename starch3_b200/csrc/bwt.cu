@@ -1,24 +1,28 @@
 // bwt.cu -- kernel (3b): the block sort of bzip2 (BZ2_blockSort,
-// bz/blocksort.c:1031-1089) for a batch of blocks, as a GPU prefix-doubling
-// suffix sort over cyclic rotations.
+// bz/blocksort.c:1031-1089) for a batch of blocks: radix sort on a prefix key, groups finished in
+// shared memory, prefix doubling as the fallback.
 //
 // What must match the reference: ptr[0..n) = rotation starts in ascending
 // order of the n cyclic rotations of the block (bz/blocksort.c:347-469 compares
 // with wrap-around) and origPtr = the index of rotation 0 (:1083-1086).  Which
 // algorithm produces the order is free (bz/blocksort.c:1058-1061).
 //
-// Algorithm (per block, all blocks of a batch in the same launches):
-//   init   rank every rotation by its first k symbols, k = max{k : A^k <= 2^30},
-//          A = symbols in use, via a 3-pass LSD radix sort on a 30-bit key.
-//   round  given the order by the first h symbols (SA, grouped; RK[i] = SA
-//          position of the first member of i's group, bit 31 = group is a
-//          singleton), obtain the order by 2h symbols with the Manber-Myers
-//          observation: walking SA in order, j = SA[k]-h arrives in ascending
-//          RK[j+h]; a STABLE counting sort of those j by RK[j] therefore sorts
-//          every group by its second half.  RK[j] < 2^20, so that is again two
-//          10-bit radix passes -- over the still-unsorted rotations only.
-//   Rounds stop when every group is a singleton or h >= n (equal rotations:
-//   a periodic block; flagged in BlockInfo.tie).
+// Algorithm (all blocks of a batch in the same launches; DESIGN.md section 4, "The block sort"):
+//   keys     k_keys: 64-bit record (40-bit mixed-radix key of the first k symbols << 20 | rotation start),
+//            k = max{k : A^k <= 2^40}, A = symbols in use; the 32-bit key of every position; the digit
+//            histograms of all four radix passes.
+//   sort     k_sweep x 4: LSD radix passes, one kernel each (tile ranking, decoupled look-back).
+//   finish   k_group_finish: every group of equal keys (<= 2048 rotations) is ranked in shared memory on
+//            the 32-bit keys of the positions k, k+k32, ... further on -- bzip2's own "bucket, then compare
+//            strings" (bz/blocksort.c:751-1011) for blocks with short common prefixes.  Writes ptr[], the
+//            last column and origPtr.
+//   fallback what the finisher leaves (groups > 2048, ties deeper than its levels) goes through Manber-Myers
+//            prefix-doubling rounds: given the order by the first h symbols (SA, grouped; RK[i] = SA position
+//            of the first member of i's group, bit 31 = group is a singleton), walking SA in order,
+//            j = SA[k]-h arrives in ascending RK[j+h]; a STABLE counting sort of those j by RK[j] sorts every
+//            group by its second half (two 10-bit radix passes over the still-unsorted rotations).  Rounds
+//            stop when every group is a singleton or h >= n (equal rotations: a periodic block, flagged in
+//            BlockInfo.tie and resolved by k_fallback_exact).
 #include "common.cuh"
 
 namespace s3g {

@@ -111,6 +111,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> part_ev;
     Ctx *sub[2] = {nullptr, nullptr};
+    double mem_frac = 0.85;                // share of the free device memory a batch of blocks may take (worker contexts: less)
     // per-kernel profiling (off by default)
     bool prof = false;
     std::string prof_filter;               // non-empty: only this kernel is timed
