@@ -170,6 +170,9 @@ struct ScatterSmem {
     uint32_t tbase[NBINS];                 // offset of the digit inside the tile
     uint16_t wcnt[(ST / 32) * NBINS];      // per-warp digit counters -> exclusive warp offsets
     uint32_t scan[33];
+    // first pass only: the records are built from the block bytes on the fly
+    __align__(16) uint8_t sym[STILE + 64];
+    uint8_t seq[256], frac[256];
 };
 
 template <int MODE>
@@ -263,15 +266,14 @@ constexpr int NPASS = KEY_BITS / 10;
 constexpr uint32_t ST_INCL = 1u << 23, ST_AGG = 1u << 22, ST_VAL = 0x000fffffu;
 
 struct KeysSmem {
-    uint64_t stage[STILE + STILE / 16];      // records, skewed so that 16-consecutive-per-thread writes are conflict-free
-    uint32_t stage32[STILE + STILE / 16];
+    uint32_t stage32[STILE + STILE / 16];    // per-position keys, skewed so that 16-consecutive-per-thread writes are conflict-free
     uint32_t hist[NPASS][NBINS];
     __align__(16) uint8_t sym[STILE + 64];
     uint8_t seq[256];
     uint8_t frac[256];
 };
 
-__global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t *ghist)
+__global__ void __launch_bounds__(ST) k_keys(BwtP P, uint32_t *ghist)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeysSmem &S = *reinterpret_cast<KeysSmem *>(smem_raw);
@@ -287,7 +289,6 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t
     uint64_t pw = 1; uint32_t pw32 = 1;                      // a^(k-1), a^(k32-1)
     for (uint32_t i = 1; i < k; i++) pw *= a;
     for (uint32_t i = 1; i < k32; i++) pw32 *= a;
-    uint64_t *out = rec_out + (uint64_t)lb * BLK_STRIDE;
     uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
     for (uint32_t t = t0; t < t0 + KT && (uint64_t)t * STILE < n; t++) {
         const uint32_t base = t * STILE, cntT = min((uint32_t)STILE, n - base);
@@ -327,7 +328,6 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t
                 uint32_t p = p0 + r;
                 if (p < cntT) {
                     uint64_t rec = ((key * f + S.frac[S.sym[p + k]]) << VAL_BITS) | (base + p);
-                    S.stage[p + (p >> 4)] = rec;
                     S.stage32[p + (p >> 4)] = key32;
 #pragma unroll
                     for (int ps = 0; ps < NPASS; ps++) atomicAdd(&S.hist[ps][(uint32_t)(rec >> (VAL_BITS + 10 * ps)) & (NBINS - 1)], 1u);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint64_t *rec_out, uint32_t
             }
         }
         __syncthreads();
-        for (uint32_t p = tid; p < cntT; p += ST) { out[base + p] = S.stage[p + (p >> 4)]; rk[base + p] = S.stage32[p + (p >> 4)]; }
+        for (uint32_t p = tid; p < cntT; p += ST) rk[base + p] = S.stage32[p + (p >> 4)];
     }
     __syncthreads();
     uint32_t *gh = ghist + (uint64_t)lb * NPASS * NBINS;
@@ -401,13 +401,63 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
     uint64_t kv[SI];
     uint16_t rnk[SI];
     uint32_t okmask = 0;
+    if (!STABLE) {
+        // first pass: thread t builds the records of positions 16 t .. 16 t + 15 of the tile with a rolling key,
+        // exactly as k_keys did for the histograms (any record-to-thread mapping will do: no stability needed)
+        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        const uint32_t k = P.init_k[lb], a = P.init_a[lb], f = P.init_f[lb];
+        const uint32_t tbase0 = tile * STILE, cntT = min((uint32_t)STILE, cnt - tbase0), tid = threadIdx.x;
+        S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
+        S.frac[tid] = (uint8_t)(tid < a ? tid * f / a : 0);
+        __syncthreads();
+        {
+            const uint32_t i0 = tid * 16;
+            if (tbase0 + i0 + 16 <= cnt) {
+                uint4 v = *reinterpret_cast<const uint4 *>(b + tbase0 + i0);
+                uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int r = 0; r < SI; r++) {
-        uint32_t p = base + r * 32;
-        kv[r] = 0;
-        if (p < cnt) { kv[r] = in[p]; okmask |= 1u << r; }
+                for (int j = 0; j < 4; j++)
+                    wv[j] = (uint32_t)S.seq[wv[j] & 255] | (uint32_t)S.seq[(wv[j] >> 8) & 255] << 8 | (uint32_t)S.seq[(wv[j] >> 16) & 255] << 16 |
+                            (uint32_t)S.seq[wv[j] >> 24] << 24;
+                *reinterpret_cast<uint4 *>(S.sym + i0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            } else {
+                for (uint32_t i = i0; i < i0 + 16 && i < cntT + k + 1; i++) {
+                    uint32_t q = tbase0 + i;
+                    if (q >= cnt) { q -= cnt; if (q >= cnt) q %= cnt; }
+                    S.sym[i] = S.seq[b[q]];
+                }
+            }
+            for (uint32_t i = STILE + tid; i < cntT + k + 1; i += ST) {
+                uint32_t q = tbase0 + i;
+                if (q >= cnt) { q -= cnt; if (q >= cnt) q %= cnt; }
+                S.sym[i] = S.seq[b[q]];
+            }
+        }
+        __syncthreads();
+        uint64_t pw = 1;
+        for (uint32_t i = 1; i < k; i++) pw *= a;
+        const uint32_t p0 = tid * SI;
+        uint64_t key = 0;
+        if (p0 < cntT) for (uint32_t j = 0; j < k; j++) key = key * a + S.sym[p0 + j];
+#pragma unroll
+        for (int r = 0; r < SI; r++) {
+            uint32_t p = p0 + r;
+            kv[r] = 0;
+            if (p < cntT) {
+                kv[r] = ((key * f + S.frac[S.sym[p + k]]) << VAL_BITS) | (tbase0 + p);
+                okmask |= 1u << r;
+                key = (key - S.sym[p] * pw) * a + S.sym[p + k];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < SI; r++) {
+            uint32_t p = base + r * 32;
+            kv[r] = 0;
+            if (p < cnt) { kv[r] = in[p]; okmask |= 1u << r; }
+        }
     }
-    {
+    if (STABLE) {
         // the tile that will be handed out about two waves from now: pull it into L2 (one 128-byte line per thread)
         uint32_t tile2 = tile + 2 * SM_COUNT * 3 / G + 1;
         if (tile2 < NT) {
@@ -1285,8 +1335,8 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->stream));
         ctx->sweep_cap = ctx->hist.cap; ctx->sweep_gen = 0;
     }
-    S3G_BYTES(ctx, 13 * N);
-    S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, P.kv0, ghist);
+    S3G_BYTES(ctx, 5 * N);
+    S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, ghist);
     S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), NBINS, 0, ghist);
     {
         uint64_t *src = P.kv0, *dst = P.kv1;
