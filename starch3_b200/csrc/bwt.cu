@@ -969,44 +969,86 @@ __global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t 
 }
 
 // Blocks with leftovers: ranks (SA position of the group head, FINAL on singletons) from the NONHEAD
-// flags, flags cleared, so that the doubling rounds can take over at depth k.
-__global__ void __launch_bounds__(1024) k_rank_rebuild(BwtP P)
+// flags, flags cleared, so that the doubling rounds can take over at depth k.  Two tile-parallel
+// launches: the last group head of every tile, then the ranks with the carry from the earlier tiles.
+constexpr int RBT = 1024;                        // threads; 4 positions each = one sort tile
+
+__global__ void __launch_bounds__(RBT) k_rebuild_agg(BwtP P)
 {
     __shared__ uint32_t sm[33];
-    const uint32_t lb = blockIdx.x, tid = threadIdx.x;
-    const uint32_t left = P.left[lb];
-    if (tid == 0) P.act[lb] = left;
-    if (!left) return;
+    const uint32_t lb = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    if (tile == 0 && tid == 0) P.act[lb] = P.left[lb];
+    if (!P.left[lb]) return;
+    const uint32_t n = P.cnt_n[lb];
+    if ((uint64_t)tile * STILE >= n) return;
+    const uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+    uint32_t lh = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t p = tile * STILE + k * RBT + tid;
+        if (p < n && !(sa[p] & NONHEAD)) lh = p + 1;
+    }
+    uint32_t tot;
+    block_excl_max<uint32_t>(lh, sm, &tot);
+    if (tid == 0) P.agg[((uint64_t)lb * NT + tile) * 2] = tot;
+}
+
+__global__ void __launch_bounds__(RBT) k_rebuild_apply(BwtP P, uint32_t *sa_clean)
+{
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t s_carry;
+    const uint32_t lb = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    if (!P.left[lb]) return;
+    const uint32_t n = P.cnt_n[lb];
+    if ((uint64_t)tile * STILE >= n) return;
+    {
+        uint32_t c = 0;
+        const uint32_t *ag = P.agg + (uint64_t)lb * NT * 2;
+        for (uint32_t t = tid; t < tile; t += RBT) c = max(c, ag[t * 2]);
+        uint32_t tot;
+        block_excl_max<uint32_t>(c, sm, &tot);
+        if (tid == 0) s_carry = tot;
+        __syncthreads();
+    }
+    const uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *out = sa_clean + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t p0 = tile * STILE + tid * 4;
+    uint32_t v[5];
+    uint32_t lh = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        uint32_t p = p0 + k;
+        v[k] = p < n ? sa[p] : 0u;                        // past the end counts as a head
+        if (k < 4 && p < n && !(v[k] & NONHEAD)) lh = p + 1;
+    }
+    uint32_t tot;
+    uint32_t hp = max(block_excl_max<uint32_t>(lh, sm, &tot), s_carry);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t p = p0 + k;
+        if (p < n) {
+            bool head = !(v[k] & NONHEAD);
+            if (head) hp = p + 1;
+            bool single = head && !(v[k + 1] & NONHEAD);
+            uint32_t val = v[k] & VMASK;
+            rk[val] = (hp - 1) | (single ? FINAL : 0u);
+            out[p] = val;                                 // flags cleared into a second array: neighbouring tiles still read them
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RBT) k_copy_clean(BwtP P, const uint32_t *sa_clean)
+{
+    const uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    if (!P.left[lb]) return;
     const uint32_t n = P.cnt_n[lb];
     uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
-    uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
-    uint32_t carry = 0;
-    for (uint32_t chunk = 0; chunk < n; chunk += 1024 * 4) {
-        uint32_t p0 = chunk + tid * 4;
-        uint32_t v[5];
-        uint32_t lh = 0;
+    const uint32_t *in = sa_clean + (uint64_t)lb * BLK_STRIDE;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            uint32_t p = p0 + k;
-            v[k] = p < n ? sa[p] : 0u;                    // past the end counts as a head
-            if (k < 4 && p < n && !(v[k] & NONHEAD)) lh = p + 1;
-        }
-        uint32_t tot;
-        uint32_t hp = max(block_excl_max<uint32_t>(lh, sm, &tot), carry);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t p = p0 + k;
-            if (p < n) {
-                bool head = !(v[k] & NONHEAD);
-                if (head) hp = p + 1;
-                bool single = head && !(v[k + 1] & NONHEAD);
-                uint32_t val = v[k] & VMASK;
-                rk[val] = (hp - 1) | (single ? FINAL : 0u);
-                sa[p] = val;
-            }
-        }
-        carry = max(carry, tot);
-        __syncthreads();
+    for (int k = 0; k < 4; k++) {
+        uint32_t p = tile * STILE + k * RBT + threadIdx.x;
+        if (p < n) sa[p] = in[p];
     }
 }
 
@@ -1365,7 +1407,10 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     if (getenv("S3G_DEBUG")) fprintf(stderr, "[s3g] bwt: %llu of %.0f rotations left to the doubling rounds\n", *h_act, N);
     if (*h_act == 0) return S3G_OK;
-    S3G_LAUNCH(ctx, k_rank_rebuild, (unsigned)nb, 1024, 0, P);
+    // (sa with flags) -> ranks; the flag-free order lands in kv1's storage and is copied back
+    S3G_LAUNCH(ctx, k_rebuild_agg, grid, RBT, 0, P);
+    S3G_LAUNCH(ctx, k_rebuild_apply, grid, RBT, 0, P, reinterpret_cast<uint32_t *>(P.kv1));
+    S3G_LAUNCH(ctx, k_copy_clean, grid, RBT, 0, P, reinterpret_cast<const uint32_t *>(P.kv1));
     ctx->sweep_cap = 0;                  // the rounds below reuse the status table as per-tile histograms
     // ---- doubling rounds: block b sorts by depth init_k[b] << round ----
     for (uint32_t round = 0; round < 32; round++) {

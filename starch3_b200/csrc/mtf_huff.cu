@@ -613,7 +613,15 @@ __global__ void __launch_bounds__(HT) k_huff(const uint16_t *mtfv_all, const int
         my_sel_bits += S.sel_mtf[g] + 1u;
         int gs = g * G_SIZE, ge = min(gs + G_SIZE, nmtf);
         const uint8_t *ln = S.len[S.selector[g]];
-        for (int i = gs; i < ge; i++) my_sym_bits += ln[mtfv[i]];
+        if (ge - gs == G_SIZE) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(mtfv + gs);     // gs * 2 bytes is 4-byte aligned
+            uint32_t w[G_SIZE / 2];
+#pragma unroll
+            for (int k = 0; k < G_SIZE / 2; k++) w[k] = src[k];
+#pragma unroll
+            for (int k = 0; k < G_SIZE / 2; k++) my_sym_bits += (uint32_t)ln[w[k] & 0xffffu] + ln[w[k] >> 16];
+        } else
+            for (int i = gs; i < ge; i++) my_sym_bits += ln[mtfv[i]];
     }
     uint32_t sel_total, sym_total;
     uint32_t sel_ex = block_excl_sum<uint32_t>(my_sel_bits, S.scan, &sel_total);
@@ -668,7 +676,19 @@ __global__ void __launch_bounds__(HT) k_huff(const uint16_t *mtfv_all, const int
             int gs = g * G_SIZE, ge = min(gs + G_SIZE, nmtf);
             const uint8_t *ln = S.len[S.selector[g]];
             const int32_t *cd = S.code[S.selector[g]];
-            for (int i = gs; i < ge; i++) { int v = mtfv[i]; bw.put(ln[v], (uint32_t)cd[v]); }
+            if (ge - gs == G_SIZE) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(mtfv + gs);
+                uint32_t w[G_SIZE / 2];
+#pragma unroll
+                for (int k = 0; k < G_SIZE / 2; k++) w[k] = src[k];
+#pragma unroll
+                for (int k = 0; k < G_SIZE / 2; k++) {
+                    uint32_t v0 = w[k] & 0xffffu, v1 = w[k] >> 16;
+                    bw.put(ln[v0], (uint32_t)cd[v0]);
+                    bw.put(ln[v1], (uint32_t)cd[v1]);
+                }
+            } else
+                for (int i = gs; i < ge; i++) { int v = mtfv[i]; bw.put(ln[v], (uint32_t)cd[v]); }
         }
         bw.end();
     }
