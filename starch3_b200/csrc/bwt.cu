@@ -703,9 +703,9 @@ __global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const 
 // A tile owns the groups that START inside it and reads past its end to the end of the last one;
 // whether a group is sorted here depends only on its size (<= FX), so the tile a group spills into
 // can tell without communication that the owner took care of it.
-constexpr int FTH = 512;                         // threads per finisher tile
-constexpr int FT = 2048;                         // SA positions owned by a tile
-constexpr int FX = 2048;                         // largest group sorted in shared memory (FX <= FT)
+constexpr int FTH = 256;                         // threads per finisher tile
+constexpr int FT = 1024;                         // SA positions owned by a tile
+constexpr int FX = 1024;                         // largest group sorted in shared memory (FX <= FT)
 constexpr int FWA = FT + FX + 64;                // window entries
 constexpr int FEPT = (FWA + FTH - 1) / FTH;      // consecutive entries per thread in the grouping phase
 constexpr int FNT = (BLK_STRIDE + FT - 1) / FT;  // finisher tiles per block slot
@@ -754,7 +754,7 @@ __device__ __forceinline__ uint32_t fin_group_end(const uint32_t *hbits, uint32_
     return ge < W ? ge : W;
 }
 
-__global__ void __launch_bounds__(FTH, 2) k_group_finish(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
+__global__ void __launch_bounds__(FTH, 4) k_group_finish(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
                                                          uint8_t *lcol)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
