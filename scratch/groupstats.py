@@ -1,0 +1,29 @@
+import sys, numpy as np
+sys.path.insert(0,'.')
+from starch3_b200 import synth
+from oracle import oracle as O
+cfg=int(sys.argv[1]); lines=int(sys.argv[2]); KB=int(sys.argv[3]) if len(sys.argv)>3 else 40
+bed=synth.bed(cfg,lines).tobytes()
+tfb,chs,_=O.transform(bed)
+c=max(chs,key=lambda c:c['tf_len'])
+s=tfb[c['tf_off']:c['tf_off']+c['tf_len']]
+blk=np.frombuffer(s[:899981],dtype=np.uint8)
+n=len(blk)
+syms,inv=np.unique(blk,return_inverse=True)
+a=len(syms); 
+k=1; pw=a
+while pw*a<=(1<<KB): pw*=a; k+=1
+f=min((1<<KB)//pw,a)
+print('n',n,'A',a,'k',k,'f',f)
+ext=np.concatenate([inv,inv[:k+1]]).astype(np.uint64)
+key=np.zeros(n,dtype=np.uint64)
+for j in range(k): key=key*np.uint64(a)+ext[j:j+n]
+key=key*np.uint64(f)+(ext[k:k+n]*np.uint64(f)//np.uint64(a))
+for bits in ([KB, KB-10, KB-20] ):
+    kk=key>>np.uint64(KB-bits)
+    u,c=np.unique(kk,return_counts=True)
+    print('bits',bits,'groups',len(u),'singletons',int((c==1).sum()),'entries in nonsingle',int(c[c>1].sum()),'max',c.max(),'sum sq (nonsingle)',int((c[c>1].astype(np.int64)**2).sum()))
+    hist=np.bincount(np.minimum(np.ceil(np.log2(c)).astype(int),12),weights=c)
+    print('   entries by log2 size',hist.astype(int).tolist())
+    hist2=np.bincount(np.minimum(np.ceil(np.log2(c)).astype(int),12),weights=c.astype(np.float64)**2)
+    print('   sumsq by log2 size',hist2.astype(np.int64).tolist())

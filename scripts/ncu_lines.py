@@ -1,23 +1,27 @@
 #!/usr/bin/env python3
-"""Per-source-line hot spots of one kernel from an ncu report (needs -lineinfo and --import-source on).
-usage: scripts/ncu_lines.py report.ncu-rep [top-n]"""
-import csv, io, subprocess, sys
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(txt)))
-cur_file = fn = None; hdr = None; lines = {}
-for row in rows:
-    if not row: continue
-    if row[0] == "File Path": cur_file = row[1]; continue
-    if row[0] == "Function Name": fn = row[1]; continue
-    if row[0] == "Line No": hdr = row; continue
-    if hdr is None or not row[0].isdigit(): continue
-    si = hdr.index("# Samples"); ii = hdr.index("Instructions Executed")
-    try: s = int(row[si]); i = int(row[ii])
-    except ValueError: continue
-    key = (fn.split("(")[0], cur_file.split("/")[-1], int(row[0]), row[1].strip())
-    a = lines.setdefault(key, [0, 0]); a[0] += s; a[1] += i
-ts = sum(a[0] for a in lines.values()) or 1; ti = sum(a[1] for a in lines.values()) or 1
-print(f"total samples {ts}, warp instructions {ti}")
-for k, a in sorted(lines.items(), key=lambda kv: -kv[1][0])[:top]:
-    print(f"{k[1]}:{k[2]:4d} smp {100 * a[0] / ts:5.1f}% ins {100 * a[1] / ti:5.1f}%  {k[3][:120]}")
+"""Top CUDA source lines by warp-stall samples, per kernel, from an ncu report captured with
+--set full --import-source on.   usage: scripts/ncu_lines.py report.ncu-rep kernel-regex [top]"""
+import csv, subprocess, sys, io
+rep, kre = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kre],
+                     capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+fn, hdr, sec = None, None, []
+def flush():
+    if not sec: return
+    i_s = hdr.index("# Samples"); i_ie = hdr.index("Instructions Executed")
+    stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    tot = sum(int(r[i_s] or 0) for r in sec)
+    print(f"== {fn[:100]}  samples={tot}")
+    for r in sorted(sec, key=lambda r: -int(r[i_s] or 0))[:top]:
+        s = int(r[i_s] or 0)
+        st = sorted(((int(r[i] or 0), hdr[i][6:]) for i in stalls), reverse=True)[:3]
+        print(f"{r[0]:>5} {100.0*s/max(tot,1):5.1f}% inst={r[i_ie]:>10} {' '.join(f'{n}:{100*v//max(s,1)}' for v,n in st if v)} | {r[1].strip()[:110]}")
+for r in rows:
+    if not r: continue
+    if r[0] == "Function Name": flush(); fn = r[1]; sec = []; continue
+    if r[0] == "Line No": hdr = r; continue
+    if r[0] == "File Path" or hdr is None: continue
+    if r[0] != "": sec.append(r)
+flush()

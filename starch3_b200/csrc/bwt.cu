@@ -57,7 +57,22 @@ enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2, MODE_KVX = 3 };   // KVX: key/va
 
 // Records are 64 bits.  Initial sort: (40-bit symbol key << 20) | rotation start.  Doubling rounds:
 // (rank << 32) | rotation start.  A radix pass takes its 10-bit digit at bit `rshift` of the record.
-constexpr int KEY_BITS = 40;             // initial key: four 10-bit passes
+constexpr int KEY_BITS = 40;             // initial key
+#ifndef S3G_SW_BITS
+#define S3G_SW_BITS 8
+#endif
+#ifndef S3G_SW_OCC
+#define S3G_SW_OCC 4
+#endif
+#ifndef S3G_SWT
+#define S3G_SWT 256
+#endif
+#ifndef S3G_SWI
+#define S3G_SWI 16
+#endif
+constexpr int SW_BITS = S3G_SW_BITS;               // digit width of the onesweep passes
+constexpr int SWN = 1 << SW_BITS;        // their bins
+constexpr int SW_OCC = S3G_SW_OCC;                // resident CTAs per SM the sweep is compiled for
 constexpr int VAL_BITS = 20;             // rotation starts are < 2^20 (BLK_STRIDE)
 
 // record p of block lb for the given source mode; returns false if the item does not take part
@@ -170,9 +185,6 @@ struct ScatterSmem {
     uint32_t tbase[NBINS];                 // offset of the digit inside the tile
     uint16_t wcnt[(ST / 32) * NBINS];      // per-warp digit counters -> exclusive warp offsets
     uint32_t scan[33];
-    // first pass only: the records are built from the block bytes on the fly
-    __align__(16) uint8_t sym[STILE + 64];
-    uint8_t seq[256], frac[256];
 };
 
 template <int MODE>
@@ -262,12 +274,29 @@ __global__ void __launch_bounds__(ST, 3) k_scatter(BwtP P, int rshift, int phase
 //             blocks in a batch the predecessor has normally published its inclusive prefix already.
 constexpr int KT = 8;                        // tiles per CTA in k_keys
 constexpr int SWEEP_G = 64;                  // blocks whose tiles are interleaved in a radix pass
-constexpr int NPASS = KEY_BITS / 10;
+constexpr int NPASS = (KEY_BITS + SW_BITS - 1) / SW_BITS;
 constexpr uint32_t ST_INCL = 1u << 23, ST_AGG = 1u << 22, ST_VAL = 0x000fffffu;
+
+constexpr int SWT = S3G_SWT;                     // threads of a sweep CTA
+constexpr int SWI = S3G_SWI;                      // records per thread
+constexpr int SW_TILE = SWT * SWI;           // records per sweep tile
+constexpr int SW_NT = (BLK_STRIDE + SW_TILE - 1) / SW_TILE;
+constexpr int SW_DPT = SWN > SWT ? SWN / SWT : 1;    // digits per thread (threads past SWN own none)
+
+struct SweepSmem {
+    uint64_t stage[SW_TILE];               // tile in digit order (the per-warp peer masks live here while ranking)
+    uint32_t gbase[SWN];                   // (global offset - tile offset) of the digit
+    uint32_t tbase[SWN];                   // offset of the digit inside the tile
+    uint16_t wcnt[(SWT / 32) * SWN];       // per-warp digit counters -> exclusive warp offsets
+    uint32_t scan[33];
+    // first pass only: the records are built from the block bytes on the fly
+    __align__(16) uint8_t sym[SW_TILE + 64];
+    uint8_t seq[256], frac[256];
+};
 
 struct KeysSmem {
     uint32_t stage32[STILE + STILE / 16];    // per-position keys, skewed so that 16-consecutive-per-thread writes are conflict-free
-    uint32_t hist[NPASS][NBINS];
+    uint32_t hist[NPASS][SWN];
     __align__(16) uint8_t sym[STILE + 64];
     uint8_t seq[256];
     uint8_t frac[256];
@@ -283,7 +312,7 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint32_t *ghist)
     if ((uint64_t)t0 * STILE >= n) return;
     const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
     const uint32_t k = P.init_k[lb], k32 = P.init_k32[lb], a = P.init_a[lb], f = P.init_f[lb];
-    for (int i = tid; i < NPASS * NBINS; i += ST) (&S.hist[0][0])[i] = 0;
+    for (int i = tid; i < NPASS * SWN; i += ST) (&S.hist[0][0])[i] = 0;
     S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
     S.frac[tid] = (uint8_t)(tid < a ? tid * f / a : 0);      // class of a symbol rank, monotone
     uint64_t pw = 1; uint32_t pw32 = 1;                      // a^(k-1), a^(k32-1)
@@ -330,7 +359,7 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint32_t *ghist)
                     uint64_t rec = ((key * f + S.frac[S.sym[p + k]]) << VAL_BITS) | (base + p);
                     S.stage32[p + (p >> 4)] = key32;
 #pragma unroll
-                    for (int ps = 0; ps < NPASS; ps++) atomicAdd(&S.hist[ps][(uint32_t)(rec >> (VAL_BITS + 10 * ps)) & (NBINS - 1)], 1u);
+                    for (int ps = 0; ps < NPASS; ps++) atomicAdd(&S.hist[ps][(uint32_t)(rec >> (VAL_BITS + SW_BITS * ps)) & (SWN - 1)], 1u);
                     uint32_t so = S.sym[p];
                     key = (key - so * pw) * a + S.sym[p + k];
                     key32 = (key32 - so * pw32) * a + S.sym[p + k32];
@@ -341,77 +370,78 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint32_t *ghist)
         for (uint32_t p = tid; p < cntT; p += ST) rk[base + p] = S.stage32[p + (p >> 4)];
     }
     __syncthreads();
-    uint32_t *gh = ghist + (uint64_t)lb * NPASS * NBINS;
-    for (int i = tid; i < NPASS * NBINS; i += ST) { uint32_t v = (&S.hist[0][0])[i]; if (v) atomicAdd(&gh[i], v); }
+    uint32_t *gh = ghist + (uint64_t)lb * NPASS * SWN;
+    for (int i = tid; i < NPASS * SWN; i += ST) { uint32_t v = (&S.hist[0][0])[i]; if (v) atomicAdd(&gh[i], v); }
 }
 
-__global__ void __launch_bounds__(NBINS) k_digit_scan(uint32_t *ghist)
+__global__ void __launch_bounds__(SWN) k_digit_scan(uint32_t *ghist)
 {
     __shared__ uint32_t sm[33];
-    uint32_t *g = ghist + ((uint64_t)blockIdx.y * NPASS + blockIdx.x) * NBINS;
+    uint32_t *g = ghist + ((uint64_t)blockIdx.y * NPASS + blockIdx.x) * SWN;
     uint32_t v = g[threadIdx.x], tot;
     g[threadIdx.x] = block_excl_sum<uint32_t>(v, sm, &tot);
 }
 
 // STABLE = false (the first pass only: the records arrive in position order, which carries no
 // meaning yet): ranks come straight from an atomicAdd on one per-tile counter per digit -- no
-// per-warp tables, no peer matching, and the 16 records of a thread rank independently.
-template <bool STABLE>
-__global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *dbase_all,
-                                                 int pass, uint32_t *ticket_ctr, uint32_t nb, uint32_t gen, uint32_t G)
+// per-warp tables, no peer matching, and the records of a thread rank independently.
+template <bool STABLE, int EXP = 0>
+__global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *dbase_all,
+                                                      int pass, uint32_t *ticket_ctr, uint32_t nb, uint32_t gen, uint32_t G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
-    // one ticket counter per bzip2 block (a single counter for the whole grid serialises ~65 k atomics on one
-    // L2 address per pass, ~35 cycles each: that alone is 1.2 ms): the CTA is bound to block blockIdx.x % nb and
-    // draws the next tile of that block
+    SweepSmem &S = *reinterpret_cast<SweepSmem *>(smem_raw);
+    // one ticket counter per bzip2 block (a single counter for the whole grid serialises its atomics on one
+    // L2 address): the CTA is bound to block blockIdx.x % nb and draws the next tile of that block.
     // CTAs are dealt to the blocks in groups of SWEEP_G: the tiles of one block run close together in time, so the
-    // 32-byte pieces a digit receives from consecutive tiles meet in L2 and leave as full lines (with the whole
+    // short pieces a digit receives from consecutive tiles meet in L2 and leave as full lines (with the whole
     // batch interleaved they were evicted one sector at a time and the pass ran at a third of the DRAM rate),
-    // while the look-back still finds its predecessors finished after about 444 / SWEEP_G tiles.
-    const uint32_t lb = blockIdx.x / (NT * G) * G + blockIdx.x % G;
+    // while the look-back still finds its predecessors finished after a few tiles.
+    const uint32_t lb = blockIdx.x / (SW_NT * G) * G + blockIdx.x % G;
     if (lb >= nb) return;
-    if (threadIdx.x == 0) S.scan[0] = atomicAdd(ticket_ctr + lb, 1u);
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) S.scan[0] = atomicAdd(ticket_ctr + lb, 1u);
     // Intra-warp matching through shared memory instead of match.any (measured on B200: match.any costs
-    // ~8 cycles per DISTINCT value in the warp, 170-250 cycles per call on these digits; an atomicOr of
-    // the lane bit into a per-warp, per-digit mask word plus a read-back gives the same peer mask for
-    // ~20).  The mask table aliases the staging buffer, which is not live until ranking is over.
-    static_assert(sizeof(S.stage) >= (ST / 32) * NBINS * 4, "mask table must fit in the staging buffer");
+    // ~8 cycles per DISTINCT value in the warp; an atomicOr of the lane bit into a per-warp, per-digit mask
+    // word plus a read-back gives the same peer mask for ~20).  The mask table aliases the staging buffer,
+    // which is not live until ranking is over.
+    static_assert(sizeof(S.stage) >= (SWT / 32) * SWN * 4, "mask table must fit in the staging buffer");
     uint32_t *Mall = reinterpret_cast<uint32_t *>(S.stage);
     uint32_t *tcnt = reinterpret_cast<uint32_t *>(S.wcnt);       // !STABLE: one counter per digit
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *zm = reinterpret_cast<uint4 *>(S.stage), *zc = reinterpret_cast<uint4 *>(S.wcnt);
         if (STABLE) {
-            for (int i = threadIdx.x; i < (ST / 32) * NBINS / 4; i += ST) zm[i] = z;      // mask table: 8 warps x 1024 words
-            for (int i = threadIdx.x; i < (ST / 32) * NBINS / 8; i += ST) zc[i] = z;      // counters: 8 warps x 1024 halfwords
+            for (int i = tid; i < (SWT / 32) * SWN / 4; i += SWT) zm[i] = z;      // mask table: one word per warp and digit
+            for (int i = tid; i < (SWT / 32) * SWN / 8; i += SWT) zc[i] = z;      // counters: one halfword per warp and digit
         } else {
-            for (int i = threadIdx.x; i < NBINS / 4; i += ST) zc[i] = z;
+            for (int i = tid; i < SWN / 4; i += SWT) zc[i] = z;
         }
     }
     __syncthreads();
     const uint32_t tile = S.scan[0];
     const uint32_t cnt = P.cnt_n[lb];
-    if ((uint64_t)tile * STILE >= cnt) return;
-    uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    uint32_t base = tile * STILE + w * (SI * 32) + l;
-    uint16_t *mycnt = S.wcnt + w * NBINS;
-    uint32_t *M = Mall + w * NBINS;
+    if ((uint64_t)tile * SW_TILE >= cnt) return;
+    uint32_t w = tid >> 5, l = tid & 31;
+    uint32_t base = tile * SW_TILE + w * (SWI * 32) + l;
+    uint16_t *mycnt = S.wcnt + w * SWN;
+    uint32_t *M = Mall + w * SWN;
     const uint64_t *in = kv_in + (uint64_t)lb * BLK_STRIDE;
-    uint64_t kv[SI];
-    uint16_t rnk[SI];
+    uint64_t kv[SWI];
+    uint16_t rnk[SWI];
     uint32_t okmask = 0;
     if (!STABLE) {
-        // first pass: thread t builds the records of positions 16 t .. 16 t + 15 of the tile with a rolling key,
+        // first pass: thread t builds the records of positions SWI t .. SWI t + SWI - 1 of the tile with a rolling key,
         // exactly as k_keys did for the histograms (any record-to-thread mapping will do: no stability needed)
         const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
         const uint32_t k = P.init_k[lb], a = P.init_a[lb], f = P.init_f[lb];
-        const uint32_t tbase0 = tile * STILE, cntT = min((uint32_t)STILE, cnt - tbase0), tid = threadIdx.x;
-        S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
-        S.frac[tid] = (uint8_t)(tid < a ? tid * f / a : 0);
+        const uint32_t tbase0 = tile * SW_TILE, cntT = min((uint32_t)SW_TILE, cnt - tbase0);
+        if (tid < 256) {
+            S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
+            S.frac[tid] = (uint8_t)(tid < a ? tid * f / a : 0);
+        }
         __syncthreads();
-        {
-            const uint32_t i0 = tid * 16;
+        for (uint32_t i0 = tid * 16; i0 < (uint32_t)SW_TILE; i0 += SWT * 16) {
             if (tbase0 + i0 + 16 <= cnt) {
                 uint4 v = *reinterpret_cast<const uint4 *>(b + tbase0 + i0);
                 uint32_t wv[4] = {v.x, v.y, v.z, v.w};
@@ -427,20 +457,20 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
                     S.sym[i] = S.seq[b[q]];
                 }
             }
-            for (uint32_t i = STILE + tid; i < cntT + k + 1; i += ST) {
-                uint32_t q = tbase0 + i;
-                if (q >= cnt) { q -= cnt; if (q >= cnt) q %= cnt; }
-                S.sym[i] = S.seq[b[q]];
-            }
+        }
+        for (uint32_t i = SW_TILE + tid; i < cntT + k + 1; i += SWT) {
+            uint32_t q = tbase0 + i;
+            if (q >= cnt) { q -= cnt; if (q >= cnt) q %= cnt; }
+            S.sym[i] = S.seq[b[q]];
         }
         __syncthreads();
         uint64_t pw = 1;
         for (uint32_t i = 1; i < k; i++) pw *= a;
-        const uint32_t p0 = tid * SI;
+        const uint32_t p0 = tid * SWI;
         uint64_t key = 0;
         if (p0 < cntT) for (uint32_t j = 0; j < k; j++) key = key * a + S.sym[p0 + j];
 #pragma unroll
-        for (int r = 0; r < SI; r++) {
+        for (int r = 0; r < SWI; r++) {
             uint32_t p = p0 + r;
             kv[r] = 0;
             if (p < cntT) {
@@ -451,30 +481,37 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < SI; r++) {
+        for (int r = 0; r < SWI; r++) {
             uint32_t p = base + r * 32;
             kv[r] = 0;
             if (p < cnt) { kv[r] = in[p]; okmask |= 1u << r; }
         }
     }
+    if (EXP == 4) {
+        uint64_t *o4 = kv_out + (uint64_t)lb * BLK_STRIDE;
+#pragma unroll
+        for (int r = 0; r < SWI; r++) if (okmask & (1u << r)) o4[base + r * 32] = kv[r];
+        return;
+    }
     if (STABLE) {
-        // the tile that will be handed out about two waves from now: pull it into L2 (one 128-byte line per thread)
-        uint32_t tile2 = tile + 2 * SM_COUNT * 3 / G + 1;
-        if (tile2 < NT) {
-            const uint8_t *pf = reinterpret_cast<const uint8_t *>(kv_in + (uint64_t)lb * BLK_STRIDE + (uint64_t)tile2 * STILE) + threadIdx.x * 128;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        // the tile that will be handed out about two waves from now: pull it into L2 (128-byte lines)
+        uint32_t tile2 = tile + 2 * SM_COUNT * SW_OCC / G + 1;
+        if (tile2 < SW_NT) {
+            const uint8_t *pf = reinterpret_cast<const uint8_t *>(kv_in + (uint64_t)lb * BLK_STRIDE + (uint64_t)tile2 * SW_TILE);
+            for (uint32_t o = tid * 128; o < (uint32_t)SW_TILE * 8; o += SWT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
         }
     }
-    constexpr int DPT = NBINS / ST;
+    constexpr int DPT = SW_DPT;
+    const bool has_digit = tid * DPT < (uint32_t)SWN;
     uint32_t tot4[DPT];
     uint32_t mysum = 0;
     if (!STABLE) {
 #pragma unroll
-        for (int r = 0; r < SI; r++)
-            if (okmask & (1u << r)) rnk[r] = (uint16_t)atomicAdd(&tcnt[(uint32_t)(kv[r] >> rshift) & (NBINS - 1)], 1u);
+        for (int r = 0; r < SWI; r++)
+            if (okmask & (1u << r)) rnk[r] = (uint16_t)atomicAdd(&tcnt[(uint32_t)(kv[r] >> rshift) & (SWN - 1)], 1u);
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < DPT; q++) { tot4[q] = tcnt[threadIdx.x * DPT + q]; mysum += tot4[q]; }
+        for (int q = 0; q < DPT; q++) { tot4[q] = has_digit ? tcnt[tid * DPT + q] : 0u; mysum += tot4[q]; }
     } else {
         const uint32_t lbit = 1u << l, ltmask = lbit - 1;
         // match.any is cheap when the warp holds few distinct digits (the upper passes of text: the records
@@ -482,15 +519,15 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
         // many.  One probe per warp and tile: equal neighbours among the first 32 records.
         bool use_match;
         {
-            uint32_t d0 = (okmask & 1u) ? ((uint32_t)(kv[0] >> rshift) & (NBINS - 1)) : 0x10000u + l;
+            uint32_t d0 = (okmask & 1u) ? ((uint32_t)(kv[0] >> rshift) & (SWN - 1)) : 0x10000u + l;
             uint32_t dn = __shfl_down_sync(0xffffffffu, d0, 1);
             use_match = __popc(__ballot_sync(0xffffffffu, l < 31 && d0 == dn)) >= 16;
         }
         if (use_match) {
 #pragma unroll
-            for (int r = 0; r < SI; r++) {
+            for (int r = 0; r < SWI; r++) {
                 bool ok = (okmask >> r) & 1u;
-                uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (NBINS - 1)) : 0xffffffffu;
+                uint32_t d = ok ? ((uint32_t)(kv[r] >> rshift) & (SWN - 1)) : 0xffffffffu;
                 unsigned peers = __match_any_sync(0xffffffffu, d);
                 unsigned lt = peers & ltmask;
                 uint32_t bb = ok ? mycnt[d] : 0u;
@@ -501,9 +538,9 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < SI; r++) {
+            for (int r = 0; r < SWI; r++) {
                 bool ok = (okmask >> r) & 1u;
-                uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
+                uint32_t d = (uint32_t)(kv[r] >> rshift) & (SWN - 1);
                 if (ok) atomicOr(&M[d], lbit);
                 __syncwarp();
                 uint32_t peers = ok ? M[d] : 0u;
@@ -519,74 +556,78 @@ __global__ void __launch_bounds__(ST, 3) k_sweep(BwtP P, int rshift, const uint6
         // per digit: exclusive prefix over warps, tile total
 #pragma unroll
         for (int q = 0; q < DPT; q++) {
-            int d = threadIdx.x * DPT + q;
-            uint32_t run = 0;
+            tot4[q] = 0;
+            if (has_digit) {
+                int d = tid * DPT + q;
+                uint32_t run = 0;
 #pragma unroll
-            for (int ww = 0; ww < ST / 32; ww++) { uint32_t c = S.wcnt[ww * NBINS + d]; S.wcnt[ww * NBINS + d] = (uint16_t)run; run += c; }
-            tot4[q] = run; mysum += run;
+                for (int ww = 0; ww < SWT / 32; ww++) { uint32_t c = S.wcnt[ww * SWN + d]; S.wcnt[ww * SWN + d] = (uint16_t)run; run += c; }
+                tot4[q] = run; mysum += run;
+            }
         }
     }
     // publish the tile's counts, look back for the exclusive prefix over earlier tiles, publish the inclusive prefix
-    static_assert(DPT == 4, "status words are moved as uint4");
     const uint32_t gtag = gen << 24;
-    volatile uint4 *status = reinterpret_cast<volatile uint4 *>(P.hist + (uint64_t)lb * NT * NBINS) + threadIdx.x;   // + tile * (NBINS / 4)
-    uint32_t ex4[DPT] = {0, 0, 0, 0};
-    if (tile > 0) {
-        {
-            uint4 v = make_uint4(gtag | ST_AGG | tot4[0], gtag | ST_AGG | tot4[1], gtag | ST_AGG | tot4[2], gtag | ST_AGG | tot4[3]);
-            volatile uint4 *dst = status + (uint64_t)tile * (NBINS / 4);
-            dst->x = v.x; dst->y = v.y; dst->z = v.z; dst->w = v.w;
-        }
-        uint32_t done = 0;                 // bit q: digit q has met an inclusive prefix
-        uint32_t spins = 0;
-        for (int32_t t = (int32_t)tile - 1; t >= 0 && done != 0xfu;) {
-            const volatile uint4 *src = status + (uint64_t)t * (NBINS / 4);
-            uint32_t x[DPT] = {src->x, src->y, src->z, src->w};
-            bool ready = true;
+    volatile uint32_t *status = P.hist + (uint64_t)lb * SW_NT * SWN + tid * DPT;     // + tile * SWN
+    uint32_t ex4[DPT];
 #pragma unroll
-            for (int q = 0; q < DPT; q++) if (!(done & (1u << q)) && (x[q] >> 24) != gen) ready = false;
-            if (!ready) {
-                if (++spins > (1u << 24)) __trap();          // a predecessor never published: fail loudly instead of hanging
-                __nanosleep(20);
-                continue;
-            }
+    for (int q = 0; q < DPT; q++) ex4[q] = 0;
+    if (has_digit) {
+        if (tile > 0) {
 #pragma unroll
-            for (int q = 0; q < DPT; q++) {
-                if (done & (1u << q)) continue;
-                ex4[q] += x[q] & ST_VAL;
-                if (x[q] & ST_INCL) done |= 1u << q;
+            for (int q = 0; q < DPT; q++) status[(uint64_t)tile * SWN + q] = gtag | ST_AGG | tot4[q];
+            uint32_t done = 0;                 // bit q: digit q has met an inclusive prefix
+            uint32_t spins = 0;
+            for (int32_t t = (int32_t)tile - 1; EXP != 2 && t >= 0 && done != (1u << DPT) - 1;) {
+                uint32_t x[DPT];
+#pragma unroll
+                for (int q = 0; q < DPT; q++) x[q] = status[(uint64_t)t * SWN + q];
+                bool ready = true;
+#pragma unroll
+                for (int q = 0; q < DPT; q++) if (!(done & (1u << q)) && (x[q] >> 24) != gen) ready = false;
+                if (!ready) {
+                    if (++spins > (1u << 24)) __trap();          // a predecessor never published: fail loudly instead of hanging
+                    __nanosleep(20);
+                    continue;
+                }
+#pragma unroll
+                for (int q = 0; q < DPT; q++) {
+                    if (done & (1u << q)) continue;
+                    ex4[q] += x[q] & ST_VAL;
+                    if (x[q] & ST_INCL) done |= 1u << q;
+                }
+                t--;
             }
-            t--;
         }
+#pragma unroll
+        for (int q = 0; q < DPT; q++) status[(uint64_t)tile * SWN + q] = gtag | ST_INCL | (ex4[q] + tot4[q]);
     }
-    {
-        volatile uint4 *dst = status + (uint64_t)tile * (NBINS / 4);
-        dst->x = gtag | ST_INCL | (ex4[0] + tot4[0]); dst->y = gtag | ST_INCL | (ex4[1] + tot4[1]);
-        dst->z = gtag | ST_INCL | (ex4[2] + tot4[2]); dst->w = gtag | ST_INCL | (ex4[3] + tot4[3]);
-    }
-    const uint32_t *dbase = dbase_all + ((uint64_t)lb * NPASS + pass) * NBINS;
+    const uint32_t *dbase = dbase_all + ((uint64_t)lb * NPASS + pass) * SWN;
     uint32_t tile_total;
     uint32_t ex = block_excl_sum<uint32_t>(mysum, S.scan, &tile_total);
+    if (has_digit) {
 #pragma unroll
-    for (int q = 0; q < DPT; q++) {
-        int d = threadIdx.x * DPT + q;
-        S.tbase[d] = ex;
-        S.gbase[d] = dbase[d] + ex4[q] - ex;          // (global offset - tile offset) of the digit
-        ex += tot4[q];
+        for (int q = 0; q < DPT; q++) {
+            int d = tid * DPT + q;
+            S.tbase[d] = ex;
+            S.gbase[d] = dbase[d] + ex4[q] - ex;          // (global offset - tile offset) of the digit
+            ex += tot4[q];
+        }
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < SI; r++) {
+    for (int r = 0; r < SWI; r++) {
         if (okmask & (1u << r)) {
-            uint32_t d = (uint32_t)(kv[r] >> rshift) & (NBINS - 1);
+            uint32_t d = (uint32_t)(kv[r] >> rshift) & (SWN - 1);
             S.stage[S.tbase[d] + (STABLE ? (uint32_t)mycnt[d] : 0u) + rnk[r]] = kv[r];
         }
     }
     __syncthreads();
     uint64_t *out = kv_out + (uint64_t)lb * BLK_STRIDE;
-    for (uint32_t i = threadIdx.x; i < tile_total; i += ST) {
+    for (uint32_t i = tid; i < tile_total; i += SWT) {
         uint64_t it = S.stage[i];
-        uint32_t d = (uint32_t)(it >> rshift) & (NBINS - 1);
+        uint32_t d = (uint32_t)(it >> rshift) & (SWN - 1);
+        if (EXP == 1) out[tile * SW_TILE + i] = it; else
         out[S.gbase[d] + i] = it;
     }
 }
@@ -1358,8 +1399,13 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_group_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KeysSmem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+#ifdef S3G_EXPERIMENT
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+#endif
         attr_done = true;
     }
     const uint32_t *no_act = nullptr;
@@ -1367,39 +1413,53 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     uint32_t *no_out = nullptr;
     uint64_t *no_save = nullptr;
     // ---- init: order by the first k symbols (40-bit key, four 10-bit onesweep passes; records end up in kv0) ----
-    S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * NPASS * (NBINS + 1) * 4));
+    S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * (NPASS * (SWN + 1) + 4) * 4));
     uint32_t *ghist = ctx->bwt_ghist.as<uint32_t>();
-    uint32_t *tickets = ghist + (size_t)nb * NPASS * NBINS;      // [NPASS][nb]
-    S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * NPASS * (NBINS + 1) * 4, ctx->stream));
+    uint32_t *tickets = ghist + (size_t)nb * NPASS * SWN;        // [NPASS][nb]
+    S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * (NPASS * (SWN + 1) + 4) * 4, ctx->stream));
     // look-back status words carry a generation tag; the table is cleared only when it is new, was used
     // by the doubling rounds (as a histogram table) or the tag wraps
-    if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS > 255) {
+    if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS + 4 > 255) {
         S3G_CUDA(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->stream));
         ctx->sweep_cap = ctx->hist.cap; ctx->sweep_gen = 0;
     }
     S3G_BYTES(ctx, 5 * N);
     S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, ghist);
-    S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), NBINS, 0, ghist);
+    S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), SWN, 0, ghist);
+    const uint64_t *sorted_kv = nullptr;
     {
         uint64_t *src = P.kv0, *dst = P.kv1;
         uint32_t G = SWEEP_G;
         if (const char *e = getenv("S3G_SWEEP_G")) { int v = atoi(e); if (v > 0) G = (uint32_t)v; }
-        const unsigned sweep_grid = (unsigned)((nb + G - 1) / G) * G * NT;
+        const unsigned sweep_grid = (unsigned)((nb + G - 1) / G) * G * SW_NT;
         for (int pass = 0; pass < NPASS; pass++) {
             S3G_BYTES(ctx, 16 * N);
             if (pass == 0)
-                S3G_LAUNCH(ctx, k_sweep<false>, sweep_grid, ST, sizeof(ScatterSmem), P, VAL_BITS, src, dst, ghist, pass, tickets + (size_t)pass * nb,
+                S3G_LAUNCH(ctx, k_sweep<false>, sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS, src, dst, ghist, pass, tickets + (size_t)pass * nb,
                            (uint32_t)nb, ++ctx->sweep_gen, G);
             else
-                S3G_LAUNCH(ctx, k_sweep<true>, sweep_grid, ST, sizeof(ScatterSmem), P, VAL_BITS + 10 * pass, src, dst, ghist, pass, tickets + (size_t)pass * nb,
+                S3G_LAUNCH(ctx, k_sweep<true>, sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, dst, ghist, pass, tickets + (size_t)pass * nb,
                            (uint32_t)nb, ++ctx->sweep_gen, G);
+#ifdef S3G_EXPERIMENT
+            if (pass == S3G_EXPERIMENT) {
+                S3G_TRY(ctx->exp_buf.ensure(slots * 8));
+                uint64_t *xb = ctx->exp_buf.as<uint64_t>();
+                uint32_t *xt = tickets + (size_t)NPASS * nb;
+                S3G_BYTES(ctx, 16 * N);
+                S3G_LAUNCH(ctx, (k_sweep<true, 1>), sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, xb, ghist, pass, xt, (uint32_t)nb, ++ctx->sweep_gen, G);
+                S3G_BYTES(ctx, 16 * N);
+                S3G_LAUNCH(ctx, (k_sweep<true, 2>), sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, xb, ghist, pass, xt + nb, (uint32_t)nb, ++ctx->sweep_gen, G);
+                S3G_BYTES(ctx, 16 * N);
+                S3G_LAUNCH(ctx, (k_sweep<true, 4>), sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, xb, ghist, pass, xt + 2 * nb, (uint32_t)nb, ++ctx->sweep_gen, G);
+            }
+#endif
             std::swap(src, dst);
         }
-        static_assert(NPASS % 2 == 0, "an even number of passes leaves the sorted records in kv0");
+        sorted_kv = src;
     }
     // ---- every group of up to FX rotations is finished in shared memory; SA, last column, origPtr ----
     S3G_BYTES(ctx, 18 * N);
-    S3G_LAUNCH(ctx, k_group_finish, dim3(FNT, (unsigned)nb), FTH, sizeof(FinSmem), P, P.kv0, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
+    S3G_LAUNCH(ctx, k_group_finish, dim3(FNT, (unsigned)nb), FTH, sizeof(FinSmem), P, sorted_kv, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
                ctx->lcol.as<uint8_t>());
     S3G_TRY(check_launch("bwt init"));
     unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
