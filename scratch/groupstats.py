@@ -27,3 +27,11 @@ for bits in ([KB, KB-10, KB-20] ):
     print('   entries by log2 size',hist.astype(int).tolist())
     hist2=np.bincount(np.minimum(np.ceil(np.log2(c)).astype(int),12),weights=c.astype(np.float64)**2)
     print('   sumsq by log2 size',hist2.astype(np.int64).tolist())
+# per-row loop lengths of the warp finisher
+order=np.argsort(key,kind='stable'); ks=key[order]
+head=np.ones(n,bool); head[1:]=ks[1:]!=ks[:-1]
+hidx=np.flatnonzero(head); size=np.diff(np.append(hidx,n))
+rows=hidx//32
+mx=np.zeros(n//32+1,dtype=np.int64)
+np.maximum.at(mx,rows,np.where(size>1,size,0))
+print('rows',len(mx),'mean max group size per row',mx.mean(),'rows with nonsingle',(mx>0).mean(), 'mean size of nonsingle entries', (size[size>1]**2).sum()/size[size>1].sum())

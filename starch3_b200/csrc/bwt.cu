@@ -1009,6 +1009,335 @@ __global__ void __launch_bounds__(FTH, 4) k_group_finish(BwtP P, const uint64_t 
     if (tid == 0 && ltot) { atomicAdd(&P.left[lb], ltot); atomicAdd(g_left, (unsigned long long)ltot); }
 }
 
+// ---- group finisher, warp form -------------------------------------------------------
+// k_finish_rows: a warp walks rows of 32 consecutive SA positions with a window of FA_WIN rows in
+// registers (rotation start | last-column symbol per entry, one head ballot per row).  A row owns the
+// groups whose head lies in it; a group that ends inside the window is ranked by the warp itself
+// (level-0 keys through a per-warp shared-memory strip, counting smaller / equal keys; the few ties go
+// to a per-warp list for the deeper levels), singletons are written straight from registers, and a
+// group that does not end inside the window is appended to a work list for k_finish_big.  Entries
+// before the first head of a row belong to an earlier row's group and are skipped: their owner wrote
+// them, or listed the group.
+// k_finish_big: one CTA per listed group: groups of up to FB_MAX rotations are ranked in shared memory
+// level by level, larger ones are written out unsorted (NONHEAD flags) for the doubling rounds.
+constexpr int FA_WARPS = 8;
+constexpr int FA_ROWS = 32;                              // rows a warp walks
+constexpr int FA_TILE = FA_WARPS * FA_ROWS * 32;         // SA positions per CTA
+constexpr int FA_NT = (BLK_STRIDE + FA_TILE - 1) / FA_TILE;
+constexpr int FA_WIN = 4;                                // rows in the window: a group of up to 97 rotations always fits
+constexpr int FA_W = FA_WIN * 32;
+constexpr uint32_t FA_BIG = 0xffffu;                     // group end: not inside the window
+
+struct FinASmem {
+    uint32_t dk[FA_WARPS][FA_W];      // level-0 keys of the window; keys of the tied list afterwards
+    uint32_t t_pw[FA_WARPS][FA_W];    // tied list: rotation start | last-column symbol << 24
+    uint16_t t_cs[FA_WARPS][FA_W];    //            window position of the tie's first slot (0xffff: resolved)
+    uint16_t t_rank[FA_WARPS][FA_W];  //            order among equals so far
+    uint8_t seq[256];
+};
+
+__device__ __forceinline__ uint32_t fa_group_end(uint32_t e, uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3)
+{
+    uint32_t mh = e >= 31 ? 0u : (h0 & (0xfffffffeu << e));
+    if (mh) return (uint32_t)__ffs(mh) - 1;
+    if (h1) return 32 + (uint32_t)__ffs(h1) - 1;
+    if (h2) return 64 + (uint32_t)__ffs(h2) - 1;
+    if (h3) return 96 + (uint32_t)__ffs(h3) - 1;
+    return FA_BIG;
+}
+
+__global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
+                                                                  uint8_t *lcol, uint64_t *big_list, uint32_t *big_cnt)
+{
+    __shared__ FinASmem S;
+    const uint32_t lb = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const uint32_t n = P.cnt_n[lb];
+    if (blockIdx.x * FA_TILE >= n) return;
+    S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
+    __syncthreads();
+    const uint32_t p0 = blockIdx.x * FA_TILE + w * (FA_ROWS * 32);
+    if (p0 >= n) return;
+    const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+    uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+    uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
+    const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
+    uint32_t *dk = S.dk[w];
+    uint32_t *t_pw = S.t_pw[w];
+    uint16_t *t_cs = S.t_cs[w], *t_rank = S.t_rank[w];
+    const uint32_t ltmask = (1u << l) - 1;
+    uint32_t leftover = 0;
+
+    // one row of the window: rotation start | last-column symbol (bz/compress.c:166-167), head ballot
+    auto load_row = [&](uint32_t rowbase, uint32_t &pwv, uint32_t &hmv) {
+        uint32_t p = rowbase + l;
+        bool head = true;                         // positions past the block end close every group
+        uint32_t v = 0;
+        if (p < n) {
+            uint64_t x = a[p];
+            uint64_t pv = p ? a[p - 1] : ~x;
+            head = ((x ^ pv) >> VAL_BITS) != 0;
+            uint32_t pos = (uint32_t)x & VMASK;
+            v = pos | (uint32_t)S.seq[b[pos ? pos - 1 : n - 1]] << 24;
+        }
+        pwv = v;
+        hmv = __ballot_sync(0xffffffffu, head);
+    };
+    auto emit = [&](uint32_t slot_abs, uint32_t pwv, uint32_t flag) {
+        uint32_t pos = pwv & VMASK;
+        sa[slot_abs] = pos | flag;
+        L[slot_abs] = (uint8_t)(pwv >> 24);
+        if (pos == 0) blocks[lb].orig_ptr = (int32_t)slot_abs;
+    };
+
+    uint32_t pw[FA_WIN], hm[FA_WIN];
+#pragma unroll
+    for (int j = 0; j < FA_WIN; j++) load_row(p0 + 32 * j, pw[j], hm[j]);
+
+    for (uint32_t R = 0; R < FA_ROWS; R++) {
+        const uint32_t rowbase = p0 + 32 * R;
+        if (rowbase >= n) break;
+        const uint32_t nv = min(32u, n - rowbase);
+        const uint32_t vmask = nv == 32 ? 0xffffffffu : (1u << nv) - 1;
+        const uint32_t h0 = hm[0] & vmask;                 // heads of real entries
+        if (h0) {
+            const uint32_t H0 = hm[0], h1 = hm[1], h2 = hm[2], h3 = hm[3];
+            // the last group that starts in this row may run on into the rows ahead
+            const uint32_t gl = 31 - (uint32_t)__clz(h0);
+            const uint32_t gel = fa_group_end(gl, H0, h1, h2, h3);
+            const bool spill = gel != FA_BIG && gel > 32;
+            const uint32_t ncov = spill ? (gel + 31) >> 5 : 1;
+            // own entry of the current row
+            const uint32_t mlow = h0 & (0xffffffffu >> (31 - l));
+            const bool owned = l < nv && mlow != 0;
+            uint32_t gs = 0, ge = 0;
+            if (owned) { gs = 31 - (uint32_t)__clz(mlow); ge = fa_group_end(l, H0, h1, h2, h3); }
+            const bool big = owned && ge == FA_BIG;
+            if (big && l == gs) big_list[atomicAdd(big_cnt, 1u)] = (uint64_t)lb << 32 | (rowbase + gs);
+            const bool single = owned && !big && ge - gs == 1;
+            if (single) emit(rowbase + l, pw[0], 0u);
+            bool memb[FA_WIN];
+            memb[0] = owned && !big && !single;
+#pragma unroll
+            for (int j = 1; j < FA_WIN; j++) memb[j] = spill && 32 * j + l < gel;
+            if (__any_sync(0xffffffffu, memb[0]) || spill) {
+                // ---- level 0: the next k32 symbols of every member, rank by counting ----
+                uint32_t key[FA_WIN];
+#pragma unroll
+                for (int j = 0; j < FA_WIN; j++) {
+                    key[j] = 0;
+                    if (j < (int)ncov && memb[j]) { key[j] = deeper_key(k30, pw[j] & VMASK, k0, n); dk[32 * j + l] = key[j]; }
+                }
+                __syncwarp();
+                uint32_t tied = 0;                         // bit j: entry j of this lane is still tied
+                uint32_t cs_[FA_WIN], rk_[FA_WIN];
+#pragma unroll
+                for (int j = 0; j < FA_WIN; j++) {
+                    cs_[j] = rk_[j] = 0;
+                    if (j < (int)ncov && memb[j]) {
+                        const uint32_t g0 = j ? gl : gs, g1 = j ? gel : ge, self = 32 * j + l, my = key[j];
+                        uint32_t ge_ = 0, le_ = 0;
+#pragma unroll 4
+                        for (uint32_t t = g0; t < g1; t++) {
+                            uint32_t x = dk[t];
+                            // += (x >= my), += (x <= my): the carry out of a subtraction, three instructions for both
+                            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(ge_) : "r"(x), "r"(my));
+                            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(le_) : "r"(my), "r"(x));
+                        }
+                        const uint32_t lt = g1 - g0 - ge_;
+                        if (ge_ + le_ - (g1 - g0) == 1) emit(rowbase + g0 + lt, pw[j], 0u);
+                        else {
+                            uint32_t eqb = 0;              // ties are rare: their order among equals is counted separately
+                            for (uint32_t t = g0; t < self; t++) eqb += dk[t] == my;
+                            tied |= 1u << j; cs_[j] = g0 + lt; rk_[j] = eqb;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (__any_sync(0xffffffffu, tied != 0)) {
+                    // ---- deeper levels on the warp's tied list ----
+                    uint32_t nt = 0;
+#pragma unroll
+                    for (int j = 0; j < FA_WIN; j++) {
+                        uint32_t m = __ballot_sync(0xffffffffu, (tied >> j) & 1u);
+                        if ((tied >> j) & 1u) {
+                            uint32_t u = nt + __popc(m & ltmask);
+                            t_pw[u] = pw[j]; t_cs[u] = (uint16_t)cs_[j]; t_rank[u] = (uint16_t)rk_[j];
+                        }
+                        nt += __popc(m);
+                    }
+                    __syncwarp();
+                    for (uint32_t level = 1; level < FLEVELS; level++) {
+#pragma unroll
+                        for (int r = 0; r < FA_WIN; r++) {
+                            uint32_t u = l + 32 * r;
+                            if (u < nt && t_cs[u] != 0xffffu) dk[u] = deeper_key(k30, t_pw[u] & VMASK, k0 + level * k32, n);
+                        }
+                        __syncwarp();
+                        uint32_t lt_[FA_WIN], eq_[FA_WIN], eqb_[FA_WIN];
+#pragma unroll
+                        for (int r = 0; r < FA_WIN; r++) {
+                            uint32_t u = l + 32 * r;
+                            lt_[r] = eq_[r] = eqb_[r] = 0;
+                            if (u < nt && t_cs[u] != 0xffffu) {
+                                uint32_t cs = t_cs[u], my = dk[u];
+                                for (uint32_t v = 0; v < nt; v++) {
+                                    if (t_cs[v] != cs) continue;
+                                    uint32_t x = dk[v];
+                                    lt_[r] += x < my;
+                                    uint32_t is = x == my;
+                                    eq_[r] += is;
+                                    eqb_[r] += is & (uint32_t)(v < u);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        bool live = false;
+#pragma unroll
+                        for (int r = 0; r < FA_WIN; r++) {
+                            uint32_t u = l + 32 * r;
+                            if (u < nt && t_cs[u] != 0xffffu) {
+                                uint32_t cs = t_cs[u];
+                                if (eq_[r] == 1) { emit(rowbase + cs + lt_[r], t_pw[u], 0u); t_cs[u] = 0xffffu; }
+                                else { t_cs[u] = (uint16_t)(cs + lt_[r]); t_rank[u] = (uint16_t)eqb_[r]; live = true; }
+                            }
+                        }
+                        __syncwarp();
+                        if (!__any_sync(0xffffffffu, live)) break;
+                    }
+                    // whatever is still tied goes out as an unsorted group
+#pragma unroll
+                    for (int r = 0; r < FA_WIN; r++) {
+                        uint32_t u = l + 32 * r;
+                        if (u < nt && t_cs[u] != 0xffffu) {
+                            uint32_t rr = t_rank[u];
+                            emit(rowbase + (uint32_t)t_cs[u] + rr, t_pw[u], rr ? NONHEAD : 0u);
+                            leftover++;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // advance the window
+#pragma unroll
+        for (int j = 0; j + 1 < FA_WIN; j++) { pw[j] = pw[j + 1]; hm[j] = hm[j + 1]; }
+        if (R + 1 < FA_ROWS) load_row(rowbase + 32 * FA_WIN, pw[FA_WIN - 1], hm[FA_WIN - 1]);
+    }
+    for (int d = 16; d; d >>= 1) leftover += __shfl_xor_sync(0xffffffffu, leftover, d);
+    if (l == 0 && leftover) { atomicAdd(&P.left[lb], leftover); atomicAdd(g_left, (unsigned long long)leftover); }
+}
+
+constexpr int FB_TH = 256;
+constexpr int FB_MAX = 2048;                     // largest group ranked in shared memory
+constexpr int FB_EPT = FB_MAX / FB_TH;
+
+struct FinBSmem {
+    uint32_t pw[FB_MAX], key[FB_MAX];
+    uint16_t cs[FB_MAX], rank[FB_MAX];
+    uint32_t end, live;
+    uint8_t seq[256];
+};
+
+__global__ void __launch_bounds__(FB_TH) k_finish_big(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks, uint8_t *lcol,
+                                                      const uint64_t *big_list, const uint32_t *big_cnt)
+{
+    __shared__ FinBSmem S;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nbig = *big_cnt;
+    for (uint32_t item = blockIdx.x; item < nbig; item += gridDim.x) {
+        const uint64_t it = big_list[item];
+        const uint32_t lb = (uint32_t)(it >> 32), start = (uint32_t)it;
+        const uint32_t n = P.cnt_n[lb];
+        const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
+        const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+        uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
+        const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
+        __syncthreads();                                  // the previous item is done with the shared arrays
+        S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
+        if (tid == 0) S.end = n;
+        __syncthreads();
+        // the group ends at the first position whose key differs
+        const uint64_t key0 = a[start] >> VAL_BITS;
+        for (uint32_t c = start + 1; c < n; c += FB_TH) {
+            uint32_t e = c + tid;
+            bool diff = e < n && (a[e] >> VAL_BITS) != key0;
+            if (diff) atomicMin(&S.end, e);
+            if (__syncthreads_or(diff)) break;
+        }
+        __syncthreads();
+        const uint32_t end = S.end, size = end - start;
+        auto emit = [&](uint32_t slot_abs, uint32_t pwv, uint32_t flag) {
+            uint32_t pos = pwv & VMASK;
+            sa[slot_abs] = pos | flag;
+            L[slot_abs] = (uint8_t)(pwv >> 24);
+            if (pos == 0) blocks[lb].orig_ptr = (int32_t)slot_abs;
+        };
+        if (size > FB_MAX) {
+            // left to the doubling rounds as one unsorted group
+            for (uint32_t e = start + tid; e < end; e += FB_TH) {
+                uint32_t pos = (uint32_t)a[e] & VMASK;
+                emit(e, pos | (uint32_t)S.seq[b[pos ? pos - 1 : n - 1]] << 24, e > start ? NONHEAD : 0u);
+            }
+            if (tid == 0) { atomicAdd(&P.left[lb], size); atomicAdd(g_left, (unsigned long long)size); }
+            continue;
+        }
+        for (uint32_t e = tid; e < size; e += FB_TH) {
+            uint32_t pos = (uint32_t)a[start + e] & VMASK;
+            S.pw[e] = pos | (uint32_t)S.seq[b[pos ? pos - 1 : n - 1]] << 24;
+            S.cs[e] = 0; S.rank[e] = (uint16_t)e;
+        }
+        if (tid == 0) S.live = 1;
+        __syncthreads();
+        for (uint32_t level = 0; level < FLEVELS; level++) {
+            for (uint32_t e = tid; e < size; e += FB_TH)
+                if (S.cs[e] != 0xffffu) S.key[e] = deeper_key(k30, S.pw[e] & VMASK, k0 + level * k32, n);
+            __syncthreads();
+            uint32_t lt_[FB_EPT], eq_[FB_EPT], eqb_[FB_EPT];
+#pragma unroll
+            for (int r = 0; r < FB_EPT; r++) {
+                uint32_t u = tid + r * FB_TH;
+                lt_[r] = eq_[r] = eqb_[r] = 0;
+                if (u < size && S.cs[u] != 0xffffu) {
+                    uint32_t cs = S.cs[u], my = S.key[u];
+                    for (uint32_t v = 0; v < size; v++) {
+                        if (S.cs[v] != cs) continue;
+                        uint32_t x = S.key[v];
+                        lt_[r] += x < my;
+                        uint32_t is = x == my;
+                        eq_[r] += is;
+                        eqb_[r] += is & (uint32_t)(v < u);
+                    }
+                }
+            }
+            __syncthreads();
+            bool live = false;
+#pragma unroll
+            for (int r = 0; r < FB_EPT; r++) {
+                uint32_t u = tid + r * FB_TH;
+                if (u < size && S.cs[u] != 0xffffu) {
+                    uint32_t cs = S.cs[u];
+                    if (eq_[r] == 1) { emit(start + cs + lt_[r], S.pw[u], 0u); S.cs[u] = 0xffffu; }
+                    else { S.cs[u] = (uint16_t)(cs + lt_[r]); S.rank[u] = (uint16_t)eqb_[r]; live = true; }
+                }
+            }
+            if (!__syncthreads_or(live)) break;
+        }
+        uint32_t leftover = 0;
+        for (uint32_t u = tid; u < size; u += FB_TH) {
+            if (S.cs[u] != 0xffffu) {
+                uint32_t rr = S.rank[u];
+                emit(start + (uint32_t)S.cs[u] + rr, S.pw[u], rr ? NONHEAD : 0u);
+                leftover++;
+            }
+        }
+        if (leftover) { atomicAdd(&P.left[lb], leftover); atomicAdd(g_left, (unsigned long long)leftover); }
+    }
+}
+
 // Blocks with leftovers: ranks (SA position of the group head, FINAL on singletons) from the NONHEAD
 // flags, flags cleared, so that the doubling rounds can take over at depth k.  Two tile-parallel
 // launches: the last group head of every tile, then the ranks with the carry from the earlier tiles.
@@ -1378,6 +1707,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.hist = ctx->hist.as<uint32_t>();
     uint32_t *misc = ctx->bwt_misc.as<uint32_t>();
     P.g_act = reinterpret_cast<unsigned long long *>(misc); misc += 4;
+    uint32_t *big_cnt = misc; misc += 2;
     P.cnt_n = misc; misc += nb;
     P.cnt_m = misc; misc += nb;
     P.act = misc; misc += 2 * nb;
@@ -1387,7 +1717,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.init_k32 = misc; misc += nb;
     P.init_f = misc; misc += nb;
     P.agg = misc;
-    S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 16, ctx->stream));
+    S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 24, ctx->stream));
     S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
     dim3 grid(NT, (unsigned)nb);
     double N = 0;                       // rotations in this batch
@@ -1459,8 +1789,13 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     }
     // ---- every group of up to FX rotations is finished in shared memory; SA, last column, origPtr ----
     S3G_BYTES(ctx, 18 * N);
-    S3G_LAUNCH(ctx, k_group_finish, dim3(FNT, (unsigned)nb), FTH, sizeof(FinSmem), P, sorted_kv, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
-               ctx->lcol.as<uint8_t>());
+    {
+        uint64_t *big_list = const_cast<uint64_t *>(sorted_kv) == P.kv0 ? P.kv1 : P.kv0;     // the free sort buffer
+        S3G_LAUNCH(ctx, k_finish_rows, dim3(FA_NT, (unsigned)nb), FA_WARPS * 32, 0, P, sorted_kv, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
+                   ctx->lcol.as<uint8_t>(), big_list, big_cnt);
+        S3G_LAUNCH(ctx, k_finish_big, SM_COUNT * 4, FB_TH, 0, P, sorted_kv, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(),
+                   big_list, big_cnt);
+    }
     S3G_TRY(check_launch("bwt init"));
     unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
     S3G_CUDA(cudaMemcpyAsync(h_act, P.g_act, 8, cudaMemcpyDeviceToHost, ctx->stream));
