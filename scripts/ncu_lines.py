@@ -8,20 +8,23 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 fn, hdr, sec = None, None, []
+def _i(x):
+    try: return int(x or 0)
+    except ValueError: return 0
 def flush():
     if not sec: return
     i_s = hdr.index("# Samples"); i_ie = hdr.index("Instructions Executed")
     stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-    tot = sum(int(r[i_s] or 0) for r in sec)
+    tot = sum(_i(r[i_s]) for r in sec)
     print(f"== {fn[:100]}  samples={tot}")
-    for r in sorted(sec, key=lambda r: -int(r[i_s] or 0))[:top]:
-        s = int(r[i_s] or 0)
-        st = sorted(((int(r[i] or 0), hdr[i][6:]) for i in stalls), reverse=True)[:3]
+    for r in sorted(sec, key=lambda r: -_i(r[i_s]))[:top]:
+        s = _i(r[i_s])
+        st = sorted(((_i(r[i]), hdr[i][6:]) for i in stalls), reverse=True)[:3]
         print(f"{r[0]:>5} {100.0*s/max(tot,1):5.1f}% inst={r[i_ie]:>10} {' '.join(f'{n}:{100*v//max(s,1)}' for v,n in st if v)} | {r[1].strip()[:110]}")
 for r in rows:
     if not r: continue
     if r[0] == "Function Name": flush(); fn = r[1]; sec = []; continue
     if r[0] == "Line No": hdr = r; continue
     if r[0] == "File Path" or hdr is None: continue
-    if r[0] != "": sec.append(r)
+    if r[0] != "" and len(r) >= len(hdr): sec.append(r)
 flush()

@@ -1069,20 +1069,27 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
     const uint32_t ltmask = (1u << l) - 1;
     uint32_t leftover = 0;
 
-    // one row of the window: rotation start | last-column symbol (bz/compress.c:166-167), head ballot
-    auto load_row = [&](uint32_t rowbase, uint32_t &pwv, uint32_t &hmv) {
+    // A row enters the window in three steps, one loop iteration apart, so that no load is waited for where
+    // it is issued: (A) the records of the row and of the position before it; (B) head ballot, rotation start
+    // and the gather of the byte before the rotation (bz/compress.c:166-167); (C) the byte's symbol rank.
+    auto issue_raw = [&](uint32_t rowbase, uint64_t &x, uint64_t &pv) {
         uint32_t p = rowbase + l;
-        bool head = true;                         // positions past the block end close every group
-        uint32_t v = 0;
-        if (p < n) {
-            uint64_t x = a[p];
-            uint64_t pv = p ? a[p - 1] : ~x;
-            head = ((x ^ pv) >> VAL_BITS) != 0;
-            uint32_t pos = (uint32_t)x & VMASK;
-            v = pos | (uint32_t)S.seq[b[pos ? pos - 1 : n - 1]] << 24;
-        }
-        pwv = v;
+        x = 0; pv = 0;
+        if (p < n) { x = a[p]; pv = a[p ? p - 1 : 0]; }
+    };
+    auto stage_b = [&](uint32_t rowbase, uint64_t x, uint64_t pv, uint32_t &posv, uint32_t &hmv, uint32_t &byv) {
+        uint32_t p = rowbase + l;
+        bool head = p >= n || p == 0 || ((x ^ pv) >> VAL_BITS) != 0;     // positions past the block end close every group
+        posv = (uint32_t)x & VMASK;
+        byv = p < n ? b[posv ? posv - 1 : n - 1] : 0;
         hmv = __ballot_sync(0xffffffffu, head);
+    };
+    auto stage_c = [&](uint32_t posv, uint32_t byv) { return posv | (uint32_t)S.seq[byv] << 24; };
+    // level-0 key of an entry of window row j unless it is a singleton (heads on both sides)
+    auto prefetch_key = [&](uint32_t rowbase_j, uint32_t pwv, uint32_t hj, uint32_t hnext) {
+        uint32_t nextbit = l < 31 ? (hj >> (l + 1)) & 1u : hnext & 1u;
+        bool single = ((hj >> l) & 1u) && nextbit;
+        return (rowbase_j + l < n && !single) ? deeper_key(k30, pwv & VMASK, k0, n) : 0u;
     };
     auto emit = [&](uint32_t slot_abs, uint32_t pwv, uint32_t flag) {
         uint32_t pos = pwv & VMASK;
@@ -1092,8 +1099,21 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
     };
 
     uint32_t pw[FA_WIN], hm[FA_WIN];
+    uint32_t kw[3];                     // level-0 keys of window rows 0..2
+    uint64_t xa, pva;                   // step A of row R + 5
+    uint32_t posb, hmb, byb;            // step B of row R + 4
 #pragma unroll
-    for (int j = 0; j < FA_WIN; j++) load_row(p0 + 32 * j, pw[j], hm[j]);
+    for (int j = 0; j < FA_WIN; j++) {
+        uint64_t x, pv; uint32_t ps, by;
+        issue_raw(p0 + 32 * j, x, pv);
+        stage_b(p0 + 32 * j, x, pv, ps, hm[j], by);
+        pw[j] = stage_c(ps, by);
+    }
+    issue_raw(p0 + 32 * 4, xa, pva);
+    stage_b(p0 + 32 * 4, xa, pva, posb, hmb, byb);
+    issue_raw(p0 + 32 * 5, xa, pva);
+    kw[0] = prefetch_key(p0, pw[0], hm[0], hm[1]);
+    kw[1] = prefetch_key(p0 + 32, pw[1], hm[1], hm[2]);
 
     for (uint32_t R = 0; R < FA_ROWS; R++) {
         const uint32_t rowbase = p0 + 32 * R;
@@ -1101,6 +1121,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
         const uint32_t nv = min(32u, n - rowbase);
         const uint32_t vmask = nv == 32 ? 0xffffffffu : (1u << nv) - 1;
         const uint32_t h0 = hm[0] & vmask;                 // heads of real entries
+        kw[2] = prefetch_key(rowbase + 64, pw[2], hm[2], hm[3]);
         if (h0) {
             const uint32_t H0 = hm[0], h1 = hm[1], h2 = hm[2], h3 = hm[3];
             // the last group that starts in this row may run on into the rows ahead
@@ -1127,7 +1148,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
 #pragma unroll
                 for (int j = 0; j < FA_WIN; j++) {
                     key[j] = 0;
-                    if (j < (int)ncov && memb[j]) { key[j] = deeper_key(k30, pw[j] & VMASK, k0, n); dk[32 * j + l] = key[j]; }
+                    if (j < (int)ncov && memb[j]) { key[j] = j < 3 ? kw[j] : deeper_key(k30, pw[j] & VMASK, k0, n); dk[32 * j + l] = key[j]; }
                 }
                 __syncwarp();
                 uint32_t tied = 0;                         // bit j: entry j of this lane is still tied
@@ -1223,7 +1244,10 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
         // advance the window
 #pragma unroll
         for (int j = 0; j + 1 < FA_WIN; j++) { pw[j] = pw[j + 1]; hm[j] = hm[j + 1]; }
-        if (R + 1 < FA_ROWS) load_row(rowbase + 32 * FA_WIN, pw[FA_WIN - 1], hm[FA_WIN - 1]);
+        kw[0] = kw[1]; kw[1] = kw[2];
+        pw[FA_WIN - 1] = stage_c(posb, byb); hm[FA_WIN - 1] = hmb;
+        stage_b(rowbase + 32 * 5, xa, pva, posb, hmb, byb);
+        issue_raw(R + 7 < FA_ROWS + 4 ? rowbase + 32 * 6 : n, xa, pva);
     }
     for (int d = 16; d; d >>= 1) leftover += __shfl_xor_sync(0xffffffffu, leftover, d);
     if (l == 0 && leftover) { atomicAdd(&P.left[lb], leftover); atomicAdd(g_left, (unsigned long long)leftover); }
