@@ -57,12 +57,15 @@ enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2, MODE_KVX = 3 };   // KVX: key/va
 
 // Records are 64 bits.  Initial sort: (40-bit symbol key << 20) | rotation start.  Doubling rounds:
 // (rank << 32) | rotation start.  A radix pass takes its 10-bit digit at bit `rshift` of the record.
-constexpr int KEY_BITS = 40;             // initial key
+#ifndef S3G_KEY_BITS
+#define S3G_KEY_BITS 44
+#endif
+constexpr int KEY_BITS = S3G_KEY_BITS;   // initial key (at most 64 - VAL_BITS)
 #ifndef S3G_SW_BITS
-#define S3G_SW_BITS 8
+#define S3G_SW_BITS 9
 #endif
 #ifndef S3G_SW_OCC
-#define S3G_SW_OCC 4
+#define S3G_SW_OCC 3
 #endif
 #ifndef S3G_SWT
 #define S3G_SWT 256
@@ -282,6 +285,8 @@ constexpr int SWI = S3G_SWI;                      // records per thread
 constexpr int SW_TILE = SWT * SWI;           // records per sweep tile
 constexpr int SW_NT = (BLK_STRIDE + SW_TILE - 1) / SW_TILE;
 constexpr int SW_DPT = SWN > SWT ? SWN / SWT : 1;    // digits per thread (threads past SWN own none)
+static_assert(SWN <= SWT || SWN % SWT == 0, "every digit needs an owner thread");
+static_assert(KEY_BITS + VAL_BITS <= 64 && NPASS * SW_BITS >= KEY_BITS, "record layout");
 
 struct SweepSmem {
     uint64_t stage[SW_TILE];               // tile in digit order (the per-warp peer masks live here while ranking)
