@@ -47,6 +47,9 @@ S3G_API const char *s3g_last_error(void);
 S3G_API int  s3g_set_stream(s3g_ctx *ctx, void *cuda_stream);
 /* Number of kernels launched by this context since creation (bench.py `gpu_launches`). */
 S3G_API uint64_t s3g_launch_count(const s3g_ctx *ctx);
+/* Times the block sort had to repeat its radix passes with peer-mask ranking because the keys left by the
+ * ordered-atomic ranking were not ascending (bwt.cu, k_sweep).  Expected to stay 0; a diagnostic. */
+S3G_API uint64_t s3g_sort_retries(const s3g_ctx *ctx);
 /* Per-kernel timing with CUDA events on the launching stream.  s3g_profile(ctx, 1) starts
  * recording; s3g_profile_report synchronises and writes one line per kernel name
  * ("name\tlaunches\ttotal_ms\talgorithmic_bytes\n") into buf, then clears the records. */

@@ -587,6 +587,14 @@ int s3g_set_stream(s3g_ctx *ctx, void *cuda_stream)
 
 uint64_t s3g_launch_count(const s3g_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+uint64_t s3g_sort_retries(const s3g_ctx *ctx)
+{
+    if (!ctx) return 0;
+    uint64_t r = ctx->sort_retries;
+    for (int k = 0; k < 2; k++) if (ctx->sub[k]) r += ctx->sub[k]->sort_retries;
+    return r;
+}
+
 int s3g_profile(s3g_ctx *ctx, int enable)
 {
     if (!ctx) { set_error("null context"); return S3G_E_PARAM; }

@@ -292,7 +292,7 @@ struct SweepSmem {
     uint64_t stage[SW_TILE];               // tile in digit order (the per-warp peer masks live here while ranking)
     uint32_t gbase[SWN];                   // (global offset - tile offset) of the digit
     uint32_t tbase[SWN];                   // offset of the digit inside the tile
-    uint16_t wcnt[(SWT / 32) * SWN];       // per-warp digit counters -> exclusive warp offsets
+    uint32_t wcnt[(SWT / 32) * SWN];       // per-warp digit counters -> exclusive warp offsets
     uint32_t scan[33];
     // first pass only: the records are built from the block bytes on the fly
     __align__(16) uint8_t sym[SW_TILE + 64];
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(SWN) k_digit_scan(uint32_t *ghist)
 // STABLE = false (the first pass only: the records arrive in position order, which carries no
 // meaning yet): ranks come straight from an atomicAdd on one per-tile counter per digit -- no
 // per-warp tables, no peer matching, and the records of a thread rank independently.
-template <bool STABLE, int EXP = 0>
+template <bool STABLE, int EXP = 0, bool SAFE = false>
 __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *dbase_all,
                                                       int pass, uint32_t *ticket_ctr, uint32_t nb, uint32_t gen, uint32_t G)
 {
@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *zm = reinterpret_cast<uint4 *>(S.stage), *zc = reinterpret_cast<uint4 *>(S.wcnt);
         if (STABLE) {
-            for (int i = tid; i < (SWT / 32) * SWN / 4; i += SWT) zm[i] = z;      // mask table: one word per warp and digit
-            for (int i = tid; i < (SWT / 32) * SWN / 8; i += SWT) zc[i] = z;      // counters: one halfword per warp and digit
+            if (SAFE) for (int i = tid; i < (SWT / 32) * SWN / 4; i += SWT) zm[i] = z;      // mask table: one word per warp and digit
+            for (int i = tid; i < (SWT / 32) * SWN / 4; i += SWT) zc[i] = z;                // counters: one word per warp and digit
         } else {
             for (int i = tid; i < SWN / 4; i += SWT) zc[i] = z;
         }
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
     if ((uint64_t)tile * SW_TILE >= cnt) return;
     uint32_t w = tid >> 5, l = tid & 31;
     uint32_t base = tile * SW_TILE + w * (SWI * 32) + l;
-    uint16_t *mycnt = S.wcnt + w * SWN;
+    uint32_t *mycnt = S.wcnt + w * SWN;
     uint32_t *M = Mall + w * SWN;
     const uint64_t *in = kv_in + (uint64_t)lb * BLK_STRIDE;
     uint64_t kv[SWI];
@@ -537,10 +537,19 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
                 unsigned lt = peers & ltmask;
                 uint32_t bb = ok ? mycnt[d] : 0u;
                 __syncwarp();
-                if (ok && lt == 0) mycnt[d] = (uint16_t)(bb + __popc(peers));
+                if (ok && lt == 0) mycnt[d] = bb + __popc(peers);
                 __syncwarp();
                 rnk[r] = (uint16_t)(bb + __popc(lt));
             }
+        } else if (!SAFE) {
+            // Ranks straight from one atomicAdd per record on the warp's own counter of the digit.  This is the
+            // stable rank only because the hardware serves the lanes of a warp that hit the same shared-memory
+            // word in ascending lane order (measured on B200: no exception in 3e10 trials, scratch/atom_order.cu),
+            // which nothing guarantees: the finisher checks that the keys it receives ascend, and run_bwt repeats
+            // the passes with SAFE = true (peer masks) if they ever do not.
+#pragma unroll
+            for (int r = 0; r < SWI; r++)
+                if ((okmask >> r) & 1u) rnk[r] = (uint16_t)atomicAdd(&mycnt[(uint32_t)(kv[r] >> rshift) & (SWN - 1)], 1u);
         } else {
 #pragma unroll
             for (int r = 0; r < SWI; r++) {
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
                 uint32_t bb = ok ? mycnt[d] : 0u;
                 __syncwarp();
                 uint32_t lt = peers & ltmask;
-                if (ok && lt == 0) { mycnt[d] = (uint16_t)(bb + __popc(peers)); M[d] = 0; }
+                if (ok && lt == 0) { mycnt[d] = bb + __popc(peers); M[d] = 0; }
                 __syncwarp();
                 rnk[r] = (uint16_t)(bb + __popc(lt));
             }
@@ -566,7 +575,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
                 int d = tid * DPT + q;
                 uint32_t run = 0;
 #pragma unroll
-                for (int ww = 0; ww < SWT / 32; ww++) { uint32_t c = S.wcnt[ww * SWN + d]; S.wcnt[ww * SWN + d] = (uint16_t)run; run += c; }
+                for (int ww = 0; ww < SWT / 32; ww++) { uint32_t c = S.wcnt[ww * SWN + d]; S.wcnt[ww * SWN + d] = run; run += c; }
                 tot4[q] = run; mysum += run;
             }
         }
@@ -624,7 +633,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
     for (int r = 0; r < SWI; r++) {
         if (okmask & (1u << r)) {
             uint32_t d = (uint32_t)(kv[r] >> rshift) & (SWN - 1);
-            S.stage[S.tbase[d] + (STABLE ? (uint32_t)mycnt[d] : 0u) + rnk[r]] = kv[r];
+            S.stage[S.tbase[d] + (STABLE ? mycnt[d] : 0u) + rnk[r]] = kv[r];
         }
     }
     __syncthreads();
@@ -1052,7 +1061,7 @@ __device__ __forceinline__ uint32_t fa_group_end(uint32_t e, uint32_t h0, uint32
 }
 
 __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
-                                                                  uint8_t *lcol, uint64_t *big_list, uint32_t *big_cnt)
+                                                                  uint8_t *lcol, uint64_t *big_list, uint32_t *big_cnt, uint32_t *unsorted)
 {
     __shared__ FinASmem S;
     const uint32_t lb = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -1085,6 +1094,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
     auto stage_b = [&](uint32_t rowbase, uint64_t x, uint64_t pv, uint32_t &posv, uint32_t &hmv, uint32_t &byv) {
         uint32_t p = rowbase + l;
         bool head = p >= n || p == 0 || ((x ^ pv) >> VAL_BITS) != 0;     // positions past the block end close every group
+        if (p < n && (pv >> VAL_BITS) > (x >> VAL_BITS)) *unsorted = 1u;   // the radix passes did not sort (see k_sweep)
         posv = (uint32_t)x & VMASK;
         byv = p < n ? b[posv ? posv - 1 : n - 1] : 0;
         hmv = __ballot_sync(0xffffffffu, head);
@@ -1736,7 +1746,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.hist = ctx->hist.as<uint32_t>();
     uint32_t *misc = ctx->bwt_misc.as<uint32_t>();
     P.g_act = reinterpret_cast<unsigned long long *>(misc); misc += 4;
-    uint32_t *big_cnt = misc; misc += 2;
+    uint32_t *big_cnt = misc; misc += 4;                       // [0] listed groups, [1] keys-out-of-order flag
     P.cnt_n = misc; misc += nb;
     P.cnt_m = misc; misc += nb;
     P.act = misc; misc += 2 * nb;
@@ -1746,8 +1756,6 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.init_k32 = misc; misc += nb;
     P.init_f = misc; misc += nb;
     P.agg = misc;
-    S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 24, ctx->stream));
-    S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
     dim3 grid(NT, (unsigned)nb);
     double N = 0;                       // rotations in this batch
     for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
@@ -1758,78 +1766,70 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_group_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KeysSmem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-#ifdef S3G_EXPERIMENT
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-#endif
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
         attr_done = true;
     }
     const uint32_t *no_act = nullptr;
     const uint64_t *no_kv = nullptr;
     uint32_t *no_out = nullptr;
     uint64_t *no_save = nullptr;
-    // ---- init: order by the first k symbols (40-bit key, four 10-bit onesweep passes; records end up in kv0) ----
-    S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * (NPASS * (SWN + 1) + 4) * 4));
+    // ---- init: order by the first k symbols (radix passes on the initial key), then the group finisher ----
+    S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * NPASS * (SWN + 1) * 4));
     uint32_t *ghist = ctx->bwt_ghist.as<uint32_t>();
     uint32_t *tickets = ghist + (size_t)nb * NPASS * SWN;        // [NPASS][nb]
-    S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * (NPASS * (SWN + 1) + 4) * 4, ctx->stream));
-    // look-back status words carry a generation tag; the table is cleared only when it is new, was used
-    // by the doubling rounds (as a histogram table) or the tag wraps
-    if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS + 4 > 255) {
-        S3G_CUDA(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->stream));
-        ctx->sweep_cap = ctx->hist.cap; ctx->sweep_gen = 0;
-    }
-    S3G_BYTES(ctx, 5 * N);
-    S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, ghist);
-    S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), SWN, 0, ghist);
-    const uint64_t *sorted_kv = nullptr;
-    {
+    unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
+    uint32_t G = SWEEP_G;
+    if (const char *e = getenv("S3G_SWEEP_G")) { int v = atoi(e); if (v > 0) G = (uint32_t)v; }
+    const unsigned sweep_grid = (unsigned)((nb + G - 1) / G) * G * SW_NT;
+    // attempt 0 ranks with ordered atomics (k_sweep, SAFE = false); if the finisher finds a key out of order
+    // the passes are repeated with peer masks.  S3G_SORT=safe skips the first attempt, S3G_SORT=broken makes it
+    // rank without any order (tests of the check and of the second attempt).
+    const char *sort_env = getenv("S3G_SORT");
+    const bool force_safe = sort_env && !strcmp(sort_env, "safe"), broken = sort_env && !strcmp(sort_env, "broken");
+    for (int attempt = force_safe ? 1 : 0; attempt < 2; attempt++) {
+        const bool safe = attempt == 1;
+        S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 32, ctx->stream));
+        S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
+        S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * NPASS * (SWN + 1) * 4, ctx->stream));
+        // look-back status words carry a generation tag; the table is cleared only when it is new, was used
+        // by the doubling rounds (as a histogram table) or the tag wraps
+        if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS > 255) {
+            S3G_CUDA(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->stream));
+            ctx->sweep_cap = ctx->hist.cap; ctx->sweep_gen = 0;
+        }
+        S3G_BYTES(ctx, 5 * N);
+        S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, ghist);
+        S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), SWN, 0, ghist);
         uint64_t *src = P.kv0, *dst = P.kv1;
-        uint32_t G = SWEEP_G;
-        if (const char *e = getenv("S3G_SWEEP_G")) { int v = atoi(e); if (v > 0) G = (uint32_t)v; }
-        const unsigned sweep_grid = (unsigned)((nb + G - 1) / G) * G * SW_NT;
         for (int pass = 0; pass < NPASS; pass++) {
             S3G_BYTES(ctx, 16 * N);
-            if (pass == 0)
-                S3G_LAUNCH(ctx, k_sweep<false>, sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS, src, dst, ghist, pass, tickets + (size_t)pass * nb,
-                           (uint32_t)nb, ++ctx->sweep_gen, G);
+            const int rshift = VAL_BITS + SW_BITS * pass;
+            uint32_t *tk = tickets + (size_t)pass * nb;
+            if (pass == 0 || (broken && !safe))
+                S3G_LAUNCH(ctx, (k_sweep<false>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+            else if (!safe)
+                S3G_LAUNCH(ctx, (k_sweep<true, 0, false>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             else
-                S3G_LAUNCH(ctx, k_sweep<true>, sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, dst, ghist, pass, tickets + (size_t)pass * nb,
-                           (uint32_t)nb, ++ctx->sweep_gen, G);
-#ifdef S3G_EXPERIMENT
-            if (pass == S3G_EXPERIMENT) {
-                S3G_TRY(ctx->exp_buf.ensure(slots * 8));
-                uint64_t *xb = ctx->exp_buf.as<uint64_t>();
-                uint32_t *xt = tickets + (size_t)NPASS * nb;
-                S3G_BYTES(ctx, 16 * N);
-                S3G_LAUNCH(ctx, (k_sweep<true, 1>), sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, xb, ghist, pass, xt, (uint32_t)nb, ++ctx->sweep_gen, G);
-                S3G_BYTES(ctx, 16 * N);
-                S3G_LAUNCH(ctx, (k_sweep<true, 2>), sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, xb, ghist, pass, xt + nb, (uint32_t)nb, ++ctx->sweep_gen, G);
-                S3G_BYTES(ctx, 16 * N);
-                S3G_LAUNCH(ctx, (k_sweep<true, 4>), sweep_grid, SWT, sizeof(SweepSmem), P, VAL_BITS + SW_BITS * pass, src, xb, ghist, pass, xt + 2 * nb, (uint32_t)nb, ++ctx->sweep_gen, G);
-            }
-#endif
+                S3G_LAUNCH(ctx, (k_sweep<true, 0, true>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             std::swap(src, dst);
         }
-        sorted_kv = src;
+        // every group that ends inside a warp's window is finished there, larger ones by one CTA each; SA, last column, origPtr
+        S3G_BYTES(ctx, 18 * N);
+        S3G_LAUNCH(ctx, k_finish_rows, dim3(FA_NT, (unsigned)nb), FA_WARPS * 32, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
+                   ctx->lcol.as<uint8_t>(), dst, big_cnt, big_cnt + 1);
+        S3G_LAUNCH(ctx, k_finish_big, SM_COUNT * 4, FB_TH, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(), dst, big_cnt);
+        S3G_TRY(check_launch("bwt init"));
+        S3G_CUDA(cudaMemcpyAsync(h_act, P.g_act, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        const uint32_t unsorted = reinterpret_cast<const uint32_t *>(h_act)[5];
+        if (getenv("S3G_DEBUG"))
+            fprintf(stderr, "[s3g] bwt attempt %d: %llu of %.0f rotations left to the doubling rounds%s\n", attempt, *h_act, N, unsorted ? "; keys OUT OF ORDER" : "");
+        if (!unsorted) break;
+        if (safe) { set_error("bwt: the radix passes did not sort the initial keys"); return S3G_E_CUDA; }
+        ctx->sort_retries++;
     }
-    // ---- every group of up to FX rotations is finished in shared memory; SA, last column, origPtr ----
-    S3G_BYTES(ctx, 18 * N);
-    {
-        uint64_t *big_list = const_cast<uint64_t *>(sorted_kv) == P.kv0 ? P.kv1 : P.kv0;     // the free sort buffer
-        S3G_LAUNCH(ctx, k_finish_rows, dim3(FA_NT, (unsigned)nb), FA_WARPS * 32, 0, P, sorted_kv, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
-                   ctx->lcol.as<uint8_t>(), big_list, big_cnt);
-        S3G_LAUNCH(ctx, k_finish_big, SM_COUNT * 4, FB_TH, 0, P, sorted_kv, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(),
-                   big_list, big_cnt);
-    }
-    S3G_TRY(check_launch("bwt init"));
-    unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
-    S3G_CUDA(cudaMemcpyAsync(h_act, P.g_act, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (getenv("S3G_DEBUG")) fprintf(stderr, "[s3g] bwt: %llu of %.0f rotations left to the doubling rounds\n", *h_act, N);
     if (*h_act == 0) return S3G_OK;
     // (sa with flags) -> ranks; the flag-free order lands in kv1's storage and is copied back
     S3G_LAUNCH(ctx, k_rebuild_agg, grid, RBT, 0, P);

@@ -181,6 +181,39 @@ def test_bwt_finisher_limits_and_fallback(ctx, oracle, name, blk):
     assert np.array_equal(ptr, optr), name
 
 
+@pytest.mark.parametrize("mode", ["safe", "broken"])
+def test_bwt_sort_safety_net(ctx, oracle, monkeypatch, mode):
+    """The radix passes rank with ordered shared-memory atomics and the finisher checks that the keys it
+    receives ascend (bwt.cu, k_sweep).  `safe` runs the peer-mask passes directly; `broken` makes the first
+    attempt rank without any order, so the check must trip and the second attempt must give the right answer."""
+    monkeypatch.setenv("S3G_SORT", mode)
+    before = ctx.sort_retries
+    blks = [_resolve_block(oracle, "cfg2", None), _resolve_block(oracle, "cfg4", None)[:300000], b"ab" * 3000 + b"c"]
+    got = ctx.bwt(blks)
+    for blk, (ptr, orig) in zip(blks, got):
+        optr, oorig = oracle.bwt(blk)
+        assert np.array_equal(ptr, optr)
+        assert orig == oorig
+    assert (ctx.sort_retries > before) == (mode == "broken")
+
+
+def test_bwt_window_limits(ctx, oracle):
+    """Groups around the sizes the warp finisher handles itself (a window of four rows: up to 97..128 rotations
+    depending on where the group starts) and the one-CTA-per-group kernel takes over (up to 2048)."""
+    rng = np.random.default_rng(5)
+    ctx9 = b"QRSTUVWXYZ012"
+    parts = [bytes(rng.integers(97, 123, 2000, dtype=np.uint8))]
+    for count in (31, 32, 33, 64, 95, 96, 97, 98, 127, 128, 129, 130, 200):
+        tag = ctx9 + b"%03d" % count
+        for i in rng.permutation(count):
+            parts.append(tag + (b"%04d" % int(i)) + bytes(rng.integers(97, 123, int(rng.integers(1, 9)), dtype=np.uint8)))
+    blk = b"".join(parts)
+    (ptr, orig), = ctx.bwt([blk])
+    optr, oorig = oracle.bwt(blk)
+    assert orig == oorig
+    assert np.array_equal(ptr, optr)
+
+
 def test_bwt_full_block_vs_reference(ctx, oracle):
     tf, _, _ = oracle.transform(synth.bed(1, 250000))
     blocks, rle = oracle.rle1_blocks(tf, 9)
