@@ -12,12 +12,19 @@
 namespace s3g {
 
 // ---- pool: compact storage of finished blocks ---------------------------------
-__global__ void k_pool_offsets(const BlockInfo *blocks, uint32_t nb, uint64_t pool_base, uint64_t *woff, uint64_t *total)
+__global__ void __launch_bounds__(1024) k_pool_offsets(const BlockInfo *blocks, uint32_t nb, uint64_t pool_base, uint64_t *woff, uint64_t *total)
 {
-    if (blockIdx.x || threadIdx.x) return;
-    uint64_t acc = pool_base;
-    for (uint32_t b = 0; b < nb; b++) { woff[b] = acc; acc += (blocks[b].n_bits + 31) >> 5; }
-    *total = acc;
+    __shared__ uint64_t sm[33];
+    uint64_t carry = pool_base;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 1024) {
+        uint32_t b = b0 + threadIdx.x;
+        uint64_t w = b < nb ? (blocks[b].n_bits + 31) >> 5 : 0, tot;
+        uint64_t ex = block_excl_sum<uint64_t>(w, sm, &tot);
+        if (b < nb) woff[b] = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
 }
 
 __global__ void k_pool_copy(const BlockInfo *blocks, const uint32_t *bits, const uint64_t *woff, uint32_t *pool)
@@ -34,7 +41,7 @@ int run_pool_append(Ctx *ctx, uint64_t b0, uint64_t nb)
     if (nb == 0) return S3G_OK;
     uint64_t *d_sc = ctx->scalars.as<uint64_t>();
     uint64_t *woff = ctx->pool_woff.as<uint64_t>() + b0;
-    S3G_LAUNCH(ctx, k_pool_offsets, 1, 1, 0, ctx->blocks.as<BlockInfo>() + b0, (uint32_t)nb, ctx->pool_words, woff, d_sc + 20);
+    S3G_LAUNCH(ctx, k_pool_offsets, 1, 1024, 0, ctx->blocks.as<BlockInfo>() + b0, (uint32_t)nb, ctx->pool_words, woff, d_sc + 20);
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 20, d_sc + 20, 8, cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     S3G_TRY(check_launch("pool offsets"));

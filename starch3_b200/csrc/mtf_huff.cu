@@ -132,46 +132,60 @@ __device__ __forceinline__ void mtf_zero_runs(const uint8_t *M, uint16_t *mtfv, 
 constexpr int MS = 512;                 // chunks (threads) per block
 constexpr int MTF_REG_MAX = 96;         // largest alphabet of the register-list kernel (12 list words; 96 x 512 x 4 B of shared memory)
 
-template <int NW>
+// List entries are FB-bit fields, FPW = 64 / FB per word (FB = 4 for alphabets <= 16: the whole list in one word;
+// FB = 5 for alphabets <= 24: two words; bytes otherwise).  Unused fields hold all ones, which no symbol equals.
+template <int FB> struct MtfPack {
+    static constexpr int FPW = 64 / FB;
+    static constexpr uint64_t WMASK = FPW * FB == 64 ? ~0ull : (1ull << (FPW * FB % 64)) - 1;
+    static constexpr uint64_t FMASK = (1ull << FB) - 1;
+    static constexpr uint64_t ones() { uint64_t k = 0; for (int i = 0; i < FPW; i++) k |= 1ull << (FB * i); return k; }
+    static constexpr uint64_t K1 = ones();
+    static constexpr uint64_t KH = K1 << (FB - 1);
+};
+
+template <int FB, int NW>
 __device__ __forceinline__ uint32_t mtf_step(uint64_t (&lst)[NW], uint32_t s)
 {
-    const uint64_t K1 = 0x0101010101010101ull, K80 = 0x8080808080808080ull;
-    uint64_t pat = (uint64_t)s * K1;
+    typedef MtfPack<FB> PK;
+    uint64_t pat = (uint64_t)s * PK::K1;
     int qh = 0; uint64_t zh = 0;
 #pragma unroll
     for (int q = NW - 1; q >= 0; q--) {
         uint64_t x = lst[q] ^ pat;
-        uint64_t z = (x - K1) & ~x & K80;        // lowest set bit marks the first zero byte of x
+        uint64_t z = (x - PK::K1) & ~x & PK::KH;      // lowest set bit marks the first zero field of x
         if (z) { qh = q; zh = z; }
     }
-    uint32_t bpos = (uint32_t)(__ffsll((long long)zh) - 1) >> 3;
-    uint64_t inmask = bpos == 7 ? ~0ull : ((1ull << (8 * (bpos + 1))) - 1);
+    uint32_t bit = (uint32_t)(__ffsll((long long)zh) - 1);
+    uint32_t bpos = FB == 8 ? bit >> 3 : FB == 4 ? bit >> 2 : (bit * 13u) >> 6;        // bit / FB (bit < 64)
+    uint64_t inmask = (bpos + 1) * FB >= 64 ? ~0ull : ((1ull << ((bpos + 1) * FB)) - 1);
     uint64_t carry = s;
 #pragma unroll
     for (int q = 0; q < NW; q++) {
         uint64_t old = lst[q];
-        uint64_t sh = (old << 8) | carry;
-        carry = old >> 56;
-        uint64_t m = q < qh ? ~0ull : (q == qh ? inmask : 0ull);
+        uint64_t sh = ((old << FB) | carry) & PK::WMASK;
+        carry = (old >> (FB * (PK::FPW - 1))) & PK::FMASK;
+        uint64_t m = q < qh ? PK::WMASK : (q == qh ? inmask : 0ull);
         lst[q] = (old & ~m) | (sh & m);
     }
-    return (uint32_t)qh * 8 + bpos;
+    return (uint32_t)qh * PK::FPW + bpos;
 }
 
-template <int NW>
+template <int FB, int NW>
 __device__ __forceinline__ void mtf_thread_chunk(const uint8_t *L, uint8_t *M, int beg, int end, const int *s_last, int a)
 {
+    typedef MtfPack<FB> PK;
     // initial list: symbols by decreasing last occurrence (virtual negative positions keep 0,1,2,.. for unseen ones)
     uint64_t lst[NW];
 #pragma unroll
-    for (int q = 0; q < NW; q++) lst[q] = ~0ull;
+    for (int q = 0; q < NW; q++) lst[q] = PK::WMASK;
     for (int c = 0; c < a; c++) {
         int v = s_last[c * MS + threadIdx.x];
         int rank = 0;
         for (int c2 = 0; c2 < a; c2++) rank += s_last[c2 * MS + threadIdx.x] > v ? 1 : 0;
+        const int rq = rank / PK::FPW, rf = rank % PK::FPW;
 #pragma unroll
         for (int q = 0; q < NW; q++)
-            if ((rank >> 3) == q) lst[q] = (lst[q] & ~(0xffull << (8 * (rank & 7)))) | ((uint64_t)c << (8 * (rank & 7)));
+            if (rq == q) lst[q] = (lst[q] & ~(PK::FMASK << (FB * rf))) | ((uint64_t)c << (FB * rf));
     }
     for (int p = beg; p < end; p += 8) {
         uint64_t in8 = *reinterpret_cast<const uint64_t *>(L + p);          // beg % 8 == 0, slots padded
@@ -180,7 +194,7 @@ __device__ __forceinline__ void mtf_thread_chunk(const uint8_t *L, uint8_t *M, i
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (k < lim) {
-                uint32_t pos = mtf_step<NW>(lst, (uint32_t)(in8 >> (8 * k)) & 0xffu);
+                uint32_t pos = mtf_step<FB, NW>(lst, (uint32_t)(in8 >> (8 * k)) & 0xffu);
                 out8 |= (uint64_t)pos << (8 * k);
             }
         }
@@ -233,19 +247,18 @@ __global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *
     __syncthreads();
     // phase C: ranks
     if (beg < end) {
-        switch ((a + 7) >> 3) {
-            case 1: mtf_thread_chunk<1>(L, M, beg, end, s_last, a); break;
-            case 2: mtf_thread_chunk<2>(L, M, beg, end, s_last, a); break;
-            case 3: mtf_thread_chunk<3>(L, M, beg, end, s_last, a); break;
-            case 4: mtf_thread_chunk<4>(L, M, beg, end, s_last, a); break;
-            case 5: mtf_thread_chunk<5>(L, M, beg, end, s_last, a); break;
-            case 6: mtf_thread_chunk<6>(L, M, beg, end, s_last, a); break;
-            case 7: mtf_thread_chunk<7>(L, M, beg, end, s_last, a); break;
-            case 8: mtf_thread_chunk<8>(L, M, beg, end, s_last, a); break;
-            case 9: mtf_thread_chunk<9>(L, M, beg, end, s_last, a); break;
-            case 10: mtf_thread_chunk<10>(L, M, beg, end, s_last, a); break;
-            case 11: mtf_thread_chunk<11>(L, M, beg, end, s_last, a); break;
-            default: mtf_thread_chunk<12>(L, M, beg, end, s_last, a); break;
+        if (a <= 16) mtf_thread_chunk<4, 1>(L, M, beg, end, s_last, a);
+        else if (a <= 24) mtf_thread_chunk<5, 2>(L, M, beg, end, s_last, a);
+        else switch ((a + 7) >> 3) {
+            case 4: mtf_thread_chunk<8, 4>(L, M, beg, end, s_last, a); break;
+            case 5: mtf_thread_chunk<8, 5>(L, M, beg, end, s_last, a); break;
+            case 6: mtf_thread_chunk<8, 6>(L, M, beg, end, s_last, a); break;
+            case 7: mtf_thread_chunk<8, 7>(L, M, beg, end, s_last, a); break;
+            case 8: mtf_thread_chunk<8, 8>(L, M, beg, end, s_last, a); break;
+            case 9: mtf_thread_chunk<8, 9>(L, M, beg, end, s_last, a); break;
+            case 10: mtf_thread_chunk<8, 10>(L, M, beg, end, s_last, a); break;
+            case 11: mtf_thread_chunk<8, 11>(L, M, beg, end, s_last, a); break;
+            default: mtf_thread_chunk<8, 12>(L, M, beg, end, s_last, a); break;
         }
     }
     __threadfence_block();

@@ -14,24 +14,43 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 #ifdef __CUDACC__
-// Kogge-Stone inclusive scan of one partial per thread through shared memory; any T / op.
+// shuffle of any trivially copyable T whose size is a multiple of 4 bytes
+template <class T> __device__ __forceinline__ T shfl_up_any(T v, int d)
+{
+    static_assert(sizeof(T) % 4 == 0, "shuffled word by word");
+    constexpr int W = sizeof(T) / 4;
+    union U { T t; uint32_t w[W]; __device__ U() {} } a, b;
+    a.t = v;
+#pragma unroll
+    for (int i = 0; i < W; i++) b.w[i] = __shfl_up_sync(0xffffffffu, a.w[i], d);
+    return b.t;
+}
+
+// Exclusive scan of one partial per thread, any T / associative op (operands stay in thread order):
+// shuffles inside the warp, the eight warp totals through shared memory.
 template <class F> __device__ __forceinline__ typename F::T block_scan_partials(typename F::T part, typename F::T *sm,
                                                                                typename F::T *block_total)
 {
     typedef typename F::T T;
-    const int t = threadIdx.x;
-    sm[t] = part;
-    __syncthreads();
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    T inc = part;
 #pragma unroll
-    for (int d = 1; d < SCAN_THREADS; d <<= 1) {
-        T v = sm[t];
-        if (t >= d) v = F::op(sm[t - d], v);
-        __syncthreads();
-        sm[t] = v;
-        __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = shfl_up_any(inc, d);
+        if (l >= d) inc = F::op(o, inc);
     }
-    T excl = t == 0 ? F::identity() : sm[t - 1];
-    *block_total = sm[SCAN_THREADS - 1];
+    if (l == 31) sm[w] = inc;
+    __syncthreads();
+    T pre = F::identity(), tot = F::identity();
+#pragma unroll
+    for (int ww = 0; ww < SCAN_THREADS / 32; ww++) {
+        T x = sm[ww];
+        if (ww < w) pre = F::op(pre, x);
+        tot = F::op(tot, x);
+    }
+    T up = shfl_up_any(inc, 1);
+    T excl = l == 0 ? pre : F::op(pre, up);
+    *block_total = tot;
     __syncthreads();
     return excl;
 }
