@@ -8,14 +8,15 @@
 // algorithm produces the order is free (bz/blocksort.c:1058-1061).
 //
 // Algorithm (all blocks of a batch in the same launches; DESIGN.md section 4, "The block sort"):
-//   keys     k_keys: 64-bit record (40-bit mixed-radix key of the first k symbols << 20 | rotation start),
-//            k = max{k : A^k <= 2^40}, A = symbols in use; the 32-bit key of every position; the digit
-//            histograms of all four radix passes.
-//   sort     k_sweep x 4: LSD radix passes, one kernel each (tile ranking, decoupled look-back).
-//   finish   k_group_finish: every group of equal keys (<= 2048 rotations) is ranked in shared memory on
-//            the 32-bit keys of the positions k, k+k32, ... further on -- bzip2's own "bucket, then compare
-//            strings" (bz/blocksort.c:751-1011) for blocks with short common prefixes.  Writes ptr[], the
-//            last column and origPtr.
+//   keys     k_keys: the 32-bit key (k32 symbols) of every position, and the digit histograms of all radix
+//            passes over the 44-bit initial key (mixed-radix key of the first k symbols, k = max{k : A^k <= 2^44},
+//            A = symbols in use, plus a class of the next symbol in the room that is left).
+//   sort     k_sweep x 5: LSD radix passes over 9-bit digits, one kernel each (the first builds the 64-bit
+//            records key << 20 | rotation start from the block bytes; tile ranking, decoupled look-back).
+//   finish   k_finish_rows / k_finish_big: every group of equal keys is ranked on the 32-bit keys of the
+//            positions k, k+k32, ... further on -- bzip2's own "bucket, then compare strings"
+//            (bz/blocksort.c:751-1011) for blocks with short common prefixes.  Writes ptr[], the last column
+//            and origPtr, and checks that the keys it receives ascend.
 //   fallback what the finisher leaves (groups > 2048, ties deeper than its levels) goes through Manber-Myers
 //            prefix-doubling rounds: given the order by the first h symbols (SA, grouped; RK[i] = SA position
 //            of the first member of i's group, bit 31 = group is a singleton), walking SA in order,
@@ -55,8 +56,8 @@ struct BwtP {
 
 enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2, MODE_KVX = 3 };   // KVX: key/value pairs saved by the histogram pass, ~0 = not taking part
 
-// Records are 64 bits.  Initial sort: (40-bit symbol key << 20) | rotation start.  Doubling rounds:
-// (rank << 32) | rotation start.  A radix pass takes its 10-bit digit at bit `rshift` of the record.
+// Records are 64 bits.  Initial sort: (44-bit symbol key << 20) | rotation start.  Doubling rounds:
+// (rank << 32) | rotation start.  A radix pass takes its digit at bit `rshift` of the record.
 #ifndef S3G_KEY_BITS
 #define S3G_KEY_BITS 44
 #endif
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(SWN) k_digit_scan(uint32_t *ghist)
 // STABLE = false (the first pass only: the records arrive in position order, which carries no
 // meaning yet): ranks come straight from an atomicAdd on one per-tile counter per digit -- no
 // per-warp tables, no peer matching, and the records of a thread rank independently.
-template <bool STABLE, int EXP = 0, bool SAFE = false>
+template <bool STABLE, bool SAFE = false>
 __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const uint64_t *kv_in, uint64_t *kv_out, const uint32_t *dbase_all,
                                                       int pass, uint32_t *ticket_ctr, uint32_t nb, uint32_t gen, uint32_t G)
 {
@@ -492,12 +493,6 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
             if (p < cnt) { kv[r] = in[p]; okmask |= 1u << r; }
         }
     }
-    if (EXP == 4) {
-        uint64_t *o4 = kv_out + (uint64_t)lb * BLK_STRIDE;
-#pragma unroll
-        for (int r = 0; r < SWI; r++) if (okmask & (1u << r)) o4[base + r * 32] = kv[r];
-        return;
-    }
     if (STABLE) {
         // the tile that will be handed out about two waves from now: pull it into L2 (128-byte lines)
         uint32_t tile2 = tile + 2 * SM_COUNT * SW_OCC / G + 1;
@@ -592,7 +587,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
             for (int q = 0; q < DPT; q++) status[(uint64_t)tile * SWN + q] = gtag | ST_AGG | tot4[q];
             uint32_t done = 0;                 // bit q: digit q has met an inclusive prefix
             uint32_t spins = 0;
-            for (int32_t t = (int32_t)tile - 1; EXP != 2 && t >= 0 && done != (1u << DPT) - 1;) {
+            for (int32_t t = (int32_t)tile - 1; t >= 0 && done != (1u << DPT) - 1;) {
                 uint32_t x[DPT];
 #pragma unroll
                 for (int q = 0; q < DPT; q++) x[q] = status[(uint64_t)t * SWN + q];
@@ -641,7 +636,6 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
     for (uint32_t i = tid; i < tile_total; i += SWT) {
         uint64_t it = S.stage[i];
         uint32_t d = (uint32_t)(it >> rshift) & (SWN - 1);
-        if (EXP == 1) out[tile * SW_TILE + i] = it; else
         out[S.gbase[d] + i] = it;
     }
 }
@@ -744,283 +738,25 @@ __global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const 
 }
 
 // ---- group finisher ---------------------------------------------------------------
-// After the initial sort every group (rotations with equal first k symbols) is contiguous in SA
-// order.  bzip2's own mainSort finishes such buckets with direct string comparisons
-// (bz/blocksort.c:347-469, :621-717) because real blocks have short common prefixes; the same holds
-// here, so one kernel finishes every group of up to FX rotations inside shared memory instead of
-// paying global radix passes per doubling round:
-//   level 0   key = the 32-bit key (k32 symbols) saved for position val+k, i.e. the NEXT symbols in one
-//             4-byte gather; rank inside the group by counting smaller/equal keys; unique keys are final
-//   level >=1 the few still-tied rotations move to a small list and repeat k32 symbols further on
-// Groups larger than FX and ties that survive FLEVELS levels (long repeats, periodic blocks) are
-// written out unsorted with a NONHEAD flag on every member but the first; only blocks that have
-// such leftovers go through the prefix-doubling rounds below.
-// A tile owns the groups that START inside it and reads past its end to the end of the last one;
-// whether a group is sorted here depends only on its size (<= FX), so the tile a group spills into
-// can tell without communication that the owner took care of it.
-constexpr int FTH = 256;                         // threads per finisher tile
-constexpr int FT = 1024;                         // SA positions owned by a tile
-constexpr int FX = 1024;                         // largest group sorted in shared memory (FX <= FT)
-constexpr int FWA = FT + FX + 64;                // window entries
-constexpr int FEPT = (FWA + FTH - 1) / FTH;      // consecutive entries per thread in the grouping phase
-constexpr int FNT = (BLK_STRIDE + FT - 1) / FT;  // finisher tiles per block slot
-constexpr int TCAP = 1024;                       // tied rotations a tile carries to deeper levels
-constexpr int FLEVELS = 12;                      // levels of k symbols before a tie is left to the doubling rounds
+// After the initial sort every group (rotations with equal initial keys) is contiguous in SA order.
+// bzip2's own mainSort finishes such buckets with direct string comparisons (bz/blocksort.c:347-469,
+// :621-717) because real blocks have short common prefixes; the same holds here, so the groups are
+// finished on deeper keys instead of paying global radix passes per doubling round:
+//   level 0   key = the 32-bit key (k32 symbols) saved for position start + k, i.e. the NEXT symbols in one
+//             4-byte gather; rank inside the group by counting smaller / equal keys; unique keys are final
+//   level >=1 the few still-tied rotations repeat this k32 symbols further on
+// Ties that survive FLEVELS levels and groups beyond FB_MAX (long repeats, periodic blocks) are written out
+// unsorted with a NONHEAD flag on every member but the first; only blocks that have such leftovers go
+// through the prefix-doubling rounds below.
+constexpr int FLEVELS = 12;                      // levels of k32 symbols before a tie is left to the doubling rounds
 constexpr uint32_t NONHEAD = 0x80000000u;        // SA flag: same (unsorted) group as the previous position
 constexpr uint32_t VMASK = 0x000fffffu;          // rotation start (< 2^20)
-
-constexpr int FROWS = (FWA + 31) / 32;           // 32-entry rows of the window
-
-struct FinSmem {
-    uint32_t key[FWA];        // low 32 bits of the initial key while grouping, level-0 key afterwards
-    uint32_t idx[FWA];        // rotation start (low 20 bits); the key's high bits above them while grouping
-    uint32_t gb[FWA];         // group start | group end << 16 (window-relative) of entries that take part in level 0
-    uint32_t out[FWA];        // final SA value per window position
-    uint32_t hbits[FROWS + 1];// bit l of word r: entry 32 r + l starts a group
-    uint32_t t_idx[TCAP], t_key[TCAP];
-    uint16_t t_cs[TCAP], t_rank[TCAP];
-    uint32_t scan[33];
-    uint32_t first_head, ntied, lo, hi, handled;
-    uint8_t seq[256];         // unseqToSeq of the block
-};
 
 __device__ __forceinline__ uint32_t deeper_key(const uint32_t *k30, uint32_t pos, uint32_t off, uint32_t n)
 {
     uint32_t p = pos + off;
     if (p >= n) { p -= n; if (p >= n) p %= n; }
     return k30[p];
-}
-
-// group start of entry e from the head bitmap: last head at or before e (0xffffffff if none in the window)
-__device__ __forceinline__ uint32_t fin_group_start(const uint32_t *hbits, uint32_t e)
-{
-    int w = (int)(e >> 5);
-    uint32_t m = hbits[w] & (0xffffffffu >> (31 - (e & 31)));
-    while (!m && w > 0) m = hbits[--w];
-    return m ? (uint32_t)w * 32 + (31 - __clz(m)) : 0xffffffffu;
-}
-// first head after e, or W if there is none
-__device__ __forceinline__ uint32_t fin_group_end(const uint32_t *hbits, uint32_t e, uint32_t W)
-{
-    uint32_t w = e >> 5, nw = (W + 31) >> 5;
-    uint32_t m = (e & 31) == 31 ? 0u : hbits[w] & (0xffffffffu << ((e & 31) + 1));
-    while (!m && ++w < nw) m = hbits[w];
-    uint32_t ge = m ? w * 32 + (uint32_t)__ffs(m) - 1 : W;
-    return ge < W ? ge : W;
-}
-
-__global__ void __launch_bounds__(FTH, 4) k_group_finish(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
-                                                         uint8_t *lcol)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FinSmem &S = *reinterpret_cast<FinSmem *>(smem_raw);
-    const uint32_t lb = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    const uint32_t n = P.cnt_n[lb];
-    const uint32_t base = tile * FT;
-    if (base >= n) return;
-    const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
-    const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
-    const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
-    const uint32_t avail = n - base;
-    constexpr int EPT = (FWA + FTH - 1) / FTH;       // entries per thread, entry = tid + j * FTH (row = warp + 16 j, bit = lane)
-    // ---- 1. load the tile, then extend to the end of the group that crosses its end ----
-    // record = key << 20 | start: key[] gets key bits 0..31, idx[] gets start | key bits 32.. << 20
-    uint32_t W = min(avail, (uint32_t)FT);
-    for (uint32_t e = tid; e < W; e += FTH) { uint64_t x = a[base + e]; S.key[e] = (uint32_t)(x >> VAL_BITS); S.idx[e] = (uint32_t)x & VMASK | (uint32_t)(x >> 52) << VAL_BITS; }
-    if (tid < 256) S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
-    if (tid == 0) {
-        S.first_head = (base == 0) || (a[base - 1] >> VAL_BITS) != (a[base] >> VAL_BITS);
-        S.ntied = 0; S.lo = 0; S.hi = 0; S.handled = 0;
-    }
-    __syncthreads();
-    if (avail > FT) {
-        const uint64_t lastkey = a[base + FT - 1] >> VAL_BITS;
-        while (W < FWA && W < avail) {
-            uint32_t e = W + tid;
-            bool found = false;
-            if (e < FWA && e < avail) {
-                uint64_t x = a[base + e];
-                S.key[e] = (uint32_t)(x >> VAL_BITS); S.idx[e] = (uint32_t)x & VMASK | (uint32_t)(x >> 52) << VAL_BITS;
-                found = (x >> VAL_BITS) != lastkey;
-            }
-            W = min(min(W + (uint32_t)FTH, (uint32_t)FWA), avail);
-            if (__syncthreads_or(found)) break;
-        }
-    }
-    const bool open_end = W < avail;              // the group holding entry W-1 continues past the window
-    const uint32_t tile_w = min(W, (uint32_t)FT);
-    // ---- 2. head bitmap: one ballot per 32-entry row ----
-#pragma unroll
-    for (int j = 0; j < EPT; j++) {
-        uint32_t e = tid + j * FTH;
-        if ((e & ~31u) < W) {                     // whole rows only: the ballot needs every lane of the warp
-            bool head = e >= W ? false
-                      : e == 0 ? S.first_head != 0 : (S.key[e] != S.key[e - 1] || (S.idx[e] ^ S.idx[e - 1]) >> VAL_BITS);
-            uint32_t hb = __ballot_sync(0xffffffffu, head);
-            if ((tid & 31) == 0) S.hbits[e >> 5] = hb;
-        }
-    }
-    __syncthreads();
-    // entries [0, c) continue a group that started in an earlier tile
-    if (tid == 0) {
-        uint32_t c = W;
-        for (uint32_t w = 0; w < (W + 31) / 32; w++) if (S.hbits[w]) { c = w * 32 + (uint32_t)__ffs(S.hbits[w]) - 1; break; }
-        // the owner sorted that group iff its size is <= FX; it ends at base + c
-        bool handled = false;
-        if (c > 0 && c < FT && !(c == W && open_end)) {
-            uint32_t end = base + c;
-            handled = end <= FX || (a[end - FX - 1] >> VAL_BITS) != (a[base] >> VAL_BITS);
-        }
-        S.handled = handled;
-        if (c >= tile_w) { S.lo = handled ? tile_w : 0; S.hi = tile_w; }   // no group starts in this tile
-        else S.lo = handled ? c : 0;
-    }
-    __syncthreads();
-    // ---- 3. classify every entry; unsorted ones fetch their level-0 key (the next k32 symbols) ----
-    const uint32_t handled = S.handled;
-    uint32_t leftover = 0;
-    uint32_t unsorted = 0;                        // bit j: entry tid + j * FTH takes part in level 0
-    uint32_t l0key[EPT];
-#pragma unroll
-    for (int j = 0; j < EPT; j++) {
-        uint32_t e = tid + j * FTH;
-        l0key[j] = 0;
-        if (e >= W) continue;
-        uint32_t v = S.idx[e] & VMASK;
-        uint32_t gs = fin_group_start(S.hbits, e);
-        if (gs == 0xffffffffu) {
-            // continuation of a group from an earlier tile: written here only when its owner could not sort it
-            if (!handled && e < tile_w) { S.out[e] = v | NONHEAD; leftover++; }
-            continue;
-        }
-        if (gs >= FT) continue;                   // belongs to the next tile
-        uint32_t ge = fin_group_end(S.hbits, e, W);
-        uint32_t size = ge - gs;
-        bool sortable = size <= FX && !(open_end && ge == W);
-        if (e + 1 == tile_w) S.hi = sortable ? ge : tile_w;     // the group holding the tile's last entry decides the written range
-        if (!sortable) {
-            if (e < tile_w) { S.out[e] = v | (e > gs ? NONHEAD : 0u); leftover++; }
-        } else if (size == 1) {
-            S.out[e] = v;
-        } else {
-            unsorted |= 1u << j;
-            S.gb[e] = gs | (ge << 16);
-            l0key[j] = deeper_key(k30, v, k0, n);
-        }
-    }
-    __syncthreads();                              // every read of the grouping keys is done
-#pragma unroll
-    for (int j = 0; j < EPT; j++) {
-        uint32_t e = tid + j * FTH;
-        if (e < W) S.idx[e] &= VMASK;
-        if (unsorted & (1u << j)) S.key[e] = l0key[j];
-    }
-    __syncthreads();
-    // ---- 4. level 0: rank inside the group by counting smaller / not larger keys ----
-#pragma unroll
-    for (int j = 0; j < EPT; j++) {
-        if (!(unsorted & (1u << j))) continue;
-        uint32_t e = tid + j * FTH;
-        uint32_t g = S.gb[e], gs = g & 0xffffu, ge = g >> 16;
-        uint32_t my = l0key[j], lt = 0, le = 0;
-#pragma unroll 4
-        for (uint32_t k = gs; k < ge; k++) {
-            uint32_t x = S.key[k];
-            lt += x < my;
-            le += x <= my;
-        }
-        uint32_t eq = le - lt;
-        if (eq == 1) S.out[gs + lt] = S.idx[e];
-        else {
-            uint32_t eqb = 0;                      // ties are rare: their order among equals is counted separately
-            for (uint32_t k = gs; k < e; k++) eqb += S.key[k] == my;
-            uint32_t slot = atomicAdd(&S.ntied, 1u);
-            if (slot < TCAP) { S.t_idx[slot] = S.idx[e]; S.t_cs[slot] = (uint16_t)(gs + lt); S.t_rank[slot] = (uint16_t)eqb; }
-            else { S.out[gs + lt + eqb] = S.idx[e] | (eqb ? NONHEAD : 0u); leftover++; }
-        }
-    }
-    __syncthreads();
-    // ---- 5. deeper levels on the tied list ----
-    const uint32_t nt_all = S.ntied;
-    const uint32_t nt = min(nt_all, (uint32_t)TCAP);
-    constexpr int TPT = TCAP / FTH;
-    if (nt_all <= TCAP) {
-        for (uint32_t level = 1; level < FLEVELS && nt; level++) {
-#pragma unroll
-            for (int r = 0; r < TPT; r++) {
-                uint32_t u = tid + r * FTH;
-                if (u < nt && S.t_cs[u] != 0xffffu) S.t_key[u] = deeper_key(k30, S.t_idx[u], k0 + level * k32, n);
-            }
-            __syncthreads();
-            uint32_t lt_[TPT], eq_[TPT], eqb_[TPT];
-#pragma unroll
-            for (int r = 0; r < TPT; r++) {
-                uint32_t u = tid + r * FTH;
-                lt_[r] = eq_[r] = eqb_[r] = 0;
-                if (u < nt && S.t_cs[u] != 0xffffu) {
-                    uint32_t cs = S.t_cs[u], my = S.t_key[u];
-                    for (uint32_t v = 0; v < nt; v++) {
-                        if (S.t_cs[v] != cs) continue;
-                        uint32_t x = S.t_key[v];
-                        lt_[r] += x < my;
-                        uint32_t is = x == my;
-                        eq_[r] += is;
-                        eqb_[r] += is & (uint32_t)(v < u);
-                    }
-                }
-            }
-            __syncthreads();
-            bool live = false;
-#pragma unroll
-            for (int r = 0; r < TPT; r++) {
-                uint32_t u = tid + r * FTH;
-                if (u < nt && S.t_cs[u] != 0xffffu) {
-                    uint32_t cs = S.t_cs[u];
-                    if (eq_[r] == 1) { S.out[cs + lt_[r]] = S.t_idx[u]; S.t_cs[u] = 0xffffu; }
-                    else { S.t_cs[u] = (uint16_t)(cs + lt_[r]); S.t_rank[u] = (uint16_t)eqb_[r]; live = true; }
-                }
-            }
-            if (!__syncthreads_or(live)) break;
-        }
-    }
-    // whatever is still tied goes out as an unsorted group
-#pragma unroll
-    for (int r = 0; r < TPT; r++) {
-        uint32_t u = tid + r * FTH;
-        if (u < nt && S.t_cs[u] != 0xffffu) {
-            uint32_t rk_ = S.t_rank[u];
-            S.out[(uint32_t)S.t_cs[u] + rk_] = S.t_idx[u] | (rk_ ? NONHEAD : 0u);
-            leftover++;
-        }
-    }
-    __syncthreads();
-    // ---- 6. write SA, the BWT last column (bz/compress.c:166-167) and origPtr (bz/blocksort.c:1083-1086) ----
-    const uint32_t lo = S.lo, hi = S.hi;
-    uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
-    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
-    uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
-    {
-        constexpr int OU = 4;
-        for (uint32_t pos0 = lo + tid; pos0 < hi; pos0 += FTH * OU) {
-            uint32_t v[OU]; uint8_t by[OU];
-#pragma unroll
-            for (int g = 0; g < OU; g++) { uint32_t pos = pos0 + g * FTH; v[g] = pos < hi ? S.out[pos] : 1u; }
-#pragma unroll
-            for (int g = 0; g < OU; g++) { uint32_t s_ = v[g] & VMASK; by[g] = b[s_ ? s_ - 1 : n - 1]; }
-#pragma unroll
-            for (int g = 0; g < OU; g++) {
-                uint32_t pos = pos0 + g * FTH;
-                if (pos < hi) {
-                    sa[base + pos] = v[g];
-                    L[base + pos] = S.seq[by[g]];
-                    if ((v[g] & VMASK) == 0) blocks[lb].orig_ptr = (int32_t)(base + pos);
-                }
-            }
-        }
-    }
-    uint32_t ltot;
-    block_excl_sum<uint32_t>(leftover, S.scan, &ltot);
-    if (tid == 0 && ltot) { atomicAdd(&P.left[lb], ltot); atomicAdd(g_left, (unsigned long long)ltot); }
 }
 
 // ---- group finisher, warp form -------------------------------------------------------
@@ -1568,7 +1304,7 @@ __global__ void k_bwt_setup(BwtP P, uint32_t nb)
 __global__ void __launch_bounds__(ST) k_bwt_finish(BwtP P, BlockInfo *blocks, uint8_t *lcol)
 {
     uint32_t lb = blockIdx.y, tile = blockIdx.x;
-    if (!P.left[lb]) return;            // finished by k_group_finish
+    if (!P.left[lb]) return;            // finished by k_finish_rows / k_finish_big
     uint32_t n = P.cnt_n[lb];
     if ((uint64_t)tile * STILE >= n) return;
     const uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
@@ -1764,10 +1500,9 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     if (!attr_done) {
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_group_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KeysSmem)));
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
         S3G_CUDA(cudaFuncSetAttribute((k_sweep<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
         attr_done = true;
     }
@@ -1810,9 +1545,9 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
             if (pass == 0 || (broken && !safe))
                 S3G_LAUNCH(ctx, (k_sweep<false>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             else if (!safe)
-                S3G_LAUNCH(ctx, (k_sweep<true, 0, false>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                S3G_LAUNCH(ctx, (k_sweep<true, false>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             else
-                S3G_LAUNCH(ctx, (k_sweep<true, 0, true>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                S3G_LAUNCH(ctx, (k_sweep<true, true>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             std::swap(src, dst);
         }
         // every group that ends inside a warp's window is finished there, larger ones by one CTA each; SA, last column, origPtr

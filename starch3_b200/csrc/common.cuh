@@ -94,7 +94,7 @@ struct Ctx {
     DevBuf scan_a, scan_b, scan_c, scalars;
     DevBuf tf, chroms, stat_a, stat_b, soff;
     DevBuf rle_carry, rle_ebase, blocks, blk_prov, blk_bytes, in_use, seq_map, stream_tab;
-    DevBuf sa, rk, kv0, kv1, hist, bwt_misc, bwt_ghist, lcol, exp_buf;
+    DevBuf sa, rk, kv0, kv1, hist, bwt_misc, bwt_ghist, lcol;
     size_t sweep_cap = 0;                  // capacity of `hist` when its look-back status words were last cleared
     uint32_t sweep_gen = 0;                // generation tag of the last radix pass (1..255)
     uint64_t sort_retries = 0;             // times the radix passes had to be repeated with peer-mask ranking (expected: never)
