@@ -21,9 +21,12 @@ def short(name):
     m = re.match(r"(k_hist|k_scatter)<(\d)>$", name)
     if m:
         return f"{m.group(1)}<{MODES[m.group(2)]}>"
-    m = re.match(r"(k_sweep)<\(bool\)([01])>$", name) or re.match(r"(k_sweep)<([01])>$", name)
+    m = re.match(r"k_sweep<(?:\(bool\))?([01]), (?:\(bool\))?([01])>$", name)
     if m:
-        return f"{m.group(1)}<{'true' if m.group(2) == '1' else 'false'}>"
+        return {"00": "k_sweep_first", "10": "k_sweep_ordered", "11": "k_sweep_masks"}.get(m.group(1) + m.group(2), name)
+    m = re.match(r"k_huff<(?:\(int\))?(\d+)>$", name)
+    if m:
+        return f"k_huff<{m.group(1)}>"
     m = re.match(r"(k_bound_\w+)<([01])>$", name)
     if m:
         return f"{m.group(1)}<{'true' if m.group(2) == '1' else 'false'}>"

@@ -1462,6 +1462,11 @@ __global__ void k_fallback_exact(BwtP P, BlockInfo *blocks)
 #undef FB_CLR
 #undef FB_GET
 
+// the three forms of a radix pass under the names the per-kernel report uses
+static const auto k_sweep_first = k_sweep<false, false>;      // pass 0: records built from the block bytes, no order to keep
+static const auto k_sweep_ordered = k_sweep<true, false>;     // stable ranks from ordered shared-memory atomics (checked by the finisher)
+static const auto k_sweep_masks = k_sweep<true, true>;        // stable ranks from peer masks (the repeat if that check fails)
+
 int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
 {
     if (nb == 0) return S3G_OK;
@@ -1501,9 +1506,9 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KeysSmem)));
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        S3G_CUDA(cudaFuncSetAttribute((k_sweep<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep_ordered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
         attr_done = true;
     }
     const uint32_t *no_act = nullptr;
@@ -1543,11 +1548,11 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
             const int rshift = VAL_BITS + SW_BITS * pass;
             uint32_t *tk = tickets + (size_t)pass * nb;
             if (pass == 0 || (broken && !safe))
-                S3G_LAUNCH(ctx, (k_sweep<false>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                S3G_LAUNCH(ctx, k_sweep_first, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             else if (!safe)
-                S3G_LAUNCH(ctx, (k_sweep<true, false>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                S3G_LAUNCH(ctx, k_sweep_ordered, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             else
-                S3G_LAUNCH(ctx, (k_sweep<true, true>), sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                S3G_LAUNCH(ctx, k_sweep_masks, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
             std::swap(src, dst);
         }
         // every group that ends inside a warp's window is finished there, larger ones by one CTA each; SA, last column, origPtr

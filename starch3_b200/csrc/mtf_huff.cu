@@ -367,7 +367,8 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
 // =============================================================================
 // (3d) Huffman table selection and emission
 // =============================================================================
-constexpr int HT = 1024;
+// k_huff runs with HT = 1024 threads (one CTA per SM: shortest time for one block) or, when a batch holds more
+// blocks than SMs, with 512 (two CTAs per SM: one block's serial phases overlap the other's parallel ones)
 constexpr int G_SIZE = 50;               // BZ_G_SIZE
 constexpr int N_ITERS = 4;               // BZ_N_ITERS
 constexpr int MAX_SEL = 18002;           // BZ_MAX_SELECTORS
@@ -471,7 +472,8 @@ struct HuffSmem {
 };
 
 // first_block_flags: bit0 set -> this block also carries nothing extra; stream headers are added by the assembler
-__global__ void __launch_bounds__(HT) k_huff(const uint16_t *mtfv_all, const int32_t *freq_all, const uint8_t *in_use_all,
+template <int HT>
+__global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all, const int32_t *freq_all, const uint8_t *in_use_all,
                                              BlockInfo *blocks, uint32_t *bits_all, uint8_t *sel_out, uint8_t *len_out,
                                              int with_block_header)
 {
@@ -718,15 +720,21 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
     S3G_TRY(ctx->bits.ensure((size_t)nb * BITS_WORDS * 4));
     static bool attr_done = false;
     if (!attr_done) {
-        S3G_CUDA(cudaFuncSetAttribute(k_huff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_huff<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_huff<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
         attr_done = true;
     }
     double N = 0;
     for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
     S3G_BYTES(ctx, 6 * 2 * 0.67 * N + 0.25 * N);      // 4 selection passes + size + emit over uint16 symbols, bits out
-    S3G_LAUNCH(ctx, k_huff, (unsigned)nb, HT, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
-               ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
-               d_sel_out, d_len_out, with_block_header);
+    if (nb > (uint64_t)SM_COUNT)
+        S3G_LAUNCH(ctx, k_huff<512>, (unsigned)nb, 512, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
+                   ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
+                   d_sel_out, d_len_out, with_block_header);
+    else
+        S3G_LAUNCH(ctx, k_huff<1024>, (unsigned)nb, 1024, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
+                   ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
+                   d_sel_out, d_len_out, with_block_header);
     return check_launch("huff");
 }
 
