@@ -450,7 +450,7 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     // cut points at line starts; the first range is shorter than the others (nothing can run until it has arrived)
     std::vector<uint64_t> cut(nparts + 1, n);
     cut[0] = 0;
-    double first = 0.75 / nparts;
+    double first = 0.5 / nparts;
     if (const char *e = getenv("S3G_FIRST")) { double v = atof(e); if (v > 0 && v < 1) first = v; }
     for (int i = 1; i < nparts; i++) {
         double frac = first + (1.0 - first) * (i - 1) / (nparts - 1);
