@@ -24,6 +24,9 @@ def short(name):
     m = re.match(r"k_sweep<(?:\(bool\))?([01]), (?:\(bool\))?([01])>$", name)
     if m:
         return {"00": "k_sweep_first", "10": "k_sweep_ordered", "11": "k_sweep_masks"}.get(m.group(1) + m.group(2), name)
+    m = re.match(r"k_mtf_small<(?:\(int\))?(\d+), (?:\(bool\))?([01])>$", name)
+    if m:
+        return "k_mtf_list_small" if m.group(2) == "1" else "k_mtf_list_big"
     m = re.match(r"k_huff<(?:\(int\))?(\d+)>$", name)
     if m:
         return f"k_huff<{m.group(1)}>"

@@ -129,7 +129,8 @@ __device__ __forceinline__ void mtf_zero_runs(const uint8_t *M, uint16_t *mtfv, 
 // masked one-byte shift.  A block is cut into 512 chunks, one per thread; the list a chunk
 // starts with is the symbols ordered by their last occurrence before the chunk.
 // =============================================================================
-constexpr int MS = 512;                 // chunks (threads) per block
+constexpr int MS_BIG = 512;             // chunks (threads) per block, lists of up to 12 words
+constexpr int MS_SMALL = 768;           // alphabets <= 24: a list of one or two words needs few registers, so two such CTAs fit an SM
 constexpr int MTF_REG_MAX = 96;         // largest alphabet of the register-list kernel (12 list words; 96 x 512 x 4 B of shared memory)
 
 // List entries are FB-bit fields, FPW = 64 / FB per word (FB = 4 for alphabets <= 16: the whole list in one word;
@@ -170,7 +171,7 @@ __device__ __forceinline__ uint32_t mtf_step(uint64_t (&lst)[NW], uint32_t s)
     return (uint32_t)qh * PK::FPW + bpos;
 }
 
-template <int FB, int NW>
+template <int FB, int NW, int MS>
 __device__ __forceinline__ void mtf_thread_chunk(const uint8_t *L, uint8_t *M, int beg, int end, const int *s_last, int a)
 {
     typedef MtfPack<FB> PK;
@@ -202,8 +203,9 @@ __device__ __forceinline__ void mtf_thread_chunk(const uint8_t *L, uint8_t *M, i
     }
 }
 
-__global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
-                                                  BlockInfo *blocks, int rows)
+template <int MS, bool SMALL>
+__global__ void __launch_bounds__(MS, 2) k_mtf_small(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
+                                                     BlockInfo *blocks, int rows)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *s_last = reinterpret_cast<int *>(smem_raw);            // [rows][MS], rows = largest alphabet (<= MTF_REG_MAX) in the batch
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *
     const uint32_t lb = blockIdx.x;
     const int n = (int)blocks[lb].nblock;
     const int a = (int)blocks[lb].n_in_use;
-    if (a > MTF_REG_MAX) return;                                // handled by k_mtf
+    if (a > MTF_REG_MAX || (a <= 24) != SMALL) return;          // handled by k_mtf or by the other instantiation
     if (a > rows) __trap();                                     // host mirror out of date: fail loudly
     const uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
     uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
@@ -247,18 +249,19 @@ __global__ void __launch_bounds__(MS) k_mtf_small(const uint8_t *lcol, uint8_t *
     __syncthreads();
     // phase C: ranks
     if (beg < end) {
-        if (a <= 16) mtf_thread_chunk<4, 1>(L, M, beg, end, s_last, a);
-        else if (a <= 24) mtf_thread_chunk<5, 2>(L, M, beg, end, s_last, a);
-        else switch ((a + 7) >> 3) {
-            case 4: mtf_thread_chunk<8, 4>(L, M, beg, end, s_last, a); break;
-            case 5: mtf_thread_chunk<8, 5>(L, M, beg, end, s_last, a); break;
-            case 6: mtf_thread_chunk<8, 6>(L, M, beg, end, s_last, a); break;
-            case 7: mtf_thread_chunk<8, 7>(L, M, beg, end, s_last, a); break;
-            case 8: mtf_thread_chunk<8, 8>(L, M, beg, end, s_last, a); break;
-            case 9: mtf_thread_chunk<8, 9>(L, M, beg, end, s_last, a); break;
-            case 10: mtf_thread_chunk<8, 10>(L, M, beg, end, s_last, a); break;
-            case 11: mtf_thread_chunk<8, 11>(L, M, beg, end, s_last, a); break;
-            default: mtf_thread_chunk<8, 12>(L, M, beg, end, s_last, a); break;
+        if (SMALL) {
+            if (a <= 16) mtf_thread_chunk<4, 1, MS>(L, M, beg, end, s_last, a);
+            else mtf_thread_chunk<5, 2, MS>(L, M, beg, end, s_last, a);
+        } else switch ((a + 7) >> 3) {
+            case 4: mtf_thread_chunk<8, 4, MS>(L, M, beg, end, s_last, a); break;
+            case 5: mtf_thread_chunk<8, 5, MS>(L, M, beg, end, s_last, a); break;
+            case 6: mtf_thread_chunk<8, 6, MS>(L, M, beg, end, s_last, a); break;
+            case 7: mtf_thread_chunk<8, 7, MS>(L, M, beg, end, s_last, a); break;
+            case 8: mtf_thread_chunk<8, 8, MS>(L, M, beg, end, s_last, a); break;
+            case 9: mtf_thread_chunk<8, 9, MS>(L, M, beg, end, s_last, a); break;
+            case 10: mtf_thread_chunk<8, 10, MS>(L, M, beg, end, s_last, a); break;
+            case 11: mtf_thread_chunk<8, 11, MS>(L, M, beg, end, s_last, a); break;
+            default: mtf_thread_chunk<8, 12, MS>(L, M, beg, end, s_last, a); break;
         }
     }
     __threadfence_block();
@@ -333,6 +336,10 @@ __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, 
     mtf_zero_runs<MT>(M, mtfv, n, a, s_freq, s_scan, blocks, lb, freq_all);
 }
 
+// the register-list kernel in its two forms, under the names the per-kernel report uses
+static const auto k_mtf_list_small = k_mtf_small<MS_SMALL, true>;
+static const auto k_mtf_list_big = k_mtf_small<MS_BIG, false>;
+
 int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
 {
     if (nb == 0) return S3G_OK;
@@ -350,15 +357,27 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
         if (a == 0) rows = MTF_REG_MAX;                        // alphabet not mirrored on the host: size for the worst case
     }
     if (ctx->h_blocks.size() < b0 + nb) rows = MTF_REG_MAX;
-    const size_t small_smem = (size_t)rows * MS * 4 + 260 * 4 + 40 * 4;
+    bool any_small = false, any_big = false;                   // which forms of the register-list kernel this batch needs
+    for (uint64_t b = 0; b < nb; b++) {
+        int a = b0 + b < ctx->h_blocks.size() ? (int)ctx->h_blocks[b0 + b].n_in_use : 0;
+        if (a == 0) any_small = any_big = true;
+        else if (a <= 24) any_small = true;
+        else if (a <= MTF_REG_MAX) any_big = true;
+    }
+    const size_t tail_smem = 260 * 4 + 40 * 4;
     static bool attr_done = false;
     if (!attr_done) {
-        S3G_CUDA(cudaFuncSetAttribute(k_mtf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MTF_REG_MAX * MS * 4 + 260 * 4 + 40 * 4)));
+        S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)24 * MS_SMALL * 4 + tail_smem)));
+        S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MTF_REG_MAX * MS_BIG * 4 + tail_smem)));
         attr_done = true;
     }
     S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
-    S3G_LAUNCH(ctx, k_mtf_small, (unsigned)nb, MS, small_smem, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
-               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, rows);
+    if (any_small)
+        S3G_LAUNCH(ctx, k_mtf_list_small, (unsigned)nb, MS_SMALL, (size_t)std::min(rows, 24) * MS_SMALL * 4 + tail_smem, ctx->lcol.as<uint8_t>(),
+                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, std::min(rows, 24));
+    if (any_big)
+        S3G_LAUNCH(ctx, k_mtf_list_big, (unsigned)nb, MS_BIG, (size_t)rows * MS_BIG * 4 + tail_smem, ctx->lcol.as<uint8_t>(),
+                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, rows);
     S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
                ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
     return check_launch("mtf");
