@@ -4,7 +4,7 @@
 # usage: scripts/gpu_profile.sh <tag> [kernel-regex]
 set -u
 TAG=${1:-r1}
-KRE=${2:-"k_sweep|k_group_finish|k_keys|k_mtf_small|k_huff"}
+KRE=${2:-"k_sweep|k_finish_rows|k_keys|k_mtf_small|k_huff"}
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?"
@@ -17,5 +17,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/la
 echo "launch list rc=$?"
 CMD2="python bench.py --lines 10000000 --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD2 > $O/plain2_$TAG.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s 8 -c 8 -f -o $O/prof_$TAG $CMD2 > $O/ncu_f_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s 9 -c 9 -f -o $O/prof_$TAG $CMD2 > $O/ncu_f_$TAG.log 2>&1
 echo "ncu full rc=$?"

@@ -67,7 +67,9 @@ if os.path.exists(f):
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-            "launch__registers_per_thread", "smsp__inst_executed.sum", "launch__grid_size"]
+            "launch__registers_per_thread", "smsp__inst_executed.sum", "launch__grid_size",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
     ix = {w: h.index(w) for w in want if w in h}
     ki = h.index("Kernel Name")
     def tobytes(v, u):
@@ -80,8 +82,9 @@ if os.path.exists(f):
     with open(os.path.join(P, f"{tag}_ncu_full_summary.md"), "w") as o:
         o.write(f"# {tag} -- `ncu --set full --clock-control none` of the dominant kernels\n\n"
                 f"Command: `python bench.py --lines {lines} --steps 1 --warmup 1 --no-cpu-baseline` (cfg2), one launch per row, in launch order.\n"
-                "dram = dram__bytes_read.sum + dram__bytes_write.sum; the other columns are % of peak sustained.\n\n"
-                "| kernel | us | dram MB | dram GB/s | L2 MB | dram % | L2 % | SM % | warps active % | regs | grid |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+                "dram = dram__bytes_read.sum + dram__bytes_write.sum; the other columns are % of peak sustained.\n"
+                "smem wf = shared-memory wavefronts (one per SM per cycle at best), of which `conflict` are bank-conflict replays; issue % = issue slots used.\n\n"
+                "| kernel | us | dram MB | dram GB/s | L2 MB | dram % | L2 % | SM % | issue % | warps active % | smem wf M | conflict M | smem pipe busy % | regs | grid |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
         for row in r[2:]:
             g = lambda w: row[ix[w]] if w in ix else "0"
             us = tous(g("gpu__time_duration.sum"), units[ix["gpu__time_duration.sum"]])
@@ -91,7 +94,11 @@ if os.path.exists(f):
             traffic.setdefault(k, []).append(dr)
             o.write(f"| {k} | {us:.1f} | {dr / 1e6:.1f} | {dr / us / 1e3:.0f} | {l2 / 1e6:.1f} | {float(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
                     f"{float(g('lts__throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(g('sm__throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
-                    f"{float(g('sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | {g('launch__registers_per_thread')} | {g('launch__grid_size')} |\n")
+                    f"{float(g('smsp__issue_active.avg.pct_of_peak_sustained_active')):.1f} | "
+                    f"{float(g('sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | {float(g('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum').replace(',', '')) / 1e6:.0f} | "
+                    f"{float(g('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum').replace(',', '')) / 1e6:.0f} | "
+                    f"{100 * float(g('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum').replace(',', '')) / 148 / (us * 1965.0):.0f} | "
+                    f"{g('launch__registers_per_thread')} | {g('launch__grid_size')} |\n")
     json.dump({"tag": tag, "lines": lines, "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over captured launches), bytes",
                "kernels": {k: sum(v) / len(v) for k, v in traffic.items()}}, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
     print("full capture:", {k: len(v) for k, v in traffic.items()})
