@@ -62,17 +62,27 @@ __device__ __forceinline__ void mtf_zero_runs(const uint8_t *M, uint16_t *mtfv, 
     uint32_t out_base = 0;       // symbols written so far
     uint32_t nz_carry = 0;       // (position + 1) of the last non-zero rank so far
     int fa = 0, fb = 0;          // private RUNA / RUNB counts
+    // the ranks of the next tile are requested while this one goes through its two block scans
+    uint64_t v_next = 0; uint8_t e_next = 1;
+    {
+        int q0 = (int)threadIdx.x * DI;
+        if (q0 + DI < n) { v_next = *reinterpret_cast<const uint64_t *>(M + q0); e_next = M[q0 + DI]; }
+    }
     for (int tile0 = 0; tile0 < n; tile0 += THREADS * DI) {
         int p0 = tile0 + (int)threadIdx.x * DI;
         uint8_t m[DI + 1];
         if (p0 + DI < n) {
-            uint64_t v = *reinterpret_cast<const uint64_t *>(M + p0);      // slots are 128-byte aligned, p0 % 8 == 0
+            uint64_t v = v_next;                                           // slots are 128-byte aligned, p0 % 8 == 0
 #pragma unroll
             for (int k = 0; k < DI; k++) m[k] = (uint8_t)(v >> (8 * k));
-            m[DI] = M[p0 + DI];
+            m[DI] = e_next;
         } else {
 #pragma unroll
             for (int k = 0; k <= DI; k++) m[k] = (p0 + k < n) ? M[p0 + k] : (uint8_t)1;   // past the end acts as non-zero
+        }
+        {
+            int q0 = p0 + THREADS * DI;
+            if (q0 + DI < n) { v_next = *reinterpret_cast<const uint64_t *>(M + q0); e_next = M[q0 + DI]; }
         }
         uint32_t lastnz = 0;
 #pragma unroll
