@@ -548,12 +548,12 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     StreamMap sm{d_soff, n_streams};
     S3G_BYTES(ctx, n);
     S3G_LAUNCH(ctx, k_rle_runs, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry);
-    S3G_LAUNCH(ctx, k_scan_agg<MaxU64>, 1, SCAN_THREADS, 0, run_carry, ntiles, (uint64_t *)nullptr);
+    S3G_LAUNCH(ctx, k_scan_agg<MaxU64>, 1, AGG_THREADS, 0, run_carry, ntiles, (uint64_t *)nullptr);
     S3G_TRY(ctx->io_c.ensure((ntiles + 1) * RT * 2));
     S3G_TRY(ctx->io_e.ensure((ntiles + 1) * RT));
     S3G_BYTES(ctx, n + n * 3 / 16);
     S3G_LAUNCH(ctx, k_rle_emit_count, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base, ctx->io_c.as<uint16_t>(), ctx->io_e.as<uint8_t>());
-    S3G_LAUNCH(ctx, k_scan_agg<SumU64b>, 1, SCAN_THREADS, 0, e_base, ntiles, d_sc + 16);
+    S3G_LAUNCH(ctx, k_scan_agg<SumU64b>, 1, AGG_THREADS, 0, e_base, ntiles, d_sc + 16);
     // e_base[ntiles] = total, so E() can be evaluated at n
     S3G_CUDA(cudaMemcpyAsync(e_base + ntiles, d_sc + 16, 8, cudaMemcpyDeviceToDevice, ctx->stream));
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 16, d_sc + 16, 8, cudaMemcpyDeviceToHost, ctx->stream));

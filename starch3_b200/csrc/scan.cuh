@@ -28,8 +28,8 @@ template <class T> __device__ __forceinline__ T shfl_up_any(T v, int d)
 
 // Exclusive scan of one partial per thread, any T / associative op (operands stay in thread order):
 // shuffles inside the warp, the eight warp totals through shared memory.
-template <class F> __device__ __forceinline__ typename F::T block_scan_partials(typename F::T part, typename F::T *sm,
-                                                                               typename F::T *block_total)
+template <class F, int NTH = SCAN_THREADS> __device__ __forceinline__ typename F::T block_scan_partials(typename F::T part, typename F::T *sm,
+                                                                                                    typename F::T *block_total)
 {
     typedef typename F::T T;
     const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -43,7 +43,7 @@ template <class F> __device__ __forceinline__ typename F::T block_scan_partials(
     __syncthreads();
     T pre = F::identity(), tot = F::identity();
 #pragma unroll
-    for (int ww = 0; ww < SCAN_THREADS / 32; ww++) {
+    for (int ww = 0; ww < NTH / 32; ww++) {
         T x = sm[ww];
         if (ww < w) pre = F::op(pre, x);
         tot = F::op(tot, x);
@@ -70,13 +70,14 @@ template <class F> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce
 }
 
 // single CTA: exclusive scan of the tile aggregates in place; total -> *total
-template <class F> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_agg(typename F::T *agg, uint64_t ntiles,
-                                                                              typename F::T *total)
+constexpr int AGG_THREADS = 1024;
+template <class F> __global__ void __launch_bounds__(AGG_THREADS) k_scan_agg(typename F::T *agg, uint64_t ntiles,
+                                                                             typename F::T *total)
 {
     typedef typename F::T T;
-    __shared__ T sm[SCAN_THREADS];
+    __shared__ T sm[AGG_THREADS / 32];
     T carry = F::identity();
-    for (uint64_t base = 0; base < ntiles; base += SCAN_TILE) {
+    for (uint64_t base = 0; base < ntiles; base += (uint64_t)AGG_THREADS * SCAN_ITEMS) {
         uint64_t i0 = base + (uint64_t)threadIdx.x * SCAN_ITEMS;
         T v[SCAN_ITEMS];
         T acc = F::identity();
@@ -86,7 +87,7 @@ template <class F> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_agg(ty
             acc = F::op(acc, v[k]);
         }
         T tot;
-        T excl = block_scan_partials<F>(acc, sm, &tot);
+        T excl = block_scan_partials<F, AGG_THREADS>(acc, sm, &tot);
         T run = F::op(carry, excl);
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) {
@@ -127,7 +128,7 @@ template <class F> int device_scan(Ctx *ctx, F f, uint64_t n, typename F::T *agg
     if (ntiles == 0) ntiles = 1;
     if (ntiles > 0x7fffffffull) { set_error("scan too large"); return S3G_E_LIMIT; }
     S3G_LAUNCH(ctx, k_scan_reduce<F>, (unsigned)ntiles, SCAN_THREADS, 0, f, n, agg);
-    S3G_LAUNCH(ctx, k_scan_agg<F>, 1, SCAN_THREADS, 0, agg, ntiles, d_total);
+    S3G_LAUNCH(ctx, k_scan_agg<F>, 1, AGG_THREADS, 0, agg, ntiles, d_total);
     S3G_LAUNCH(ctx, k_scan_apply<F>, (unsigned)ntiles, SCAN_THREADS, 0, f, n, agg);
     return check_launch("device_scan");
 }

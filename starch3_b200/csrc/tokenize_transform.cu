@@ -317,7 +317,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     uint64_t *tile_cnt = ctx->tile_cnt.as<uint64_t>();
     S3G_BYTES(ctx, n);
     S3G_LAUNCH(ctx, k_count_newlines, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt, skip);
-    S3G_LAUNCH(ctx, k_scan_agg<SumU64>, 1, SCAN_THREADS, 0, tile_cnt, ntiles, d_sc + 0);
+    S3G_LAUNCH(ctx, k_scan_agg<SumU64>, 1, AGG_THREADS, 0, tile_cnt, ntiles, d_sc + 0);
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 8, cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     uint64_t n_lines = ctx->h_scalars[0];
@@ -368,7 +368,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     Stat3 *d_stat_total = reinterpret_cast<Stat3 *>(d_sc + 8);
     unsigned sgrid = (unsigned)(stiles - 1 ? stiles - 1 : 1);
     S3G_LAUNCH(ctx, k_scan_reduce<StatScan>, sgrid, SCAN_THREADS, 0, f3, n_lines, ctx->scan_c.as<Stat3>());
-    S3G_LAUNCH(ctx, k_scan_agg<StatScan>, 1, SCAN_THREADS, 0, ctx->scan_c.as<Stat3>(), (uint64_t)sgrid, d_stat_total);
+    S3G_LAUNCH(ctx, k_scan_agg<StatScan>, 1, AGG_THREADS, 0, ctx->scan_c.as<Stat3>(), (uint64_t)sgrid, d_stat_total);
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     S3G_TRY(check_launch("transform sizes"));
