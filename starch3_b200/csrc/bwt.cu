@@ -786,14 +786,12 @@ struct FinASmem {
     uint8_t seq[256];
 };
 
-__device__ __forceinline__ uint32_t fa_group_end(uint32_t e, uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3)
+// end of the group that holds entry e of the current row: the next head in the row, else `ahead`, the first
+// head of the rows ahead (the same for every lane: computed once per row)
+__device__ __forceinline__ uint32_t fa_group_end(uint32_t e, uint32_t h0, uint32_t ahead)
 {
     uint32_t mh = e >= 31 ? 0u : (h0 & (0xfffffffeu << e));
-    if (mh) return (uint32_t)__ffs(mh) - 1;
-    if (h1) return 32 + (uint32_t)__ffs(h1) - 1;
-    if (h2) return 64 + (uint32_t)__ffs(h2) - 1;
-    if (h3) return 96 + (uint32_t)__ffs(h3) - 1;
-    return FA_BIG;
+    return mh ? (uint32_t)__ffs(mh) - 1 : ahead;
 }
 
 __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
@@ -874,17 +872,19 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
         const uint32_t h0 = hm[0] & vmask;                 // heads of real entries
         kw[2] = prefetch_key(rowbase + 64, pw[2], hm[2], hm[3]);
         if (h0) {
-            const uint32_t H0 = hm[0], h1 = hm[1], h2 = hm[2], h3 = hm[3];
+            const uint32_t H0 = hm[0];
+            const uint32_t ahead = hm[1] ? 32 + (uint32_t)__ffs(hm[1]) - 1 : hm[2] ? 64 + (uint32_t)__ffs(hm[2]) - 1
+                                 : hm[3] ? 96 + (uint32_t)__ffs(hm[3]) - 1 : FA_BIG;
             // the last group that starts in this row may run on into the rows ahead
             const uint32_t gl = 31 - (uint32_t)__clz(h0);
-            const uint32_t gel = fa_group_end(gl, H0, h1, h2, h3);
+            const uint32_t gel = fa_group_end(gl, H0, ahead);
             const bool spill = gel != FA_BIG && gel > 32;
             const uint32_t ncov = spill ? (gel + 31) >> 5 : 1;
             // own entry of the current row
             const uint32_t mlow = h0 & (0xffffffffu >> (31 - l));
             const bool owned = l < nv && mlow != 0;
             uint32_t gs = 0, ge = 0;
-            if (owned) { gs = 31 - (uint32_t)__clz(mlow); ge = fa_group_end(l, H0, h1, h2, h3); }
+            if (owned) { gs = 31 - (uint32_t)__clz(mlow); ge = fa_group_end(l, H0, ahead); }
             const bool big = owned && ge == FA_BIG;
             if (big && l == gs) big_list[atomicAdd(big_cnt, 1u)] = (uint64_t)lb << 32 | (rowbase + gs);
             const bool single = owned && !big && ge - gs == 1;
@@ -1008,7 +1008,9 @@ constexpr int FB_TH = 256;
 constexpr int FB_MAX = 2048;                     // largest group ranked in shared memory
 constexpr int FB_EPT = FB_MAX / FB_TH;
 
+constexpr int FB_SORT_MIN = 256;                 // groups above this size get their level-0 order from a bitonic sort
 struct FinBSmem {
+    uint64_t srt[FB_MAX];                        // (level-0 key << 32 | member index), sorted
     uint32_t pw[FB_MAX], key[FB_MAX];
     uint16_t cs[FB_MAX], rank[FB_MAX];
     uint32_t end, live;
@@ -1067,7 +1069,46 @@ __global__ void __launch_bounds__(FB_TH) k_finish_big(BwtP P, const uint64_t *kv
         }
         if (tid == 0) S.live = 1;
         __syncthreads();
-        for (uint32_t level = 0; level < FLEVELS; level++) {
+        uint32_t level0 = 0;
+        bool need_levels = true;
+        if (size > FB_SORT_MIN) {
+            // level 0 by sorting: counting costs size^2 comparisons, and sorted BED with serial ids makes groups of
+            // hundreds of rotations whose next symbols all differ
+            uint32_t p2 = 512;
+            while (p2 < size) p2 <<= 1;
+            for (uint32_t e = tid; e < p2; e += FB_TH)
+                S.srt[e] = e < size ? (uint64_t)deeper_key(k30, S.pw[e] & VMASK, k0, n) << 32 | e : ~0ull;
+            __syncthreads();
+            for (uint32_t kk = 2; kk <= p2; kk <<= 1) {
+                for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                    for (uint32_t t = tid; t < p2 / 2; t += FB_TH) {
+                        uint32_t i = 2 * t - (t & (j - 1)), ix = i + j;          // the pair (i, i + j), i without bit j
+                        uint64_t x = S.srt[i], y = S.srt[ix];
+                        bool up = (i & kk) == 0;
+                        if ((x > y) == up) { S.srt[i] = y; S.srt[ix] = x; }
+                    }
+                    __syncthreads();
+                }
+            }
+            // unique keys are final; runs of equal keys go on to the deeper levels as ties
+            bool mytie = false;
+            for (uint32_t p_ = tid; p_ < size; p_ += FB_TH) {
+                uint64_t x = S.srt[p_];
+                uint32_t key = (uint32_t)(x >> 32), e = (uint32_t)x;
+                bool tie_lo = p_ > 0 && (uint32_t)(S.srt[p_ - 1] >> 32) == key;
+                bool tie_hi = p_ + 1 < size && (uint32_t)(S.srt[p_ + 1] >> 32) == key;
+                if (!tie_lo && !tie_hi) { emit(start + p_, S.pw[e], 0u); S.cs[e] = 0xffffu; }
+                else {
+                    uint32_t c = p_;
+                    while (c > 0 && (uint32_t)(S.srt[c - 1] >> 32) == key) c--;
+                    S.cs[e] = (uint16_t)c; S.rank[e] = (uint16_t)(p_ - c);
+                    mytie = true;
+                }
+            }
+            need_levels = __syncthreads_or(mytie);
+            level0 = 1;
+        }
+        for (uint32_t level = level0; need_levels && level < FLEVELS; level++) {
             for (uint32_t e = tid; e < size; e += FB_TH)
                 if (S.cs[e] != 0xffffu) S.key[e] = deeper_key(k30, S.pw[e] & VMASK, k0 + level * k32, n);
             __syncthreads();
