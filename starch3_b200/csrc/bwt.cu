@@ -13,7 +13,8 @@
 //            A = symbols in use, plus a class of the next symbol in the room that is left).
 //   sort     k_sweep x 5: LSD radix passes over 9-bit digits, one kernel each (the first builds the 64-bit
 //            records key << 20 | rotation start from the block bytes; tile ranking, decoupled look-back).
-//   finish   k_finish_rows / k_finish_big: every group of equal keys is ranked on the 32-bit keys of the
+//   finish   k_finish_rows / k_finish_mid / k_finish_big (a warp's window / a warp / a CTA per group, by size):
+//            every group of equal keys is ranked on the 32-bit keys of the
 //            positions k, k+k32, ... further on -- bzip2's own "bucket, then compare strings"
 //            (bz/blocksort.c:751-1011) for blocks with short common prefixes.  Writes ptr[], the last column
 //            and origPtr, and checks that the keys it receives ascend.
@@ -765,11 +766,12 @@ __device__ __forceinline__ uint32_t deeper_key(const uint32_t *k30, uint32_t pos
 // groups whose head lies in it; a group that ends inside the window is ranked by the warp itself
 // (level-0 keys through a per-warp shared-memory strip, counting smaller / equal keys; the few ties go
 // to a per-warp list for the deeper levels), singletons are written straight from registers, and a
-// group that does not end inside the window is appended to a work list for k_finish_big.  Entries
+// group that does not end inside the window is appended to a work list for k_finish_mid.  Entries
 // before the first head of a row belong to an earlier row's group and are skipped: their owner wrote
 // them, or listed the group.
-// k_finish_big: one CTA per listed group: groups of up to FB_MAX rotations are ranked in shared memory
-// level by level, larger ones are written out unsorted (NONHEAD flags) for the doubling rounds.
+// k_finish_mid: one warp per listed group of up to FM_MAX rotations; k_finish_big: one CTA per longer group: up to
+// FB_MAX rotations are ranked in shared memory (level 0 by a bitonic sort, ties level by level), larger ones are
+// written out unsorted (NONHEAD flags) for the doubling rounds.
 constexpr int FA_WARPS = 8;
 constexpr int FA_ROWS = 32;                              // rows a warp walks
 constexpr int FA_TILE = FA_WARPS * FA_ROWS * 32;         // SA positions per CTA
@@ -1002,6 +1004,125 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
     }
     for (int d = 16; d; d >>= 1) leftover += __shfl_xor_sync(0xffffffffu, leftover, d);
     if (l == 0 && leftover) { atomicAdd(&P.left[lb], leftover); atomicAdd(g_left, (unsigned long long)leftover); }
+}
+
+// k_finish_mid: one WARP per listed group of up to FM_MAX rotations (sorted BED with serial ids makes very many groups
+// of a hundred or so: a CTA each would spend its time in barriers); longer ones are passed on to k_finish_big.
+constexpr int FM_MAX = 256;
+constexpr int FM_WARPS = 8;
+constexpr int FM_EPL = FM_MAX / 32;               // entries per lane
+struct FinMSmem {
+    uint32_t key[FM_WARPS][FM_MAX], pw[FM_WARPS][FM_MAX];
+    uint16_t cs[FM_WARPS][FM_MAX], rank[FM_WARPS][FM_MAX];
+};
+
+__global__ void __launch_bounds__(FM_WARPS * 32) k_finish_mid(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
+                                                              uint8_t *lcol, const uint64_t *big_list, const uint32_t *big_cnt,
+                                                              uint64_t *big_list2, uint32_t *big_cnt2)
+{
+    __shared__ FinMSmem S;
+    const uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const uint32_t nbig = *big_cnt;
+    uint32_t *key = S.key[w], *pw = S.pw[w];
+    uint16_t *cs = S.cs[w], *rank = S.rank[w];
+    for (uint32_t item = blockIdx.x * FM_WARPS + w; item < nbig; item += gridDim.x * FM_WARPS) {
+        const uint64_t it = big_list[item];
+        const uint32_t lb = (uint32_t)(it >> 32), start = (uint32_t)it;
+        const uint32_t n = P.cnt_n[lb];
+        const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
+        const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *seq = P.seq + (uint64_t)lb * 256;
+        uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
+        uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
+        const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
+        // the group ends at the first position whose key differs
+        const uint64_t key0 = a[start] >> VAL_BITS;
+        uint32_t end = 0;
+        for (uint32_t c = start + 1; c <= start + FM_MAX; c += 32) {
+            uint32_t e = c + l;
+            bool diff = e >= n || (a[e] >> VAL_BITS) != key0;
+            uint32_t m = __ballot_sync(0xffffffffu, diff);
+            if (m) { end = c + (uint32_t)__ffs(m) - 1; break; }
+        }
+        if (end == 0 || end - start > FM_MAX) {
+            if (l == 0) big_list2[atomicAdd(big_cnt2, 1u)] = it;
+            continue;
+        }
+        const uint32_t size = end - start;
+        auto emit = [&](uint32_t slot_abs, uint32_t pwv, uint32_t flag) {
+            uint32_t pos = pwv & VMASK;
+            sa[slot_abs] = pos | flag;
+            L[slot_abs] = (uint8_t)(pwv >> 24);
+            if (pos == 0) blocks[lb].orig_ptr = (int32_t)slot_abs;
+        };
+        __syncwarp();
+        for (uint32_t e = l; e < size; e += 32) {
+            uint32_t pos = (uint32_t)a[start + e] & VMASK;
+            pw[e] = pos | (uint32_t)seq[b[pos ? pos - 1 : n - 1]] << 24;
+            cs[e] = 0; rank[e] = (uint16_t)e;
+        }
+        __syncwarp();
+        for (uint32_t level = 0; level < FLEVELS; level++) {
+            for (uint32_t e = l; e < size; e += 32)
+                if (cs[e] != 0xffffu) key[e] = deeper_key(k30, pw[e] & VMASK, k0 + level * k32, n);
+            __syncwarp();
+            uint32_t lt_[FM_EPL], eq_[FM_EPL], eqb_[FM_EPL];
+#pragma unroll
+            for (int r = 0; r < FM_EPL; r++) {
+                uint32_t u = l + 32 * r;
+                lt_[r] = eq_[r] = eqb_[r] = 0;
+                if (u < size && cs[u] != 0xffffu) {
+                    const uint32_t c = cs[u], my = key[u];
+                    if (level == 0) {
+                        // everybody is in the one group: two carry-out additions per comparison (see k_finish_rows)
+                        uint32_t ge_ = 0, le_ = 0;
+#pragma unroll 4
+                        for (uint32_t v = 0; v < size; v++) {
+                            uint32_t x = key[v];
+                            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(ge_) : "r"(x), "r"(my));
+                            asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(le_) : "r"(my), "r"(x));
+                        }
+                        lt_[r] = size - ge_; eq_[r] = ge_ + le_ - size;
+                        if (eq_[r] > 1) for (uint32_t v = 0; v < u; v++) eqb_[r] += key[v] == my;
+                    } else {
+                        for (uint32_t v = 0; v < size; v++) {
+                            if (cs[v] != c) continue;
+                            uint32_t x = key[v];
+                            lt_[r] += x < my;
+                            uint32_t is = x == my;
+                            eq_[r] += is;
+                            eqb_[r] += is & (uint32_t)(v < u);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            bool live = false;
+#pragma unroll
+            for (int r = 0; r < FM_EPL; r++) {
+                uint32_t u = l + 32 * r;
+                if (u < size && cs[u] != 0xffffu) {
+                    uint32_t c = cs[u];
+                    if (eq_[r] == 1) { emit(start + c + lt_[r], pw[u], 0u); cs[u] = 0xffffu; }
+                    else { cs[u] = (uint16_t)(c + lt_[r]); rank[u] = (uint16_t)eqb_[r]; live = true; }
+                }
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, live)) break;
+        }
+        uint32_t leftover = 0;
+        for (uint32_t u = l; u < size; u += 32) {
+            if (cs[u] != 0xffffu) {
+                uint32_t rr = rank[u];
+                emit(start + (uint32_t)cs[u] + rr, pw[u], rr ? NONHEAD : 0u);
+                leftover++;
+            }
+        }
+        for (int d = 16; d; d >>= 1) leftover += __shfl_xor_sync(0xffffffffu, leftover, d);
+        if (l == 0 && leftover) { atomicAdd(&P.left[lb], leftover); atomicAdd(g_left, (unsigned long long)leftover); }
+        __syncwarp();
+    }
 }
 
 constexpr int FB_TH = 256;
@@ -1528,7 +1649,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.hist = ctx->hist.as<uint32_t>();
     uint32_t *misc = ctx->bwt_misc.as<uint32_t>();
     P.g_act = reinterpret_cast<unsigned long long *>(misc); misc += 4;
-    uint32_t *big_cnt = misc; misc += 4;                       // [0] listed groups, [1] keys-out-of-order flag
+    uint32_t *big_cnt = misc; misc += 4;                       // [0] listed groups, [1] keys-out-of-order flag, [2] groups passed on to k_finish_big
     P.cnt_n = misc; misc += nb;
     P.cnt_m = misc; misc += nb;
     P.act = misc; misc += 2 * nb;
@@ -1600,7 +1721,11 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
         S3G_BYTES(ctx, 18 * N);
         S3G_LAUNCH(ctx, k_finish_rows, dim3(FA_NT, (unsigned)nb), FA_WARPS * 32, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
                    ctx->lcol.as<uint8_t>(), dst, big_cnt, big_cnt + 1);
-        S3G_LAUNCH(ctx, k_finish_big, SM_COUNT * 4, FB_TH, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(), dst, big_cnt);
+        uint64_t *list2 = dst + slots / 2;                         // second half of the free sort buffer
+        S3G_LAUNCH(ctx, k_finish_mid, SM_COUNT * 4, FM_WARPS * 32, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(),
+                   dst, big_cnt, list2, big_cnt + 2);
+        S3G_LAUNCH(ctx, k_finish_big, SM_COUNT * 4, FB_TH, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(), list2,
+                   big_cnt + 2);
         S3G_TRY(check_launch("bwt init"));
         S3G_CUDA(cudaMemcpyAsync(h_act, P.g_act, 32, cudaMemcpyDeviceToHost, ctx->stream));
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
