@@ -199,14 +199,20 @@ def test_bwt_sort_safety_net(ctx, oracle, monkeypatch, mode):
 
 def test_bwt_window_limits(ctx, oracle):
     """Groups around the sizes the warp finisher handles itself (a window of four rows: up to 97..128 rotations
-    depending on where the group starts) and the one-CTA-per-group kernel takes over (up to 2048)."""
+    depending on where the group starts), the warp-per-group kernel (up to 256) and the CTA-per-group kernel
+    (counting up to 256, bitonic level 0 above, up to 2048) take over."""
     rng = np.random.default_rng(5)
     ctx9 = b"QRSTUVWXYZ012"
     parts = [bytes(rng.integers(97, 123, 2000, dtype=np.uint8))]
-    for count in (31, 32, 33, 64, 95, 96, 97, 98, 127, 128, 129, 130, 200):
+    for count in (31, 32, 33, 64, 95, 96, 97, 98, 127, 128, 129, 130, 200, 255, 256, 257, 300, 511, 512, 513, 1000, 1500):
         tag = ctx9 + b"%03d" % count
         for i in rng.permutation(count):
             parts.append(tag + (b"%04d" % int(i)) + bytes(rng.integers(97, 123, int(rng.integers(1, 9)), dtype=np.uint8)))
+    # the same with ties at level 0 (equal for 12 symbols after the context, then a distinct number)
+    for count in (120, 250, 400):
+        tag = ctx9 + b"T%03d" % count + b"=" * 12
+        for i in rng.permutation(count):
+            parts.append(tag + (b"%04d" % int(i)) + b"\n")
     blk = b"".join(parts)
     (ptr, orig), = ctx.bwt([blk])
     optr, oorig = oracle.bwt(blk)
