@@ -11,7 +11,7 @@ for line in open(f'gpurun_out/bench_v_{v}.log'):
     if line.startswith('{'):
         j=json.loads(line); ks=j['kernels']
         sw=sum(x['ms'] for k,x in ks.items() if 'k_sweep' in k)
-        print(v, 'step', round(j['ms_per_step'],2), 'sweeps', round(sw,2), {k:x['ms'] for k,x in ks.items() if any(t in k for t in ('sweep','finish','keys','huff','mtf_small'))})
+        print(v, 'step', round(j['ms_per_step'],2), 'sweeps', round(sw,2), {k:x['ms'] for k,x in ks.items() if any(t in k for t in ('sweep','finish','keys','huff','mtf','zrun'))})
         break
 else: print(v,'FAILED'); print(open(f'gpurun_out/bench_v_{v}.log').read()[-600:])
 P

@@ -849,6 +849,9 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
         if (pos == 0) blocks[lb].orig_ptr = (int32_t)slot_abs;
     };
 
+    // the warp's records: into L2 now (64 lines), so that the row loads below meet L2 latency, not DRAM latency
+    for (uint32_t o = l * 16; o < (FA_ROWS + FA_WIN + 2) * 32 && p0 + o < n; o += 32 * 16)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a + p0 + o));
     uint32_t pw[FA_WIN], hm[FA_WIN];
     uint32_t kw[3];                     // level-0 keys of window rows 0..2
     uint64_t xa, pva;                   // step A of row R + 5
