@@ -850,12 +850,13 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
     };
 
     // the warp's records: into L2 now (64 lines), so that the row loads below meet L2 latency, not DRAM latency
-    for (uint32_t o = l * 16; o < (FA_ROWS + FA_WIN + 2) * 32 && p0 + o < n; o += 32 * 16)
+    for (uint32_t o = l * 16; o < (FA_ROWS + FA_WIN + 3) * 32 && p0 + o < n; o += 32 * 16)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a + p0 + o));
     uint32_t pw[FA_WIN], hm[FA_WIN];
     uint32_t kw[3];                     // level-0 keys of window rows 0..2
-    uint64_t xa, pva;                   // step A of row R + 5
-    uint32_t posb, hmb, byb;            // step B of row R + 4
+    uint64_t xa, pva;                   // step A of row R + 6
+    uint32_t posb, hmb, byb;            // step B of row R + 5
+    uint32_t posc, hmc, byc;            // step B of row R + 4, one iteration older (its gather has had two iterations)
 #pragma unroll
     for (int j = 0; j < FA_WIN; j++) {
         uint64_t x, pv; uint32_t ps, by;
@@ -864,8 +865,10 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
         pw[j] = stage_c(ps, by);
     }
     issue_raw(p0 + 32 * 4, xa, pva);
-    stage_b(p0 + 32 * 4, xa, pva, posb, hmb, byb);
+    stage_b(p0 + 32 * 4, xa, pva, posc, hmc, byc);
     issue_raw(p0 + 32 * 5, xa, pva);
+    stage_b(p0 + 32 * 5, xa, pva, posb, hmb, byb);
+    issue_raw(p0 + 32 * 6, xa, pva);
     kw[0] = prefetch_key(p0, pw[0], hm[0], hm[1]);
     kw[1] = prefetch_key(p0 + 32, pw[1], hm[1], hm[2]);
 
@@ -1001,9 +1004,10 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
 #pragma unroll
         for (int j = 0; j + 1 < FA_WIN; j++) { pw[j] = pw[j + 1]; hm[j] = hm[j + 1]; }
         kw[0] = kw[1]; kw[1] = kw[2];
-        pw[FA_WIN - 1] = stage_c(posb, byb); hm[FA_WIN - 1] = hmb;
-        stage_b(rowbase + 32 * 5, xa, pva, posb, hmb, byb);
-        issue_raw(R + 7 < FA_ROWS + 4 ? rowbase + 32 * 6 : n, xa, pva);
+        pw[FA_WIN - 1] = stage_c(posc, byc); hm[FA_WIN - 1] = hmc;
+        posc = posb; hmc = hmb; byc = byb;
+        stage_b(rowbase + 32 * 6, xa, pva, posb, hmb, byb);
+        issue_raw(R + 8 < FA_ROWS + 4 ? rowbase + 32 * 7 : n, xa, pva);
     }
     for (int d = 16; d; d >>= 1) leftover += __shfl_xor_sync(0xffffffffu, leftover, d);
     if (l == 0 && leftover) { atomicAdd(&P.left[lb], leftover); atomicAdd(g_left, (unsigned long long)leftover); }
