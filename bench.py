@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lines", type=int, default=10_000_000, help="lines per GPU (cfg2: 10 M)")
-    ap.add_argument("--ref-lines", type=int, default=2_000_000, help="bounded CPU sample, lines of cfg2")
+    ap.add_argument("--ref-lines", type=int, default=6_000_000, help="bounded CPU sample, lines of cfg2 (about 20 core-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
