@@ -142,13 +142,23 @@ __global__ void k_parse_lines(const uint8_t *__restrict__ bed, const uint64_t *_
     start[i] = v_start; stop[i] = v_stop; rem_off[i] = ro; flags[i] = fl;
 }
 
+__constant__ uint64_t POW10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+                                   10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull,
+                                   1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
+                                   10000000000000000000ull};
+// decimal digits of a (1..20): floor(bits * log10(2)) is the count or one short of it (no division)
+__device__ __forceinline__ int dec_digits(uint64_t a)
+{
+    int b = 64 - __clzll((long long)(a | 1));
+    int t = (b * 1233) >> 12;
+    int d = t + (a >= POW10[t] ? 1 : 0);
+    return d < 1 ? 1 : d;
+}
 __device__ __forceinline__ int dec_len(int64_t v)
 {
     // printed length of "%lld": n_digits (hpp:559-581) plus the sign it does not count
     uint64_t a = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
-    int d = 1;
-    while (a >= 10) { a /= 10; d++; }
-    return d + (v < 0);
+    return dec_digits(a) + (v < 0);
 }
 
 struct LineView {
@@ -254,13 +264,16 @@ __global__ void k_chrom_table(const uint8_t *bed, const uint64_t *line_start, co
 __device__ __forceinline__ uint64_t put_dec(uint8_t *dst, int64_t v)
 {
     uint64_t a = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
-    char buf[20];
-    int nd = 0;
-    do { buf[nd++] = (char)('0' + a % 10); a /= 10; } while (a);
     uint64_t k = 0;
     if (v < 0) dst[k++] = '-';
-    for (int j = nd - 1; j >= 0; j--) dst[k++] = (uint8_t)buf[j];
-    return k;
+    const int nd = dec_digits(a);
+    if (a <= 0xffffffffull) {            // the usual case: 32-bit divisions by a constant
+        uint32_t x = (uint32_t)a;
+        for (int j = nd - 1; j >= 0; j--) { uint32_t q = x / 10u; dst[k + j] = (uint8_t)('0' + (x - q * 10u)); x = q; }
+    } else {
+        for (int j = nd - 1; j >= 0; j--) { uint64_t q = a / 10u; dst[k + j] = (uint8_t)('0' + (uint32_t)(a - q * 10u)); a = q; }
+    }
+    return k + nd;
 }
 
 // One thread formats one line.  The 256 lines of a CTA produce one contiguous piece of the transformed
