@@ -161,6 +161,18 @@ def test_pipelined_host_entry_matches_one_shot(ctx, oracle, cfg, lines, parts, m
            [(c["name"], c["line_count"], c["bz_off"], c["bz_len"], c["tf_off"], c["tf_len"]) for c in one.chroms]
 
 
+def test_pipelined_host_entry_on_a_fresh_context(oracle, monkeypatch):
+    """The first call a context ever sees is the pipelined one (nothing allocated by earlier stages)."""
+    import starch3_b200 as s3
+    monkeypatch.setenv("S3G_PARTS", "3")
+    bed = synth.bed(2, 50000).tobytes()
+    c = s3.Context(0)
+    try:
+        assert c.compress_bed(bed, 9, note="f").archive == oracle.archive(bed, 9, "f")
+    finally:
+        c.close()
+
+
 def test_pipelined_host_entry_edge_inputs(ctx, oracle, monkeypatch):
     monkeypatch.setenv("S3G_PARTS", "3")
     for bed in (b"", b"chr1\t1\t2\n", b"chr1\t1\t2\nchr2\t5\t9\tx\n", b"chr1\t1\t2\nchr1\t5\t9\nchr1\t7\t1",
