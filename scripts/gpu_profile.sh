@@ -11,7 +11,7 @@ python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$
 tail -3 $O/pytest_$TAG.log
 python bench.py > $O/bench_$TAG.log 2>&1; echo "bench rc=$?"
 python bench.py --impl reference --steps 1 --warmup 0 > $O/bench_ref_$TAG.log 2>&1; echo "ref rc=$?"
-CMD="python bench.py --lines 2000000 --steps 1 --warmup 1 --no-cpu-baseline"
+CMD="python bench.py --lines 10000000 --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD > $O/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_l_$TAG.log 2>&1
 echo "launch list rc=$?"

@@ -50,8 +50,8 @@ if os.path.exists(f):
     total = sum(a[1] for a in tot.values())
     with open(os.path.join(P, f"{tag}_launch_list_summary.md"), "w") as o:
         o.write(f"# {tag} -- ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n"
-                "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --lines 2000000 --steps 1 --warmup 1 --no-cpu-baseline`\n"
-                "(cfg2, 2 M lines; warm-up, timed and e2e steps all captured; cold-cache, serialised: compare SHARES).\n\n"
+                "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --lines 10000000 --steps 1 --warmup 1 --no-cpu-baseline`\n"
+                "(cfg2, 10 M lines = the bench workload; warm-up, timed and e2e steps all captured; cold-cache, serialised: compare SHARES).\n\n"
                 "| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for k, a in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             o.write(f"| {k} | {a[0]} | {a[1]:.1f} | {100 * a[1] / total:.1f}% |\n")
