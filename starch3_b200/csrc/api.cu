@@ -61,7 +61,7 @@ static DevBuf *const *all_bufs(Ctx *c, size_t *n)
     B(scan_a); B(scan_b); B(scan_c); B(scalars); B(tf); B(chroms); B(stat_a); B(stat_b); B(soff);
     B(rle_carry); B(rle_ebase); B(blocks); B(blk_prov); B(blk_bytes); B(in_use); B(seq_map); B(stream_tab);
     B(sa); B(rk); B(kv0); B(kv1); B(hist); B(bwt_misc); B(bwt_ghist); B(lcol);
-    B(mtf0); B(mtfv16); B(mtf_freq); B(bits); B(pool); B(pool_woff); B(streams); B(stream_meta);
+    B(mtf0); B(mtfv16); B(mtf_freq); B(ztiles); B(bits); B(pool); B(pool_woff); B(streams); B(stream_meta);
     B(io_a); B(io_b); B(io_c); B(io_d); B(io_e);
 #undef B
     *n = k;

@@ -98,7 +98,7 @@ struct Ctx {
     size_t sweep_cap = 0;                  // capacity of `hist` when its look-back status words were last cleared
     uint32_t sweep_gen = 0;                // generation tag of the last radix pass (1..255)
     uint64_t sort_retries = 0;             // times the radix passes had to be repeated with peer-mask ranking (expected: never)
-    DevBuf mtf0, mtfv16, mtf_freq, bits, pool, pool_woff, streams, stream_meta;
+    DevBuf mtf0, mtfv16, mtf_freq, ztiles, bits, pool, pool_woff, streams, stream_meta;
     DevBuf io_a, io_b, io_c, io_d, io_e;   // staging for the stage entry points
     // host mirrors
     std::vector<BlockInfo> h_blocks;

@@ -133,6 +133,158 @@ __device__ __forceinline__ void mtf_zero_runs(const uint8_t *M, uint16_t *mtfv, 
     for (int i = threadIdx.x; i < 258; i += THREADS) fq[i] = s_freq[i];
 }
 
+// The same coding, tile-parallel, for batches that cannot fill the SMs with one CTA per block (k_mtf* with
+// zero_runs = 0 leave the ranks in M[]): a run's digits are written where the run ENDS, with its start = the position
+// after the last non-zero rank before it.  Inside a tile that start is known except for the first run end when no
+// non-zero rank precedes it in the tile; so
+//   k_zrun_tiles    per tile: position of its last non-zero rank, its symbol count without that one open run,
+//                   and where that run ends;
+//   k_zrun_offsets  per block: exclusive max-scan (carry of the last non-zero position) and sum-scan (output
+//                   offsets) over its tiles, EOB, nMTF;
+//   k_zrun_emit     per tile: the symbols (put together in shared memory, written as one piece) and the frequencies.
+constexpr int ZT = 256;                  // threads per tile
+constexpr int ZDI = 16;                  // ranks per thread
+constexpr int ZTILE = ZT * ZDI;          // ranks per tile
+constexpr int ZNT = (BLK_STRIDE + ZTILE - 1) / ZTILE;
+
+struct ZTileInfo { uint32_t lastnz, base, open_end, off; };       // per block and tile; lastnz becomes the carry, off is filled by k_zrun_offsets
+
+// ranks of one thread: m[0..ZDI) and the rank after them (positions past the block end act as non-zero)
+__device__ __forceinline__ void zrun_load(const uint8_t *M, int p0, int n, uint8_t (&m)[ZDI + 1])
+{
+    if (p0 + ZDI < n) {
+#pragma unroll
+        for (int q = 0; q < ZDI / 16; q++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(M + p0 + 16 * q);      // slots are 128-byte aligned, p0 % 16 == 0
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) m[16 * q + k] = (uint8_t)(w4[k >> 2] >> (8 * (k & 3)));
+        }
+        m[ZDI] = M[p0 + ZDI];
+    } else {
+#pragma unroll
+        for (int k = 0; k <= ZDI; k++) m[k] = (p0 + k < n) ? M[p0 + k] : (uint8_t)1;
+    }
+}
+
+__global__ void __launch_bounds__(ZT) k_zrun_tiles(const uint8_t *mtf0, const BlockInfo *blocks, ZTileInfo *tiles)
+{
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_open;
+    const uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    const int n = (int)blocks[lb].nblock;
+    const int tile0 = (int)tile * ZTILE;
+    if (tile0 >= n) return;
+    const uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
+    if (threadIdx.x == 0) s_open = 0;
+    const int p0 = tile0 + (int)threadIdx.x * ZDI;
+    uint8_t m[ZDI + 1];
+    zrun_load(M, p0, n, m);
+    uint32_t lastnz = 0;
+#pragma unroll
+    for (int k = 0; k < ZDI; k++) if (p0 + k < n && m[k]) lastnz = (uint32_t)(p0 + k + 1);
+    uint32_t tmax;
+    uint32_t ex = block_excl_max<uint32_t>(lastnz, s_scan, &tmax);      // position + 1 of the last non-zero rank before mine, in this tile
+    uint32_t emit = 0, rs_k = ex;
+#pragma unroll
+    for (int k = 0; k < ZDI; k++) {
+        if (p0 + k < n) {
+            if (m[k]) { emit++; rs_k = (uint32_t)(p0 + k + 1); }
+            else if (m[k + 1]) {
+                if (rs_k) { uint32_t r = (uint32_t)(p0 + k + 1) - rs_k; emit += 31 - __clz(r + 1); }
+                else s_open = (uint32_t)(p0 + k + 1);          // the one run end whose start lies before the tile
+            }
+        }
+    }
+    uint32_t ttot;
+    block_excl_sum<uint32_t>(emit, s_scan, &ttot);
+    if (threadIdx.x == 0) {
+        ZTileInfo t; t.lastnz = tmax; t.base = ttot; t.open_end = s_open; t.off = 0;
+        tiles[(uint64_t)lb * ZNT + tile] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_zrun_offsets(ZTileInfo *tiles_all, uint16_t *mtfv_all, int32_t *freq_all, BlockInfo *blocks)
+{
+    __shared__ uint32_t s_scan[33];
+    static_assert(ZNT <= 256, "one thread per tile");
+    const uint32_t lb = blockIdx.x, t = threadIdx.x;
+    const int n = (int)blocks[lb].nblock;
+    const int a = (int)blocks[lb].n_in_use;
+    const uint32_t nt = (uint32_t)((n + ZTILE - 1) / ZTILE);
+    ZTileInfo *tiles = tiles_all + (uint64_t)lb * ZNT;
+    ZTileInfo ti; ti.lastnz = 0; ti.base = 0; ti.open_end = 0; ti.off = 0;
+    if (t < nt) ti = tiles[t];
+    uint32_t tmax, ttot;
+    uint32_t carry = block_excl_max<uint32_t>(ti.lastnz, s_scan, &tmax);     // last non-zero position + 1 in the earlier tiles
+    uint32_t cnt = ti.base;
+    if (ti.open_end) { uint32_t r = ti.open_end - carry; cnt += 31 - __clz(r + 1); }
+    uint32_t off = block_excl_sum<uint32_t>(cnt, s_scan, &ttot);
+    if (t < nt) { tiles[t].off = off; tiles[t].lastnz = carry; }
+    if (t == 0) {
+        mtfv_all[(uint64_t)lb * BLK_STRIDE + ttot] = (uint16_t)(a + 1);       // EOB
+        atomicAdd(&freq_all[(uint64_t)lb * 258 + a + 1], 1);
+        blocks[lb].n_mtf = ttot + 1;
+    }
+}
+
+__global__ void __launch_bounds__(ZT) k_zrun_emit(const uint8_t *mtf0, const BlockInfo *blocks, const ZTileInfo *tiles, uint16_t *mtfv_all,
+                                                 int32_t *freq_all)
+{
+    __shared__ uint32_t s_scan[33];
+    __shared__ int s_freq[258];
+    __shared__ uint16_t s_out[ZTILE + 32];      // at most one symbol per rank, except that the one open run gives up to 20 digits
+    const uint32_t lb = blockIdx.y, tile = blockIdx.x;
+    const int n = (int)blocks[lb].nblock;
+    const int tile0 = (int)tile * ZTILE;
+    if (tile0 >= n) return;
+    const uint8_t *M = mtf0 + (uint64_t)lb * BLK_STRIDE;
+    uint16_t *mtfv = mtfv_all + (uint64_t)lb * BLK_STRIDE;
+    for (int i = threadIdx.x; i < 258; i += ZT) s_freq[i] = 0;
+    const ZTileInfo ti = tiles[(uint64_t)lb * ZNT + tile];
+    const int p0 = tile0 + (int)threadIdx.x * ZDI;
+    uint8_t m[ZDI + 1];
+    zrun_load(M, p0, n, m);
+    uint32_t lastnz = 0;
+#pragma unroll
+    for (int k = 0; k < ZDI; k++) if (p0 + k < n && m[k]) lastnz = (uint32_t)(p0 + k + 1);
+    uint32_t tmax;
+    uint32_t ex = block_excl_max<uint32_t>(lastnz, s_scan, &tmax);
+    const uint32_t rs = ex ? ex : ti.lastnz;                   // the zero run in effect starts at position rs
+    uint32_t emit = 0, rs_k = rs;
+#pragma unroll
+    for (int k = 0; k < ZDI; k++) {
+        if (p0 + k < n) {
+            if (m[k]) { emit++; rs_k = (uint32_t)(p0 + k + 1); }
+            else if (m[k + 1]) { uint32_t r = (uint32_t)(p0 + k + 1) - rs_k; emit += 31 - __clz(r + 1); }
+        }
+    }
+    uint32_t ttot;
+    uint32_t o = block_excl_sum<uint32_t>(emit, s_scan, &ttot);          // also orders the s_freq zeroing before the atomics
+    int fa = 0, fb = 0;
+    rs_k = rs;
+#pragma unroll
+    for (int k = 0; k < ZDI; k++) {
+        if (p0 + k < n) {
+            if (m[k]) { s_out[o++] = (uint16_t)(m[k] + 1); atomicAdd(&s_freq[m[k] + 1], 1); rs_k = (uint32_t)(p0 + k + 1); }
+            else if (m[k + 1]) {
+                uint32_t zp = (uint32_t)(p0 + k + 1) - rs_k - 1;
+                for (;;) {
+                    if (zp & 1) { s_out[o++] = 1; fb++; } else { s_out[o++] = 0; fa++; }
+                    if (zp < 2) break;
+                    zp = (zp - 2) >> 1;
+                }
+            }
+        }
+    }
+    if (fa) atomicAdd(&s_freq[0], fa);
+    if (fb) atomicAdd(&s_freq[1], fb);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ttot; i += ZT) mtfv[ti.off + i] = s_out[i];
+    int32_t *fq = freq_all + (uint64_t)lb * 258;
+    for (int i = threadIdx.x; i < 258; i += ZT) { int v = s_freq[i]; if (v) atomicAdd(&fq[i], v); }
+}
+
 // =============================================================================
 // (3c, alphabets of at most 32 symbols -- every BED-derived stream) MTF with the list held in
 // registers: 8 entries per 64-bit word, position found with a zero-byte test, move-to-front as a
@@ -215,7 +367,7 @@ __device__ __forceinline__ void mtf_thread_chunk(const uint8_t *L, uint8_t *M, i
 
 template <int MS, bool SMALL>
 __global__ void __launch_bounds__(MS, 2) k_mtf_small(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
-                                                     BlockInfo *blocks, int rows)
+                                                     BlockInfo *blocks, int rows, int zero_runs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *s_last = reinterpret_cast<int *>(smem_raw);            // [rows][MS], rows = largest alphabet (<= MTF_REG_MAX) in the batch
@@ -274,13 +426,14 @@ __global__ void __launch_bounds__(MS, 2) k_mtf_small(const uint8_t *lcol, uint8_
             default: mtf_thread_chunk<8, 12, MS>(L, M, beg, end, s_last, a); break;
         }
     }
+    if (!zero_runs) return;             // coded by the k_zrun_* kernels
     __threadfence_block();
     __syncthreads();
     mtf_zero_runs<MS>(M, mtfv, n, a, s_freq, s_scan, blocks, lb, freq_all);
 }
 
 __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, uint16_t *mtfv_all, int32_t *freq_all,
-                                            BlockInfo *blocks)
+                                            BlockInfo *blocks, int zero_runs)
 {
     __shared__ int s_last[32 * 256];
     __shared__ int s_freq[258];
@@ -341,6 +494,7 @@ __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, 
             default: mtf_chunk<8>(L, M, beg, end, il, a); break;
         }
     }
+    if (!zero_runs) return;
     __threadfence_block();
     __syncthreads();
     mtf_zero_runs<MT>(M, mtfv, n, a, s_freq, s_scan, blocks, lb, freq_all);
@@ -375,6 +529,10 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
         else if (a <= MTF_REG_MAX) any_big = true;
     }
     const size_t tail_smem = 260 * 4 + 40 * 4;
+    // zero-run coding inside the MTF kernels (one CTA per block) when the batch fills the SMs, as tile-parallel kernels of
+    // its own when it does not (S3G_ZRUN=fused|split overrides: both forms are tested)
+    int fused = nb >= (uint64_t)SM_COUNT ? 1 : 0;
+    if (const char *e = getenv("S3G_ZRUN")) fused = !strcmp(e, "split") ? 0 : !strcmp(e, "fused") ? 1 : fused;
     static bool attr_done = false;
     if (!attr_done) {
         S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)24 * MS_SMALL * 4 + tail_smem)));
@@ -384,12 +542,22 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
     if (any_small)
         S3G_LAUNCH(ctx, k_mtf_list_small, (unsigned)nb, MS_SMALL, (size_t)std::min(rows, 24) * MS_SMALL * 4 + tail_smem, ctx->lcol.as<uint8_t>(),
-                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, std::min(rows, 24));
+                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, std::min(rows, 24), fused);
     if (any_big)
         S3G_LAUNCH(ctx, k_mtf_list_big, (unsigned)nb, MS_BIG, (size_t)rows * MS_BIG * 4 + tail_smem, ctx->lcol.as<uint8_t>(),
-                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, rows);
+                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, rows, fused);
     S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
-               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0);
+               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, fused);
+    if (!fused) {
+        // zero-run coding, tile-parallel over the ranks
+        S3G_TRY(ctx->ztiles.ensure((size_t)nb * ZNT * sizeof(ZTileInfo)));
+        S3G_CUDA(cudaMemsetAsync(ctx->mtf_freq.p, 0, (size_t)nb * 258 * 4, ctx->stream));
+        S3G_LAUNCH(ctx, k_zrun_tiles, dim3(ZNT, (unsigned)nb), ZT, 0, ctx->mtf0.as<uint8_t>(), ctx->blocks.as<BlockInfo>() + b0, ctx->ztiles.as<ZTileInfo>());
+        S3G_LAUNCH(ctx, k_zrun_offsets, (unsigned)nb, 256, 0, ctx->ztiles.as<ZTileInfo>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
+                   ctx->blocks.as<BlockInfo>() + b0);
+        S3G_LAUNCH(ctx, k_zrun_emit, dim3(ZNT, (unsigned)nb), ZT, 0, ctx->mtf0.as<uint8_t>(), ctx->blocks.as<BlockInfo>() + b0, ctx->ztiles.as<ZTileInfo>(),
+                   ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>());
+    }
     return check_launch("mtf");
 }
 

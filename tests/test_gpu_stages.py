@@ -252,6 +252,33 @@ def test_mtf_and_huffman(ctx, oracle, name, blk):
         assert np.array_equal(h["bits"], ref["bits"])
 
 
+@pytest.mark.parametrize("zrun", ["fused", "split"])
+@pytest.mark.parametrize("name,blk", BLOCKS, ids=[n for n, _ in BLOCKS])
+def test_mtf_zero_run_forms(ctx, oracle, name, blk, zrun, monkeypatch):
+    """Zero-run coding runs inside the MTF kernels for batches that fill the SMs and as tile-parallel kernels for
+    smaller ones (mtf_huff.cu, k_zrun_*): both forms on every block, whatever the batch size would pick."""
+    monkeypatch.setenv("S3G_ZRUN", zrun)
+    blk = _resolve_block(oracle, name, blk)
+    ptr, _ = oracle.bwt(blk)
+    in_use = np.zeros(256, dtype=np.uint8)
+    in_use[np.frombuffer(blk, dtype=np.uint8)] = 1
+    omtfv, ofreq, nu = oracle.mtf(blk, ptr, in_use)
+    mtfv, freq = ctx.mtf(blk, ptr, in_use)
+    assert np.array_equal(mtfv, omtfv)
+    assert np.array_equal(freq[:nu + 2], ofreq[:nu + 2])
+
+
+@pytest.mark.parametrize("zrun", ["fused", "split"])
+def test_archive_with_either_zero_run_form(ctx, oracle, zrun, monkeypatch):
+    monkeypatch.setenv("S3G_ZRUN", zrun)
+    bed = synth.bed(5, 60000).tobytes()
+    assert ctx.compress_bed(bed, 9, note="z").archive == oracle.archive(bed, 9, "z")
+    # long zero runs across tile boundaries, and a block that is one run
+    for data in (b"a" * 70000 + b"b" + b"a" * 9000 + b"cab" * 5000, b"\n".join(b"7" for _ in range(40000)) + b"\n", b"q" * 300000):
+        z = ctx.bz_compress(data, 9)
+        assert z == oracle.bz_compress(data, 9)
+
+
 @pytest.mark.parametrize("name,data,level", STREAMS, ids=[s[0] for s in STREAMS])
 def test_bz_compress_stream(ctx, oracle, name, data, level):
     z = ctx.bz_compress(data, level)
