@@ -1,19 +1,20 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the starch3 compression hot path (BED -> starch transform ->
-per-chromosome bzip2) on B200, in input BED MB/s, with the kernel roofline and the CPU
-baseline beside it.
+per-chromosome bzip2) on B200, in input BED MB/s, with the roofline and the CPU baselines beside it.
 
-    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+    python bench.py --gpus N --steps K --warmup W                    # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path, same input
+    python bench.py --cfg 3 [--lines L]                              # another BASELINE.json config
 
-A "step" is one pass of the whole hot path over one batch of synthetic input: the
-configuration BASELINE.json's metric is quoted on, configs[1] (hg38-shaped BED6, 10 M elements
-over 24 chromosomes, bzip2 at 900k blocks).  One process per GPU; with N > 1 every rank
-compresses its own 10 M-line input (independent chromosomes/blocks, no data-path collective:
-"weak" scaling) and the value is the total MB of all ranks over the max-over-ranks device time.
+A "step" is one pass of the whole hot path over ONE synthetic input: by default the configuration
+BASELINE.json's metric is quoted on, configs[1] (hg38-shaped BED6, 10 M elements over 24 chromosomes, bzip2 at
+900k blocks).  One process per GPU.  With N > 1 the ranks compress ONE input together (strong scaling): rank r
+tokenises and transforms its newline-aligned byte range, the transformed pieces are exchanged over NVLink
+(all-gather), every rank compresses its share of the bzip2 blocks, and rank 0 joins the block bit strings into
+the archive -- the same bytes as the 1-GPU archive (checked against the reference-libbz2 oracle after the
+timed loops; no value is printed otherwise).
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -28,7 +29,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "input BED MB/s compressed (byte-identical archive)"
 UNIT = "MB/s"
-WORKLOAD = "cfg2: synthetic hg38-shaped BED6, 24 chromosomes, ids and scores, bzip2 900k blocks"
+WORKLOADS = {
+    1: ("cfg1: synthetic sorted BED3, single chromosome (chr1), bzip2 900k blocks", 1_000_000),
+    2: ("cfg2: synthetic hg38-shaped BED6, 24 chromosomes, ids and scores, bzip2 900k blocks", 10_000_000),
+    3: ("cfg3: dense DNase-footprint-like BED3, short uniform-length intervals, one chromosome, bzip2 900k blocks", 100_000_000),
+    4: ("cfg4: sparse wide-interval BED6, high-entropy names and scores, one chromosome, bzip2 900k blocks", 20_000_000),
+    5: ("cfg5: whole-genome mix of cfg1-4 shapes across 24 chromosomes, bzip2 900k blocks", 400_000_000),
+}
 
 
 def measured_peak_hbm():
@@ -87,30 +94,40 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# the reference arm / CPU baseline: the reference's own algorithm on the host cores
+# the reference arm / CPU baselines: the reference's own algorithm on the host cores
 # -------------------------------------------------------------------------------------------------
 def cpu_compress(bed_np, threads):
-    """Restated transform (oracle) + the reference's vendored libbz2 when oracle/_ref is present,
-    one bzip2 stream per chromosome, whole chromosomes spread over `threads` host threads
-    (BASELINE.md plan B2).  Returns (seconds, kind, compressed bytes)."""
-    from concurrent.futures import ThreadPoolExecutor
+    """Restated transform (oracle) + the reference's vendored libbz2 when oracle/_ref is present, chromosomes and
+    the blocks of a chromosome spread over `threads` host threads (BASELINE.md plan B2; block-level threads keep
+    all cores busy on the single-chromosome configs too, and the bytes are the serial reference's:
+    oracle.archive_mt).  Returns (seconds, kind, archive bytes)."""
     from oracle import oracle as O
     kind = "reference" if O.have_ref() else "port"
-    comp = O.ref_bz_compress if O.have_ref() else O.bz_compress
     t0 = time.perf_counter()
-    tf, chroms, _ = O.transform(bed_np)
-    tfv = memoryview(tf)
-    streams = [tfv[c["tf_off"]:c["tf_off"] + c["tf_len"]] for c in chroms]
-    order = sorted(range(len(streams)), key=lambda i: -len(streams[i]))
-    out = [None] * len(streams)
+    arc = O.archive_mt(bed_np, 9, "", threads=threads)
+    return time.perf_counter() - t0, kind, arc
 
-    def work(i):
-        out[i] = comp(np.frombuffer(streams[i], dtype=np.uint8), 9)
 
-    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
-        list(ex.map(work, order))
-    dt = time.perf_counter() - t0
-    return dt, kind, sum(len(z) for z in out)
+def cpu_baselines(cfg, lines, threads):
+    """B0 (the reference binary as shipped, cfg1 shape only: it performs the transform but never compresses,
+    SURVEY.md F2) and B1 (the completed CPU path on one core) on bounded samples."""
+    from oracle import oracle as O
+    from starch3_b200 import synth
+    out = {}
+    if os.path.exists(O.REF_BINARY):
+        s = synth.bed(1, 60_000, seed=42)
+        t0 = time.perf_counter()
+        p = subprocess.run([O.REF_BINARY], input=s.tobytes(), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+        if p.returncode == 0:
+            out["B0_reference_binary"] = {"value": s.nbytes / 1e6 / dt, "unit": UNIT, "cores": 2, "kind": "reference",
+                                          "sample": f"60000 lines of cfg1 ({s.nbytes / 1e6:.2f} MB), {dt:.1f} s; oracle/_ref/starch3_ref "
+                                                    "as shipped: transform only, no compression, stderr to /dev/null"}
+    s = synth.bed(cfg, min(lines, 1_000_000), seed=42)
+    dt, kind, _ = cpu_compress(s, 1)
+    out["B1_one_core"] = {"value": s.nbytes / 1e6 / dt, "unit": UNIT, "cores": 1, "kind": kind,
+                          "sample": f"{min(lines, 1_000_000)} lines of cfg{cfg} ({s.nbytes / 1e6:.1f} MB BED), one pass, {dt:.1f} s"}
+    return out
 
 
 def run_reference(args, rank, world):
@@ -118,23 +135,31 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    threads = min(cores, 24)            # one stream per chromosome: 24 is all the parallelism the reference path has
-    sample_lines = args.ref_lines
-    bed = synth.bed(2, sample_lines, seed=42)
+    threads = min(cores, 32)
+    workload, _ = WORKLOADS[args.cfg]
+    bed = synth.bed(args.cfg, args.lines, seed=42)
+    # the whole K/W run has to end within a few minutes: a step is the whole input unless that is too slow,
+    # then a bounded sample of it (stated in `sample`)
+    sample_lines = args.lines
+    if args.ref_lines and args.ref_lines < args.lines:
+        sample_lines = args.ref_lines
+        bed = synth.bed(args.cfg, sample_lines, seed=42)
     times = []
+    kind = "port"
     for i in range(args.warmup + args.steps):
-        dt, kind, zbytes = cpu_compress(bed, threads)
+        dt, kind, _ = cpu_compress(bed, threads)
         if i >= args.warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
     value = bed.nbytes / 1e6 / (ms / 1000.0)
-    sample = f"{sample_lines} lines of cfg2 ({bed.nbytes / 1e6:.1f} MB BED) per step"
+    sample = f"{sample_lines} lines of cfg{args.cfg} ({bed.nbytes / 1e6:.1f} MB BED) per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "lines_per_step": sample_lines, "input_mb_per_step": bed.nbytes / 1e6,
-                   "note": "CPU: restated transform + reference libbz2 1.0.6 (level 9, workFactor 30), chromosomes over host threads"},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload, "lines_per_step": sample_lines, "input_mb_per_step": bed.nbytes / 1e6,
+                   "same_input_as_b200_arm": sample_lines == args.lines,
+                   "note": "CPU: restated transform + reference libbz2 1.0.6 (level 9, workFactor 30), chromosomes and blocks over host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -145,6 +170,21 @@ def run_reference(args, rank, world):
 # -------------------------------------------------------------------------------------------------
 # this repository's arm
 # -------------------------------------------------------------------------------------------------
+def stage_table(res, nbytes, ms_scale, peak):
+    """SURVEY.md section 8(d) bytes per stage over the CUDA-event time of the stage (s3g_result.stage_ms)."""
+    b_in, b_tf, b_blk, m, b_out = nbytes, res.tf_bytes, res.rle_bytes, res.mtf_symbols, res.streams_size
+    alg = {"tokenise+transform": b_in + b_tf, "rle1+cut+crc": b_tf + b_blk, "blocksort": 2 * b_blk, "mtf": b_blk + 2 * m,
+           "huffman": 10 * m + b_out, "assemble": None}
+    out = {}
+    for nm, ms in res.stage_ms.items():
+        ms *= ms_scale
+        a = alg.get(nm)
+        out[nm] = {"ms": round(ms, 3), "algorithmic_mb": round(a / 1e6, 1) if a else None,
+                   "GBps": round(a / ms / 1e6, 1) if a and ms > 0 else None,
+                   "frac": round(a / ms / 1e6 / peak, 4) if a and ms > 0 else None}
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import starch3_b200 as s3
@@ -153,12 +193,12 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from starch3_b200 import multigpu
+        return multigpu.bench(args, rank, world, local_rank, METRIC, UNIT, WORKLOADS, measured_peak_hbm, ClockSampler, cpu_compress)
 
-    bed = synth.bed(2, args.lines, seed=42 + rank)              # each rank: its own genome
+    workload, _ = WORKLOADS[args.cfg]
+    bed = synth.bed(args.cfg, args.lines, seed=42)
     nbytes = int(bed.nbytes)
     pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     pinned.numpy()[:] = bed
@@ -168,10 +208,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+    def sync():
         torch.cuda.synchronize()
 
     # ---- device-resident: input already in HBM, output left in HBM ----
@@ -189,116 +226,126 @@ def run_b200(args, rank, world, local_rank):
     top_name = max(table.items(), key=lambda kv: kv[1][1])[0]
     # timed region: K steps; only the dominant kernel keeps its events (its duration is measured live, here)
     ctx.profile_filter(top_name)
-    barrier()
+    sync()
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    stage_sum = {}
     for _ in range(args.steps):
         res = ctx.compress_bed_device(d_bed.data_ptr(), nbytes, 9, want_archive=False)
+        for k, v in res.stage_ms.items():
+            stage_sum[k] = stage_sum.get(k, 0.0) + v
     e1.record(stream)
-    barrier()
+    sync()
     dev_ms = e0.elapsed_time(e1)
     prof = ctx.profile_report()
     ctx.profile(False)
     ctx.profile_filter(None)
     lib_ms = res.device_ms
     launches = ctx.launch_count - launches0
-    # the same K steps once more without any events
-    barrier()
+    res.stage_ms = {k: v / args.steps for k, v in stage_sum.items()}
+    # the same K steps once more without any per-kernel events
+    sync()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
     for _ in range(args.steps):
-        res = ctx.compress_bed_device(d_bed.data_ptr(), nbytes, 9, want_archive=False)
+        ctx.compress_bed_device(d_bed.data_ptr(), nbytes, 9, want_archive=False)
     f1.record(stream)
-    barrier()
+    sync()
     noprof_ms = f0.elapsed_time(f1) / args.steps
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
 
     # ---- end to end: host buffer in, archive in host memory out, through the C ABI ----
-    host_view = pinned.numpy()
-    for _ in range(min(args.warmup, 2)):
-        r2 = ctx.compress_bed(host_view, 9, lazy=True)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r2 = ctx.compress_bed(host_view, 9, lazy=True)     # archive left in the library's pinned buffer
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    def e2e(host_view):
+        for _ in range(min(args.warmup, 2)):
+            r = ctx.compress_bed(host_view, 9, lazy=True)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = ctx.compress_bed(host_view, 9, lazy=True)     # archive left in the library's pinned buffer
+        sync()
+        return (time.perf_counter() - t0) * 1000.0 / args.steps, r
+
+    e2e_ms, r2 = e2e(pinned.numpy())
+    archive = bytes(r2.archive_view)                          # what the parity check below compares
     archive_bytes = int(r2.archive_size)
+    e2e_pageable_ms, _ = e2e(bed)                             # the same call fed from ordinary (pageable) memory, as the CLI does
 
-    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(nbytes)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    total_bytes = float(tot[0])
-
-    if rank == 0:
-        ms_per_step = dev_ms_max / args.steps
-        value = total_bytes / 1e6 / (ms_per_step / 1000.0)
-        e2e_value = total_bytes / 1e6 / (e2e_ms_max / args.steps / 1000.0)
-        peak, peak_src = measured_peak_hbm()
-        # dominant kernel: largest share of the per-kernel CUDA-event time in the timed region; its
-        # algorithmic bytes are accounted per launch inside the library (S3G_BYTES)
-        tot_kernel_ms = sum(v[1] for v in table.values()) or 1.0       # one step, every kernel (last warm-up step)
-        top_n, top_ms, top_bytes = prof[top_name]                        # the timed region, dominant kernel only
-        n_blocks, tf_bytes = res.n_blocks, res.tf_bytes
-        bytes_per_launch = top_bytes / top_n if top_n else 0.0
-        achieved = bytes_per_launch / (top_ms / top_n / 1000.0) / 1e9 if top_n and top_ms else 0.0
-        traffic = ncu_traffic(top_name, args.lines)
-        # whole-pipeline figure of SURVEY.md section 8(d): A = B_in + 2 B_tf + 4 B_blk + 12 M + B_out
-        b_out = res.streams_size
-        m_sym = 0.67 * tf_bytes
-        a_total = nbytes + 2 * tf_bytes + 4 * tf_bytes + 12 * m_sym + b_out
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "lines_per_gpu": args.lines, "input_mb_per_gpu": nbytes / 1e6,
-                       "transformed_mb_per_gpu": tf_bytes / 1e6, "bzip2_blocks_per_gpu": n_blocks,
-                       "compressed_mb_per_gpu": b_out / 1e6, "l2": "input (%.0f MB) larger than the 126 MB L2" % (nbytes / 1e6),
-                       "parallelism": f"{world} independent rank(s), chromosomes/blocks per rank, no collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": archive_bytes,
-                    "ms_per_step": e2e_ms_max / args.steps},
-            "gpu_launches": int(launches),
-            "ms_per_step_without_any_events": noprof_ms, "library_first_to_last_kernel_ms": lib_ms,
-            "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_share_of_step": table[top_name][1] / tot_kernel_ms, "launches": top_n,
-                         "avg_launch_ms": top_ms / top_n if top_n else None, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "note": "algorithmic bytes per launch are accounted inside the library (S3G_BYTES, DESIGN.md section 4); traffic = ncu dram bytes per launch from profiles/ncu_traffic.json",
-                         "pipeline": {"algorithmic_bytes_per_step": a_total, "achieved": a_total / (ms_per_step / 1000.0) / 1e9,
-                                      "frac": a_total / (ms_per_step / 1000.0) / 1e9 / peak}},
-            "kernels_note": "one step (the last warm-up step) with events around every launch",
-            "kernels": {k: {"launches": v[0], "ms": round(v[1], 3),
-                            "GBps": round(v[2] / (v[1] / 1000.0) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None,
-                            "frac": round(v[2] / (v[1] / 1000.0) / 1e9 / peak, 4) if v[1] > 0 and v[2] > 0 else None}
-                        for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])},
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            threads = min(cores, 24)
-            sample = synth.bed(2, args.ref_lines, seed=42)
+    ms_per_step = dev_ms / args.steps
+    value = nbytes / 1e6 / (ms_per_step / 1000.0)
+    peak, peak_src = measured_peak_hbm()
+    # ---- parity: the archive the timed call produced against the reference-libbz2 oracle (outside the timed region) ----
+    parity = None
+    cpu_dt = None
+    if not args.no_parity:
+        cpu_dt, okind, expect = cpu_compress(bed, min(os.cpu_count() or 1, 32))
+        parity = archive == expect
+        if not parity:
+            raise SystemExit(f"bench.py: the archive differs from the {okind} oracle's ({len(archive)} vs {len(expect)} bytes): no value reported")
+    # ---- roofline: SURVEY.md section 8(d), A = B_in + 2 B_tf + 4 B_blk + 12 M + B_out over first-to-last-kernel time ----
+    b_tf, b_blk, m_sym, b_out = res.tf_bytes, res.rle_bytes, res.mtf_symbols, res.streams_size
+    a_total = nbytes + 2 * b_tf + 4 * b_blk + 12 * m_sym + b_out
+    achieved = a_total / (ms_per_step / 1000.0) / 1e9
+    tot_kernel_ms = sum(v[1] for v in table.values()) or 1.0       # one step, every kernel (last warm-up step)
+    top_n, top_ms, top_bytes = prof[top_name]                        # the timed region, dominant kernel only
+    k_bytes = top_bytes / top_n if top_n else 0.0
+    k_ach = k_bytes / (top_ms / top_n / 1000.0) / 1e9 if top_n and top_ms else 0.0
+    stage_scale = ms_per_step / (sum(res.stage_ms.values()) or 1.0)  # stage marks cover first to last kernel of the call
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "parity_checked": parity,
+        "config": {"workload": workload, "lines": args.lines, "input_mb": nbytes / 1e6,
+                   "transformed_mb": b_tf / 1e6, "rle_mb": b_blk / 1e6, "mtf_symbols_m": m_sym / 1e6, "bzip2_blocks": res.n_blocks,
+                   "compressed_mb": b_out / 1e6, "l2": "input (%.0f MB) larger than the 126 MB L2" % (nbytes / 1e6),
+                   "parallelism": "1 GPU"},
+        "e2e": {"value": nbytes / 1e6 / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": archive_bytes,
+                "ms_per_step": e2e_ms, "host_buffer": "pinned (caller-provided); archive left in the library's pinned buffer"},
+        "e2e_pageable": {"value": nbytes / 1e6 / (e2e_pageable_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_pageable_ms,
+                         "host_buffer": "pageable (malloc), as the CLI client feeds it"},
+        "gpu_launches": int(launches),
+        "ms_per_step_without_any_events": noprof_ms, "library_first_to_last_kernel_ms": lib_ms,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": a_total,
+                     "formula": "A = B_in + 2 B_tf + 4 B_blk + 12 M + B_out (SURVEY.md 8(d)) with the measured B_blk and M; frac = A / t_device / peak",
+                     "kernel": top_name, "kernel_frac": k_ach / peak, "kernel_achieved": k_ach,
+                     "kernel_share_of_step": table[top_name][1] / tot_kernel_ms, "kernel_launches": top_n,
+                     "kernel_avg_launch_ms": top_ms / top_n if top_n else None, "kernel_algorithmic_bytes_per_launch": k_bytes,
+                     "traffic": ncu_traffic(top_name, args.cfg, args.lines),
+                     "note": "kernel_* = the dominant kernel, timed live with CUDA events inside the timed region; its algorithmic bytes per launch are "
+                             "accounted inside the library (S3G_BYTES, DESIGN.md section 4); traffic = ncu dram bytes per launch from profiles/ncu_traffic.json"},
+        "stages": stage_table(res, nbytes, stage_scale, peak),
+        "kernels_note": "one step (the last warm-up step) with events around every launch",
+        "kernels": {k: {"launches": v[0], "ms": round(v[1], 3),
+                        "GBps": round(v[2] / (v[1] / 1000.0) / 1e9, 1) if v[1] > 0 and v[2] > 0 else None,
+                        "frac": round(v[2] / (v[1] / 1000.0) / 1e9 / peak, 4) if v[1] > 0 and v[2] > 0 else None}
+                    for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        threads = min(cores, 32)
+        sample_lines = min(args.lines, args.ref_lines or args.lines)
+        sample = bed if sample_lines == args.lines else synth.bed(args.cfg, sample_lines, seed=42)
+        if sample_lines == args.lines and cpu_dt is not None:
+            dt, kind = cpu_dt, okind               # the parity check above just timed exactly this
+        else:
             dt, kind, _ = cpu_compress(sample, threads)
-            line["cpu_baseline"] = {"value": sample.nbytes / 1e6 / dt, "unit": UNIT, "cores": threads, "kind": kind,
-                                    "sample": f"{args.ref_lines} lines of cfg2 ({sample.nbytes / 1e6:.1f} MB BED), one pass, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        line["cpu_baseline"] = {"value": sample.nbytes / 1e6 / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                                "sample": f"{sample_lines} lines of cfg{args.cfg} ({sample.nbytes / 1e6:.1f} MB BED), one pass, {dt:.1f} s (B2: all host threads)"}
+        line["cpu_baseline"].update(cpu_baselines(args.cfg, args.lines, threads))
+    print(json.dumps(line), flush=True)
     ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
 
 
-def ncu_traffic(kernel, lines):
+def ncu_traffic(kernel, cfg, lines):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture
     (profiles/ncu_traffic.json, written from one `ncu --set full` run of this same workload), or None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
-        if int(d.get("lines", -1)) != int(lines):
+        if int(d.get("lines", -1)) != int(lines) or int(d.get("cfg", 2)) != int(cfg):
             return None
         return d["kernels"].get(kernel)
     except Exception:
@@ -311,10 +358,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--lines", type=int, default=10_000_000, help="lines per GPU (cfg2: 10 M)")
-    ap.add_argument("--ref-lines", type=int, default=6_000_000, help="bounded CPU sample, lines of cfg2 (about 20 core-seconds)")
+    ap.add_argument("--cfg", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (default: 2, the one the metric is quoted on)")
+    ap.add_argument("--lines", type=int, default=0, help="lines of the input (default: the config's BASELINE size; cfg5: 40 M)")
+    ap.add_argument("--ref-lines", type=int, default=0, help="bound the CPU arm to a sample of this many lines (default: the same input)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the archive comparison with the oracle (never for a reported number)")
     args = ap.parse_args()
+    if not args.lines:
+        args.lines = WORKLOADS[args.cfg][1] if args.cfg != 5 else 40_000_000
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

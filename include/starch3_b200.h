@@ -88,7 +88,14 @@ typedef struct s3g_result {
     void      *d_streams;      /* device: concatenated bzip2 streams (valid until the next call on ctx) */
     uint64_t   streams_size;
     double     device_ms;      /* CUDA-event time, first kernel to last kernel */
+    /* measured sizes of the intermediate stages (B_blk and M of the roofline formula) */
+    uint64_t   rle_bytes;      /* bytes after RLE1, all blocks (sum of nblock) */
+    uint64_t   mtf_symbols;    /* MTF/RUNA/RUNB symbols incl. EOB, all blocks (sum of nMTF) */
+    /* CUDA-event time per stage of the device-resident call, ms: [0] tokenise + transform, [1] RLE1 + cut + CRC,
+     * [2] block sort, [3] MTF + zero runs, [4] Huffman + pool, [5] assembly; zero after the pipelined host entry */
+    double     stage_ms[8];
 } s3g_result;
+#define S3G_STAGE_NAMES "tokenise+transform", "rle1+cut+crc", "blocksort", "mtf", "huffman", "assemble"
 
 /*
  * The whole hot path: tokenise + transform + per-chromosome bzip2 + container.

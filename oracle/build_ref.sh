@@ -25,11 +25,17 @@ done
 gcc $CFLAGS -fvisibility=default -I"$BZ" -c "$HERE/ref_harness.c" -o "$SCR/ref_harness.o"
 gcc -shared -o "$OUT/libs3ref.so" "$SCR"/{ref_harness,blocksort,huffman,crctable,randtable,decompress,bzlib}.o
 echo "build_ref: built $OUT/libs3ref.so"
-# the reference binary (needs jansson only to satisfy the #include / link line)
-if [ "${S3_SKIP_REF_BINARY:-0}" != "1" ] && [ ! -x "$OUT/starch3_ref" ]; then
+# the reference's vendored jansson 2.9: pins the archive metadata text (jansson_harness.c), and the reference
+# binary needs it to satisfy its #include / link line
+if [ ! -f "$OUT/libs3jansson.so" ] || { [ "${S3_SKIP_REF_BINARY:-0}" != "1" ] && [ ! -x "$OUT/starch3_ref" ]; }; then
   tar xzf "$REF/third-party/jansson-2.9.tar.gz" -C "$SCR"
-  ( cd "$SCR/jansson-2.9" && ./configure --prefix="$SCR/jansson" --disable-shared >/dev/null 2>&1 \
+  ( cd "$SCR/jansson-2.9" && CFLAGS="-O2 -fPIC" ./configure --prefix="$SCR/jansson" --disable-shared >/dev/null 2>&1 \
       && make -j8 >/dev/null 2>&1 && make install >/dev/null 2>&1 )
+  gcc -O2 -fPIC -shared -fvisibility=hidden -I"$SCR/jansson/include" "$HERE/jansson_harness.c" \
+      "$SCR/jansson/lib/libjansson.a" -o "$OUT/libs3jansson.so"
+  echo "build_ref: built $OUT/libs3jansson.so"
+fi
+if [ "${S3_SKIP_REF_BINARY:-0}" != "1" ] && [ ! -x "$OUT/starch3_ref" ]; then
   ( cd "$BZ" && make libbz2.a CC=gcc >/dev/null 2>&1 )
   g++ -std=c++11 -O3 -D_LARGEFILE64_SOURCE -D_FILE_OFFSET_BITS=64 -DDEBUG -w \
       -I"$REF/include" -I"$BZ" -I"$SCR/jansson/include" \

@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(HERE, "libs3oracle.so")
 _REF_SO = os.path.join(HERE, "_ref", "libs3ref.so")
+_JANSSON_SO = os.path.join(HERE, "_ref", "libs3jansson.so")
 REF_BINARY = os.path.join(HERE, "_ref", "starch3_ref")
 
 u8p = C.POINTER(C.c_uint8)
@@ -24,7 +25,7 @@ def build(force=False):
     if force or not os.path.exists(_ORACLE_SO) or os.path.getmtime(_ORACLE_SO) < os.path.getmtime(src):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
                                "-o", _ORACLE_SO, src])
-    if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF_SO)):
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(_REF_SO) or not os.path.exists(_JANSSON_SO)):
         subprocess.check_call([os.path.join(HERE, "build_ref.sh")])
 
 
@@ -248,6 +249,31 @@ def _json_string(b: bytes) -> bytes:
     return bytes(out)
 
 
+def have_jansson():
+    return os.path.exists(_JANSSON_SO)
+
+
+def jansson_header(level, note, streams):
+    """The metadata object printed by the reference's vendored jansson 2.9 (oracle/jansson_harness.c):
+    streams = [(name bytes, offset, size, lines, blocks, transformedBytes, nonUniqueBases, uniqueBases)].
+    Returns None when jansson refuses the object (a name or note that is not valid UTF-8)."""
+    L = C.CDLL(_JANSSON_SO)
+    L.s3ref_archive_header.restype = C.c_int64
+    L.s3ref_archive_header.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_uint64]
+    names = np.frombuffer(b"".join(s[0] for s in streams) + b"\0", dtype=np.uint8)
+    lens = np.array([len(s[0]) for s in streams] + [0], dtype=np.uint32)
+    fields = np.array([list(s[1:8]) for s in streams] + [[0] * 7], dtype=np.int64)
+    note_b = note.encode() if isinstance(note, str) else (note or b"")
+    cap = 4096 + len(note_b) * 6 + sum(len(s[0]) * 6 + 256 for s in streams)
+    out = np.empty(cap, dtype=np.uint8)
+    n = L.s3ref_archive_header(level, note_b, len(note_b), len(streams), _ptr(names), _ptr(lens), _ptr(fields), _ptr(out), cap)
+    if n == -1:
+        return None
+    assert n >= 0, n
+    return out[:n].tobytes()
+
+
 def archive(bed, level=9, note=""):
     """The whole path on the CPU: restated transform, one bzip2 stream per chromosome
     (reference libbz2 when oracle/_ref is built, else the restatement), container."""
@@ -261,6 +287,127 @@ def archive(bed, level=9, note=""):
         metas.append(b'{"chromosome":' + _json_string(c["name"]) +
                      b',"offset":%d,"size":%d,"lines":%d,"blocks":%d,"transformedBytes":%d,"nonUniqueBases":%d,"uniqueBases":%d}'
                      % (off, len(z), c["line_count"], nblk, c["tf_len"], c["bases_nonunique"], c["bases_unique"]))
+        streams.append(z)
+        off += len(z)
+    note_b = note.encode() if isinstance(note, str) else (note or b"")
+    hdr = (b'{"archive":{"type":"starch","version":{"major":3,"minor":0,"revision":0},"creator":"starch3_b200",'
+           b'"compression":"bzip2","blockSize100k":%d,"note":' % level) + _json_string(note_b) + b'},"streams":[' + b",".join(metas) + b"]}"
+    return bytes([0xca, 0x5c, 0xad, 0x1a]) + hdr + b"\n" + b"".join(streams)
+
+
+# ---- block-parallel form of the same reference compressor -------------------------------------------------
+# libbz2 compresses one stream on one core; the BASELINE-size single-chromosome inputs (cfg1/3/4) would take
+# minutes.  A bzip2 stream is "BZh<level>" + the blocks bit-concatenated + trailer (bz/compress.c:602-667), a block
+# depends only on its own input range (blocks are whole RLE1 chunks, bz/bzlib.c:225-338), and the ranges come from the
+# restated cut (s3o_rle1_blocks).  So: compress every range as a stream of its own with the reference libbz2 on a
+# thread pool, lift the block bits out of each, and join them.  tests/test_oracle.py pins this against
+# ref_bz_compress / bz_compress of the whole stream.
+_TRAILER = 0x177245385090
+
+
+def block_ranges(data, level=9):
+    """-> [(in_start, in_end)] of the blocks the reference cuts `data` into (no RLE bytes returned)."""
+    a = _u8(data)
+    cap = len(a) // (100000 * level - 19 - 260) + 4
+    descs = (BlockDesc * cap)()
+    n = lib().s3o_rle1_blocks(_ptr(a), len(a), level, descs, cap, None, 0)
+    assert n >= 0, n
+    return [(d.in_start, d.in_end) for d in descs[:n] if d.nblock]
+
+
+def _block_bits(z):
+    """(block bits as int, number of bits, block crc) of a ONE-block bzip2 stream z."""
+    v = int.from_bytes(z, "big")
+    total = len(z) * 8
+    for pad in range(8):                      # the trailer is followed by 0..7 padding bits
+        if (v >> (pad + 32)) & ((1 << 48) - 1) == _TRAILER:
+            nbits = total - pad - 80 - 32     # minus trailer, minus "BZh9"
+            bits = (v >> (pad + 80)) & ((1 << nbits) - 1)
+            crc = (bits >> (nbits - 80)) & 0xffffffff     # after the 48-bit block magic
+            return bits, nbits, crc
+    raise AssertionError("no stream trailer found")
+
+
+def bz_compress_blockwise(data, level=9, threads=None):
+    """Same bytes as ref_bz_compress(data, level) (bz_compress when oracle/_ref is absent), block-parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+    a = _u8(data)
+    comp = ref_bz_compress if have_ref() else bz_compress
+    ranges = block_ranges(a, level)
+    if len(ranges) <= 1:
+        return comp(a, level)
+    threads = threads or min(32, os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(lambda r: _block_bits(comp(a[r[0]:r[1]], level)), ranges))
+    acc = int.from_bytes(b"BZh" + bytes([48 + level]), "big")
+    nacc = 32
+    comb = 0
+    chunks = []
+    for bits, nbits, crc in parts:
+        comb = (((comb << 1) | (comb >> 31)) & 0xffffffff) ^ crc          # bz/compress.c:607-608
+        acc = (acc << nbits) | bits
+        nacc += nbits
+        if nacc >= 1 << 23:                    # flush whole bytes so the big integer stays small
+            keep = nacc & 7
+            chunks.append((acc >> keep).to_bytes((nacc - keep) // 8, "big"))
+            acc &= (1 << keep) - 1
+            nacc = keep
+    acc = (acc << 80) | (_TRAILER << 32) | comb
+    nacc += 80
+    pad = (-nacc) & 7
+    chunks.append((acc << pad).to_bytes((nacc + pad) // 8, "big"))
+    return b"".join(chunks)
+
+
+def archive_mt(bed, level=9, note="", threads=None):
+    """oracle.archive(bed, level, note) computed with all host threads: chromosomes and, inside a chromosome,
+    bzip2 blocks in parallel.  Used at the BASELINE sizes (10 M .. 100 M lines)."""
+    from concurrent.futures import ThreadPoolExecutor
+    threads = threads or min(32, os.cpu_count() or 1)
+    tf, chroms, _ = transform(bed)
+    tfa = np.frombuffer(tf, dtype=np.uint8)
+    comp = ref_bz_compress if have_ref() else bz_compress
+    # work units: (chromosome, block range); a one-block chromosome is compressed whole
+    units = []
+    per_chrom = []
+    for ci, c in enumerate(chroms):
+        s = tfa[c["tf_off"]:c["tf_off"] + c["tf_len"]]
+        rng = block_ranges(s, level)
+        per_chrom.append((s, rng))
+        if len(rng) <= 1:
+            units.append((ci, None))
+        else:
+            units.extend((ci, r) for r in rng)
+
+    def work(u):
+        ci, r = u
+        s = per_chrom[ci][0]
+        return comp(s, level) if r is None else _block_bits(comp(s[r[0]:r[1]], level))
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        done = list(ex.map(work, units))
+    streams, metas, off, k = [], [], 0, 0
+    for ci, c in enumerate(chroms):
+        rng = per_chrom[ci][1]
+        if len(rng) <= 1:
+            z = done[k]; k += 1
+        else:
+            acc = int.from_bytes(b"BZh" + bytes([48 + level]), "big"); nacc = 32; comb = 0; chunks = []
+            for bits, nbits, crc in done[k:k + len(rng)]:
+                comb = (((comb << 1) | (comb >> 31)) & 0xffffffff) ^ crc
+                acc = (acc << nbits) | bits; nacc += nbits
+                if nacc >= 1 << 23:
+                    keep = nacc & 7
+                    chunks.append((acc >> keep).to_bytes((nacc - keep) // 8, "big"))
+                    acc &= (1 << keep) - 1; nacc = keep
+            k += len(rng)
+            acc = (acc << 80) | (_TRAILER << 32) | comb; nacc += 80
+            pad = (-nacc) & 7
+            chunks.append((acc << pad).to_bytes((nacc + pad) // 8, "big"))
+            z = b"".join(chunks)
+        metas.append(b'{"chromosome":' + _json_string(c["name"]) +
+                     b',"offset":%d,"size":%d,"lines":%d,"blocks":%d,"transformedBytes":%d,"nonUniqueBases":%d,"uniqueBases":%d}'
+                     % (off, len(z), c["line_count"], len(rng), c["tf_len"], c["bases_nonunique"], c["bases_unique"]))
         streams.append(z)
         off += len(z)
     note_b = note.encode() if isinstance(note, str) else (note or b"")

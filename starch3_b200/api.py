@@ -41,7 +41,11 @@ class CResult(C.Structure):
     _fields_ = [("archive", C.POINTER(C.c_uint8)), ("archive_size", C.c_uint64), ("streams_off", C.c_uint64),
                 ("chroms", C.POINTER(CChrom)), ("n_chroms", C.c_uint64), ("n_lines", C.c_uint64),
                 ("n_blocks", C.c_uint64), ("tf_bytes", C.c_uint64), ("dropped_tail_bytes", C.c_uint64),
-                ("d_streams", C.c_void_p), ("streams_size", C.c_uint64), ("device_ms", C.c_double)]
+                ("d_streams", C.c_void_p), ("streams_size", C.c_uint64), ("device_ms", C.c_double),
+                ("rle_bytes", C.c_uint64), ("mtf_symbols", C.c_uint64), ("stage_ms", C.c_double * 8)]
+
+
+STAGE_NAMES = ["tokenise+transform", "rle1+cut+crc", "blocksort", "mtf", "huffman", "assemble"]
 
 
 class CBlockDesc(C.Structure):
@@ -115,6 +119,9 @@ class Result:
         self.tf_bytes = cres.tf_bytes
         self.dropped_tail_bytes = cres.dropped_tail_bytes
         self.device_ms = cres.device_ms
+        self.rle_bytes = cres.rle_bytes
+        self.mtf_symbols = cres.mtf_symbols
+        self.stage_ms = {nm: cres.stage_ms[i] for i, nm in enumerate(STAGE_NAMES)}
         self.streams_size = cres.streams_size
         self.streams_off = cres.streams_off
         self.d_streams = cres.d_streams

@@ -52,6 +52,31 @@ void prof_end(Ctx *ctx, int idx)
     if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].e1, ctx->stream);
 }
 
+void stage_mark(Ctx *ctx, int stage)
+{
+    size_t k = ctx->marks.size();
+    if (k >= ctx->mark_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+        ctx->mark_pool.push_back(e);
+    }
+    cudaEventRecord(ctx->mark_pool[k], ctx->stream);
+    ctx->marks.emplace_back(stage, ctx->mark_pool[k]);
+}
+
+// after the call's final synchronise: per-stage sums of the intervals between consecutive marks
+static void stage_collect(Ctx *ctx, double *stage_ms)
+{
+    for (int i = 0; i < 8; i++) stage_ms[i] = 0;
+    for (size_t k = 0; k + 1 < ctx->marks.size(); k++) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, ctx->marks[k].second, ctx->marks[k + 1].second) != cudaSuccess) { cudaGetLastError(); continue; }
+        int st = ctx->marks[k].first;
+        if (st >= 0 && st < 8) stage_ms[st] += t;
+    }
+    ctx->marks.clear();
+}
+
 static DevBuf *const *all_bufs(Ctx *c, size_t *n)
 {
     static thread_local DevBuf *list[64];
@@ -106,7 +131,9 @@ static int compress_streams(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uin
     const bool timing = getenv("S3G_TIMING") != nullptr;
     double t0 = timing ? host_ms() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
     CutResult cut;
+    stage_mark(ctx, 1);
     S3G_TRY(run_rle_cut(ctx, d_in, n, d_soff, n_streams, level, &cut));
+    ctx->last_rle_bytes = cut.rle_bytes;
     if (timing) t1 = host_ms();
     uint64_t nb = cut.n_blocks;
     *n_blocks_out = nb;
@@ -125,15 +152,20 @@ static int compress_streams(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uin
         for (uint64_t b0 = 0; b0 < nb; b0 += batch) {
             uint64_t cnt = std::min<uint64_t>(batch, nb - b0);
             if (timing) t2 = host_ms();
+            stage_mark(ctx, 2);
             S3G_TRY(run_bwt(ctx, b0, cnt));
             if (timing) t3 = host_ms();
+            stage_mark(ctx, 3);
             S3G_TRY(run_mtf(ctx, b0, cnt));
+            stage_mark(ctx, 4);
             S3G_TRY(run_huff(ctx, b0, cnt, 1, nullptr, nullptr));
             S3G_TRY(run_pool_append(ctx, b0, cnt));
             if (timing) t4 = host_ms();
         }
     }
+    stage_mark(ctx, 5);
     S3G_TRY(run_assemble(ctx, nb, n_streams, level, total_bytes));
+    stage_mark(ctx, -1);
     if (timing) {
         t5 = host_ms();
         fprintf(stderr, "[s3g timing] rle+cut %.2f  batch setup %.2f  bwt %.2f  mtf+huff+pool (enqueue) %.2f  assemble %.2f  total %.2f ms (host clock)\n",
@@ -211,7 +243,8 @@ struct PartOut {
     std::vector<uint8_t> names;        // their names, back to back
     uint64_t n_seen = 0;               // chromosomes found in the range
     uint64_t cs_next = 0;              // absolute offset of the chromosome left for the next range
-    uint64_t streams_size = 0, n_blocks = 0, dropped = 0, tf_kept = 0;
+    uint64_t streams_size = 0, n_blocks = 0, dropped = 0, tf_kept = 0, rle_bytes = 0, mtf_symbols = 0;
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // tokenise + transform the range; decides how many chromosomes are compressed here
@@ -220,6 +253,9 @@ static int part_front(Ctx *ctx, const uint8_t *d_bed, uint64_t off, uint64_t len
     const uint64_t base = off & ~(uint64_t)15;                 // the tokenizer loads 16-byte vectors
     const bool timing = getenv("S3G_TIMING") != nullptr;
     double tt0 = timing ? host_ms() : 0;
+    ctx->marks.clear();
+    ctx->last_rle_bytes = 0;
+    stage_mark(ctx, 0);
     S3G_TRY(run_transform(ctx, d_bed + base, len + (off - base), &tr, false, (uint32_t)(off - base)));
     if (timing) fprintf(stderr, "[s3g timing] transform %.2f ms (host clock)\n", host_ms() - tt0);
     po.n_seen = tr.n_chroms;
@@ -249,10 +285,15 @@ static int part_back(Ctx *ctx, const uint8_t *d_bed, uint64_t off, int level, bo
         S3G_TRY(compress_streams(ctx, ctx->tf.as<uint8_t>(), po.tf_kept, ctx->soff.as<uint64_t>(), kept, level, &n_blocks,
                                  &total_bytes));
     }
+    else stage_mark(ctx, -1);
     S3G_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     po.n_blocks = n_blocks;
     po.streams_size = total_bytes;
+    po.rle_bytes = ctx->last_rle_bytes;
     ctx->last_streams_size = total_bytes;
+    ctx->last_streams_host = nullptr;
+    ctx->h_blocks.resize(n_blocks);
+    if (n_blocks) S3G_CUDA(cudaMemcpyAsync(ctx->h_blocks.data(), ctx->blocks.p, n_blocks * sizeof(BlockInfo), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<StreamMeta> meta(kept);
     std::vector<uint64_t> name_off(kept + 1, 0);
     for (uint64_t c = 0; c < kept; c++) name_off[c + 1] = name_off[c] + po.chroms[c].name_len;
@@ -270,6 +311,8 @@ static int part_back(Ctx *ctx, const uint8_t *d_bed, uint64_t off, int level, bo
         }
     }
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (const BlockInfo &B : ctx->h_blocks) po.mtf_symbols += B.n_mtf;
+    stage_collect(ctx, po.stage_ms);
     for (uint64_t c = 0; c < kept; c++) {
         po.chroms[c].bz_off = meta[c].byte_off; po.chroms[c].bz_len = meta[c].byte_len;
         po.chroms[c].n_blocks = (uint32_t)meta[c].n_blocks;
@@ -316,6 +359,8 @@ static int compress_bed_impl(Ctx *ctx, const uint8_t *d_bed, uint64_t n, int lev
     res->d_streams = ctx->streams.p;
     res->streams_size = po.streams_size;
     res->dropped_tail_bytes = po.dropped;
+    res->rle_bytes = po.rle_bytes; res->mtf_symbols = po.mtf_symbols;
+    memcpy(res->stage_ms, po.stage_ms, sizeof res->stage_ms);
     ctx->h_chroms = po.chroms;
     fill_result(res, po.chroms);
     if (!res->chroms) { set_error("out of host memory"); return S3G_E_NOMEM; }
@@ -461,7 +506,7 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     S3G_TRY(ctx->bed.ensure(n + 64));
     // the archive buffer must exist before the workers copy into it: the compressed size is not known yet,
     // half of the input is generous for BED (the one-shot path takes over if it ever is not)
-    S3G_TRY(ensure_archive(ctx, HDR_RESERVE + std::max<uint64_t>(n / 2, ctx->last_streams_size + (ctx->last_streams_size >> 3)) + 4096));
+    S3G_TRY(ensure_archive(ctx, HDR_RESERVE + std::max<uint64_t>(n / 2, ctx->archive_hint + (ctx->archive_hint >> 3)) + 4096));
     cudaEvent_t t0 = ctx->ev0, t1 = ctx->ev1;
     S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));
     for (int i = 0; i < nparts; i++) {
@@ -490,6 +535,7 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
         chroms.insert(chroms.end(), po.chroms.begin(), po.chroms.end());
         if (!po.chroms.empty()) names.insert(names.end(), po.names.begin(), po.names.end() - 1);
         res->n_blocks += po.n_blocks;
+        res->rle_bytes += po.rle_bytes; res->mtf_symbols += po.mtf_symbols;
     }
     names.push_back(0);
     { uint64_t t = 0; for (s3g_chrom &c : chroms) { c.tf_off = t; t += c.tf_len; } }    // as in one transformed buffer
@@ -512,8 +558,10 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     res->streams_off = streams_off;
     res->streams_size = sh.streams_so_far;
     res->archive_size = streams_off + sh.streams_so_far;
-    res->d_streams = nullptr;                                  // the streams of the ranges live in the worker contexts
-    ctx->last_streams_size = sh.streams_so_far;
+    res->d_streams = nullptr;                                  // the streams of the ranges lived in the worker contexts
+    ctx->last_streams_size = sh.streams_so_far;                // s3g_read_streams serves them from the pinned archive
+    ctx->last_streams_host = ctx->h_archive + HDR_RESERVE;
+    ctx->archive_hint = sh.streams_so_far;
     return S3G_OK;
 }
 
@@ -550,11 +598,16 @@ int s3g_init(int device, s3g_ctx **out)
     s3g_ctx *c = new (std::nothrow) s3g_ctx();
     if (!c) { set_error("out of host memory"); return S3G_E_NOMEM; }
     c->device = device;
-    S3G_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->stream = c->own_stream;
-    S3G_CUDA(cudaEventCreate(&c->ev0));
-    S3G_CUDA(cudaEventCreate(&c->ev1));
-    S3G_CUDA(cudaMallocHost(&c->h_scalars, 64 * 8));
+    auto setup = [&]() -> int {
+        S3G_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        S3G_CUDA(cudaEventCreate(&c->ev0));
+        S3G_CUDA(cudaEventCreate(&c->ev1));
+        S3G_CUDA(cudaMallocHost(&c->h_scalars, 64 * 8));
+        return S3G_OK;
+    };
+    int rc = setup();
+    if (rc != S3G_OK) { s3g_destroy(c); return rc; }       // s3g_destroy releases whatever was created
     *out = c;
     return S3G_OK;
 }
@@ -563,7 +616,7 @@ void s3g_destroy(s3g_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     size_t k; DevBuf *const *bl = all_bufs(ctx, &k);
     for (size_t i = 0; i < k; i++) bl[i]->release();
     for (int k2 = 0; k2 < 2; k2++) if (ctx->sub[k2]) { s3g_destroy(static_cast<s3g_ctx *>(ctx->sub[k2])); ctx->sub[k2] = nullptr; }
@@ -574,6 +627,7 @@ void s3g_destroy(s3g_ctx *ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->mark_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -662,6 +716,10 @@ int s3g_read_streams(s3g_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n)
     if (!ctx || !dst || !n) { set_error("null argument"); return S3G_E_PARAM; }
     *n = ctx->last_streams_size;
     if (*n > cap) { set_error("cap too small: need %llu", (unsigned long long)*n); return S3G_E_CAPACITY; }
+    if (ctx->last_streams_host) {          // pipelined host entry: the streams went straight into the pinned archive
+        memcpy(dst, ctx->last_streams_host, *n);
+        return S3G_OK;
+    }
     S3G_CUDA(cudaSetDevice(ctx->device));
     if (*n) S3G_CUDA(cudaMemcpyAsync(dst, ctx->streams.p, *n, cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -754,7 +812,7 @@ int s3g_rle1(s3g_ctx *ctx, const uint8_t *in, uint64_t n, int level, s3g_blockde
         }
         if (rle_out) {
             if (off + B.nblock > rle_cap) { set_error("rle_cap too small"); return S3G_E_CAPACITY; }
-            S3G_CUDA(cudaMemcpyAsync(rle_out + off, ctx->blk_bytes.as<uint8_t>() + b * (uint64_t)BLK_STRIDE, B.nblock, cudaMemcpyDeviceToHost, ctx->stream));
+            S3G_CUDA(cudaMemcpyAsync(rle_out + off, ctx->blk_bytes.as<uint8_t>() + B.blk_off, B.nblock, cudaMemcpyDeviceToHost, ctx->stream));
         }
         off += B.nblock;
     }
@@ -767,7 +825,7 @@ __global__ void k_in_use_from_bytes(const uint8_t *blk, const BlockInfo *blocks,
 {
     uint64_t b = blockIdx.y;
     uint32_t n = blocks[b].nblock;
-    const uint8_t *p = blk + b * (uint64_t)BLK_STRIDE;
+    const uint8_t *p = blk + blocks[b].blk_off;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) in_use[b * 256 + p[i]] = 1;
 }
 __global__ void k_block_maps_api(const uint8_t *in_use, BlockInfo *blocks, uint8_t *seq_map)
@@ -793,17 +851,21 @@ static int load_blocks(Ctx *ctx, const uint8_t *blocks, const uint64_t *off, uin
 {
     ctx->h_blocks.assign(nb, BlockInfo());
     S3G_TRY(ctx->blocks.ensure(nb * sizeof(BlockInfo)));
-    S3G_TRY(ctx->blk_bytes.ensure(nb * (uint64_t)BLK_STRIDE));
+    if (nb > 65535) { set_error("at most 65535 blocks per stage call"); return S3G_E_LIMIT; }
     S3G_TRY(ctx->in_use.ensure(nb * 256));
     S3G_TRY(ctx->seq_map.ensure(nb * 256));
+    uint64_t packed = 0;
     for (uint64_t b = 0; b < nb; b++) {
         uint64_t len = off[b + 1] - off[b];
         if (len == 0 || len > 900000) { set_error("block %llu has invalid length %llu", (unsigned long long)b, (unsigned long long)len); return S3G_E_PARAM; }
         BlockInfo &B = ctx->h_blocks[b];
         memset(&B, 0, sizeof B);
-        B.nblock = (uint32_t)len; B.orig_ptr = -1;
-        S3G_CUDA(cudaMemcpyAsync(ctx->blk_bytes.as<uint8_t>() + b * (uint64_t)BLK_STRIDE, blocks + off[b], len, cudaMemcpyHostToDevice, ctx->stream));
+        B.nblock = (uint32_t)len; B.orig_ptr = -1; B.blk_off = packed;
+        packed += blk_slot_bytes(B.nblock);
     }
+    S3G_TRY(ctx->blk_bytes.ensure(packed + 256));
+    for (uint64_t b = 0; b < nb; b++)
+        S3G_CUDA(cudaMemcpyAsync(ctx->blk_bytes.as<uint8_t>() + ctx->h_blocks[b].blk_off, blocks + off[b], off[b + 1] - off[b], cudaMemcpyHostToDevice, ctx->stream));
     S3G_CUDA(cudaMemcpyAsync(ctx->blocks.p, ctx->h_blocks.data(), nb * sizeof(BlockInfo), cudaMemcpyHostToDevice, ctx->stream));
     if (in_use) S3G_CUDA(cudaMemcpyAsync(ctx->in_use.p, in_use, nb * 256, cudaMemcpyHostToDevice, ctx->stream));
     else {

@@ -98,12 +98,13 @@ __device__ __forceinline__ void or_bits(uint32_t *dst, uint64_t bitpos, uint32_t
 
 __global__ void k_concat(const BlockInfo *blocks, const uint32_t *pool, const uint64_t *woff, const StreamMeta *meta, uint32_t *dst)
 {
-    uint64_t b = blockIdx.y;
+    // 32 CTAs per block, block index in grid.x (grid.y stops at 65535; many small chromosomes make more blocks than that)
+    uint64_t b = blockIdx.x >> 5, part = blockIdx.x & 31;
     const BlockInfo &B = blocks[b];
     uint64_t nw = (B.n_bits + 31) >> 5;
     const uint32_t *src = pool + woff[b];
     uint64_t base = meta[B.chrom].byte_off * 8 + B.bit_off;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x)
+    for (uint64_t i = part * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)32 * blockDim.x)
         or_bits(dst, base + i * 32, src[i]);
 }
 
@@ -147,8 +148,8 @@ int run_assemble(Ctx *ctx, uint64_t n_blocks, uint64_t n_streams, int level, uin
     uint32_t *dst = ctx->streams.as<uint32_t>();
     S3G_CUDA(cudaMemsetAsync(dst, 0, words * 4, ctx->stream));
     if (n_blocks) {
-        dim3 grid(32, (unsigned)n_blocks);
-        S3G_LAUNCH(ctx, k_concat, grid, 256, 0, blocks, ctx->pool.as<uint32_t>(), ctx->pool_woff.as<uint64_t>(), meta, dst);
+        if (n_blocks > (1ull << 26)) { set_error("too many bzip2 blocks in one call"); return S3G_E_LIMIT; }
+        S3G_LAUNCH(ctx, k_concat, (unsigned)(n_blocks * 32), 256, 0, blocks, ctx->pool.as<uint32_t>(), ctx->pool_woff.as<uint64_t>(), meta, dst);
     }
     S3G_LAUNCH(ctx, k_stream_frame, (unsigned)((n_streams + 63) / 64), 64, 0, blocks, first_block, meta, n_streams, level, dst);
     S3G_LAUNCH(ctx, k_bswap, 592, 256, 0, dst, words);

@@ -37,7 +37,7 @@ constexpr int NT = (BLK_STRIDE + STILE - 1) / STILE;   // tiles per block slot (
 constexpr uint32_t FINAL = 0x80000000u;
 
 struct BwtP {
-    const uint8_t *blk;        // block bytes of batch block 0 (slot stride BLK_STRIDE)
+    const uint8_t *blk;        // packed block bytes of the call (block lb of the batch at blocks[lb].blk_off)
     const uint8_t *seq;        // unseqToSeq maps, 256 per block
     const BlockInfo *blocks;   // batch block 0
     uint32_t *sa, *rk;         // [nb][BLK_STRIDE]
@@ -87,7 +87,7 @@ __device__ __forceinline__ bool get_item(const BwtP &P, uint32_t lb, uint32_t p,
 {
     if (p >= cnt) return false;
     if (MODE == MODE_INIT) {
-        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *b = P.blk + P.blocks[lb].blk_off;
         const uint8_t *sq = P.seq + (uint64_t)lb * 256;
         uint32_t k = P.init_k[lb], k32 = P.init_k32[lb], a = P.init_a[lb];
         uint64_t key_ = 0;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint32_t *ghist)
     const uint32_t n = P.cnt_n[lb];
     const uint32_t t0 = blockIdx.x * KT;
     if ((uint64_t)t0 * STILE >= n) return;
-    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *b = P.blk + P.blocks[lb].blk_off;
     const uint32_t k = P.init_k[lb], k32 = P.init_k32[lb], a = P.init_a[lb], f = P.init_f[lb];
     for (int i = tid; i < NPASS * SWN; i += ST) (&S.hist[0][0])[i] = 0;
     S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
     if (!STABLE) {
         // first pass: thread t builds the records of positions SWI t .. SWI t + SWI - 1 of the tile with a rolling key,
         // exactly as k_keys did for the histograms (any record-to-thread mapping will do: no stability needed)
-        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *b = P.blk + P.blocks[lb].blk_off;
         const uint32_t k = P.init_k[lb], a = P.init_a[lb], f = P.init_f[lb];
         const uint32_t tbase0 = tile * SW_TILE, cntT = min((uint32_t)SW_TILE, cnt - tbase0);
         if (tid < 256) {
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
     if (p0 >= n) return;
     const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
     const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
-    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *b = P.blk + P.blocks[lb].blk_off;
     uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
     uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
     const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
@@ -1038,7 +1038,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32) k_finish_mid(BwtP P, const uint
         const uint32_t n = P.cnt_n[lb];
         const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
         const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
-        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *b = P.blk + P.blocks[lb].blk_off;
         const uint8_t *seq = P.seq + (uint64_t)lb * 256;
         uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
         uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
@@ -1157,7 +1157,7 @@ __global__ void __launch_bounds__(FB_TH) k_finish_big(BwtP P, const uint64_t *kv
         const uint32_t n = P.cnt_n[lb];
         const uint64_t *a = kv + (uint64_t)lb * BLK_STRIDE;
         const uint32_t *k30 = P.rk + (uint64_t)lb * BLK_STRIDE;
-        const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+        const uint8_t *b = P.blk + P.blocks[lb].blk_off;
         uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
         uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
         const uint32_t k0 = P.init_k[lb], k32 = P.init_k32[lb];
@@ -1478,7 +1478,7 @@ __global__ void __launch_bounds__(ST) k_bwt_finish(BwtP P, BlockInfo *blocks, ui
     if ((uint64_t)tile * STILE >= n) return;
     const uint32_t *sa = P.sa + (uint64_t)lb * BLK_STRIDE;
     const uint32_t *rk = P.rk + (uint64_t)lb * BLK_STRIDE;
-    const uint8_t *b = P.blk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *b = P.blk + P.blocks[lb].blk_off;
     const uint8_t *sq = P.seq + (uint64_t)lb * 256;
     uint8_t *L = lcol + (uint64_t)lb * BLK_STRIDE;
     bool tie = false;
@@ -1575,7 +1575,7 @@ __global__ void k_fallback_exact(BwtP P, BlockInfo *blocks)
     uint32_t lb = blockIdx.x;
     if (threadIdx.x != 0 || !blocks[lb].tie) return;
     const int n = (int)P.cnt_n[lb];
-    const uint8_t *blk = P.blk + (uint64_t)lb * BLK_STRIDE;
+    const uint8_t *blk = P.blk + P.blocks[lb].blk_off;
     FbState st;
     st.fmap = P.sa + (uint64_t)lb * BLK_STRIDE;
     st.ec = P.rk + (uint64_t)lb * BLK_STRIDE;
@@ -1648,7 +1648,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (9 * 4 + NT * 2 * 4) + 64));
     S3G_TRY(ctx->lcol.ensure(slots));
     BwtP P;
-    P.blk = ctx->blk_bytes.as<uint8_t>() + b0 * (uint64_t)BLK_STRIDE;
+    P.blk = ctx->blk_bytes.as<uint8_t>();
     P.seq = ctx->seq_map.as<uint8_t>() + b0 * 256;
     P.blocks = ctx->blocks.as<BlockInfo>() + b0;
     P.sa = ctx->sa.as<uint32_t>(); P.rk = ctx->rk.as<uint32_t>();
@@ -1670,15 +1670,15 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     double N = 0;                       // rotations in this batch
     for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
     const double HS = (double)nb * NT * NBINS * 4 * 2;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // per context, not per process: the attribute belongs to the device the context is bound to
+    if (!ctx->attr_bwt) {
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_scatter<MODE_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KeysSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_sweep_ordered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_sweep_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        attr_done = true;
+        ctx->attr_bwt = true;
     }
     const uint32_t *no_act = nullptr;
     const uint64_t *no_kv = nullptr;

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <utility>
 #include "../../include/starch3_b200.h"
 
 namespace s3g {
@@ -58,7 +59,9 @@ struct DevBuf {
 };
 
 // ---- geometry of one bzip2 block in the batched device layout -------------
-// Every block owns a fixed-stride slot, so block b's arrays start at b*BLK_STRIDE.
+// Inside a batch of stages 3b..3d every block owns a fixed-stride slot, so batch block b's arrays start at
+// b*BLK_STRIDE.  The post-RLE1 bytes of ALL blocks of a call are packed instead (BlockInfo.blk_off): an input of
+// many small chromosomes has many small blocks.
 // nblock never exceeds 100000*9-19 + 9 (bz/bzlib.c:194, :284-289 and the final flush).
 constexpr uint32_t BLK_STRIDE = 900096;         // elements per block slot (multiple of 128)
 constexpr uint32_t BITS_WORDS = 491520;         // 32-bit words per block of emitted bits (>= 17 bit * 900001 + header)
@@ -78,7 +81,10 @@ struct BlockInfo {
     uint32_t pad;
     uint64_t n_bits;             // bits of this block incl. its 105-bit block header
     uint64_t bit_off;            // bit offset inside its stream
+    uint64_t blk_off;            // where the block's post-RLE1 bytes start inside ctx->blk_bytes (packed, 128-byte aligned)
 };
+// bytes a block of n post-RLE1 bytes takes in the packed blk_bytes buffer
+__host__ __device__ inline uint64_t blk_slot_bytes(uint32_t n) { return ((uint64_t)n + 64 + 127) & ~(uint64_t)127; }
 
 // ---- per-device context -----------------------------------------------------
 struct Ctx {
@@ -86,6 +92,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: each context sets it once on its own device
+    bool attr_bwt = false, attr_mtf = false, attr_huff = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // pinned host scratch for small read-backs
     uint64_t *h_scalars = nullptr;   // 64 x u64
@@ -104,7 +112,13 @@ struct Ctx {
     std::vector<BlockInfo> h_blocks;
     std::vector<s3g_chrom> h_chroms;
     uint64_t pool_words = 0;               // words appended to the pool so far
-    uint64_t last_streams_size = 0;
+    uint64_t last_streams_size = 0;        // bytes of ctx->streams written by the last call on this context
+    uint64_t archive_hint = 0;             // compressed size of the last host-entry call: sizes the next pinned archive buffer
+    const uint8_t *last_streams_host = nullptr;   // after the pipelined host entry the streams live in the pinned archive only
+    // stage marks of the current call: (stage id, event); consecutive marks bracket a stage
+    std::vector<cudaEvent_t> mark_pool;
+    std::vector<std::pair<int, cudaEvent_t>> marks;
+    uint64_t last_rle_bytes = 0;
     uint8_t *h_archive = nullptr;          // pinned; holds the archive of the last compress call
     size_t h_archive_cap = 0;
     // pipelined host entry (s3g_compress_bed on large inputs): upload stream, one event per input range,
@@ -138,6 +152,8 @@ struct Ctx {
     } while (0)
 
 int check_launch(const char *what);
+// stage mark: the time until the next mark is charged to `stage` (s3g_result.stage_ms)
+void stage_mark(Ctx *ctx, int stage);
 int prof_begin(Ctx *ctx, const char *name);
 void prof_end(Ctx *ctx, int idx);
 
@@ -222,9 +238,10 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
 
 struct CutResult {
     uint64_t n_blocks = 0;
+    uint64_t rle_bytes = 0;        // bytes after RLE1, all blocks
 };
 // kernel (3a) over a concatenated buffer of `n_streams` streams; stream s covers [d_soff[s], d_soff[s+1]).
-// Leaves ctx->blocks (BlockInfo[n_blocks]), ctx->blk_bytes (slot b at b*BLK_STRIDE), ctx->in_use (256 B per block).
+// Leaves ctx->blocks (BlockInfo[n_blocks]), ctx->blk_bytes (block b at BlockInfo.blk_off), ctx->in_use (256 B per block).
 int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams,
                 int level, CutResult *out);
 

@@ -533,11 +533,10 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
     // its own when it does not (S3G_ZRUN=fused|split overrides: both forms are tested)
     int fused = nb >= (uint64_t)SM_COUNT ? 1 : 0;
     if (const char *e = getenv("S3G_ZRUN")) fused = !strcmp(e, "split") ? 0 : !strcmp(e, "fused") ? 1 : fused;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->attr_mtf) {
         S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)24 * MS_SMALL * 4 + tail_smem)));
         S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MTF_REG_MAX * MS_BIG * 4 + tail_smem)));
-        attr_done = true;
+        ctx->attr_mtf = true;
     }
     S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
     if (any_small)
@@ -915,11 +914,10 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
 {
     if (nb == 0) return S3G_OK;
     S3G_TRY(ctx->bits.ensure((size_t)nb * BITS_WORDS * 4));
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->attr_huff) {
         S3G_CUDA(cudaFuncSetAttribute(k_huff<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
         S3G_CUDA(cudaFuncSetAttribute(k_huff<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
-        attr_done = true;
+        ctx->attr_huff = true;
     }
     double N = 0;
     for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;

@@ -352,6 +352,23 @@ __global__ void k_compact_blocks(const BlockInfo *prov, const uint64_t *prov_bas
     if (threadIdx.x == 0 && chroms) chroms[s].n_blocks = (uint32_t)nb;
 }
 
+// packed layout of the block bytes: blk_off = exclusive sum of the slot sizes (one CTA, chunks of 1024 blocks)
+__global__ void __launch_bounds__(1024) k_block_offsets_dev(BlockInfo *blocks, const uint64_t *nb_p, uint64_t *total)
+{
+    __shared__ uint64_t sm[33];
+    const uint64_t nb = *nb_p;
+    uint64_t carry = 0;
+    for (uint64_t b0 = 0; b0 < nb; b0 += 1024) {
+        uint64_t b = b0 + threadIdx.x;
+        uint64_t w = b < nb ? blk_slot_bytes(blocks[b].nblock) : 0, tot;
+        uint64_t ex = block_excl_sum<uint64_t>(w, sm, &tot);
+        if (b < nb) blocks[b].blk_off = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
 // ---- pass 4: write the RLE1 bytes into the block slots ----------------------
 // A tile that lies inside one block (all but one tile in ~220) stages its output in shared memory at
 // the same 16-byte phase as its destination and writes it out with aligned vector stores; the bytes
@@ -408,7 +425,7 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
             }
         }
         __syncthreads();
-        uint8_t *dst = blk_bytes + bi * (uint64_t)BLK_STRIDE + (d0 - ph);        // 16-byte aligned
+        uint8_t *dst = blk_bytes + blocks[bi].blk_off + (d0 - ph);        // 16-byte aligned
         const uint32_t lo_b = ph, hi_b = ph + tot;                                // valid bytes of s_buf
         for (uint32_t c = threadIdx.x * 16; c < hi_b; c += RT * 16) {
             if (c >= lo_b && c + 16 <= hi_b) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(s_buf + c);
@@ -427,7 +444,7 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
     }
     uint64_t bi = lo;
     uint64_t b_end = blocks[bi].in_end, b_e0 = blocks[bi].e_base;
-    uint8_t *dst = blk_bytes + bi * (uint64_t)BLK_STRIDE;
+    uint8_t *dst = blk_bytes + blocks[bi].blk_off;
     uint8_t *use = in_use + bi * 256;
 #pragma unroll
     for (int k = 0; k < RB; k++) {
@@ -436,7 +453,7 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
             if (i >= b_end) {
                 bi++;
                 b_end = blocks[bi].in_end; b_e0 = blocks[bi].e_base;
-                dst = blk_bytes + bi * (uint64_t)BLK_STRIDE; use = in_use + bi * 256;
+                dst = blk_bytes + blocks[bi].blk_off; use = in_use + bi * 256;
             }
             uint8_t by = (uint8_t)byte_of(w, k);
             if (r.emit_mask & (1u << k)) { dst[e - b_e0] = by; use[by] = 1; e++; }
@@ -572,13 +589,16 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     S3G_LAUNCH(ctx, k_stream_block_scan, 1, 1, 0, bps, n_streams, first_block, d_sc + 17);
     S3G_LAUNCH(ctx, k_compact_blocks, (unsigned)n_streams, 64, 0, ctx->blk_prov.as<BlockInfo>(), prov_base, first_block,
                n_streams, ctx->blocks.as<BlockInfo>(), (s3g_chrom *)nullptr);
-    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 17, d_sc + 17, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // slot_cap bounds the block count: the packed offsets are computed before the count comes back
+    S3G_LAUNCH(ctx, k_block_offsets_dev, 1, 1024, 0, ctx->blocks.as<BlockInfo>(), d_sc + 17, d_sc + 18);
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 17, d_sc + 17, 16, cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     S3G_TRY(check_launch("rle cut"));
     uint64_t nb = ctx->h_scalars[17];
     out->n_blocks = nb;
+    out->rle_bytes = e_total;
     if (nb == 0) return S3G_OK;
-    S3G_TRY(ctx->blk_bytes.ensure(nb * (uint64_t)BLK_STRIDE));
+    S3G_TRY(ctx->blk_bytes.ensure(ctx->h_scalars[18] + 256));
     S3G_TRY(ctx->in_use.ensure(nb * 256));
     S3G_TRY(ctx->seq_map.ensure(nb * 256));
     S3G_CUDA(cudaMemsetAsync(ctx->in_use.p, 0, nb * 256, ctx->stream));

@@ -341,7 +341,7 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_LAUNCH(ctx, k_line_starts, (unsigned)ntiles, NL_THREADS, 0, d_bed, n, tile_cnt, line_start, skip);
     if (n_lines == 0) {
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-        out->dropped = n;
+        out->dropped = n - skip;               // the skip bytes belong to the line before the range
         return check_launch("line_starts");
     }
     S3G_TRY(ctx->start.ensure(n_lines * 8));

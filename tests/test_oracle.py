@@ -183,3 +183,38 @@ def test_archive_container(oracle):
     assert [s["lines"] for s in meta["streams"]] == [1, 2]
     # compact jansson-style text: no spaces, insertion order
     assert arc[4:nl].startswith(b'{"archive":{"type":"starch","version":{"major":3,"minor":0,"revision":0},')
+
+
+def test_metadata_text_is_what_the_reference_jansson_prints(oracle):
+    """ARCHIVE_FORMAT.md says the metadata is the text jansson 2.9 json_dumps(JSON_COMPACT) prints; here the
+    reference's own vendored jansson (oracle/_ref/libs3jansson.so, built from its tarball) prints it."""
+    import json
+    if not oracle.have_jansson():
+        pytest.skip("oracle/_ref/libs3jansson.so not built (no /root/reference here)")
+    cases = [
+        (synth.bed(2, 3000).tobytes(), 9, ""),
+        (synth.bed(5, 2000).tobytes(), 3, 'note with "quotes"\tand\\slashes/\x01\x1f and caf\u00e9'),
+        (b'we"ird\\n\x07me\t1\t5\n' + "chr\u00e9\t2\t9\tz\n".encode() + b"a/b\t1\t2\n\x7f\t3\t4\n", 1, "x"),
+        (b"", 9, "empty"),
+    ]
+    for bed, level, note in cases:
+        arc = oracle.archive(bed, level, note)
+        nl = arc.index(b"\n", 4)
+        meta = json.loads(arc[4:nl])
+        streams = [(s["chromosome"].encode(), s["offset"], s["size"], s["lines"], s["blocks"], s["transformedBytes"],
+                    s["nonUniqueBases"], s["uniqueBases"]) for s in meta["streams"]]
+        assert oracle.jansson_header(level, note, streams) == arc[4:nl]
+    # jansson refuses text that is not UTF-8; this writer passes the bytes through (documented in ARCHIVE_FORMAT.md)
+    assert oracle.jansson_header(9, "", [(b"chr\xff", 0, 1, 1, 1, 1, 1, 1)]) is None
+
+
+@pytest.mark.parametrize("cfg,lines,level", [(1, 200000, 1), (2, 200000, 2), (4, 60000, 3), (3, 400000, 1), (5, 60000, 9)])
+def test_block_parallel_oracle_equals_serial(oracle, cfg, lines, level):
+    """archive_mt / bz_compress_blockwise (blocks of one stream compressed on a thread pool and re-joined bit by
+    bit) are the checker at the BASELINE sizes; here they are pinned against the serial reference libbz2."""
+    bed = synth.bed(cfg, lines).tobytes()
+    assert oracle.archive_mt(bed, level, "mt") == oracle.archive(bed, level, "mt")
+    tf, ch, _ = oracle.transform(bed)
+    s = tf[ch[0]["tf_off"]:ch[0]["tf_off"] + ch[0]["tf_len"]]
+    comp = oracle.ref_bz_compress if oracle.have_ref() else oracle.bz_compress
+    assert oracle.bz_compress_blockwise(s, level) == comp(s, level)
