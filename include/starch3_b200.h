@@ -117,6 +117,44 @@ S3G_API void s3g_result_free(s3g_result *res);
 /* Copy the device-resident streams of the last compress call (s3g_result.d_streams) to the host. */
 S3G_API int s3g_read_streams(s3g_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
 
+/* ---- one archive from several GPUs ----
+ * The path cut into phases that a host runs on every GPU, with small exchanges in between: one process per GPU
+ * (starch3_b200/multigpu.py, torch.distributed) or one process with a context per device (s3g_multi_*, below).
+ * GPU r owns a newline-aligned byte range of the input; update_transformation_state (hpp:428-504) reads only the
+ * previous line, so the range is handed over together with the one line before it (the "halo").
+ * All pointers named d_* are device pointers on the context's device. */
+typedef struct s3g_shard_summary {
+    uint64_t n_lines;            /* lines of the range (the halo line not counted) */
+    int64_t  tail_max;           /* largest stop since the last chromosome change, INT64_MIN if none: uniqueBases of the
+                                    next range needs the largest stop of ALL earlier lines of its first chromosome */
+    uint32_t continues;          /* the first line of the range has the halo line's chromosome (hpp:331) */
+    uint32_t single_piece;       /* no chromosome change inside the range */
+    uint64_t dropped_tail_bytes; /* unterminated last line (hpp:181-190); only the last range can have one */
+} s3g_shard_summary;
+/* phase 1: tokenizer over d_range[0, n); its first halo_bytes bytes are the line before the range (0: none). */
+S3G_API int s3g_shard_tokenize(s3g_ctx *ctx, const void *d_range, uint64_t n, uint64_t halo_bytes, s3g_shard_summary *out);
+/* phase 2: transform + statistics.  carry_max = largest stop of all earlier lines of the range's first chromosome on
+ * other GPUs (INT64_MIN if the range does not continue one).  pieces = the chromosome pieces of the range in order
+ * (name_off relative to d_range; tf_off relative to *d_tf; bz_* unused); *d_tf stays valid until the next call. */
+S3G_API int s3g_shard_transform(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint64_t cap, uint64_t *n_pieces,
+                                void **d_tf, uint64_t *tf_len);
+/* phase 3: RLE1 lengths + block cut (bz/bzlib.c:225-338, :370-412) over ALL transformed bytes, stream s =
+ * d_tf_all[soff[s], soff[s+1]) (soff on the host).  Every GPU computes the same plan; nblock / stream_of describe
+ * its blocks in archive order.  d_tf_all must stay valid until s3g_shard_compress returns. */
+S3G_API int s3g_shard_plan(s3g_ctx *ctx, const void *d_tf_all, uint64_t tf_total, const uint64_t *soff, uint64_t n_streams,
+                           int block_size_100k, uint64_t *n_blocks, uint32_t *nblock, uint32_t *stream_of, uint64_t cap);
+/* phase 4: RLE1 bytes, CRC, BZ2_blockSort, MTF, Huffman of blocks [b_lo, b_hi) of the plan; per-block results out. */
+S3G_API int s3g_shard_compress(s3g_ctx *ctx, uint64_t b_lo, uint64_t b_hi, uint64_t *n_bits, uint32_t *crc, uint32_t *n_mtf);
+/* phase 5: given bit length and CRC of EVERY block, place the own blocks (and the "BZh9" header / trailer +
+ * combined CRC, bz/compress.c:607-609, :622-628, :657-666, of the streams that begin / end among them) into a byte
+ * string that covers bytes [byte_lo, byte_hi) of the concatenated streams.  Its first and last byte may be shared
+ * with the neighbouring GPUs' strings (blocks are not byte aligned): the host ORs them.  stream_off / stream_len
+ * (n_streams each, may be NULL) = the layout of the streams. */
+S3G_API int s3g_shard_assemble(s3g_ctx *ctx, const uint64_t *n_bits_all, const uint32_t *crc_all, uint64_t b_lo, uint64_t b_hi,
+                               void **d_bytes, uint64_t *byte_lo, uint64_t *byte_hi, uint64_t *stream_off, uint64_t *stream_len);
+/* CUDA-event time per stage (indices as s3g_result.stage_ms) of the phases run on ctx since s3g_shard_tokenize. */
+S3G_API int s3g_stage_times(s3g_ctx *ctx, double *stage_ms8);
+
 /* ---- stage entry points (host buffers in / out), for the parity tests ---- */
 
 /* Kernel (1): produce_line + consume_line tokenizer (hpp:158-199, :220-309).

@@ -20,6 +20,7 @@ S3G_OK, S3G_E_CUDA, S3G_E_PARAM, S3G_E_NOMEM, S3G_E_MALFORMED, S3G_E_CAPACITY, S
 C_ABI_SYMBOLS = [
     "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_sort_retries", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
+    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_stage_times",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
 ]
 
@@ -46,6 +47,11 @@ class CResult(C.Structure):
 
 
 STAGE_NAMES = ["tokenise+transform", "rle1+cut+crc", "blocksort", "mtf", "huffman", "assemble"]
+
+
+class CShardSummary(C.Structure):
+    _fields_ = [("n_lines", C.c_uint64), ("tail_max", C.c_int64), ("continues", C.c_uint32), ("single_piece", C.c_uint32),
+                ("dropped_tail_bytes", C.c_uint64)]
 
 
 class CBlockDesc(C.Structure):
@@ -88,6 +94,12 @@ def lib():
         L.s3g_compress_bed_device.argtypes = [vp, vp, u64, i32, C.c_char_p, i32, C.POINTER(CResult)]
         L.s3g_result_free.argtypes = [C.POINTER(CResult)]; L.s3g_result_free.restype = None
         L.s3g_read_streams.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.s3g_shard_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(CShardSummary)]
+        L.s3g_shard_transform.argtypes = [vp, C.c_int64, vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+        L.s3g_shard_plan.argtypes = [vp, vp, u64, vp, u64, i32, C.POINTER(u64), vp, vp, u64]
+        L.s3g_shard_compress.argtypes = [vp, u64, u64, vp, vp, vp]
+        L.s3g_shard_assemble.argtypes = [vp, vp, vp, u64, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), vp, vp]
+        L.s3g_stage_times.argtypes = [vp, vp]
         L.s3g_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(u64), vp, vp, vp, vp, vp]
         L.s3g_transform.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.s3g_rle1.argtypes = [vp, vp, u64, i32, vp, u64, C.POINTER(u64), vp, u64]
@@ -244,6 +256,56 @@ class Context:
         n = C.c_uint64(0)
         self._check(self._lib.s3g_read_streams(self._h, _p(out), size, C.byref(n)))
         return out[:n.value].tobytes()
+
+    # ---- one archive from several GPUs: the phases (include/starch3_b200.h, csrc/shard.cu) ----
+    def shard_tokenize(self, d_range, n, halo_bytes):
+        out = CShardSummary()
+        self._check(self._lib.s3g_shard_tokenize(self._h, C.c_void_p(d_range), n, halo_bytes, C.byref(out)))
+        return dict(n_lines=out.n_lines, tail_max=out.tail_max, continues=out.continues, single_piece=out.single_piece,
+                    dropped_tail_bytes=out.dropped_tail_bytes)
+
+    def shard_transform(self, carry_max, cap=4096):
+        """-> (pieces: list of dict, device pointer of the transformed bytes, their length)"""
+        while True:
+            pieces = (CChrom * cap)()
+            n = C.c_uint64(0); d_tf = C.c_void_p(); tl = C.c_uint64(0)
+            rc = self._lib.s3g_shard_transform(self._h, carry_max, pieces, cap, C.byref(n), C.byref(d_tf), C.byref(tl))
+            if rc == S3G_E_CAPACITY and cap < (1 << 24):
+                cap *= 16
+                continue
+            self._check(rc)
+            break
+        out = [{k: getattr(pieces[i], k) for k, _ in CChrom._fields_} for i in range(n.value)]
+        return out, d_tf.value or 0, tl.value
+
+    def shard_plan(self, d_tf_all, tf_total, soff, level=9):
+        """-> (nblock[], stream_of[]) of every block, in archive order"""
+        soff = np.ascontiguousarray(soff, dtype=np.uint64)
+        n_streams = len(soff) - 1
+        cap = int(tf_total // (100000 * level - 19 - 260)) + n_streams + 8
+        nblock = np.zeros(cap, dtype=np.uint32); sof = np.zeros(cap, dtype=np.uint32)
+        nb = C.c_uint64(0)
+        self._check(self._lib.s3g_shard_plan(self._h, C.c_void_p(d_tf_all), tf_total, _p(soff), n_streams, level, C.byref(nb),
+                                             _p(nblock), _p(sof), cap))
+        return nblock[:nb.value].copy(), sof[:nb.value].copy()
+
+    def shard_compress(self, b_lo, b_hi):
+        k = max(1, b_hi - b_lo)
+        n_bits = np.zeros(k, dtype=np.uint64); crc = np.zeros(k, dtype=np.uint32); n_mtf = np.zeros(k, dtype=np.uint32)
+        self._check(self._lib.s3g_shard_compress(self._h, b_lo, b_hi, _p(n_bits), _p(crc), _p(n_mtf)))
+        return n_bits[:b_hi - b_lo], crc[:b_hi - b_lo], n_mtf[:b_hi - b_lo]
+
+    def shard_assemble(self, n_bits_all, crc_all, b_lo, b_hi, n_streams):
+        nb = np.ascontiguousarray(n_bits_all, dtype=np.uint64); cr = np.ascontiguousarray(crc_all, dtype=np.uint32)
+        so = np.zeros(max(1, n_streams), dtype=np.uint64); sl = np.zeros(max(1, n_streams), dtype=np.uint64)
+        d = C.c_void_p(); lo = C.c_uint64(0); hi = C.c_uint64(0)
+        self._check(self._lib.s3g_shard_assemble(self._h, _p(nb), _p(cr), b_lo, b_hi, C.byref(d), C.byref(lo), C.byref(hi), _p(so), _p(sl)))
+        return d.value or 0, lo.value, hi.value, so[:n_streams], sl[:n_streams]
+
+    def stage_times(self):
+        t = (C.c_double * 8)()
+        self._check(self._lib.s3g_stage_times(self._h, t))
+        return {nm: t[i] for i, nm in enumerate(STAGE_NAMES)}
 
     # ---- stages ----
     def tokenize(self, bed):

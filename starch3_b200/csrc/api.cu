@@ -65,7 +65,7 @@ void stage_mark(Ctx *ctx, int stage)
 }
 
 // after the call's final synchronise: per-stage sums of the intervals between consecutive marks
-static void stage_collect(Ctx *ctx, double *stage_ms)
+void stage_collect(Ctx *ctx, double *stage_ms)
 {
     for (int i = 0; i < 8; i++) stage_ms[i] = 0;
     for (size_t k = 0; k + 1 < ctx->marks.size(); k++) {
@@ -125,52 +125,49 @@ static double host_ms()
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+// stages 3b..3d + pool for blocks [b_lo, b_hi) of ctx->blocks (their RLE1 bytes are in place), in batches
+int compress_block_range(Ctx *ctx, uint64_t b_lo, uint64_t b_hi)
+{
+    const uint64_t nb = b_hi > b_lo ? b_hi - b_lo : 0;
+    if (!nb) return S3G_OK;
+    // the batch buffers are grow-only: size them once for the batch this input needs
+    uint64_t held = 0;
+    DevBuf *batch_bufs[] = {&ctx->sa, &ctx->rk, &ctx->kv0, &ctx->kv1, &ctx->hist, &ctx->lcol, &ctx->mtf0, &ctx->mtfv16, &ctx->bits};
+    for (DevBuf *b : batch_bufs) held += b->cap;
+    // steady state: the buffers already hold this many blocks; cudaMemGetInfo is only asked when they must grow
+    // (it takes anywhere from 0.1 to 20 ms on a shared host)
+    uint64_t have = held / batch_bytes_per_block();
+    uint64_t batch = have >= nb && !getenv("S3G_BATCH") ? nb : pick_batch(nb, ctx->mem_frac);
+    if (have > batch && !getenv("S3G_BATCH")) batch = std::min<uint64_t>(nb, have);
+    for (uint64_t b0 = b_lo; b0 < b_hi; b0 += batch) {
+        uint64_t cnt = std::min<uint64_t>(batch, b_hi - b0);
+        stage_mark(ctx, 2);
+        S3G_TRY(run_bwt(ctx, b0, cnt));
+        stage_mark(ctx, 3);
+        S3G_TRY(run_mtf(ctx, b0, cnt));
+        stage_mark(ctx, 4);
+        S3G_TRY(run_huff(ctx, b0, cnt, 1, nullptr, nullptr));
+        S3G_TRY(run_pool_append(ctx, b0, cnt));
+    }
+    return S3G_OK;
+}
+
+// stages 3a..3e over `n_streams` streams laid out back to back in d_in
 static int compress_streams(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams, int level,
                             uint64_t *n_blocks_out, uint64_t *total_bytes)
 {
-    const bool timing = getenv("S3G_TIMING") != nullptr;
-    double t0 = timing ? host_ms() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
     CutResult cut;
     stage_mark(ctx, 1);
     S3G_TRY(run_rle_cut(ctx, d_in, n, d_soff, n_streams, level, &cut));
     ctx->last_rle_bytes = cut.rle_bytes;
-    if (timing) t1 = host_ms();
     uint64_t nb = cut.n_blocks;
     *n_blocks_out = nb;
     ctx->pool_words = 0;
     S3G_TRY(ctx->pool_woff.ensure((nb + 1) * 8));
-    if (nb) {
-        // the batch buffers are grow-only: size them once for the batch this input needs
-        uint64_t held = 0;
-        DevBuf *batch_bufs[] = {&ctx->sa, &ctx->rk, &ctx->kv0, &ctx->kv1, &ctx->hist, &ctx->lcol, &ctx->mtf0, &ctx->mtfv16, &ctx->bits};
-        for (DevBuf *b : batch_bufs) held += b->cap;
-        // steady state: the buffers already hold this many blocks; cudaMemGetInfo is only asked when they must grow
-        // (it takes anywhere from 0.1 to 20 ms on a shared host)
-        uint64_t have = held / batch_bytes_per_block();
-        uint64_t batch = have >= nb && !getenv("S3G_BATCH") ? nb : pick_batch(nb, ctx->mem_frac);
-        if (have > batch) batch = std::min<uint64_t>(nb, have);
-        for (uint64_t b0 = 0; b0 < nb; b0 += batch) {
-            uint64_t cnt = std::min<uint64_t>(batch, nb - b0);
-            if (timing) t2 = host_ms();
-            stage_mark(ctx, 2);
-            S3G_TRY(run_bwt(ctx, b0, cnt));
-            if (timing) t3 = host_ms();
-            stage_mark(ctx, 3);
-            S3G_TRY(run_mtf(ctx, b0, cnt));
-            stage_mark(ctx, 4);
-            S3G_TRY(run_huff(ctx, b0, cnt, 1, nullptr, nullptr));
-            S3G_TRY(run_pool_append(ctx, b0, cnt));
-            if (timing) t4 = host_ms();
-        }
-    }
+    S3G_TRY(compress_block_range(ctx, 0, nb));
     stage_mark(ctx, 5);
     S3G_TRY(run_assemble(ctx, nb, n_streams, level, total_bytes));
     stage_mark(ctx, -1);
-    if (timing) {
-        t5 = host_ms();
-        fprintf(stderr, "[s3g timing] rle+cut %.2f  batch setup %.2f  bwt %.2f  mtf+huff+pool (enqueue) %.2f  assemble %.2f  total %.2f ms (host clock)\n",
-                t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t5 - t0);
-    }
     return S3G_OK;
 }
 
@@ -628,6 +625,7 @@ void s3g_destroy(s3g_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->mark_pool) cudaEventDestroy(e);
+    shard_state_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -157,4 +157,95 @@ int run_assemble(Ctx *ctx, uint64_t n_blocks, uint64_t n_streams, int level, uin
     return check_launch("assemble");
 }
 
+// ---- a GPU's share of the blocks (multi-GPU, shard.cu) ---------------------------------------------------
+// The block table (ctx->h_blocks: n_bits, crc, chrom of EVERY block, own or not) fixes the layout of all streams; this
+// GPU places its blocks [b_lo, b_hi), plus the header of every stream whose first block and the trailer of every
+// stream whose last block it owns, into a local byte string that covers bytes [byte_lo, byte_hi) of the global
+// streams buffer.  The two end bytes may be shared with the neighbouring shares (blocks are not byte aligned): the
+// host ORs them.
+__global__ void k_concat_range(const BlockInfo *blocks, const uint32_t *pool, const uint64_t *woff, const uint64_t *pos, uint32_t *dst)
+{
+    uint64_t b = blockIdx.x >> 5, part = blockIdx.x & 31;            // relative to the first own block
+    uint64_t nw = (blocks[b].n_bits + 31) >> 5;
+    const uint32_t *src = pool + woff[b];
+    uint64_t base = pos[b];
+    for (uint64_t i = part * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)32 * blockDim.x)
+        or_bits(dst, base + i * 32, src[i]);
+}
+__global__ void k_patch_words(const uint64_t *patch, uint64_t n, uint32_t *dst)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) or_bits(dst, patch[2 * i], (uint32_t)patch[2 * i + 1]);
+}
+
+int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, uint64_t b_hi, uint64_t *byte_lo, uint64_t *byte_hi,
+                       std::vector<StreamMeta> *metas)
+{
+    const std::vector<BlockInfo> &hb = ctx->h_blocks;
+    const uint64_t nb = hb.size();
+    metas->assign(n_streams, StreamMeta());
+    std::vector<uint64_t> gpos(nb, 0), first(n_streams + 1, nb);     // global bit position of every block; first block of a stream
+    {
+        uint64_t b = 0, byte_off = 0;
+        for (uint64_t s = 0; s < n_streams; s++) {
+            first[s] = b;
+            uint64_t bits = 32; uint32_t comb = 0;
+            for (; b < nb && hb[b].chrom == s; b++) {
+                gpos[b] = byte_off * 8 + bits;
+                bits += hb[b].n_bits;
+                comb = ((comb << 1) | (comb >> 31)) ^ hb[b].crc;                 // bz/compress.c:607-608
+            }
+            bits += 48 + 32;
+            StreamMeta &m = (*metas)[s];
+            m.byte_off = byte_off; m.byte_len = (bits + 7) >> 3; m.n_blocks = b - first[s]; m.combined_crc = comb; m.pad = 0;
+            byte_off += m.byte_len;
+        }
+        first[n_streams] = nb;
+        if (b != nb) { set_error("block table and stream table disagree"); return S3G_E_PARAM; }
+    }
+    *byte_lo = *byte_hi = 0;
+    if (b_lo >= b_hi) return S3G_OK;
+    // bit range of the share
+    const uint64_t s_lo = hb[b_lo].chrom, s_hi = hb[b_hi - 1].chrom;
+    const bool own_head = first[s_lo] == b_lo, own_tail = first[s_hi + 1] == b_hi;
+    const uint64_t bit_lo = own_head ? (*metas)[s_lo].byte_off * 8 : gpos[b_lo];
+    const uint64_t bit_hi = own_tail ? ((*metas)[s_hi].byte_off + (*metas)[s_hi].byte_len) * 8 : gpos[b_hi - 1] + hb[b_hi - 1].n_bits;
+    *byte_lo = bit_lo >> 3; *byte_hi = (bit_hi + 7) >> 3;
+    const uint64_t base_bit = *byte_lo * 8;
+    const uint64_t words = (*byte_hi - *byte_lo + 3) / 4 + 4;
+    S3G_TRY(ctx->streams.ensure(words * 4));
+    uint32_t *dst = ctx->streams.as<uint32_t>();
+    S3G_CUDA(cudaMemsetAsync(dst, 0, words * 4, ctx->stream));
+    // positions of the own blocks, and the header / trailer words of the streams that begin / end in the share
+    std::vector<uint64_t> up;
+    up.reserve((b_hi - b_lo) + 8 * (s_hi - s_lo + 1));
+    for (uint64_t b = b_lo; b < b_hi; b++) up.push_back(gpos[b] - base_bit);
+    const uint64_t patch_at = up.size();
+    uint64_t n_patch = 0;
+    for (uint64_t s = s_lo; s <= s_hi; s++) {
+        const StreamMeta &m = (*metas)[s];
+        if (first[s] >= b_lo && first[s] < b_hi) {
+            up.push_back(m.byte_off * 8 - base_bit); up.push_back(0x425a6800u | (uint32_t)('0' + level)); n_patch++;   // bz/compress.c:622-628
+        }
+        const uint64_t last = first[s + 1] - 1;
+        if (last >= b_lo && last < b_hi) {
+            const uint64_t end = gpos[last] + hb[last].n_bits - base_bit;                                                 // :657-666
+            up.push_back(end); up.push_back(0x17724538u);
+            up.push_back(end + 32); up.push_back(0x50900000u | (m.combined_crc >> 16));
+            up.push_back(end + 64); up.push_back((uint64_t)(uint32_t)(m.combined_crc << 16));
+            n_patch += 3;
+        }
+    }
+    S3G_TRY(ctx->io_d.ensure(up.size() * 8 + 64));
+    S3G_CUDA(cudaMemcpyAsync(ctx->io_d.p, up.data(), up.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));                   // `up` is pageable and dies with this frame
+    if ((b_hi - b_lo) > (1ull << 26)) { set_error("too many bzip2 blocks in one call"); return S3G_E_LIMIT; }
+    S3G_LAUNCH(ctx, k_concat_range, (unsigned)((b_hi - b_lo) * 32), 256, 0, ctx->blocks.as<BlockInfo>() + b_lo, ctx->pool.as<uint32_t>(),
+               ctx->pool_woff.as<uint64_t>() + b_lo, ctx->io_d.as<uint64_t>(), dst);
+    if (n_patch)
+        S3G_LAUNCH(ctx, k_patch_words, (unsigned)((n_patch + 127) / 128), 128, 0, ctx->io_d.as<uint64_t>() + patch_at, n_patch, dst);
+    S3G_LAUNCH(ctx, k_bswap, 592, 256, 0, dst, words);
+    return check_launch("assemble range");
+}
+
 }  // namespace s3g

@@ -119,6 +119,9 @@ struct Ctx {
     std::vector<cudaEvent_t> mark_pool;
     std::vector<std::pair<int, cudaEvent_t>> marks;
     uint64_t last_rle_bytes = 0;
+    void *shard = nullptr;                 // state between the s3g_shard_* phases (shard.cu)
+    // the plan run_rle_plan left (input of run_rle_fill)
+    const uint8_t *rle_in = nullptr; uint64_t rle_n = 0; const uint64_t *rle_soff = nullptr; uint64_t rle_streams = 0, rle_blocks = 0;
     uint8_t *h_archive = nullptr;          // pinned; holds the archive of the last compress call
     size_t h_archive_cap = 0;
     // pipelined host entry (s3g_compress_bed on large inputs): upload stream, one event per input range,
@@ -154,6 +157,8 @@ struct Ctx {
 int check_launch(const char *what);
 // stage mark: the time until the next mark is charged to `stage` (s3g_result.stage_ms)
 void stage_mark(Ctx *ctx, int stage);
+void stage_collect(Ctx *ctx, double *stage_ms);
+void shard_state_free(Ctx *ctx);
 int prof_begin(Ctx *ctx, const char *name);
 void prof_end(Ctx *ctx, int idx);
 
@@ -235,6 +240,10 @@ struct TfResult {
 // kernels (1)+(2); leaves ctx->tf (bytes), ctx->chroms (s3g_chrom[n_chroms]) and the per-line arrays on device
 // `skip` (< 16): leading bytes of d_bed that belong to the line before the range (see k_count_newlines)
 int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip = 0);
+// the same in pieces, for ranges handed between GPUs (shard.cu): `halo` = line 0 is the last line before the range
+int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out);
+int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_max, uint64_t *last_flag, uint32_t *continues);
+int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max);
 
 struct CutResult {
     uint64_t n_blocks = 0;
@@ -244,6 +253,10 @@ struct CutResult {
 // Leaves ctx->blocks (BlockInfo[n_blocks]), ctx->blk_bytes (block b at BlockInfo.blk_off), ctx->in_use (256 B per block).
 int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams,
                 int level, CutResult *out);
+// the same in two steps: the plan of ALL blocks, then the bytes / CRC / maps of a range of them (a GPU's share)
+int run_rle_plan(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams,
+                 int level, CutResult *out);
+int run_rle_fill(Ctx *ctx, uint64_t b_lo, uint64_t b_hi);
 
 // kernels (3b..3d) on blocks [b0, b0+nb) of ctx->blocks
 int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb);                 // -> ctx->sa, ctx->lcol, BlockInfo.orig_ptr / tie
@@ -256,6 +269,11 @@ int run_pool_append(Ctx *ctx, uint64_t b0, uint64_t nb);
 // fills ctx->stream_meta (StreamMeta[n_streams])
 struct StreamMeta { uint64_t byte_off, byte_len, n_blocks; uint32_t combined_crc, pad; };
 int run_assemble(Ctx *ctx, uint64_t n_blocks, uint64_t n_streams, int level, uint64_t *total_bytes);
+// the same for a GPU's share [b_lo, b_hi) of the blocks; needs n_bits / crc / chrom of EVERY block in ctx->h_blocks.
+// Leaves bytes [byte_lo, byte_hi) of the global streams buffer in ctx->streams.
+int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, uint64_t b_hi, uint64_t *byte_lo, uint64_t *byte_hi,
+                       std::vector<StreamMeta> *metas);
+int compress_block_range(Ctx *ctx, uint64_t b_lo, uint64_t b_hi);
 
 }  // namespace s3g
 

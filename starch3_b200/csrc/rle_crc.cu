@@ -353,16 +353,16 @@ __global__ void k_compact_blocks(const BlockInfo *prov, const uint64_t *prov_bas
 }
 
 // packed layout of the block bytes: blk_off = exclusive sum of the slot sizes (one CTA, chunks of 1024 blocks)
-__global__ void __launch_bounds__(1024) k_block_offsets_dev(BlockInfo *blocks, const uint64_t *nb_p, uint64_t *total)
+// Only blocks [b_lo, b_hi) get a slot (a GPU that compresses a share of the blocks holds only their bytes).
+__global__ void __launch_bounds__(1024) k_block_offsets_dev(BlockInfo *blocks, uint64_t b_lo, uint64_t b_hi, uint64_t *total)
 {
     __shared__ uint64_t sm[33];
-    const uint64_t nb = *nb_p;
     uint64_t carry = 0;
-    for (uint64_t b0 = 0; b0 < nb; b0 += 1024) {
+    for (uint64_t b0 = b_lo; b0 < b_hi; b0 += 1024) {
         uint64_t b = b0 + threadIdx.x;
-        uint64_t w = b < nb ? blk_slot_bytes(blocks[b].nblock) : 0, tot;
+        uint64_t w = b < b_hi ? blk_slot_bytes(blocks[b].nblock) : 0, tot;
         uint64_t ex = block_excl_sum<uint64_t>(w, sm, &tot);
-        if (b < nb) blocks[b].blk_off = carry + ex;
+        if (b < b_hi) blocks[b].blk_off = carry + ex;
         carry += tot;
         __syncthreads();
     }
@@ -378,7 +378,7 @@ constexpr int RW_BUF = RTILE + RTILE / 4 + 32;        // a tile emits at most 5/
 
 __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n, StreamMap sm, const uint64_t *run_carry,
                                                    const uint64_t *e_base, const BlockInfo *blocks, uint64_t n_blocks,
-                                                   uint8_t *blk_bytes, uint8_t *in_use)
+                                                   uint8_t *blk_bytes, uint8_t *in_use, uint64_t tile0, uint64_t b_lo, uint64_t b_hi)
 {
     __shared__ uint64_t s_max[33];
     __shared__ uint32_t s_sum[33];
@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
     __shared__ int s_fast;
     __shared__ __align__(16) uint8_t s_buf[RW_BUF];
     __shared__ uint8_t s_used[256];
-    const uint64_t tile_begin = (uint64_t)blockIdx.x * RTILE;
+    const uint64_t tile = tile0 + blockIdx.x;            // the grid covers the tiles of the input range of blocks [b_lo, b_hi)
+    const uint64_t tile_begin = tile * RTILE;
     if (threadIdx.x == 0) {
         find_tile_starts(sm, tile_begin, &ts);
         // block containing the tile's first byte: last block with in_start <= tile_begin
@@ -406,12 +407,13 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
     load_win(in, n, tile_begin + (uint64_t)threadIdx.x * RB, w);
     uint32_t sm_mask = run_start_mask(w, sm, ts, n);
     RleLocal r;
-    rle_local(w, sm_mask, run_carry[blockIdx.x], s_max, r);
+    rle_local(w, sm_mask, run_carry[tile], s_max, r);
     uint32_t tot;
     uint32_t ex = block_excl_sum<uint32_t>(r.total, s_sum, &tot);
     if (s_fast) {
         const uint64_t bi = s_bi;
-        const uint64_t d0 = e_base[blockIdx.x] - blocks[bi].e_base;     // offset of the tile's output inside the block slot
+        if (bi < b_lo || bi >= b_hi) return;               // another GPU's block
+        const uint64_t d0 = e_base[tile] - blocks[bi].e_base;     // offset of the tile's output inside the block slot
         const uint32_t ph = (uint32_t)d0 & 15u;
         if (w.cnt) {
             uint32_t o = ph + ex;
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
         return;
     }
     if (w.cnt == 0) return;
-    uint64_t e = e_base[blockIdx.x] + ex;
+    uint64_t e = e_base[tile] + ex;
     // block containing my first byte: last block with in_start <= pos0
     uint64_t lo = 0, hi = n_blocks - 1;
     while (lo < hi) {
@@ -456,8 +458,9 @@ __global__ void __launch_bounds__(RT) k_rle_write(const uint8_t *in, uint64_t n,
                 dst = blk_bytes + blocks[bi].blk_off; use = in_use + bi * 256;
             }
             uint8_t by = (uint8_t)byte_of(w, k);
-            if (r.emit_mask & (1u << k)) { dst[e - b_e0] = by; use[by] = 1; e++; }
-            if (r.cnt_mask & (1u << k)) { uint8_t cv = (uint8_t)((r.cnt_val[k >> 2] >> (8 * (k & 3))) & 0xffu); dst[e - b_e0] = cv; use[cv] = 1; e++; }
+            const bool mine = bi >= b_lo && bi < b_hi;
+            if (r.emit_mask & (1u << k)) { if (mine) { dst[e - b_e0] = by; use[by] = 1; } e++; }
+            if (r.cnt_mask & (1u << k)) { uint8_t cv = (uint8_t)((r.cnt_val[k >> 2] >> (8 * (k & 3))) & 0xffu); if (mine) { dst[e - b_e0] = cv; use[cv] = 1; } e++; }
         }
     }
 }
@@ -549,8 +552,10 @@ __global__ void k_block_maps(const uint8_t *in_use, BlockInfo *blocks, uint8_t *
     if (threadIdx.x == 0) blocks[b].n_in_use = tot;
 }
 
-int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams, int level,
-                CutResult *out)
+// block plan of the streams in d_in: cut points, sizes (ctx->blocks, mirrored in ctx->h_blocks).  d_in and d_soff must
+// stay valid until the last run_rle_fill of the plan.
+int run_rle_plan(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams, int level,
+                 CutResult *out)
 {
     *out = CutResult();
     uint32_t nmax = 100000u * (uint32_t)level - 19;     // bz/bzlib.c:194
@@ -589,31 +594,61 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
     S3G_LAUNCH(ctx, k_stream_block_scan, 1, 1, 0, bps, n_streams, first_block, d_sc + 17);
     S3G_LAUNCH(ctx, k_compact_blocks, (unsigned)n_streams, 64, 0, ctx->blk_prov.as<BlockInfo>(), prov_base, first_block,
                n_streams, ctx->blocks.as<BlockInfo>(), (s3g_chrom *)nullptr);
-    // slot_cap bounds the block count: the packed offsets are computed before the count comes back
-    S3G_LAUNCH(ctx, k_block_offsets_dev, 1, 1024, 0, ctx->blocks.as<BlockInfo>(), d_sc + 17, d_sc + 18);
-    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 17, d_sc + 17, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 17, d_sc + 17, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // host mirror of the block table (sizes drive batching and the byte accounting of the later stages)
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     S3G_TRY(check_launch("rle cut"));
     uint64_t nb = ctx->h_scalars[17];
     out->n_blocks = nb;
     out->rle_bytes = e_total;
+    ctx->rle_in = d_in; ctx->rle_n = n; ctx->rle_soff = d_soff; ctx->rle_streams = n_streams; ctx->rle_blocks = nb;
+    ctx->h_blocks.resize(nb);
     if (nb == 0) return S3G_OK;
-    S3G_TRY(ctx->blk_bytes.ensure(ctx->h_scalars[18] + 256));
     S3G_TRY(ctx->in_use.ensure(nb * 256));
     S3G_TRY(ctx->seq_map.ensure(nb * 256));
-    S3G_CUDA(cudaMemsetAsync(ctx->in_use.p, 0, nb * 256, ctx->stream));
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_blocks.data(), ctx->blocks.p, nb * sizeof(BlockInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    return S3G_OK;
+}
+
+// RLE1 bytes, CRC, bytes in use and unseqToSeq maps of blocks [b_lo, b_hi) of the plan left by run_rle_plan
+int run_rle_fill(Ctx *ctx, uint64_t b_lo, uint64_t b_hi)
+{
+    const uint64_t nb = ctx->rle_blocks;
+    if (b_lo >= b_hi || b_hi > nb) return S3G_OK;
+    const uint8_t *d_in = ctx->rle_in;
+    const uint64_t n = ctx->rle_n;
+    StreamMap sm{ctx->rle_soff, ctx->rle_streams};
+    uint64_t *d_sc = ctx->scalars.as<uint64_t>();
+    uint64_t *run_carry = ctx->rle_carry.as<uint64_t>(), *e_base = ctx->rle_ebase.as<uint64_t>();
     BlockInfo *blocks = ctx->blocks.as<BlockInfo>();
-    S3G_BYTES(ctx, n + e_total);
-    S3G_LAUNCH(ctx, k_rle_write, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base, blocks, nb,
-               ctx->blk_bytes.as<uint8_t>(), ctx->in_use.as<uint8_t>());
-    S3G_BYTES(ctx, n);
-    S3G_LAUNCH(ctx, k_block_crc, (unsigned)nb, CRC_T, 0, d_in, blocks);
-    S3G_LAUNCH(ctx, k_block_maps, (unsigned)nb, 256, 0, ctx->in_use.as<uint8_t>(), blocks, ctx->seq_map.as<uint8_t>());
-    // host mirror of the block table (sizes drive batching and the byte accounting of the later stages)
-    ctx->h_blocks.resize(nb);
-    S3G_CUDA(cudaMemcpyAsync(ctx->h_blocks.data(), blocks, nb * sizeof(BlockInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t packed = 0;
+    for (uint64_t b = b_lo; b < b_hi; b++) { ctx->h_blocks[b].blk_off = packed; packed += blk_slot_bytes(ctx->h_blocks[b].nblock); }
+    S3G_TRY(ctx->blk_bytes.ensure(packed + 256));
+    S3G_LAUNCH(ctx, k_block_offsets_dev, 1, 1024, 0, blocks, b_lo, b_hi, d_sc + 18);
+    S3G_CUDA(cudaMemsetAsync(ctx->in_use.as<uint8_t>() + b_lo * 256, 0, (b_hi - b_lo) * 256, ctx->stream));
+    const uint64_t in_lo = ctx->h_blocks[b_lo].in_start, in_hi = ctx->h_blocks[b_hi - 1].in_end;
+    const uint64_t tile0 = in_lo / RTILE, tile1 = (in_hi + RTILE - 1) / RTILE;
+    double e_own = 0;
+    for (uint64_t b = b_lo; b < b_hi; b++) e_own += ctx->h_blocks[b].nblock;
+    S3G_BYTES(ctx, (double)(in_hi - in_lo) + e_own);
+    if (tile1 > tile0)
+        S3G_LAUNCH(ctx, k_rle_write, (unsigned)(tile1 - tile0), RT, 0, d_in, n, sm, run_carry, e_base, blocks, nb,
+                   ctx->blk_bytes.as<uint8_t>(), ctx->in_use.as<uint8_t>(), tile0, b_lo, b_hi);
+    S3G_BYTES(ctx, (double)(in_hi - in_lo));
+    S3G_LAUNCH(ctx, k_block_crc, (unsigned)(b_hi - b_lo), CRC_T, 0, d_in, blocks + b_lo);
+    S3G_LAUNCH(ctx, k_block_maps, (unsigned)(b_hi - b_lo), 256, 0, ctx->in_use.as<uint8_t>() + b_lo * 256, blocks + b_lo, ctx->seq_map.as<uint8_t>() + b_lo * 256);
+    // the mirror learns CRC and alphabet size (the later stages size their launches from it)
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_blocks.data() + b_lo, blocks + b_lo, (b_hi - b_lo) * sizeof(BlockInfo), cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     return check_launch("rle write");
+}
+
+int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams, int level,
+                CutResult *out)
+{
+    S3G_TRY(run_rle_plan(ctx, d_in, n, d_soff, n_streams, level, out));
+    return run_rle_fill(ctx, 0, out->n_blocks);
 }
 
 }  // namespace s3g

@@ -166,6 +166,8 @@ struct LineView {
     const int64_t *start, *stop;
     const uint32_t *rem_off;
     const uint8_t *flags;
+    uint32_t halo;      // 1: line 0 is the last line BEFORE the range (multi-GPU ranges, shard.cu): it hands its stop,
+                        // length and chromosome to line 1 and is itself neither written nor counted
     __device__ __forceinline__ void prev(uint64_t i, int64_t *p_stop, int64_t *p_len) const
     {
         if (flags[i] & 1) { *p_stop = 0; *p_len = 0; }                         // hpp:523-532
@@ -173,6 +175,7 @@ struct LineView {
     }
     __device__ __forceinline__ uint32_t out_len(uint64_t i) const
     {
+        if (halo && i == 0) return 0;
         int64_t ps, pl; prev(i, &ps, &pl);
         int64_t s = start[i], t = stop[i];
         int64_t len = (int64_t)((uint64_t)t - (uint64_t)s), d = (int64_t)((uint64_t)s - (uint64_t)ps);
@@ -199,15 +202,23 @@ struct UniqScan {
     const int64_t *start, *stop;
     const uint8_t *flags;
     int64_t *uniq;
+    uint32_t halo;          // see LineView
+    int64_t carry_max;      // halo: the largest stop among ALL earlier lines of the halo line's chromosome (they live on other GPUs)
     __host__ __device__ static T identity() { T t; t.v = INT64_MIN; t.seg = 0; t.pad = 0; return t; }
     __host__ __device__ static T op(T a, T b)
     {
         if (b.seg) return b;
         T r; r.v = a.v > b.v ? a.v : b.v; r.seg = a.seg; r.pad = 0; return r;
     }
-    __device__ T load(uint64_t i) const { T t; t.v = stop[i]; t.seg = flags[i] & 1; t.pad = 0; return t; }
+    __device__ T load(uint64_t i) const
+    {
+        T t; t.v = stop[i]; t.seg = flags[i] & 1; t.pad = 0;
+        if (halo && i == 0) t.v = carry_max;
+        return t;
+    }
     __device__ void store(uint64_t i, T excl, T) const
     {
+        if (halo && i == 0) { uniq[0] = 0; return; }
         int64_t rm = (flags[i] & 1) ? INT64_MIN : excl.v;
         int64_t s = start[i], t = stop[i];
         int64_t lo = s > rm ? s : rm;
@@ -224,11 +235,14 @@ struct StatScan {
     const uint8_t *flags;
     uint64_t *chrom_first;     // [n_chroms]
     Stat3 *chrom_pref;         // [n_chroms]
+    uint32_t halo;             // see LineView: the halo line opens piece 0 and contributes nothing
     __host__ __device__ static T identity() { T t; t.len_sum = 0; t.uniq_sum = 0; t.chroms = 0; return t; }
     __host__ __device__ static T op(T a, T b) { T r; r.len_sum = a.len_sum + b.len_sum; r.uniq_sum = a.uniq_sum + b.uniq_sum; r.chroms = a.chroms + b.chroms; return r; }
     __device__ T load(uint64_t i) const
     {
-        T t; t.len_sum = (int64_t)((uint64_t)stop[i] - (uint64_t)start[i]); t.uniq_sum = uniq[i]; t.chroms = flags[i] & 1; return t;
+        T t; t.len_sum = (int64_t)((uint64_t)stop[i] - (uint64_t)start[i]); t.uniq_sum = uniq[i]; t.chroms = flags[i] & 1;
+        if (halo && i == 0) { t.len_sum = 0; t.uniq_sum = 0; }
+        return t;
     }
     __device__ void store(uint64_t i, T excl, T) const
     {
@@ -238,7 +252,7 @@ struct StatScan {
 
 __global__ void k_chrom_table(const uint8_t *bed, const uint64_t *line_start, const uint64_t *line_tf_off,
                               const uint64_t *chrom_first, const Stat3 *chrom_pref, const Stat3 *stat_total,
-                              uint64_t n_chroms, uint64_t n_lines, uint64_t tf_total, s3g_chrom *out)
+                              uint64_t n_chroms, uint64_t n_lines, uint64_t tf_total, s3g_chrom *out, uint32_t halo)
 {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chroms) return;
@@ -254,7 +268,7 @@ __global__ void k_chrom_table(const uint8_t *bed, const uint64_t *line_start, co
     r.n_blocks = 0;
     r.tf_off = line_tf_off[first];
     r.tf_len = (next < n_lines ? line_tf_off[next] : tf_total) - r.tf_off;
-    r.line_count = (int64_t)(next - first);
+    r.line_count = (int64_t)(next - first) - (halo && c == 0 ? 1 : 0);
     r.bases_nonunique = b.len_sum - a.len_sum;
     r.bases_unique = b.uniq_sum - a.uniq_sum;
     r.bz_off = 0; r.bz_len = 0;
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(WT_LINES) k_write_tf(const uint8_t *__restrict
     const bool staged = o_end - o_begin <= WT_BUF;
     const uint32_t ph = (uint32_t)o_begin & 15u;
     uint64_t i = i0 + threadIdx.x;
-    if (i < n_lines) {
+    if (i < n_lines && !(lv.halo && i == 0)) {
         int64_t ps, pl; lv.prev(i, &ps, &pl);
         int64_t s = lv.start[i], t = lv.stop[i];
         int64_t len = (int64_t)((uint64_t)t - (uint64_t)s), d = (int64_t)((uint64_t)s - (uint64_t)ps);
@@ -317,7 +331,27 @@ __global__ void __launch_bounds__(WT_LINES) k_write_tf(const uint8_t *__restrict
     }
 }
 
-int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip)
+// ---- tail summary of a range (multi-GPU ranges: what the next range must know) ---------------------------
+__global__ void k_last_flag(const uint8_t *flags, uint64_t n_lines, unsigned long long *last)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool f = i < n_lines && (flags[i] & 1);
+    // the largest flagged index of the warp, then one atomic per warp that has one
+    unsigned m = __ballot_sync(0xffffffffu, f);
+    if (m && (threadIdx.x & 31) == 31 - __clz(m)) atomicMax(last, (unsigned long long)i);
+}
+__global__ void k_tail_max(const int64_t *stop, uint64_t n_lines, const unsigned long long *last, uint32_t halo, long long *tail_max)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = *last;
+    if (halo && lo == 0) lo = 1;                   // the halo line itself is covered by the carry it brings
+    long long v = (i < n_lines && i >= lo) ? (long long)stop[i] : (long long)INT64_MIN;
+    for (int d = 16; d; d >>= 1) { long long o = __shfl_xor_sync(0xffffffffu, v, d); v = o > v ? o : v; }
+    if ((threadIdx.x & 31) == 0 && v != (long long)INT64_MIN) atomicMax(tail_max, v);
+}
+
+// kernels (1): line framing + tokenizer over d_bed[0, n).  Leaves the per-line arrays in ctx.
+int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out)
 {
     *out = TfResult();
     uint64_t ntiles = (n + NL_TILE - 1) / NL_TILE;
@@ -348,22 +382,49 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_TRY(ctx->stop.ensure(n_lines * 8));
     S3G_TRY(ctx->rem_off.ensure(n_lines * 4));
     S3G_TRY(ctx->flags.ensure(n_lines));
+    unsigned lgrid = (unsigned)((n_lines + 255) / 256);
+    S3G_BYTES(ctx, n + 29 * n_lines);
+    S3G_LAUNCH(ctx, k_parse_lines, lgrid, 256, 0, d_bed, line_start, n_lines, ctx->start.as<int64_t>(), ctx->stop.as<int64_t>(),
+               ctx->rem_off.as<uint32_t>(), ctx->flags.as<uint8_t>(), (unsigned long long *)(d_sc + 1));
+    // last line start tells how many unterminated tail bytes are dropped (hpp:181-190)
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 40, line_start + n_lines, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 1, d_sc + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return S3G_OK;
+}
+
+// summary of the tokenised range for the hand-over between GPUs (needs run_tokenize's arrays); synchronises
+int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_max, uint64_t *last_flag, uint32_t *continues)
+{
+    uint64_t *d_sc = ctx->scalars.as<uint64_t>();
+    *tail_max = INT64_MIN; *last_flag = 0; *continues = 0;
+    if (n_lines == 0) { S3G_CUDA(cudaStreamSynchronize(ctx->stream)); return S3G_OK; }
+    long long neg = (long long)INT64_MIN;
+    S3G_CUDA(cudaMemsetAsync(d_sc + 44, 0, 8, ctx->stream));
+    S3G_CUDA(cudaMemcpyAsync(d_sc + 45, &neg, 8, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned g = (unsigned)((n_lines + 255) / 256);
+    S3G_LAUNCH(ctx, k_last_flag, g, 256, 0, ctx->flags.as<uint8_t>(), n_lines, (unsigned long long *)(d_sc + 44));
+    S3G_LAUNCH(ctx, k_tail_max, g, 256, 0, ctx->stop.as<int64_t>(), n_lines, (const unsigned long long *)(d_sc + 44), halo, (long long *)(d_sc + 45));
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 44, d_sc + 44, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    uint8_t *hf = reinterpret_cast<uint8_t *>(ctx->h_scalars + 46);
+    hf[0] = 1;
+    if (halo && n_lines > 1) S3G_CUDA(cudaMemcpyAsync(hf, ctx->flags.as<uint8_t>() + 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    *last_flag = ctx->h_scalars[44];
+    *tail_max = (int64_t)ctx->h_scalars[45];
+    *continues = (halo && n_lines > 1 && !(hf[0] & 1)) ? 1u : 0u;
+    return check_launch("range summary");
+}
+
+// kernels (2) over the lines left by run_tokenize
+int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max)
+{
+    uint64_t *d_sc = ctx->scalars.as<uint64_t>();
+    const uint64_t n_lines = out->n_lines;
+    uint64_t *line_start = ctx->line_start.as<uint64_t>();
     int64_t *start = ctx->start.as<int64_t>(), *stop = ctx->stop.as<int64_t>();
     uint32_t *rem_off = ctx->rem_off.as<uint32_t>();
     uint8_t *flags = ctx->flags.as<uint8_t>();
     unsigned lgrid = (unsigned)((n_lines + 255) / 256);
-    S3G_BYTES(ctx, n + 29 * n_lines);
-    S3G_LAUNCH(ctx, k_parse_lines, lgrid, 256, 0, d_bed, line_start, n_lines, start, stop, rem_off, flags,
-               (unsigned long long *)(d_sc + 1));
-    // last line start tells how many unterminated tail bytes are dropped (hpp:181-190)
-    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 40, line_start + n_lines, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (tokenize_only) {
-        S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 1, d_sc + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-        out->dropped = n - ctx->h_scalars[40];
-        if (ctx->h_scalars[1]) { set_error("%llu malformed BED line(s): fewer than three fields", (unsigned long long)ctx->h_scalars[1]); return S3G_E_MALFORMED; }
-        return check_launch("tokenize");
-    }
     // ---- sizes: output offsets, unique-base contributions, chromosome count ----
     uint64_t stiles = (n_lines + SCAN_TILE - 1) / SCAN_TILE + 1;
     S3G_TRY(ctx->line_tf_off.ensure(n_lines * 8));
@@ -371,12 +432,12 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_TRY(ctx->scan_a.ensure(stiles * sizeof(uint64_t)));
     S3G_TRY(ctx->scan_b.ensure(stiles * sizeof(SegMax)));
     S3G_TRY(ctx->scan_c.ensure(stiles * sizeof(Stat3)));
-    LineView lv{line_start, start, stop, rem_off, flags};
+    LineView lv{line_start, start, stop, rem_off, flags, halo};
     OutLenScan f1; f1.lv = lv; f1.line_tf_off = ctx->line_tf_off.as<uint64_t>();
     S3G_TRY(device_scan(ctx, f1, n_lines, ctx->scan_a.as<uint64_t>(), d_sc + 3));
-    UniqScan f2; f2.start = start; f2.stop = stop; f2.flags = flags; f2.uniq = ctx->stat_a.as<int64_t>();
+    UniqScan f2; f2.start = start; f2.stop = stop; f2.flags = flags; f2.uniq = ctx->stat_a.as<int64_t>(); f2.halo = halo; f2.carry_max = carry_max;
     S3G_TRY(device_scan(ctx, f2, n_lines, ctx->scan_b.as<SegMax>(), (SegMax *)nullptr));
-    StatScan f3; f3.start = start; f3.stop = stop; f3.uniq = ctx->stat_a.as<int64_t>(); f3.flags = flags;
+    StatScan f3; f3.start = start; f3.stop = stop; f3.uniq = ctx->stat_a.as<int64_t>(); f3.flags = flags; f3.halo = halo;
     f3.chrom_first = nullptr; f3.chrom_pref = nullptr;
     Stat3 *d_stat_total = reinterpret_cast<Stat3 *>(d_sc + 8);
     unsigned sgrid = (unsigned)(stiles - 1 ? stiles - 1 : 1);
@@ -398,10 +459,23 @@ int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, boo
     S3G_LAUNCH(ctx, k_scan_apply<StatScan>, sgrid, SCAN_THREADS, 0, f3, n_lines, ctx->scan_c.as<Stat3>());
     S3G_LAUNCH(ctx, k_chrom_table, (unsigned)((out->n_chroms + 127) / 128), 128, 0, d_bed, line_start,
                ctx->line_tf_off.as<uint64_t>(), ctx->chrom_first.as<uint64_t>(), ctx->stat_b.as<Stat3>(), d_stat_total,
-               out->n_chroms, n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>());
+               out->n_chroms, n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>(), halo);
     S3G_BYTES(ctx, n + out->tf_len + 37 * n_lines);
     S3G_LAUNCH(ctx, k_write_tf, lgrid, WT_LINES, 0, d_bed, lv, ctx->line_tf_off.as<uint64_t>(), n_lines, out->tf_len, ctx->tf.as<uint8_t>());
     return check_launch("transform write");
+}
+
+int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip)
+{
+    S3G_TRY(run_tokenize(ctx, d_bed, n, skip, out));
+    if (out->n_lines == 0) return S3G_OK;
+    if (tokenize_only) {
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        out->dropped = n - ctx->h_scalars[40];
+        if (ctx->h_scalars[1]) { set_error("%llu malformed BED line(s): fewer than three fields", (unsigned long long)ctx->h_scalars[1]); return S3G_E_MALFORMED; }
+        return check_launch("tokenize");
+    }
+    return run_transform_rest(ctx, d_bed, n, out, 0, INT64_MIN);
 }
 
 }  // namespace s3g

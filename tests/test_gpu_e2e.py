@@ -136,14 +136,6 @@ def test_cli_client_matches_library(ctx, tmp_path):
     assert gz.returncode != 0 and b"unsupported" in gz.stderr          # starch3api.hpp:777-779
 
 
-def test_sharded_single_rank_gpu(ctx, oracle):
-    """The multi-GPU host logic (starch3_b200/shard.py) with the real per-rank compressor."""
-    from starch3_b200 import shard
-    bed = synth.bed(5, 30000).tobytes() + b"chr1\t5\t9\n"
-    arc = shard.compress_sharded(bed, shard.gpu_compress_fn(ctx), 9, "s")
-    assert arc == ctx.compress_bed(bed, 9, note="s").archive == oracle.archive(bed, 9, "s")
-
-
 @pytest.mark.parametrize("cfg,lines,parts", [(2, 60000, 2), (2, 60000, 4), (2, 60000, 7), (5, 50000, 3), (1, 40000, 4), (2, 30, 5), (4, 20000, 2)])
 def test_pipelined_host_entry_matches_one_shot(ctx, oracle, cfg, lines, parts, monkeypatch):
     """s3g_compress_bed cuts large inputs into ranges that are uploaded and compressed in a pipeline
