@@ -194,8 +194,8 @@ def run_b200(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        from starch3_b200 import multigpu
-        return multigpu.bench(args, rank, world, local_rank, METRIC, UNIT, WORKLOADS, measured_peak_hbm, ClockSampler, cpu_compress)
+        import bench_multigpu
+        return bench_multigpu.bench(args, rank, world, local_rank, METRIC, UNIT, WORKLOADS, measured_peak_hbm, ClockSampler, cpu_compress)
 
     workload, _ = WORKLOADS[args.cfg]
     bed = synth.bed(args.cfg, args.lines, seed=42)

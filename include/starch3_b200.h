@@ -50,6 +50,10 @@ S3G_API uint64_t s3g_launch_count(const s3g_ctx *ctx);
 /* Times the block sort had to repeat its radix passes with peer-mask ranking because the keys left by the
  * ordered-atomic ranking were not ascending (bwt.cu, k_sweep).  Expected to stay 0; a diagnostic. */
 S3G_API uint64_t s3g_sort_retries(const s3g_ctx *ctx);
+/* Block-sort diagnostics: out[0] = bzip2 blocks sorted by the bucket form (bwt_bucket.cu) since the context was created,
+ * out[1] = batches in which it handed blocks back to the radix form (a sub-bucket of more than 256 equal keys, or a
+ * bucket beyond its shared-memory capacity), out[2] = s3g_sort_retries. */
+S3G_API int s3g_sort_stats(const s3g_ctx *ctx, uint64_t out[3]);
 /* Per-kernel timing with CUDA events on the launching stream.  s3g_profile(ctx, 1) starts
  * recording; s3g_profile_report synchronises and writes one line per kernel name
  * ("name\tlaunches\ttotal_ms\talgorithmic_bytes\n") into buf, then clears the records. */

@@ -18,7 +18,7 @@ lib_path = os.path.join(HERE, "libstarch3_b200.so")
 S3G_OK, S3G_E_CUDA, S3G_E_PARAM, S3G_E_NOMEM, S3G_E_MALFORMED, S3G_E_CAPACITY, S3G_E_LIMIT = 0, -1, -2, -3, -4, -5, -6
 
 C_ABI_SYMBOLS = [
-    "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_sort_retries", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
+    "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_stage_times",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
@@ -87,6 +87,7 @@ def lib():
         L.s3g_set_stream.argtypes = [vp, vp]
         L.s3g_launch_count.argtypes = [vp]; L.s3g_launch_count.restype = u64
         L.s3g_sort_retries.argtypes = [vp]; L.s3g_sort_retries.restype = u64
+        L.s3g_sort_stats.argtypes = [vp, vp]
         L.s3g_profile.argtypes = [vp, i32]
         L.s3g_profile_report.argtypes = [vp, C.c_char_p, u64]
         L.s3g_profile_filter.argtypes = [vp, C.c_char_p]
@@ -204,6 +205,13 @@ class Context:
     @property
     def sort_retries(self):
         return self._lib.s3g_sort_retries(self._h)
+
+    @property
+    def sort_stats(self):
+        """(blocks sorted by the bucket form, batches in which it handed blocks back to the radix form, radix retries)"""
+        out = (C.c_uint64 * 3)()
+        self._check(self._lib.s3g_sort_stats(self._h, out))
+        return tuple(out)
 
     def profile(self, enable=True):
         self._check(self._lib.s3g_profile(self._h, 1 if enable else 0))

@@ -647,6 +647,15 @@ uint64_t s3g_sort_retries(const s3g_ctx *ctx)
     return r;
 }
 
+int s3g_sort_stats(const s3g_ctx *ctx, uint64_t out[3])
+{
+    if (!ctx || !out) { set_error("null argument"); return S3G_E_PARAM; }
+    out[0] = ctx->bucket_blocks; out[1] = ctx->bucket_handed_back; out[2] = ctx->sort_retries;
+    for (int k = 0; k < 2; k++)
+        if (ctx->sub[k]) { out[0] += ctx->sub[k]->bucket_blocks; out[1] += ctx->sub[k]->bucket_handed_back; out[2] += ctx->sub[k]->sort_retries; }
+    return S3G_OK;
+}
+
 int s3g_profile(s3g_ctx *ctx, int enable)
 {
     if (!ctx) { set_error("null context"); return S3G_E_PARAM; }

@@ -25,60 +25,9 @@
 //            group by its second half (two 10-bit radix passes over the still-unsorted rotations).  Rounds
 //            stop when every group is a singleton or h >= n (equal rotations: a periodic block, flagged in
 //            BlockInfo.tie and resolved by k_fallback_exact).
-#include "common.cuh"
+#include "bwt.cuh"
 
 namespace s3g {
-
-constexpr int ST = 256;                 // threads per sort tile
-constexpr int SI = 16;                  // items per thread
-constexpr int STILE = ST * SI;          // 4096 items per tile
-constexpr int NBINS = 1024;             // 10-bit digits
-constexpr int NT = (BLK_STRIDE + STILE - 1) / STILE;   // tiles per block slot (220)
-constexpr uint32_t FINAL = 0x80000000u;
-
-struct BwtP {
-    const uint8_t *blk;        // packed block bytes of the call (block lb of the batch at blocks[lb].blk_off)
-    const uint8_t *seq;        // unseqToSeq maps, 256 per block
-    const BlockInfo *blocks;   // batch block 0
-    uint32_t *sa, *rk;         // [nb][BLK_STRIDE]
-    uint64_t *kv0, *kv1;       // [nb][BLK_STRIDE] (key << 32 | val)
-    uint32_t *hist;            // [nb][NT][NBINS] (tile-major: every access below is coalesced over digits)
-    uint32_t *cnt_n;           // [nb] block sizes
-    uint32_t *cnt_m;           // [nb] active items after pass 1
-    uint32_t *act;             // [2][nb] unsorted rotations per block (ping-pong by round)
-    uint32_t *agg;             // [nb][NT][2] tile aggregates of the boundary scans
-    unsigned long long *g_act; // [2] batch totals
-    uint32_t *init_k;          // [nb] symbols in the initial key
-    uint32_t *init_k32;        // [nb] symbols in the 32-bit per-position key the group finisher compares (<= init_k)
-    uint32_t *init_f;          // [nb] classes of the symbol after the k-th that still fit below 2^40 (floor(2^40 / a^k) >= 1)
-    uint32_t *init_a;          // [nb] alphabet size
-    uint32_t *left;            // [nb] rotations the group finisher left unsorted (blocks that need doubling rounds)
-};
-
-enum { MODE_INIT = 0, MODE_MM = 1, MODE_KV = 2, MODE_KVX = 3 };   // KVX: key/value pairs saved by the histogram pass, ~0 = not taking part
-
-// Records are 64 bits.  Initial sort: (44-bit symbol key << 20) | rotation start.  Doubling rounds:
-// (rank << 32) | rotation start.  A radix pass takes its digit at bit `rshift` of the record.
-#ifndef S3G_KEY_BITS
-#define S3G_KEY_BITS 44
-#endif
-constexpr int KEY_BITS = S3G_KEY_BITS;   // initial key (at most 64 - VAL_BITS)
-#ifndef S3G_SW_BITS
-#define S3G_SW_BITS 9
-#endif
-#ifndef S3G_SW_OCC
-#define S3G_SW_OCC 3
-#endif
-#ifndef S3G_SWT
-#define S3G_SWT 256
-#endif
-#ifndef S3G_SWI
-#define S3G_SWI 16
-#endif
-constexpr int SW_BITS = S3G_SW_BITS;               // digit width of the onesweep passes
-constexpr int SWN = 1 << SW_BITS;        // their bins
-constexpr int SW_OCC = S3G_SW_OCC;                // resident CTAs per SM the sweep is compiled for
-constexpr int VAL_BITS = 20;             // rotation starts are < 2^20 (BLK_STRIDE)
 
 // record p of block lb for the given source mode; returns false if the item does not take part
 template <int MODE>
@@ -314,6 +263,7 @@ __global__ void __launch_bounds__(ST) k_keys(BwtP P, uint32_t *ghist)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeysSmem &S = *reinterpret_cast<KeysSmem *>(smem_raw);
     const uint32_t lb = blockIdx.y, tid = threadIdx.x;
+    if (P.mode[lb] != P.want) return;
     const uint32_t n = P.cnt_n[lb];
     const uint32_t t0 = blockIdx.x * KT;
     if ((uint64_t)t0 * STILE >= n) return;
@@ -405,7 +355,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
     // batch interleaved they were evicted one sector at a time and the pass ran at a third of the DRAM rate),
     // while the look-back still finds its predecessors finished after a few tiles.
     const uint32_t lb = blockIdx.x / (SW_NT * G) * G + blockIdx.x % G;
-    if (lb >= nb) return;
+    if (lb >= nb || P.mode[lb] != P.want) return;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) S.scan[0] = atomicAdd(ticket_ctr + lb, 1u);
     // Intra-warp matching through shared memory instead of match.any (measured on B200: match.any costs
@@ -749,9 +699,6 @@ __global__ void __launch_bounds__(ST) k_bound_agg(BwtP P, uint32_t round, const 
 // Ties that survive FLEVELS levels and groups beyond FB_MAX (long repeats, periodic blocks) are written out
 // unsorted with a NONHEAD flag on every member but the first; only blocks that have such leftovers go
 // through the prefix-doubling rounds below.
-constexpr int FLEVELS = 12;                      // levels of k32 symbols before a tie is left to the doubling rounds
-constexpr uint32_t NONHEAD = 0x80000000u;        // SA flag: same (unsorted) group as the previous position
-constexpr uint32_t VMASK = 0x000fffffu;          // rotation start (< 2^20)
 
 __device__ __forceinline__ uint32_t deeper_key(const uint32_t *k30, uint32_t pos, uint32_t off, uint32_t n)
 {
@@ -801,6 +748,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const 
 {
     __shared__ FinASmem S;
     const uint32_t lb = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    if (P.mode[lb] != P.want) return;
     const uint32_t n = P.cnt_n[lb];
     if (blockIdx.x * FA_TILE >= n) return;
     S.seq[tid] = P.seq[(uint64_t)lb * 256 + tid];
@@ -1448,11 +1396,13 @@ __global__ void __launch_bounds__(ST) k_rank_update(BwtP P, uint32_t round, cons
     }
 }
 
-__global__ void k_bwt_setup(BwtP P, uint32_t nb)
+// bucket_min: blocks of at least this many bytes (and two symbols) are sorted by the bucket form; 0 = none
+__global__ void k_bwt_setup(BwtP P, uint32_t nb, uint32_t bucket_min)
 {
     uint32_t lb = blockIdx.x * blockDim.x + threadIdx.x;
     if (lb >= nb) return;
     uint32_t n = P.blocks[lb].nblock, a = P.blocks[lb].n_in_use;
+    P.mode[lb] = bucket_min && n >= bucket_min && a >= 2 ? 1u : 0u;
     if (a < 1) a = 1;
     uint32_t k = 1, k32 = 1;
     if (a >= 2) {
@@ -1570,6 +1520,15 @@ __device__ void fb_qsort3(const FbState &st, int lo0, int hi0)
     }
 }
 
+// a block (mode == which) that is sorted once more: forget the leftovers counted for it
+__global__ void k_reset_left(BwtP P, uint32_t nb, uint32_t which, unsigned long long *g_left)
+{
+    uint32_t lb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lb >= nb || P.mode[lb] != which) return;
+    uint32_t l = P.left[lb];
+    if (l) { atomicAdd(g_left, (unsigned long long)0 - (unsigned long long)l); P.left[lb] = 0; }
+}
+
 __global__ void k_fallback_exact(BwtP P, BlockInfo *blocks)
 {
     uint32_t lb = blockIdx.x;
@@ -1645,7 +1604,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->kv0.ensure(slots * 8));
     S3G_TRY(ctx->kv1.ensure(slots * 8));
     S3G_TRY(ctx->hist.ensure((size_t)nb * NBINS * NT * 4));
-    S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (9 * 4 + NT * 2 * 4) + 64));
+    S3G_TRY(ctx->bwt_misc.ensure((size_t)nb * (10 * 4 + NT * 2 * 4) + 64));
     S3G_TRY(ctx->lcol.ensure(slots));
     BwtP P;
     P.blk = ctx->blk_bytes.as<uint8_t>();
@@ -1665,6 +1624,8 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     P.left = misc; misc += nb;
     P.init_k32 = misc; misc += nb;
     P.init_f = misc; misc += nb;
+    P.mode = misc; misc += nb;
+    P.want = 0;
     P.agg = misc;
     dim3 grid(NT, (unsigned)nb);
     double N = 0;                       // rotations in this batch
@@ -1684,64 +1645,103 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     const uint64_t *no_kv = nullptr;
     uint32_t *no_out = nullptr;
     uint64_t *no_save = nullptr;
-    // ---- init: order by the first k symbols (radix passes on the initial key), then the group finisher ----
+    (void)no_act;
     S3G_TRY(ctx->bwt_ghist.ensure((size_t)nb * NPASS * (SWN + 1) * 4));
     uint32_t *ghist = ctx->bwt_ghist.as<uint32_t>();
     uint32_t *tickets = ghist + (size_t)nb * NPASS * SWN;        // [NPASS][nb]
     unsigned long long *h_act = reinterpret_cast<unsigned long long *>(ctx->h_scalars + 32);
+    const uint32_t *h_act32 = reinterpret_cast<const uint32_t *>(h_act);
     uint32_t G = SWEEP_G;
     if (const char *e = getenv("S3G_SWEEP_G")) { int v = atoi(e); if (v > 0) G = (uint32_t)v; }
     const unsigned sweep_grid = (unsigned)((nb + G - 1) / G) * G * SW_NT;
-    // attempt 0 ranks with ordered atomics (k_sweep, SAFE = false); if the finisher finds a key out of order
-    // the passes are repeated with peer masks.  S3G_SORT=safe skips the first attempt, S3G_SORT=broken makes it
-    // rank without any order (tests of the check and of the second attempt).
+    // Which form sorts a block: the bucket form (bwt_bucket.cu) takes the blocks of at least BUCKET_MIN bytes, the radix
+    // form below the small ones and whatever the bucket form hands back.  S3G_SORT=radix keeps every block here;
+    // S3G_SORT=safe skips the radix form's first attempt (ordered atomics) and S3G_SORT=broken makes that attempt
+    // rank without any order (tests of the ascending-key check and of the second attempt) -- both imply radix.
     const char *sort_env = getenv("S3G_SORT");
     const bool force_safe = sort_env && !strcmp(sort_env, "safe"), broken = sort_env && !strcmp(sort_env, "broken");
-    for (int attempt = force_safe ? 1 : 0; attempt < 2; attempt++) {
-        const bool safe = attempt == 1;
-        S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 32, ctx->stream));
-        S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb);
-        S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * NPASS * (SWN + 1) * 4, ctx->stream));
-        // look-back status words carry a generation tag; the table is cleared only when it is new, was used
-        // by the doubling rounds (as a histogram table) or the tag wraps
-        if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS > 255) {
-            S3G_CUDA(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->stream));
-            ctx->sweep_cap = ctx->hist.cap; ctx->sweep_gen = 0;
+    const bool radix_only = force_safe || broken || (sort_env && !strcmp(sort_env, "radix"));
+    constexpr uint32_t BUCKET_MIN = 8192;
+    uint64_t n_bucket = 0;
+    if (!radix_only)
+        for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++)
+            n_bucket += ctx->h_blocks[b0 + b].nblock >= BUCKET_MIN && ctx->h_blocks[b0 + b].n_in_use >= 2;
+    S3G_CUDA(cudaMemsetAsync(P.g_act, 0, 32, ctx->stream));          // leftover totals, list counters, flags
+    S3G_LAUNCH(ctx, k_bwt_setup, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb, radix_only ? 0u : BUCKET_MIN);
+
+    // ---- radix form on the blocks whose mode is `want`: order by the first k symbols (radix passes on the initial key),
+    // then the group finisher; ends with the totals on the host ----
+    auto radix_form = [&](uint32_t want) -> int {
+        P.want = want;
+        // attempt 0 ranks with ordered atomics (k_sweep, SAFE = false); if the finisher finds a key out of order
+        // the passes are repeated with peer masks
+        for (int attempt = force_safe ? 1 : 0; attempt < 2; attempt++) {
+            const bool safe = attempt == 1;
+            S3G_CUDA(cudaMemsetAsync(big_cnt, 0, 12, ctx->stream));      // listed groups, out-of-order flag, groups passed on
+            S3G_CUDA(cudaMemsetAsync(ghist, 0, (size_t)nb * NPASS * (SWN + 1) * 4, ctx->stream));
+            // look-back status words carry a generation tag; the table is cleared only when it is new, was used
+            // by the doubling rounds or the bucket form, or the tag wraps
+            if (ctx->sweep_cap != ctx->hist.cap || ctx->sweep_gen + NPASS > 255) {
+                S3G_CUDA(cudaMemsetAsync(ctx->hist.p, 0, ctx->hist.cap, ctx->stream));
+                ctx->sweep_cap = ctx->hist.cap; ctx->sweep_gen = 0;
+            }
+            S3G_BYTES(ctx, 5 * N);
+            S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, ghist);
+            S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), SWN, 0, ghist);
+            uint64_t *src = P.kv0, *dst = P.kv1;
+            for (int pass = 0; pass < NPASS; pass++) {
+                S3G_BYTES(ctx, 16 * N);
+                const int rshift = VAL_BITS + SW_BITS * pass;
+                uint32_t *tk = tickets + (size_t)pass * nb;
+                if (pass == 0 || (broken && !safe))
+                    S3G_LAUNCH(ctx, k_sweep_first, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                else if (!safe)
+                    S3G_LAUNCH(ctx, k_sweep_ordered, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                else
+                    S3G_LAUNCH(ctx, k_sweep_masks, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
+                std::swap(src, dst);
+            }
+            // every group that ends inside a warp's window is finished there, larger ones by one CTA each; SA, last column, origPtr
+            S3G_BYTES(ctx, 18 * N);
+            S3G_LAUNCH(ctx, k_finish_rows, dim3(FA_NT, (unsigned)nb), FA_WARPS * 32, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
+                       ctx->lcol.as<uint8_t>(), dst, big_cnt, big_cnt + 1);
+            uint64_t *list2 = dst + slots / 2;                         // second half of the free sort buffer
+            S3G_LAUNCH(ctx, k_finish_mid, SM_COUNT * 4, FM_WARPS * 32, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(),
+                       dst, big_cnt, list2, big_cnt + 2);
+            S3G_LAUNCH(ctx, k_finish_big, SM_COUNT * 4, FB_TH, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(), list2,
+                       big_cnt + 2);
+            S3G_TRY(check_launch("bwt init"));
+            S3G_CUDA(cudaMemcpyAsync(h_act, P.g_act, 32, cudaMemcpyDeviceToHost, ctx->stream));
+            S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+            const uint32_t unsorted = h_act32[5];
+            if (getenv("S3G_DEBUG"))
+                fprintf(stderr, "[s3g] bwt radix form (mode %u) attempt %d: %llu of %.0f rotations left to the doubling rounds%s\n", want, attempt, *h_act, N,
+                        unsorted ? "; keys OUT OF ORDER" : "");
+            if (!unsorted) return S3G_OK;
+            if (safe) { set_error("bwt: the radix passes did not sort the initial keys"); return S3G_E_CUDA; }
+            ctx->sort_retries++;
+            S3G_LAUNCH(ctx, k_reset_left, (unsigned)((nb + 127) / 128), 128, 0, P, (uint32_t)nb, want, P.g_act);   // the repeat counts them again
         }
-        S3G_BYTES(ctx, 5 * N);
-        S3G_LAUNCH(ctx, k_keys, dim3((NT + KT - 1) / KT, (unsigned)nb), ST, sizeof(KeysSmem), P, ghist);
-        S3G_LAUNCH(ctx, k_digit_scan, dim3(NPASS, (unsigned)nb), SWN, 0, ghist);
-        uint64_t *src = P.kv0, *dst = P.kv1;
-        for (int pass = 0; pass < NPASS; pass++) {
-            S3G_BYTES(ctx, 16 * N);
-            const int rshift = VAL_BITS + SW_BITS * pass;
-            uint32_t *tk = tickets + (size_t)pass * nb;
-            if (pass == 0 || (broken && !safe))
-                S3G_LAUNCH(ctx, k_sweep_first, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
-            else if (!safe)
-                S3G_LAUNCH(ctx, k_sweep_ordered, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
-            else
-                S3G_LAUNCH(ctx, k_sweep_masks, sweep_grid, SWT, sizeof(SweepSmem), P, rshift, src, dst, ghist, pass, tk, (uint32_t)nb, ++ctx->sweep_gen, G);
-            std::swap(src, dst);
-        }
-        // every group that ends inside a warp's window is finished there, larger ones by one CTA each; SA, last column, origPtr
-        S3G_BYTES(ctx, 18 * N);
-        S3G_LAUNCH(ctx, k_finish_rows, dim3(FA_NT, (unsigned)nb), FA_WARPS * 32, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0,
-                   ctx->lcol.as<uint8_t>(), dst, big_cnt, big_cnt + 1);
-        uint64_t *list2 = dst + slots / 2;                         // second half of the free sort buffer
-        S3G_LAUNCH(ctx, k_finish_mid, SM_COUNT * 4, FM_WARPS * 32, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(),
-                   dst, big_cnt, list2, big_cnt + 2);
-        S3G_LAUNCH(ctx, k_finish_big, SM_COUNT * 4, FB_TH, 0, P, src, P.g_act, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>(), list2,
-                   big_cnt + 2);
-        S3G_TRY(check_launch("bwt init"));
+        return S3G_OK;
+    };
+
+    bool have_totals = false;
+    if (n_bucket) {
+        S3G_TRY(run_bucket_sort(ctx, P, b0, nb, P.g_act, big_cnt + 3));
+        ctx->bucket_blocks += n_bucket;
+    }
+    if (n_bucket < nb) { S3G_TRY(radix_form(0)); have_totals = n_bucket == 0; }
+    if (!have_totals) {
         S3G_CUDA(cudaMemcpyAsync(h_act, P.g_act, 32, cudaMemcpyDeviceToHost, ctx->stream));
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-        const uint32_t unsorted = reinterpret_cast<const uint32_t *>(h_act)[5];
+        S3G_TRY(check_launch("bwt bucket form"));
         if (getenv("S3G_DEBUG"))
-            fprintf(stderr, "[s3g] bwt attempt %d: %llu of %.0f rotations left to the doubling rounds%s\n", attempt, *h_act, N, unsorted ? "; keys OUT OF ORDER" : "");
-        if (!unsorted) break;
-        if (safe) { set_error("bwt: the radix passes did not sort the initial keys"); return S3G_E_CUDA; }
-        ctx->sort_retries++;
+            fprintf(stderr, "[s3g] bwt bucket form: %llu blocks, %llu of %.0f rotations left to the doubling rounds%s\n", (unsigned long long)n_bucket, *h_act, N,
+                    h_act32[7] ? "; some blocks handed to the radix form" : "");
+        if (h_act32[7]) {
+            ctx->bucket_handed_back++;
+            S3G_TRY(radix_form(2));
+        }
     }
     if (*h_act == 0) return S3G_OK;
     // (sa with flags) -> ranks; the flag-free order lands in kv1's storage and is copied back

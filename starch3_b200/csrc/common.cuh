@@ -93,7 +93,8 @@ struct Ctx {
     cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: each context sets it once on its own device
-    bool attr_bwt = false, attr_mtf = false, attr_huff = false;
+    bool attr_bwt = false, attr_mtf = false, attr_huff = false, attr_bs = false;
+    uint64_t bucket_blocks = 0, bucket_handed_back = 0;   // blocks sorted by the bucket form; batches in which it handed blocks back
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // pinned host scratch for small read-backs
     uint64_t *h_scalars = nullptr;   // 64 x u64

@@ -179,6 +179,64 @@ def test_bwt_finisher_limits_and_fallback(ctx, oracle, name, blk):
     assert np.array_equal(ptr, optr), name
 
 
+def _bucket_blocks():
+    """Blocks for the bucket form (bwt_bucket.cu, blocks of 8192 bytes and more): real shapes, groups of equal keys up to
+    its sub-bucket capacity (256) with ties 1 .. 4 deeper levels long and ties that outlast its 12 levels (left to the
+    doubling rounds), an alphabet of 2 and of 256 symbols, and sizes around the bucket-count steps."""
+    rng = np.random.default_rng(23)
+    def tagged(groups, depth, filler=20000):
+        parts = [bytes(rng.integers(97, 123, filler, dtype=np.uint8))]
+        for gi, count in enumerate(groups):
+            tag = b"KEYKEYKEYKEY%03d" % gi + bytes(rng.integers(97, 123, depth, dtype=np.uint8))   # shared by the group, not self-similar
+            for i in rng.permutation(count):
+                parts.append(tag + (b"%04d" % int(i)) + bytes(rng.integers(97, 123, int(rng.integers(1, 7)), dtype=np.uint8)))
+        return b"".join(parts)
+    yield "groups_shallow", tagged([2, 3, 17, 31, 32, 33, 63, 64, 65, 100, 128, 129, 200, 255], 0)
+    yield "groups_deep20", tagged([5, 40, 90, 150, 250], 20)
+    yield "groups_deep60", tagged([7, 64, 130, 240], 60)
+    yield "groups_beyond_levels", tagged([3, 50, 120], 400)
+    yield "two_symbols", bytes(rng.integers(0, 2, 60000, dtype=np.uint8) + 65)
+    yield "all_bytes", bytes(rng.integers(0, 256, 70000, dtype=np.uint8))
+    for n in (8192, 8193, 14081, 28160, 28161, 56321, 450000):
+        yield "random%d" % n, bytes(rng.integers(97, 110, n, dtype=np.uint8))
+    yield "skewed", bytes(rng.choice(np.frombuffer(b"aaaaaaaaaaaaaaaaaaaaaaaab\ncd", dtype=np.uint8), 300000))
+
+
+BUCKET_BLOCKS = list(_bucket_blocks())
+
+
+@pytest.mark.parametrize("name,blk", BUCKET_BLOCKS, ids=[n for n, _ in BUCKET_BLOCKS])
+def test_bwt_bucket_form(ctx, oracle, name, blk):
+    before = ctx.sort_stats
+    (ptr, orig), = ctx.bwt([blk])
+    after = ctx.sort_stats
+    optr, oorig = oracle.bwt(blk)
+    assert orig == oorig, name
+    assert np.array_equal(ptr, optr), name
+    assert after[0] == before[0] + 1, "the bucket form did not run"
+    if name != "skewed":
+        assert after[1] == before[1], "handed back to the radix form"
+
+
+def test_bwt_bucket_and_radix_forms_in_one_batch(ctx, oracle, monkeypatch):
+    """Small blocks (radix form), large ones (bucket form) and one the bucket form hands back (2048 equal keys) in the
+    same batch; then every block through the radix form alone (S3G_SORT=radix): same order."""
+    rng = np.random.default_rng(3)
+    blks = [b"abc" * 100, _resolve_block(oracle, "cfg2", None), bytes(rng.integers(97, 123, 5000, dtype=np.uint8)),
+            dict(_finisher_blocks())["group2049"], _resolve_block(oracle, "cfg4", None)[:200000], b"ab" * 3000 + b"c",
+            _resolve_block(oracle, "cfg3", None)[:120000]]
+    expect = [oracle.bwt(b) for b in blks]
+    for mode in (None, "radix"):
+        if mode:
+            monkeypatch.setenv("S3G_SORT", mode)
+        before = ctx.sort_stats
+        got = ctx.bwt(blks)
+        for (ptr, orig), (optr, oorig) in zip(got, expect):
+            assert orig == oorig and np.array_equal(ptr, optr)
+        grew = ctx.sort_stats[0] - before[0]
+        assert grew == (0 if mode else 4)
+
+
 @pytest.mark.parametrize("mode", ["safe", "broken"])
 def test_bwt_sort_safety_net(ctx, oracle, monkeypatch, mode):
     """The radix passes rank with ordered shared-memory atomics and the finisher checks that the keys it
