@@ -1654,13 +1654,14 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     uint32_t G = SWEEP_G;
     if (const char *e = getenv("S3G_SWEEP_G")) { int v = atoi(e); if (v > 0) G = (uint32_t)v; }
     const unsigned sweep_grid = (unsigned)((nb + G - 1) / G) * G * SW_NT;
-    // Which form sorts a block: the bucket form (bwt_bucket.cu) takes the blocks of at least BUCKET_MIN bytes, the radix
-    // form below the small ones and whatever the bucket form hands back.  S3G_SORT=radix keeps every block here;
-    // S3G_SORT=safe skips the radix form's first attempt (ordered atomics) and S3G_SORT=broken makes that attempt
-    // rank without any order (tests of the ascending-key check and of the second attempt) -- both imply radix.
+    // Which form sorts a block.  The radix form below is the default.  S3G_SORT=bucket gives the blocks of at least
+    // BUCKET_MIN bytes to the bucket form (bwt_bucket.cu: 27 HBM bytes per rotation instead of 111, but bound by
+    // instruction issue and slower on B200 today -- DESIGN.md section 7); the radix form then sorts the small blocks and
+    // whatever the bucket form hands back.  S3G_SORT=safe skips the radix form's first attempt (ordered atomics) and
+    // S3G_SORT=broken makes that attempt rank without any order (tests of the ascending-key check and of the second attempt).
     const char *sort_env = getenv("S3G_SORT");
     const bool force_safe = sort_env && !strcmp(sort_env, "safe"), broken = sort_env && !strcmp(sort_env, "broken");
-    const bool radix_only = force_safe || broken || (sort_env && !strcmp(sort_env, "radix"));
+    const bool radix_only = !(sort_env && !strcmp(sort_env, "bucket"));
     constexpr uint32_t BUCKET_MIN = 8192;
     uint64_t n_bucket = 0;
     if (!radix_only)
@@ -1739,7 +1740,12 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
             fprintf(stderr, "[s3g] bwt bucket form: %llu blocks, %llu of %.0f rotations left to the doubling rounds%s\n", (unsigned long long)n_bucket, *h_act, N,
                     h_act32[7] ? "; some blocks handed to the radix form" : "");
         if (h_act32[7]) {
-            ctx->bucket_handed_back++;
+            std::vector<uint32_t> hm(nb);
+            S3G_CUDA(cudaMemcpy(hm.data(), P.mode, nb * 4, cudaMemcpyDeviceToHost));
+            uint64_t back = 0;
+            for (uint32_t m : hm) back += m == 2;
+            ctx->bucket_handed_back += back;
+            if (getenv("S3G_DEBUG")) fprintf(stderr, "[s3g] bwt bucket form handed %llu of %llu blocks back\n", (unsigned long long)back, (unsigned long long)nb);
             S3G_TRY(radix_form(2));
         }
     }

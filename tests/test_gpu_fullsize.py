@@ -119,3 +119,16 @@ def test_header_text_is_janssons(ctx, oracle):
     streams = [(s["chromosome"].encode(), s["offset"], s["size"], s["lines"], s["blocks"], s["transformedBytes"],
                 s["nonUniqueBases"], s["uniqueBases"]) for s in meta["streams"]]
     assert oracle.jansson_header(9, note, streams) == arc[4:nl]
+
+
+def test_archive_byte_parity_bucket_form_of_the_block_sort(ctx, oracle, monkeypatch):
+    """S3G_SORT=bucket: every block of at least 8192 bytes through bwt_bucket.cu (sample-sort buckets finished in shared
+    memory) -- 3 M lines of cfg2 (89 blocks, 24 chromosomes) and 1 M lines of cfg4 (70 symbols)."""
+    monkeypatch.setenv("S3G_SORT", "bucket")
+    monkeypatch.setenv("S3G_PARTS", "1")
+    for cfg, lines in ((2, 3_000_000), (4, 1_000_000)):
+        bed = synth.bed(cfg, lines)
+        before = ctx.sort_stats
+        res = ctx.compress_bed(bed, 9, note="bucket")
+        assert ctx.sort_stats[0] - before[0] >= res.n_blocks - 24
+        _same(res.archive, oracle.archive_mt(bed, 9, "bucket"))

@@ -187,7 +187,8 @@ def _bucket_blocks():
     def tagged(groups, depth, filler=20000):
         parts = [bytes(rng.integers(97, 123, filler, dtype=np.uint8))]
         for gi, count in enumerate(groups):
-            tag = b"KEYKEYKEYKEY%03d" % gi + bytes(rng.integers(97, 123, depth, dtype=np.uint8))   # shared by the group, not self-similar
+            # the group's own random context (no key is shared between groups), then `depth` symbols shared by the group
+            tag = bytes(rng.integers(65, 91, 12, dtype=np.uint8)) + b"%03d" % gi + bytes(rng.integers(97, 123, depth, dtype=np.uint8))
             for i in rng.permutation(count):
                 parts.append(tag + (b"%04d" % int(i)) + bytes(rng.integers(97, 123, int(rng.integers(1, 7)), dtype=np.uint8)))
         return b"".join(parts)
@@ -206,7 +207,8 @@ BUCKET_BLOCKS = list(_bucket_blocks())
 
 
 @pytest.mark.parametrize("name,blk", BUCKET_BLOCKS, ids=[n for n, _ in BUCKET_BLOCKS])
-def test_bwt_bucket_form(ctx, oracle, name, blk):
+def test_bwt_bucket_form(ctx, oracle, name, blk, monkeypatch):
+    monkeypatch.setenv("S3G_SORT", "bucket")
     before = ctx.sort_stats
     (ptr, orig), = ctx.bwt([blk])
     after = ctx.sort_stats
@@ -220,21 +222,23 @@ def test_bwt_bucket_form(ctx, oracle, name, blk):
 
 def test_bwt_bucket_and_radix_forms_in_one_batch(ctx, oracle, monkeypatch):
     """Small blocks (radix form), large ones (bucket form) and one the bucket form hands back (2048 equal keys) in the
-    same batch; then every block through the radix form alone (S3G_SORT=radix): same order."""
+    same batch (S3G_SORT=bucket); then every block through the radix form alone (the default): same order."""
     rng = np.random.default_rng(3)
     blks = [b"abc" * 100, _resolve_block(oracle, "cfg2", None), bytes(rng.integers(97, 123, 5000, dtype=np.uint8)),
             dict(_finisher_blocks())["group2049"], _resolve_block(oracle, "cfg4", None)[:200000], b"ab" * 3000 + b"c",
             _resolve_block(oracle, "cfg3", None)[:120000]]
     expect = [oracle.bwt(b) for b in blks]
-    for mode in (None, "radix"):
+    for mode in ("bucket", None):
         if mode:
             monkeypatch.setenv("S3G_SORT", mode)
+        else:
+            monkeypatch.delenv("S3G_SORT")
         before = ctx.sort_stats
         got = ctx.bwt(blks)
         for (ptr, orig), (optr, oorig) in zip(got, expect):
             assert orig == oorig and np.array_equal(ptr, optr)
         grew = ctx.sort_stats[0] - before[0]
-        assert grew == (0 if mode else 4)
+        assert grew == (4 if mode else 0)
 
 
 @pytest.mark.parametrize("mode", ["safe", "broken"])
