@@ -1449,9 +1449,8 @@ __global__ void __launch_bounds__(ST) k_bwt_finish(BwtP P, BlockInfo *blocks, ui
 // When a block is a power of a shorter string, equal rotations tie and the position of
 // rotation 0 inside its tie group is whatever libbz2's fallbackSort leaves behind
 // (bz/blocksort.c:212-329 with its helper sorts :32-61 and :93-180; SURVEY.md section 7 shows
-// libbz2 always ends in fallbackSort for such blocks).  One thread replays that algorithm
-// step for step on the intact block.  Rare: nblockMAX is prime, so only stream-tail blocks
-// can be periodic.
+// libbz2 always ends in fallbackSort for such blocks).  k_fallback_exact replays that algorithm
+// on the intact block.  Rare: nblockMAX is prime, so only stream-tail blocks can be periodic.
 struct FbState {
     uint32_t *fmap, *ec, *bh;
 };
@@ -1529,62 +1528,132 @@ __global__ void k_reset_left(BwtP P, uint32_t nb, uint32_t which, unsigned long 
     if (l) { atomicAdd(g_left, (unsigned long long)0 - (unsigned long long)l); P.left[lb] = 0; }
 }
 
-__global__ void k_fallback_exact(BwtP P, BlockInfo *blocks)
+// largest set bit <= i / smallest set bit >= i of the bucket-head bit vector (bit 0 and bit n are always set)
+__device__ __forceinline__ int fb_head(const uint32_t *bh, int i)
 {
-    uint32_t lb = blockIdx.x;
-    if (threadIdx.x != 0 || !blocks[lb].tie) return;
+    int w = i >> 5;
+    uint32_t m = bh[w] & (0xffffffffu >> (31 - (i & 31)));
+    while (!m) m = bh[--w];
+    return (w << 5) + 31 - __clz((int)m);
+}
+__device__ __forceinline__ int fb_next(const uint32_t *bh, int i)
+{
+    int w = i >> 5;
+    uint32_t m = bh[w] & (0xffffffffu << (i & 31));
+    while (!m) m = bh[++w];
+    return (w << 5) + __ffs((int)m) - 1;
+}
+
+// One CTA per periodic block.  fallbackSort is a sequence of rounds; inside a round every bucket (maximal range of
+// equal rank so far) is sorted by its own fallbackQSort3 call, which starts from r = 0 (bz/blocksort.c:104), reads
+// only eclass[] -- fixed during the round -- and permutes only its own range of fmap: the calls of a round are
+// independent, so they are replayed one thread per bucket.  A bucket whose keys are all equal is left untouched by
+// fallbackQSort3 / fallbackSimpleSort (bz/blocksort.c:32-61, :93-180: only strict comparisons move anything), so only
+// the non-uniform buckets are replayed at all; everything else in a round (eclass update, the scan for the buckets,
+// the new bucket heads) is position-parallel.
+constexpr int FBT = 1024;
+__global__ void __launch_bounds__(FBT) k_fallback_exact(BwtP P, BlockInfo *blocks)
+{
+    const uint32_t lb = blockIdx.x;
+    if (!blocks[lb].tie) return;
     const int n = (int)P.cnt_n[lb];
     const uint8_t *blk = P.blk + P.blocks[lb].blk_off;
     FbState st;
     st.fmap = P.sa + (uint64_t)lb * BLK_STRIDE;
     st.ec = P.rk + (uint64_t)lb * BLK_STRIDE;
     st.bh = reinterpret_cast<uint32_t *>(P.kv0 + (uint64_t)lb * BLK_STRIDE);
-    int32_t ftab[257];
-    for (int i = 0; i < 257; i++) ftab[i] = 0;
-    for (int i = 0; i < n; i++) ftab[blk[i]]++;
-    { int32_t acc = 0; for (int i = 0; i < 256; i++) { acc += ftab[i]; ftab[i] = acc; } }
-    for (int i = 0; i < n; i++) { int k = --ftab[blk[i]]; st.fmap[k] = (uint32_t)i; }
-    int nbh = n / 32 + 8;
-    for (int i = 0; i < nbh; i++) st.bh[i] = 0;
-    for (int i = 0; i < 256; i++) FB_SET(ftab[i]);
-    for (int i = 0; i < 32; i++) { FB_SET(n + 2 * i); FB_CLR(n + 2 * i + 1); }
-    for (long long H = 1;;) {
-        int j = 0;
-        for (int i = 0; i < n; i++) {
-            if (FB_GET(i)) j = i;
-            int k = (int)st.fmap[i] - (int)H; if (k < 0) k += n;
-            st.ec[k] = (uint32_t)j;
+    uint32_t *scr = reinterpret_cast<uint32_t *>(P.kv1 + (uint64_t)lb * BLK_STRIDE);     // 2 * BLK_STRIDE words
+    uint32_t *cnt = scr;                                   // [256][FBT] occurrences of a byte value in a thread's segment
+    uint32_t *dlist = scr + 256 * FBT;                     // heads of the non-uniform buckets of the round (at most n / 2)
+    uint32_t *dmark = dlist + BLK_STRIDE / 2 + 64;         // [n] round in which a bucket was listed
+    __shared__ uint32_t s_tot[256], s_start[256];
+    __shared__ uint32_t s_nd, s_notdone, s_refined;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int seg = (n + FBT - 1) / FBT;
+    const int i0 = t * seg < n ? t * seg : n, i1 = i0 + seg < n ? i0 + seg : n;
+    // ---- initial order: by first byte, positions DESCENDING inside a byte value (bz/blocksort.c:236-241) ----
+    for (int c = 0; c < 256; c++) cnt[c * FBT + t] = 0;
+    for (int i = i0; i < i1; i++) cnt[blk[i] * FBT + t]++;
+    for (int i = i0; i < i1; i++) dmark[i] = 0;
+    __syncthreads();
+    for (int c = warp; c < 256; c += FBT / 32) {
+        uint32_t run = 0;
+        for (int k = 0; k < FBT; k += 32) {
+            uint32_t v = cnt[c * FBT + k + lane];
+            uint32_t inc = warp_incl_sum<uint32_t>(v);
+            cnt[c * FBT + k + lane] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        int notdone = 0, r = -1;
-        bool refined = false;
-        for (;;) {
-            int k = r + 1;
-            while (FB_GET(k)) k++;
-            int l = k - 1;
-            if (l >= n) break;
-            while (!FB_GET(k)) k++;
-            r = k - 1;
-            if (r >= n) break;
-            if (r > l) {
-                notdone += r - l + 1;
-                fb_qsort3(st, l, r);
-                int32_t cc = -1;
-                for (int i = l; i <= r; i++) {
-                    int32_t c1 = (int32_t)st.ec[st.fmap[i]];
-                    if (cc != c1) { if (i > l) refined = true; FB_SET(i); cc = c1; }
-                }
+        if (lane == 0) s_tot[c] = run;
+    }
+    __syncthreads();
+    if (t == 0) { uint32_t acc = 0; for (int c = 0; c < 256; c++) { s_start[c] = acc; acc += s_tot[c]; } }
+    const int nbh = n / 32 + 8;
+    for (int w = t; w < nbh; w += FBT) st.bh[w] = 0;
+    __syncthreads();
+    for (int i = i0; i < i1; i++) {
+        uint32_t c = blk[i];
+        uint32_t r = cnt[c * FBT + t]++;
+        st.fmap[s_start[c] + s_tot[c] - 1 - r] = (uint32_t)i;
+    }
+    if (t < 256) atomicOr(&st.bh[s_start[t] >> 5], 1u << (s_start[t] & 31));
+    if (t < 32) atomicOr(&st.bh[(n + 2 * t) >> 5], 1u << ((n + 2 * t) & 31));
+    __syncthreads();
+    uint32_t round = 0;
+    for (long long H = 1;;) {
+        round++;
+        if (t == 0) { s_nd = 0; s_notdone = 0; s_refined = 0; }
+        if (i0 < i1) {
+            int j = fb_head(st.bh, i0);
+            for (int i = i0; i < i1; i++) {
+                if (FB_GET(i)) j = i;
+                int k = (int)st.fmap[i] - (int)H; if (k < 0) k += n;
+                st.ec[k] = (uint32_t)j;
             }
         }
+        __syncthreads();
+        if (i0 < i1) {
+            int j = fb_head(st.bh, i0);
+            uint32_t prevkey = i0 > 0 ? st.ec[st.fmap[i0 - 1]] : 0;
+            bool nonhead = false;
+            for (int i = i0; i < i1; i++) {
+                uint32_t key = st.ec[st.fmap[i]];
+                if (FB_GET(i)) j = i;
+                else {
+                    nonhead = true;
+                    if (key != prevkey && atomicExch(&dmark[j], round) != round) dlist[atomicAdd(&s_nd, 1u)] = (uint32_t)j;
+                }
+                prevkey = key;
+            }
+            if (nonhead) s_notdone = 1;
+        }
+        __syncthreads();
+        const uint32_t nd = s_nd;
+        for (uint32_t b = t; b < nd; b += FBT) {
+            int l = (int)dlist[b];
+            int r = fb_next(st.bh, l + 1) - 1;
+            fb_qsort3(st, l, r);
+        }
+        __syncthreads();
+        if (i0 < i1) {
+            uint32_t prevkey = i0 > 0 ? st.ec[st.fmap[i0 - 1]] : 0;
+            bool refined = false;
+            for (int i = i0; i < i1; i++) {
+                uint32_t key = st.ec[st.fmap[i]];
+                if (!FB_GET(i) && key != prevkey) { atomicOr(&st.bh[i >> 5], 1u << (i & 31)); refined = true; }
+                prevkey = key;
+            }
+            if (refined) s_refined = 1;
+        }
+        __syncthreads();
         H *= 2;
-        if (H > n || notdone == 0) break;
-        // A round that splits no bucket is a fixed point of the doubling (every bucket's keys are equal, and
-        // fallbackQSort3 / fallbackSimpleSort leave all-equal ranges untouched: bz/blocksort.c:32-61, :93-180),
-        // so the remaining rounds of the reference change nothing.  Periodic blocks get here after few rounds.
-        if (!refined) break;
+        // A round that splits no bucket is a fixed point of the doubling (every bucket's keys are equal), so the remaining
+        // rounds of the reference change nothing.  Periodic blocks get here after few rounds.
+        const bool stop = H > n || !s_notdone || !s_refined;
+        __syncthreads();
+        if (stop) break;
     }
-    int32_t orig = -1;
-    for (int i = 0; i < n; i++) if (st.fmap[i] == 0) { orig = i; break; }
-    blocks[lb].orig_ptr = orig;
+    for (int i = i0; i < i1; i++) if (st.fmap[i] == 0) blocks[lb].orig_ptr = i;
 }
 #undef FB_SET
 #undef FB_CLR
@@ -1790,7 +1859,7 @@ int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb)
     }
     S3G_BYTES(ctx, 10 * N);
     S3G_LAUNCH(ctx, k_bwt_finish, grid, ST, 0, P, ctx->blocks.as<BlockInfo>() + b0, ctx->lcol.as<uint8_t>());
-    S3G_LAUNCH(ctx, k_fallback_exact, (unsigned)nb, 32, 0, P, ctx->blocks.as<BlockInfo>() + b0);
+    S3G_LAUNCH(ctx, k_fallback_exact, (unsigned)nb, FBT, 0, P, ctx->blocks.as<BlockInfo>() + b0);
     return check_launch("bwt finish");
 }
 

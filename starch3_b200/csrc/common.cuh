@@ -99,9 +99,12 @@ struct Ctx {
     // pinned host scratch for small read-backs
     uint64_t *h_scalars = nullptr;   // 64 x u64
     // stage buffers (grow-only)
-    DevBuf bed, tile_cnt, line_start, start, stop, rem_off, flags, line_tf_off, chrom_first;
-    DevBuf scan_a, scan_b, scan_c, scalars;
-    DevBuf tf, chroms, stat_a, stat_b, soff;
+    DevBuf bed, tile_cnt, line_start, start, stop, rem_off, flags, chrom_first;
+    DevBuf scan_a, scan_b, scalars;
+    DevBuf tf, chroms, stat_b, soff;
+    // what run_tokenize measured (tokenize_transform.cu): inputs of run_transform_rest / run_range_summary
+    uint32_t front_halo = 0, front_skip = 0, front_line1_flag = 0;
+    int64_t front_tail_max = INT64_MIN;
     DevBuf rle_carry, rle_ebase, blocks, blk_prov, blk_bytes, in_use, seq_map, stream_tab;
     DevBuf sa, rk, kv0, kv1, hist, bwt_misc, bwt_ghist, lcol;
     size_t sweep_cap = 0;                  // capacity of `hist` when its look-back status words were last cleared
@@ -242,9 +245,9 @@ struct TfResult {
 // `skip` (< 16): leading bytes of d_bed that belong to the line before the range (see k_count_newlines)
 int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip = 0);
 // the same in pieces, for ranges handed between GPUs (shard.cu): `halo` = line 0 is the last line before the range
-int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out);
+int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out, uint32_t halo);
 int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_max, uint64_t *last_flag, uint32_t *continues);
-int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max);
+int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump = false);
 
 struct CutResult {
     uint64_t n_blocks = 0;

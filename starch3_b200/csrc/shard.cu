@@ -58,20 +58,16 @@ int s3g_shard_tokenize(s3g_ctx *ctx, const void *d_range, uint64_t n, uint64_t h
     ctx->marks.clear();
     ctx->last_rle_bytes = 0;
     stage_mark(ctx, 0);
-    S3G_TRY(run_tokenize(ctx, S.base, S.n, S.skip, &S.tr));
+    S3G_TRY(run_tokenize(ctx, S.base, S.n, S.skip, &S.tr, S.halo));
     uint64_t last_flag = 0; uint32_t cont = 0; int64_t tmax = INT64_MIN;
     S3G_TRY(run_range_summary(ctx, S.tr.n_lines, S.halo, &tmax, &last_flag, &cont));
     stage_mark(ctx, -1);
-    if (S.tr.n_lines && ctx->h_scalars[1]) {
-        set_error("%llu malformed BED line(s): fewer than three fields", (unsigned long long)ctx->h_scalars[1]);
-        return S3G_E_MALFORMED;
-    }
     if (S.halo && S.tr.n_lines == 0) { set_error("halo line is not newline-terminated"); return S3G_E_PARAM; }
     out->n_lines = S.tr.n_lines - (S.halo ? 1 : 0);
     out->tail_max = tmax;
     out->continues = cont;
     out->single_piece = last_flag == 0 ? 1u : 0u;
-    out->dropped_tail_bytes = S.tr.n_lines ? S.n - ctx->h_scalars[40] : S.tr.dropped;
+    out->dropped_tail_bytes = S.tr.dropped;
     return S3G_OK;
 }
 

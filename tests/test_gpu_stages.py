@@ -28,9 +28,27 @@ def _beds():
     yield "one", b"chrZ\t0\t1\n"
     yield "manychroms", b"".join(f"s{i}\t{i}\t{i + 3}\tn{i}\n".encode() for i in range(5000))
     yield "longrem", b"chr1\t1\t2\t" + b"x" * 5000 + b"\nchr1\t2\t3\t" + b"y\tz" * 700 + b"\n"
+    # the fused front end walks the input in 8 KiB tiles with the 512 bytes before them staged: lines that end exactly
+    # at, one before and one after a tile boundary; a line longer than two tiles followed by short ones; the shortest
+    # valid lines (2731 of them per tile); chromosome changes at tile boundaries
+    for d in (-1, 0, 1):
+        head = b"chrA\t10\t20\t" + b"q" * (8192 + d - 12 - 1) + b"\n"
+        yield f"tile_edge{d:+d}", head + b"chrA\t15\t30\nchrB\t1\t2\tz\n" + b"chrB\t7\t9\n" * 900
+    yield "verylong", b"c\t1\t5\n" + b"c\t2\t9\t" + b"L" * 20000 + b"\n" + b"".join(f"c\t{i}\t{i + 4}\n".encode() for i in range(10, 3000))
+    yield "tiny_lines", b"\t\t\n" * 9000
+    yield "tiny_changes", b"".join((b"a" if (i // 7) % 2 else b"") + b"\t%d\t%d\n" % (i, i + 1) for i in range(8000))
+    yield "edge_changes", b"".join(f"k{i // 315}\t{i}\t{i + 2}\tabcdefgh\n".encode() for i in range(4000))
 
 
 BEDS = list(_beds())
+
+
+def _num(field):
+    """[sign]digits up to the first other byte, 0 if there are none (the in-domain behaviour of sscanf("%lld"), hpp:306-307)"""
+    import re
+    m = re.match(rb"[+-]?[0-9]*", field)
+    txt = m.group(0)
+    return int(txt) if txt.strip(b"+-") else 0
 
 
 @pytest.mark.parametrize("name,bed", BEDS, ids=[n for n, _ in BEDS])
@@ -43,7 +61,7 @@ def test_tokenize(ctx, oracle, name, bed):
     for i, ln in enumerate(lines):
         f = ln.split(b"\t", 3)
         assert t["line_start"][i] == pos
-        assert t["start"][i] == int(f[1]) and t["stop"][i] == int(f[2])
+        assert t["start"][i] == _num(f[1]) and t["stop"][i] == _num(f[2])
         assert t["rem_off"][i] == (len(ln) - len(f[3]) if len(f) == 4 else len(ln))
         assert t["chrom_change"][i] == (1 if f[0] != prev_chr else 0)
         prev_chr = f[0]
@@ -73,6 +91,10 @@ def test_transform_errors(ctx):
     assert e.value.code == -4
     assert ctx.transform(b"") == (b"", [], 0)
     assert ctx.transform(b"no newline") == (b"", [], 10)
+    for bad in (b"\n" * 10000, b"chr1\t1\t2\n" * 2000 + b"chr1\t5\n" + b"chr1\t7\t8\n" * 2000, b"a\tb\n"):
+        with pytest.raises(s3.Starch3Error) as e:
+            ctx.transform(bad)
+        assert e.value.code == -4
 
 
 def _streams():
@@ -173,6 +195,32 @@ def _finisher_blocks():
 
 @pytest.mark.parametrize("name,blk", list(_finisher_blocks()), ids=[n for n, _ in _finisher_blocks()])
 def test_bwt_finisher_limits_and_fallback(ctx, oracle, name, blk):
+    (ptr, orig), = ctx.bwt([blk])
+    optr, oorig = oracle.bwt(blk)
+    assert orig == oorig, name
+    assert np.array_equal(ptr, optr), name
+
+
+def _periodic_blocks():
+    """Blocks that are a power of a shorter string: equal rotations tie and origPtr (and the order inside the ties) is
+    whatever fallbackSort leaves (bz/blocksort.c:212-329), replayed by k_fallback_exact -- one thread per non-uniform
+    bucket of a round.  Short periods (all buckets uniform after the first round), long periods over small and large
+    alphabets (rounds that really sort), a full-size block."""
+    rng = np.random.default_rng(3)
+    yield "p2", b"5\n" * 3000
+    yield "p2_big", b"5\n" * 400000
+    yield "p7", b"p20\n5\n\n" * 20000
+    yield "p1", b"x" * 100000
+    yield "ab", b"ab" * 6000
+    yield "allbytes", bytes(range(256)) * 40
+    yield "text1000", bytes(rng.integers(97, 123, 1000, dtype=np.uint8)) * 300
+    yield "bits5000", bytes(rng.integers(48, 50, 5000, dtype=np.uint8)) * 60
+    yield "bedlike", b"".join(b"%d\tid-%d\t%d\t+\n" % (i * 7 % 50, i, i * 13 % 1000) for i in range(40)) * 200
+    yield "small", b"abcab" * 7
+
+
+@pytest.mark.parametrize("name,blk", list(_periodic_blocks()), ids=[n for n, _ in _periodic_blocks()])
+def test_bwt_periodic_blocks(ctx, oracle, name, blk):
     (ptr, orig), = ctx.bwt([blk])
     optr, oorig = oracle.bwt(blk)
     assert orig == oorig, name
