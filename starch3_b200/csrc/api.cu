@@ -83,7 +83,7 @@ static DevBuf *const *all_bufs(Ctx *c, size_t *n)
     size_t k = 0;
 #define B(x) list[k++] = &c->x
     B(bed); B(tile_cnt); B(line_start); B(start); B(stop); B(rem_off); B(flags); B(chrom_first);
-    B(scan_a); B(scan_b); B(scalars); B(tf); B(chroms); B(stat_b); B(soff);
+    B(scan_a); B(scan_b); B(scan_c); B(scalars); B(tf); B(chroms); B(stat_b); B(soff);
     B(rle_carry); B(rle_ebase); B(blocks); B(blk_prov); B(blk_bytes); B(in_use); B(seq_map); B(stream_tab);
     B(sa); B(rk); B(kv0); B(kv1); B(hist); B(bwt_misc); B(bwt_ghist); B(lcol);
     B(mtf0); B(mtfv16); B(mtf_freq); B(ztiles); B(bits); B(pool); B(pool_woff); B(streams); B(stream_meta);

@@ -100,7 +100,7 @@ struct Ctx {
     uint64_t *h_scalars = nullptr;   // 64 x u64
     // stage buffers (grow-only)
     DevBuf bed, tile_cnt, line_start, start, stop, rem_off, flags, chrom_first;
-    DevBuf scan_a, scan_b, scalars;
+    DevBuf scan_a, scan_b, scan_c, scalars;
     DevBuf tf, chroms, stat_b, soff;
     // what run_tokenize measured (tokenize_transform.cu): inputs of run_transform_rest / run_range_summary
     uint32_t front_halo = 0, front_skip = 0, front_line1_flag = 0;

@@ -10,33 +10,37 @@
 //
 // The per-line dependencies are radius-1 (previous stop, previous length, previous chromosome); everything
 // else is prefix sums (output offsets, line and chromosome indices) and one segmented running maximum
-// (unique bases).  Nothing per line is kept in HBM: the input is read twice, in tiles of 8 KiB, and only the
-// transformed bytes are written.
+// (unique bases).  Nothing per line is kept in HBM: the input is read twice and only the transformed bytes
+// are written.  The unit of work is a CHUNK of 2 KiB handled by ONE WARP, which owns the lines that END in
+// the chunk; warps never wait for each other inside a pass (no block barrier in the line loops).
 //
-//   k_front_measure  a tile owns the lines that END in it.  It stages its bytes (plus the 512 bytes before
-//                    them) in shared memory with 16-byte loads, builds newline and tab bit masks, parses its
-//                    lines (a thread per line, fields found in the tab mask), and reduces
-//                    {lines, output bytes, chromosome starts, running max of stop}.  The exclusive prefix of
-//                    every tile comes from a decoupled look-back over the earlier tiles in the same launch.
-//   k_front_write    the same tile walk with the prefix known: formats the transformed lines into shared
-//                    memory at the destination's 16-byte phase and stores them as aligned vectors; chromosome
-//                    table seeds, per-chromosome sums (one atomic per tile), optionally the per-line arrays
-//                    (the s3g_tokenize parity entry point).
+//   k_front_measure  lane l loads bytes [64 l, 64 l + 64) of the chunk as four 16-byte vectors and turns them
+//                    into a newline and a tab bit mask; the newline offsets become the warp's line list, the tab
+//                    masks (plus those of the 256 bytes before the chunk) let a lane find the fields of its line
+//                    without touching the bytes.  32 lines per round, a lane per line: integer parse,
+//                    chromosome test against the line before, output length; warp reductions give the chunk's
+//                    {lines, output bytes, chromosome starts, running max of stop}.  The eight chunks of a CTA
+//                    are combined once at its end.
+//   k_front_scan     exclusive scan of the per-tile aggregates (one CTA; 40 bytes per 16 KiB of input).
+//   k_front_write    the same walk with the prefix known: formats the transformed lines into the warp's strip of
+//                    shared memory at the destination's 16-byte phase and stores them as aligned vectors;
+//                    chromosome table seeds, per-chromosome sums (one atomic pair per chunk, spread over 32
+//                    slots), optionally the per-line arrays (the s3g_tokenize parity entry point).
 //   k_chrom_finish   chromosome table from the seeds and sums.
 #include "common.cuh"
 #include "scan.cuh"
 
 namespace s3g {
 
-constexpr int FT = 8192;                 // input bytes per tile
-constexpr int FBACK = 512;               // staged bytes before the tile (the line that ends before it, and the one before)
-constexpr int FTH = 256;                 // threads per tile
-constexpr int FSTAGE = FBACK + FT;
-constexpr int FMAXL = FT / 3 + 2;        // a line with three fields has at least 3 bytes ("\t\t\n")
-constexpr int FOBUF = FT + 2048;         // staged output bytes of a tile (more: direct stores)
+constexpr int FCH = 2048;                // input bytes per chunk (one warp)
+constexpr int FWARPS = 8;                // chunks per CTA ("tile": 16 KiB)
+constexpr int FTH = FWARPS * 32;
+constexpr int FBACK = 256;               // bytes before the chunk whose tabs and newlines are in the masks too
+constexpr int FMAXL = FCH / 3 + 2;       // a line with three fields has at least 3 bytes ("\t\t\n")
+constexpr int FOB = FCH + 512;           // staged output bytes of a chunk (more: direct stores)
 
 // scalar slots (ctx->scalars, u64 each)
-enum { SC_MALFORMED = 1, SC_LASTNL = 2, SC_LINE1 = 3, SC_TICKET = 4, SC_ERROR = 5, SC_TOTAL = 8 /* FAgg: 5 slots */ };
+enum { SC_MALFORMED = 1, SC_LASTNL = 2, SC_LINE1 = 3, SC_TOTAL = 8 /* FAgg: 5 slots */ };
 
 // what a tile (or a prefix of tiles) contributes; fagg_op is associative, operands in input order
 struct FAgg {
@@ -74,9 +78,9 @@ __device__ __forceinline__ unsigned eq_mask16(const uint32_t w[4], uint32_t pat)
     unsigned m = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        unsigned b = __vcmpeq4(w[q], pat) & 0x01010101u;
-        b = (b | (b >> 7) | (b >> 14) | (b >> 21)) & 0xfu;
-        m |= b << (4 * q);
+        const uint32_t t = w[q] ^ pat;                                             // zero byte <=> equal
+        const uint32_t z = ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu);  // 0x80 in every zero byte, exact
+        m |= (((z >> 7) * 0x01020408u) >> 24) << (4 * q);                          // bits 0, 8, 16, 24 -> bits 0..3
     }
     return m;
 }
@@ -114,18 +118,16 @@ __device__ __forceinline__ uint32_t put_dec(uint8_t *dst, int64_t v)
     return k + nd;
 }
 
-// ---- one tile's view of the input -------------------------------------------------------------------
-struct TileSh {
-    __align__(16) uint8_t buf[FSTAGE];       // bytes [lo, lo + FSTAGE)
-    uint32_t nlw[FSTAGE / 32];               // newline bits, bit i of word w <=> byte lo + 32 w + i
-    uint32_t tbw[FSTAGE / 32];               // tab bits
-    uint16_t nl[FMAXL];                      // newlines inside the tile, offsets from tile0, ascending
-    int64_t st[FTH], sp[FTH];                // start / stop of the lines of the current round
-    uint32_t sum_a[33], sum_b[33];
-    SegMax seg_sm[FTH / 32];
-    uint64_t lo, tile0, start0, prev_start;
-    int64_t carry_start, carry_stop;         // start / stop of the line before the current round
-    uint32_t k, has_prev, has_prev2, tile;
+// ---- one chunk as its warp sees it ---------------------------------------------------------------------
+struct WarpSh {
+    uint64_t tb[FBACK / 64 + FCH / 64];      // tab masks: entry q covers bytes [chunk0 - FBACK + 64 q, + 64)
+    uint16_t nl[FMAXL + 2];                  // newlines inside the chunk, offsets from chunk0, ascending
+};
+struct ChunkGeom {                           // the same in every lane
+    uint64_t chunk0, start0, prev_start;     // start0: where the chunk's first line starts; prev_start: the line before it
+    int64_t mask_lo;                         // position of bit 0 of tb[0]
+    uint64_t n;                              // bytes of the buffer
+    uint32_t k, has_prev, has_prev2;         // k: lines that end in the chunk
 };
 
 struct Parsed {
@@ -133,50 +135,82 @@ struct Parsed {
     uint32_t rem_off, name_len, malformed;
 };
 
-// sscanf("%lld") over the documented domain (hpp:306-307): [sign] digits, up to the first other byte
-__device__ __forceinline__ int64_t parse_int(const uint8_t *p, uint32_t len)
+// eight bytes starting at position p (little endian: the byte at p is the lowest); needs [p & ~7, (p & ~7) + 16) readable
+__device__ __forceinline__ uint64_t load8(const uint8_t *__restrict__ bed, uint64_t p)
 {
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(bed + (p & ~7ull));
+    const uint64_t lo = q[0], hi = q[1];
+    const uint32_t sh = (uint32_t)(p & 7) * 8;
+    return sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+}
+// the decimal number in the `len` (1..8) HIGH bytes of x (string order = memory order), or false if one of them is not a digit
+__device__ __forceinline__ bool swar_digits(uint64_t x, uint32_t len, uint64_t *val)
+{
+    const uint32_t drop = 8 * (8 - len);
+    x = drop ? ((x >> drop) << drop) | (0x3030303030303030ull >> (64 - drop)) : x;      // the bytes before the number become '0'
+    const uint64_t d = x - 0x3030303030303030ull;
+    if (((d + 0x7676767676767676ull) | d | x) & 0x8080808080808080ull) return false;    // a byte outside '0'..'9'
+    uint64_t v = (d * 2561ull) >> 8;                                                     // pairs: 10 a + b
+    v = ((v & 0x00ff00ff00ff00ffull) * 6553601ull) >> 16;                                // 100 ab + cd
+    v = ((v & 0x0000ffff0000ffffull) * 42949672960001ull) >> 32;                         // 10000 abcd + efgh
+    *val = v;
+    return true;
+}
+// sscanf("%lld") over the documented domain (hpp:306-307): [sign] digits, up to the first other byte.  The field is
+// bed[a, b); n = bytes of the buffer.  Fields of up to 16 digits are converted eight bytes at a time.
+__device__ __forceinline__ int64_t parse_int(const uint8_t *__restrict__ bed, uint64_t n, uint64_t a, uint64_t b)
+{
+    if (a >= b) return 0;
+    int neg = 0;
+    const uint8_t c0 = bed[a];
+    if (c0 == '-' || c0 == '+') { neg = c0 == '-'; a++; }
+    const uint32_t len = (uint32_t)(b - a);
+    if (len >= 1 && len <= 16 && b >= 16 && ((b + 7) & ~7ull) + 8 <= n) {
+        uint64_t lo, hi = 0;
+        const uint32_t l8 = len > 8 ? 8 : len;
+        bool ok = swar_digits(load8(bed, b - 8), l8, &lo);
+        if (ok && len > 8) ok = swar_digits(load8(bed, b - 16), len - 8, &hi);
+        if (ok) {
+            const uint64_t acc = hi * 100000000ull + lo;
+            return neg ? (int64_t)(0 - acc) : (int64_t)acc;
+        }
+    }
     uint64_t acc = 0;
-    int neg = 0, st = 0;                      // 0 = expecting sign/digit, 1 = in digits
-    for (uint32_t i = 0; i < len; i++) {
-        uint8_t c = p[i];
-        if (st == 0 && (c == '-' || c == '+')) { neg = (c == '-'); st = 1; }
-        else if (c >= '0' && c <= '9') { acc = acc * 10 + (uint64_t)(c - '0'); st = 1; }
-        else break;
+    for (uint64_t i = a; i < b; i++) {
+        uint32_t d = (uint32_t)bed[i] - '0';
+        if (d > 9u) break;
+        acc = acc * 10 + d;
     }
     return neg ? (int64_t)(0 - acc) : (int64_t)acc;
 }
 
-// first tab in [p, e) of the staged bytes, or e
-__device__ __forceinline__ uint64_t next_tab(const TileSh &S, uint64_t p, uint64_t e)
+// first tab in [p, e), or e; p at or after the first masked byte
+__device__ __forceinline__ uint64_t next_tab(const WarpSh &W, int64_t mask_lo, uint64_t p, uint64_t e)
 {
     if (p >= e) return e;
-    uint32_t i = (uint32_t)(p - S.lo), iend = (uint32_t)(e - S.lo);
-    uint32_t w = i >> 5;
-    uint32_t m = S.tbw[w] & (0xffffffffu << (i & 31));
+    uint32_t i = (uint32_t)((int64_t)p - mask_lo), iend = (uint32_t)((int64_t)e - mask_lo);
+    uint32_t w = i >> 6;
+    uint64_t m = W.tb[w] & (~0ull << (i & 63));
     while (m == 0) {
         w++;
-        if ((w << 5) >= iend) return e;
-        m = S.tbw[w];
+        if ((w << 6) >= iend) return e;
+        m = W.tb[w];
     }
-    uint32_t q = (w << 5) + (uint32_t)__ffs((int)m) - 1;
-    return q < iend ? S.lo + q : e;
+    uint32_t q = (w << 6) + (uint32_t)__ffsll((long long)m) - 1;
+    return q < iend ? (uint64_t)(mask_lo + q) : e;
 }
 
 // line [s, e), bed[e] == '\n'; fields as consume_line finds them (hpp:220-309)
-__device__ __forceinline__ Parsed parse_line(const TileSh &S, const uint8_t *bed, uint64_t s, uint64_t e)
+__device__ __forceinline__ Parsed parse_line(const WarpSh &W, const ChunkGeom &G, const uint8_t *__restrict__ bed, uint64_t s, uint64_t e)
 {
     Parsed P;
     P.start = 0; P.stop = 0; P.malformed = 0;
     uint64_t t1, t2, t3;
-    const uint8_t *src;                                // src[p - off] = byte at absolute position p
-    uint64_t off;
-    if (s >= S.lo) {                                   // staged: tabs from the bit mask
-        t1 = next_tab(S, s, e);
-        t2 = t1 < e ? next_tab(S, t1 + 1, e) : e;
-        t3 = t2 < e ? next_tab(S, t2 + 1, e) : e;
-        src = S.buf; off = S.lo;
-    } else {                                           // a line longer than the staged window: bytes from global memory
+    if ((int64_t)s >= G.mask_lo) {                     // tabs from the bit masks
+        t1 = next_tab(W, G.mask_lo, s, e);
+        t2 = t1 < e ? next_tab(W, G.mask_lo, t1 + 1, e) : e;
+        t3 = t2 < e ? next_tab(W, G.mask_lo, t2 + 1, e) : e;
+    } else {                                           // a line that starts before the masked bytes
         uint64_t q = s;
         while (q < e && bed[q] != '\t') q++;
         t1 = q;
@@ -184,28 +218,21 @@ __device__ __forceinline__ Parsed parse_line(const TileSh &S, const uint8_t *bed
         t2 = q;
         if (q < e) { q++; while (q < e && bed[q] != '\t') q++; }
         t3 = q;
-        src = bed; off = 0;
     }
     P.name_len = (uint32_t)(t1 - s);
     if (t2 >= e) {                                     // fewer than three fields
         P.malformed = 1;
-        P.name_len = (uint32_t)((t1 < e ? t1 : e) - s);
         P.rem_off = (uint32_t)(e - s);
         return P;
     }
-    P.start = parse_int(src + (t1 + 1 - off), (uint32_t)(t2 - t1 - 1));
-    P.stop = parse_int(src + (t2 + 1 - off), (uint32_t)(t3 - t2 - 1));
+    P.start = parse_int(bed, G.n, t1 + 1, t2);
+    P.stop = parse_int(bed, G.n, t2 + 1, t3);
     P.rem_off = (uint32_t)((t3 < e ? t3 + 1 : e) - s);
     return P;
 }
 
-__device__ __forceinline__ uint8_t byte_at(const TileSh &S, const uint8_t *bed, uint64_t pos)
-{
-    return pos >= S.lo ? S.buf[pos - S.lo] : bed[pos];
-}
-
 // largest p in [floor, hi) with bed[p] == '\n', or -1; one warp
-__device__ __forceinline__ int64_t scan_back(const uint8_t *bed, uint64_t hi, uint64_t floor)
+__device__ __forceinline__ int64_t scan_back(const uint8_t *__restrict__ bed, uint64_t hi, uint64_t floor)
 {
     const unsigned l = threadIdx.x & 31;
     while (hi > floor) {
@@ -218,126 +245,138 @@ __device__ __forceinline__ int64_t scan_back(const uint8_t *bed, uint64_t hi, ui
     return -1;
 }
 
-// stage the tile, build the masks, list its newlines, find where its first line and the line before it start
-__device__ __forceinline__ void tile_setup(TileSh &S, const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t tile)
+// 64 bytes -> newline and tab masks (bit i <=> byte i)
+__device__ __forceinline__ void masks64(const uint8_t *__restrict__ bed, uint64_t n, uint64_t pos, uint64_t *nlm, uint64_t *tbm)
 {
-    const uint64_t tile0 = (uint64_t)tile * FT;
-    const uint32_t back = tile ? FBACK : 0;
-    const uint64_t lo = tile0 - back;
-    if (threadIdx.x == 0) { S.lo = lo; S.tile0 = tile0; S.tile = tile; }
-    uint16_t *nl16 = reinterpret_cast<uint16_t *>(S.nlw), *tb16 = reinterpret_cast<uint16_t *>(S.tbw);
-    for (uint32_t c = threadIdx.x; c < (back + FT) / 16; c += FTH) {
-        uint64_t pos = lo + 16ull * c;
+    uint64_t mn = 0, mt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint64_t p = pos + 16ull * q;
         uint32_t w[4] = {0, 0, 0, 0};
-        if (pos + 16 <= n) {
-            uint4 v = *reinterpret_cast<const uint4 *>(bed + pos);
+        if (p + 16 <= n) {
+            uint4 v = *reinterpret_cast<const uint4 *>(bed + p);
             w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        } else if (pos < n) {
-            for (uint32_t k = 0; k < (uint32_t)(n - pos); k++) w[k >> 2] |= (uint32_t)bed[pos + k] << (8 * (k & 3));
-        }
-        *reinterpret_cast<uint4 *>(S.buf + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
-        unsigned mn = eq_mask16(w, 0x0a0a0a0au), mt = eq_mask16(w, 0x09090909u);
-        if (pos < skip) mn &= 0xffffffffu << (skip - (uint32_t)pos);     // the bytes before the range: not ours (skip < 16)
-        nl16[c] = (uint16_t)mn; tb16[c] = (uint16_t)mt;
-    }
-    __syncthreads();
-    // newlines inside the tile -> compact list
-    {
-        uint32_t w = S.nlw[back / 32 + threadIdx.x];
-        uint32_t tot;
-        uint32_t ex = block_excl_sum<uint32_t>(__popc(w), S.sum_a, &tot);
-        while (w) {
-            int b = __ffs((int)w) - 1;
-            w &= w - 1;
-            if (ex < FMAXL) S.nl[ex] = (uint16_t)(threadIdx.x * 32 + b);
-            ex++;
-        }
-        if (threadIdx.x == 0) S.k = tot;
-    }
-    // the last two newlines before the tile
-    if (threadIdx.x < 32) {
-        const unsigned l = threadIdx.x;
-        int64_t nl1 = -1, nl2 = -1;
-        if (tile) {
-            uint32_t w = l < FBACK / 32 ? S.nlw[l] : 0;
-            unsigned nz = __ballot_sync(0xffffffffu, w != 0);
-            if (nz) {
-                int hl = 31 - __clz((int)nz);
-                uint32_t hw = __shfl_sync(0xffffffffu, w, hl);
-                int hb = 31 - __clz((int)hw);
-                nl1 = (int64_t)(lo + (uint64_t)hl * 32 + hb);
-                uint32_t hw2 = hw & ~(1u << hb);
-                unsigned nz2 = nz & ~(1u << hl);
-                if (hw2) nl2 = (int64_t)(lo + (uint64_t)hl * 32 + (31 - __clz((int)hw2)));
-                else if (nz2) {
-                    int hl2 = 31 - __clz((int)nz2);
-                    uint32_t w2 = __shfl_sync(0xffffffffu, w, hl2);
-                    nl2 = (int64_t)(lo + (uint64_t)hl2 * 32 + (31 - __clz((int)w2)));
-                }
-                if (nl2 < 0) nl2 = scan_back(bed, lo, skip);
-            } else {
-                nl1 = scan_back(bed, lo, skip);
-                if (nl1 >= 0) nl2 = scan_back(bed, (uint64_t)nl1, skip);
+        } else if (p < n) {
+            for (uint32_t k = 0; k < (uint32_t)(n - p); k++) {
+                uint32_t by = (uint32_t)bed[p + k] << (8 * (k & 3));
+                if ((k >> 2) == 0) w[0] |= by; else if ((k >> 2) == 1) w[1] |= by; else if ((k >> 2) == 2) w[2] |= by; else w[3] |= by;
             }
         }
-        if (l == 0) {
-            S.has_prev = nl1 >= 0; S.has_prev2 = nl2 >= 0;
-            S.start0 = nl1 >= 0 ? (uint64_t)nl1 + 1 : skip;
-            S.prev_start = nl2 >= 0 ? (uint64_t)nl2 + 1 : skip;
-        }
+        mn |= (uint64_t)eq_mask16(w, 0x0a0a0a0au) << (16 * q);
+        mt |= (uint64_t)eq_mask16(w, 0x09090909u) << (16 * q);
     }
-    __syncthreads();
-    // start / stop of the line before the tile's first line: what its first line's deltas refer to
-    if (threadIdx.x == 0) {
-        S.carry_start = 0; S.carry_stop = 0;
-        if (S.has_prev) {
-            Parsed P = parse_line(S, bed, S.prev_start, S.start0 - 1);
-            S.carry_start = P.start; S.carry_stop = P.stop;
-        }
-    }
-    __syncthreads();
+    *nlm = mn; *tbm = mt;
 }
 
-// what a line contributes, given the line before it
+// masks, line list, and where the chunk's first line and the line before it start; all lanes of the warp
+__device__ __forceinline__ void chunk_setup(WarpSh &W, ChunkGeom &G, const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint64_t chunk)
+{
+    const unsigned l = threadIdx.x & 31;
+    const uint64_t chunk0 = chunk * FCH;
+    G.chunk0 = chunk0; G.n = n;
+    G.mask_lo = (int64_t)chunk0 - FBACK;
+    G.k = 0; G.has_prev = 0; G.has_prev2 = 0; G.start0 = skip; G.prev_start = skip;
+    if (chunk0 >= n) return;
+    uint64_t mn, mt;
+    masks64(bed, n, chunk0 + 64ull * l, &mn, &mt);
+    if (chunk == 0 && 64u * l < skip) mn &= ~0ull << skip;                 // the bytes before the range: not ours (skip < 16)
+    W.tb[FBACK / 64 + l] = mt;
+    int64_t nl1 = -1, nl2 = -1;
+    if (chunk) {
+        // the 256 bytes before the chunk: tab masks for the lines that start there, and the last two newlines
+        uint64_t bn = 0, bt = 0;
+        if (l < FBACK / 64) { masks64(bed, n, chunk0 - FBACK + 64ull * l, &bn, &bt); W.tb[l] = bt; }
+        unsigned nz = __ballot_sync(0xffffffffu, bn != 0);
+        if (nz) {
+            int hl = 31 - __clz((int)nz);
+            uint64_t hw = __shfl_sync(0xffffffffu, bn, hl);
+            int hb = 63 - __clzll((long long)hw);
+            nl1 = (int64_t)(chunk0 - FBACK + 64ull * hl + hb);
+            uint64_t hw2 = hw & ~(1ull << hb);
+            unsigned nz2 = nz & ~(1u << hl);
+            if (hw2) nl2 = (int64_t)(chunk0 - FBACK + 64ull * hl + (63 - __clzll((long long)hw2)));
+            else if (nz2) {
+                int hl2 = 31 - __clz((int)nz2);
+                uint64_t w2 = __shfl_sync(0xffffffffu, bn, hl2);
+                nl2 = (int64_t)(chunk0 - FBACK + 64ull * hl2 + (63 - __clzll((long long)w2)));
+            }
+            if (nl2 < 0) nl2 = scan_back(bed, chunk0 - FBACK, skip);
+        } else {
+            nl1 = scan_back(bed, chunk0 - FBACK, skip);
+            if (nl1 >= 0) nl2 = scan_back(bed, (uint64_t)nl1, skip);
+        }
+    }
+    // the chunk's newlines -> compact list
+    uint32_t c = (uint32_t)__popcll((long long)mn);
+    uint32_t inc = warp_incl_sum<uint32_t>(c);
+    uint32_t ex = inc - c;
+    G.k = __shfl_sync(0xffffffffu, inc, 31);
+    while (mn) {
+        int b = __ffsll((long long)mn) - 1;
+        mn &= mn - 1;
+        if (ex < FMAXL) W.nl[ex] = (uint16_t)(64 * l + b);
+        ex++;
+    }
+    G.has_prev = nl1 >= 0; G.has_prev2 = nl2 >= 0;
+    G.start0 = nl1 >= 0 ? (uint64_t)nl1 + 1 : skip;
+    G.prev_start = nl2 >= 0 ? (uint64_t)nl2 + 1 : skip;
+    __syncwarp();
+}
+
+// what a lane holds in a round.  Item v = 32 * round + lane of a chunk: v = 0 is the line BEFORE the chunk's first line (it
+// only hands its start, stop and name on), v = 1 .. k are the chunk's lines.
 struct LineOut {
     uint64_t s, e;
     Parsed P;
+    uint32_t owned;         // one of the chunk's lines
     uint32_t flag;          // chromosome differs from the previous line (hpp:331), or first line of the input
     uint32_t first_global;  // first line of the input
     uint32_t out_len;
     int64_t pstop, plen;
 };
 
-// round `base`: thread t takes the tile's line base + t
-__device__ __forceinline__ bool line_of_round(TileSh &S, const uint8_t *bed, uint32_t base, uint32_t halo, LineOut &L)
+// carry_*: start / stop of the last item of the round before (in/out); every lane of the warp calls
+__device__ __forceinline__ void line_of_round(const WarpSh &W, const ChunkGeom &G, const uint8_t *__restrict__ bed, uint32_t round, uint32_t halo,
+                                              int64_t &carry_start, int64_t &carry_stop, LineOut &L)
 {
-    const uint32_t j = base + threadIdx.x;
-    const bool act = j < S.k;
+    const unsigned l = threadIdx.x & 31;
+    const uint32_t v = round * 32 + l;
+    const bool act = v <= G.k && (v >= 1 || G.has_prev);
+    L.owned = act && v >= 1;
     L.flag = 0; L.first_global = 0; L.out_len = 0; L.pstop = 0; L.plen = 0;
     L.P.start = 0; L.P.stop = 0; L.P.rem_off = 0; L.P.name_len = 0; L.P.malformed = 0; L.s = 0; L.e = 0;
     if (act) {
-        L.s = j == 0 ? S.start0 : S.tile0 + S.nl[j - 1] + 1;
-        L.e = S.tile0 + S.nl[j];
-        L.P = parse_line(S, bed, L.s, L.e);
-        L.first_global = (j == 0 && !S.has_prev) ? 1u : 0u;
-        if (L.first_global) L.flag = 1;
+        if (v == 0) { L.s = G.prev_start; L.e = G.start0 - 1; }
         else {
-            // strcmp(chr, previous chr) != 0 (hpp:331); the previous line's field ends at its first tab
-            uint64_t ps = j == 0 ? S.prev_start : (j == 1 ? S.start0 : S.tile0 + S.nl[j - 2] + 1);
-            uint32_t cl = L.P.name_len;
-            bool diff = false;
-            for (uint32_t q = 0; q < cl; q++)
-                if (byte_at(S, bed, L.s + q) != byte_at(S, bed, ps + q)) { diff = true; break; }
-            if (!diff && byte_at(S, bed, ps + cl) != '\t') diff = true;
-            L.flag = diff ? 1u : 0u;
+            L.s = v == 1 ? G.start0 : G.chunk0 + W.nl[v - 2] + 1;
+            L.e = G.chunk0 + W.nl[v - 1];
         }
-        S.st[threadIdx.x] = L.P.start; S.sp[threadIdx.x] = L.P.stop;
+        L.P = parse_line(W, G, bed, L.s, L.e);
+        if (v >= 1) {
+            L.first_global = (v == 1 && !G.has_prev) ? 1u : 0u;
+            if (L.first_global) L.flag = 1;
+            else {
+                // strcmp(chr, previous chr) != 0 (hpp:331); the previous line's field ends at its first tab
+                const uint64_t ps = v == 1 ? G.prev_start : (v == 2 ? G.start0 : G.chunk0 + W.nl[v - 3] + 1);
+                const uint32_t cl = L.P.name_len;
+                bool diff = false;
+                if (cl < 8 && ((L.s + 7) & ~7ull) + 16 <= G.n && !L.P.malformed) {
+                    // name and the tab that ends it, both lines, eight bytes at once
+                    const uint64_t x = load8(bed, L.s) ^ load8(bed, ps);
+                    diff = (x << (8 * (7 - cl))) != 0;
+                } else {
+                    for (uint32_t q = 0; q < cl; q++)
+                        if (bed[L.s + q] != bed[ps + q]) { diff = true; break; }
+                    if (!diff && bed[ps + cl] != '\t') diff = true;
+                }
+                L.flag = diff ? 1u : 0u;
+            }
+        }
     }
-    __syncthreads();
-    if (act) {
-        int64_t a, b;
-        if (threadIdx.x == 0) { a = S.carry_start; b = S.carry_stop; }
-        else { a = S.st[threadIdx.x - 1]; b = S.sp[threadIdx.x - 1]; }
+    int64_t a = __shfl_up_sync(0xffffffffu, L.P.start, 1), b = __shfl_up_sync(0xffffffffu, L.P.stop, 1);
+    if (l == 0) { a = carry_start; b = carry_stop; }
+    carry_start = __shfl_sync(0xffffffffu, L.P.start, 31); carry_stop = __shfl_sync(0xffffffffu, L.P.stop, 31);
+    if (L.owned) {
         if (!L.flag) { L.pstop = b; L.plen = (int64_t)((uint64_t)b - (uint64_t)a); }      // hpp:523-532 resets both at a chromosome start
         int64_t len = (int64_t)((uint64_t)L.P.stop - (uint64_t)L.P.start), d = (int64_t)((uint64_t)L.P.start - (uint64_t)L.pstop);
         uint32_t rem_len = (uint32_t)(L.e - L.s) - L.P.rem_off;
@@ -345,139 +384,124 @@ __device__ __forceinline__ bool line_of_round(TileSh &S, const uint8_t *bed, uin
         if (len != L.plen) o += 2 + (uint32_t)dec_len(len);
         L.out_len = (halo && L.first_global) ? 0 : o;     // the halo line hands over its stop, length and chromosome only
     }
-    return act;
 }
-// after the scans of a round (they synchronise): the round's last line becomes the carry
-__device__ __forceinline__ void round_carry(TileSh &S, uint32_t base, const LineOut &L)
+
+// inclusive segmented max over the lanes (a set flag restarts the maximum); returns the lane's (v, f) with f = a flag at or before it
+__device__ __forceinline__ void warp_segmax_incl(int64_t &v, uint32_t &f)
 {
-    if (threadIdx.x == FTH - 1 && base + FTH - 1 < S.k) { S.carry_start = L.P.start; S.carry_stop = L.P.stop; }
+    const unsigned l = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int64_t ov = __shfl_up_sync(0xffffffffu, v, d);
+        uint32_t of = __shfl_up_sync(0xffffffffu, f, d);
+        if (l >= (unsigned)d) { if (!f) { v = ov > v ? ov : v; f = of; } }
+    }
 }
 
 // ---- pass 1 -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_agg(FAgg *dst, const FAgg &a)
+__global__ void __launch_bounds__(FTH) k_front_measure(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo,
+                                                       FAgg *__restrict__ tile_agg, FAgg *__restrict__ chunk_pre, uint32_t *__restrict__ chunk_out,
+                                                       unsigned long long *sc)
 {
-    volatile uint64_t *d = reinterpret_cast<volatile uint64_t *>(dst);
-    d[0] = a.lines; d[1] = a.out; d[2] = a.chroms; d[3] = (uint64_t)a.v; d[4] = (uint64_t)a.seg;
-}
-__device__ __forceinline__ FAgg load_agg(const FAgg *src)
-{
-    const volatile uint64_t *s = reinterpret_cast<const volatile uint64_t *>(src);
-    FAgg a;
-    a.lines = s[0]; a.out = s[1]; a.chroms = s[2]; a.v = (int64_t)s[3]; a.seg = (uint32_t)s[4]; a.pad = 0;
-    return a;
-}
-__device__ __forceinline__ FAgg shfl_down_agg(const FAgg &a, int d)
-{
-    FAgg r;
-    r.lines = __shfl_down_sync(0xffffffffu, a.lines, d); r.out = __shfl_down_sync(0xffffffffu, a.out, d);
-    r.chroms = __shfl_down_sync(0xffffffffu, a.chroms, d); r.v = __shfl_down_sync(0xffffffffu, a.v, d);
-    r.seg = __shfl_down_sync(0xffffffffu, a.seg, d); r.pad = 0;
-    return r;
+    __shared__ WarpSh Ws[FWARPS];
+    __shared__ FAgg s_agg[FWARPS];
+    __shared__ unsigned long long s_lastnl[FWARPS];
+    __shared__ uint32_t s_mal[FWARPS];
+    const unsigned l = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t chunk = (uint64_t)blockIdx.x * FWARPS + wid;
+    WarpSh &W = Ws[wid];
+    ChunkGeom G;
+    chunk_setup(W, G, bed, n, skip, chunk);
+    FAgg A = fagg_identity();
+    A.lines = G.k;
+    uint32_t malformed = 0;
+    if (G.k > FMAXL) malformed = 1;                        // lines shorter than three bytes
+    else if (G.k) {
+        int64_t cs = 0, ce = 0;
+        const uint32_t rounds = (G.k + 1 + 31) / 32;
+        for (uint32_t r = 0; r < rounds; r++) {
+            LineOut L;
+            line_of_round(W, G, bed, r, halo, cs, ce, L);
+            uint32_t tot_out = __reduce_add_sync(0xffffffffu, L.out_len);
+            unsigned mflag = __ballot_sync(0xffffffffu, L.flag != 0);
+            malformed |= __any_sync(0xffffffffu, L.owned && L.P.malformed) ? 1u : 0u;
+            int64_t v = L.owned ? ((halo && L.first_global) ? INT64_MIN : L.P.stop) : INT64_MIN;
+            uint32_t f = L.flag;
+            warp_segmax_incl(v, f);
+            FAgg R; R.lines = 0; R.out = tot_out; R.chroms = __popc(mflag); R.pad = 0;
+            R.v = __shfl_sync(0xffffffffu, v, 31); R.seg = mflag != 0;
+            A = fagg_op(A, R);
+            // the flag of the input's second line (does the range continue the halo line's chromosome?)
+            const uint32_t vv = r * 32 + l;
+            if (L.owned && ((vv == 2 && !G.has_prev) || (vv == 1 && G.has_prev && !G.has_prev2))) sc[SC_LINE1] = L.flag;
+        }
+    }
+    if (l == 0) {
+        s_agg[wid] = A; s_mal[wid] = malformed;
+        unsigned long long last = 0;
+        if (G.k && G.k <= FMAXL) last = G.chunk0 + W.nl[G.k - 1] + 1;
+        s_lastnl[wid] = last;
+        chunk_out[chunk] = (uint32_t)A.out;
+    }
+    if (G.k > FMAXL) {
+        // the compact list is cut short: the chunk's last newline from the masks
+        uint64_t mn, mt;
+        masks64(bed, n, G.chunk0 + 64ull * l, &mn, &mt);
+        unsigned nz = __ballot_sync(0xffffffffu, mn != 0);
+        int hl = 31 - __clz((int)nz);
+        uint64_t hw = __shfl_sync(0xffffffffu, mn, hl);
+        if (l == 0) s_lastnl[wid] = G.chunk0 + 64ull * hl + (63 - __clzll((long long)hw)) + 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        FAgg run = fagg_identity();
+        unsigned long long last = 0; uint32_t mal = 0;
+        for (int w = 0; w < FWARPS; w++) {
+            chunk_pre[(uint64_t)blockIdx.x * FWARPS + w] = run;
+            run = fagg_op(run, s_agg[w]);
+            if (s_lastnl[w] > last) last = s_lastnl[w];
+            mal |= s_mal[w];
+        }
+        tile_agg[blockIdx.x] = run;
+        if (mal) atomicAdd(&sc[SC_MALFORMED], 1ull);
+        if (last) atomicMax(&sc[SC_LASTNL], last);
+    }
 }
 
-// status[tile]: 0 = nothing yet, 1 = agg[tile] valid, 2 = inc[tile] (inclusive prefix) valid
-__global__ void __launch_bounds__(FTH) k_front_measure(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo, uint32_t ntiles,
-                                                       uint32_t *status, FAgg *agg, FAgg *inc, unsigned long long *sc)
+struct FAggF {
+    typedef FAgg T;
+    __host__ __device__ static T identity() { return fagg_identity(); }
+    __host__ __device__ static T op(const T &a, const T &b) { return fagg_op(a, b); }
+};
+
+// exclusive scan of the tile aggregates in two levels: spans of 1024 tiles (a thread per tile), then the span totals.
+// tile t's prefix = span_pre[t / 1024] (+) agg[t]; totals -> sc[SC_TOTAL ..]
+constexpr int FSCAN_T = 1024;
+__global__ void __launch_bounds__(FSCAN_T) k_front_scan_tiles(FAgg *agg, uint64_t ntiles, FAgg *span_tot)
 {
-    __shared__ TileSh S;
-    __shared__ uint32_t s_ticket;
-    // tiles are handed out in launch order, so the tiles a look-back waits for are always running or done
-    if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(&sc[SC_TICKET], 1ull);
-    __syncthreads();
-    const uint32_t tile = s_ticket;
-    tile_setup(S, bed, n, skip, tile);
-    const uint32_t k = S.k;
-    FAgg A = fagg_identity();
-    A.lines = k;
-    uint32_t malformed = 0;
-    if (k > FMAXL) malformed = 1;                          // lines shorter than three bytes
-    else {
-        for (uint32_t base = 0; base < k; base += FTH) {
-            LineOut L;
-            bool act = line_of_round(S, bed, base, halo, L);
-            uint32_t tot_out, tot_ch;
-            block_excl_sum<uint32_t>(L.out_len, S.sum_a, &tot_out);
-            block_excl_sum<uint32_t>(L.flag, S.sum_b, &tot_ch);
-            SegMax mine = SegMaxF::identity();
-            if (act) { mine.v = (halo && L.first_global) ? INT64_MIN : L.P.stop; mine.seg = (int32_t)L.flag; }
-            SegMax tot_seg;
-            block_scan_partials<SegMaxF, FTH>(mine, S.seg_sm, &tot_seg);
-            malformed |= (uint32_t)__syncthreads_or(act && L.P.malformed);
-            // the flag of the input's second line (does the range continue the halo line's chromosome?)
-            if (act) {
-                uint32_t j = base + threadIdx.x;
-                if ((j == 1 && !S.has_prev) || (j == 0 && S.has_prev && !S.has_prev2)) sc[SC_LINE1] = L.flag;
-            }
-            FAgg R; R.lines = 0; R.out = tot_out; R.chroms = tot_ch; R.v = tot_seg.v; R.seg = (uint32_t)tot_seg.seg; R.pad = 0;
-            A = fagg_op(A, R);
-            round_carry(S, base, L);
-        }
+    __shared__ FAgg sm[FSCAN_T / 32];
+    const uint64_t t = (uint64_t)blockIdx.x * FSCAN_T + threadIdx.x;
+    FAgg a = t < ntiles ? agg[t] : fagg_identity();
+    FAgg tot;
+    FAgg ex = block_scan_partials<FAggF, FSCAN_T>(a, sm, &tot);
+    if (t < ntiles) agg[t] = ex;
+    if (threadIdx.x == 0) span_tot[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(FSCAN_T) k_front_scan_spans(FAgg *span, uint64_t nspans, unsigned long long *sc)
+{
+    __shared__ FAgg sm[FSCAN_T / 32];
+    FAgg carry = fagg_identity();
+    for (uint64_t base = 0; base < nspans; base += FSCAN_T) {
+        const uint64_t i = base + threadIdx.x;
+        FAgg a = i < nspans ? span[i] : fagg_identity();
+        FAgg tot;
+        FAgg ex = block_scan_partials<FAggF, FSCAN_T>(a, sm, &tot);
+        if (i < nspans) span[i] = fagg_op(carry, ex);
+        carry = fagg_op(carry, tot);
     }
     if (threadIdx.x == 0) {
-        if (malformed) atomicAdd(&sc[SC_MALFORMED], 1ull);
-        if (k) atomicMax(&sc[SC_LASTNL], (unsigned long long)(S.tile0 + S.nl[(k <= FMAXL ? k : FMAXL) - 1] + 1));
-    }
-    if (k > FMAXL && threadIdx.x == 0) {
-        // the compact list is cut short: the true last newline of the tile comes from the mask
-        uint64_t last = 0;
-        for (int w = FT / 32 - 1; w >= 0; w--) {
-            uint32_t m = S.nlw[(tile ? FBACK : 0) / 32 + w];
-            if (m) { last = S.tile0 + (uint64_t)w * 32 + (31 - __clz((int)m)) + 1; break; }
-        }
-        atomicMax(&sc[SC_LASTNL], (unsigned long long)last);
-    }
-    // ---- decoupled look-back (warp 0) ----
-    if (threadIdx.x < 32) {
-        const unsigned l = threadIdx.x;
-        FAgg excl = fagg_identity();
-        if (tile > 0) {
-            if (l == 0) { store_agg(&agg[tile], A); __threadfence(); *reinterpret_cast<volatile uint32_t *>(&status[tile]) = 1u; }
-            int64_t basei = (int64_t)tile - 1;
-            long long t_begin = clock64();
-            bool failed = false;
-            while (true) {
-                int64_t idx = basei - (int64_t)l;
-                uint32_t f = idx >= 0 ? *reinterpret_cast<volatile uint32_t *>(&status[idx]) : 2u;   // before tile 0: an empty prefix
-                unsigned m2 = __ballot_sync(0xffffffffu, f == 2u), m0 = __ballot_sync(0xffffffffu, f == 0u);
-                int first2 = m2 ? __ffs((int)m2) - 1 : 32;
-                unsigned need = first2 >= 31 ? 0xffffffffu : ((2u << first2) - 1u);
-                if (m0 & need) {
-                    // an earlier tile has not published yet: poll again (bounded: a lost tile must not hang the device)
-                    bool give_up = clock64() - t_begin > 4000000000ll || *reinterpret_cast<volatile unsigned long long *>(&sc[SC_ERROR]) != 0;
-                    if (__any_sync(0xffffffffu, give_up)) { failed = true; break; }
-                    continue;
-                }
-                __threadfence();
-                FAgg p = fagg_identity();
-                if (idx >= 0) {
-                    if ((int)l < first2) p = load_agg(&agg[idx]);
-                    else if ((int)l == first2) p = load_agg(&inc[idx]);
-                }
-                // lane l holds tile basei - l: higher lanes are earlier tiles, so they are the left operand
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    FAgg q = shfl_down_agg(p, d);
-                    if (l + d < 32) p = fagg_op(q, p);
-                }
-                p.lines = __shfl_sync(0xffffffffu, p.lines, 0); p.out = __shfl_sync(0xffffffffu, p.out, 0);
-                p.chroms = __shfl_sync(0xffffffffu, p.chroms, 0); p.v = __shfl_sync(0xffffffffu, p.v, 0);
-                p.seg = __shfl_sync(0xffffffffu, p.seg, 0);
-                excl = fagg_op(p, excl);
-                if (first2 < 32) break;
-                basei -= 32;
-            }
-            if (failed && l == 0) sc[SC_ERROR] = 1ull;
-        }
-        if (l == 0) {
-            FAgg I = fagg_op(excl, A);
-            store_agg(&inc[tile], I);
-            __threadfence();
-            *reinterpret_cast<volatile uint32_t *>(&status[tile]) = 2u;
-            if (tile == ntiles - 1) {
-                sc[SC_TOTAL + 0] = I.lines; sc[SC_TOTAL + 1] = I.out; sc[SC_TOTAL + 2] = I.chroms;
-                sc[SC_TOTAL + 3] = (unsigned long long)I.v; sc[SC_TOTAL + 4] = I.seg;
-            }
-        }
+        sc[SC_TOTAL + 0] = carry.lines; sc[SC_TOTAL + 1] = carry.out; sc[SC_TOTAL + 2] = carry.chroms;
+        sc[SC_TOTAL + 3] = (unsigned long long)carry.v; sc[SC_TOTAL + 4] = carry.seg;
     }
 }
 
@@ -495,63 +519,80 @@ struct DumpArrays {            // the per-line arrays of the s3g_tokenize entry 
 
 template <bool DUMP>
 __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo, int64_t carry_max,
-                                                     const FAgg *__restrict__ inc, uint64_t n_lines, uint8_t *__restrict__ tf,
-                                                     ChromSeed *seeds, unsigned long long *stat_len, unsigned long long *stat_uniq, DumpArrays da)
+                                                     const FAgg *__restrict__ span_pre, const FAgg *__restrict__ tile_pre, const FAgg *__restrict__ chunk_pre,
+                                                     const uint32_t *__restrict__ chunk_out, uint64_t n_lines, uint8_t *__restrict__ tf,
+                                                     ChromSeed *seeds, unsigned long long *stat_len, unsigned long long *stat_uniq, uint32_t stat_slots,
+                                                     DumpArrays da)
 {
-    __shared__ TileSh S;
-    __shared__ __align__(16) uint8_t s_out[FOBUF + 16];
-    __shared__ unsigned long long s_red[2][FTH / 32];
-    const uint32_t tile = blockIdx.x;
-    tile_setup(S, bed, n, skip, tile);
-    const uint32_t k = S.k;
-    if (k == 0 || k > FMAXL) return;
-    const FAgg ex0 = tile ? inc[tile - 1] : fagg_identity();
-    const uint64_t o_begin = ex0.out, o_end = inc[tile].out;
-    const bool staged = o_end - o_begin <= FOBUF;
+    __shared__ WarpSh Ws[FWARPS];
+    __shared__ __align__(16) uint8_t s_out[FWARPS][FOB + 16];
+    const unsigned l = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t chunk = (uint64_t)blockIdx.x * FWARPS + wid;
+    WarpSh &W = Ws[wid];
+    ChunkGeom G;
+    chunk_setup(W, G, bed, n, skip, chunk);
+    if (G.k == 0 || G.k > FMAXL) return;
+    const FAgg ex0 = fagg_op(fagg_op(span_pre[blockIdx.x / FSCAN_T], tile_pre[blockIdx.x]), chunk_pre[chunk]);
+    const uint64_t o_begin = ex0.out;
+    const uint32_t o_len = chunk_out[chunk];
+    const bool staged = o_len <= FOB;
     const uint32_t ph = (uint32_t)o_begin & 15u;
+    uint8_t *const obuf = s_out[wid];
     uint64_t run_out = 0, run_ch = 0;
-    SegMax run_seg; run_seg.v = ex0.v; run_seg.seg = (int32_t)ex0.seg; run_seg.pad = 0;
-    for (uint32_t base = 0; base < k; base += FTH) {
+    int64_t run_v = ex0.v;                                 // largest stop of the current chromosome so far
+    const uint64_t c0 = ex0.chroms - 1;                    // the chromosome the chunk begins in (unless its first line starts one)
+    unsigned long long acc_len = 0, acc_uniq = 0;          // sums of the lines that belong to c0
+    int64_t cs = 0, ce = 0;
+    const uint32_t rounds = (G.k + 1 + 31) / 32;
+    for (uint32_t r = 0; r < rounds; r++) {
         LineOut L;
-        bool act = line_of_round(S, bed, base, halo, L);
-        uint32_t tot_out, tot_ch;
-        uint32_t ex_out = block_excl_sum<uint32_t>(L.out_len, S.sum_a, &tot_out);
-        uint32_t ex_ch = block_excl_sum<uint32_t>(L.flag, S.sum_b, &tot_ch);
-        SegMax mine = SegMaxF::identity();
-        if (act) { mine.v = (halo && L.first_global) ? INT64_MIN : L.P.stop; mine.seg = (int32_t)L.flag; }
-        SegMax tot_seg;
-        SegMax ex_seg = block_scan_partials<SegMaxF, FTH>(mine, S.seg_sm, &tot_seg);
-        unsigned long long my_len = 0, my_uniq = 0;
-        uint64_t chrom = 0;
-        if (act) {
-            const uint64_t g = ex0.lines + base + threadIdx.x;               // line index in the input
-            const uint64_t o = o_begin + run_out + ex_out;
-            chrom = ex0.chroms + run_ch + ex_ch + L.flag - 1;
+        line_of_round(W, G, bed, r, halo, cs, ce, L);
+        const uint32_t inc_out = warp_incl_sum<uint32_t>(L.out_len);
+        const uint32_t tot_out = __shfl_sync(0xffffffffu, inc_out, 31);
+        const unsigned mflag = __ballot_sync(0xffffffffu, L.flag != 0);
+        const uint32_t ex_ch = __popc(mflag & ((1u << l) - 1u));
+        int64_t v = L.owned ? ((halo && L.first_global) ? INT64_MIN : L.P.stop) : INT64_MIN;
+        uint32_t f = L.flag;
+        warp_segmax_incl(v, f);
+        // exclusive: what the lanes before this one leave
+        int64_t pv = __shfl_up_sync(0xffffffffu, v, 1);
+        uint32_t pf = __shfl_up_sync(0xffffffffu, f, 1);
+        if (l == 0) { pv = INT64_MIN; pf = 0; }
+        const int64_t tot_v = __shfl_sync(0xffffffffu, v, 31);
+        if (L.owned) {
+            const uint64_t g = ex0.lines + r * 32 + l - 1;                       // line index in the input
+            const uint64_t o = o_begin + run_out + (inc_out - L.out_len);
+            const uint64_t chrom = ex0.chroms + run_ch + ex_ch + L.flag - 1;
             const bool is_halo = halo && L.first_global;
-            int64_t rm = L.flag ? INT64_MIN : SegMaxF::op(run_seg, ex_seg).v;  // largest stop of the earlier lines of this chromosome
-            if (halo && chrom == 0 && carry_max > rm) rm = carry_max;          // ... including those on other GPUs
+            int64_t rm = L.flag ? INT64_MIN : (pf ? pv : (run_v > pv ? run_v : pv));   // largest stop of the earlier lines of this chromosome
+            if (halo && chrom == 0 && carry_max > rm) rm = carry_max;                  // ... including those on other GPUs
             const int64_t s = L.P.start, t = L.P.stop;
             const int64_t len = (int64_t)((uint64_t)t - (uint64_t)s), d = (int64_t)((uint64_t)s - (uint64_t)L.pstop);
             if (!is_halo) {
-                int64_t lo = s > rm ? s : rm;
-                my_len = (unsigned long long)len;
-                my_uniq = t > lo ? (unsigned long long)(t - lo) : 0ull;
-                uint8_t *w = staged ? s_out + ph + (uint32_t)(o - o_begin) : tf + o;
+                const int64_t lo = s > rm ? s : rm;
+                const unsigned long long my_len = (unsigned long long)len, my_uniq = t > lo ? (unsigned long long)(t - lo) : 0ull;
+                if (chrom == c0) { acc_len += my_len; acc_uniq += my_uniq; }
+                else {
+                    const uint64_t slot = chrom * stat_slots + (blockIdx.x & (stat_slots - 1));
+                    if (my_len) atomicAdd(&stat_len[slot], my_len);
+                    if (my_uniq) atomicAdd(&stat_uniq[slot], my_uniq);
+                }
+                uint8_t *w = staged ? obuf + ph + (uint32_t)(o - o_begin) : tf + o;
                 if (len != L.plen) { *w++ = 'p'; w += put_dec(w, len); *w++ = '\n'; }      // hpp:438-455
                 w += put_dec(w, d);                                                        // hpp:456-500
-                uint64_t r = L.s + L.P.rem_off;
-                if (r < L.e) {
+                const uint64_t rr = L.s + L.P.rem_off;
+                if (rr < L.e) {
                     *w++ = '\t';
-                    const uint8_t *src = L.s >= S.lo ? S.buf + (r - S.lo) : bed + r;
-                    const uint32_t rl = (uint32_t)(L.e - r);
+                    const uint8_t *src = bed + rr;
+                    const uint32_t rl = (uint32_t)(L.e - rr);
                     for (uint32_t q = 0; q < rl; q++) w[q] = src[q];
                     w += rl;
                 }
                 *w = '\n';
             }
             if (L.flag) {
-                ChromSeed cs; cs.first_line = g; cs.name_off = L.s; cs.tf_off = o; cs.name_len = L.P.name_len; cs.pad = 0;
-                seeds[chrom] = cs;
+                ChromSeed sd; sd.first_line = g; sd.name_off = L.s; sd.tf_off = o; sd.name_len = L.P.name_len; sd.pad = 0;
+                seeds[chrom] = sd;
             }
             if (DUMP) {
                 da.line_start[g] = L.s;
@@ -559,38 +600,28 @@ __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__
                 da.start[g] = s; da.stop[g] = t; da.rem_off[g] = L.P.rem_off; da.flags[g] = (uint8_t)(L.flag | (L.P.malformed << 1));
             }
         }
-        // per-chromosome sums: one atomic per tile round unless a chromosome starts inside it
-        if (tot_ch == 0) {
-            unsigned long long a = my_len, b = my_uniq;
+        run_out += tot_out; run_ch += __popc(mflag);
+        run_v = mflag ? tot_v : (run_v > tot_v ? run_v : tot_v);
+    }
+    // per-chromosome sums of the chunk's first chromosome: one atomic pair per chunk
 #pragma unroll
-            for (int dd = 16; dd; dd >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, dd); b += __shfl_xor_sync(0xffffffffu, b, dd); }
-            if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = a; s_red[1][threadIdx.x >> 5] = b; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long ta = 0, tb = 0;
-                for (int w = 0; w < FTH / 32; w++) { ta += s_red[0][w]; tb += s_red[1][w]; }
-                const uint64_t c0 = ex0.chroms + run_ch - 1;      // every line of the round belongs to it
-                if (ta) atomicAdd(&stat_len[c0], ta);
-                if (tb) atomicAdd(&stat_uniq[c0], tb);
-            }
-        } else if (act) {
-            if (my_len) atomicAdd(&stat_len[chrom], my_len);
-            if (my_uniq) atomicAdd(&stat_uniq[chrom], my_uniq);
-        }
-        run_out += tot_out; run_ch += tot_ch; run_seg = SegMaxF::op(run_seg, tot_seg);
-        round_carry(S, base, L);
+    for (int dd = 16; dd; dd >>= 1) { acc_len += __shfl_xor_sync(0xffffffffu, acc_len, dd); acc_uniq += __shfl_xor_sync(0xffffffffu, acc_uniq, dd); }
+    if (l == 0 && ex0.chroms) {
+        const uint64_t slot = c0 * stat_slots + (blockIdx.x & (stat_slots - 1));
+        if (acc_len) atomicAdd(&stat_len[slot], acc_len);
+        if (acc_uniq) atomicAdd(&stat_uniq[slot], acc_uniq);
     }
     if (!staged) return;
-    __syncthreads();
+    __syncwarp();
     uint8_t *dst = tf + (o_begin - ph);                                       // 16-byte aligned (tf comes from cudaMalloc)
-    const uint32_t lo_b = ph, hi_b = ph + (uint32_t)(o_end - o_begin);
-    for (uint32_t c = threadIdx.x * 16; c < hi_b; c += FTH * 16) {
-        if (c >= lo_b && c + 16 <= hi_b) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(s_out + c);
-        else for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = s_out[j];
+    const uint32_t lo_b = ph, hi_b = ph + o_len;
+    for (uint32_t c = l * 16; c < hi_b; c += 32 * 16) {
+        if (c >= lo_b && c + 16 <= hi_b) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(obuf + c);
+        else for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = obuf[j];
     }
 }
 
-__global__ void k_chrom_finish(const ChromSeed *seeds, const unsigned long long *stat_len, const unsigned long long *stat_uniq,
+__global__ void k_chrom_finish(const ChromSeed *seeds, const unsigned long long *stat_len, const unsigned long long *stat_uniq, uint32_t stat_slots,
                                uint64_t n_chroms, uint64_t n_lines, uint64_t tf_total, s3g_chrom *out, uint32_t halo)
 {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -601,8 +632,10 @@ __global__ void k_chrom_finish(const ChromSeed *seeds, const unsigned long long 
     r.tf_off = a.tf_off;
     r.tf_len = (c + 1 < n_chroms ? seeds[c + 1].tf_off : tf_total) - a.tf_off;
     r.line_count = (int64_t)((c + 1 < n_chroms ? seeds[c + 1].first_line : n_lines) - a.first_line) - (halo && c == 0 ? 1 : 0);
-    r.bases_nonunique = (int64_t)stat_len[c];
-    r.bases_unique = (int64_t)stat_uniq[c];
+    unsigned long long sl = 0, su = 0;
+    for (uint32_t k = 0; k < stat_slots; k++) { sl += stat_len[c * stat_slots + k]; su += stat_uniq[c * stat_slots + k]; }
+    r.bases_nonunique = (int64_t)sl;
+    r.bases_unique = (int64_t)su;
     r.bz_off = 0; r.bz_len = 0;
     out[c] = r;
 }
@@ -612,24 +645,26 @@ __global__ void k_chrom_finish(const ChromSeed *seeds, const unsigned long long 
 int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out, uint32_t halo)
 {
     *out = TfResult();
-    uint64_t ntiles = (n + FT - 1) / FT;
+    uint64_t ntiles = (n + (uint64_t)FCH * FWARPS - 1) / ((uint64_t)FCH * FWARPS);
     if (ntiles == 0) ntiles = 1;
     if (ntiles > 0x7fffffffull) { set_error("input too large"); return S3G_E_LIMIT; }
-    S3G_TRY(ctx->tile_cnt.ensure(ntiles * 4));
-    S3G_TRY(ctx->scan_a.ensure(ntiles * sizeof(FAgg)));
-    S3G_TRY(ctx->scan_b.ensure(ntiles * sizeof(FAgg)));
+    S3G_TRY(ctx->tile_cnt.ensure(ntiles * FWARPS * 4));                  // output bytes per chunk
+    S3G_TRY(ctx->scan_a.ensure(ntiles * sizeof(FAgg)));                  // per tile: aggregate, then exclusive prefix
+    S3G_TRY(ctx->scan_b.ensure(ntiles * FWARPS * sizeof(FAgg)));         // per chunk: prefix inside its tile
     S3G_TRY(ctx->scalars.ensure(64 * 8));
     uint64_t *d_sc = ctx->scalars.as<uint64_t>();
     S3G_CUDA(cudaMemsetAsync(d_sc, 0, 64 * 8, ctx->stream));
-    S3G_CUDA(cudaMemsetAsync(ctx->tile_cnt.p, 0, ntiles * 4, ctx->stream));
     S3G_BYTES(ctx, n);
-    S3G_LAUNCH(ctx, k_front_measure, (unsigned)ntiles, FTH, 0, d_bed, n, skip, halo, (uint32_t)ntiles, ctx->tile_cnt.as<uint32_t>(),
-               ctx->scan_a.as<FAgg>(), ctx->scan_b.as<FAgg>(), (unsigned long long *)d_sc);
+    S3G_LAUNCH(ctx, k_front_measure, (unsigned)ntiles, FTH, 0, d_bed, n, skip, halo, ctx->scan_a.as<FAgg>(), ctx->scan_b.as<FAgg>(),
+               ctx->tile_cnt.as<uint32_t>(), (unsigned long long *)d_sc);
+    const uint64_t nspans = (ntiles + FSCAN_T - 1) / FSCAN_T;
+    S3G_TRY(ctx->scan_c.ensure(nspans * sizeof(FAgg)));
+    S3G_LAUNCH(ctx, k_front_scan_tiles, (unsigned)nspans, FSCAN_T, 0, ctx->scan_a.as<FAgg>(), ntiles, ctx->scan_c.as<FAgg>());
+    S3G_LAUNCH(ctx, k_front_scan_spans, 1, FSCAN_T, 0, ctx->scan_c.as<FAgg>(), nspans, (unsigned long long *)d_sc);
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     S3G_TRY(check_launch("front measure"));
     const uint64_t *h = ctx->h_scalars;
-    if (h[SC_ERROR]) { set_error("tokenizer look-back timed out"); return S3G_E_CUDA; }
     out->n_lines = h[SC_TOTAL + 0];
     out->tf_len = h[SC_TOTAL + 1];
     out->n_chroms = h[SC_TOTAL + 2];
@@ -638,7 +673,7 @@ int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfRe
     ctx->front_tail_max = (int64_t)h[SC_TOTAL + 3];
     ctx->front_line1_flag = (uint32_t)h[SC_LINE1];
     if (out->n_lines && h[SC_MALFORMED]) {
-        set_error("malformed BED line(s): fewer than three fields (in %llu 8 KiB tile(s) of the input)", (unsigned long long)h[SC_MALFORMED]);
+        set_error("malformed BED line(s): fewer than three fields (in %llu 16 KiB tile(s) of the input)", (unsigned long long)h[SC_MALFORMED]);
         return S3G_E_MALFORMED;
     }
     return S3G_OK;
@@ -659,14 +694,15 @@ int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_m
 int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump)
 {
     const uint64_t n_lines = out->n_lines, n_chroms = out->n_chroms;
-    uint64_t ntiles = (n + FT - 1) / FT;
+    uint64_t ntiles = (n + (uint64_t)FCH * FWARPS - 1) / ((uint64_t)FCH * FWARPS);
     if (ntiles == 0) ntiles = 1;
+    const uint32_t slots = n_chroms <= 4096 ? 32u : 1u;            // same-address atomics serialise: spread a chromosome's sums
     S3G_TRY(ctx->tf.ensure(out->tf_len + 64));
     S3G_TRY(ctx->chrom_first.ensure((n_chroms + 1) * sizeof(ChromSeed)));
-    S3G_TRY(ctx->stat_b.ensure((n_chroms + 1) * 16));
+    S3G_TRY(ctx->stat_b.ensure((n_chroms + 1) * slots * 16));
     S3G_TRY(ctx->chroms.ensure((n_chroms + 1) * sizeof(s3g_chrom)));
-    unsigned long long *stat_len = ctx->stat_b.as<unsigned long long>(), *stat_uniq = stat_len + (n_chroms + 1);
-    S3G_CUDA(cudaMemsetAsync(stat_len, 0, (n_chroms + 1) * 16, ctx->stream));
+    unsigned long long *stat_len = ctx->stat_b.as<unsigned long long>(), *stat_uniq = stat_len + (n_chroms + 1) * slots;
+    S3G_CUDA(cudaMemsetAsync(stat_len, 0, (n_chroms + 1) * slots * 16, ctx->stream));
     DumpArrays da = {nullptr, nullptr, nullptr, nullptr, nullptr};
     S3G_BYTES(ctx, n + out->tf_len);
     if (dump) {
@@ -677,13 +713,15 @@ int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out
         S3G_TRY(ctx->flags.ensure(n_lines));
         da.line_start = ctx->line_start.as<uint64_t>(); da.start = ctx->start.as<int64_t>(); da.stop = ctx->stop.as<int64_t>();
         da.rem_off = ctx->rem_off.as<uint32_t>(); da.flags = ctx->flags.as<uint8_t>();
-        S3G_LAUNCH(ctx, k_front_write<true>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_b.as<FAgg>(), n_lines,
-                   ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(), stat_len, stat_uniq, da);
+        S3G_LAUNCH(ctx, k_front_write<true>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_c.as<FAgg>(), ctx->scan_a.as<FAgg>(),
+                   ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(),
+                   stat_len, stat_uniq, slots, da);
     } else {
-        S3G_LAUNCH(ctx, k_front_write<false>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_b.as<FAgg>(), n_lines,
-                   ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(), stat_len, stat_uniq, da);
+        S3G_LAUNCH(ctx, k_front_write<false>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_c.as<FAgg>(), ctx->scan_a.as<FAgg>(),
+                   ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(),
+                   stat_len, stat_uniq, slots, da);
     }
-    S3G_LAUNCH(ctx, k_chrom_finish, (unsigned)((n_chroms + 127) / 128), 128, 0, ctx->chrom_first.as<ChromSeed>(), stat_len, stat_uniq,
+    S3G_LAUNCH(ctx, k_chrom_finish, (unsigned)((n_chroms + 127) / 128), 128, 0, ctx->chrom_first.as<ChromSeed>(), stat_len, stat_uniq, slots,
                n_chroms, n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>(), halo);
     return check_launch("transform write");
 }
