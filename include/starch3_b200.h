@@ -206,6 +206,27 @@ S3G_API int s3g_huff(s3g_ctx *ctx, const uint16_t *mtfv, uint32_t n_mtf, const i
 S3G_API int s3g_bz_compress(s3g_ctx *ctx, const uint8_t *in, uint64_t n, int block_size_100k,
                     uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 
+/* ---- the decoder path: archive -> BED, on the GPU ----
+ * The reference has no decoder (its libbz2 carries BZ2_bzDecompress, bz/bzlib.c:551-900 + bz/decompress.c:106-646, which
+ * nothing calls); these entry points are what an `unstarch3` would bind.  The inverse of update_transformation_state
+ * (hpp:428-504) is the one ARCHIVE_FORMAT.md states. */
+typedef struct s3g_decode_info {
+    uint64_t n_streams, n_blocks;  /* chromosome streams / bzip2 blocks decoded */
+    uint64_t tf_bytes;             /* transformed bytes (all streams) */
+    double   device_ms;            /* CUDA-event time, upload to last kernel */
+    void    *d_bed;                /* device: the BED text (valid until the next call on ctx) */
+} s3g_decode_info;
+/* A whole archive (ARCHIVE_FORMAT.md) back to BED text.  bed may be NULL (only *bed_len and info are produced).
+ * Every block CRC and every stream's combined CRC is checked (bz/bzlib.c:843-866); a mismatch is S3G_E_PARAM. */
+S3G_API int s3g_decompress_archive(s3g_ctx *ctx, const uint8_t *archive, uint64_t n, uint8_t *bed, uint64_t bed_cap,
+                                   uint64_t *bed_len, s3g_decode_info *info);
+/* One complete bzip2 stream -> its bytes; what BZ2_bzDecompressInit / BZ2_bzDecompress / BZ2_bzDecompressEnd
+ * (bz/bzlib.h:121-135) do for one stream. */
+S3G_API int s3g_bz_decompress(s3g_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+/* One transformed stream -> the BED lines of chromosome `name`. */
+S3G_API int s3g_inverse_transform(s3g_ctx *ctx, const uint8_t *tf, uint64_t n, const uint8_t *name, uint32_t name_len,
+                                  uint8_t *bed, uint64_t bed_cap, uint64_t *bed_len);
+
 #ifdef __cplusplus
 }
 #endif

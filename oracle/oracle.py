@@ -295,6 +295,50 @@ def archive(bed, level=9, note=""):
     return bytes([0xca, 0x5c, 0xad, 0x1a]) + hdr + b"\n" + b"".join(streams)
 
 
+# ---- the decoder path's checker --------------------------------------------------------------------------
+def inverse_transform(name, tf):
+    """ARCHIVE_FORMAT.md "Streams": a line p<L> sets the element length, any other line <d>[\t<rest>] is an element with
+    start = previous stop + d, stop = start + L; both start at 0 (the inverse of starch3api.hpp:428-504)."""
+    out = []
+    prev_stop = 0
+    cur_len = 0
+    for ln in bytes(tf).split(b"\n")[:-1]:
+        if ln[:1] == b"p":
+            cur_len = int(ln[1:])
+            continue
+        f = ln.split(b"\t", 1)
+        start = prev_stop + int(f[0])
+        stop = start + cur_len
+        out.append(name + b"\t%d\t%d" % (start, stop) + (b"\t" + f[1] if len(f) == 2 else b"") + b"\n")
+        prev_stop = stop
+    return b"".join(out)
+
+
+def bz_decompress(z, cap=None):
+    """One bzip2 stream -> bytes: the reference's vendored BZ2_bzDecompress when oracle/_ref is built, else CPython's bz2."""
+    if have_ref():
+        return ref_bz_decompress(z, cap if cap is not None else max(len(z) * 60, 1 << 20))
+    import bz2
+    return bz2.decompress(bytes(z))
+
+
+def unarchive(arc):
+    """archive -> BED text, on the CPU (ARCHIVE_FORMAT.md "Reading")."""
+    import json
+    arc = bytes(arc)
+    assert arc[:4] == bytes([0xca, 0x5c, 0xad, 0x1a])
+    nl = arc.index(b"\n", 4)
+    meta = json.loads(arc[4:nl].decode("utf-8", "surrogateescape"))
+    payload = arc[nl + 1:]
+    out = []
+    for st in meta["streams"]:
+        z = payload[st["offset"]:st["offset"] + st["size"]]
+        tf = bz_decompress(z, st["transformedBytes"] + 16)
+        assert len(tf) == st["transformedBytes"]
+        out.append(inverse_transform(st["chromosome"].encode("utf-8", "surrogateescape"), tf))
+    return b"".join(out)
+
+
 # ---- block-parallel form of the same reference compressor -------------------------------------------------
 # libbz2 compresses one stream on one core; the BASELINE-size single-chromosome inputs (cfg1/3/4) would take
 # minutes.  A bzip2 stream is "BZh<level>" + the blocks bit-concatenated + trailer (bz/compress.c:602-667), a block

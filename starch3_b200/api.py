@@ -22,6 +22,7 @@ C_ABI_SYMBOLS = [
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_stage_times",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
+    "s3g_decompress_archive", "s3g_bz_decompress", "s3g_inverse_transform",
 ]
 
 
@@ -52,6 +53,11 @@ STAGE_NAMES = ["tokenise+transform", "rle1+cut+crc", "blocksort", "mtf", "huffma
 class CShardSummary(C.Structure):
     _fields_ = [("n_lines", C.c_uint64), ("tail_max", C.c_int64), ("continues", C.c_uint32), ("single_piece", C.c_uint32),
                 ("dropped_tail_bytes", C.c_uint64)]
+
+
+class CDecodeInfo(C.Structure):
+    _fields_ = [("n_streams", C.c_uint64), ("n_blocks", C.c_uint64), ("tf_bytes", C.c_uint64), ("device_ms", C.c_double),
+                ("d_bed", C.c_void_p)]
 
 
 class CBlockDesc(C.Structure):
@@ -109,6 +115,9 @@ def lib():
         L.s3g_huff.argtypes = [vp, vp, C.c_uint32, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, vp, vp, u64,
                                C.POINTER(u64)]
         L.s3g_bz_compress.argtypes = [vp, vp, u64, i32, vp, u64, C.POINTER(u64)]
+        L.s3g_decompress_archive.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(CDecodeInfo)]
+        L.s3g_bz_decompress.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64)]
+        L.s3g_inverse_transform.argtypes = [vp, vp, u64, vp, C.c_uint32, vp, u64, C.POINTER(u64)]
         _lib = L
     return _lib
 
@@ -389,6 +398,43 @@ class Context:
                                        _p(bits), len(bits), C.byref(nbits)))
         return dict(n_groups=ng.value, n_selectors=ns.value, selector=sel[:ns.value].copy(), len=lens,
                     bits=bits[:(nbits.value + 7) // 8].copy(), nbits=nbits.value)
+
+    # ---- the decoder path ----
+    def decompress_archive(self, archive, want_bed=True):
+        """archive bytes -> (BED bytes or None, info dict); the whole decoder on the GPU"""
+        a = _u8(archive)
+        n = C.c_uint64(0)
+        info = CDecodeInfo()
+        self._check(self._lib.s3g_decompress_archive(self._h, _p(a), len(a), None, 0, C.byref(n), C.byref(info)))
+        d = dict(n_streams=info.n_streams, n_blocks=info.n_blocks, tf_bytes=info.tf_bytes, device_ms=info.device_ms, bed_len=n.value)
+        if not want_bed:
+            return None, d
+        out = np.empty(max(n.value, 1), dtype=np.uint8)
+        self._check(self._lib.s3g_decompress_archive(self._h, _p(a), len(a), _p(out), len(out), C.byref(n), C.byref(info)))
+        d["device_ms"] = info.device_ms
+        return out[:n.value].tobytes(), d
+
+    def bz_decompress(self, data, cap=None):
+        a = _u8(data)
+        cap = cap or (len(a) * 8 + (1 << 20))
+        n = C.c_uint64(0)
+        while True:
+            out = np.empty(cap, dtype=np.uint8)
+            rc = self._lib.s3g_bz_decompress(self._h, _p(a), len(a), _p(out), cap, C.byref(n))
+            if rc == S3G_E_CAPACITY and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc)
+            return out[:n.value].tobytes()
+
+    def inverse_transform(self, tf, name):
+        a = _u8(tf)
+        nm = _u8(name)
+        cap = 2 * len(a) + (len(nm) + 48) * (int(np.count_nonzero(a == 10)) + 1)
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_uint64(0)
+        self._check(self._lib.s3g_inverse_transform(self._h, _p(a), len(a), _p(nm), len(nm), _p(out), cap, C.byref(n)))
+        return out[:n.value].tobytes()
 
     def bz_compress(self, data, block_size_100k=9):
         a = _u8(data)

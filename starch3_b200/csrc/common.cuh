@@ -123,6 +123,7 @@ struct Ctx {
     std::vector<cudaEvent_t> mark_pool;
     std::vector<std::pair<int, cudaEvent_t>> marks;
     uint64_t last_rle_bytes = 0;
+    uint64_t last_dec_blocks = 0;          // bzip2 blocks decoded by the last decoder call (decode.cu)
     void *shard = nullptr;                 // state between the s3g_shard_* phases (shard.cu)
     // the plan run_rle_plan left (input of run_rle_fill)
     const uint8_t *rle_in = nullptr; uint64_t rle_n = 0; const uint64_t *rle_soff = nullptr; uint64_t rle_streams = 0, rle_blocks = 0;
@@ -261,6 +262,7 @@ int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_sof
 int run_rle_plan(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams,
                  int level, CutResult *out);
 int run_rle_fill(Ctx *ctx, uint64_t b_lo, uint64_t b_hi);
+int run_block_crc(Ctx *ctx, const uint8_t *d_in, BlockInfo *d_blocks, uint64_t nb, double bytes);
 
 // kernels (3b..3d) on blocks [b0, b0+nb) of ctx->blocks
 int run_bwt(Ctx *ctx, uint64_t b0, uint64_t nb);                 // -> ctx->sa, ctx->lcol, BlockInfo.orig_ptr / tie

@@ -644,6 +644,15 @@ int run_rle_fill(Ctx *ctx, uint64_t b_lo, uint64_t b_hi)
     return check_launch("rle write");
 }
 
+// CRC-32/BZIP2 of d_in[in_start, in_end) of each of the nb descriptors -> BlockInfo.crc (the decoder checks its output with it)
+int run_block_crc(Ctx *ctx, const uint8_t *d_in, BlockInfo *d_blocks, uint64_t nb, double bytes)
+{
+    if (!nb) return S3G_OK;
+    S3G_BYTES(ctx, bytes);
+    S3G_LAUNCH(ctx, k_block_crc, (unsigned)nb, CRC_T, 0, d_in, d_blocks);
+    return check_launch("block crc");
+}
+
 int run_rle_cut(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_soff, uint64_t n_streams, int level,
                 CutResult *out)
 {

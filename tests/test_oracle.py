@@ -218,3 +218,13 @@ def test_block_parallel_oracle_equals_serial(oracle, cfg, lines, level):
     s = tf[ch[0]["tf_off"]:ch[0]["tf_off"] + ch[0]["tf_len"]]
     comp = oracle.ref_bz_compress if oracle.have_ref() else oracle.bz_compress
     assert oracle.bz_compress_blockwise(s, level) == comp(s, level)
+
+
+def test_oracle_unarchive_roundtrip(oracle):
+    """the decoder path's checker: unarchive(archive(bed)) == bed on every synthetic shape (CPU only)"""
+    from starch3_b200 import synth
+    for cfg in (1, 2, 3, 4, 5):
+        bed = synth.bed(cfg, 20000).tobytes()
+        assert oracle.unarchive(oracle.archive(bed)) == bed, cfg
+    assert oracle.inverse_transform(b"chr1", b"p100\n100\tid1\t5\t+\n-50\tid2\t7\t-\n50\tid3\t1\t+\np50\n0\n") == \
+        b"chr1\t100\t200\tid1\t5\t+\nchr1\t150\t250\tid2\t7\t-\nchr1\t300\t400\tid3\t1\t+\nchr1\t400\t450\n"
