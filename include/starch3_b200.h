@@ -98,6 +98,12 @@ typedef struct s3g_result {
     /* CUDA-event time per stage of the device-resident call, ms: [0] tokenise + transform, [1] RLE1 + cut + CRC,
      * [2] block sort, [3] MTF + zero runs, [4] Huffman + pool, [5] assembly; zero after the pipelined host entry */
     double     stage_ms[8];
+    /* input hardening: none of these changes the output, they tell the caller that the input is outside
+     * the sorted-BED domain the reference assumes */
+    uint64_t   unsorted_lines;     /* elements that start before the previous element of their chromosome */
+    uint64_t   crlf_lines;         /* lines that end in "\r\n": the carriage return stays part of the line's last field */
+    uint64_t   reappearing_chroms; /* streams whose chromosome name already opened an earlier stream (hpp:331 compares with
+                                      the previous line only); 0 when the call did not build the archive */
 } s3g_result;
 #define S3G_STAGE_NAMES "tokenise+transform", "rle1+cut+crc", "blocksort", "mtf", "huffman", "assemble"
 
@@ -118,6 +124,13 @@ S3G_API int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int b
 S3G_API int s3g_compress_bed_device(s3g_ctx *ctx, const void *d_bed, uint64_t n, int block_size_100k,
                             const char *note, int want_archive, s3g_result *res);
 S3G_API void s3g_result_free(s3g_result *res);
+/* Bounded-memory ingestion: the same archive from input handed over in pieces of any size -- replaces the
+ * byte-wise reader of produce_line (hpp:158-199) over stdin or a file (hpp:728-736, :890-905).  range_bytes (0 = 256 MiB)
+ * bounds what is resident: one range in pinned host memory, the chromosome still open plus one range on the device, and
+ * the compressed streams so far.  A chromosome is compressed once the input has moved on to the next one. */
+S3G_API int s3g_stream_begin(s3g_ctx *ctx, int block_size_100k, const char *note, uint64_t range_bytes);
+S3G_API int s3g_stream_write(s3g_ctx *ctx, const uint8_t *bed, uint64_t n);
+S3G_API int s3g_stream_end(s3g_ctx *ctx, s3g_result *res);
 /* Copy the device-resident streams of the last compress call (s3g_result.d_streams) to the host. */
 S3G_API int s3g_read_streams(s3g_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
 

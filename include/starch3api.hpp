@@ -83,6 +83,7 @@ namespace starch3
         unsigned char _header_magic_bytes[4];
         int _device;
         int _block_size_100k;
+        bool _unstarch;                    // --unstarch: the decoder path (archive in, BED out)
 
     public:
         Starch();
@@ -125,6 +126,8 @@ namespace starch3
         void set_device(int d) { _device = d; }
         void set_block_size_100k(int k) { _block_size_100k = k; }
         int get_block_size_100k(void) { return _block_size_100k; }
+        void set_unstarch(bool u) { _unstarch = u; }
+        bool get_unstarch(void) { return _unstarch; }
 
         static const compression_method_t client_starch_default_compression_method;
         static const std::string client_name;
@@ -150,28 +153,10 @@ namespace starch3
         static void fail(int code, const char* msg) { std::fprintf(stderr, "Error: %s\n", msg); std::exit(code); }
 
         // ---- thread entry points (pthread signature, as hpp:158 / :201 / :347 / :371) ----
-        // Bulk line reader: everything the input stream holds goes into sb->in_line.
-        static void* produce_line(void* arg) {
-            shared_buffer_t* sb = static_cast<shared_buffer_t*>(arg);
-            pthread_mutex_lock(&sb->lock);
-            size_t used = 0;
-            for (;;) {
-                if (used == sb->in_line_capacity) {
-                    char* grown = static_cast<char*>(realloc(sb->in_line, sb->in_line_capacity * 2));
-                    if (!grown) fail(ENOMEM, "Not enough memory for reallocation of shared_buffer_t line character buffer");
-                    sb->in_line = grown; sb->in_line_capacity *= 2;
-                }
-                size_t got = fread(sb->in_line + used, 1, sb->in_line_capacity - used, sb->in_stream);
-                used += got;
-                if (got == 0) break;
-            }
-            sb->in_line_size = used;
-            sb->is_eof = true;
-            sb->is_new_line_available = true;
-            pthread_cond_broadcast(&sb->new_line_is_available);
-            pthread_mutex_unlock(&sb->lock);
-            return NULL;
-        }
+        // Line reader.  A regular file of moderate size is read whole (the batch call then overlaps its upload with the
+        // kernels); stdin, pipes, files beyond 4 GiB and S3G_STREAM=1 go through the bounded-memory entry instead: 64 MiB
+        // at a time into s3g_stream_write (the getc loop of hpp:158-199 becomes fread + one call per piece).
+        static void* produce_line(void* arg);
         // Waits for the input, then runs the whole path once.
         static void* consume_line(void* arg) {
             shared_buffer_t* sb = static_cast<shared_buffer_t*>(arg);
@@ -264,7 +249,7 @@ namespace starch3
 
     inline void Starch::initialize_out_stream(void) {
         set_out_stream(stdout);
-        std::fwrite(_header_magic_bytes, 1, 4, stdout);     // the only bytes the reference ever writes (hpp:765-769)
+        if (!_unstarch) std::fwrite(_header_magic_bytes, 1, 4, stdout);     // the only bytes the reference ever writes (hpp:765-769)
     }
 
     inline void Starch::initialize_out_compression_stream(void) {
@@ -319,7 +304,7 @@ namespace starch3
         std::memcpy(_header_magic_bytes, mb, 4);
     }
 
-    inline Starch::Starch() : _bz_stream_ptr(NULL), _in_stream(NULL), _out_stream(NULL), _device(0), _block_size_100k(9) {
+    inline Starch::Starch() : _bz_stream_ptr(NULL), _in_stream(NULL), _out_stream(NULL), _device(0), _block_size_100k(9), _unstarch(false) {
         set_note(std::string());
         set_compression_method(k_compression_method_undefined);
         initialize_header_magic_bytes();
@@ -328,12 +313,73 @@ namespace starch3
 
     inline Starch::~Starch() { }
 
+    inline void* Starch::produce_line(void* arg) {
+        shared_buffer_t* sb = static_cast<shared_buffer_t*>(arg);
+        pthread_mutex_lock(&sb->lock);
+        struct stat st;
+        bool streaming = std::getenv("S3G_STREAM") != NULL;
+        if (fstat(fileno(sb->in_stream), &st) != 0 || !S_ISREG(st.st_mode) || st.st_size > (off_t)(4ll << 30)) streaming = true;
+        if (self && self->get_unstarch()) streaming = false;
+        if (streaming && self && self->get_device_context()) {
+            const size_t piece = 64u << 20;
+            if (sb->in_line_capacity < piece) {
+                char* grown = static_cast<char*>(realloc(sb->in_line, piece));
+                if (!grown) fail(ENOMEM, "Not enough memory for reallocation of shared_buffer_t line character buffer");
+                sb->in_line = grown; sb->in_line_capacity = piece;
+            }
+            size_t range = 0;
+            if (const char* e = std::getenv("S3G_STREAM_RANGE")) range = static_cast<size_t>(std::atoll(e));
+            int rc = s3g_stream_begin(self->get_device_context(), self->get_block_size_100k(), self->get_note().c_str(), range);
+            for (size_t got; rc == S3G_OK && (got = fread(sb->in_line, 1, piece, sb->in_stream)) > 0;)
+                rc = s3g_stream_write(self->get_device_context(), reinterpret_cast<const uint8_t*>(sb->in_line), got);
+            if (rc != S3G_OK) {
+                std::fprintf(stderr, "Error: %s\n", s3g_last_error());
+                std::exit(rc == S3G_E_NOMEM ? ENOMEM : rc == S3G_E_MALFORMED ? EINVAL : rc == S3G_E_CUDA ? ENODEV : EINVAL);
+            }
+            sb->in_line_size = 0;
+            sb->next_in = 1;                      // the input went through s3g_stream_write
+        } else {
+            size_t used = 0;
+            for (;;) {
+                if (used == sb->in_line_capacity) {
+                    char* grown = static_cast<char*>(realloc(sb->in_line, sb->in_line_capacity * 2));
+                    if (!grown) fail(ENOMEM, "Not enough memory for reallocation of shared_buffer_t line character buffer");
+                    sb->in_line = grown; sb->in_line_capacity *= 2;
+                }
+                size_t got = fread(sb->in_line + used, 1, sb->in_line_capacity - used, sb->in_stream);
+                used += got;
+                if (got == 0) break;
+            }
+            sb->in_line_size = used;
+        }
+        sb->is_eof = true;
+        sb->is_new_line_available = true;
+        pthread_cond_broadcast(&sb->new_line_is_available);
+        pthread_mutex_unlock(&sb->lock);
+        return NULL;
+    }
+
     inline void Starch::process_tf_buffer(shared_buffer_t* sb) {
         Starch* me = self;
         if (!me || !me->get_device_context()) fail(EINVAL, "compression stream is not initialised");
+        FILE* out = me->get_out_stream() ? me->get_out_stream() : stdout;
+        if (me->get_unstarch()) {
+            // the decoder path: sb->in_line holds an archive, the BED text goes out
+            uint64_t need = 0;
+            int rc = s3g_decompress_archive(me->get_device_context(), reinterpret_cast<const uint8_t*>(sb->in_line), sb->in_line_size, NULL, 0, &need, NULL);
+            uint8_t* bed = rc == S3G_OK ? static_cast<uint8_t*>(std::malloc(need ? need : 1)) : NULL;
+            if (rc == S3G_OK && !bed) fail(ENOMEM, "Not enough memory for the decoded BED text");
+            if (rc == S3G_OK) rc = s3g_decompress_archive(me->get_device_context(), reinterpret_cast<const uint8_t*>(sb->in_line), sb->in_line_size, bed, need, &need, NULL);
+            if (rc != S3G_OK) { std::fprintf(stderr, "Error: %s\n", s3g_last_error()); std::exit(rc == S3G_E_NOMEM ? ENOMEM : rc == S3G_E_CUDA ? ENODEV : EINVAL); }
+            if (need && std::fwrite(bed, 1, need, out) != need) fail(EIO, "could not write the BED text");
+            std::fflush(out);
+            std::free(bed);
+            return;
+        }
         s3g_result res;
-        int rc = s3g_compress_bed(me->get_device_context(), reinterpret_cast<const uint8_t*>(sb->in_line), sb->in_line_size,
-                                  me->get_block_size_100k(), me->get_note().c_str(), &res);
+        int rc = sb->next_in ? s3g_stream_end(me->get_device_context(), &res)
+                             : s3g_compress_bed(me->get_device_context(), reinterpret_cast<const uint8_t*>(sb->in_line), sb->in_line_size,
+                                                me->get_block_size_100k(), me->get_note().c_str(), &res);
         if (rc != S3G_OK) {
             std::fprintf(stderr, "Error: %s\n", s3g_last_error());
             std::exit(rc == S3G_E_NOMEM ? ENOMEM : rc == S3G_E_MALFORMED ? EINVAL : rc == S3G_E_CUDA ? ENODEV : EINVAL);
@@ -341,9 +387,17 @@ namespace starch3
         if (res.dropped_tail_bytes)
             std::fprintf(stderr, "Warning: the last line is not newline-terminated; %llu byte(s) ignored, as the reference does\n",
                          static_cast<unsigned long long>(res.dropped_tail_bytes));
+        if (res.unsorted_lines)
+            std::fprintf(stderr, "Warning: %llu element(s) start before the previous element of their chromosome: the input is not sorted\n",
+                         static_cast<unsigned long long>(res.unsorted_lines));
+        if (res.reappearing_chroms)
+            std::fprintf(stderr, "Warning: %llu chromosome stream(s) repeat an earlier chromosome name: the input is not sorted by chromosome\n",
+                         static_cast<unsigned long long>(res.reappearing_chroms));
+        if (res.crlf_lines)
+            std::fprintf(stderr, "Warning: %llu line(s) end in CR LF; the carriage return is kept as part of the line's last field\n",
+                         static_cast<unsigned long long>(res.crlf_lines));
         sb->tf_state->line_count = static_cast<int64_t>(res.n_lines);
         // the magic bytes are already out (initialize_out_stream); write the rest of the archive
-        FILE* out = me->get_out_stream() ? me->get_out_stream() : stdout;
         if (res.archive_size > 4 && std::fwrite(res.archive + 4, 1, res.archive_size - 4, out) != res.archive_size - 4)
             fail(EIO, "could not write the archive");
         std::fflush(out);

@@ -20,6 +20,7 @@ S3G_OK, S3G_E_CUDA, S3G_E_PARAM, S3G_E_NOMEM, S3G_E_MALFORMED, S3G_E_CAPACITY, S
 C_ABI_SYMBOLS = [
     "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
+    "s3g_stream_begin", "s3g_stream_write", "s3g_stream_end",
     "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_stage_times",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
     "s3g_decompress_archive", "s3g_bz_decompress", "s3g_inverse_transform",
@@ -44,7 +45,8 @@ class CResult(C.Structure):
                 ("chroms", C.POINTER(CChrom)), ("n_chroms", C.c_uint64), ("n_lines", C.c_uint64),
                 ("n_blocks", C.c_uint64), ("tf_bytes", C.c_uint64), ("dropped_tail_bytes", C.c_uint64),
                 ("d_streams", C.c_void_p), ("streams_size", C.c_uint64), ("device_ms", C.c_double),
-                ("rle_bytes", C.c_uint64), ("mtf_symbols", C.c_uint64), ("stage_ms", C.c_double * 8)]
+                ("rle_bytes", C.c_uint64), ("mtf_symbols", C.c_uint64), ("stage_ms", C.c_double * 8),
+                ("unsorted_lines", C.c_uint64), ("crlf_lines", C.c_uint64), ("reappearing_chroms", C.c_uint64)]
 
 
 STAGE_NAMES = ["tokenise+transform", "rle1+cut+crc", "blocksort", "mtf", "huffman", "assemble"]
@@ -101,6 +103,9 @@ def lib():
         L.s3g_compress_bed_device.argtypes = [vp, vp, u64, i32, C.c_char_p, i32, C.POINTER(CResult)]
         L.s3g_result_free.argtypes = [C.POINTER(CResult)]; L.s3g_result_free.restype = None
         L.s3g_read_streams.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.s3g_stream_begin.argtypes = [vp, i32, C.c_char_p, u64]
+        L.s3g_stream_write.argtypes = [vp, vp, u64]
+        L.s3g_stream_end.argtypes = [vp, C.POINTER(CResult)]
         L.s3g_shard_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(CShardSummary)]
         L.s3g_shard_transform.argtypes = [vp, C.c_int64, vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
         L.s3g_shard_plan.argtypes = [vp, vp, u64, vp, u64, i32, C.POINTER(u64), vp, vp, u64]
@@ -144,6 +149,9 @@ class Result:
         self.rle_bytes = cres.rle_bytes
         self.mtf_symbols = cres.mtf_symbols
         self.stage_ms = {nm: cres.stage_ms[i] for i, nm in enumerate(STAGE_NAMES)}
+        self.unsorted_lines = cres.unsorted_lines
+        self.crlf_lines = cres.crlf_lines
+        self.reappearing_chroms = cres.reappearing_chroms
         self.streams_size = cres.streams_size
         self.streams_off = cres.streams_off
         self.d_streams = cres.d_streams
@@ -250,6 +258,22 @@ class Context:
             res = Result(r, a)
             if not lazy:
                 res.archive          # copy out now: the view dies with the next call
+            return res
+        finally:
+            self._lib.s3g_result_free(C.byref(r))
+
+    def compress_stream(self, pieces, block_size_100k=9, note=None, range_bytes=0):
+        """bounded-memory ingestion: `pieces` is an iterable of bytes-like chunks of the BED text (any sizes)"""
+        self._check(self._lib.s3g_stream_begin(self._h, block_size_100k, note.encode() if isinstance(note, str) else note, range_bytes))
+        for pc in pieces:
+            a = _u8(pc)
+            self._check(self._lib.s3g_stream_write(self._h, _p(a), len(a)))
+        r = CResult()
+        rc = self._lib.s3g_stream_end(self._h, C.byref(r))
+        try:
+            self._check(rc)
+            res = Result(r, None)
+            res.archive
             return res
         finally:
             self._lib.s3g_result_free(C.byref(r))

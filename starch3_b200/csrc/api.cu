@@ -241,6 +241,7 @@ struct PartOut {
     uint64_t n_seen = 0;               // chromosomes found in the range
     uint64_t cs_next = 0;              // absolute offset of the chromosome left for the next range
     uint64_t streams_size = 0, n_blocks = 0, dropped = 0, tf_kept = 0, rle_bytes = 0, mtf_symbols = 0;
+    uint64_t unsorted = 0, crlf = 0;   // input diagnostics over the lines of the chromosomes compressed here
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -253,7 +254,7 @@ static int part_front(Ctx *ctx, const uint8_t *d_bed, uint64_t off, uint64_t len
     ctx->marks.clear();
     ctx->last_rle_bytes = 0;
     stage_mark(ctx, 0);
-    S3G_TRY(run_transform(ctx, d_bed + base, len + (off - base), &tr, false, (uint32_t)(off - base)));
+    S3G_TRY(run_transform(ctx, d_bed + base, len + (off - base), &tr, false, (uint32_t)(off - base), last_part));
     if (timing) fprintf(stderr, "[s3g timing] transform %.2f ms (host clock)\n", host_ms() - tt0);
     po.n_seen = tr.n_chroms;
     po.dropped = tr.dropped;
@@ -261,6 +262,7 @@ static int part_front(Ctx *ctx, const uint8_t *d_bed, uint64_t off, uint64_t len
     if (tr.n_chroms) {
         S3G_CUDA(cudaMemcpyAsync(ctx->h_chroms.data(), ctx->chroms.p, tr.n_chroms * sizeof(s3g_chrom), cudaMemcpyDeviceToHost, ctx->stream));
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        po.unsorted = front_unsorted(ctx); po.crlf = front_crlf(ctx);
     }
     const uint64_t kept = last_part ? tr.n_chroms : (tr.n_chroms ? tr.n_chroms - 1 : 0);
     po.cs_next = (!last_part && tr.n_chroms) ? base + ctx->h_chroms[tr.n_chroms - 1].name_off : off + len;
@@ -318,6 +320,20 @@ static int part_back(Ctx *ctx, const uint8_t *d_bed, uint64_t off, int level, bo
     return S3G_OK;
 }
 
+// chromosomes whose name already opened an earlier stream (interleaved / unsorted input: hpp:331 compares with the
+// previous line only, so each reappearance is a stream of its own)
+static uint64_t count_reappearing(const std::vector<s3g_chrom> &ch, const uint8_t *names)
+{
+    std::vector<std::string> v;
+    v.reserve(ch.size());
+    uint64_t off = 0;
+    for (const s3g_chrom &c : ch) { v.emplace_back(reinterpret_cast<const char *>(names + off), c.name_len); off += c.name_len; }
+    std::sort(v.begin(), v.end());
+    uint64_t dup = 0;
+    for (size_t i = 1; i < v.size(); i++) if (v[i] == v[i - 1]) dup++;
+    return dup;
+}
+
 static int ensure_archive(Ctx *ctx, uint64_t bytes)
 {
     if (bytes <= ctx->h_archive_cap) return S3G_OK;
@@ -357,6 +373,8 @@ static int compress_bed_impl(Ctx *ctx, const uint8_t *d_bed, uint64_t n, int lev
     res->streams_size = po.streams_size;
     res->dropped_tail_bytes = po.dropped;
     res->rle_bytes = po.rle_bytes; res->mtf_symbols = po.mtf_symbols;
+    res->unsorted_lines = po.unsorted; res->crlf_lines = po.crlf;
+    if (want_archive) res->reappearing_chroms = count_reappearing(po.chroms, po.names.data());
     memcpy(res->stage_ms, po.stage_ms, sizeof res->stage_ms);
     ctx->h_chroms = po.chroms;
     fill_result(res, po.chroms);
@@ -533,8 +551,10 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
         if (!po.chroms.empty()) names.insert(names.end(), po.names.begin(), po.names.end() - 1);
         res->n_blocks += po.n_blocks;
         res->rle_bytes += po.rle_bytes; res->mtf_symbols += po.mtf_symbols;
+        res->unsorted_lines += po.unsorted; res->crlf_lines += po.crlf;
     }
     names.push_back(0);
+    res->reappearing_chroms = count_reappearing(chroms, names.data());
     { uint64_t t = 0; for (s3g_chrom &c : chroms) { c.tf_off = t; t += c.tf_len; } }    // as in one transformed buffer
     res->dropped_tail_bytes = parts[nparts - 1].dropped;
     for (int k = 0; k < 2; k++) { ctx->launches += ctx->sub[k]->launches; ctx->sub[k]->launches = 0; }
@@ -559,6 +579,81 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     ctx->last_streams_size = sh.streams_so_far;                // s3g_read_streams serves them from the pinned archive
     ctx->last_streams_host = ctx->h_archive + HDR_RESERVE;
     ctx->archive_hint = sh.streams_so_far;
+    return S3G_OK;
+}
+
+// ---- bounded-memory ingestion ---------------------------------------------------------------
+// s3g_stream_begin / _write / _end take the input in pieces of any size.  Bytes collect in a pinned staging buffer of
+// `range_bytes`; a full buffer is cut at its last line feed, uploaded behind what the device still holds, and
+// compressed like a range of the pipelined entry: the chromosomes that END in it leave as finished bzip2 streams, the
+// chromosome still open stays on the device for the next range.  Resident: one range on the host, the open chromosome
+// plus one range on the device, and the compressed streams so far (host).
+struct StreamState {
+    int level = 9;
+    std::string note;
+    uint64_t range_bytes = 0;
+    uint8_t *h_stage = nullptr; uint64_t stage_fill = 0;
+    DevBuf dev[2]; int cur = 0; uint64_t dev_fill = 0;
+    std::vector<s3g_chrom> chroms; std::vector<uint8_t> names; std::vector<uint8_t> streams;
+    uint64_t n_blocks = 0, rle_bytes = 0, mtf_symbols = 0, dropped = 0, unsorted = 0, crlf = 0, ranges = 0;
+    double device_ms = 0;
+    ~StreamState() { if (h_stage) cudaFreeHost(h_stage); dev[0].release(); dev[1].release(); }
+};
+void stream_state_free(Ctx *ctx) { delete static_cast<StreamState *>(ctx->stream_state); ctx->stream_state = nullptr; }
+
+// grow a device buffer keeping its first `keep` bytes
+static int grow_keep(Ctx *ctx, DevBuf &b, uint64_t need, uint64_t keep)
+{
+    if (need <= b.cap) return S3G_OK;
+    DevBuf nb;
+    S3G_TRY(nb.ensure(need + need / 4));
+    if (keep) S3G_CUDA(cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    b.release();
+    b = nb;
+    return S3G_OK;
+}
+
+// upload stage[0, take) behind the device's open chromosome and compress what is complete
+static int stream_flush(Ctx *ctx, StreamState &S, uint64_t take, bool last)
+{
+    DevBuf &D = S.dev[S.cur];
+    S3G_TRY(grow_keep(ctx, D, S.dev_fill + take + 64, S.dev_fill));
+    if (take) S3G_CUDA(cudaMemcpyAsync(D.as<uint8_t>() + S.dev_fill, S.h_stage, take, cudaMemcpyHostToDevice, ctx->stream));
+    S.dev_fill += take;
+    S3G_CUDA(cudaMemsetAsync(D.as<uint8_t>() + S.dev_fill, 0, 64, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));          // the staging buffer is refilled by the caller
+    if (S.stage_fill > take) memmove(S.h_stage, S.h_stage + take, S.stage_fill - take);
+    S.stage_fill -= take;
+    if (S.dev_fill == 0) return S3G_OK;
+    PartOut po;
+    TfResult tr;
+    S3G_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    S3G_TRY(part_front(ctx, D.as<uint8_t>(), 0, S.dev_fill, last, po, tr));
+    S3G_TRY(part_back(ctx, D.as<uint8_t>(), 0, S.level, true, po));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) S.device_ms += ms; else cudaGetLastError();
+    S.ranges++;
+    const uint64_t at = S.streams.size();
+    for (s3g_chrom &c : po.chroms) { c.bz_off += at; S.chroms.push_back(c); }
+    if (!po.chroms.empty()) S.names.insert(S.names.end(), po.names.begin(), po.names.end() - 1);
+    if (po.streams_size) {
+        S.streams.resize(at + po.streams_size);
+        S3G_CUDA(cudaMemcpyAsync(S.streams.data() + at, ctx->streams.p, po.streams_size, cudaMemcpyDeviceToHost, ctx->stream));
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    S.n_blocks += po.n_blocks; S.rle_bytes += po.rle_bytes; S.mtf_symbols += po.mtf_symbols; S.unsorted += po.unsorted; S.crlf += po.crlf;
+    if (last) { S.dropped = po.dropped; S.dev_fill = 0; return S3G_OK; }
+    // the open chromosome moves to the front of the other buffer
+    const uint64_t tail = S.dev_fill - po.cs_next;
+    if (po.cs_next) {
+        DevBuf &O = S.dev[S.cur ^ 1];
+        S3G_TRY(O.ensure(tail + S.range_bytes + 64));
+        if (tail) S3G_CUDA(cudaMemcpyAsync(O.p, D.as<uint8_t>() + po.cs_next, tail, cudaMemcpyDeviceToDevice, ctx->stream));
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+        S.cur ^= 1;
+    }
+    S.dev_fill = tail;
     return S3G_OK;
 }
 
@@ -626,6 +721,7 @@ void s3g_destroy(s3g_ctx *ctx)
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->mark_pool) cudaEventDestroy(e);
     shard_state_free(ctx);
+    stream_state_free(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -716,6 +812,88 @@ int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int level, co
     }
     S3G_TRY(stage_in(ctx, ctx->bed, bed, n));
     return compress_bed_impl(ctx, ctx->bed.as<uint8_t>(), n, level, note, 1, res);
+}
+
+int s3g_stream_begin(s3g_ctx *ctx, int level, const char *note, uint64_t range_bytes)
+{
+    if (!ctx) { set_error("null context"); return S3G_E_PARAM; }
+    if (level < 1 || level > 9) { set_error("block_size_100k must be 1..9"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    stream_state_free(ctx);
+    StreamState *S = new (std::nothrow) StreamState();
+    if (!S) { set_error("out of host memory"); return S3G_E_NOMEM; }
+    S->level = level; S->note = note ? note : "";
+    S->range_bytes = range_bytes ? std::max<uint64_t>(range_bytes, 4096) : (256ull << 20);
+    if (cudaMallocHost(&S->h_stage, S->range_bytes) != cudaSuccess) { cudaGetLastError(); delete S; set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+    ctx->stream_state = S;
+    return S3G_OK;
+}
+
+int s3g_stream_write(s3g_ctx *ctx, const uint8_t *bed, uint64_t n)
+{
+    if (!ctx || (!bed && n)) { set_error("null argument"); return S3G_E_PARAM; }
+    StreamState *S = static_cast<StreamState *>(ctx->stream_state);
+    if (!S) { set_error("s3g_stream_write without s3g_stream_begin"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    while (n) {
+        const uint64_t room = S->range_bytes - S->stage_fill, k = std::min(room, n);
+        memcpy(S->h_stage + S->stage_fill, bed, k);
+        S->stage_fill += k; bed += k; n -= k;
+        if (S->stage_fill == S->range_bytes) {
+            // cut at the last line feed; a range without one (a line longer than the range) is uploaded whole
+            uint64_t take = S->stage_fill;
+            while (take && S->h_stage[take - 1] != '\n') take--;
+            const bool whole_lines = take != 0;
+            if (!whole_lines) take = S->stage_fill;
+            if (whole_lines) { int rc = stream_flush(ctx, *S, take, false); if (rc != S3G_OK) { stream_state_free(ctx); return rc; } }
+            else {
+                // no line ends in this range: park the bytes on the device, nothing to compress yet
+                DevBuf &D = S->dev[S->cur];
+                int rc = grow_keep(ctx, D, S->dev_fill + take + 64, S->dev_fill);
+                if (rc != S3G_OK) { stream_state_free(ctx); return rc; }
+                S3G_CUDA(cudaMemcpyAsync(D.as<uint8_t>() + S->dev_fill, S->h_stage, take, cudaMemcpyHostToDevice, ctx->stream));
+                S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+                S->dev_fill += take; S->stage_fill = 0;
+            }
+        }
+    }
+    return S3G_OK;
+}
+
+int s3g_stream_end(s3g_ctx *ctx, s3g_result *res)
+{
+    if (!ctx || !res) { set_error("null argument"); return S3G_E_PARAM; }
+    StreamState *S = static_cast<StreamState *>(ctx->stream_state);
+    if (!S) { set_error("s3g_stream_end without s3g_stream_begin"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    memset(res, 0, sizeof *res);
+    int rc = stream_flush(ctx, *S, S->stage_fill, true);
+    if (rc != S3G_OK) { stream_state_free(ctx); return rc; }
+    { uint64_t t = 0; for (s3g_chrom &c : S->chroms) { c.tf_off = t; t += c.tf_len; c.name_off = 0; } }   // no input buffer to point into
+    S->names.push_back(0);
+    std::vector<uint64_t> name_off(S->chroms.size() + 1, 0);
+    for (size_t c = 0; c < S->chroms.size(); c++) name_off[c + 1] = name_off[c] + S->chroms[c].name_len;
+    std::string hdr = build_header(S->names.data(), name_off, S->chroms, S->level, S->note.c_str());
+    const uint64_t streams_off = 4 + hdr.size() + 1;
+    rc = ensure_archive(ctx, streams_off + S->streams.size());
+    if (rc != S3G_OK) { stream_state_free(ctx); return rc; }
+    static const uint8_t magic[4] = {0xca, 0x5c, 0xad, 0x1a};      // hpp:907-910
+    memcpy(ctx->h_archive, magic, 4);
+    memcpy(ctx->h_archive + 4, hdr.data(), hdr.size());
+    ctx->h_archive[4 + hdr.size()] = '\n';
+    if (!S->streams.empty()) memcpy(ctx->h_archive + streams_off, S->streams.data(), S->streams.size());
+    res->archive = ctx->h_archive; res->archive_size = streams_off + S->streams.size(); res->streams_off = streams_off;
+    res->streams_size = S->streams.size(); res->d_streams = nullptr;
+    res->n_blocks = S->n_blocks; res->rle_bytes = S->rle_bytes; res->mtf_symbols = S->mtf_symbols; res->dropped_tail_bytes = S->dropped;
+    res->unsorted_lines = S->unsorted; res->crlf_lines = S->crlf; res->device_ms = S->device_ms;
+    res->reappearing_chroms = count_reappearing(S->chroms, S->names.data());
+    ctx->h_chroms = S->chroms;
+    fill_result(res, S->chroms);
+    ctx->last_streams_size = S->streams.size();
+    ctx->last_streams_host = ctx->h_archive + streams_off;
+    stream_state_free(ctx);
+    if (!res->chroms) { set_error("out of host memory"); return S3G_E_NOMEM; }
+    return S3G_OK;
 }
 
 int s3g_read_streams(s3g_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n)

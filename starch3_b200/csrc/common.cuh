@@ -125,6 +125,7 @@ struct Ctx {
     uint64_t last_rle_bytes = 0;
     uint64_t last_dec_blocks = 0;          // bzip2 blocks decoded by the last decoder call (decode.cu)
     void *shard = nullptr;                 // state between the s3g_shard_* phases (shard.cu)
+    void *stream_state = nullptr;          // state between s3g_stream_begin and s3g_stream_end (api.cu)
     // the plan run_rle_plan left (input of run_rle_fill)
     const uint8_t *rle_in = nullptr; uint64_t rle_n = 0; const uint64_t *rle_soff = nullptr; uint64_t rle_streams = 0, rle_blocks = 0;
     uint8_t *h_archive = nullptr;          // pinned; holds the archive of the last compress call
@@ -164,6 +165,7 @@ int check_launch(const char *what);
 void stage_mark(Ctx *ctx, int stage);
 void stage_collect(Ctx *ctx, double *stage_ms);
 void shard_state_free(Ctx *ctx);
+void stream_state_free(Ctx *ctx);
 int prof_begin(Ctx *ctx, const char *name);
 void prof_end(Ctx *ctx, int idx);
 
@@ -244,11 +246,14 @@ struct TfResult {
 };
 // kernels (1)+(2); leaves ctx->tf (bytes), ctx->chroms (s3g_chrom[n_chroms]) and the per-line arrays on device
 // `skip` (< 16): leading bytes of d_bed that belong to the line before the range (see k_count_newlines)
-int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip = 0);
+int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip = 0, bool last_part = true);
+// after the synchronise that follows run_transform: diagnostics of the lines of the chromosomes the range keeps
+inline uint64_t front_unsorted(const Ctx *ctx);
+inline uint64_t front_crlf(const Ctx *ctx);
 // the same in pieces, for ranges handed between GPUs (shard.cu): `halo` = line 0 is the last line before the range
 int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out, uint32_t halo);
 int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_max, uint64_t *last_flag, uint32_t *continues);
-int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump = false);
+int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump = false, bool last_part = true);
 
 struct CutResult {
     uint64_t n_blocks = 0;
@@ -280,6 +285,9 @@ int run_assemble(Ctx *ctx, uint64_t n_blocks, uint64_t n_streams, int level, uin
 int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, uint64_t b_hi, uint64_t *byte_lo, uint64_t *byte_hi,
                        std::vector<StreamMeta> *metas);
 int compress_block_range(Ctx *ctx, uint64_t b_lo, uint64_t b_hi);
+
+inline uint64_t front_unsorted(const Ctx *ctx) { return ctx->h_scalars[4]; }
+inline uint64_t front_crlf(const Ctx *ctx) { return ctx->h_scalars[5]; }
 
 }  // namespace s3g
 

@@ -36,14 +36,14 @@ int main(int argc, char** argv)
     return EXIT_SUCCESS;
 }
 
-std::string starch3::Starch::get_client_starch_opt_string(void) { return "n:bghvd:k:?"; }
+std::string starch3::Starch::get_client_starch_opt_string(void) { return "n:bghvud:k:?"; }
 
 struct option* starch3::Starch::get_client_starch_long_options(void)
 {
     static struct option opts[] = {
         {"note", required_argument, NULL, 'n'},   {"bzip2", no_argument, NULL, 'b'},       {"gzip", no_argument, NULL, 'g'},
         {"help", no_argument, NULL, 'h'},         {"version", no_argument, NULL, 'v'},     {"device", required_argument, NULL, 'd'},
-        {"block-size", required_argument, NULL, 'k'}, {NULL, no_argument, NULL, 0}};
+        {"block-size", required_argument, NULL, 'k'}, {"unstarch", no_argument, NULL, 'u'}, {NULL, no_argument, NULL, 0}};
     return opts;
 }
 
@@ -57,6 +57,7 @@ void starch3::Starch::initialize_command_line_options(int argc, char** argv)
         case 'b': set_compression_method(k_bzip2); methods++; break;
         case 'g': set_compression_method(k_gzip); methods++; break;
         case 'd': set_device(std::atoi(optarg)); break;
+        case 'u': set_unstarch(true); break;
         case 'k': {
             int k = std::atoi(optarg);
             if (k < 1 || k > 9) fail(EINVAL, "bzip2 initialization failed - incorrect parameters");
@@ -98,7 +99,8 @@ std::string starch3::Starch::get_client_starch_io_options(void)
            "  --note=\"foo bar...\"   Append note to output archive metadata (optional)\n"
            "  --bzip2 | --gzip      Compression backend (bzip2 is the default; gzip is unsupported)\n"
            "  --device=N            CUDA device to use (default 0)\n"
-           "  --block-size=K        bzip2 block size in 100 kB units, 1..9 (default 9)\n";
+           "  --block-size=K        bzip2 block size in 100 kB units, 1..9 (default 9)\n"
+           "  --unstarch            Decode: the input is a starch3 archive, the output its BED text\n";
 }
 std::string starch3::Starch::get_client_starch_general_options(void)
 {

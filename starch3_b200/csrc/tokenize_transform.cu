@@ -40,7 +40,7 @@ constexpr int FMAXL = FCH / 3 + 2;       // a line with three fields has at leas
 constexpr int FOB = FCH + 512;           // staged output bytes of a chunk (more: direct stores)
 
 // scalar slots (ctx->scalars, u64 each)
-enum { SC_MALFORMED = 1, SC_LASTNL = 2, SC_LINE1 = 3, SC_TOTAL = 8 /* FAgg: 5 slots */ };
+enum { SC_MALFORMED = 1, SC_LASTNL = 2, SC_LINE1 = 3, SC_UNSORTED = 4, SC_CRLF = 5, SC_TOTAL = 8 /* FAgg: 5 slots */ };
 
 // what a tile (or a prefix of tiles) contributes; fagg_op is associative, operands in input order
 struct FAgg {
@@ -332,6 +332,7 @@ struct LineOut {
     uint32_t flag;          // chromosome differs from the previous line (hpp:331), or first line of the input
     uint32_t first_global;  // first line of the input
     uint32_t out_len;
+    uint32_t unsorted;      // starts before the previous element of its chromosome (input hardening)
     int64_t pstop, plen;
 };
 
@@ -343,7 +344,7 @@ __device__ __forceinline__ void line_of_round(const WarpSh &W, const ChunkGeom &
     const uint32_t v = round * 32 + l;
     const bool act = v <= G.k && (v >= 1 || G.has_prev);
     L.owned = act && v >= 1;
-    L.flag = 0; L.first_global = 0; L.out_len = 0; L.pstop = 0; L.plen = 0;
+    L.flag = 0; L.first_global = 0; L.out_len = 0; L.pstop = 0; L.plen = 0; L.unsorted = 0;
     L.P.start = 0; L.P.stop = 0; L.P.rem_off = 0; L.P.name_len = 0; L.P.malformed = 0; L.s = 0; L.e = 0;
     if (act) {
         if (v == 0) { L.s = G.prev_start; L.e = G.start0 - 1; }
@@ -377,7 +378,7 @@ __device__ __forceinline__ void line_of_round(const WarpSh &W, const ChunkGeom &
     if (l == 0) { a = carry_start; b = carry_stop; }
     carry_start = __shfl_sync(0xffffffffu, L.P.start, 31); carry_stop = __shfl_sync(0xffffffffu, L.P.stop, 31);
     if (L.owned) {
-        if (!L.flag) { L.pstop = b; L.plen = (int64_t)((uint64_t)b - (uint64_t)a); }      // hpp:523-532 resets both at a chromosome start
+        if (!L.flag) { L.pstop = b; L.plen = (int64_t)((uint64_t)b - (uint64_t)a); L.unsorted = L.P.start < a; }   // hpp:523-532 resets both at a chromosome start
         int64_t len = (int64_t)((uint64_t)L.P.stop - (uint64_t)L.P.start), d = (int64_t)((uint64_t)L.P.start - (uint64_t)L.pstop);
         uint32_t rem_len = (uint32_t)(L.e - L.s) - L.P.rem_off;
         uint32_t o = (uint32_t)dec_len(d) + 1 + (rem_len ? rem_len + 1 : 0);
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__
                                                      const FAgg *__restrict__ span_pre, const FAgg *__restrict__ tile_pre, const FAgg *__restrict__ chunk_pre,
                                                      const uint32_t *__restrict__ chunk_out, uint64_t n_lines, uint8_t *__restrict__ tf,
                                                      ChromSeed *seeds, unsigned long long *stat_len, unsigned long long *stat_uniq, uint32_t stat_slots,
-                                                     DumpArrays da)
+                                                     uint64_t diag_chroms, unsigned long long *sc, DumpArrays da)
 {
     __shared__ WarpSh Ws[FWARPS];
     __shared__ __align__(16) uint8_t s_out[FWARPS][FOB + 16];
@@ -542,6 +543,7 @@ __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__
     int64_t run_v = ex0.v;                                 // largest stop of the current chromosome so far
     const uint64_t c0 = ex0.chroms - 1;                    // the chromosome the chunk begins in (unless its first line starts one)
     unsigned long long acc_len = 0, acc_uniq = 0;          // sums of the lines that belong to c0
+    uint32_t n_unsorted = 0, n_crlf = 0;                   // diagnostics over the lines of chromosomes < diag_chroms
     int64_t cs = 0, ce = 0;
     const uint32_t rounds = (G.k + 1 + 31) / 32;
     for (uint32_t r = 0; r < rounds; r++) {
@@ -564,6 +566,10 @@ __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__
             const uint64_t o = o_begin + run_out + (inc_out - L.out_len);
             const uint64_t chrom = ex0.chroms + run_ch + ex_ch + L.flag - 1;
             const bool is_halo = halo && L.first_global;
+            if (chrom < diag_chroms && !is_halo) {
+                n_unsorted += L.unsorted;
+                n_crlf += (L.e > L.s && bed[L.e - 1] == '\r') ? 1u : 0u;
+            }
             int64_t rm = L.flag ? INT64_MIN : (pf ? pv : (run_v > pv ? run_v : pv));   // largest stop of the earlier lines of this chromosome
             if (halo && chrom == 0 && carry_max > rm) rm = carry_max;                  // ... including those on other GPUs
             const int64_t s = L.P.start, t = L.P.stop;
@@ -603,6 +609,9 @@ __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__
         run_out += tot_out; run_ch += __popc(mflag);
         run_v = mflag ? tot_v : (run_v > tot_v ? run_v : tot_v);
     }
+    n_unsorted = __reduce_add_sync(0xffffffffu, n_unsorted); n_crlf = __reduce_add_sync(0xffffffffu, n_crlf);
+    if (l == 0 && n_unsorted) atomicAdd(&sc[SC_UNSORTED], (unsigned long long)n_unsorted);
+    if (l == 0 && n_crlf) atomicAdd(&sc[SC_CRLF], (unsigned long long)n_crlf);
     // per-chromosome sums of the chunk's first chromosome: one atomic pair per chunk
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) { acc_len += __shfl_xor_sync(0xffffffffu, acc_len, dd); acc_uniq += __shfl_xor_sync(0xffffffffu, acc_uniq, dd); }
@@ -691,9 +700,12 @@ int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_m
 }
 
 // kernel (2) over the range measured by run_tokenize; dump = also leave the per-line arrays in ctx
-int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump)
+int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump, bool last_part)
 {
     const uint64_t n_lines = out->n_lines, n_chroms = out->n_chroms;
+    // a range that is not the last hands its last chromosome to the next range, which counts that chromosome's lines
+    const uint64_t diag_chroms = last_part ? n_chroms : (n_chroms ? n_chroms - 1 : 0);
+    uint64_t *d_sc = ctx->scalars.as<uint64_t>();
     uint64_t ntiles = (n + (uint64_t)FCH * FWARPS - 1) / ((uint64_t)FCH * FWARPS);
     if (ntiles == 0) ntiles = 1;
     const uint32_t slots = n_chroms <= 4096 ? 32u : 1u;            // same-address atomics serialise: spread a chromosome's sums
@@ -715,22 +727,24 @@ int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out
         da.rem_off = ctx->rem_off.as<uint32_t>(); da.flags = ctx->flags.as<uint8_t>();
         S3G_LAUNCH(ctx, k_front_write<true>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_c.as<FAgg>(), ctx->scan_a.as<FAgg>(),
                    ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(),
-                   stat_len, stat_uniq, slots, da);
+                   stat_len, stat_uniq, slots, diag_chroms, (unsigned long long *)d_sc, da);
     } else {
         S3G_LAUNCH(ctx, k_front_write<false>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_c.as<FAgg>(), ctx->scan_a.as<FAgg>(),
                    ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(),
-                   stat_len, stat_uniq, slots, da);
+                   stat_len, stat_uniq, slots, diag_chroms, (unsigned long long *)d_sc, da);
     }
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + SC_UNSORTED, d_sc + SC_UNSORTED, 16, cudaMemcpyDeviceToHost, ctx->stream));   // read after the caller's next synchronise
     S3G_LAUNCH(ctx, k_chrom_finish, (unsigned)((n_chroms + 127) / 128), 128, 0, ctx->chrom_first.as<ChromSeed>(), stat_len, stat_uniq, slots,
                n_chroms, n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>(), halo);
     return check_launch("transform write");
 }
 
-int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip)
+int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip, bool last_part)
 {
     S3G_TRY(run_tokenize(ctx, d_bed, n, skip, out, 0));
+    ctx->h_scalars[SC_UNSORTED] = 0; ctx->h_scalars[SC_CRLF] = 0;
     if (out->n_lines == 0) return S3G_OK;
-    S3G_TRY(run_transform_rest(ctx, d_bed, n, out, 0, INT64_MIN, tokenize_only));
+    S3G_TRY(run_transform_rest(ctx, d_bed, n, out, 0, INT64_MIN, tokenize_only, last_part));
     if (tokenize_only) {
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
         return check_launch("tokenize");

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     from starch3_b200.api import CChrom, CResult, CBlockDesc
     assert ctypes.sizeof(CChrom) == 72
     assert ctypes.sizeof(CBlockDesc) == 8 + 8 + 4 + 4 + 256
-    assert ctypes.sizeof(CResult) == (12 + 2 + 8) * 8
+    assert ctypes.sizeof(CResult) == (12 + 2 + 8 + 3) * 8
 
 
 def test_no_cpu_fallback():

@@ -174,3 +174,68 @@ def test_pipelined_host_entry_edge_inputs(ctx, oracle, monkeypatch):
     monkeypatch.setenv("S3G_PARTS", "2")
     with pytest.raises(Exception):
         ctx.compress_bed(b"chr1\t1\t2\n" * 50 + b"chr1\t5\n" + b"chr2\t1\t2\n" * 50, 9)
+
+
+@pytest.mark.parametrize("cfg,lines,rng,piece", [(2, 60000, 200_000, 65536), (5, 60000, 4096, 1000), (1, 60000, 300_000, 7), (2, 30000, 1 << 20, 1 << 22)])
+def test_bounded_memory_ingestion(ctx, oracle, cfg, lines, rng, piece):
+    """s3g_stream_*: the input arrives in pieces, at most one range of it is resident beside the open chromosome; ranges
+    smaller than a chromosome (the chromosome waits on the device), smaller than a line's neighbourhood, larger than the
+    input -- always the one-shot archive"""
+    bed = synth.bed(cfg, lines).tobytes()
+    pieces = [bed[i:i + piece] for i in range(0, len(bed), piece)] if piece < len(bed) // 4 or piece > 1000 else \
+        [bed[:5], bed[5:12], bed[12:40000], bed[40000:]]
+    res = ctx.compress_stream(pieces, 9, note="s", range_bytes=rng)
+    assert res.archive == oracle.archive(bed, 9, "s")
+    assert res.n_lines == lines
+
+
+def test_bounded_memory_ingestion_edges(ctx, oracle):
+    assert ctx.compress_stream([], 9).archive == oracle.archive(b"", 9, "")
+    assert ctx.compress_stream([b"chr1\t1\t2\nchr1\t5\t6"], 9).dropped_tail_bytes == 8
+    long_line = b"chr1\t1\t2\t" + b"x" * 20000 + b"\nchr2\t2\t3\n"
+    assert ctx.compress_stream([long_line[:9000], long_line[9000:]], 9, range_bytes=4096).archive == oracle.archive(long_line, 9, "")
+    import starch3_b200 as s3
+    with pytest.raises(s3.Starch3Error) as e:
+        ctx.compress_stream([b"chr1\t1\t2\n" * 3000, b"chr1\t5\n", b"chr2\t1\t2\n" * 3000], 9, range_bytes=8192)
+    assert e.value.code == -4
+    assert ctx.compress_bed(b"chrZ\t0\t1\n", 9).n_lines == 1        # the context is still usable
+
+
+def test_input_hardening_diagnostics(ctx, oracle):
+    """unsorted starts, CRLF line ends and chromosomes that come back are reported, never "repaired": the
+    archive is what the reference's transform + libbz2 give for those bytes"""
+    sorted_bed = synth.bed(2, 20000).tobytes()
+    r = ctx.compress_bed(sorted_bed, 9)
+    assert (r.unsorted_lines, r.crlf_lines, r.reappearing_chroms) == (0, 0, 0)
+    bed = b"chr1\t50\t60\nchr1\t10\t20\nchr1\t10\t25\nchr2\t5\t9\r\nchr2\t7\t8\tname\r\nchr1\t1\t2\nchr2\t1\t2\n"
+    r = ctx.compress_bed(bed, 9)
+    assert r.unsorted_lines == 1 and r.crlf_lines == 2 and r.reappearing_chroms == 2
+    assert r.archive == oracle.archive(bed, 9, "")
+    # the carriage return of a BED3 line is not part of the number (sscanf stops there, hpp:306-307) and is not kept;
+    # behind a fourth field it is an ordinary byte of the remainder
+    tf, _, _ = oracle.transform(b"c\t1\t2\r\nc\t3\t4\tx\r\n")
+    assert tf == b"p1\n1\n1\tx\r\n"
+    assert ctx.transform(b"c\t1\t2\r\nc\t3\t4\tx\r\n")[0] == tf
+
+
+def test_cli_streaming_and_unstarch(ctx, tmp_path):
+    """stdin goes through the bounded-memory entry (64 MiB pieces; the range forced small here), --unstarch is the
+    decoder path; the warnings of the input diagnostics reach stderr"""
+    import os
+    import subprocess
+    import starch3_b200 as s3
+    exe = os.path.join(os.path.dirname(s3.lib_path), "starch3")
+    bed = synth.bed(5, 40000).tobytes()
+    env = dict(os.environ, S3G_STREAM_RANGE="150000")
+    p = subprocess.run([exe, "--note", "st"], input=bed, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr[-500:]
+    assert p.stdout == ctx.compress_bed(bed, 9, note="st").archive
+    f = tmp_path / "a.starch3"
+    f.write_bytes(p.stdout)
+    u = subprocess.run([exe, "--unstarch", str(f)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert u.returncode == 0, u.stderr[-500:]
+    assert u.stdout == bed
+    u2 = subprocess.run([exe, "--unstarch"], input=p.stdout[:-50], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert u2.returncode != 0 and b"Error:" in u2.stderr
+    w = subprocess.run([exe], input=b"chr1\t50\t60\nchr1\t10\t20\r\nchr2\t1\t2\nchr1\t1\t2\n", stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert w.returncode == 0 and b"not sorted" in w.stderr and b"CR LF" in w.stderr and b"repeat an earlier chromosome" in w.stderr

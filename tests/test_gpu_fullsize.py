@@ -132,3 +132,17 @@ def test_archive_byte_parity_bucket_form_of_the_block_sort(ctx, oracle, monkeypa
         res = ctx.compress_bed(bed, 9, note="bucket")
         assert ctx.sort_stats[0] - before[0] >= res.n_blocks - 24
         _same(res.archive, oracle.archive_mt(bed, 9, "bucket"))
+
+
+@pytest.mark.parametrize("cfg,lines", [(2, 10_000_000), (3, 30_000_000)])
+def test_decoder_roundtrip_at_size(ctx, cfg, lines):
+    """the decoder path at size: cfg2 at its 10 M lines (296 blocks over 24 streams), 30 M lines of cfg3 (one stream of
+    75 blocks): the archive decodes to the BED text it was made from, every block and stream CRC checked on the way"""
+    bed = synth.bed(cfg, lines)
+    res = ctx.compress_bed(bed, 9, note="", lazy=True)
+    arc = bytes(res.archive_view)
+    n_blocks = res.n_blocks
+    del res
+    got, info = ctx.decompress_archive(arc)
+    assert info["n_blocks"] == n_blocks
+    assert len(got) == bed.nbytes and np.array_equal(np.frombuffer(got, dtype=np.uint8), bed)
