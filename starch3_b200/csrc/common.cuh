@@ -160,6 +160,22 @@ struct Ctx {
         (ctx)->launches++;                                                  \
     } while (0)
 
+// the same for a kernel whose CTAs form thread-block clusters of `cs` along x (cs == 1: an ordinary launch)
+#define S3G_LAUNCH_CLUSTER(ctx, kernel, grid, block, smem, cs, ...)          \
+    do {                                                                    \
+        int pi_ = s3g::prof_begin((ctx), #kernel);                          \
+        cudaLaunchConfig_t cfg_ = {};                                       \
+        cfg_.gridDim = (grid); cfg_.blockDim = (block);                     \
+        cfg_.dynamicSmemBytes = (smem); cfg_.stream = (ctx)->stream;        \
+        cudaLaunchAttribute at_[1];                                         \
+        at_[0].id = cudaLaunchAttributeClusterDimension;                    \
+        at_[0].val.clusterDim.x = (cs); at_[0].val.clusterDim.y = 1; at_[0].val.clusterDim.z = 1; \
+        cfg_.attrs = at_; cfg_.numAttrs = (cs) > 1 ? 1 : 0;                 \
+        cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                     \
+        s3g::prof_end((ctx), pi_);                                          \
+        (ctx)->launches++;                                                  \
+    } while (0)
+
 int check_launch(const char *what);
 // stage mark: the time until the next mark is charged to `stage` (s3g_result.stage_ms)
 void stage_mark(Ctx *ctx, int stage);

@@ -1,8 +1,14 @@
 // mtf_huff.cu -- kernels (3c) and (3d): move-to-front + RUNA/RUNB zero-run coding
 // (generateMTFValues, bz/compress.c:120-231) and bzip2's iterative Huffman table
 // selection and emission (sendMTFValues, bz/compress.c:239-598; BZ2_hbMakeCodeLengths
-// / BZ2_hbAssignCodes, bz/huffman.c:63-166).  One CTA per bzip2 block.
+// / BZ2_hbAssignCodes, bz/huffman.c:63-166).  One CTA per bzip2 block when a batch holds enough blocks to fill the
+// SMs; a batch of fewer blocks spreads every block over a thread-block CLUSTER of 2, 4 or 8 CTAs that exchange
+// what they need through distributed shared memory (the per-symbol last occurrences of the MTF chunks; the symbol
+// frequencies, selector history and bit counts of the Huffman groups).
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace s3g {
 
@@ -373,7 +379,10 @@ __global__ void __launch_bounds__(MS, 2) k_mtf_small(const uint8_t *lcol, uint8_
     int *s_last = reinterpret_cast<int *>(smem_raw);            // [rows][MS], rows = largest alphabet (<= MTF_REG_MAX) in the batch
     int *s_freq = s_last + rows * MS;                           // [258]
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_freq + 260);
-    const uint32_t lb = blockIdx.x;
+    int *s_pub = reinterpret_cast<int *>(s_scan + 40);          // [256] cluster form: last occurrence of every symbol in this CTA's chunks
+    // grid = (cs, blocks): the cs CTAs of a cluster share one bzip2 block, CTA `rank` takes chunks rank * MS .. of its MS * cs
+    const uint32_t lb = blockIdx.y;
+    const int rank = (int)blockIdx.x, cs = (int)gridDim.x;
     const int n = (int)blocks[lb].nblock;
     const int a = (int)blocks[lb].n_in_use;
     if (a > MTF_REG_MAX || (a <= 24) != SMALL) return;          // handled by k_mtf or by the other instantiation
@@ -385,10 +394,9 @@ __global__ void __launch_bounds__(MS, 2) k_mtf_small(const uint8_t *lcol, uint8_
     for (int i = tid; i < a * MS; i += MS) s_last[i] = 0;
     for (int i = tid; i < 258; i += MS) s_freq[i] = 0;
     __syncthreads();
-    int chunk = (((n + MS - 1) / MS) + 7) & ~7;
-    int beg = tid * chunk, end = beg + chunk;
-    if (beg > n) beg = n;
-    if (end > n) end = n;
+    int chunk = (((n + MS * cs - 1) / (MS * cs)) + 7) & ~7;
+    long long beg_ll = (long long)(rank * MS + tid) * chunk;
+    int beg = beg_ll > n ? n : (int)beg_ll, end = beg_ll + chunk > n ? n : (int)(beg_ll + chunk);
     // phase A: last occurrence (position + 1) of every symbol inside my chunk: a forward sweep of
     // fire-and-forget shared-memory stores (bank = tid, conflict-free), 8 bytes per load
     for (int p = beg; p < end; p += 8) {
@@ -399,15 +407,30 @@ __global__ void __launch_bounds__(MS, 2) k_mtf_small(const uint8_t *lcol, uint8_
             if (k < lim) s_last[((uint32_t)(in8 >> (8 * k)) & 0xffu) * MS + tid] = p + k + 1;
     }
     __syncthreads();
-    // phase B: exclusive "latest occurrence" over the chunks
+    // phase B: exclusive "latest occurrence" over the chunks; in the cluster form the chunks of the CTAs before this one
+    // come first: every CTA publishes where it last saw each symbol, and reads the nearest earlier CTA that saw it
+    if (cs > 1) {
+        if (tid < a) {
+            int last = 0;
+            for (int ch = 0; ch < MS; ch++) { int t = s_last[tid * MS + ch]; if (t) last = t; }
+            s_pub[tid] = last;
+        }
+        cg::this_cluster().sync();
+    }
     if (tid < a) {
         int run = -(tid + 1);
+        if (cs > 1)
+            for (int r = rank - 1; r >= 0; r--) {
+                int v = cg::this_cluster().map_shared_rank(s_pub, r)[tid];
+                if (v) { run = v; break; }
+            }
         for (int ch = 0; ch < MS; ch++) {
             int t = s_last[tid * MS + ch];
             s_last[tid * MS + ch] = run;
             if (t) run = t;
         }
     }
+    if (cs > 1) cg::this_cluster().sync();      // no CTA leaves while its table may still be read
     __syncthreads();
     // phase C: ranks
     if (beg < end) {
@@ -504,6 +527,16 @@ __global__ void __launch_bounds__(MT) k_mtf(const uint8_t *lcol, uint8_t *mtf0, 
 static const auto k_mtf_list_small = k_mtf_small<MS_SMALL, true>;
 static const auto k_mtf_list_big = k_mtf_small<MS_BIG, false>;
 
+// CTAs per bzip2 block for a batch of nb blocks when `slots` CTAs of the kernel fit the GPU at once: 1, 2, 4 or 8
+// (S3G_CLUSTER=n forces a size, tests run both forms)
+static unsigned cluster_size(uint64_t nb, uint64_t slots)
+{
+    unsigned cs = 1;
+    while (cs < 8 && (uint64_t)(cs * 2) * nb <= slots) cs *= 2;
+    if (const char *e = getenv("S3G_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cs = (unsigned)v; }
+    return cs;
+}
+
 int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
 {
     if (nb == 0) return S3G_OK;
@@ -528,7 +561,7 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
         else if (a <= 24) any_small = true;
         else if (a <= MTF_REG_MAX) any_big = true;
     }
-    const size_t tail_smem = 260 * 4 + 40 * 4;
+    const size_t tail_smem = 260 * 4 + 40 * 4 + 256 * 4;
     // zero-run coding inside the MTF kernels (one CTA per block) when the batch fills the SMs, as tile-parallel kernels of
     // its own when it does not (S3G_ZRUN=fused|split overrides: both forms are tested)
     int fused = nb >= (uint64_t)SM_COUNT ? 1 : 0;
@@ -539,11 +572,13 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
         ctx->attr_mtf = true;
     }
     S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
+    // a batch that leaves SMs idle spreads every block over a cluster of cs CTAs (cs * nb <= two CTAs per SM)
+    const unsigned cs = fused ? 1u : cluster_size(nb, 2 * SM_COUNT);
     if (any_small)
-        S3G_LAUNCH(ctx, k_mtf_list_small, (unsigned)nb, MS_SMALL, (size_t)std::min(rows, 24) * MS_SMALL * 4 + tail_smem, ctx->lcol.as<uint8_t>(),
+        S3G_LAUNCH_CLUSTER(ctx, k_mtf_list_small, dim3(cs, (unsigned)nb), MS_SMALL, (size_t)std::min(rows, 24) * MS_SMALL * 4 + tail_smem, cs, ctx->lcol.as<uint8_t>(),
                    ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, std::min(rows, 24), fused);
     if (any_big)
-        S3G_LAUNCH(ctx, k_mtf_list_big, (unsigned)nb, MS_BIG, (size_t)rows * MS_BIG * 4 + tail_smem, ctx->lcol.as<uint8_t>(),
+        S3G_LAUNCH_CLUSTER(ctx, k_mtf_list_big, dim3(cs, (unsigned)nb), MS_BIG, (size_t)rows * MS_BIG * 4 + tail_smem, cs, ctx->lcol.as<uint8_t>(),
                    ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, rows, fused);
     S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
                ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, fused);
@@ -665,6 +700,10 @@ struct HuffSmem {
     uint32_t scan[33];
     uint32_t tab_bits[8];
     uint32_t hdr_bits;
+    // cluster form: what the CTAs of a block tell each other
+    int32_t  rtot[6][ALPHA_MAX];       // symbol frequencies summed over the cluster
+    uint32_t pub_last[6];              // last group (+1) of this CTA's range that chose table t
+    uint32_t pub_bits[2];              // selector bits / symbol bits of this CTA's range
 };
 
 // first_block_flags: bit0 set -> this block also carries nothing extra; stream headers are added by the assembler
@@ -675,7 +714,9 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HuffSmem &S = *reinterpret_cast<HuffSmem *>(smem_raw);
-    const uint32_t lb = blockIdx.x;
+    // grid = (cs, blocks): the cs CTAs of a cluster share one bzip2 block; CTA `rank` owns the groups [gr0, gr1)
+    const uint32_t lb = blockIdx.y;
+    const int rank = (int)blockIdx.x, cs = (int)gridDim.x;
     BlockInfo &B = blocks[lb];
     const int nmtf = (int)B.n_mtf;
     const int alpha = (int)B.n_in_use + 2;
@@ -686,6 +727,7 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
     const int ng = nmtf < 200 ? 2 : nmtf < 600 ? 3 : nmtf < 1200 ? 4 : nmtf < 2400 ? 5 : 6;   // bz/compress.c:273-277
     const int nsel = (nmtf + G_SIZE - 1) / G_SIZE;
     const int tid = threadIdx.x;
+    const int gr0 = (int)((long long)nsel * rank / cs), gr1 = (int)((long long)nsel * (rank + 1) / cs);
 
     for (int i = tid; i < 6 * (ALPHA_MAX + 2); i += HT) (&S.len[0][0])[i] = 15;   // BZ_GREATER_ICOST
     __syncthreads();
@@ -711,7 +753,7 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
             S.len_pack[v] = pk;
         }
         __syncthreads();
-        for (int g = tid; g < nsel; g += HT) {
+        for (int g = gr0 + tid; g < gr1; g += HT) {
             const int gs = g * G_SIZE, cnt = min(G_SIZE, nmtf - gs);
             uint32_t w[G_SIZE / 2];
             const uint32_t *src = reinterpret_cast<const uint32_t *>(mtfv + gs);     // gs * 2 bytes is 4-byte aligned
@@ -756,7 +798,18 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
             }
         }
         __syncthreads();
-        if (tid < ng) hb_make_lengths(S.len[tid], S.rfreq[tid], alpha, 17, S.heaps[tid]);
+        if (cs > 1) {
+            // every CTA sums the frequencies of all CTAs and builds the same lengths from them
+            cg::cluster_group cl = cg::this_cluster();
+            cl.sync();
+            for (int i = tid; i < 6 * ALPHA_MAX; i += HT) {
+                int sum = 0;
+                for (int r = 0; r < cs; r++) sum += (&cl.map_shared_rank(&S, r)->rfreq[0][0])[i];
+                (&S.rtot[0][0])[i] = sum;
+            }
+            cl.sync();                          // all have read: the next pass may clear rfreq
+            if (tid < ng) hb_make_lengths(S.len[tid], S.rtot[tid], alpha, 17, S.heaps[tid]);
+        } else if (tid < ng) hb_make_lengths(S.len[tid], S.rfreq[tid], alpha, 17, S.heaps[tid]);
         __syncthreads();
     }
     // codes (bz/huffman.c:152-166) and per-table header sizes
@@ -785,8 +838,8 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
     // index (virtual last use -(t+1)).  Each thread owns a run of selectors and needs, per table,
     // the last use before its run: six exclusive block-wide max-scans.
     {
-        const int spt0 = (nsel + HT - 1) / HT;
-        const int a0 = min(tid * spt0, nsel), a1 = min(a0 + spt0, nsel);
+        const int spt0 = (gr1 - gr0 + HT - 1) / HT;
+        const int a0 = min(gr0 + tid * spt0, gr1), a1 = min(a0 + spt0, gr1);
         int last[6];
 #pragma unroll
         for (int t = 0; t < 6; t++) last[t] = 0;                 // (position + 1), 0 = not used in my run
@@ -796,12 +849,23 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
             for (int t = 0; t < 6; t++) if (v == t) last[t] = i + 1;
         }
         int before[6];
+        uint32_t exv[6];
 #pragma unroll
         for (int t = 0; t < 6; t++) {
             uint32_t tot;
-            uint32_t ex = block_excl_max<uint32_t>((uint32_t)last[t], S.scan, &tot);
-            before[t] = ex ? (int)ex : -t;                         // -t orders never-used tables 0,1,2,... (ties impossible)
+            exv[t] = block_excl_max<uint32_t>((uint32_t)last[t], S.scan, &tot);
+            if (tid == 0) S.pub_last[t] = tot;
         }
+        if (cs > 1) {
+            // the groups of the CTAs before this one come first
+            cg::cluster_group cl = cg::this_cluster();
+            cl.sync();
+#pragma unroll
+            for (int t = 0; t < 6; t++)
+                for (int r = 0; r < rank; r++) { uint32_t v = cl.map_shared_rank(&S, r)->pub_last[t]; if (v > exv[t]) exv[t] = v; }
+        }
+#pragma unroll
+        for (int t = 0; t < 6; t++) before[t] = exv[t] ? (int)exv[t] : -t;   // -t orders never-used tables 0,1,2,... (ties impossible)
         for (int i = a0; i < a1; i++) {
             int v = S.selector[i];
             int lv = 0;
@@ -817,8 +881,8 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
     }
     __syncthreads();
     // ---- layout: [fixed part][selectors][tables][symbols] ----
-    const int spt = (nsel + HT - 1) / HT;          // selectors (= groups) per thread
-    const int g0 = min(tid * spt, nsel), g1 = min(g0 + spt, nsel);
+    const int spt = (gr1 - gr0 + HT - 1) / HT;     // selectors (= groups) per thread
+    const int g0 = min(gr0 + tid * spt, gr1), g1 = min(g0 + spt, gr1);
     uint32_t my_sel_bits = 0, my_sym_bits = 0;
     for (int g = g0; g < g1; g++) {
         my_sel_bits += S.sel_mtf[g] + 1u;
@@ -837,14 +901,28 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
     uint32_t sel_total, sym_total;
     uint32_t sel_ex = block_excl_sum<uint32_t>(my_sel_bits, S.scan, &sel_total);
     uint32_t sym_ex = block_excl_sum<uint32_t>(my_sym_bits, S.scan, &sym_total);
+    if (cs > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        if (tid == 0) { S.pub_bits[0] = sel_total; S.pub_bits[1] = sym_total; }
+        cl.sync();
+        uint32_t sa = 0, sb = 0, ta = 0, tb = 0;
+        for (int r = 0; r < cs; r++) {
+            const HuffSmem *R = cl.map_shared_rank(&S, r);
+            uint32_t x = R->pub_bits[0], y = R->pub_bits[1];
+            if (r < rank) { sa += x; sb += y; }
+            ta += x; tb += y;
+        }
+        sel_ex += sa; sym_ex += sb; sel_total = ta; sym_total = tb;
+    }
     uint32_t tab_total = 0, tab_off[6];
     for (int t = 0; t < ng; t++) { tab_off[t] = tab_total; tab_total += S.tab_bits[t]; }
     const uint64_t sel_base = S.hdr_bits, tab_base = sel_base + sel_total, sym_base = tab_base + tab_total;
     const uint64_t total_bits = sym_base + sym_total;
     const uint32_t total_words = (uint32_t)((total_bits + 31) >> 5) + 1;
-    for (uint32_t i = tid; i < total_words; i += HT) words[i] = 0;
+    for (uint32_t i = rank * HT + tid; i < total_words; i += HT * cs) words[i] = 0;
     __syncthreads();
-    if (tid == 0) {
+    if (cs > 1) { __threadfence(); cg::this_cluster().sync(); }      // every word is cleared before anyone ORs into it; last remote read is behind us
+    if (rank == 0 && tid == 0) {
         BitW bw; bw.begin(words, 0);
         if (with_block_header) {     // bz/compress.c:632-650
             bw.put(24, 0x314159u); bw.put(24, 0x265359u);
@@ -868,7 +946,7 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
         for (int g = g0; g < g1; g++) { int j = S.sel_mtf[g]; bw.put(j + 1, (1u << (j + 1)) - 2u); }
         bw.end();
     }
-    if (tid >= 128 && tid < 128 + ng) {   // delta-coded tables (:531-539)
+    if (rank == 0 && tid >= 128 && tid < 128 + ng) {   // delta-coded tables (:531-539)
         int t = tid - 128;
         BitW bw; bw.begin(words, tab_base + tab_off[t]);
         int cur = S.len[t][0];
@@ -903,10 +981,11 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
         }
         bw.end();
     }
-    if (tid == 0) B.n_bits = total_bits;
+    if (rank == 0 && tid == 0) B.n_bits = total_bits;
     if (sel_out) {
-        for (int i = tid; i < nsel; i += HT) sel_out[(uint64_t)lb * (MAX_SEL + 2) + i] = S.selector[i];
-        for (int i = tid; i < 6 * ALPHA_MAX; i += HT) len_out[(uint64_t)lb * 6 * ALPHA_MAX + i] = S.len[i / ALPHA_MAX][i % ALPHA_MAX];
+        for (int i = gr0 + tid; i < gr1; i += HT) sel_out[(uint64_t)lb * (MAX_SEL + 2) + i] = S.selector[i];
+        if (rank == 0)
+            for (int i = tid; i < 6 * ALPHA_MAX; i += HT) len_out[(uint64_t)lb * 6 * ALPHA_MAX + i] = S.len[i / ALPHA_MAX][i % ALPHA_MAX];
     }
 }
 
@@ -923,13 +1002,16 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
     for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
     S3G_BYTES(ctx, 6 * 2 * 0.67 * N + 0.25 * N);      // 4 selection passes + size + emit over uint16 symbols, bits out
     if (nb > (uint64_t)SM_COUNT)
-        S3G_LAUNCH(ctx, k_huff<512>, (unsigned)nb, 512, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
+        S3G_LAUNCH(ctx, k_huff<512>, dim3(1, (unsigned)nb), 512, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
                    ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
                    d_sel_out, d_len_out, with_block_header);
-    else
-        S3G_LAUNCH(ctx, k_huff<1024>, (unsigned)nb, 1024, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
+    else {
+        // fewer blocks than SMs: every block over a cluster of cs CTAs (one CTA of 1024 threads per SM)
+        const unsigned cs = cluster_size(nb, SM_COUNT);
+        S3G_LAUNCH_CLUSTER(ctx, k_huff<1024>, dim3(cs, (unsigned)nb), 1024, sizeof(HuffSmem), cs, ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
                    ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
                    d_sel_out, d_len_out, with_block_header);
+    }
     return check_launch("huff");
 }
 

@@ -376,6 +376,41 @@ def test_mtf_zero_run_forms(ctx, oracle, name, blk, zrun, monkeypatch):
     assert np.array_equal(freq[:nu + 2], ofreq[:nu + 2])
 
 
+@pytest.mark.parametrize("cs", [1, 2, 4, 8])
+@pytest.mark.parametrize("name", ["digits", "tiny5", "random256", "repeats", "tf_cfg2", "tf_cfg4"])
+def test_mtf_and_huffman_cluster_sizes(ctx, oracle, name, cs, monkeypatch):
+    """A batch smaller than the GPU spreads each bzip2 block over a thread-block cluster of 2, 4 or 8 CTAs (mtf_huff.cu:
+    last occurrences, symbol frequencies, selector history and bit counts go through distributed shared memory).  Every
+    size, forced, gives the ranks, frequencies, selectors, code lengths and bits of the one-CTA form and of the oracle."""
+    monkeypatch.setenv("S3G_CLUSTER", str(cs))
+    blk = _resolve_block(oracle, name, dict(BLOCKS)[name])
+    ptr, _ = oracle.bwt(blk)
+    in_use = np.zeros(256, dtype=np.uint8)
+    in_use[np.frombuffer(blk, dtype=np.uint8)] = 1
+    omtfv, ofreq, nu = oracle.mtf(blk, ptr, in_use)
+    mtfv, freq = ctx.mtf(blk, ptr, in_use)
+    assert np.array_equal(mtfv, omtfv)
+    assert np.array_equal(freq[:nu + 2], ofreq[:nu + 2])
+    oh = oracle.huff_select(omtfv, ofreq, nu)
+    h = ctx.huff(omtfv, ofreq, in_use)
+    assert np.array_equal(h["selector"], oh["selector"])
+    assert np.array_equal(h["len"][:oh["n_groups"], :nu + 2], oh["len"][:oh["n_groups"], :nu + 2])
+    if oracle.have_ref():
+        ref = oracle.ref_mtf_huff(blk, ptr, in_use)
+        assert h["nbits"] == ref["nbits"]
+        assert np.array_equal(h["bits"], ref["bits"])
+
+
+@pytest.mark.parametrize("cs", [1, 2, 4, 8])
+def test_archive_with_every_cluster_size(ctx, oracle, cs, monkeypatch):
+    monkeypatch.setenv("S3G_CLUSTER", str(cs))
+    monkeypatch.setenv("S3G_PARTS", "1")
+    bed = synth.bed(5, 60000).tobytes()
+    assert ctx.compress_bed(bed, 9, note="c").archive == oracle.archive(bed, 9, "c")
+    bed = synth.bed(4, 40000).tobytes()          # 70 symbols: the 512-thread form of the MTF kernel
+    assert ctx.compress_bed(bed, 9, note="c").archive == oracle.archive(bed, 9, "c")
+
+
 @pytest.mark.parametrize("zrun", ["fused", "split"])
 def test_archive_with_either_zero_run_form(ctx, oracle, zrun, monkeypatch):
     monkeypatch.setenv("S3G_ZRUN", zrun)
