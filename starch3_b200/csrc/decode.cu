@@ -80,19 +80,35 @@ __global__ void k_find_magic(const uint8_t *__restrict__ z, uint64_t n_words, ui
 enum { DE_OK = 0, DE_RANDOMISED = -1, DE_HEADER = -2, DE_SELECTOR = -3, DE_CODELEN = -4, DE_SYMBOL = -5, DE_OVERRUN = -6, DE_ORIGPTR = -7,
        DE_TRUNCATED = -8 };
 
+// The 32 lanes of the decoding warp run the SAME decode in lockstep (identical state, broadcast reads): the symbol loop is
+// serial, but this way the compressed words come into shared memory 2 KiB at a time through coalesced loads, and the
+// decoded bytes leave through coalesced 16-byte stores, instead of one exposed global-memory round trip per word.
+constexpr int DEC_IBW = 512;           // compressed words staged at a time
+constexpr int DEC_OB = 2048;           // decoded bytes staged before they are written out
 struct BitReader {
     const uint8_t *z;
-    uint64_t wi;           // next word to fetch
+    uint32_t *ib;          // [DEC_IBW] staged big-endian words
+    uint64_t gw;           // payload word index of ib[0]
+    int ipos;              // next word of ib to take
     uint64_t buf;          // unread bits, left aligned
     int cnt;               // how many
-    __device__ __forceinline__ void init(const uint8_t *zz, uint64_t bit)
+    __device__ __forceinline__ void refill()
     {
-        z = zz; wi = bit >> 5; buf = 0; cnt = 0;
+        __syncwarp();
+        for (int k = threadIdx.x & 31; k < DEC_IBW; k += 32) ib[k] = be32(z, gw + k);
+        __syncwarp();
+        ipos = 0;
+    }
+    __device__ __forceinline__ void init(const uint8_t *zz, uint32_t *stage, uint64_t bit)
+    {
+        z = zz; ib = stage; gw = bit >> 5; buf = 0; cnt = 0;
+        refill();
         if (bit & 31) get((int)(bit & 31));
     }
     __device__ __forceinline__ void fill()
     {
-        buf |= (uint64_t)be32(z, wi++) << (32 - cnt);
+        if (ipos == DEC_IBW) { gw += DEC_IBW; refill(); }
+        buf |= (uint64_t)ib[ipos++] << (32 - cnt);
         cnt += 32;
     }
     __device__ __forceinline__ uint32_t get(int k)            // 1 <= k <= 32
@@ -108,7 +124,7 @@ struct BitReader {
         return (uint32_t)(buf >> (64 - k));
     }
     __device__ __forceinline__ void skip(int k) { buf <<= k; cnt -= k; }
-    __device__ __forceinline__ uint64_t pos() const { return wi * 32 - (uint64_t)cnt; }
+    __device__ __forceinline__ uint64_t pos() const { return (gw + (uint64_t)ipos) * 32 - (uint64_t)cnt; }
 };
 
 constexpr int LUT_BITS = 9;
@@ -120,19 +136,21 @@ struct DecSh {
     uint16_t lut[6][1 << LUT_BITS];      // (code length << 9) | symbol; 0 = longer than LUT_BITS
     uint8_t yy[256], seq2unseq[256];
     int32_t min_len[6];
+    uint32_t in_stage[DEC_IBW];
+    __align__(16) uint8_t out_stage[DEC_OB];
 };
 
 __global__ void __launch_bounds__(32) k_bz_decode(const uint8_t *__restrict__ z, DecBlock *blocks, uint8_t *lcol)
 {
     __shared__ DecSh S;
     DecBlock &B = blocks[blockIdx.x];
-    if (threadIdx.x != 0) return;
+    const unsigned lane = threadIdx.x;
     uint8_t *L = lcol + (uint64_t)blockIdx.x * BLK_STRIDE;
     BitReader br;
-    br.init(z, B.bit_pos + 48);
-    B.nblock = 0; B.end_bit = 0;
-#define DEC_FAIL(code) do { B.status = (code); return; } while (0)
-    B.crc = br.get(32);
+    br.init(z, S.in_stage, B.bit_pos + 48);
+    if (lane == 0) { B.nblock = 0; B.end_bit = 0; }
+#define DEC_FAIL(code) do { if (lane == 0) B.status = (code); return; } while (0)
+    const uint32_t stored_crc = br.get(32);
     if (br.get(1)) DEC_FAIL(DE_RANDOMISED);                        // bz/decompress.c:226: never written by 1.0.x compressors
     const uint32_t orig = br.get(24);
     // symbols in use (bz/decompress.c:243-262)
@@ -208,7 +226,19 @@ __global__ void __launch_bounds__(32) k_bz_decode(const uint8_t *__restrict__ z,
     for (int i = 0; i < 256; i++) S.yy[i] = (uint8_t)i;
     const int EOB = n_in_use + 1;
     const uint32_t nmax = B.nblock_max;
-    uint32_t nblock = 0;
+    uint32_t nblock = 0, flushed = 0;       // nblock: bytes decoded; flushed: of them, written to L
+    // a decoded byte goes to the staging strip; a full strip leaves as 16-byte vectors, four per lane
+    auto emit = [&](uint8_t by) {
+        S.out_stage[nblock - flushed] = by;
+        nblock++;
+        if (nblock - flushed == DEC_OB) {
+            __syncwarp();
+            for (int k = lane; k < DEC_OB / 16; k += 32)
+                *reinterpret_cast<uint4 *>(L + flushed + 16 * k) = *reinterpret_cast<const uint4 *>(S.out_stage + 16 * k);
+            __syncwarp();
+            flushed = nblock;
+        }
+    };
     int group_no = -1, group_pos = 0, g = 0;
     auto next_sym = [&](int &sym) -> int {
         if (group_pos == 0) {
@@ -248,8 +278,7 @@ __global__ void __launch_bounds__(32) k_bz_decode(const uint8_t *__restrict__ z,
             es++;
             const uint8_t uc = S.seq2unseq[S.yy[0]];
             if ((uint64_t)nblock + (uint64_t)es > nmax) DEC_FAIL(DE_OVERRUN);
-            for (int q = 0; q < es; q++) L[nblock + q] = uc;
-            nblock += (uint32_t)es;
+            for (int q = 0; q < es; q++) emit(uc);
             continue;
         }
         if (nblock >= nmax) DEC_FAIL(DE_OVERRUN);
@@ -258,13 +287,15 @@ __global__ void __launch_bounds__(32) k_bz_decode(const uint8_t *__restrict__ z,
         const uint8_t uc = S.yy[nn];
         for (int q = nn; q > 0; q--) S.yy[q] = S.yy[q - 1];
         S.yy[0] = uc;
-        L[nblock++] = S.seq2unseq[uc];
+        emit(S.seq2unseq[uc]);
         if ((rc = next_sym(sym)) != DE_OK) DEC_FAIL(rc);
         if ((nblock & 4095u) == 0 && br.pos() > B.limit_bit) DEC_FAIL(DE_TRUNCATED);
     }
+    __syncwarp();
+    for (uint32_t k = flushed + lane; k < nblock; k += 32) L[k] = S.out_stage[k - flushed];
     if (orig >= nblock) DEC_FAIL(DE_ORIGPTR);                   // bz/decompress.c:461
     if (br.pos() > B.limit_bit) DEC_FAIL(DE_TRUNCATED);
-    B.nblock = nblock; B.orig_ptr = orig; B.end_bit = br.pos(); B.status = DE_OK;
+    if (lane == 0) { B.nblock = nblock; B.orig_ptr = orig; B.crc = stored_crc; B.end_bit = br.pos(); B.status = DE_OK; }
 #undef DEC_FAIL
 }
 
@@ -447,15 +478,46 @@ template <bool WRITE> __device__ __forceinline__ uint32_t unrle_walk(const uint8
     return o;
 }
 
-template <bool WRITE> __global__ void __launch_bounds__(128) k_unrle(DecBlock *blocks, uint32_t nb, const uint8_t *in_all, uint8_t *out)
+// A block is cut into UNRLE_S segments, a warp each.  A segment starts at a position q with byte[q] != byte[q-1] and
+// byte[q-1] != byte[q-2]: q cannot be a count byte (that needs four equal bytes before it) and it opens a new run whatever
+// came before, so the walk can start there with a fresh state.  seg_len: [blocks][UNRLE_S] decoded bytes per segment.
+constexpr uint32_t UNRLE_S = 64;
+__device__ __forceinline__ uint32_t unrle_sync_point(const uint8_t *__restrict__ in, uint32_t n, uint32_t from)
 {
-    const uint32_t b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const unsigned l = threadIdx.x & 31;
+    if (from == 0) return 0;
+    for (uint32_t base = from; base < n; base += 32) {
+        const uint32_t i = base + l;
+        bool ok = false;
+        if (i < n && i >= 2) { const uint8_t b0 = in[i], b1 = in[i - 1], b2 = in[i - 2]; ok = b0 != b1 && b1 != b2; }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) return base + (uint32_t)__ffs((int)m) - 1;
+    }
+    return n;
+}
+template <bool WRITE> __global__ void __launch_bounds__(128) k_unrle(DecBlock *blocks, uint32_t nb, const uint8_t *in_all, uint8_t *out, uint32_t *seg_len)
+{
+    const uint32_t w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t b = w / UNRLE_S, sg = w % UNRLE_S;
+    const unsigned l = threadIdx.x & 31;
     if (b >= nb) return;
     DecBlock &B = blocks[b];
     if (B.status != DE_OK) return;
     const uint8_t *in = in_all + (uint64_t)b * BLK_STRIDE;
-    uint32_t len = unrle_walk<WRITE>(in, B.nblock, WRITE ? out + B.out_off : nullptr);
-    if (!WRITE && (threadIdx.x & 31) == 0) B.out_len = len;
+    const uint32_t n = B.nblock;
+    const uint32_t per = ((n + UNRLE_S - 1) / UNRLE_S + 31) & ~31u;
+    const uint32_t nom0 = min(sg * per, n), nom1 = min((sg + 1) * per, n);
+    const uint32_t s0 = unrle_sync_point(in, n, nom0);
+    const uint32_t s1 = sg + 1 == UNRLE_S ? n : unrle_sync_point(in, n, nom1);
+    uint8_t *dst = nullptr;
+    if (WRITE) {
+        uint32_t before = 0;
+        for (uint32_t k = l; k < sg; k += 32) before += seg_len[(uint64_t)b * UNRLE_S + k];
+        before = __reduce_add_sync(0xffffffffu, before);
+        dst = out + B.out_off + before;
+    }
+    const uint32_t len = s1 > s0 ? unrle_walk<WRITE>(in + s0, s1 - s0, dst) : 0;
+    if (!WRITE && l == 0) { seg_len[(uint64_t)b * UNRLE_S + sg] = len; atomicAdd(&B.out_len, len); }
 }
 
 // ---- inverse transform ---------------------------------------------------------------------------------
@@ -721,7 +783,9 @@ static int decode_streams(Ctx *ctx, const uint8_t *d_z, uint64_t nz, const std::
         S3G_LAUNCH(ctx, k_ibwt_walk_b, wg, 256, 0, d_blocks, ctx->sa.as<uint32_t>(), ctx->io_e.as<uint32_t>(), ctx->mtf0.as<uint8_t>());
         // ---- undo RLE1: sizes, then bytes ----
         S3G_BYTES(ctx, N);
-        S3G_LAUNCH(ctx, k_unrle<false>, (unsigned)((nb + 3) / 4), 128, 0, d_blocks, (uint32_t)nb, ctx->mtf0.as<uint8_t>(), (uint8_t *)nullptr);
+        S3G_TRY(ctx->ztiles.ensure(nb * (uint64_t)UNRLE_S * 4));
+        S3G_LAUNCH(ctx, k_unrle<false>, (unsigned)((nb * UNRLE_S + 3) / 4), 128, 0, d_blocks, (uint32_t)nb, ctx->mtf0.as<uint8_t>(), (uint8_t *)nullptr,
+                   ctx->ztiles.as<uint32_t>());
         S3G_CUDA(cudaMemcpyAsync(blocks.data(), d_blocks, nb * sizeof(DecBlock), cudaMemcpyDeviceToHost, ctx->stream));
         S3G_CUDA(cudaStreamSynchronize(ctx->stream));
         S3G_TRY(check_launch("inverse bwt"));
@@ -741,7 +805,8 @@ static int decode_streams(Ctx *ctx, const uint8_t *d_z, uint64_t nz, const std::
         DecBlock *d_blocks = ctx->blocks.as<DecBlock>();
         S3G_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), nb * sizeof(DecBlock), cudaMemcpyHostToDevice, ctx->stream));
         S3G_BYTES(ctx, 2.0 * (double)total);
-        S3G_LAUNCH(ctx, k_unrle<true>, (unsigned)((nb + 3) / 4), 128, 0, d_blocks, (uint32_t)nb, ctx->mtf0.as<uint8_t>(), ctx->tf.as<uint8_t>());
+        S3G_LAUNCH(ctx, k_unrle<true>, (unsigned)((nb * UNRLE_S + 3) / 4), 128, 0, d_blocks, (uint32_t)nb, ctx->mtf0.as<uint8_t>(), ctx->tf.as<uint8_t>(),
+                   ctx->ztiles.as<uint32_t>());
         // ---- block CRCs over the decoded bytes (bz/bzlib.c:843-846) ----
         std::vector<BlockInfo> bi(chain.size());
         for (size_t c = 0; c < chain.size(); c++) { memset(&bi[c], 0, sizeof(BlockInfo)); bi[c].in_start = blocks[chain[c]].out_off; bi[c].in_end = bi[c].in_start + blocks[chain[c]].out_len; }

@@ -564,7 +564,7 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
     const size_t tail_smem = 260 * 4 + 40 * 4 + 256 * 4;
     // zero-run coding inside the MTF kernels (one CTA per block) when the batch fills the SMs, as tile-parallel kernels of
     // its own when it does not (S3G_ZRUN=fused|split overrides: both forms are tested)
-    int fused = nb >= (uint64_t)SM_COUNT ? 1 : 0;
+    int fused = nb > (uint64_t)SM_COUNT ? 1 : 0;             // up to one block per SM: clusters of 2 or more CTAs per block
     if (const char *e = getenv("S3G_ZRUN")) fused = !strcmp(e, "split") ? 0 : !strcmp(e, "fused") ? 1 : fused;
     if (!ctx->attr_mtf) {
         S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)24 * MS_SMALL * 4 + tail_smem)));

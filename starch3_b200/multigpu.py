@@ -100,14 +100,19 @@ def merge_pieces(per_rank):
 
 
 def block_shares(nblock, world):
-    """Contiguous shares of the block list, balanced by bytes -> bounds[world + 1]"""
+    """Contiguous shares of the block list, balanced by bytes, no share larger than ceil(blocks / world) -> bounds[world + 1].
+    (MTF and Huffman are one CTA -- or one cluster -- per block: a share of 149 blocks takes a 148-SM GPU as long as one of 296.)"""
+    nb = len(nblock)
     cum = np.concatenate(([0], np.cumsum(nblock.astype(np.int64))))
     total = int(cum[-1])
+    cap = (nb + world - 1) // world
     bounds = [0]
     for r in range(1, world):
         b = int(np.searchsorted(cum, (total * r + world // 2) // world, side="left"))
-        bounds.append(min(max(b, bounds[-1]), len(nblock)))
-    bounds.append(len(nblock))
+        b = min(b, bounds[-1] + cap)                 # this share within the cap ...
+        b = max(b, nb - (world - r) * cap)           # ... and the shares after it too
+        bounds.append(min(max(b, bounds[-1]), nb))
+    bounds.append(nb)
     return bounds
 
 
