@@ -80,36 +80,25 @@ __global__ void k_find_magic(const uint8_t *__restrict__ z, uint64_t n_words, ui
 enum { DE_OK = 0, DE_RANDOMISED = -1, DE_HEADER = -2, DE_SELECTOR = -3, DE_CODELEN = -4, DE_SYMBOL = -5, DE_OVERRUN = -6, DE_ORIGPTR = -7,
        DE_TRUNCATED = -8 };
 
-// The 32 lanes of the decoding warp run the SAME decode in lockstep (identical state, broadcast reads): the symbol loop is
-// serial, but this way the compressed words come into shared memory 2 KiB at a time through coalesced loads, and the
-// decoded bytes leave through coalesced 16-byte stores, instead of one exposed global-memory round trip per word.
-constexpr int DEC_IBW = 512;           // compressed words staged at a time
-constexpr int DEC_OB = 2048;           // decoded bytes staged before they are written out
 struct BitReader {
     const uint8_t *z;
-    uint32_t *ib;          // [DEC_IBW] staged big-endian words
-    uint64_t gw;           // payload word index of ib[0]
-    int ipos;              // next word of ib to take
+    uint64_t wi;           // next word to take
+    uint32_t nextw;        // ... already on its way: the load is issued one word ahead, so its latency hides behind the ~8 symbols
+                           // decoded from the word before it
     uint64_t buf;          // unread bits, left aligned
     int cnt;               // how many
-    __device__ __forceinline__ void refill()
+    __device__ __forceinline__ void init(const uint8_t *zz, uint64_t bit)
     {
-        __syncwarp();
-        for (int k = threadIdx.x & 31; k < DEC_IBW; k += 32) ib[k] = be32(z, gw + k);
-        __syncwarp();
-        ipos = 0;
-    }
-    __device__ __forceinline__ void init(const uint8_t *zz, uint32_t *stage, uint64_t bit)
-    {
-        z = zz; ib = stage; gw = bit >> 5; buf = 0; cnt = 0;
-        refill();
+        z = zz; wi = bit >> 5; buf = 0; cnt = 0;
+        nextw = be32(z, wi);
         if (bit & 31) get((int)(bit & 31));
     }
     __device__ __forceinline__ void fill()
     {
-        if (ipos == DEC_IBW) { gw += DEC_IBW; refill(); }
-        buf |= (uint64_t)ib[ipos++] << (32 - cnt);
+        buf |= (uint64_t)nextw << (32 - cnt);
         cnt += 32;
+        wi++;
+        nextw = be32(z, wi);
     }
     __device__ __forceinline__ uint32_t get(int k)            // 1 <= k <= 32
     {
@@ -124,7 +113,7 @@ struct BitReader {
         return (uint32_t)(buf >> (64 - k));
     }
     __device__ __forceinline__ void skip(int k) { buf <<= k; cnt -= k; }
-    __device__ __forceinline__ uint64_t pos() const { return (gw + (uint64_t)ipos) * 32 - (uint64_t)cnt; }
+    __device__ __forceinline__ uint64_t pos() const { return wi * 32 - (uint64_t)cnt; }
 };
 
 constexpr int LUT_BITS = 9;
@@ -136,21 +125,19 @@ struct DecSh {
     uint16_t lut[6][1 << LUT_BITS];      // (code length << 9) | symbol; 0 = longer than LUT_BITS
     uint8_t yy[256], seq2unseq[256];
     int32_t min_len[6];
-    uint32_t in_stage[DEC_IBW];
-    __align__(16) uint8_t out_stage[DEC_OB];
 };
 
 __global__ void __launch_bounds__(32) k_bz_decode(const uint8_t *__restrict__ z, DecBlock *blocks, uint8_t *lcol)
 {
     __shared__ DecSh S;
     DecBlock &B = blocks[blockIdx.x];
-    const unsigned lane = threadIdx.x;
+    if (threadIdx.x != 0) return;
     uint8_t *L = lcol + (uint64_t)blockIdx.x * BLK_STRIDE;
     BitReader br;
-    br.init(z, S.in_stage, B.bit_pos + 48);
-    if (lane == 0) { B.nblock = 0; B.end_bit = 0; }
-#define DEC_FAIL(code) do { if (lane == 0) B.status = (code); return; } while (0)
-    const uint32_t stored_crc = br.get(32);
+    br.init(z, B.bit_pos + 48);
+    B.nblock = 0; B.end_bit = 0;
+#define DEC_FAIL(code) do { B.status = (code); return; } while (0)
+    B.crc = br.get(32);
     if (br.get(1)) DEC_FAIL(DE_RANDOMISED);                        // bz/decompress.c:226: never written by 1.0.x compressors
     const uint32_t orig = br.get(24);
     // symbols in use (bz/decompress.c:243-262)
@@ -224,21 +211,18 @@ __global__ void __launch_bounds__(32) k_bz_decode(const uint8_t *__restrict__ z,
     }
     // the symbols (bz/decompress.c:330-455)
     for (int i = 0; i < 256; i++) S.yy[i] = (uint8_t)i;
+    // alphabets of up to 32 symbols (sorted BED: 12..20) keep the move-to-front list in four registers, one byte per entry
+    // holding the byte VALUE (seqToUnseq folded in): a move to the front is shifts and masks, no memory
+    const bool small = n_in_use <= 32;
+    uint64_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    if (small)
+        for (int i = n_in_use - 1; i >= 0; i--) {
+            const uint64_t v = S.seq2unseq[i];
+            l3 = (l3 << 8) | (l2 >> 56); l2 = (l2 << 8) | (l1 >> 56); l1 = (l1 << 8) | (l0 >> 56); l0 = (l0 << 8) | v;
+        }
     const int EOB = n_in_use + 1;
     const uint32_t nmax = B.nblock_max;
-    uint32_t nblock = 0, flushed = 0;       // nblock: bytes decoded; flushed: of them, written to L
-    // a decoded byte goes to the staging strip; a full strip leaves as 16-byte vectors, four per lane
-    auto emit = [&](uint8_t by) {
-        S.out_stage[nblock - flushed] = by;
-        nblock++;
-        if (nblock - flushed == DEC_OB) {
-            __syncwarp();
-            for (int k = lane; k < DEC_OB / 16; k += 32)
-                *reinterpret_cast<uint4 *>(L + flushed + 16 * k) = *reinterpret_cast<const uint4 *>(S.out_stage + 16 * k);
-            __syncwarp();
-            flushed = nblock;
-        }
-    };
+    uint32_t nblock = 0;
     int group_no = -1, group_pos = 0, g = 0;
     auto next_sym = [&](int &sym) -> int {
         if (group_pos == 0) {
@@ -276,26 +260,49 @@ __global__ void __launch_bounds__(32) k_bz_decode(const uint8_t *__restrict__ z,
                 if ((rc = next_sym(sym)) != DE_OK) DEC_FAIL(rc);
             } while (sym <= 1);
             es++;
-            const uint8_t uc = S.seq2unseq[S.yy[0]];
+            const uint8_t uc = small ? (uint8_t)l0 : S.seq2unseq[S.yy[0]];
             if ((uint64_t)nblock + (uint64_t)es > nmax) DEC_FAIL(DE_OVERRUN);
-            for (int q = 0; q < es; q++) emit(uc);
+            for (int q = 0; q < es; q++) L[nblock + q] = uc;
+            nblock += (uint32_t)es;
             continue;
         }
         if (nblock >= nmax) DEC_FAIL(DE_OVERRUN);
         const int nn = sym - 1;
         if (nn >= n_in_use) DEC_FAIL(DE_SYMBOL);
-        const uint8_t uc = S.yy[nn];
-        for (int q = nn; q > 0; q--) S.yy[q] = S.yy[q - 1];
-        S.yy[0] = uc;
-        emit(S.seq2unseq[uc]);
+        if (small) {
+            const int sh = (nn & 7) * 8;
+            uint64_t v;
+            if (nn < 8) {
+                v = (l0 >> sh) & 0xffull;
+                l0 = (l0 & ~((2ull << (sh + 7)) - 1ull)) | ((l0 & ((1ull << sh) - 1ull)) << 8) | v;
+            } else {
+                const int w = nn >> 3;
+                const uint64_t cur = w == 1 ? l1 : (w == 2 ? l2 : l3);
+                v = (cur >> sh) & 0xffull;
+                const uint64_t upd = (cur & ~((2ull << (sh + 7)) - 1ull)) | ((cur & ((1ull << sh) - 1ull)) << 8);
+                // the words below w move up by one entry; w takes the entry that falls out of w - 1
+                const uint64_t c0 = l0 >> 56, c1 = l1 >> 56, c2 = l2 >> 56;
+                l0 = (l0 << 8) | v;
+                if (w == 1) l1 = upd | c0;
+                else {
+                    l1 = (l1 << 8) | c0;
+                    if (w == 2) l2 = upd | c1;
+                    else { l2 = (l2 << 8) | c1; l3 = upd | c2; }
+                }
+            }
+            L[nblock++] = (uint8_t)v;
+        } else {
+            const uint8_t uc = S.yy[nn];
+            for (int q = nn; q > 0; q--) S.yy[q] = S.yy[q - 1];
+            S.yy[0] = uc;
+            L[nblock++] = S.seq2unseq[uc];
+        }
         if ((rc = next_sym(sym)) != DE_OK) DEC_FAIL(rc);
         if ((nblock & 4095u) == 0 && br.pos() > B.limit_bit) DEC_FAIL(DE_TRUNCATED);
     }
-    __syncwarp();
-    for (uint32_t k = flushed + lane; k < nblock; k += 32) L[k] = S.out_stage[k - flushed];
     if (orig >= nblock) DEC_FAIL(DE_ORIGPTR);                   // bz/decompress.c:461
     if (br.pos() > B.limit_bit) DEC_FAIL(DE_TRUNCATED);
-    if (lane == 0) { B.nblock = nblock; B.orig_ptr = orig; B.crc = stored_crc; B.end_bit = br.pos(); B.status = DE_OK; }
+    B.nblock = nblock; B.orig_ptr = orig; B.end_bit = br.pos(); B.status = DE_OK;
 #undef DEC_FAIL
 }
 

@@ -110,7 +110,29 @@ __device__ __forceinline__ uint32_t run_start_mask(const Win &w, const StreamMap
     return m & 0x1ffffu;
 }
 
-// ---- pass 1: last run start per tile (max-scan aggregate) --------------------
+// position + 1 of the last run start before `tile_begin` (0: none) -- what the max-scan over k_rle_runs' aggregates used to
+// deliver.  A run starts where a byte differs from the one before it, at a stream start, and at position 0; the search
+// walks back from the tile 32 bytes at a time (long runs are rare).  One warp; every lane gets the result.
+__device__ __forceinline__ uint64_t tile_run_carry(const uint8_t *__restrict__ in, const StreamMap &sm, const TileStarts &ts, uint64_t tile_begin)
+{
+    if (tile_begin == 0) return 0;
+    const unsigned l = threadIdx.x & 31;
+    // the last stream start before the tile bounds the search
+    const uint64_t floor = ts.k0 > 0 ? sm.soff[ts.k0 - 1] : 0;      // soff[0] == 0: a start at or before every position
+    uint64_t hi = tile_begin;                                       // candidates p in [floor, hi)
+    while (hi > floor) {
+        const bool inr = hi >= (uint64_t)l + 1 && hi - 1 - l >= floor;
+        const uint64_t p = hi - 1 - l;
+        const bool st = inr && (p == floor || in[p] != in[p - 1]);
+        const unsigned m = __ballot_sync(0xffffffffu, st);
+        if (m) return hi - 1 - (uint64_t)(__ffs((int)m) - 1) + 1;
+        if (hi < 32 + floor) break;
+        hi -= 32;
+    }
+    return floor + 1;
+}
+
+// ---- pass 1 (kept for reference by the stage tests): last run start per tile (max-scan aggregate) --------------------
 __global__ void __launch_bounds__(RT) k_rle_runs(const uint8_t *in, uint64_t n, StreamMap sm, uint64_t *agg)
 {
     __shared__ uint64_t s[33];
@@ -124,6 +146,40 @@ __global__ void __launch_bounds__(RT) k_rle_runs(const uint8_t *in, uint64_t n, 
     uint64_t tot;
     block_excl_max<uint64_t>(last, s, &tot);
     if (threadIdx.x == 0) agg[blockIdx.x] = tot;
+}
+
+// exclusive sum of the per-tile counts in two levels (1024 tiles per CTA, then the CTA totals): what one CTA of
+// k_scan_agg did in 70 us
+constexpr int SS_T = 1024;
+__global__ void __launch_bounds__(SS_T) k_sum_tiles(uint64_t *v, uint64_t n, uint64_t *span_tot)
+{
+    __shared__ uint64_t sm[33];
+    const uint64_t i = (uint64_t)blockIdx.x * SS_T + threadIdx.x;
+    uint64_t a = i < n ? v[i] : 0, tot;
+    uint64_t ex = block_excl_sum<uint64_t>(a, sm, &tot);
+    if (i < n) v[i] = ex;
+    if (threadIdx.x == 0) span_tot[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SS_T) k_sum_spans(uint64_t *v, uint64_t n, uint64_t *span, uint64_t nspans, uint64_t *total)
+{
+    // the spans' totals are few (n / 1024): every CTA scans them in shared memory, then adds its span's prefix to its tiles
+    __shared__ uint64_t sm[33];
+    __shared__ uint64_t s_pre, s_total;
+    uint64_t carry = 0, mine = 0;
+    for (uint64_t base = 0; base < nspans; base += SS_T) {
+        const uint64_t k = base + threadIdx.x;
+        uint64_t a = k < nspans ? span[k] : 0, tot;
+        uint64_t ex = block_excl_sum<uint64_t>(a, sm, &tot);
+        if (k == blockIdx.x) mine = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+    if (blockIdx.x / SS_T * SS_T + threadIdx.x == blockIdx.x) s_pre = mine;     // the thread that met span blockIdx.x
+    if (threadIdx.x == 0) s_total = carry;
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * SS_T + threadIdx.x;
+    if (i < n) v[i] += s_pre;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total) *total = s_total;
 }
 
 struct MaxU64 {
@@ -189,20 +245,26 @@ __device__ __forceinline__ void rle_local(const Win &w, uint32_t startmask, uint
 }
 
 // ---- pass 2: emitted bytes per tile -----------------------------------------
-__global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64_t n, StreamMap sm, const uint64_t *run_carry,
+__global__ void __launch_bounds__(RT) k_rle_emit_count(const uint8_t *in, uint64_t n, StreamMap sm, uint64_t *run_carry,
                                                         uint64_t *agg, uint16_t *win_e, uint8_t *win_c)
 {
     __shared__ uint64_t s_max[33];
     __shared__ uint32_t s_sum[33];
     __shared__ TileStarts ts;
+    __shared__ uint64_t s_carry;
     if (threadIdx.x == 0) find_tile_starts(sm, (uint64_t)blockIdx.x * RTILE, &ts);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint64_t c = tile_run_carry(in, sm, ts, (uint64_t)blockIdx.x * RTILE);
+        if (threadIdx.x == 0) { s_carry = c; run_carry[blockIdx.x] = c; }       // k_rle_write reads it back
+    }
     __syncthreads();
     Win w;
     load_win(in, n, (uint64_t)blockIdx.x * RTILE + (uint64_t)threadIdx.x * RB, w);
     uint32_t sm_mask = run_start_mask(w, sm, ts, n);
     RleLocal r;
     uint32_t c0 = 0;
-    rle_local(w, sm_mask, run_carry[blockIdx.x], s_max, r, &c0);
+    rle_local(w, sm_mask, s_carry, s_max, r, &c0);
     uint32_t tot;
     uint32_t ex = block_excl_sum<uint32_t>(r.total, s_sum, &tot);
     if (threadIdx.x == 0) agg[blockIdx.x] = tot;
@@ -568,14 +630,14 @@ int run_rle_plan(Ctx *ctx, const uint8_t *d_in, uint64_t n, const uint64_t *d_so
     uint64_t *d_sc = ctx->scalars.as<uint64_t>();
     uint64_t *run_carry = ctx->rle_carry.as<uint64_t>(), *e_base = ctx->rle_ebase.as<uint64_t>();
     StreamMap sm{d_soff, n_streams};
-    S3G_BYTES(ctx, n);
-    S3G_LAUNCH(ctx, k_rle_runs, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry);
-    S3G_LAUNCH(ctx, k_scan_agg<MaxU64>, 1, AGG_THREADS, 0, run_carry, ntiles, (uint64_t *)nullptr);
     S3G_TRY(ctx->io_c.ensure((ntiles + 1) * RT * 2));
     S3G_TRY(ctx->io_e.ensure((ntiles + 1) * RT));
     S3G_BYTES(ctx, n + n * 3 / 16);
     S3G_LAUNCH(ctx, k_rle_emit_count, (unsigned)ntiles, RT, 0, d_in, n, sm, run_carry, e_base, ctx->io_c.as<uint16_t>(), ctx->io_e.as<uint8_t>());
-    S3G_LAUNCH(ctx, k_scan_agg<SumU64b>, 1, AGG_THREADS, 0, e_base, ntiles, d_sc + 16);
+    const uint64_t nspans = (ntiles + SS_T - 1) / SS_T;
+    S3G_TRY(ctx->io_d.ensure((nspans + 1) * 8));
+    S3G_LAUNCH(ctx, k_sum_tiles, (unsigned)nspans, SS_T, 0, e_base, ntiles, ctx->io_d.as<uint64_t>());
+    S3G_LAUNCH(ctx, k_sum_spans, (unsigned)nspans, SS_T, 0, e_base, ntiles, ctx->io_d.as<uint64_t>(), nspans, d_sc + 16);
     // e_base[ntiles] = total, so E() can be evaluated at n
     S3G_CUDA(cudaMemcpyAsync(e_base + ntiles, d_sc + 16, 8, cudaMemcpyDeviceToDevice, ctx->stream));
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + 16, d_sc + 16, 8, cudaMemcpyDeviceToHost, ctx->stream));
