@@ -83,22 +83,23 @@ enum { DE_OK = 0, DE_RANDOMISED = -1, DE_HEADER = -2, DE_SELECTOR = -3, DE_CODEL
 struct BitReader {
     const uint8_t *z;
     uint64_t wi;           // next word to take
-    uint32_t nextw;        // ... already on its way: the load is issued one word ahead, so its latency hides behind the ~8 symbols
+    uint32_t nextw;        // ... (as loaded, little endian) already on its way: the load is issued one word ahead, so its latency hides behind the ~8 symbols
                            // decoded from the word before it
     uint64_t buf;          // unread bits, left aligned
     int cnt;               // how many
     __device__ __forceinline__ void init(const uint8_t *zz, uint64_t bit)
     {
         z = zz; wi = bit >> 5; buf = 0; cnt = 0;
-        nextw = be32(z, wi);
+        nextw = reinterpret_cast<const uint32_t *>(z)[wi];
         if (bit & 31) get((int)(bit & 31));
     }
     __device__ __forceinline__ void fill()
     {
-        buf |= (uint64_t)nextw << (32 - cnt);
+        // the byte swap happens here, at the use: swapping where the load is issued would wait for it on the spot
+        buf |= (uint64_t)__byte_perm(nextw, 0, 0x0123) << (32 - cnt);
         cnt += 32;
         wi++;
-        nextw = be32(z, wi);
+        nextw = reinterpret_cast<const uint32_t *>(z)[wi];
     }
     __device__ __forceinline__ uint32_t get(int k)            // 1 <= k <= 32
     {
