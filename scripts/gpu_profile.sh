@@ -4,18 +4,18 @@
 # usage: scripts/gpu_profile.sh <tag> [kernel-regex]
 set -u
 TAG=${1:-r1}
-KRE=${2:-"k_sweep|k_finish_rows|k_keys|k_mtf_small|k_huff"}
+KRE=${2:-"k_sweep|k_finish_rows|k_keys|k_mtf_small|k_huff|k_front|k_rle_write"}
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?"
 tail -3 $O/pytest_$TAG.log
 python bench.py > $O/bench_$TAG.log 2>&1; echo "bench rc=$?"
 python bench.py --impl reference --steps 1 --warmup 0 > $O/bench_ref_$TAG.log 2>&1; echo "ref rc=$?"
-CMD="python bench.py --lines 10000000 --steps 1 --warmup 1 --no-cpu-baseline"
+for c in 1 3 4; do python bench.py --cfg $c --no-cpu-baseline > $O/bench_${TAG}_cfg$c.log 2>&1; echo "cfg$c rc=$?"; done
+CMD="python bench.py --lines 10000000 --steps 1 --warmup 1 --no-cpu-baseline --no-parity"
 $CMD > $O/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_l_$TAG.log 2>&1
 echo "launch list rc=$?"
-CMD2="python bench.py --lines 10000000 --steps 1 --warmup 1 --no-cpu-baseline"
-$CMD2 > $O/plain2_$TAG.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s 9 -c 9 -f -o $O/prof_$TAG $CMD2 > $O/ncu_f_$TAG.log 2>&1
+$CMD > $O/plain2_$TAG.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s 12 -c 14 -f -o $O/prof_$TAG $CMD > $O/ncu_f_$TAG.log 2>&1
 echo "ncu full rc=$?"

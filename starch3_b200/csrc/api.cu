@@ -417,6 +417,7 @@ constexpr uint64_t HDR_RESERVE = 1ull << 20;          // the header is right-ali
 struct PipeShared {
     std::mutex mu;
     std::condition_variable cv;
+    std::vector<char> queued;      // range i's upload has been handed to the copy stream (its event is recorded)
     int next_front = 0;            // range whose transform may start
     uint64_t cs = 0;               // where it starts
     bool single_chrom = false;     // a range ended inside the chromosome it began with: stop cutting, the last range takes all
@@ -453,6 +454,12 @@ static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::v
         int rc = S3G_OK;
         TfResult tr;
         PartOut &po = parts[i];
+        {
+            // a pageable input is staged by copier threads: the range's event exists only once its last piece is queued
+            std::unique_lock<std::mutex> lk(sh.mu);
+            sh.cv.wait(lk, [&] { return sh.queued[i] || sh.rc != S3G_OK; });
+            if (sh.rc != S3G_OK) return;
+        }
         if (cudaStreamWaitEvent(w->stream, main_ctx->part_ev[i], 0) != cudaSuccess) rc = S3G_E_CUDA;
         if (rc == S3G_OK) rc = part_front(w, d_bed, off, cut[i + 1] - off, last, po, tr);
         {
@@ -489,6 +496,48 @@ static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::v
     }
 }
 
+// Pageable input (the CLI reads files into malloc'd memory): cudaMemcpyAsync from it is synchronous and staged by the
+// driver at a third of the link's speed, and it would hold up the calling thread while the workers wait.  Instead
+// STAGE_THREADS copier threads move the input through pinned pieces of their own (two each, so a thread copies one
+// while the other is on its way to the device); the thread that queues the last piece of a range records the range's event.
+constexpr int STAGE_THREADS = 4;
+constexpr uint64_t STAGE_PIECE = 8ull << 20;
+static void stage_copier(Ctx *ctx, int tid, const uint8_t *bed, uint64_t n, const std::vector<uint64_t> &cut, int nparts,
+                         std::vector<int> &left, PipeShared &sh)
+{
+    cudaSetDevice(ctx->device);
+    uint8_t *slot[2] = {ctx->h_stage + (uint64_t)(2 * tid) * STAGE_PIECE, ctx->h_stage + (uint64_t)(2 * tid + 1) * STAGE_PIECE};
+    cudaEvent_t ev[2] = {ctx->stage_ev[2 * tid], ctx->stage_ev[2 * tid + 1]};
+    bool used[2] = {false, false};
+    uint64_t piece = 0;
+    int k = 0;
+    for (int i = 0; i < nparts; i++) {
+        for (uint64_t off = cut[i]; off < cut[i + 1] || (off == cut[i] && cut[i] == cut[i + 1]); off += STAGE_PIECE, piece++) {
+            const uint64_t len = std::min<uint64_t>(STAGE_PIECE, cut[i + 1] - off);
+            if ((int)(piece % STAGE_THREADS) == tid) {
+                bool ok = true;
+                if (len) {
+                    if (used[k]) ok = cudaEventSynchronize(ev[k]) == cudaSuccess;
+                    memcpy(slot[k], bed + off, len);
+                    ok = ok && cudaMemcpyAsync(ctx->bed.as<uint8_t>() + off, slot[k], len, cudaMemcpyHostToDevice, ctx->copy_stream) == cudaSuccess;
+                    ok = ok && cudaEventRecord(ev[k], ctx->copy_stream) == cudaSuccess;
+                    used[k] = true; k ^= 1;
+                }
+                std::unique_lock<std::mutex> lk(sh.mu);
+                if (!ok) { sh.rc = S3G_E_CUDA; sh.err = "staged upload failed"; sh.cv.notify_all(); return; }
+                if (--left[i] == 0) {
+                    if (i == nparts - 1) cudaMemsetAsync(ctx->bed.as<uint8_t>() + n, 0, 64, ctx->copy_stream);
+                    cudaEventRecord(ctx->part_ev[i], ctx->copy_stream);
+                    sh.queued[i] = 1;
+                    sh.cv.notify_all();
+                }
+            }
+            if (cut[i] == cut[i + 1]) break;
+        }
+    }
+    for (int q = 0; q < 2; q++) if (used[q]) cudaEventSynchronize(ev[q]);
+}
+
 static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int level, const char *note, int nparts, s3g_result *res)
 {
     memset(res, 0, sizeof *res);
@@ -523,19 +572,46 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     // half of the input is generous for BED (the one-shot path takes over if it ever is not)
     S3G_TRY(ensure_archive(ctx, HDR_RESERVE + std::max<uint64_t>(n / 2, ctx->archive_hint + (ctx->archive_hint >> 3)) + 4096));
     cudaEvent_t t0 = ctx->ev0, t1 = ctx->ev1;
-    S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));
-    for (int i = 0; i < nparts; i++) {
-        if (cut[i + 1] > cut[i])
-            S3G_CUDA(cudaMemcpyAsync(ctx->bed.as<uint8_t>() + cut[i], bed + cut[i], cut[i + 1] - cut[i], cudaMemcpyHostToDevice, ctx->copy_stream));
-        if (i == nparts - 1) S3G_CUDA(cudaMemsetAsync(ctx->bed.as<uint8_t>() + n, 0, 64, ctx->copy_stream));
-        S3G_CUDA(cudaEventRecord(ctx->part_ev[i], ctx->copy_stream));
+    // is the caller's buffer pinned?  (an unregistered pointer reports cudaMemoryTypeUnregistered, or an error on old drivers)
+    bool pinned_input = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, bed) == cudaSuccess) pinned_input = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+        else cudaGetLastError();
+        if (getenv("S3G_NO_STAGING")) pinned_input = true;
     }
     std::vector<PartOut> parts(nparts);
     PipeShared sh;
     sh.archive_cap = ctx->h_archive_cap;
+    sh.queued.assign(nparts, 0);
+    std::vector<int> left(nparts, 0);
+    std::vector<std::thread> copiers;
+    S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));
+    if (pinned_input) {
+        for (int i = 0; i < nparts; i++) {
+            if (cut[i + 1] > cut[i])
+                S3G_CUDA(cudaMemcpyAsync(ctx->bed.as<uint8_t>() + cut[i], bed + cut[i], cut[i + 1] - cut[i], cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (i == nparts - 1) S3G_CUDA(cudaMemsetAsync(ctx->bed.as<uint8_t>() + n, 0, 64, ctx->copy_stream));
+            S3G_CUDA(cudaEventRecord(ctx->part_ev[i], ctx->copy_stream));
+            sh.queued[i] = 1;
+        }
+    } else {
+        if (!ctx->h_stage) {
+            if (cudaMallocHost(&ctx->h_stage, 2ull * STAGE_THREADS * STAGE_PIECE) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+            for (int q = 0; q < 2 * STAGE_THREADS; q++) {
+                cudaEvent_t e;
+                S3G_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->stage_ev.push_back(e);
+            }
+        }
+        for (int i = 0; i < nparts; i++) left[i] = cut[i + 1] > cut[i] ? (int)((cut[i + 1] - cut[i] + STAGE_PIECE - 1) / STAGE_PIECE) : 1;
+        for (int t = 0; t < STAGE_THREADS; t++)
+            copiers.emplace_back(stage_copier, ctx, t, bed, n, std::cref(cut), nparts, std::ref(left), std::ref(sh));
+    }
     std::thread th0(pipe_worker, ctx, ctx->sub[0], 0, nparts, std::cref(cut), level, std::ref(parts), std::ref(sh));
     std::thread th1(pipe_worker, ctx, ctx->sub[1], 1, nparts, std::cref(cut), level, std::ref(parts), std::ref(sh));
     th0.join(); th1.join();
+    for (std::thread &c : copiers) c.join();
     if (sh.rc == S3G_E_CAPACITY) return S3G_E_CAPACITY;       // caller falls back to the one-shot path
     if (sh.rc != S3G_OK) { set_error("%s", sh.err.c_str()); return sh.rc; }
     S3G_CUDA(cudaEventRecord(t1, ctx->sub[(nparts - 1) & 1]->stream));
@@ -716,6 +792,8 @@ void s3g_destroy(s3g_ctx *ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (cudaEvent_t e : ctx->stage_ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);

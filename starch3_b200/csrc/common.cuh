@@ -133,6 +133,8 @@ struct Ctx {
     // pipelined host entry (s3g_compress_bed on large inputs): upload stream, one event per input range,
     // and two worker contexts that compress ranges while later ranges are still on their way
     cudaStream_t copy_stream = nullptr;
+    uint8_t *h_stage = nullptr;            // pinned pieces the copier threads stage a pageable input through
+    std::vector<cudaEvent_t> stage_ev;
     std::vector<cudaEvent_t> part_ev;
     Ctx *sub[2] = {nullptr, nullptr};
     double mem_frac = 0.85;                // share of the free device memory a batch of blocks may take (worker contexts: less)

@@ -204,15 +204,26 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
     -> dict(streams table, n_blocks, rle/mtf totals ...) and, on rank 0, `payload`: device tensor with the
     concatenated bzip2 streams."""
     i64 = torch.int64
+    import os, time
+    _t = [] if os.environ.get("S3G_SHARD_TIMING") else None      # wall clock per phase (host view, rank 0 prints)
+    def _mark(name):
+        if _t is not None:
+            if device.type == "cuda":
+                torch.cuda.synchronize()
+            _t.append((name, time.perf_counter()))
+    _mark("start")
     # ---- phase 1: tokenizer; exchange the summaries ----
     sm = ph.tokenize(d_range, n_range, halo)
+    _mark("tokenize")
     mine = torch.tensor([sm["tail_max"], sm["continues"], sm["single_piece"], sm["n_lines"], sm["dropped_tail_bytes"]], dtype=i64, device=device)
     allsm = torch.empty(world * 5, dtype=i64, device=device)
     dist.all_gather_into_tensor(allsm, mine)
     allsm = allsm.cpu().numpy().reshape(world, 5)
     carries = carry_chain([tuple(int(x) for x in allsm[r, :4]) for r in range(world)])
+    _mark("x summaries")
     # ---- phase 2: transform; exchange piece tables and transformed bytes ----
     pieces, tf = ph.transform(carries[rank])
+    _mark("transform")
     names = [bytes(names_src[p["name_off"] + range_base:p["name_off"] + range_base + p["name_len"]]) for p in pieces]
     cap = OPT_PIECES
     while True:
@@ -231,6 +242,7 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
     per_rank = [(int(allsm[r, 1]), unpack_pieces(alltab[r, 1:], int(alltab[r, 0, 0]))) for r in range(world)]
     tf_lens = [int(alltab[r, 0, 1]) for r in range(world)]
     streams = merge_pieces(per_rank)
+    _mark("x pieces")
     tf_total = sum(tf_lens)
     tf_all = torch.empty(tf_total + 64, dtype=torch.uint8, device=device)
     offs = np.concatenate(([0], np.cumsum(tf_lens))).astype(np.int64)
@@ -250,13 +262,16 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
     else:
         tf_all[:tf_total] = tf
     soff = np.array([s["tf_off"] for s in streams] + [tf_total], dtype=np.uint64)
+    _mark("x transformed bytes")
     # ---- phase 3: the block plan (every rank computes the same one) ----
     nblock, stream_of = ph.plan(tf_all, tf_total, soff, level)
+    _mark("plan")
     nb = len(nblock)
     bounds = block_shares(nblock, world)
     b_lo, b_hi = bounds[rank], bounds[rank + 1]
     # ---- phase 4: the rank's share of the blocks; exchange bit lengths and CRCs ----
     n_bits, crc, n_mtf = ph.compress(b_lo, b_hi)
+    _mark("compress")
     tab = np.zeros((nb + 1, 2), dtype=np.int64)
     tab[b_lo:b_hi, 0] = n_bits.astype(np.int64); tab[b_lo:b_hi, 1] = crc.astype(np.int64)
     tab[nb, 0] = int(n_mtf.sum())
@@ -265,8 +280,10 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
         dist.all_reduce(t)
     tab = t.cpu().numpy().reshape(nb + 1, 2)
     n_bits_all = tab[:nb, 0].astype(np.uint64); crc_all = tab[:nb, 1].astype(np.uint32)
+    _mark("x block table")
     # ---- phase 5: place the share; gather on rank 0 ----
     piece, lo, hi, stream_off, stream_len = ph.assemble(n_bits_all, crc_all, b_lo, b_hi, len(streams))
+    _mark("assemble")
     total = int(stream_off[-1] + stream_len[-1]) if len(streams) else 0
     span = torch.tensor([lo, hi], dtype=i64, device=device)
     spans = torch.empty(world * 2, dtype=i64, device=device)
@@ -292,6 +309,9 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
             dist.send(piece[:hi - lo].contiguous(), dst=0)
     else:
         payload = piece[:total]
+    _mark("x byte strings")
+    if _t is not None and rank == 0:
+        print("[shard timing, ms] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(_t, _t[1:])), flush=True)
     blocks_of = np.bincount(stream_of, minlength=len(streams)) if nb else np.zeros(len(streams), dtype=np.int64)
     return dict(streams=streams, blocks_of=blocks_of, stream_off=stream_off, stream_len=stream_len, payload=payload, total=total,
                 n_blocks=nb, n_lines=int(allsm[:, 3].sum()), dropped=int(allsm[world - 1, 4]), tf_total=tf_total,
