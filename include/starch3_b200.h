@@ -147,6 +147,7 @@ typedef struct s3g_shard_summary {
     uint32_t continues;          /* the first line of the range has the halo line's chromosome (hpp:331) */
     uint32_t single_piece;       /* no chromosome change inside the range */
     uint64_t dropped_tail_bytes; /* unterminated last line (hpp:181-190); only the last range can have one */
+    uint64_t tf_bytes;           /* transformed bytes the range will write in phase 2 */
 } s3g_shard_summary;
 /* phase 1: tokenizer over d_range[0, n); its first halo_bytes bytes are the line before the range (0: none). */
 S3G_API int s3g_shard_tokenize(s3g_ctx *ctx, const void *d_range, uint64_t n, uint64_t halo_bytes, s3g_shard_summary *out);
@@ -155,6 +156,13 @@ S3G_API int s3g_shard_tokenize(s3g_ctx *ctx, const void *d_range, uint64_t n, ui
  * (name_off relative to d_range; tf_off relative to *d_tf; bz_* unused); *d_tf stays valid until the next call. */
 S3G_API int s3g_shard_transform(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint64_t cap, uint64_t *n_pieces,
                                 void **d_tf, uint64_t *tf_len);
+/* phase 2, fused with the exchange that follows it: the transform kernel stores the range's transformed bytes at dst_off
+ * into EVERY buffer of peer_bufs (device addresses valid on this GPU: its own copy of the transformed buffer first, then the
+ * peers' copies through their NVLink-mapped pointers, e.g. torch symmetric memory or cudaIpc / cudaDeviceEnablePeerAccess
+ * mappings; 16-byte aligned, at most 8).  dst_off = sum of tf_bytes of the ranges before this one (s3g_shard_summary).
+ * When every GPU has returned from this call, every buffer holds all transformed bytes: no all-gather follows. */
+S3G_API int s3g_shard_transform_peers(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint64_t cap, uint64_t *n_pieces,
+                                      const uint64_t *peer_bufs, uint32_t n_peers, uint64_t dst_off, uint64_t *tf_len);
 /* phase 3: RLE1 lengths + block cut (bz/bzlib.c:225-338, :370-412) over ALL transformed bytes, stream s =
  * d_tf_all[soff[s], soff[s+1]) (soff on the host).  Every GPU computes the same plan; nblock / stream_of describe
  * its blocks in archive order.  d_tf_all must stay valid until s3g_shard_compress returns. */

@@ -271,7 +271,10 @@ inline uint64_t front_crlf(const Ctx *ctx);
 // the same in pieces, for ranges handed between GPUs (shard.cu): `halo` = line 0 is the last line before the range
 int run_tokenize(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out, uint32_t halo);
 int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_max, uint64_t *last_flag, uint32_t *continues);
-int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump = false, bool last_part = true);
+// peer_bufs (n_peers > 0): the transformed bytes go into these buffers at peer_off instead of ctx->tf (N-GPU path: this GPU's
+// own buffer first, then the peers' copies of it through their NVLink-mapped pointers)
+int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump = false, bool last_part = true,
+                       const uint64_t *peer_bufs = nullptr, uint32_t n_peers = 0, uint64_t peer_off = 0);
 
 struct CutResult {
     uint64_t n_blocks = 0;

@@ -68,6 +68,7 @@ int s3g_shard_tokenize(s3g_ctx *ctx, const void *d_range, uint64_t n, uint64_t h
     out->continues = cont;
     out->single_piece = last_flag == 0 ? 1u : 0u;
     out->dropped_tail_bytes = S.tr.dropped;
+    out->tf_bytes = S.tr.tf_len;
     return S3G_OK;
 }
 
@@ -94,6 +95,33 @@ int s3g_shard_transform(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint
         k++;
     }
     *n_pieces = k; *d_tf = ctx->tf.p; *tf_len = S.tr.tf_len;
+    return S3G_OK;
+}
+
+int s3g_shard_transform_peers(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint64_t cap, uint64_t *n_pieces,
+                              const uint64_t *peer_bufs, uint32_t n_peers, uint64_t dst_off, uint64_t *tf_len)
+{
+    if (!ctx || !n_pieces || !tf_len || !peer_bufs || n_peers == 0) { set_error("null argument"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    ShardState &S = st(ctx);
+    *n_pieces = 0; *tf_len = 0;
+    if (S.tr.n_lines == 0) return S3G_OK;
+    stage_mark(ctx, 0);
+    S3G_TRY(run_transform_rest(ctx, S.base, S.n, &S.tr, S.halo, carry_max, false, true, peer_bufs, n_peers, dst_off));
+    ctx->h_chroms.resize(S.tr.n_chroms);
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_chroms.data(), ctx->chroms.p, S.tr.n_chroms * sizeof(s3g_chrom), cudaMemcpyDeviceToHost, ctx->stream));
+    stage_mark(ctx, -1);
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t k = 0;
+    for (uint64_t c = 0; c < S.tr.n_chroms; c++) {
+        s3g_chrom ch = ctx->h_chroms[c];
+        if (S.halo && c == 0 && ch.line_count == 0) continue;      // the halo line's chromosome ended with it
+        if (k >= cap) { set_error("piece table too small"); return S3G_E_CAPACITY; }
+        ch.name_off -= S.skip;
+        if (pieces) pieces[k] = ch;
+        k++;
+    }
+    *n_pieces = k; *tf_len = S.tr.tf_len;
     return S3G_OK;
 }
 

@@ -507,6 +507,12 @@ __global__ void __launch_bounds__(FSCAN_T) k_front_scan_spans(FAgg *span, uint64
 }
 
 // ---- pass 2 -------------------------------------------------------------------------------------------
+// where the transformed bytes go: up to 8 buffers (this GPU's first), the range's bytes at offset `off` in each
+struct PeerDst {
+    uint8_t *ptr[8];
+    uint64_t off;
+    uint32_t n;
+};
 struct ChromSeed {
     uint64_t first_line, name_off, tf_off;
     uint32_t name_len, pad;
@@ -519,9 +525,9 @@ struct DumpArrays {            // the per-line arrays of the s3g_tokenize entry 
 };
 
 template <bool DUMP>
-__global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo, int64_t carry_max,
+__global__ void __launch_bounds__(FTH, 3) k_front_write(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo, int64_t carry_max,
                                                      const FAgg *__restrict__ span_pre, const FAgg *__restrict__ tile_pre, const FAgg *__restrict__ chunk_pre,
-                                                     const uint32_t *__restrict__ chunk_out, uint64_t n_lines, uint8_t *__restrict__ tf,
+                                                     const uint32_t *__restrict__ chunk_out, uint64_t n_lines, const __grid_constant__ PeerDst pd,
                                                      ChromSeed *seeds, unsigned long long *stat_len, unsigned long long *stat_uniq, uint32_t stat_slots,
                                                      uint64_t diag_chroms, unsigned long long *sc, DumpArrays da)
 {
@@ -537,7 +543,8 @@ __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__
     const uint64_t o_begin = ex0.out;
     const uint32_t o_len = chunk_out[chunk];
     const bool staged = o_len <= FOB;
-    const uint32_t ph = (uint32_t)o_begin & 15u;
+    uint8_t *const tf = pd.ptr[0] + pd.off;                // destination 0 (this GPU's own buffer); pd.off keeps 16-byte phase in mind:
+    const uint32_t ph = (uint32_t)(pd.off + o_begin) & 15u; // every destination buffer is 16-byte aligned, so the phase is the same in all
     uint8_t *const obuf = s_out[wid];
     uint64_t run_out = 0, run_ch = 0;
     int64_t run_v = ex0.v;                                 // largest stop of the current chromosome so far
@@ -620,13 +627,24 @@ __global__ void __launch_bounds__(FTH) k_front_write(const uint8_t *__restrict__
         if (acc_len) atomicAdd(&stat_len[slot], acc_len);
         if (acc_uniq) atomicAdd(&stat_uniq[slot], acc_uniq);
     }
-    if (!staged) return;
     __syncwarp();
-    uint8_t *dst = tf + (o_begin - ph);                                       // 16-byte aligned (tf comes from cudaMalloc)
+    if (!staged) {
+        // (a chunk whose output outgrew the strip was written straight into destination 0) the other destinations get copies
+        for (uint32_t k = 1; k < pd.n; k++) {
+            uint8_t *d = pd.ptr[k] + pd.off + o_begin;
+            for (uint32_t j = l; j < o_len; j += 32) d[j] = tf[o_begin + j];
+        }
+        return;
+    }
+    // the strip leaves as aligned 16-byte vectors -- into this GPU's buffer and, in the N-GPU path, into every peer's copy of
+    // the transformed buffer through its NVLink-mapped pointer: the all-gather of the transformed bytes is these stores
     const uint32_t lo_b = ph, hi_b = ph + o_len;
-    for (uint32_t c = l * 16; c < hi_b; c += 32 * 16) {
-        if (c >= lo_b && c + 16 <= hi_b) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(obuf + c);
-        else for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = obuf[j];
+    for (uint32_t k = 0; k < pd.n; k++) {
+        uint8_t *dst = pd.ptr[k] + pd.off + o_begin - ph;                     // 16-byte aligned
+        for (uint32_t c = l * 16; c < hi_b; c += 32 * 16) {
+            if (c >= lo_b && c + 16 <= hi_b) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(obuf + c);
+            else for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = obuf[j];
+        }
     }
 }
 
@@ -700,7 +718,8 @@ int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_m
 }
 
 // kernel (2) over the range measured by run_tokenize; dump = also leave the per-line arrays in ctx
-int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump, bool last_part)
+int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump, bool last_part,
+                       const uint64_t *peer_bufs, uint32_t n_peers, uint64_t peer_off)
 {
     const uint64_t n_lines = out->n_lines, n_chroms = out->n_chroms;
     // a range that is not the last hands its last chromosome to the next range, which counts that chromosome's lines
@@ -709,7 +728,19 @@ int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out
     uint64_t ntiles = (n + (uint64_t)FCH * FWARPS - 1) / ((uint64_t)FCH * FWARPS);
     if (ntiles == 0) ntiles = 1;
     const uint32_t slots = n_chroms <= 4096 ? 32u : 1u;            // same-address atomics serialise: spread a chromosome's sums
-    S3G_TRY(ctx->tf.ensure(out->tf_len + 64));
+    PeerDst pd;
+    memset(&pd, 0, sizeof pd);
+    if (n_peers) {
+        if (n_peers > 8) { set_error("at most 8 destination buffers"); return S3G_E_PARAM; }
+        for (uint32_t k = 0; k < n_peers; k++) {
+            if (peer_bufs[k] & 15) { set_error("destination buffers must be 16-byte aligned"); return S3G_E_PARAM; }
+            pd.ptr[k] = reinterpret_cast<uint8_t *>(peer_bufs[k]);
+        }
+        pd.n = n_peers; pd.off = peer_off;
+    } else {
+        S3G_TRY(ctx->tf.ensure(out->tf_len + 64));
+        pd.ptr[0] = ctx->tf.as<uint8_t>(); pd.n = 1; pd.off = 0;
+    }
     S3G_TRY(ctx->chrom_first.ensure((n_chroms + 1) * sizeof(ChromSeed)));
     S3G_TRY(ctx->stat_b.ensure((n_chroms + 1) * slots * 16));
     S3G_TRY(ctx->chroms.ensure((n_chroms + 1) * sizeof(s3g_chrom)));
@@ -726,11 +757,11 @@ int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out
         da.line_start = ctx->line_start.as<uint64_t>(); da.start = ctx->start.as<int64_t>(); da.stop = ctx->stop.as<int64_t>();
         da.rem_off = ctx->rem_off.as<uint32_t>(); da.flags = ctx->flags.as<uint8_t>();
         S3G_LAUNCH(ctx, k_front_write<true>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_c.as<FAgg>(), ctx->scan_a.as<FAgg>(),
-                   ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(),
+                   ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, pd, ctx->chrom_first.as<ChromSeed>(),
                    stat_len, stat_uniq, slots, diag_chroms, (unsigned long long *)d_sc, da);
     } else {
         S3G_LAUNCH(ctx, k_front_write<false>, (unsigned)ntiles, FTH, 0, d_bed, n, ctx->front_skip, halo, carry_max, ctx->scan_c.as<FAgg>(), ctx->scan_a.as<FAgg>(),
-                   ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, ctx->tf.as<uint8_t>(), ctx->chrom_first.as<ChromSeed>(),
+                   ctx->scan_b.as<FAgg>(), ctx->tile_cnt.as<uint32_t>(), n_lines, pd, ctx->chrom_first.as<ChromSeed>(),
                    stat_len, stat_uniq, slots, diag_chroms, (unsigned long long *)d_sc, da);
     }
     S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars + SC_UNSORTED, d_sc + SC_UNSORTED, 16, cudaMemcpyDeviceToHost, ctx->stream));   // read after the caller's next synchronise

@@ -83,3 +83,27 @@ def test_processes_over_nccl(oracle, tmp_path):
                             "--master-port", str(port), str(f)], capture_output=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     assert out.read_bytes() == oracle.archive_mt(synth.bed(5, 600000), 9, "nccl")
+
+
+def test_transform_into_several_buffers(ctx, oracle):
+    """s3g_shard_transform_peers: the transform kernel stores a range's transformed bytes at an offset into every buffer it
+    is given (in the N-GPU path: this GPU's copy of the transformed buffer and the peers' copies through their NVLink-mapped
+    pointers; here three buffers on one device).  Every buffer ends up with the bytes s3g_shard_transform leaves in its own,
+    and nothing outside [offset, offset + length) is touched."""
+    import torch
+    for cfg, lines, off in ((2, 60000, 0), (3, 200000, 7), (4, 20000, 4099), (5, 30000, 13)):
+        bed = synth.bed(cfg, lines)
+        d = torch.from_numpy(bed).cuda()
+        sm = ctx.shard_tokenize(d.data_ptr(), d.numel(), 0)
+        pieces, ptr, n = ctx.shard_transform(M.I64_MIN)
+        want = torch.as_tensor(M._DevView(ptr, n), device="cuda").clone()
+        assert sm["tf_bytes"] == n
+        bufs = [torch.full((n + off + 4096,), 0xAB, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        ctx.shard_tokenize(d.data_ptr(), d.numel(), 0)
+        pieces2, n2 = ctx.shard_transform_peers(M.I64_MIN, [b.data_ptr() for b in bufs], off)
+        assert n2 == n and [(p["tf_off"], p["tf_len"], p["line_count"]) for p in pieces2] == [(p["tf_off"], p["tf_len"], p["line_count"]) for p in pieces]
+        for b in bufs:
+            assert torch.equal(b[off:off + n], want)
+            assert bool((b[:off] == 0xAB).all()) and bool((b[off + n:] == 0xAB).all())
+        tf, _, _ = oracle.transform(bed.tobytes())
+        assert bytes(want.cpu().numpy()) == tf
