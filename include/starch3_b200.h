@@ -160,9 +160,12 @@ S3G_API int s3g_shard_transform(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *piec
  * into EVERY buffer of peer_bufs (device addresses valid on this GPU: its own copy of the transformed buffer first, then the
  * peers' copies through their NVLink-mapped pointers, e.g. torch symmetric memory or cudaIpc / cudaDeviceEnablePeerAccess
  * mappings; 16-byte aligned, at most 8).  dst_off = sum of tf_bytes of the ranges before this one (s3g_shard_summary).
+ * multicast_buf: the NVLS multicast address of the same buffers (a store to it is replicated by the NVSwitch into every
+ * GPU's copy; torch symmetric memory: multicast_ptr), or 0: then the kernel stores into each buffer in turn.
  * When every GPU has returned from this call, every buffer holds all transformed bytes: no all-gather follows. */
 S3G_API int s3g_shard_transform_peers(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint64_t cap, uint64_t *n_pieces,
-                                      const uint64_t *peer_bufs, uint32_t n_peers, uint64_t dst_off, uint64_t *tf_len);
+                                      const uint64_t *peer_bufs, uint32_t n_peers, uint64_t multicast_buf, uint64_t dst_off,
+                                      uint64_t *tf_len);
 /* phase 3: RLE1 lengths + block cut (bz/bzlib.c:225-338, :370-412) over ALL transformed bytes, stream s =
  * d_tf_all[soff[s], soff[s+1]) (soff on the host).  Every GPU computes the same plan; nblock / stream_of describe
  * its blocks in archive order.  d_tf_all must stay valid until s3g_shard_compress returns. */
@@ -177,6 +180,10 @@ S3G_API int s3g_shard_compress(s3g_ctx *ctx, uint64_t b_lo, uint64_t b_hi, uint6
  * (n_streams each, may be NULL) = the layout of the streams. */
 S3G_API int s3g_shard_assemble(s3g_ctx *ctx, const uint64_t *n_bits_all, const uint32_t *crc_all, uint64_t b_lo, uint64_t b_hi,
                                void **d_bytes, uint64_t *byte_lo, uint64_t *byte_hi, uint64_t *stream_off, uint64_t *stream_len);
+/* phase 5, gather fused: store the byte string s3g_shard_assemble left on this GPU at byte_lo of `gather_buf` -- a device
+ * address valid on this GPU, typically the NVLink-mapped pointer of the buffer on the GPU that collects the archive.  The
+ * buffer must be zero where nothing was placed yet: the string's end bytes are ORed in (shared with the neighbours). */
+S3G_API int s3g_shard_place(s3g_ctx *ctx, uint64_t gather_buf, uint64_t byte_lo, uint64_t byte_hi);
 /* CUDA-event time per stage (indices as s3g_result.stage_ms) of the phases run on ctx since s3g_shard_tokenize. */
 S3G_API int s3g_stage_times(s3g_ctx *ctx, double *stage_ms8);
 

@@ -21,7 +21,7 @@ C_ABI_SYMBOLS = [
     "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_stream_begin", "s3g_stream_write", "s3g_stream_end",
-    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_stage_times",
+    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_stage_times",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
     "s3g_decompress_archive", "s3g_bz_decompress", "s3g_inverse_transform",
 ]
@@ -108,10 +108,11 @@ def lib():
         L.s3g_stream_end.argtypes = [vp, C.POINTER(CResult)]
         L.s3g_shard_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(CShardSummary)]
         L.s3g_shard_transform.argtypes = [vp, C.c_int64, vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
-        L.s3g_shard_transform_peers.argtypes = [vp, C.c_int64, vp, u64, C.POINTER(u64), vp, C.c_uint32, u64, C.POINTER(u64)]
+        L.s3g_shard_transform_peers.argtypes = [vp, C.c_int64, vp, u64, C.POINTER(u64), vp, C.c_uint32, u64, u64, C.POINTER(u64)]
         L.s3g_shard_plan.argtypes = [vp, vp, u64, vp, u64, i32, C.POINTER(u64), vp, vp, u64]
         L.s3g_shard_compress.argtypes = [vp, u64, u64, vp, vp, vp]
         L.s3g_shard_assemble.argtypes = [vp, vp, vp, u64, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), vp, vp]
+        L.s3g_shard_place.argtypes = [vp, u64, u64, u64]
         L.s3g_stage_times.argtypes = [vp, vp]
         L.s3g_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(u64), vp, vp, vp, vp, vp]
         L.s3g_transform.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64), C.POINTER(u64)]
@@ -306,14 +307,14 @@ class Context:
         return dict(n_lines=out.n_lines, tail_max=out.tail_max, continues=out.continues, single_piece=out.single_piece,
                     dropped_tail_bytes=out.dropped_tail_bytes, tf_bytes=out.tf_bytes)
 
-    def shard_transform_peers(self, carry_max, peer_bufs, dst_off, cap=4096):
+    def shard_transform_peers(self, carry_max, peer_bufs, dst_off, cap=4096, multicast_buf=0):
         """the transform with its all-gather fused in: the bytes go to dst_off of every buffer in peer_bufs (device
         addresses, this GPU's own first).  -> (pieces, transformed bytes written)"""
         pb = np.ascontiguousarray(peer_bufs, dtype=np.uint64)
         while True:
             pieces = (CChrom * cap)()
             n = C.c_uint64(0); tl = C.c_uint64(0)
-            rc = self._lib.s3g_shard_transform_peers(self._h, carry_max, pieces, cap, C.byref(n), _p(pb), len(pb), dst_off, C.byref(tl))
+            rc = self._lib.s3g_shard_transform_peers(self._h, carry_max, pieces, cap, C.byref(n), _p(pb), len(pb), multicast_buf, dst_off, C.byref(tl))
             if rc == S3G_E_CAPACITY and cap < (1 << 24):
                 cap *= 16
                 continue
@@ -358,6 +359,9 @@ class Context:
         d = C.c_void_p(); lo = C.c_uint64(0); hi = C.c_uint64(0)
         self._check(self._lib.s3g_shard_assemble(self._h, _p(nb), _p(cr), b_lo, b_hi, C.byref(d), C.byref(lo), C.byref(hi), _p(so), _p(sl)))
         return d.value or 0, lo.value, hi.value, so[:n_streams], sl[:n_streams]
+
+    def shard_place(self, gather_buf, lo, hi):
+        self._check(self._lib.s3g_shard_place(self._h, gather_buf, lo, hi))
 
     def stage_times(self):
         t = (C.c_double * 8)()

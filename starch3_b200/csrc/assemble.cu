@@ -178,6 +178,50 @@ __global__ void k_patch_words(const uint64_t *patch, uint64_t n, uint32_t *dst)
     if (i < n) or_bits(dst, patch[2 * i], (uint32_t)patch[2 * i + 1]);
 }
 
+// the share's byte string (ctx->streams, `len` bytes) into a gather buffer at `at`.  The buffer may live on another GPU
+// (an NVLink-mapped peer pointer) and is zero where nobody has written: the string's first and last byte may be shared
+// with the neighbouring shares, so they are ORed in (an atomic on the 32-bit word that holds them); the bytes between
+// belong to this share alone and are stored.
+__global__ void k_place_bytes(const uint8_t *__restrict__ src, uint8_t *dst, uint64_t at, uint64_t len)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+    if (t == 0) {
+        auto or_byte = [&](uint64_t pos, uint8_t v) {
+            const uint64_t a = at + pos;
+            atomicOr(reinterpret_cast<uint32_t *>(dst + (a & ~3ull)), (uint32_t)v << (8 * (a & 3)));
+        };
+        or_byte(0, src[0]);
+        if (len > 1) or_byte(len - 1, src[len - 1]);
+    }
+    if (len <= 2) return;
+    // interior [1, len - 1): bytes up to the first 16-byte boundary of the destination, aligned vectors, the rest
+    const uint64_t d0 = at + 1, d1 = at + len - 1;                     // destination range
+    const uint64_t v0 = (d0 + 15) & ~15ull, v1 = d1 & ~15ull;
+    if (v0 >= v1) {
+        for (uint64_t p = d0 + t; p < d1; p += nt) dst[p] = src[p - at];
+        return;
+    }
+    for (uint64_t p = d0 + t; p < v0; p += nt) dst[p] = src[p - at];
+    for (uint64_t p = v1 + t; p < d1; p += nt) dst[p] = src[p - at];
+    const uint32_t sh = (uint32_t)((v0 - at) & 3);                     // source phase relative to its 4-byte words
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src + ((v0 - at) & ~3ull));
+    for (uint64_t u = t; u < (v1 - v0) / 16; u += nt) {
+        const uint32_t *q = sw + 4 * u;
+        uint32_t w[5] = {q[0], q[1], q[2], q[3], sh ? q[4] : 0u};
+        uint4 o;
+        o.x = __funnelshift_r(w[0], w[1], 8 * sh); o.y = __funnelshift_r(w[1], w[2], 8 * sh);
+        o.z = __funnelshift_r(w[2], w[3], 8 * sh); o.w = __funnelshift_r(w[3], w[4], 8 * sh);
+        *reinterpret_cast<uint4 *>(dst + v0 + 16 * u) = o;
+    }
+}
+int run_place_bytes(Ctx *ctx, uint8_t *dst, uint64_t at, uint64_t len)
+{
+    if (!len) return S3G_OK;
+    S3G_BYTES(ctx, 2.0 * (double)len);
+    S3G_LAUNCH(ctx, k_place_bytes, 592, 256, 0, ctx->streams.as<uint8_t>(), dst, at, len);
+    return check_launch("place bytes");
+}
+
 int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, uint64_t b_hi, uint64_t *byte_lo, uint64_t *byte_hi,
                        std::vector<StreamMeta> *metas)
 {

@@ -274,7 +274,7 @@ int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_m
 // peer_bufs (n_peers > 0): the transformed bytes go into these buffers at peer_off instead of ctx->tf (N-GPU path: this GPU's
 // own buffer first, then the peers' copies of it through their NVLink-mapped pointers)
 int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump = false, bool last_part = true,
-                       const uint64_t *peer_bufs = nullptr, uint32_t n_peers = 0, uint64_t peer_off = 0);
+                       const uint64_t *peer_bufs = nullptr, uint32_t n_peers = 0, uint64_t peer_off = 0, uint64_t multicast_buf = 0);
 
 struct CutResult {
     uint64_t n_blocks = 0;
@@ -305,6 +305,8 @@ int run_assemble(Ctx *ctx, uint64_t n_blocks, uint64_t n_streams, int level, uin
 // Leaves bytes [byte_lo, byte_hi) of the global streams buffer in ctx->streams.
 int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, uint64_t b_hi, uint64_t *byte_lo, uint64_t *byte_hi,
                        std::vector<StreamMeta> *metas);
+// the byte string run_assemble_range left in ctx->streams -> dst[at, at + len) (dst may be a peer GPU's buffer)
+int run_place_bytes(Ctx *ctx, uint8_t *dst, uint64_t at, uint64_t len);
 int compress_block_range(Ctx *ctx, uint64_t b_lo, uint64_t b_hi);
 
 inline uint64_t front_unsorted(const Ctx *ctx) { return ctx->h_scalars[4]; }

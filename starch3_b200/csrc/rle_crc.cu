@@ -364,8 +364,26 @@ __global__ void __launch_bounds__(32) k_rle_cut(CutWalker cw, uint32_t nmax, uin
         uint64_t target = base + nmax;
         uint64_t x = s1, ex = e1;
         if (e1 >= target) {
-            // 32-ary search for the last tile whose prefix is still below the target
+            // the last tile whose prefix is still below the target.  RLE1 rarely changes the length of text, so the tile is
+            // first looked for in a window of 32 around where it would be if it changed nothing; the 32-ary search over
+            // all tiles of the stream runs only if the window does not hold the crossing
             uint64_t lo = start / RTILE, hi = (s1 - 1) / RTILE;
+            {
+                const uint64_t guess = (start + nmax) / RTILE;
+                const uint64_t w0 = guess > lo + 20 ? guess - 20 : lo;
+                const uint64_t probe = w0 + l;
+                const bool in = probe <= hi;
+                const bool below = in && cw.e_base[probe] < target;
+                const unsigned mb = __ballot_sync(0xffffffffu, below), mi = __ballot_sync(0xffffffffu, in);
+                // monotone: the lanes below the target come first.  Usable if the first probe is below (or is the stream's
+                // first tile) and some probe inside the stream is not below (or the window reaches the stream's last tile)
+                const bool left_ok = (mb & 1u) || w0 == lo;
+                const bool right_ok = (mi & ~mb) != 0 || w0 + 31 >= hi;
+                if (left_ok && right_ok && mi) {
+                    const unsigned cnt = __popc(mb);
+                    lo = hi = cnt ? w0 + cnt - 1 : lo;
+                }
+            }
             while (lo < hi) {
                 uint64_t span = hi - lo, stepw = (span + 31) / 32;
                 uint64_t probe = lo + (uint64_t)(l + 1) * stepw;

@@ -99,7 +99,7 @@ int s3g_shard_transform(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint
 }
 
 int s3g_shard_transform_peers(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces, uint64_t cap, uint64_t *n_pieces,
-                              const uint64_t *peer_bufs, uint32_t n_peers, uint64_t dst_off, uint64_t *tf_len)
+                              const uint64_t *peer_bufs, uint32_t n_peers, uint64_t multicast_buf, uint64_t dst_off, uint64_t *tf_len)
 {
     if (!ctx || !n_pieces || !tf_len || !peer_bufs || n_peers == 0) { set_error("null argument"); return S3G_E_PARAM; }
     S3G_CUDA(cudaSetDevice(ctx->device));
@@ -107,7 +107,7 @@ int s3g_shard_transform_peers(s3g_ctx *ctx, int64_t carry_max, s3g_chrom *pieces
     *n_pieces = 0; *tf_len = 0;
     if (S.tr.n_lines == 0) return S3G_OK;
     stage_mark(ctx, 0);
-    S3G_TRY(run_transform_rest(ctx, S.base, S.n, &S.tr, S.halo, carry_max, false, true, peer_bufs, n_peers, dst_off));
+    S3G_TRY(run_transform_rest(ctx, S.base, S.n, &S.tr, S.halo, carry_max, false, true, peer_bufs, n_peers, dst_off, multicast_buf));
     ctx->h_chroms.resize(S.tr.n_chroms);
     S3G_CUDA(cudaMemcpyAsync(ctx->h_chroms.data(), ctx->chroms.p, S.tr.n_chroms * sizeof(s3g_chrom), cudaMemcpyDeviceToHost, ctx->stream));
     stage_mark(ctx, -1);
@@ -193,6 +193,20 @@ int s3g_shard_assemble(s3g_ctx *ctx, const uint64_t *n_bits_all, const uint32_t 
         if (stream_len) stream_len[s] = metas[s].byte_len;
     }
     *d_bytes = ctx->streams.p;
+    return S3G_OK;
+}
+
+int s3g_shard_place(s3g_ctx *ctx, uint64_t gather_buf, uint64_t byte_lo, uint64_t byte_hi)
+{
+    if (!ctx || (!gather_buf && byte_hi > byte_lo)) { set_error("null argument"); return S3G_E_PARAM; }
+    if (gather_buf & 3) { set_error("gather buffer must be 4-byte aligned"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    if (byte_hi > byte_lo) {
+        stage_mark(ctx, 5);
+        S3G_TRY(run_place_bytes(ctx, reinterpret_cast<uint8_t *>(gather_buf), byte_lo, byte_hi - byte_lo));
+        stage_mark(ctx, -1);
+    }
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
     return S3G_OK;
 }
 

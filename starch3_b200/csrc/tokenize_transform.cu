@@ -510,9 +510,17 @@ __global__ void __launch_bounds__(FSCAN_T) k_front_scan_spans(FAgg *span, uint64
 // where the transformed bytes go: up to 8 buffers (this GPU's first), the range's bytes at offset `off` in each
 struct PeerDst {
     uint8_t *ptr[8];
+    uint8_t *mc;          // NVLS multicast address of the same buffers (a store to it lands in every GPU's copy), or null
     uint64_t off;
     uint32_t n;
 };
+// one 16-byte store that the NVSwitch replicates into every GPU's copy of the buffer
+__device__ __forceinline__ void multimem_st16(uint8_t *mc_addr, const uint4 &v)
+{
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc_addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
 struct ChromSeed {
     uint64_t first_line, name_off, tf_off;
     uint32_t name_len, pad;
@@ -639,6 +647,19 @@ __global__ void __launch_bounds__(FTH, 3) k_front_write(const uint8_t *__restric
     // the strip leaves as aligned 16-byte vectors -- into this GPU's buffer and, in the N-GPU path, into every peer's copy of
     // the transformed buffer through its NVLink-mapped pointer: the all-gather of the transformed bytes is these stores
     const uint32_t lo_b = ph, hi_b = ph + o_len;
+    if (pd.mc) {
+        // whole vectors once, through the multicast address; the ragged ends byte by byte into every copy
+        uint8_t *mdst = pd.mc + pd.off + o_begin - ph;
+        for (uint32_t c = l * 16; c < hi_b; c += 32 * 16) {
+            if (c >= lo_b && c + 16 <= hi_b) multimem_st16(mdst + c, *reinterpret_cast<const uint4 *>(obuf + c));
+            else
+                for (uint32_t k = 0; k < pd.n; k++) {
+                    uint8_t *dst = pd.ptr[k] + pd.off + o_begin - ph;
+                    for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = obuf[j];
+                }
+        }
+        return;
+    }
     for (uint32_t k = 0; k < pd.n; k++) {
         uint8_t *dst = pd.ptr[k] + pd.off + o_begin - ph;                     // 16-byte aligned
         for (uint32_t c = l * 16; c < hi_b; c += 32 * 16) {
@@ -719,7 +740,7 @@ int run_range_summary(Ctx *ctx, uint64_t n_lines, uint32_t halo, int64_t *tail_m
 
 // kernel (2) over the range measured by run_tokenize; dump = also leave the per-line arrays in ctx
 int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, uint32_t halo, int64_t carry_max, bool dump, bool last_part,
-                       const uint64_t *peer_bufs, uint32_t n_peers, uint64_t peer_off)
+                       const uint64_t *peer_bufs, uint32_t n_peers, uint64_t peer_off, uint64_t multicast_buf)
 {
     const uint64_t n_lines = out->n_lines, n_chroms = out->n_chroms;
     // a range that is not the last hands its last chromosome to the next range, which counts that chromosome's lines
@@ -737,6 +758,8 @@ int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out
             pd.ptr[k] = reinterpret_cast<uint8_t *>(peer_bufs[k]);
         }
         pd.n = n_peers; pd.off = peer_off;
+        if (multicast_buf & 15) { set_error("multicast address must be 16-byte aligned"); return S3G_E_PARAM; }
+        pd.mc = reinterpret_cast<uint8_t *>(multicast_buf);
     } else {
         S3G_TRY(ctx->tf.ensure(out->tf_len + 64));
         pd.ptr[0] = ctx->tf.as<uint8_t>(); pd.n = 1; pd.off = 0;

@@ -14,6 +14,8 @@ with torch.distributed for the exchanges between them:
 The archive is the same bytes as the 1-GPU archive.  `Phases` is the GPU implementation over the C ABI; the tests
 drive the same orchestration with a CPU checker in its place (tests/test_multigpu.py, gloo, world size 2 and 3).
 """
+import os
+
 import numpy as np
 
 MAGIC = bytes([0xca, 0x5c, 0xad, 0x1a])
@@ -196,13 +198,20 @@ class Phases:
             return self._symm_t, self._symm_ptrs
         try:
             import torch.distributed._symmetric_memory as symm
-            cap = int(nbytes + nbytes // 4 + (1 << 20))
-            t = symm.empty(cap, dtype=self.torch.uint8, device=self.device)
+            cap = int(nbytes + nbytes // 4 + (1 << 20)) & ~255
+            # second half: where rank 0 collects the finished byte strings (a bzip2 stream is never much larger than its input)
+            t = symm.empty(2 * cap + (1 << 20), dtype=self.torch.uint8, device=self.device)
             hdl = symm.rendezvous(t, dist.group.WORLD)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             if len(ptrs) != dist.get_world_size() or any(p == 0 or p % 16 for p in ptrs):
                 raise RuntimeError("unexpected symmetric-memory pointers")
             self._symm_t, self._symm_hdl, self._symm_ptrs, self._symm_cap = t, hdl, ptrs, cap
+            mc = 0
+            try:
+                mc = int(hdl.multicast_ptr or 0)      # NVLS: one store, replicated by the switch into every rank's buffer
+            except Exception:
+                mc = 0
+            self._symm_mc = 0 if (mc % 16 or os.environ.get("S3G_NO_MULTICAST")) else mc
             return t, ptrs
         except Exception as e:                     # no NVLink peer mapping here: fall back, once, loudly
             import sys
@@ -210,9 +219,12 @@ class Phases:
             self._symm_off = True
             return None
 
+    def place(self, gather_ptr, lo, hi):
+        self.ctx.shard_place(gather_ptr, lo, hi)
+
     def transform_into(self, carry, peer_ptrs, rank, dst_off):
         order = [peer_ptrs[rank]] + [p for r, p in enumerate(peer_ptrs) if r != rank]      # this GPU's own buffer first
-        return self.ctx.shard_transform_peers(carry, order, dst_off)
+        return self.ctx.shard_transform_peers(carry, order, dst_off, multicast_buf=getattr(self, "_symm_mc", 0))
 
     def plan(self, tf_all, tf_total, soff, level):
         return self.ctx.shard_plan(tf_all.data_ptr(), tf_total, soff, level)
@@ -261,8 +273,15 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
     peer = None
     if world > 1 and hasattr(ph, "peer_buffer") and dist.get_backend() == "nccl" and int(allsm[:, 5].min()) >= 0 and not os.environ.get("S3G_NO_PEER_STORES"):
         peer = ph.peer_buffer(dist, int(allsm[:, 5].sum()) + 64)
+    gather = None
     if peer is not None:
         tf_all, peer_ptrs = peer
+        gather_at = ph._symm_cap                       # offset of the gather region inside the symmetric buffer
+        gather = tf_all[gather_at:]
+        if rank == 0:
+            # zero before anybody places a string: the others get here only after the block-table exchange below, which
+            # this rank enters after this memset has run (s3g_shard_compress synchronises)
+            gather[:min(int(gather.numel()), int(allsm[:, 5].sum()) + (1 << 20))].zero_()
         pieces, my_tf_len = ph.transform_into(carries[rank], peer_ptrs, rank, int(allsm[:rank, 5].sum()))
         tf = None
     else:
@@ -348,12 +367,24 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
     piece, lo, hi, stream_off, stream_len = ph.assemble(n_bits_all, crc_all, b_lo, b_hi, len(streams))
     _mark("assemble")
     total = int(stream_off[-1] + stream_len[-1]) if len(streams) else 0
-    span = torch.tensor([lo, hi], dtype=i64, device=device)
-    spans = torch.empty(world * 2, dtype=i64, device=device)
-    dist.all_gather_into_tensor(spans, span)
-    spans = spans.cpu().numpy().reshape(world, 2)
     payload = None
-    if world > 1:
+    use_gather = world > 1 and gather is not None and total + 8 <= int(gather.numel())
+    if not use_gather:
+        span = torch.tensor([lo, hi], dtype=i64, device=device)
+        spans = torch.empty(world * 2, dtype=i64, device=device)
+        dist.all_gather_into_tensor(spans, span)
+        spans = spans.cpu().numpy().reshape(world, 2)
+    if use_gather:
+        # every rank stores its string into rank 0's gather region through the NVLink-mapped pointer (the end bytes ORed
+        # in): no spans to exchange, no receives, one small all-reduce as the "everybody has stored" point
+        if hi > lo:
+            ph.place(peer_ptrs[0] + gather_at, lo, hi)
+        done = torch.zeros(1, dtype=i64, device=device)
+        dist.all_reduce(done)                        # a rank contributes only after its place kernel has finished
+        done.cpu()
+        if rank == 0:
+            payload = gather[:total + 8]
+    elif world > 1:
         if rank == 0:
             payload = torch.zeros(total + 8, dtype=torch.uint8, device=device)
             payload[lo:hi] = piece[:hi - lo]
@@ -374,6 +405,7 @@ def compress_sharded(ph, dist, rank, world, d_range, n_range, halo, names_src, r
         payload = piece[:total]
     _mark("x byte strings")
     if _t is not None and rank == 0:
+        print(f"[shard] peer stores {'on' if peer is not None else 'off'}, multicast {'on' if getattr(ph, '_symm_mc', 0) else 'off'}, gather by stores {'on' if use_gather else 'off'}", flush=True)
         print("[shard timing, ms] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(_t, _t[1:])), flush=True)
     blocks_of = np.bincount(stream_of, minlength=len(streams)) if nb else np.zeros(len(streams), dtype=np.int64)
     return dict(streams=streams, blocks_of=blocks_of, stream_off=stream_off, stream_len=stream_len, payload=payload, total=total,
