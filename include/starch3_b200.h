@@ -184,6 +184,12 @@ S3G_API int s3g_shard_assemble(s3g_ctx *ctx, const uint64_t *n_bits_all, const u
  * address valid on this GPU, typically the NVLink-mapped pointer of the buffer on the GPU that collects the archive.  The
  * buffer must be zero where nothing was placed yet: the string's end bytes are ORed in (shared with the neighbours). */
 S3G_API int s3g_shard_place(s3g_ctx *ctx, uint64_t gather_buf, uint64_t byte_lo, uint64_t byte_hi);
+/* The phases above driven by ONE process: ctxs[k] = a context per GPU (s3g_init(device_k, &ctxs[k]); a device may appear
+ * more than once), a host thread each.  The small tables are exchanged in host memory; the two bulk exchanges are stores
+ * over NVLink through peer access (s3g_shard_transform_peers, s3g_shard_place).  The archive -- owned by ctxs[0] like the
+ * archive of s3g_compress_bed -- is the same bytes as the single-GPU archive.  What `starch3 --devices=0,1,...` calls. */
+S3G_API int s3g_multi_compress_bed(s3g_ctx **ctxs, int n_ctx, const uint8_t *bed, uint64_t n, int block_size_100k,
+                                   const char *note, s3g_result *res);
 /* CUDA-event time per stage (indices as s3g_result.stage_ms) of the phases run on ctx since s3g_shard_tokenize. */
 S3G_API int s3g_stage_times(s3g_ctx *ctx, double *stage_ms8);
 

@@ -84,6 +84,8 @@ namespace starch3
         int _device;
         int _block_size_100k;
         bool _unstarch;                    // --unstarch: the decoder path (archive in, BED out)
+        std::vector<int> _devices;         // --devices=0,1,..: one archive from several GPUs (s3g_multi_compress_bed)
+        std::vector<s3g_ctx*> _more_ctx;   // the contexts of the devices after the first
 
     public:
         Starch();
@@ -126,6 +128,9 @@ namespace starch3
         void set_device(int d) { _device = d; }
         void set_block_size_100k(int k) { _block_size_100k = k; }
         int get_block_size_100k(void) { return _block_size_100k; }
+        void set_devices(const std::vector<int>& d) { _devices = d; if (!d.empty()) _device = d[0]; }
+        const std::vector<int>& get_devices(void) { return _devices; }
+        std::vector<s3g_ctx*>& get_more_contexts(void) { return _more_ctx; }
         void set_unstarch(bool u) { _unstarch = u; }
         bool get_unstarch(void) { return _unstarch; }
 
@@ -277,6 +282,8 @@ namespace starch3
     inline void Starch::setup_bz_stream_callbacks(Starch*) { /* the stream-end hook (bz/bzlib.c:470) has no per-stream work left: metadata comes back with the batch */ }
 
     inline void Starch::delete_bz_stream_ptr(void) {
+        for (size_t k = 0; k < _more_ctx.size(); k++) s3g_destroy(_more_ctx[k]);
+        _more_ctx.clear();
         if (!_bz_stream_ptr) return;
         s3g_destroy(_bz_stream_ptr);
         _bz_stream_ptr = NULL;
@@ -377,9 +384,23 @@ namespace starch3
             return;
         }
         s3g_result res;
-        int rc = sb->next_in ? s3g_stream_end(me->get_device_context(), &res)
-                             : s3g_compress_bed(me->get_device_context(), reinterpret_cast<const uint8_t*>(sb->in_line), sb->in_line_size,
-                                                me->get_block_size_100k(), me->get_note().c_str(), &res);
+        int rc;
+        if (sb->next_in) rc = s3g_stream_end(me->get_device_context(), &res);
+        else if (me->get_devices().size() > 1) {
+            // one archive from several GPUs: a context per device, the phases driven by s3g_multi_compress_bed
+            std::vector<s3g_ctx*> ctxs(1, me->get_device_context());
+            rc = S3G_OK;
+            for (size_t k = 1; k < me->get_devices().size() && rc == S3G_OK; k++) {
+                s3g_ctx* c = NULL;
+                rc = s3g_init(me->get_devices()[k], &c);
+                if (rc == S3G_OK) { ctxs.push_back(c); me->get_more_contexts().push_back(c); }
+            }
+            if (rc == S3G_OK)
+                rc = s3g_multi_compress_bed(ctxs.data(), static_cast<int>(ctxs.size()), reinterpret_cast<const uint8_t*>(sb->in_line), sb->in_line_size,
+                                            me->get_block_size_100k(), me->get_note().c_str(), &res);
+        } else
+            rc = s3g_compress_bed(me->get_device_context(), reinterpret_cast<const uint8_t*>(sb->in_line), sb->in_line_size,
+                                  me->get_block_size_100k(), me->get_note().c_str(), &res);
         if (rc != S3G_OK) {
             std::fprintf(stderr, "Error: %s\n", s3g_last_error());
             std::exit(rc == S3G_E_NOMEM ? ENOMEM : rc == S3G_E_MALFORMED ? EINVAL : rc == S3G_E_CUDA ? ENODEV : EINVAL);

@@ -21,9 +21,10 @@ C_ABI_SYMBOLS = [
     "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_stream_begin", "s3g_stream_write", "s3g_stream_end",
-    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_stage_times",
+    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_multi_compress_bed", "s3g_stage_times",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
     "s3g_decompress_archive", "s3g_bz_decompress", "s3g_inverse_transform",
+    "s3g_BZ2_bzCompressInit", "s3g_BZ2_bzCompress", "s3g_BZ2_bzCompressEnd",
 ]
 
 
@@ -113,6 +114,7 @@ def lib():
         L.s3g_shard_compress.argtypes = [vp, u64, u64, vp, vp, vp]
         L.s3g_shard_assemble.argtypes = [vp, vp, vp, u64, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), vp, vp]
         L.s3g_shard_place.argtypes = [vp, u64, u64, u64]
+        L.s3g_multi_compress_bed.argtypes = [vp, i32, vp, u64, i32, C.c_char_p, C.POINTER(CResult)]
         L.s3g_stage_times.argtypes = [vp, vp]
         L.s3g_tokenize.argtypes = [vp, vp, u64, u64, C.POINTER(u64), vp, vp, vp, vp, vp]
         L.s3g_transform.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64), C.POINTER(u64)]
@@ -183,6 +185,21 @@ class Result:
         c = self.chroms[i]
         o = self.streams_off + c["bz_off"]
         return self.archive[o:o + c["bz_len"]]
+
+
+def multi_compress_bed(contexts, bed, block_size_100k=9, note=None):
+    """One archive from several GPUs in this process (s3g_multi_compress_bed): `contexts` = one Context per GPU."""
+    a = _u8(bed)
+    hs = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    r = CResult()
+    rc = lib().s3g_multi_compress_bed(hs, len(contexts), _p(a), len(a), block_size_100k, note.encode() if isinstance(note, str) else note, C.byref(r))
+    try:
+        contexts[0]._check(rc)
+        res = Result(r, None)
+        res.archive
+        return res
+    finally:
+        lib().s3g_result_free(C.byref(r))
 
 
 class Context:

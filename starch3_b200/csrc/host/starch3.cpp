@@ -36,14 +36,14 @@ int main(int argc, char** argv)
     return EXIT_SUCCESS;
 }
 
-std::string starch3::Starch::get_client_starch_opt_string(void) { return "n:bghvud:k:?"; }
+std::string starch3::Starch::get_client_starch_opt_string(void) { return "n:bghvud:k:D:?"; }
 
 struct option* starch3::Starch::get_client_starch_long_options(void)
 {
     static struct option opts[] = {
         {"note", required_argument, NULL, 'n'},   {"bzip2", no_argument, NULL, 'b'},       {"gzip", no_argument, NULL, 'g'},
         {"help", no_argument, NULL, 'h'},         {"version", no_argument, NULL, 'v'},     {"device", required_argument, NULL, 'd'},
-        {"block-size", required_argument, NULL, 'k'}, {"unstarch", no_argument, NULL, 'u'}, {NULL, no_argument, NULL, 0}};
+        {"block-size", required_argument, NULL, 'k'}, {"unstarch", no_argument, NULL, 'u'}, {"devices", required_argument, NULL, 'D'}, {NULL, no_argument, NULL, 0}};
     return opts;
 }
 
@@ -58,6 +58,20 @@ void starch3::Starch::initialize_command_line_options(int argc, char** argv)
         case 'g': set_compression_method(k_gzip); methods++; break;
         case 'd': set_device(std::atoi(optarg)); break;
         case 'u': set_unstarch(true); break;
+        case 'D': {
+            std::vector<int> devs;
+            for (const char* p = optarg; *p;) {
+                char* e = NULL;
+                long v = std::strtol(p, &e, 10);
+                if (e == p || v < 0) fail(EINVAL, "--devices takes a comma-separated list of CUDA device numbers");
+                devs.push_back(static_cast<int>(v));
+                p = *e == ',' ? e + 1 : e;
+                if (*e && *e != ',') fail(EINVAL, "--devices takes a comma-separated list of CUDA device numbers");
+            }
+            if (devs.empty() || devs.size() > 8) fail(EINVAL, "--devices takes 1 to 8 device numbers");
+            set_devices(devs);
+            break;
+        }
         case 'k': {
             int k = std::atoi(optarg);
             if (k < 1 || k > 9) fail(EINVAL, "bzip2 initialization failed - incorrect parameters");
@@ -99,6 +113,7 @@ std::string starch3::Starch::get_client_starch_io_options(void)
            "  --note=\"foo bar...\"   Append note to output archive metadata (optional)\n"
            "  --bzip2 | --gzip      Compression backend (bzip2 is the default; gzip is unsupported)\n"
            "  --device=N            CUDA device to use (default 0)\n"
+           "  --devices=A,B,...     One archive from several GPUs (up to 8; byte ranges and bzip2 blocks are dealt to them)\n"
            "  --block-size=K        bzip2 block size in 100 kB units, 1..9 (default 9)\n"
            "  --unstarch            Decode: the input is a starch3 archive, the output its BED text\n";
 }

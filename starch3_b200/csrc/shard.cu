@@ -1,7 +1,7 @@
 // shard.cu -- one archive from several GPUs: the hot path cut into phases that a host
 // runs on every GPU with small exchanges in between.  The host is either one process per GPU
 // (starch3_b200/multigpu.py: torch.distributed over NCCL/NVLink for the exchanges) or one process with a context per
-// device (s3g_multi_compress_bed, multi.cu: peer copies).
+// device (s3g_multi_compress_bed, multi.cu: stores over NVLink through peer access).
 //
 //   phase               per GPU                                                    exchanged afterwards
 //   s3g_shard_tokenize  line framing + tokenizer of the GPU's newline-aligned      summary: largest stop since the last

@@ -12,8 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_symbols():
+    """every function include/*.h declares: starch3_b200.h (S3G_API) and the libbz2-shaped front s3g_bzlib.h (S3G_BZ_API)"""
     txt = open(os.path.join(ROOT, "include", "starch3_b200.h")).read()
-    return sorted(set(re.findall(r"S3G_API[^;(]*?\b(s3g_\w+)\s*\(", txt)))
+    syms = set(re.findall(r"S3G_API[^;(]*?\b(s3g_\w+)\s*\(", txt))
+    txt = open(os.path.join(ROOT, "include", "s3g_bzlib.h")).read()
+    syms |= set(re.findall(r"S3G_BZ_API[^;(]*?\b(s3g_\w+)\s*\(", txt))
+    return sorted(syms)
 
 
 def test_header_and_binding_agree():

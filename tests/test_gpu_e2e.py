@@ -239,3 +239,19 @@ def test_cli_streaming_and_unstarch(ctx, tmp_path):
     assert u2.returncode != 0 and b"Error:" in u2.stderr
     w = subprocess.run([exe], input=b"chr1\t50\t60\nchr1\t10\t20\r\nchr2\t1\t2\nchr1\t1\t2\n", stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert w.returncode == 0 and b"not sorted" in w.stderr and b"CR LF" in w.stderr and b"repeat an earlier chromosome" in w.stderr
+
+
+def test_cli_several_devices(ctx, tmp_path):
+    """--devices: one archive from several contexts (the same GPU named twice on a one-GPU box), the single-GPU bytes"""
+    import os
+    import subprocess
+    import torch
+    import starch3_b200 as s3
+    exe = os.path.join(os.path.dirname(s3.lib_path), "starch3")
+    bed = synth.bed(2, 80000).tobytes()
+    f = tmp_path / "in.bed"
+    f.write_bytes(bed)
+    devs = ",".join(str(d) for d in range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else "0,0,0"
+    p = subprocess.run([exe, "--devices", devs, "--note", "md", str(f)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert p.returncode == 0, p.stderr[-500:]
+    assert p.stdout == ctx.compress_bed(bed, 9, note="md").archive

@@ -107,3 +107,54 @@ def test_transform_into_several_buffers(ctx, oracle):
             assert bool((b[:off] == 0xAB).all()) and bool((b[off + n:] == 0xAB).all())
         tf, _, _ = oracle.transform(bed.tobytes())
         assert bytes(want.cpu().numpy()) == tf
+
+
+@pytest.mark.parametrize("world,cfg,lines,level", [(1, 2, 60000, 9), (2, 2, 120000, 9), (3, 5, 90000, 9), (4, 1, 400000, 9), (2, 3, 900000, 9),
+                                                   (3, 4, 60000, 1), (8, 1, 1200000, 9)])
+def test_cpp_host_virtual_ranks(ctx, oracle, world, cfg, lines, level):
+    """s3g_multi_compress_bed (multi.cu): the phases driven by one C++ process, a host thread and a context per rank; on a
+    one-GPU box the contexts share the device.  Same bytes as the single-GPU archive and the oracle's."""
+    import starch3_b200 as s3
+    bed = synth.bed(cfg, lines)
+    ctxs = [s3.Context(0) for _ in range(world)]
+    try:
+        res = s3.multi_compress_bed(ctxs, bed, level, note="cpp")
+        assert res.archive == ctx.compress_bed(bed, level, note="cpp").archive
+        assert res.archive == oracle.archive_mt(bed, level, "cpp")
+        assert res.n_lines == lines and res.n_blocks > 0
+        again = s3.multi_compress_bed(ctxs, bed, level, note="cpp")            # contexts are reusable
+        assert again.archive == res.archive
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_cpp_host_edge_inputs(oracle):
+    import starch3_b200 as s3
+    ctxs = [s3.Context(0) for _ in range(3)]
+    try:
+        for bed in (b"c1\t10\t500\nc1\t20\t30\nc1\t40\t600\tx\nc1\t100\t200\nc2\t5\t6\n", b"chr1\t1\t2\n", b"",
+                    b"chrA\t10\t20\n" * 3 + b"chrB\t1\t2\n" * 2 + b"chrA\t5\t6\n", b"chr1\t1\t2\nchr1\t5\t9\nchr1\t7\t1"):
+            assert s3.multi_compress_bed(ctxs, bed, 9, note="").archive == oracle.archive(bed, 9, ""), bed
+        with pytest.raises(s3.Starch3Error) as e:
+            s3.multi_compress_bed(ctxs, b"chr1\t1\t2\n" * 3000 + b"chr1\t5\n" + b"chr2\t1\t2\n" * 3000, 9)
+        assert e.value.code == -4
+        assert s3.multi_compress_bed(ctxs, b"chr1\t1\t2\n", 9).n_lines == 1       # still usable after the error
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_cpp_host_one_context_per_device(oracle):
+    import torch
+    import starch3_b200 as s3
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU")
+    bed = synth.bed(2, 400000)
+    ctxs = [s3.Context(d) for d in range(n)]
+    try:
+        assert s3.multi_compress_bed(ctxs, bed, 9, note="dev").archive == oracle.archive_mt(bed, 9, "dev")
+    finally:
+        for c in ctxs:
+            c.close()

@@ -434,3 +434,55 @@ def test_bz_compress_golden_samples(ctx, idx, level):
     gold = golden(f"sample{idx}.bz2")
     data = bz2.decompress(gold)
     assert ctx.bz_compress(data, level) == gold
+
+
+def test_libbz2_shaped_front(ctx, oracle):
+    """include/s3g_bzlib.h: the bz_stream layout of the reference's patched libbz2 (bz/bzlib.h:48-69) and its three compress
+    calls (bz/bzlib.h:103-117) over the GPU compressor: input in pieces with BZ_RUN, BZ_FINISH into a small output buffer,
+    the stream-end functor called once (bz/bzlib.c:470), the bytes those of libbz2."""
+    import ctypes as C
+    import starch3_b200 as s3
+    L = s3.lib()
+
+    class BzStream(C.Structure):
+        _fields_ = [("next_in", C.c_void_p), ("avail_in", C.c_uint), ("total_in_lo32", C.c_uint), ("total_in_hi32", C.c_uint),
+                    ("next_out", C.c_void_p), ("avail_out", C.c_uint), ("total_out_lo32", C.c_uint), ("total_out_hi32", C.c_uint),
+                    ("state", C.c_void_p), ("bzalloc", C.c_void_p), ("bzfree", C.c_void_p), ("opaque", C.c_void_p),
+                    ("handler", C.c_void_p), ("block_close_functor", C.c_void_p)]
+    assert C.sizeof(BzStream) == 96          # the stock 80 bytes plus the two pointers of the patch
+    FUNC = C.CFUNCTYPE(None, C.c_void_p)
+    calls = []
+    cb = FUNC(lambda h: calls.append(h))
+    L.s3g_BZ2_bzCompressInit.argtypes = [C.POINTER(BzStream), C.c_int, C.c_int, C.c_int]
+    L.s3g_BZ2_bzCompress.argtypes = [C.POINTER(BzStream), C.c_int]
+    L.s3g_BZ2_bzCompressEnd.argtypes = [C.POINTER(BzStream)]
+    tf, chroms, _ = oracle.transform(synth.bed(2, 60000).tobytes())
+    data = tf[:1500000]
+    for level, piece, outcap in ((9, 100000, 4096), (1, 333333, 1 << 20)):
+        z = BzStream()
+        assert L.s3g_BZ2_bzCompressInit(C.byref(z), level, 0, 30) == 0
+        assert z.block_close_functor is None
+        z.block_close_functor = C.cast(cb, C.c_void_p); z.handler = 0x1234
+        src = C.create_string_buffer(data, len(data))
+        out = C.create_string_buffer(outcap)
+        got = bytearray()
+        for off in range(0, len(data), piece):
+            z.next_in = C.addressof(src) + off; z.avail_in = min(piece, len(data) - off)
+            z.next_out = C.addressof(out); z.avail_out = outcap
+            assert L.s3g_BZ2_bzCompress(C.byref(z), 0) == 1                  # BZ_RUN -> BZ_RUN_OK
+            assert z.avail_in == 0
+        assert L.s3g_BZ2_bzCompress(C.byref(z), 0) == -2                     # BZ_RUN without input: no progress (bz/bzlib.c:432)
+        while True:
+            z.next_out = C.addressof(out); z.avail_out = outcap
+            rc = L.s3g_BZ2_bzCompress(C.byref(z), 2)                         # BZ_FINISH
+            got += out.raw[:outcap - z.avail_out]
+            if rc == 4:                                                      # BZ_STREAM_END
+                break
+            assert rc == 3                                                   # BZ_FINISH_OK
+        assert L.s3g_BZ2_bzCompress(C.byref(z), 2) == -1                     # BZ_SEQUENCE_ERROR after the end
+        assert z.total_in_lo32 == len(data) and z.total_out_lo32 == len(got)
+        assert L.s3g_BZ2_bzCompressEnd(C.byref(z)) == 0 and z.state is None
+        assert bytes(got) == (oracle.ref_bz_compress if oracle.have_ref() else oracle.bz_compress)(data, level)
+    assert calls == [0x1234, 0x1234]
+    bad = BzStream()
+    assert L.s3g_BZ2_bzCompressInit(C.byref(bad), 0, 0, 30) == -2 and L.s3g_BZ2_bzCompress(C.byref(bad), 0) == -2
