@@ -573,9 +573,12 @@ __device__ uint32_t gf_xpow8(uint64_t nbytes)
 }
 
 constexpr int CRC_T = 512;
-// CRC-32/BZIP2 (MSB first, bz/bzlib_private.h:157-172) of the pre-RLE bytes of a block: 512 segments, each
-// by slicing-by-4 (four table look-ups per aligned 32-bit word, 16-byte loads), combined with x^(8n) mod P.
-__global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInfo *blocks)
+// CRC-32/BZIP2 (MSB first, bz/bzlib_private.h:157-172) of the pre-RLE bytes of a block.  The block is cut into `parts`
+// pieces, a CTA each (a batch of few blocks would otherwise leave most SMs idle: ten blocks took as long as 148), every
+// piece into 512 segments, each by slicing-by-4 (four table look-ups per aligned 32-bit word, 16-byte loads).  A segment's
+// register is moved to the end of the BLOCK by a multiplication with x^(8 * bytes after it) mod P; what is left is a sum
+// (XOR) over segments and pieces: the pieces meet in BlockInfo.crc by atomicXor, k_crc_finish complements the sum.
+__global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInfo *blocks, uint32_t parts)
 {
     __shared__ uint32_t tab[4][256];       // tab[k][b]: the CRC register after byte b and k zero bytes
     __shared__ uint32_t part[CRC_T];
@@ -589,13 +592,18 @@ __global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInf
         for (int i = threadIdx.x; i < 256; i += CRC_T) { uint32_t c = tab[k - 1][i]; tab[k][i] = (c << 8) ^ tab[0][c >> 24]; }
         __syncthreads();
     }
-    BlockInfo *bi = &blocks[blockIdx.x];
-    uint64_t a = bi->in_start, len = bi->in_end - bi->in_start;
-    uint64_t per = ((len + CRC_T - 1) / CRC_T + 15) & ~15ull;
-    uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per;
-    if (lo > len) lo = len;
-    if (hi > len) hi = len;
-    uint32_t c = threadIdx.x == 0 ? 0xFFFFFFFFu : 0u;     // only the first segment carries the init state
+    BlockInfo *bi = &blocks[blockIdx.x / parts];
+    const uint32_t pc = blockIdx.x % parts;
+    const uint64_t a = bi->in_start, len = bi->in_end - bi->in_start;
+    // this CTA's piece [p0, p1) of the block, cut at multiples of 16 bytes
+    const uint64_t per_piece = ((len + parts - 1) / parts + 15) & ~15ull;
+    const uint64_t p0 = min(pc * per_piece, len), p1 = min(p0 + per_piece, len);
+    const uint64_t plen = p1 - p0;
+    uint64_t per = ((plen + CRC_T - 1) / CRC_T + 15) & ~15ull;
+    uint64_t lo = p0 + (uint64_t)threadIdx.x * per, hi = lo + per;
+    if (lo > p1) lo = p1;
+    if (hi > p1) hi = p1;
+    uint32_t c = (pc == 0 && threadIdx.x == 0) ? 0xFFFFFFFFu : 0u;     // only the block's first segment carries the init state
     const uint8_t *p = in + a;
     uint64_t i = lo;
     auto word = [&](uint32_t w) {
@@ -608,7 +616,7 @@ __global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInf
         word(v.x); word(v.y); word(v.z); word(v.w);
     }
     for (; i < hi; i++) c = (c << 8) ^ tab[0][(c >> 24) ^ p[i]];
-    // shift by the bytes that follow this segment
+    // shift by the bytes of the block that follow this segment
     uint64_t after = len - hi;
     if (c != 0 && after) c = gf_mulmod(c, gf_xpow8(after));
     part[threadIdx.x] = c;
@@ -617,7 +625,19 @@ __global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInf
         if (threadIdx.x < d) part[threadIdx.x] ^= part[threadIdx.x + d];
         __syncthreads();
     }
-    if (threadIdx.x == 0) bi->crc = ~part[0];
+    if (threadIdx.x == 0 && (part[0] || pc == 0)) atomicXor(&bi->crc, part[0]);
+}
+__global__ void k_crc_finish(BlockInfo *blocks, uint64_t nb)
+{
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) blocks[b].crc = ~blocks[b].crc;
+}
+// pieces per block for a batch of nb blocks
+static uint32_t crc_parts(uint64_t nb)
+{
+    uint32_t parts = 1;
+    while (parts < 16 && (uint64_t)parts * 2 * nb <= 2 * (uint64_t)SM_COUNT) parts *= 2;
+    return parts;
 }
 
 // unseqToSeq map + nInUse per block (makeMaps_e, bz/compress.c:106-115)
@@ -716,7 +736,12 @@ int run_rle_fill(Ctx *ctx, uint64_t b_lo, uint64_t b_hi)
         S3G_LAUNCH(ctx, k_rle_write, (unsigned)(tile1 - tile0), RT, 0, d_in, n, sm, run_carry, e_base, blocks, nb,
                    ctx->blk_bytes.as<uint8_t>(), ctx->in_use.as<uint8_t>(), tile0, b_lo, b_hi);
     S3G_BYTES(ctx, (double)(in_hi - in_lo));
-    S3G_LAUNCH(ctx, k_block_crc, (unsigned)(b_hi - b_lo), CRC_T, 0, d_in, blocks + b_lo);
+    {
+        // the block table's crc fields are zero (the cut leaves them so): the pieces XOR into them
+        const uint32_t parts = crc_parts(b_hi - b_lo);
+        S3G_LAUNCH(ctx, k_block_crc, (unsigned)((b_hi - b_lo) * parts), CRC_T, 0, d_in, blocks + b_lo, parts);
+        S3G_LAUNCH(ctx, k_crc_finish, (unsigned)((b_hi - b_lo + 255) / 256), 256, 0, blocks + b_lo, b_hi - b_lo);
+    }
     S3G_LAUNCH(ctx, k_block_maps, (unsigned)(b_hi - b_lo), 256, 0, ctx->in_use.as<uint8_t>() + b_lo * 256, blocks + b_lo, ctx->seq_map.as<uint8_t>() + b_lo * 256);
     // the mirror learns CRC and alphabet size (the later stages size their launches from it)
     S3G_CUDA(cudaMemcpyAsync(ctx->h_blocks.data() + b_lo, blocks + b_lo, (b_hi - b_lo) * sizeof(BlockInfo), cudaMemcpyDeviceToHost, ctx->stream));
@@ -729,7 +754,9 @@ int run_block_crc(Ctx *ctx, const uint8_t *d_in, BlockInfo *d_blocks, uint64_t n
 {
     if (!nb) return S3G_OK;
     S3G_BYTES(ctx, bytes);
-    S3G_LAUNCH(ctx, k_block_crc, (unsigned)nb, CRC_T, 0, d_in, d_blocks);
+    const uint32_t parts = crc_parts(nb);                  // the descriptors' crc fields must be zero on entry
+    S3G_LAUNCH(ctx, k_block_crc, (unsigned)(nb * parts), CRC_T, 0, d_in, d_blocks, parts);
+    S3G_LAUNCH(ctx, k_crc_finish, (unsigned)((nb + 255) / 256), 256, 0, d_blocks, nb);
     return check_launch("block crc");
 }
 
