@@ -87,7 +87,7 @@ static DevBuf *const *all_bufs(Ctx *c, size_t *n)
     B(rle_carry); B(rle_ebase); B(blocks); B(blk_prov); B(blk_bytes); B(in_use); B(seq_map); B(stream_tab);
     B(sa); B(rk); B(kv0); B(kv1); B(hist); B(bwt_misc); B(bwt_ghist); B(lcol);
     B(mtf0); B(mtfv16); B(mtf_freq); B(ztiles); B(bits); B(pool); B(pool_woff); B(streams); B(stream_meta);
-    B(io_a); B(io_b); B(io_c); B(io_d); B(io_e);
+    B(io_a); B(io_b); B(io_c); B(io_d); B(io_e); B(chain_tf[0]); B(chain_tf[1]); B(chain_out);
 #undef B
     *n = k;
     return list;
@@ -538,17 +538,64 @@ static void stage_copier(Ctx *ctx, int tid, const uint8_t *bed, uint64_t n, cons
     for (int q = 0; q < 2; q++) if (used[q]) cudaEventSynchronize(ev[q]);
 }
 
-static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int level, const char *note, int nparts, s3g_result *res)
+// Queues the upload of the ranges cut[0..nparts] of `bed` into ctx->bed on the copy stream, one event (ctx->part_ev[i]) per
+// range; sh.queued[i] says that range i's event has been recorded.  Pinned input: everything is queued before this returns.
+// Pageable input: copier threads (join them) stage it through pinned pieces.
+static int start_upload(Ctx *ctx, const uint8_t *bed, uint64_t n, const std::vector<uint64_t> &cut, int nparts, PipeShared &sh,
+                        std::vector<int> &left, std::vector<std::thread> &copiers)
 {
-    memset(res, 0, sizeof *res);
-    if (level < 1 || level > 9) { set_error("block_size_100k must be 1..9"); return S3G_E_PARAM; }
-    S3G_CUDA(cudaSetDevice(ctx->device));
+    // is the caller's buffer pinned?  (an unregistered pointer reports cudaMemoryTypeUnregistered, or an error on old drivers)
+    bool pinned_input = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, bed) == cudaSuccess) pinned_input = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+        else cudaGetLastError();
+        if (getenv("S3G_NO_STAGING")) pinned_input = true;
+    }
+    sh.queued.assign(nparts, 0);
+    left.assign(nparts, 0);
+    if (pinned_input) {
+        for (int i = 0; i < nparts; i++) {
+            if (cut[i + 1] > cut[i])
+                S3G_CUDA(cudaMemcpyAsync(ctx->bed.as<uint8_t>() + cut[i], bed + cut[i], cut[i + 1] - cut[i], cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (i == nparts - 1) S3G_CUDA(cudaMemsetAsync(ctx->bed.as<uint8_t>() + n, 0, 64, ctx->copy_stream));
+            S3G_CUDA(cudaEventRecord(ctx->part_ev[i], ctx->copy_stream));
+            sh.queued[i] = 1;
+        }
+    } else {
+        if (!ctx->h_stage) {
+            if (cudaMallocHost(&ctx->h_stage, 2ull * STAGE_THREADS * STAGE_PIECE) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+            for (int q = 0; q < 2 * STAGE_THREADS; q++) {
+                cudaEvent_t e;
+                S3G_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->stage_ev.push_back(e);
+            }
+        }
+        for (int i = 0; i < nparts; i++) left[i] = cut[i + 1] > cut[i] ? (int)((cut[i + 1] - cut[i] + STAGE_PIECE - 1) / STAGE_PIECE) : 1;
+        for (int t = 0; t < STAGE_THREADS; t++)
+            copiers.emplace_back(stage_copier, ctx, t, bed, n, std::cref(cut), nparts, std::ref(left), std::ref(sh));
+    }
+    return S3G_OK;
+}
+
+// copy stream and one event per range
+static int ensure_pipe_objects(Ctx *ctx, int nparts)
+{
     if (!ctx->copy_stream) S3G_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while ((int)ctx->part_ev.size() < nparts) {
         cudaEvent_t e;
         S3G_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->part_ev.push_back(e);
     }
+    return S3G_OK;
+}
+
+static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int level, const char *note, int nparts, s3g_result *res)
+{
+    memset(res, 0, sizeof *res);
+    if (level < 1 || level > 9) { set_error("block_size_100k must be 1..9"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    S3G_TRY(ensure_pipe_objects(ctx, nparts));
     for (int k = 0; k < 2; k++)
         if (!ctx->sub[k]) {
             s3g_ctx *c = nullptr;
@@ -572,41 +619,15 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     // half of the input is generous for BED (the one-shot path takes over if it ever is not)
     S3G_TRY(ensure_archive(ctx, HDR_RESERVE + std::max<uint64_t>(n / 2, ctx->archive_hint + (ctx->archive_hint >> 3)) + 4096));
     cudaEvent_t t0 = ctx->ev0, t1 = ctx->ev1;
-    // is the caller's buffer pinned?  (an unregistered pointer reports cudaMemoryTypeUnregistered, or an error on old drivers)
-    bool pinned_input = false;
-    {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, bed) == cudaSuccess) pinned_input = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
-        else cudaGetLastError();
-        if (getenv("S3G_NO_STAGING")) pinned_input = true;
-    }
     std::vector<PartOut> parts(nparts);
     PipeShared sh;
     sh.archive_cap = ctx->h_archive_cap;
-    sh.queued.assign(nparts, 0);
-    std::vector<int> left(nparts, 0);
+    std::vector<int> left;
     std::vector<std::thread> copiers;
     S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));
-    if (pinned_input) {
-        for (int i = 0; i < nparts; i++) {
-            if (cut[i + 1] > cut[i])
-                S3G_CUDA(cudaMemcpyAsync(ctx->bed.as<uint8_t>() + cut[i], bed + cut[i], cut[i + 1] - cut[i], cudaMemcpyHostToDevice, ctx->copy_stream));
-            if (i == nparts - 1) S3G_CUDA(cudaMemsetAsync(ctx->bed.as<uint8_t>() + n, 0, 64, ctx->copy_stream));
-            S3G_CUDA(cudaEventRecord(ctx->part_ev[i], ctx->copy_stream));
-            sh.queued[i] = 1;
-        }
-    } else {
-        if (!ctx->h_stage) {
-            if (cudaMallocHost(&ctx->h_stage, 2ull * STAGE_THREADS * STAGE_PIECE) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
-            for (int q = 0; q < 2 * STAGE_THREADS; q++) {
-                cudaEvent_t e;
-                S3G_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                ctx->stage_ev.push_back(e);
-            }
-        }
-        for (int i = 0; i < nparts; i++) left[i] = cut[i + 1] > cut[i] ? (int)((cut[i + 1] - cut[i] + STAGE_PIECE - 1) / STAGE_PIECE) : 1;
-        for (int t = 0; t < STAGE_THREADS; t++)
-            copiers.emplace_back(stage_copier, ctx, t, bed, n, std::cref(cut), nparts, std::ref(left), std::ref(sh));
+    {
+        int rc = start_upload(ctx, bed, n, cut, nparts, sh, left, copiers);
+        if (rc != S3G_OK) { for (std::thread &c : copiers) c.join(); return rc; }
     }
     std::thread th0(pipe_worker, ctx, ctx->sub[0], 0, nparts, std::cref(cut), level, std::ref(parts), std::ref(sh));
     std::thread th1(pipe_worker, ctx, ctx->sub[1], 1, nparts, std::cref(cut), level, std::ref(parts), std::ref(sh));
@@ -655,6 +676,251 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     ctx->last_streams_size = sh.streams_so_far;                // s3g_read_streams serves them from the pinned archive
     ctx->last_streams_host = ctx->h_archive + HDR_RESERVE;
     ctx->archive_hint = sh.streams_so_far;
+    return S3G_OK;
+}
+
+// ---- chained host entry: ranges of ONE chromosome ---------------------------------------------------
+// The pipelined entry above hands out whole chromosomes, so an input that is one long chromosome (BASELINE.json
+// configs 1 and 3) gets no overlap from it: the upload and the compression run one after the other.  Here the unit is the
+// bzip2 BLOCK.  The input is cut into ranges at line starts; as soon as a range has arrived it is tokenised and
+// transformed with the phases of the N-GPU path (shard.cu: the line before the range is its "halo", the largest stop so
+// far is carried), its transformed bytes go behind the tail the step before left unfinished, the block cut runs over
+// tail + new bytes, and every block whose cut can no longer move is sorted and coded while the next range is still on its
+// way.  A block's cut depends on the bytes up to the first byte of the run that did not fit (bz/bzlib.c:225-293, :307),
+// so a block that ends at least two bytes before the end of what is there is final; the bytes after the last final
+// block (less than two blocks) are the next step's tail, and a step starts there with the clean run state the reference
+// has at that point (the pending run goes to the next block whole).  The bits of a step continue where the step before
+// stopped (bz/compress.c:609 keeps bsBuff across blocks): stream headers, trailers and combined CRCs come from the
+// carried state, the byte strings meet in a device buffer whose seam bytes are ORed (k_place_bytes).  The archive is
+// the same bytes as the one-shot path's.
+static int grow_keep(Ctx *ctx, DevBuf &b, uint64_t need, uint64_t keep);
+struct ChainStream {
+    std::string name;
+    s3g_chrom c;
+};
+
+static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int level, const char *note, int nparts, s3g_result *res)
+{
+    memset(res, 0, sizeof *res);
+    if (level < 1 || level > 9) { set_error("block_size_100k must be 1..9"); return S3G_E_PARAM; }
+    S3G_CUDA(cudaSetDevice(ctx->device));
+    // ranges: equal sizes, cut at line starts, none empty; halo = the line before a range
+    std::vector<uint64_t> cut(1, 0);
+    for (int i = 1; i < nparts; i++) {
+        uint64_t p = std::max<uint64_t>(cut.back(), (uint64_t)((__uint128_t)n * i / nparts));
+        const void *nl = p < n ? memchr(bed + p, '\n', n - p) : nullptr;
+        p = nl ? (uint64_t)((const uint8_t *)nl - bed) + 1 : n;
+        if (p > cut.back() && p < n) cut.push_back(p);
+    }
+    cut.push_back(n);
+    nparts = (int)cut.size() - 1;
+    std::vector<uint64_t> halo(nparts, 0);
+    for (int i = 1; i < nparts; i++) {
+        uint64_t q = cut[i] - 1;                         // bed[cut[i] - 1] is the line feed that ends the halo line
+        while (q > 0 && bed[q - 1] != '\n') q--;
+        halo[i] = cut[i] - q;
+    }
+    S3G_TRY(ensure_pipe_objects(ctx, nparts));
+    if (!ctx->out_stream) S3G_CUDA(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+    if (!ctx->out_ev) S3G_CUDA(cudaEventCreateWithFlags(&ctx->out_ev, cudaEventDisableTiming));
+    S3G_TRY(ctx->bed.ensure(n + 64));
+    S3G_TRY(ensure_archive(ctx, HDR_RESERVE + std::max<uint64_t>(n / 2, ctx->archive_hint + (ctx->archive_hint >> 3)) + 4096));
+    const uint64_t out_cap = ctx->h_archive_cap - HDR_RESERVE;
+    S3G_TRY(ctx->chain_out.ensure(out_cap + 64));
+    S3G_CUDA(cudaMemsetAsync(ctx->chain_out.p, 0, out_cap + 64, ctx->stream));     // seam bytes are ORed into it
+    uint64_t range_max = 0;
+    for (int i = 0; i < nparts; i++) range_max = std::max(range_max, cut[i + 1] - cut[i]);
+    for (int k = 0; k < 2; k++) S3G_TRY(ctx->chain_tf[k].ensure(range_max + (4ull << 20)));
+    cudaEvent_t t0 = ctx->ev0, t1 = ctx->ev1;
+    PipeShared sh;
+    std::vector<int> left;
+    std::vector<std::thread> copiers;
+    S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));
+    int rc = start_upload(ctx, bed, n, cut, nparts, sh, left, copiers);
+
+    std::vector<ChainStream> streams;            // the archive's streams, in order; the last one may be open
+    bool open = false;                           // streams.back() has blocks still to come
+    uint64_t open_bits = 0; uint32_t open_comb = 0;   // bits of the open stream so far (its header included), combined CRC so far
+    uint64_t out_bytes = 0;                      // bytes of the closed streams = where the open / next stream starts
+    uint64_t copied = 0;                         // bytes of chain_out already on their way to the host
+    uint64_t tail_len = 0;                       // unfinished bytes of the open stream at the start of chain_tf[cur]
+    int cur = 0;
+    int64_t run_max = INT64_MIN;                 // largest stop since the last chromosome start (carry_chain of multi.cu)
+    const uint8_t *d_bed = ctx->bed.as<uint8_t>();
+    s3g_ctx *cx = static_cast<s3g_ctx *>(ctx);           // the phases of shard.cu take the C handle
+    std::vector<s3g_chrom> pc(256);
+    std::vector<uint64_t> soff, items;
+    std::vector<uint32_t> gidx;                  // step stream -> index into `streams`
+
+    auto step = [&](int i) -> int {
+        const bool last = i == nparts - 1;
+        {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            sh.cv.wait(lk, [&] { return sh.queued[i] || sh.rc != S3G_OK; });
+            if (sh.rc != S3G_OK) { set_error("%s", sh.err.c_str()); return sh.rc; }
+        }
+        S3G_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->part_ev[i], 0));
+        // ---- tokenise + transform the range behind the tail ----
+        const uint64_t lo = cut[i] - halo[i], len = cut[i + 1] - lo;
+        s3g_shard_summary sm;
+        S3G_TRY(s3g_shard_tokenize(cx, d_bed + lo, len, halo[i], &sm));
+        const int64_t carry = sm.continues ? run_max : INT64_MIN;
+        if (sm.n_lines) run_max = (sm.single_piece && sm.continues) ? std::max(sm.tail_max, carry) : sm.tail_max;
+        res->n_lines += sm.n_lines;
+        if (last) res->dropped_tail_bytes = sm.dropped_tail_bytes;
+        DevBuf &T = ctx->chain_tf[cur];
+        S3G_TRY(grow_keep(ctx, T, tail_len + sm.tf_bytes + 256, tail_len));
+        uint64_t np = 0, tl = 0;
+        for (;;) {
+            const uint64_t buf = (uint64_t)(uintptr_t)T.p;
+            int r2 = s3g_shard_transform_peers(cx, carry, pc.data(), pc.size(), &np, &buf, 1, 0, tail_len, &tl);
+            if (r2 == S3G_E_CAPACITY && pc.size() < (1u << 24)) { pc.resize(pc.size() * 16); continue; }
+            S3G_TRY(r2);
+            break;
+        }
+        if (tl != sm.tf_bytes) { set_error("transformed size differs from the measured one"); return S3G_E_CUDA; }
+        if (sm.n_lines) { res->unsorted_lines += front_unsorted(ctx); res->crlf_lines += front_crlf(ctx); }
+        res->tf_bytes += tl;
+        // ---- the step's streams: the tail (+ the piece that continues it), then the range's other chromosomes ----
+        const uint64_t n_step = tail_len + tl;
+        soff.clear(); gidx.clear();
+        if (tail_len) { soff.push_back(0); gidx.push_back((uint32_t)streams.size() - 1); }
+        uint64_t off = tail_len;
+        for (uint64_t q = 0; q < np; q++) {
+            const s3g_chrom &p = pc[q];
+            if (q == 0 && sm.continues && open) {
+                s3g_chrom &c = streams.back().c;
+                c.tf_len += p.tf_len; c.line_count += p.line_count; c.bases_nonunique += p.bases_nonunique; c.bases_unique += p.bases_unique;
+                if (!tail_len) { set_error("chained entry: an open stream without a tail"); return S3G_E_CUDA; }
+            } else {
+                ChainStream cs;
+                cs.name.assign(reinterpret_cast<const char *>(bed + lo + p.name_off), p.name_len);
+                memset(&cs.c, 0, sizeof cs.c);
+                cs.c.name_off = lo + p.name_off; cs.c.name_len = p.name_len;
+                cs.c.tf_len = p.tf_len; cs.c.line_count = p.line_count; cs.c.bases_nonunique = p.bases_nonunique; cs.c.bases_unique = p.bases_unique;
+                streams.push_back(cs);
+                soff.push_back(off); gidx.push_back((uint32_t)streams.size() - 1);
+            }
+            off += p.tf_len;
+        }
+        if (off != n_step) { set_error("chained entry: piece table and transformed size disagree"); return S3G_E_CUDA; }
+        const uint64_t ns = gidx.size();
+        if (ns == 0) return S3G_OK;                              // nothing yet (a range without a complete line)
+        soff.push_back(n_step);
+        // ---- block cut over tail + new bytes; the blocks whose cut is final ----
+        uint64_t nb = 0;
+        S3G_TRY(s3g_shard_plan(cx, T.p, n_step, soff.data(), ns, level, &nb, nullptr, nullptr, ~0ull));
+        const std::vector<BlockInfo> &hb = ctx->h_blocks;
+        uint64_t b_fin = nb;
+        if (!last) while (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1 && hb[b_fin - 1].in_end + 2 > n_step) b_fin--;
+        S3G_TRY(s3g_shard_compress(cx, 0, b_fin, nullptr, nullptr, nullptr));
+        // ---- where the step's bits go ----
+        items.clear();
+        std::vector<uint64_t> patches;
+        uint64_t bit_lo = ~0ull, bit_hi = 0, b = 0;
+        auto mark = [&](uint64_t at, uint64_t nbits) { bit_lo = std::min(bit_lo, at); bit_hi = std::max(bit_hi, at + nbits); };
+        for (uint64_t s = 0; s < ns; s++) {
+            s3g_chrom &c = streams[gidx[s]].c;
+            uint64_t bits; uint32_t comb;
+            if (s == 0 && tail_len) { bits = open_bits; comb = open_comb; }
+            else {
+                c.bz_off = out_bytes; c.tf_off = 0;
+                patches.push_back(out_bytes * 8); patches.push_back(0x425a6800u | (uint32_t)('0' + level));       // bz/compress.c:622-628
+                mark(out_bytes * 8, 32);
+                bits = 32; comb = 0;
+            }
+            bool all_final = true;
+            for (; b < nb && hb[b].chrom == s; b++) {
+                if (b >= b_fin) { all_final = false; continue; }
+                items.push_back(out_bytes * 8 + bits);
+                mark(out_bytes * 8 + bits, hb[b].n_bits);
+                bits += hb[b].n_bits;
+                comb = ((comb << 1) | (comb >> 31)) ^ hb[b].crc;                                                  // :607-608
+                c.n_blocks++;
+                res->n_blocks++; res->rle_bytes += hb[b].nblock; res->mtf_symbols += hb[b].n_mtf;
+            }
+            if (all_final) {
+                const uint64_t end = out_bytes * 8 + bits;                                                        // :657-666
+                patches.push_back(end); patches.push_back(0x17724538u);
+                patches.push_back(end + 32); patches.push_back(0x50900000u | (comb >> 16));
+                patches.push_back(end + 64); patches.push_back((uint64_t)(uint32_t)(comb << 16));
+                mark(end, 80);
+                bits += 80;
+                c.bz_len = (bits + 7) >> 3;
+                out_bytes += c.bz_len;
+                open = false;
+            } else {
+                open = true; open_bits = bits; open_comb = comb;
+            }
+        }
+        if (b != nb) { set_error("chained entry: block table and stream table disagree"); return S3G_E_CUDA; }
+        if (bit_hi > bit_lo) {
+            const uint64_t byte_lo = bit_lo >> 3, byte_hi = (bit_hi + 7) >> 3;
+            if (byte_hi > out_cap) return S3G_E_CAPACITY;                        // caller falls back to the one-shot path
+            for (uint64_t &v : items) v -= byte_lo * 8;
+            const uint64_t n_patch = patches.size() / 2;
+            for (uint64_t k = 0; k < patches.size(); k += 2) patches[k] -= byte_lo * 8;
+            items.insert(items.end(), patches.begin(), patches.end());
+            S3G_TRY(run_assemble_items(ctx, 0, b_fin, items, n_patch, byte_hi - byte_lo));
+            S3G_TRY(run_place_bytes(ctx, ctx->chain_out.as<uint8_t>(), byte_lo, byte_hi - byte_lo));
+            // the bytes that are complete leave for the host beside the next step's kernels
+            const uint64_t done = last ? out_bytes : (bit_hi >> 3);
+            if (done > copied) {
+                S3G_CUDA(cudaEventRecord(ctx->out_ev, ctx->stream));
+                S3G_CUDA(cudaStreamWaitEvent(ctx->out_stream, ctx->out_ev, 0));
+                S3G_CUDA(cudaMemcpyAsync(ctx->h_archive + HDR_RESERVE + copied, ctx->chain_out.as<uint8_t>() + copied, done - copied,
+                                         cudaMemcpyDeviceToHost, ctx->out_stream));
+                copied = done;
+            }
+        }
+        // ---- the tail moves to the front of the other buffer ----
+        if (last) { tail_len = 0; return S3G_OK; }
+        const uint64_t tail_start = (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1) ? hb[b_fin - 1].in_end : soff[ns - 1];
+        const uint64_t new_tail = n_step - tail_start;
+        DevBuf &N = ctx->chain_tf[cur ^ 1];
+        S3G_TRY(N.ensure(new_tail + range_max + (4ull << 20)));
+        if (new_tail) S3G_CUDA(cudaMemcpyAsync(N.p, static_cast<const uint8_t *>(T.p) + tail_start, new_tail, cudaMemcpyDeviceToDevice, ctx->stream));
+        tail_len = new_tail; cur ^= 1;
+        return S3G_OK;
+    };
+
+    for (int i = 0; rc == S3G_OK && i < nparts; i++) rc = step(i);
+    for (std::thread &c : copiers) c.join();
+    if (rc != S3G_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->out_stream); cudaStreamSynchronize(ctx->stream); return rc; }
+    if (open) { set_error("chained entry: a stream was left open"); return S3G_E_CUDA; }
+    S3G_CUDA(cudaEventRecord(t1, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->out_stream));
+    S3G_CUDA(cudaEventSynchronize(t1));
+    float ms = 0;
+    S3G_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    res->device_ms = ms;                                       // first upload to last kernel
+    // ---- the archive ----
+    std::vector<s3g_chrom> chroms;
+    std::vector<uint8_t> names;
+    { uint64_t t = 0; for (ChainStream &cs : streams) { cs.c.tf_off = t; t += cs.c.tf_len; chroms.push_back(cs.c); names.insert(names.end(), cs.name.begin(), cs.name.end()); } }
+    names.push_back(0);
+    res->reappearing_chroms = count_reappearing(chroms, names.data());
+    ctx->h_chroms = chroms;
+    fill_result(res, chroms);
+    if (!res->chroms) { set_error("out of host memory"); return S3G_E_NOMEM; }
+    std::vector<uint64_t> name_off(chroms.size() + 1, 0);
+    for (size_t c = 0; c < chroms.size(); c++) name_off[c + 1] = name_off[c] + chroms[c].name_len;
+    std::string hdr = build_header(names.data(), name_off, chroms, level, note);
+    const uint64_t streams_off = 4 + hdr.size() + 1;
+    if (streams_off > HDR_RESERVE) { s3g_result_free(res); return S3G_E_CAPACITY; }      // enormous chromosome table: one-shot path
+    uint8_t *arc = ctx->h_archive + HDR_RESERVE - streams_off;
+    static const uint8_t magic[4] = {0xca, 0x5c, 0xad, 0x1a};      // hpp:907-910
+    memcpy(arc, magic, 4);
+    memcpy(arc + 4, hdr.data(), hdr.size());
+    arc[4 + hdr.size()] = '\n';
+    res->archive = arc;
+    res->streams_off = streams_off;
+    res->streams_size = out_bytes;
+    res->archive_size = streams_off + out_bytes;
+    res->d_streams = ctx->chain_out.p;
+    ctx->last_streams_size = out_bytes;
+    ctx->last_streams_host = ctx->h_archive + HDR_RESERVE;
+    ctx->archive_hint = out_bytes;
     return S3G_OK;
 }
 
@@ -790,6 +1056,8 @@ void s3g_destroy(s3g_ctx *ctx)
     for (int k2 = 0; k2 < 2; k2++) if (ctx->sub[k2]) { s3g_destroy(static_cast<s3g_ctx *>(ctx->sub[k2])); ctx->sub[k2] = nullptr; }
     for (cudaEvent_t e : ctx->part_ev) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
+    if (ctx->out_ev) cudaEventDestroy(ctx->out_ev);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -881,10 +1149,36 @@ int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int level, co
 {
     if (!ctx || !res || (!bed && n)) { set_error("null argument"); return S3G_E_PARAM; }
     S3G_CUDA(cudaSetDevice(ctx->device));
-    int nparts = n >= PIPE_MIN_BYTES ? 3 : 1;
+    uint64_t pipe_min = PIPE_MIN_BYTES;
+    if (const char *e = getenv("S3G_PIPE_MIN")) { long long v = atoll(e); if (v > 0) pipe_min = (uint64_t)v; }
+    int nparts = n >= pipe_min ? 3 : 1;
     if (const char *e = getenv("S3G_PARTS")) { int v = atoi(e); if (v >= 1 && v <= 64) nparts = v; }
     if (nparts > 1 && !ctx->prof) {
-        int rc = compress_bed_pipelined(ctx, bed, n, level, note, nparts, res);
+        // Few chromosome changes (one long chromosome, BASELINE.json configs 1 and 3): ranges of whole chromosomes would not
+        // overlap anything, so the ranges are chained at block granularity instead.  Sampled at eight line starts.
+        bool chain = false;
+        if (const char *e = getenv("S3G_CHAIN")) chain = atoi(e) != 0;
+        else {
+            int changes = 0;
+            std::string prev;
+            for (int k = 0; k < 8; k++) {
+                uint64_t p = (uint64_t)((__uint128_t)n * k / 8);
+                if (k) { const void *nl = memchr(bed + p, '\n', n - p); if (!nl) break; p = (uint64_t)((const uint8_t *)nl - bed) + 1; }
+                uint64_t q = p;
+                while (q < n && q - p < 256 && bed[q] != '\t' && bed[q] != '\n') q++;
+                std::string name(reinterpret_cast<const char *>(bed + p), q - p);
+                if (k && name != prev) changes++;
+                prev = name;
+            }
+            chain = changes < 4;
+        }
+        int rc;
+        if (chain) {
+            uint64_t range = 160ull << 20;
+            if (const char *e = getenv("S3G_CHAIN_BYTES")) { long long v = atoll(e); if (v > 0) range = (uint64_t)v; }
+            const int steps = (int)std::min<uint64_t>(256, std::max<uint64_t>(2, (n + range - 1) / range));
+            rc = compress_bed_chained(ctx, bed, n, level, note, steps, res);
+        } else rc = compress_bed_pipelined(ctx, bed, n, level, note, nparts, res);
         if (rc != S3G_E_CAPACITY) return rc;
         s3g_result_free(res);                                  // does not fit the pipelined buffers: one piece
     }

@@ -222,6 +222,31 @@ int run_place_bytes(Ctx *ctx, uint8_t *dst, uint64_t at, uint64_t len)
     return check_launch("place bytes");
 }
 
+// Blocks [b_lo, b_hi) of ctx->blocks (their bits in the pool) at the bit positions items[0 .. b_hi - b_lo), then
+// n_patch (bit position, 32-bit word) pairs -- stream headers and trailers -- all relative to the first bit of a byte
+// string of `nbytes` bytes, which is left in ctx->streams.
+int run_assemble_items(Ctx *ctx, uint64_t b_lo, uint64_t b_hi, const std::vector<uint64_t> &items, uint64_t n_patch, uint64_t nbytes)
+{
+    const uint64_t words = (nbytes + 3) / 4 + 4;
+    S3G_TRY(ctx->streams.ensure(words * 4));
+    uint32_t *dst = ctx->streams.as<uint32_t>();
+    S3G_CUDA(cudaMemsetAsync(dst, 0, words * 4, ctx->stream));
+    if (items.size() != (b_hi - b_lo) + 2 * n_patch) { set_error("assemble: item table does not match the block range"); return S3G_E_PARAM; }
+    if (items.empty()) return S3G_OK;
+    const uint64_t patch_at = b_hi - b_lo;
+    S3G_TRY(ctx->io_d.ensure(items.size() * 8 + 64));
+    S3G_CUDA(cudaMemcpyAsync(ctx->io_d.p, items.data(), items.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));                   // `items` is pageable and may die with the caller's frame
+    if ((b_hi - b_lo) > (1ull << 26)) { set_error("too many bzip2 blocks in one call"); return S3G_E_LIMIT; }
+    if (b_hi > b_lo)
+        S3G_LAUNCH(ctx, k_concat_range, (unsigned)((b_hi - b_lo) * 32), 256, 0, ctx->blocks.as<BlockInfo>() + b_lo, ctx->pool.as<uint32_t>(),
+                   ctx->pool_woff.as<uint64_t>() + b_lo, ctx->io_d.as<uint64_t>(), dst);
+    if (n_patch)
+        S3G_LAUNCH(ctx, k_patch_words, (unsigned)((n_patch + 127) / 128), 128, 0, ctx->io_d.as<uint64_t>() + patch_at, n_patch, dst);
+    S3G_LAUNCH(ctx, k_bswap, 592, 256, 0, dst, words);
+    return check_launch("assemble items");
+}
+
 int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, uint64_t b_hi, uint64_t *byte_lo, uint64_t *byte_hi,
                        std::vector<StreamMeta> *metas)
 {
@@ -256,15 +281,10 @@ int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, u
     const uint64_t bit_hi = own_tail ? ((*metas)[s_hi].byte_off + (*metas)[s_hi].byte_len) * 8 : gpos[b_hi - 1] + hb[b_hi - 1].n_bits;
     *byte_lo = bit_lo >> 3; *byte_hi = (bit_hi + 7) >> 3;
     const uint64_t base_bit = *byte_lo * 8;
-    const uint64_t words = (*byte_hi - *byte_lo + 3) / 4 + 4;
-    S3G_TRY(ctx->streams.ensure(words * 4));
-    uint32_t *dst = ctx->streams.as<uint32_t>();
-    S3G_CUDA(cudaMemsetAsync(dst, 0, words * 4, ctx->stream));
     // positions of the own blocks, and the header / trailer words of the streams that begin / end in the share
     std::vector<uint64_t> up;
     up.reserve((b_hi - b_lo) + 8 * (s_hi - s_lo + 1));
     for (uint64_t b = b_lo; b < b_hi; b++) up.push_back(gpos[b] - base_bit);
-    const uint64_t patch_at = up.size();
     uint64_t n_patch = 0;
     for (uint64_t s = s_lo; s <= s_hi; s++) {
         const StreamMeta &m = (*metas)[s];
@@ -280,16 +300,7 @@ int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, u
             n_patch += 3;
         }
     }
-    S3G_TRY(ctx->io_d.ensure(up.size() * 8 + 64));
-    S3G_CUDA(cudaMemcpyAsync(ctx->io_d.p, up.data(), up.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    S3G_CUDA(cudaStreamSynchronize(ctx->stream));                   // `up` is pageable and dies with this frame
-    if ((b_hi - b_lo) > (1ull << 26)) { set_error("too many bzip2 blocks in one call"); return S3G_E_LIMIT; }
-    S3G_LAUNCH(ctx, k_concat_range, (unsigned)((b_hi - b_lo) * 32), 256, 0, ctx->blocks.as<BlockInfo>() + b_lo, ctx->pool.as<uint32_t>(),
-               ctx->pool_woff.as<uint64_t>() + b_lo, ctx->io_d.as<uint64_t>(), dst);
-    if (n_patch)
-        S3G_LAUNCH(ctx, k_patch_words, (unsigned)((n_patch + 127) / 128), 128, 0, ctx->io_d.as<uint64_t>() + patch_at, n_patch, dst);
-    S3G_LAUNCH(ctx, k_bswap, 592, 256, 0, dst, words);
-    return check_launch("assemble range");
+    return run_assemble_items(ctx, b_lo, b_hi, up, n_patch, *byte_hi - *byte_lo);
 }
 
 }  // namespace s3g

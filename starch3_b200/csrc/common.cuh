@@ -137,6 +137,11 @@ struct Ctx {
     std::vector<cudaEvent_t> stage_ev;
     std::vector<cudaEvent_t> part_ev;
     Ctx *sub[2] = {nullptr, nullptr};
+    // chained host entry (one chromosome spans several ranges): transformed bytes of the current step behind the tail the step
+    // before left unfinished (ping-pong), and the compressed bytes of all steps
+    DevBuf chain_tf[2], chain_out;
+    cudaStream_t out_stream = nullptr;     // device-to-host copies of finished bytes beside the next step's kernels
+    cudaEvent_t out_ev = nullptr;
     double mem_frac = 0.85;                // share of the free device memory a batch of blocks may take (worker contexts: less)
     // per-kernel profiling (off by default)
     bool prof = false;
@@ -305,6 +310,9 @@ int run_assemble(Ctx *ctx, uint64_t n_blocks, uint64_t n_streams, int level, uin
 // Leaves bytes [byte_lo, byte_hi) of the global streams buffer in ctx->streams.
 int run_assemble_range(Ctx *ctx, uint64_t n_streams, int level, uint64_t b_lo, uint64_t b_hi, uint64_t *byte_lo, uint64_t *byte_hi,
                        std::vector<StreamMeta> *metas);
+// the common back end: blocks [b_lo, b_hi) at the bit positions items[0 .. b_hi - b_lo), then n_patch (bit position, word)
+// pairs, relative to the first bit of the `nbytes` bytes left in ctx->streams
+int run_assemble_items(Ctx *ctx, uint64_t b_lo, uint64_t b_hi, const std::vector<uint64_t> &items, uint64_t n_patch, uint64_t nbytes);
 // the byte string run_assemble_range left in ctx->streams -> dst[at, at + len) (dst may be a peer GPU's buffer)
 int run_place_bytes(Ctx *ctx, uint8_t *dst, uint64_t at, uint64_t len);
 int compress_block_range(Ctx *ctx, uint64_t b_lo, uint64_t b_hi);

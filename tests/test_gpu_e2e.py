@@ -143,6 +143,7 @@ def test_pipelined_host_entry_matches_one_shot(ctx, oracle, cfg, lines, parts, m
     the one-shot path and as the oracle's, whether a chromosome spans several ranges (cfg 1, 4: all of
     them) or ends inside one."""
     bed = synth.bed(cfg, lines).tobytes()
+    monkeypatch.setenv("S3G_CHAIN", "0")         # the chained entry (one chromosome over several ranges) has its own tests below
     monkeypatch.setenv("S3G_PARTS", "1")
     one = ctx.compress_bed(bed, 9, note="p")
     monkeypatch.setenv("S3G_PARTS", str(parts))
@@ -156,6 +157,7 @@ def test_pipelined_host_entry_matches_one_shot(ctx, oracle, cfg, lines, parts, m
 def test_pipelined_host_entry_on_a_fresh_context(oracle, monkeypatch):
     """The first call a context ever sees is the pipelined one (nothing allocated by earlier stages)."""
     import starch3_b200 as s3
+    monkeypatch.setenv("S3G_CHAIN", "0")
     monkeypatch.setenv("S3G_PARTS", "3")
     bed = synth.bed(2, 50000).tobytes()
     c = s3.Context(0)
@@ -166,6 +168,7 @@ def test_pipelined_host_entry_on_a_fresh_context(oracle, monkeypatch):
 
 
 def test_pipelined_host_entry_edge_inputs(ctx, oracle, monkeypatch):
+    monkeypatch.setenv("S3G_CHAIN", "0")
     monkeypatch.setenv("S3G_PARTS", "3")
     for bed in (b"", b"chr1\t1\t2\n", b"chr1\t1\t2\nchr2\t5\t9\tx\n", b"chr1\t1\t2\nchr1\t5\t9\nchr1\t7\t1",
                 b"chrA\t10\t20\n" * 3 + b"chrB\t1\t2\n" * 2 + b"chrA\t5\t6\n"):
@@ -174,6 +177,79 @@ def test_pipelined_host_entry_edge_inputs(ctx, oracle, monkeypatch):
     monkeypatch.setenv("S3G_PARTS", "2")
     with pytest.raises(Exception):
         ctx.compress_bed(b"chr1\t1\t2\n" * 50 + b"chr1\t5\n" + b"chr2\t1\t2\n" * 50, 9)
+
+
+def _stats(r):
+    return (r.n_lines, r.n_blocks, r.tf_bytes, r.rle_bytes, r.mtf_symbols, r.dropped_tail_bytes, r.unsorted_lines, r.crlf_lines,
+            r.reappearing_chroms,
+            [(c["name"], c["line_count"], c["n_blocks"], c["bz_off"], c["bz_len"], c["tf_off"], c["tf_len"], c["bases_nonunique"], c["bases_unique"])
+             for c in r.chroms])
+
+
+@pytest.mark.parametrize("cfg,lines,rng,level", [(1, 60000, 150_000, 9), (3, 150000, 400_000, 9), (2, 60000, 200_000, 9), (5, 50000, 100_000, 3),
+                                                 (4, 30000, 300_000, 1), (1, 200000, 1_000_000, 1), (3, 400000, 700_000, 1), (2, 30, 100, 9),
+                                                 (2, 40000, 3_000, 2)])
+def test_chained_host_entry_matches_one_shot(ctx, oracle, cfg, lines, rng, level, monkeypatch):
+    """s3g_compress_bed on an input of few chromosomes chains its ranges at bzip2-block granularity (api.cu,
+    compress_bed_chained): a range is transformed behind the unfinished tail of the step before, the blocks whose cut is final
+    are compressed, their bits continue where the step before stopped.  Forced here on small inputs with ranges from a few
+    lines to several blocks: same archive, same statistics as the one-shot path and as the oracle."""
+    bed = synth.bed(cfg, lines).tobytes()
+    monkeypatch.setenv("S3G_PARTS", "1")
+    one = ctx.compress_bed(bed, level, note="c")
+    monkeypatch.setenv("S3G_PARTS", "2")
+    monkeypatch.setenv("S3G_CHAIN", "1")
+    monkeypatch.setenv("S3G_CHAIN_BYTES", str(rng))
+    chained = ctx.compress_bed(bed, level, note="c")
+    assert chained.archive == one.archive
+    assert chained.archive == oracle.archive(bed, level, "c")
+    assert _stats(chained) == _stats(one)
+    assert ctx.read_streams(chained.streams_size) == one.archive[one.streams_off:]
+
+
+def test_chained_host_entry_full_size_blocks_pinned_input(ctx, oracle, monkeypatch):
+    """BASELINE.json config 1 at its size (1 M lines, one chromosome, ten 900k blocks) in three ranges, from pinned memory
+    (the ranges' uploads are queued at once) and from pageable memory (copier threads stage them)"""
+    import torch
+    bed = synth.bed(1, 1000000)
+    monkeypatch.setenv("S3G_PARTS", "1")
+    one = ctx.compress_bed(bed.tobytes(), 9)
+    monkeypatch.setenv("S3G_PARTS", "2")
+    monkeypatch.setenv("S3G_CHAIN", "1")
+    monkeypatch.setenv("S3G_CHAIN_BYTES", str(9 << 20))
+    pinned = torch.from_numpy(bed.copy()).pin_memory()
+    a = ctx.compress_bed(pinned.numpy(), 9)
+    b = ctx.compress_bed(bed.tobytes(), 9)
+    assert a.archive == one.archive == b.archive and a.n_blocks == one.n_blocks >= 9
+    assert a.archive == oracle.archive(bed.tobytes(), 9, "")
+
+
+def test_chained_host_entry_is_chosen_for_one_long_chromosome(ctx, oracle, monkeypatch):
+    """no switch set: an input above the pipelining threshold that is one chromosome goes through the chained entry, one with
+    many chromosomes through the chromosome pipeline; both give the one-shot archive"""
+    monkeypatch.setenv("S3G_PIPE_MIN", str(1 << 20))
+    monkeypatch.setenv("S3G_CHAIN_BYTES", str(1 << 20))
+    for cfg, lines in ((3, 200000), (2, 60000)):
+        bed = synth.bed(cfg, lines).tobytes()
+        assert ctx.compress_bed(bed, 9).archive == oracle.archive(bed, 9, "")
+
+
+def test_chained_host_entry_edge_inputs(ctx, oracle, monkeypatch):
+    monkeypatch.setenv("S3G_PARTS", "2")
+    monkeypatch.setenv("S3G_CHAIN", "1")
+    monkeypatch.setenv("S3G_CHAIN_BYTES", "16")
+    for bed in (b"", b"chr1\t1\t2\n", b"chr1\t1\t2\nchr2\t5\t9\tx\n", b"chr1\t1\t2\nchr1\t5\t9\nchr1\t7\t1",
+                b"chrA\t10\t20\n" * 3 + b"chrB\t1\t2\n" * 2 + b"chrA\t5\t6\n", b"c\t1\t2\n" * 40 + b"d\t3\t9\n" + b"e\t1\t5\tq\n" * 7,
+                b"chr1\t50\t60\nchr1\t10\t20\nchr1\t10\t25\nchr2\t5\t9\r\nchr2\t7\t8\tname\r\nchr1\t1\t2\nchr2\t1\t2\n"):
+        monkeypatch.setenv("S3G_PARTS", "1")
+        one = ctx.compress_bed(bed, 9)
+        monkeypatch.setenv("S3G_PARTS", "2")
+        res = ctx.compress_bed(bed, 9)
+        assert res.archive == oracle.archive(bed, 9, ""), bed
+        assert _stats(res) == _stats(one), bed
+    with pytest.raises(Exception):
+        ctx.compress_bed(b"chr1\t1\t2\n" * 50 + b"chr1\t5\n" + b"chr2\t1\t2\n" * 50, 9)
+    assert ctx.compress_bed(b"chrZ\t0\t1\n", 9).n_lines == 1        # the context is still usable
 
 
 @pytest.mark.parametrize("cfg,lines,rng,piece", [(2, 60000, 200_000, 65536), (5, 60000, 4096, 1000), (1, 60000, 300_000, 7), (2, 30000, 1 << 20, 1 << 22)])
