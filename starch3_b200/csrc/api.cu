@@ -77,6 +77,29 @@ void stage_collect(Ctx *ctx, double *stage_ms)
     ctx->marks.clear();
 }
 
+__global__ void k_fetch_host(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int upload_small(Ctx *ctx, int slot, void *d_dst, const void *h_src, size_t bytes)
+{
+    if (bytes == 0) return S3G_OK;
+    if (bytes & 7) { set_error("upload_small: size must be a multiple of 8"); return S3G_E_PARAM; }
+    if (bytes > ctx->h_small_cap[slot]) {
+        S3G_CUDA(cudaStreamSynchronize(ctx->stream));             // nobody reads the old area any more
+        if (ctx->h_small[slot]) cudaFreeHost(ctx->h_small[slot]);
+        ctx->h_small[slot] = nullptr; ctx->h_small_cap[slot] = 0;
+        const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+        if (cudaMallocHost(&ctx->h_small[slot], want) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+        ctx->h_small_cap[slot] = want;
+    }
+    memcpy(ctx->h_small[slot], h_src, bytes);
+    const uint64_t n = bytes / 8;
+    S3G_LAUNCH(ctx, k_fetch_host, (unsigned)std::min<uint64_t>(64, (n + 255) / 256), 256, 0, ctx->h_small[slot], static_cast<uint64_t *>(d_dst), n);
+    return S3G_OK;
+}
+
 static DevBuf *const *all_bufs(Ctx *c, size_t *n)
 {
     static thread_local DevBuf *list[64];
@@ -303,7 +326,7 @@ static int part_back(Ctx *ctx, const uint8_t *d_bed, uint64_t off, int level, bo
             // chromosome names (a few bytes each) come back through one gather
             S3G_TRY(ctx->io_a.ensure((kept + 1) * 8));
             S3G_TRY(ctx->io_b.ensure(name_off[kept] + 16));
-            S3G_CUDA(cudaMemcpyAsync(ctx->io_a.p, name_off.data(), (kept + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            S3G_TRY(upload_small(ctx, 0, ctx->io_a.p, name_off.data(), (kept + 1) * 8));     // not behind the next range's upload on the copy engine
             S3G_LAUNCH(ctx, k_gather_names, (unsigned)kept, 32, 0, d_bed + base, ctx->chroms.as<s3g_chrom>(), kept,
                        ctx->io_a.as<uint64_t>(), ctx->io_b.as<uint8_t>());
             S3G_CUDA(cudaMemcpyAsync(po.names.data(), ctx->io_b.p, name_off[kept], cudaMemcpyDeviceToHost, ctx->stream));
@@ -752,8 +775,12 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
     std::vector<uint64_t> soff, items;
     std::vector<uint32_t> gidx;                  // step stream -> index into `streams`
 
+    const bool timing = getenv("S3G_TIMING") != nullptr;
+    const double tt0 = timing ? host_ms() : 0;
     auto step = [&](int i) -> int {
         const bool last = i == nparts - 1;
+        const double ts0 = timing ? host_ms() : 0;
+        double ts1 = 0, ts2 = 0, ts3 = 0;
         {
             std::unique_lock<std::mutex> lk(sh.mu);
             sh.cv.wait(lk, [&] { return sh.queued[i] || sh.rc != S3G_OK; });
@@ -764,6 +791,7 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
         const uint64_t lo = cut[i] - halo[i], len = cut[i + 1] - lo;
         s3g_shard_summary sm;
         S3G_TRY(s3g_shard_tokenize(cx, d_bed + lo, len, halo[i], &sm));
+        if (timing) ts1 = host_ms();
         const int64_t carry = sm.continues ? run_max : INT64_MIN;
         if (sm.n_lines) run_max = (sm.single_piece && sm.continues) ? std::max(sm.tail_max, carry) : sm.tail_max;
         res->n_lines += sm.n_lines;
@@ -809,11 +837,16 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
         soff.push_back(n_step);
         // ---- block cut over tail + new bytes; the blocks whose cut is final ----
         uint64_t nb = 0;
+        if (timing) ts2 = host_ms();
         S3G_TRY(s3g_shard_plan(cx, T.p, n_step, soff.data(), ns, level, &nb, nullptr, nullptr, ~0ull));
         const std::vector<BlockInfo> &hb = ctx->h_blocks;
         uint64_t b_fin = nb;
         if (!last) while (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1 && hb[b_fin - 1].in_end + 2 > n_step) b_fin--;
+        if (timing) ts3 = host_ms();
         S3G_TRY(s3g_shard_compress(cx, 0, b_fin, nullptr, nullptr, nullptr));
+        if (timing)
+            fprintf(stderr, "[s3g timing] step %d: starts %.2f ms, range measured +%.2f, transformed +%.2f, plan +%.2f (%llu blocks, %llu final), coded +%.2f\n", i,
+                    ts0 - tt0, ts1 - ts0, ts2 - ts1, ts3 - ts2, (unsigned long long)nb, (unsigned long long)b_fin, host_ms() - ts3);
         // ---- where the step's bits go ----
         items.clear();
         std::vector<uint64_t> patches;
@@ -885,6 +918,7 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
     };
 
     for (int i = 0; rc == S3G_OK && i < nparts; i++) rc = step(i);
+    if (timing) fprintf(stderr, "[s3g timing] last step ends %.2f ms\n", host_ms() - tt0);
     for (std::thread &c : copiers) c.join();
     if (rc != S3G_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->out_stream); cudaStreamSynchronize(ctx->stream); return rc; }
     if (open) { set_error("chained entry: a stream was left open"); return S3G_E_CUDA; }
@@ -894,6 +928,7 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
     float ms = 0;
     S3G_CUDA(cudaEventElapsedTime(&ms, t0, t1));
     res->device_ms = ms;                                       // first upload to last kernel
+    if (timing) fprintf(stderr, "[s3g timing] all bytes on the host %.2f ms\n", host_ms() - tt0);
     // ---- the archive ----
     std::vector<s3g_chrom> chroms;
     std::vector<uint8_t> names;
@@ -1061,6 +1096,7 @@ void s3g_destroy(s3g_ctx *ctx)
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->h_archive) cudaFreeHost(ctx->h_archive);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int k2 = 0; k2 < 2; k2++) if (ctx->h_small[k2]) cudaFreeHost(ctx->h_small[k2]);
     for (cudaEvent_t e : ctx->stage_ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1174,7 +1210,12 @@ int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int level, co
         }
         int rc;
         if (chain) {
-            uint64_t range = 160ull << 20;
+            // Range size: while a range is on its way every launch and read-back of a step is slower (the GPU fetches its commands
+            // over the PCIe direction the upload saturates: a step of 96 MiB takes 2.9 ms beside an upload and 1.65 ms after
+            // it), so a step costs about 2 ms + 10 us per MiB and keeps up with the 19 us per MiB of the upload from about
+            // 224 MiB; larger ranges only lengthen the last step, which nothing hides (measured: 96 MiB 64.5 ms, 160 MiB
+            // 55.3 ms, 224 and 320 MiB 53.1 ms on 2.6 GB).
+            uint64_t range = 256ull << 20;
             if (const char *e = getenv("S3G_CHAIN_BYTES")) { long long v = atoll(e); if (v > 0) range = (uint64_t)v; }
             const int steps = (int)std::min<uint64_t>(256, std::max<uint64_t>(2, (n + range - 1) / range));
             rc = compress_bed_chained(ctx, bed, n, level, note, steps, res);

@@ -235,8 +235,8 @@ int run_assemble_items(Ctx *ctx, uint64_t b_lo, uint64_t b_hi, const std::vector
     if (items.empty()) return S3G_OK;
     const uint64_t patch_at = b_hi - b_lo;
     S3G_TRY(ctx->io_d.ensure(items.size() * 8 + 64));
-    S3G_CUDA(cudaMemcpyAsync(ctx->io_d.p, items.data(), items.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    S3G_CUDA(cudaStreamSynchronize(ctx->stream));                   // `items` is pageable and may die with the caller's frame
+    S3G_TRY(upload_small(ctx, 1, ctx->io_d.p, items.data(), items.size() * 8));   // staged: `items` may die with the caller's frame; the callers
+                                                                                  // synchronise (place / read-back) before the next table
     if ((b_hi - b_lo) > (1ull << 26)) { set_error("too many bzip2 blocks in one call"); return S3G_E_LIMIT; }
     if (b_hi > b_lo)
         S3G_LAUNCH(ctx, k_concat_range, (unsigned)((b_hi - b_lo) * 32), 256, 0, ctx->blocks.as<BlockInfo>() + b_lo, ctx->pool.as<uint32_t>(),

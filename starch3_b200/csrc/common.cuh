@@ -141,6 +141,10 @@ struct Ctx {
     // before left unfinished (ping-pong), and the compressed bytes of all steps
     DevBuf chain_tf[2], chain_out;
     cudaStream_t out_stream = nullptr;     // device-to-host copies of finished bytes beside the next step's kernels
+    // small host tables reach the device through a kernel that reads pinned host memory (upload_small): a cudaMemcpyAsync
+    // would queue on the copy engine behind a range of the input that is on its way (up to 3 ms at 160 MB)
+    uint64_t *h_small[2] = {nullptr, nullptr};
+    size_t h_small_cap[2] = {0, 0};
     cudaEvent_t out_ev = nullptr;
     double mem_frac = 0.85;                // share of the free device memory a batch of blocks may take (worker contexts: less)
     // per-kernel profiling (off by default)
@@ -184,6 +188,9 @@ struct Ctx {
     } while (0)
 
 int check_launch(const char *what);
+// `bytes` (a multiple of 8) of a small host table -> device memory, in stream order, without the copy engine; `slot` (0, 1)
+// names the pinned staging area: a slot must not be reused before the stream has passed the earlier upload
+int upload_small(Ctx *ctx, int slot, void *d_dst, const void *h_src, size_t bytes);
 // stage mark: the time until the next mark is charged to `stage` (s3g_result.stage_ms)
 void stage_mark(Ctx *ctx, int stage);
 void stage_collect(Ctx *ctx, double *stage_ms);

@@ -137,8 +137,7 @@ int s3g_shard_plan(s3g_ctx *ctx, const void *d_tf_all, uint64_t tf_total, const 
     *n_blocks = 0;
     if (n_streams == 0) { ctx->h_blocks.clear(); ctx->rle_blocks = 0; return S3G_OK; }
     S3G_TRY(ctx->soff.ensure((n_streams + 2) * 8));
-    S3G_CUDA(cudaMemcpyAsync(ctx->soff.p, soff, (n_streams + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    S3G_TRY(upload_small(ctx, 0, ctx->soff.p, soff, (n_streams + 1) * 8));     // run_rle_plan synchronises before the slot is used again
     CutResult cut;
     stage_mark(ctx, 1);
     S3G_TRY(run_rle_plan(ctx, static_cast<const uint8_t *>(d_tf_all), tf_total, ctx->soff.as<uint64_t>(), n_streams, level, &cut));
