@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
             }
         }
         __syncthreads();
-        // per digit: exclusive prefix over warps, tile total
+        // per digit: tile total (the exclusive prefix over warps is written further down, with the digit's offset inside the
+        // tile already added: the scatter then reads one table entry per record instead of two)
 #pragma unroll
         for (int q = 0; q < DPT; q++) {
             tot4[q] = 0;
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
                 int d = tid * DPT + q;
                 uint32_t run = 0;
 #pragma unroll
-                for (int ww = 0; ww < SWT / 32; ww++) { uint32_t c = S.wcnt[ww * SWN + d]; S.wcnt[ww * SWN + d] = run; run += c; }
+                for (int ww = 0; ww < SWT / 32; ww++) run += S.wcnt[ww * SWN + d];
                 tot4[q] = run; mysum += run;
             }
         }
@@ -571,6 +572,12 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
             int d = tid * DPT + q;
             S.tbase[d] = ex;
             S.gbase[d] = dbase[d] + ex4[q] - ex;          // (global offset - tile offset) of the digit
+            if (STABLE) {
+                // per warp: where its records of the digit start inside the tile
+                uint32_t run = ex;
+#pragma unroll
+                for (int ww = 0; ww < SWT / 32; ww++) { uint32_t c = S.wcnt[ww * SWN + d]; S.wcnt[ww * SWN + d] = run; run += c; }
+            }
             ex += tot4[q];
         }
     }
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(SWT, SW_OCC) k_sweep(BwtP P, int rshift, const
     for (int r = 0; r < SWI; r++) {
         if (okmask & (1u << r)) {
             uint32_t d = (uint32_t)(kv[r] >> rshift) & (SWN - 1);
-            S.stage[S.tbase[d] + (STABLE ? mycnt[d] : 0u) + rnk[r]] = kv[r];
+            S.stage[(STABLE ? mycnt[d] : S.tbase[d]) + rnk[r]] = kv[r];
         }
     }
     __syncthreads();
