@@ -448,6 +448,7 @@ struct PipeShared {
     uint64_t streams_so_far = 0, archive_cap = 0;
     int rc = S3G_OK;
     std::string err;
+    double t0 = 0;                 // host clock at the start of the call (S3G_TIMING)
 };
 
 static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::vector<uint64_t> &cut, int level,
@@ -483,8 +484,11 @@ static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::v
             sh.cv.wait(lk, [&] { return sh.queued[i] || sh.rc != S3G_OK; });
             if (sh.rc != S3G_OK) return;
         }
+        const bool timing = sh.t0 != 0;
+        const double tf0 = timing ? host_ms() : 0;
         if (cudaStreamWaitEvent(w->stream, main_ctx->part_ev[i], 0) != cudaSuccess) rc = S3G_E_CUDA;
         if (rc == S3G_OK) rc = part_front(w, d_bed, off, cut[i + 1] - off, last, po, tr);
+        const double tf1 = timing ? host_ms() : 0;
         {
             std::unique_lock<std::mutex> lk(sh.mu);
             if (rc != S3G_OK) { sh.rc = rc; sh.err = g_err; sh.cv.notify_all(); return; }
@@ -494,6 +498,9 @@ static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::v
             sh.cv.notify_all();
         }
         rc = part_back(w, d_bed, off, level, true, po);
+        if (timing)
+            fprintf(stderr, "[s3g timing] range %d (worker %d): front %.2f .. %.2f ms, %llu chromosomes, %llu blocks coded by %.2f ms\n", i, wid, tf0 - sh.t0,
+                    tf1 - sh.t0, (unsigned long long)po.chroms.size(), (unsigned long long)po.n_blocks, host_ms() - sh.t0);
         // streams of the ranges go out in order, straight into their place in the pinned archive
         {
             std::unique_lock<std::mutex> lk(sh.mu);
@@ -515,6 +522,7 @@ static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::v
                     return;
                 }
             }
+            if (timing) fprintf(stderr, "[s3g timing] range %d: streams on the host %.2f ms\n", i, host_ms() - sh.t0);
         }
     }
 }
@@ -645,6 +653,7 @@ static int compress_bed_pipelined(Ctx *ctx, const uint8_t *bed, uint64_t n, int 
     std::vector<PartOut> parts(nparts);
     PipeShared sh;
     sh.archive_cap = ctx->h_archive_cap;
+    if (getenv("S3G_TIMING")) sh.t0 = host_ms();
     std::vector<int> left;
     std::vector<std::thread> copiers;
     S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));

@@ -726,7 +726,13 @@ __device__ __forceinline__ uint32_t deeper_key(const uint32_t *k30, uint32_t pos
 // k_finish_mid: one warp per listed group of up to FM_MAX rotations; k_finish_big: one CTA per longer group: up to
 // FB_MAX rotations are ranked in shared memory (level 0 by a bitonic sort, ties level by level), larger ones are
 // written out unsorted (NONHEAD flags) for the doubling rounds.
-constexpr int FA_WARPS = 8;
+#ifndef S3G_FA_OCC
+#define S3G_FA_OCC 4
+#endif
+#ifndef S3G_FA_WARPS
+#define S3G_FA_WARPS 8
+#endif
+constexpr int FA_WARPS = S3G_FA_WARPS;
 constexpr int FA_ROWS = 32;                              // rows a warp walks
 constexpr int FA_TILE = FA_WARPS * FA_ROWS * 32;         // SA positions per CTA
 constexpr int FA_NT = (BLK_STRIDE + FA_TILE - 1) / FA_TILE;
@@ -750,7 +756,7 @@ __device__ __forceinline__ uint32_t fa_group_end(uint32_t e, uint32_t h0, uint32
     return mh ? (uint32_t)__ffs(mh) - 1 : ahead;
 }
 
-__global__ void __launch_bounds__(FA_WARPS * 32, 4) k_finish_rows(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
+__global__ void __launch_bounds__(FA_WARPS * 32, S3G_FA_OCC) k_finish_rows(BwtP P, const uint64_t *kv, unsigned long long *g_left, BlockInfo *blocks,
                                                                   uint8_t *lcol, uint64_t *big_list, uint32_t *big_cnt, uint32_t *unsorted)
 {
     __shared__ FinASmem S;
