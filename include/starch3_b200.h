@@ -50,6 +50,10 @@ S3G_API uint64_t s3g_launch_count(const s3g_ctx *ctx);
 /* Times the block sort had to repeat its radix passes with peer-mask ranking because the keys left by the
  * ordered-atomic ranking were not ascending (bwt.cu, k_sweep).  Expected to stay 0; a diagnostic. */
 S3G_API uint64_t s3g_sort_retries(const s3g_ctx *ctx);
+/* How the last s3g_compress_bed on this context overlapped the upload: 0 = one piece (input below 48 MB, or a fallback),
+ * n > 0 = n ranges by chromosome (two worker contexts), n < 0 = -n ranges chained at bzip2-block granularity (an input of
+ * few chromosomes); DESIGN.md section 5b.  A diagnostic: the archive is the same bytes in every case. */
+S3G_API int s3g_last_host_entry(const s3g_ctx *ctx);
 /* Block-sort diagnostics: out[0] = bzip2 blocks sorted by the bucket form (bwt_bucket.cu) since the context was created,
  * out[1] = batches in which it handed blocks back to the radix form (a sub-bucket of more than 256 equal keys, or a
  * bucket beyond its shared-memory capacity), out[2] = s3g_sort_retries. */

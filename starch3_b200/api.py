@@ -18,7 +18,7 @@ lib_path = os.path.join(HERE, "libstarch3_b200.so")
 S3G_OK, S3G_E_CUDA, S3G_E_PARAM, S3G_E_NOMEM, S3G_E_MALFORMED, S3G_E_CAPACITY, S3G_E_LIMIT = 0, -1, -2, -3, -4, -5, -6
 
 C_ABI_SYMBOLS = [
-    "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
+    "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_last_host_entry", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_stream_begin", "s3g_stream_write", "s3g_stream_end",
     "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_multi_compress_bed", "s3g_stage_times",
@@ -96,6 +96,7 @@ def lib():
         L.s3g_set_stream.argtypes = [vp, vp]
         L.s3g_launch_count.argtypes = [vp]; L.s3g_launch_count.restype = u64
         L.s3g_sort_retries.argtypes = [vp]; L.s3g_sort_retries.restype = u64
+        L.s3g_last_host_entry.argtypes = [vp]; L.s3g_last_host_entry.restype = i32
         L.s3g_sort_stats.argtypes = [vp, vp]
         L.s3g_profile.argtypes = [vp, i32]
         L.s3g_profile_report.argtypes = [vp, C.c_char_p, u64]
@@ -237,6 +238,11 @@ class Context:
     @property
     def launch_count(self):
         return self._lib.s3g_launch_count(self._h)
+
+    @property
+    def last_host_entry(self):
+        """0: one piece; n > 0: n ranges by chromosome; n < 0: -n ranges chained by block (s3g_last_host_entry)"""
+        return self._lib.s3g_last_host_entry(self._h)
 
     @property
     def sort_retries(self):

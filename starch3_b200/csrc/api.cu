@@ -731,6 +731,201 @@ struct ChainStream {
     s3g_chrom c;
 };
 
+// the state that goes from one step to the next, and one step
+struct Chain {
+    Ctx *ctx = nullptr;
+    int level = 9;
+    std::vector<ChainStream> streams;            // the archive's streams, in order; the last one may be open
+    bool open = false;                           // streams.back() has blocks still to come
+    uint64_t open_bits = 0; uint32_t open_comb = 0;   // bits of the open stream so far (its header included), combined CRC so far
+    uint64_t out_bytes = 0;                      // bytes of the closed streams = where the open / next stream starts
+    uint64_t tail_len = 0;                       // unfinished bytes of the open stream at the start of chain_tf[cur]
+    int cur = 0;
+    int64_t run_max = INT64_MIN;                 // largest stop since the last chromosome start (carry_chain of multi.cu)
+    uint64_t tf_room = 4ull << 20;               // transformed bytes a step is expected to add (sizes the other buffer)
+    uint64_t n_lines = 0, n_blocks = 0, rle_bytes = 0, mtf_symbols = 0, tf_bytes = 0, dropped = 0, unsorted = 0, crlf = 0;
+    // where the compressed bytes go.  Either a zeroed device buffer of out_cap bytes (the seam bytes of consecutive steps are
+    // ORed there by k_place_bytes) whose complete bytes are copied to h_out on the context's out_stream beside the next
+    // step's kernels; or a host vector (the seam byte is ORed on the host).
+    uint8_t *d_out = nullptr; uint64_t out_cap = 0; uint8_t *h_out = nullptr; uint64_t copied = 0;
+    std::vector<uint8_t> *v_out = nullptr;
+    std::vector<s3g_chrom> pc = std::vector<s3g_chrom>(256);
+    std::vector<uint64_t> soff, items, patches;
+    std::vector<uint32_t> gidx;                  // step stream -> index into `streams`
+    std::vector<uint8_t> tmp;
+    bool timing = false; double tt0 = 0; int step_no = 0;
+
+    // d_range: the range on the device, its first `halo` bytes the line before it; h_own: host copy of the range's own bytes
+    // (chromosome names are read there); name_base: offset of the range's own bytes in the caller's input (s3g_chrom.name_off)
+    int step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8_t *h_own, uint64_t name_base, bool last);
+    void result(s3g_result *res, std::vector<s3g_chrom> &chroms, std::vector<uint8_t> &names);
+};
+
+int Chain::step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8_t *h_own, uint64_t name_base, bool last)
+{
+    s3g_ctx *cx = static_cast<s3g_ctx *>(ctx);           // the phases of shard.cu take the C handle
+    const double ts0 = timing ? host_ms() : 0;
+    double ts1 = 0, ts2 = 0, ts3 = 0;
+    // ---- tokenise + transform the range behind the tail ----
+    s3g_shard_summary sm;
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    if (timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, ctx->stream); }
+    S3G_TRY(s3g_shard_tokenize(cx, d_range, len, halo, &sm));
+    if (timing) {
+        ts1 = host_ms();
+        cudaEventRecord(eb, ctx->stream); cudaEventSynchronize(eb);
+        float g = 0; cudaEventElapsedTime(&g, ea, eb);
+        fprintf(stderr, "[s3g timing]   tokenizer of %llu bytes (halo %llu): %.2f ms on the device, %.2f ms on the host clock\n", (unsigned long long)len,
+                (unsigned long long)halo, g, ts1 - ts0);
+        cudaEventDestroy(ea); cudaEventDestroy(eb);
+    }
+    const int64_t carry = sm.continues ? run_max : INT64_MIN;
+    if (sm.n_lines) run_max = (sm.single_piece && sm.continues) ? std::max(sm.tail_max, carry) : sm.tail_max;
+    n_lines += sm.n_lines;
+    if (last) dropped = sm.dropped_tail_bytes;
+    DevBuf &T = ctx->chain_tf[cur];
+    S3G_TRY(grow_keep(ctx, T, tail_len + sm.tf_bytes + 256, tail_len));
+    uint64_t np = 0, tl = 0;
+    for (;;) {
+        const uint64_t buf = (uint64_t)(uintptr_t)T.p;
+        int r2 = s3g_shard_transform_peers(cx, carry, pc.data(), pc.size(), &np, &buf, 1, 0, tail_len, &tl);
+        if (r2 == S3G_E_CAPACITY && pc.size() < (1u << 24)) { pc.resize(pc.size() * 16); continue; }
+        S3G_TRY(r2);
+        break;
+    }
+    if (tl != sm.tf_bytes) { set_error("transformed size differs from the measured one"); return S3G_E_CUDA; }
+    if (sm.n_lines) { unsorted += front_unsorted(ctx); crlf += front_crlf(ctx); }
+    tf_bytes += tl;
+    // ---- the step's streams: the tail (+ the piece that continues it), then the range's other chromosomes ----
+    const uint64_t n_step = tail_len + tl;
+    soff.clear(); gidx.clear();
+    if (tail_len) { soff.push_back(0); gidx.push_back((uint32_t)streams.size() - 1); }
+    uint64_t off = tail_len;
+    for (uint64_t q = 0; q < np; q++) {
+        const s3g_chrom &p = pc[q];
+        if (q == 0 && sm.continues && open) {
+            s3g_chrom &c = streams.back().c;
+            c.tf_len += p.tf_len; c.line_count += p.line_count; c.bases_nonunique += p.bases_nonunique; c.bases_unique += p.bases_unique;
+            if (!tail_len) { set_error("chained entry: an open stream without a tail"); return S3G_E_CUDA; }
+        } else {
+            if (p.name_off < halo) { set_error("chained entry: a new chromosome that starts in the halo line"); return S3G_E_CUDA; }
+            ChainStream cs;
+            cs.name.assign(reinterpret_cast<const char *>(h_own + (p.name_off - halo)), p.name_len);
+            memset(&cs.c, 0, sizeof cs.c);
+            cs.c.name_off = name_base + (p.name_off - halo); cs.c.name_len = p.name_len;
+            cs.c.tf_len = p.tf_len; cs.c.line_count = p.line_count; cs.c.bases_nonunique = p.bases_nonunique; cs.c.bases_unique = p.bases_unique;
+            streams.push_back(cs);
+            soff.push_back(off); gidx.push_back((uint32_t)streams.size() - 1);
+        }
+        off += p.tf_len;
+    }
+    if (off != n_step) { set_error("chained entry: piece table and transformed size disagree"); return S3G_E_CUDA; }
+    const uint64_t ns = gidx.size();
+    step_no++;
+    if (ns == 0) return S3G_OK;                              // nothing yet (a range without a complete line)
+    soff.push_back(n_step);
+    // ---- block cut over tail + new bytes; the blocks whose cut is final ----
+    uint64_t nb = 0;
+    if (timing) ts2 = host_ms();
+    S3G_TRY(s3g_shard_plan(cx, T.p, n_step, soff.data(), ns, level, &nb, nullptr, nullptr, ~0ull));
+    const std::vector<BlockInfo> &hb = ctx->h_blocks;
+    uint64_t b_fin = nb;
+    if (!last) while (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1 && hb[b_fin - 1].in_end + 2 > n_step) b_fin--;
+    if (timing) ts3 = host_ms();
+    S3G_TRY(s3g_shard_compress(cx, 0, b_fin, nullptr, nullptr, nullptr));
+    if (timing)
+        fprintf(stderr, "[s3g timing] step %d: starts %.2f ms, range measured +%.2f, transformed +%.2f, plan +%.2f (%llu blocks, %llu final), coded +%.2f\n",
+                step_no - 1, ts0 - tt0, ts1 - ts0, ts2 - ts1, ts3 - ts2, (unsigned long long)nb, (unsigned long long)b_fin, host_ms() - ts3);
+    // ---- where the step's bits go ----
+    items.clear(); patches.clear();
+    uint64_t bit_lo = ~0ull, bit_hi = 0, b = 0;
+    auto mark = [&](uint64_t at, uint64_t nbits) { bit_lo = std::min(bit_lo, at); bit_hi = std::max(bit_hi, at + nbits); };
+    for (uint64_t s = 0; s < ns; s++) {
+        s3g_chrom &c = streams[gidx[s]].c;
+        uint64_t bits; uint32_t comb;
+        if (s == 0 && tail_len) { bits = open_bits; comb = open_comb; }
+        else {
+            c.bz_off = out_bytes; c.tf_off = 0;
+            patches.push_back(out_bytes * 8); patches.push_back(0x425a6800u | (uint32_t)('0' + level));       // bz/compress.c:622-628
+            mark(out_bytes * 8, 32);
+            bits = 32; comb = 0;
+        }
+        bool all_final = true;
+        for (; b < nb && hb[b].chrom == s; b++) {
+            if (b >= b_fin) { all_final = false; continue; }
+            items.push_back(out_bytes * 8 + bits);
+            mark(out_bytes * 8 + bits, hb[b].n_bits);
+            bits += hb[b].n_bits;
+            comb = ((comb << 1) | (comb >> 31)) ^ hb[b].crc;                                                  // :607-608
+            c.n_blocks++;
+            n_blocks++; rle_bytes += hb[b].nblock; mtf_symbols += hb[b].n_mtf;
+        }
+        if (all_final) {
+            const uint64_t end = out_bytes * 8 + bits;                                                        // :657-666
+            patches.push_back(end); patches.push_back(0x17724538u);
+            patches.push_back(end + 32); patches.push_back(0x50900000u | (comb >> 16));
+            patches.push_back(end + 64); patches.push_back((uint64_t)(uint32_t)(comb << 16));
+            mark(end, 80);
+            bits += 80;
+            c.bz_len = (bits + 7) >> 3;
+            out_bytes += c.bz_len;
+            open = false;
+        } else {
+            open = true; open_bits = bits; open_comb = comb;
+        }
+    }
+    if (b != nb) { set_error("chained entry: block table and stream table disagree"); return S3G_E_CUDA; }
+    if (bit_hi > bit_lo) {
+        const uint64_t byte_lo = bit_lo >> 3, byte_hi = (bit_hi + 7) >> 3, nbytes = byte_hi - byte_lo;
+        if (d_out && byte_hi > out_cap) return S3G_E_CAPACITY;               // caller falls back to the one-shot path
+        for (uint64_t &v : items) v -= byte_lo * 8;
+        const uint64_t n_patch = patches.size() / 2;
+        for (uint64_t k = 0; k < patches.size(); k += 2) patches[k] -= byte_lo * 8;
+        items.insert(items.end(), patches.begin(), patches.end());
+        S3G_TRY(run_assemble_items(ctx, 0, b_fin, items, n_patch, nbytes));
+        if (d_out) {
+            S3G_TRY(run_place_bytes(ctx, d_out, byte_lo, nbytes));
+            // the bytes that are complete leave for the host beside the next step's kernels
+            const uint64_t done = last ? out_bytes : (bit_hi >> 3);
+            if (h_out && done > copied) {
+                S3G_CUDA(cudaEventRecord(ctx->out_ev, ctx->stream));
+                S3G_CUDA(cudaStreamWaitEvent(ctx->out_stream, ctx->out_ev, 0));
+                S3G_CUDA(cudaMemcpyAsync(h_out + copied, d_out + copied, done - copied, cudaMemcpyDeviceToHost, ctx->out_stream));
+                copied = done;
+            }
+        } else {
+            // the first byte may be shared with the step before (blocks are not byte aligned): OR it, copy the rest
+            tmp.resize(nbytes);
+            S3G_CUDA(cudaMemcpyAsync(tmp.data(), ctx->streams.p, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+            S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (v_out->size() < byte_hi) v_out->resize(byte_hi, 0);
+            (*v_out)[byte_lo] |= tmp[0];
+            if (nbytes > 1) memcpy(v_out->data() + byte_lo + 1, tmp.data() + 1, nbytes - 1);
+        }
+    }
+    // ---- the tail moves to the front of the other buffer ----
+    if (last) { tail_len = 0; return S3G_OK; }
+    const uint64_t tail_start = (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1) ? hb[b_fin - 1].in_end : soff[ns - 1];
+    const uint64_t new_tail = n_step - tail_start;
+    DevBuf &N = ctx->chain_tf[cur ^ 1];
+    S3G_TRY(N.ensure(new_tail + tf_room));
+    if (new_tail) S3G_CUDA(cudaMemcpyAsync(N.p, static_cast<const uint8_t *>(T.p) + tail_start, new_tail, cudaMemcpyDeviceToDevice, ctx->stream));
+    tail_len = new_tail; cur ^= 1;
+    return S3G_OK;
+}
+
+// statistics and the chromosome table of the finished chain
+void Chain::result(s3g_result *res, std::vector<s3g_chrom> &chroms, std::vector<uint8_t> &names)
+{
+    res->n_lines = n_lines; res->n_blocks = n_blocks; res->rle_bytes = rle_bytes; res->mtf_symbols = mtf_symbols; res->tf_bytes = tf_bytes;
+    res->dropped_tail_bytes = dropped; res->unsorted_lines = unsorted; res->crlf_lines = crlf;
+    chroms.clear(); names.clear();
+    uint64_t t = 0;
+    for (ChainStream &cs : streams) { cs.c.tf_off = t; t += cs.c.tf_len; chroms.push_back(cs.c); names.insert(names.end(), cs.name.begin(), cs.name.end()); }
+    names.push_back(0);
+    res->reappearing_chroms = count_reappearing(chroms, names.data());
+}
+
 static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int level, const char *note, int nparts, s3g_result *res)
 {
     memset(res, 0, sizeof *res);
@@ -770,180 +965,43 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
     S3G_CUDA(cudaEventRecord(t0, ctx->copy_stream));
     int rc = start_upload(ctx, bed, n, cut, nparts, sh, left, copiers);
 
-    std::vector<ChainStream> streams;            // the archive's streams, in order; the last one may be open
-    bool open = false;                           // streams.back() has blocks still to come
-    uint64_t open_bits = 0; uint32_t open_comb = 0;   // bits of the open stream so far (its header included), combined CRC so far
-    uint64_t out_bytes = 0;                      // bytes of the closed streams = where the open / next stream starts
-    uint64_t copied = 0;                         // bytes of chain_out already on their way to the host
-    uint64_t tail_len = 0;                       // unfinished bytes of the open stream at the start of chain_tf[cur]
-    int cur = 0;
-    int64_t run_max = INT64_MIN;                 // largest stop since the last chromosome start (carry_chain of multi.cu)
+    Chain ch;
+    ch.ctx = ctx; ch.level = level; ch.tf_room = range_max + (4ull << 20);
+    ch.d_out = ctx->chain_out.as<uint8_t>(); ch.out_cap = out_cap; ch.h_out = ctx->h_archive + HDR_RESERVE;
+    ch.timing = getenv("S3G_TIMING") != nullptr; ch.tt0 = ch.timing ? host_ms() : 0;
     const uint8_t *d_bed = ctx->bed.as<uint8_t>();
-    s3g_ctx *cx = static_cast<s3g_ctx *>(ctx);           // the phases of shard.cu take the C handle
-    std::vector<s3g_chrom> pc(256);
-    std::vector<uint64_t> soff, items;
-    std::vector<uint32_t> gidx;                  // step stream -> index into `streams`
-
-    const bool timing = getenv("S3G_TIMING") != nullptr;
-    const double tt0 = timing ? host_ms() : 0;
-    auto step = [&](int i) -> int {
-        const bool last = i == nparts - 1;
-        const double ts0 = timing ? host_ms() : 0;
-        double ts1 = 0, ts2 = 0, ts3 = 0;
+    for (int i = 0; rc == S3G_OK && i < nparts;) {
+        // A step takes the next range and every range behind it that has already arrived: when the GPU is the slower side
+        // (cfg4: 21 ms of upload, 69 ms of work) the steps grow by themselves and the batches of blocks fill the GPU; when
+        // the upload is (cfg3) a step is one range.
+        int j = i;
         {
             std::unique_lock<std::mutex> lk(sh.mu);
             sh.cv.wait(lk, [&] { return sh.queued[i] || sh.rc != S3G_OK; });
-            if (sh.rc != S3G_OK) { set_error("%s", sh.err.c_str()); return sh.rc; }
+            if (sh.rc != S3G_OK) { set_error("%s", sh.err.c_str()); rc = sh.rc; break; }
+            while (j + 1 < nparts && sh.queued[j + 1] && cudaEventQuery(ctx->part_ev[j + 1]) == cudaSuccess) j++;
+            cudaGetLastError();                          // cudaErrorNotReady is not an error
         }
-        S3G_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->part_ev[i], 0));
-        // ---- tokenise + transform the range behind the tail ----
-        const uint64_t lo = cut[i] - halo[i], len = cut[i + 1] - lo;
-        s3g_shard_summary sm;
-        S3G_TRY(s3g_shard_tokenize(cx, d_bed + lo, len, halo[i], &sm));
-        if (timing) ts1 = host_ms();
-        const int64_t carry = sm.continues ? run_max : INT64_MIN;
-        if (sm.n_lines) run_max = (sm.single_piece && sm.continues) ? std::max(sm.tail_max, carry) : sm.tail_max;
-        res->n_lines += sm.n_lines;
-        if (last) res->dropped_tail_bytes = sm.dropped_tail_bytes;
-        DevBuf &T = ctx->chain_tf[cur];
-        S3G_TRY(grow_keep(ctx, T, tail_len + sm.tf_bytes + 256, tail_len));
-        uint64_t np = 0, tl = 0;
-        for (;;) {
-            const uint64_t buf = (uint64_t)(uintptr_t)T.p;
-            int r2 = s3g_shard_transform_peers(cx, carry, pc.data(), pc.size(), &np, &buf, 1, 0, tail_len, &tl);
-            if (r2 == S3G_E_CAPACITY && pc.size() < (1u << 24)) { pc.resize(pc.size() * 16); continue; }
-            S3G_TRY(r2);
-            break;
-        }
-        if (tl != sm.tf_bytes) { set_error("transformed size differs from the measured one"); return S3G_E_CUDA; }
-        if (sm.n_lines) { res->unsorted_lines += front_unsorted(ctx); res->crlf_lines += front_crlf(ctx); }
-        res->tf_bytes += tl;
-        // ---- the step's streams: the tail (+ the piece that continues it), then the range's other chromosomes ----
-        const uint64_t n_step = tail_len + tl;
-        soff.clear(); gidx.clear();
-        if (tail_len) { soff.push_back(0); gidx.push_back((uint32_t)streams.size() - 1); }
-        uint64_t off = tail_len;
-        for (uint64_t q = 0; q < np; q++) {
-            const s3g_chrom &p = pc[q];
-            if (q == 0 && sm.continues && open) {
-                s3g_chrom &c = streams.back().c;
-                c.tf_len += p.tf_len; c.line_count += p.line_count; c.bases_nonunique += p.bases_nonunique; c.bases_unique += p.bases_unique;
-                if (!tail_len) { set_error("chained entry: an open stream without a tail"); return S3G_E_CUDA; }
-            } else {
-                ChainStream cs;
-                cs.name.assign(reinterpret_cast<const char *>(bed + lo + p.name_off), p.name_len);
-                memset(&cs.c, 0, sizeof cs.c);
-                cs.c.name_off = lo + p.name_off; cs.c.name_len = p.name_len;
-                cs.c.tf_len = p.tf_len; cs.c.line_count = p.line_count; cs.c.bases_nonunique = p.bases_nonunique; cs.c.bases_unique = p.bases_unique;
-                streams.push_back(cs);
-                soff.push_back(off); gidx.push_back((uint32_t)streams.size() - 1);
-            }
-            off += p.tf_len;
-        }
-        if (off != n_step) { set_error("chained entry: piece table and transformed size disagree"); return S3G_E_CUDA; }
-        const uint64_t ns = gidx.size();
-        if (ns == 0) return S3G_OK;                              // nothing yet (a range without a complete line)
-        soff.push_back(n_step);
-        // ---- block cut over tail + new bytes; the blocks whose cut is final ----
-        uint64_t nb = 0;
-        if (timing) ts2 = host_ms();
-        S3G_TRY(s3g_shard_plan(cx, T.p, n_step, soff.data(), ns, level, &nb, nullptr, nullptr, ~0ull));
-        const std::vector<BlockInfo> &hb = ctx->h_blocks;
-        uint64_t b_fin = nb;
-        if (!last) while (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1 && hb[b_fin - 1].in_end + 2 > n_step) b_fin--;
-        if (timing) ts3 = host_ms();
-        S3G_TRY(s3g_shard_compress(cx, 0, b_fin, nullptr, nullptr, nullptr));
-        if (timing)
-            fprintf(stderr, "[s3g timing] step %d: starts %.2f ms, range measured +%.2f, transformed +%.2f, plan +%.2f (%llu blocks, %llu final), coded +%.2f\n", i,
-                    ts0 - tt0, ts1 - ts0, ts2 - ts1, ts3 - ts2, (unsigned long long)nb, (unsigned long long)b_fin, host_ms() - ts3);
-        // ---- where the step's bits go ----
-        items.clear();
-        std::vector<uint64_t> patches;
-        uint64_t bit_lo = ~0ull, bit_hi = 0, b = 0;
-        auto mark = [&](uint64_t at, uint64_t nbits) { bit_lo = std::min(bit_lo, at); bit_hi = std::max(bit_hi, at + nbits); };
-        for (uint64_t s = 0; s < ns; s++) {
-            s3g_chrom &c = streams[gidx[s]].c;
-            uint64_t bits; uint32_t comb;
-            if (s == 0 && tail_len) { bits = open_bits; comb = open_comb; }
-            else {
-                c.bz_off = out_bytes; c.tf_off = 0;
-                patches.push_back(out_bytes * 8); patches.push_back(0x425a6800u | (uint32_t)('0' + level));       // bz/compress.c:622-628
-                mark(out_bytes * 8, 32);
-                bits = 32; comb = 0;
-            }
-            bool all_final = true;
-            for (; b < nb && hb[b].chrom == s; b++) {
-                if (b >= b_fin) { all_final = false; continue; }
-                items.push_back(out_bytes * 8 + bits);
-                mark(out_bytes * 8 + bits, hb[b].n_bits);
-                bits += hb[b].n_bits;
-                comb = ((comb << 1) | (comb >> 31)) ^ hb[b].crc;                                                  // :607-608
-                c.n_blocks++;
-                res->n_blocks++; res->rle_bytes += hb[b].nblock; res->mtf_symbols += hb[b].n_mtf;
-            }
-            if (all_final) {
-                const uint64_t end = out_bytes * 8 + bits;                                                        // :657-666
-                patches.push_back(end); patches.push_back(0x17724538u);
-                patches.push_back(end + 32); patches.push_back(0x50900000u | (comb >> 16));
-                patches.push_back(end + 64); patches.push_back((uint64_t)(uint32_t)(comb << 16));
-                mark(end, 80);
-                bits += 80;
-                c.bz_len = (bits + 7) >> 3;
-                out_bytes += c.bz_len;
-                open = false;
-            } else {
-                open = true; open_bits = bits; open_comb = comb;
-            }
-        }
-        if (b != nb) { set_error("chained entry: block table and stream table disagree"); return S3G_E_CUDA; }
-        if (bit_hi > bit_lo) {
-            const uint64_t byte_lo = bit_lo >> 3, byte_hi = (bit_hi + 7) >> 3;
-            if (byte_hi > out_cap) return S3G_E_CAPACITY;                        // caller falls back to the one-shot path
-            for (uint64_t &v : items) v -= byte_lo * 8;
-            const uint64_t n_patch = patches.size() / 2;
-            for (uint64_t k = 0; k < patches.size(); k += 2) patches[k] -= byte_lo * 8;
-            items.insert(items.end(), patches.begin(), patches.end());
-            S3G_TRY(run_assemble_items(ctx, 0, b_fin, items, n_patch, byte_hi - byte_lo));
-            S3G_TRY(run_place_bytes(ctx, ctx->chain_out.as<uint8_t>(), byte_lo, byte_hi - byte_lo));
-            // the bytes that are complete leave for the host beside the next step's kernels
-            const uint64_t done = last ? out_bytes : (bit_hi >> 3);
-            if (done > copied) {
-                S3G_CUDA(cudaEventRecord(ctx->out_ev, ctx->stream));
-                S3G_CUDA(cudaStreamWaitEvent(ctx->out_stream, ctx->out_ev, 0));
-                S3G_CUDA(cudaMemcpyAsync(ctx->h_archive + HDR_RESERVE + copied, ctx->chain_out.as<uint8_t>() + copied, done - copied,
-                                         cudaMemcpyDeviceToHost, ctx->out_stream));
-                copied = done;
-            }
-        }
-        // ---- the tail moves to the front of the other buffer ----
-        if (last) { tail_len = 0; return S3G_OK; }
-        const uint64_t tail_start = (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1) ? hb[b_fin - 1].in_end : soff[ns - 1];
-        const uint64_t new_tail = n_step - tail_start;
-        DevBuf &N = ctx->chain_tf[cur ^ 1];
-        S3G_TRY(N.ensure(new_tail + range_max + (4ull << 20)));
-        if (new_tail) S3G_CUDA(cudaMemcpyAsync(N.p, static_cast<const uint8_t *>(T.p) + tail_start, new_tail, cudaMemcpyDeviceToDevice, ctx->stream));
-        tail_len = new_tail; cur ^= 1;
-        return S3G_OK;
-    };
-
-    for (int i = 0; rc == S3G_OK && i < nparts; i++) rc = step(i);
-    if (timing) fprintf(stderr, "[s3g timing] last step ends %.2f ms\n", host_ms() - tt0);
+        if (cudaStreamWaitEvent(ctx->stream, ctx->part_ev[j], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = S3G_E_CUDA; break; }
+        const uint64_t lo = cut[i] - halo[i];
+        rc = ch.step(d_bed + lo, cut[j + 1] - lo, halo[i], bed + cut[i], cut[i], j == nparts - 1);
+        i = j + 1;
+    }
+    if (ch.timing) fprintf(stderr, "[s3g timing] last step ends %.2f ms\n", host_ms() - ch.tt0);
     for (std::thread &c : copiers) c.join();
     if (rc != S3G_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->out_stream); cudaStreamSynchronize(ctx->stream); return rc; }
-    if (open) { set_error("chained entry: a stream was left open"); return S3G_E_CUDA; }
+    if (ch.open) { set_error("chained entry: a stream was left open"); return S3G_E_CUDA; }
     S3G_CUDA(cudaEventRecord(t1, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->out_stream));
     S3G_CUDA(cudaEventSynchronize(t1));
     float ms = 0;
     S3G_CUDA(cudaEventElapsedTime(&ms, t0, t1));
-    res->device_ms = ms;                                       // first upload to last kernel
-    if (timing) fprintf(stderr, "[s3g timing] all bytes on the host %.2f ms\n", host_ms() - tt0);
+    if (ch.timing) fprintf(stderr, "[s3g timing] all bytes on the host %.2f ms\n", host_ms() - ch.tt0);
     // ---- the archive ----
     std::vector<s3g_chrom> chroms;
     std::vector<uint8_t> names;
-    { uint64_t t = 0; for (ChainStream &cs : streams) { cs.c.tf_off = t; t += cs.c.tf_len; chroms.push_back(cs.c); names.insert(names.end(), cs.name.begin(), cs.name.end()); } }
-    names.push_back(0);
-    res->reappearing_chroms = count_reappearing(chroms, names.data());
+    ch.result(res, chroms, names);
+    res->device_ms = ms;                                       // first upload to last kernel
     ctx->h_chroms = chroms;
     fill_result(res, chroms);
     if (!res->chroms) { set_error("out of host memory"); return S3G_E_NOMEM; }
@@ -959,31 +1017,33 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
     arc[4 + hdr.size()] = '\n';
     res->archive = arc;
     res->streams_off = streams_off;
-    res->streams_size = out_bytes;
-    res->archive_size = streams_off + out_bytes;
+    res->streams_size = ch.out_bytes;
+    res->archive_size = streams_off + ch.out_bytes;
     res->d_streams = ctx->chain_out.p;
-    ctx->last_streams_size = out_bytes;
+    ctx->last_streams_size = ch.out_bytes;
     ctx->last_streams_host = ctx->h_archive + HDR_RESERVE;
-    ctx->archive_hint = out_bytes;
+    ctx->archive_hint = ch.out_bytes;
     return S3G_OK;
 }
 
 // ---- bounded-memory ingestion ---------------------------------------------------------------
 // s3g_stream_begin / _write / _end take the input in pieces of any size.  Bytes collect in a pinned staging buffer of
-// `range_bytes`; a full buffer is cut at its last line feed, uploaded behind what the device still holds, and
-// compressed like a range of the pipelined entry: the chromosomes that END in it leave as finished bzip2 streams, the
-// chromosome still open stays on the device for the next range.  Resident: one range on the host, the open chromosome
-// plus one range on the device, and the compressed streams so far (host).
+// `range_bytes`; a full buffer is cut at its last line feed, uploaded behind a copy of the line before it (the halo) and
+// goes through one step of the chain above: the bzip2 blocks whose cut is final leave as bits that continue the step
+// before, the unfinished tail of the transformed bytes (less than two blocks) waits on the device.  Resident: one range
+// on the host, one range plus that tail on the device, and the compressed bytes so far (host) -- whatever the size of a
+// chromosome.
 struct StreamState {
-    int level = 9;
     std::string note;
     uint64_t range_bytes = 0;
     uint8_t *h_stage = nullptr; uint64_t stage_fill = 0;
-    DevBuf dev[2]; int cur = 0; uint64_t dev_fill = 0;
-    std::vector<s3g_chrom> chroms; std::vector<uint8_t> names; std::vector<uint8_t> streams;
-    uint64_t n_blocks = 0, rle_bytes = 0, mtf_symbols = 0, dropped = 0, unsorted = 0, crlf = 0, ranges = 0;
+    DevBuf dev;
+    std::vector<uint8_t> halo;                   // the last line of the range before
+    std::vector<uint8_t> streams;
+    Chain chain;
+    uint64_t ranges = 0;
     double device_ms = 0;
-    ~StreamState() { if (h_stage) cudaFreeHost(h_stage); dev[0].release(); dev[1].release(); }
+    ~StreamState() { if (h_stage) cudaFreeHost(h_stage); dev.release(); }
 };
 void stream_state_free(Ctx *ctx) { delete static_cast<StreamState *>(ctx->stream_state); ctx->stream_state = nullptr; }
 
@@ -1000,46 +1060,33 @@ static int grow_keep(Ctx *ctx, DevBuf &b, uint64_t need, uint64_t keep)
     return S3G_OK;
 }
 
-// upload stage[0, take) behind the device's open chromosome and compress what is complete
+// upload stage[0, take) behind the halo line and run one step of the chain
 static int stream_flush(Ctx *ctx, StreamState &S, uint64_t take, bool last)
 {
-    DevBuf &D = S.dev[S.cur];
-    S3G_TRY(grow_keep(ctx, D, S.dev_fill + take + 64, S.dev_fill));
-    if (take) S3G_CUDA(cudaMemcpyAsync(D.as<uint8_t>() + S.dev_fill, S.h_stage, take, cudaMemcpyHostToDevice, ctx->stream));
-    S.dev_fill += take;
-    S3G_CUDA(cudaMemsetAsync(D.as<uint8_t>() + S.dev_fill, 0, 64, ctx->stream));
-    S3G_CUDA(cudaStreamSynchronize(ctx->stream));          // the staging buffer is refilled by the caller
-    if (S.stage_fill > take) memmove(S.h_stage, S.h_stage + take, S.stage_fill - take);
-    S.stage_fill -= take;
-    if (S.dev_fill == 0) return S3G_OK;
-    PartOut po;
-    TfResult tr;
+    const uint64_t halo = S.halo.size();
+    if (take == 0 && !last) return S3G_OK;
+    if (take == 0 && S.ranges == 0) return S3G_OK;          // an empty input: no step at all
+    S3G_TRY(S.dev.ensure(halo + take + 64));
+    uint8_t *d = S.dev.as<uint8_t>();
+    if (halo) S3G_CUDA(cudaMemcpyAsync(d, S.halo.data(), halo, cudaMemcpyHostToDevice, ctx->stream));
+    if (take) S3G_CUDA(cudaMemcpyAsync(d + halo, S.h_stage, take, cudaMemcpyHostToDevice, ctx->stream));
+    S3G_CUDA(cudaMemsetAsync(d + halo + take, 0, 64, ctx->stream));
     S3G_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    S3G_TRY(part_front(ctx, D.as<uint8_t>(), 0, S.dev_fill, last, po, tr));
-    S3G_TRY(part_back(ctx, D.as<uint8_t>(), 0, S.level, true, po));
+    S.chain.tf_room = S.range_bytes + (4ull << 20);
+    S3G_TRY(S.chain.step(d, halo + take, halo, S.h_stage, 0, last));
+    S3G_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));          // the staging buffer is refilled by the caller
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) S.device_ms += ms; else cudaGetLastError();
     S.ranges++;
-    const uint64_t at = S.streams.size();
-    for (s3g_chrom &c : po.chroms) { c.bz_off += at; S.chroms.push_back(c); }
-    if (!po.chroms.empty()) S.names.insert(S.names.end(), po.names.begin(), po.names.end() - 1);
-    if (po.streams_size) {
-        S.streams.resize(at + po.streams_size);
-        S3G_CUDA(cudaMemcpyAsync(S.streams.data() + at, ctx->streams.p, po.streams_size, cudaMemcpyDeviceToHost, ctx->stream));
-        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!last && take) {
+        // the next range's halo: this range's last line (a range ends with a line feed)
+        uint64_t q = take - 1;
+        while (q > 0 && S.h_stage[q - 1] != '\n') q--;
+        S.halo.assign(S.h_stage + q, S.h_stage + take);
     }
-    S.n_blocks += po.n_blocks; S.rle_bytes += po.rle_bytes; S.mtf_symbols += po.mtf_symbols; S.unsorted += po.unsorted; S.crlf += po.crlf;
-    if (last) { S.dropped = po.dropped; S.dev_fill = 0; return S3G_OK; }
-    // the open chromosome moves to the front of the other buffer
-    const uint64_t tail = S.dev_fill - po.cs_next;
-    if (po.cs_next) {
-        DevBuf &O = S.dev[S.cur ^ 1];
-        S3G_TRY(O.ensure(tail + S.range_bytes + 64));
-        if (tail) S3G_CUDA(cudaMemcpyAsync(O.p, D.as<uint8_t>() + po.cs_next, tail, cudaMemcpyDeviceToDevice, ctx->stream));
-        S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-        S.cur ^= 1;
-    }
-    S.dev_fill = tail;
+    if (S.stage_fill > take) memmove(S.h_stage, S.h_stage + take, S.stage_fill - take);
+    S.stage_fill -= take;
     return S3G_OK;
 }
 
@@ -1125,6 +1172,7 @@ int s3g_set_stream(s3g_ctx *ctx, void *cuda_stream)
 }
 
 uint64_t s3g_launch_count(const s3g_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int s3g_last_host_entry(const s3g_ctx *ctx) { return ctx ? ctx->last_host_entry : 0; }
 
 uint64_t s3g_sort_retries(const s3g_ctx *ctx)
 {
@@ -1228,10 +1276,15 @@ int s3g_compress_bed(s3g_ctx *ctx, const uint8_t *bed, uint64_t n, int level, co
             if (const char *e = getenv("S3G_CHAIN_BYTES")) { long long v = atoll(e); if (v > 0) range = (uint64_t)v; }
             const int steps = (int)std::min<uint64_t>(256, std::max<uint64_t>(2, (n + range - 1) / range));
             rc = compress_bed_chained(ctx, bed, n, level, note, steps, res);
-        } else rc = compress_bed_pipelined(ctx, bed, n, level, note, nparts, res);
+            ctx->last_host_entry = -steps;
+        } else {
+            rc = compress_bed_pipelined(ctx, bed, n, level, note, nparts, res);
+            ctx->last_host_entry = nparts;
+        }
         if (rc != S3G_E_CAPACITY) return rc;
         s3g_result_free(res);                                  // does not fit the pipelined buffers: one piece
     }
+    ctx->last_host_entry = 0;
     S3G_TRY(stage_in(ctx, ctx->bed, bed, n));
     return compress_bed_impl(ctx, ctx->bed.as<uint8_t>(), n, level, note, 1, res);
 }
@@ -1244,9 +1297,10 @@ int s3g_stream_begin(s3g_ctx *ctx, int level, const char *note, uint64_t range_b
     stream_state_free(ctx);
     StreamState *S = new (std::nothrow) StreamState();
     if (!S) { set_error("out of host memory"); return S3G_E_NOMEM; }
-    S->level = level; S->note = note ? note : "";
+    S->note = note ? note : "";
     S->range_bytes = range_bytes ? std::max<uint64_t>(range_bytes, 4096) : (256ull << 20);
     if (cudaMallocHost(&S->h_stage, S->range_bytes) != cudaSuccess) { cudaGetLastError(); delete S; set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+    S->chain.ctx = ctx; S->chain.level = level; S->chain.v_out = &S->streams;
     ctx->stream_state = S;
     return S3G_OK;
 }
@@ -1262,20 +1316,17 @@ int s3g_stream_write(s3g_ctx *ctx, const uint8_t *bed, uint64_t n)
         memcpy(S->h_stage + S->stage_fill, bed, k);
         S->stage_fill += k; bed += k; n -= k;
         if (S->stage_fill == S->range_bytes) {
-            // cut at the last line feed; a range without one (a line longer than the range) is uploaded whole
+            // cut at the last line feed
             uint64_t take = S->stage_fill;
             while (take && S->h_stage[take - 1] != '\n') take--;
-            const bool whole_lines = take != 0;
-            if (!whole_lines) take = S->stage_fill;
-            if (whole_lines) { int rc = stream_flush(ctx, *S, take, false); if (rc != S3G_OK) { stream_state_free(ctx); return rc; } }
+            if (take) { int rc = stream_flush(ctx, *S, take, false); if (rc != S3G_OK) { stream_state_free(ctx); return rc; } }
             else {
-                // no line ends in this range: park the bytes on the device, nothing to compress yet
-                DevBuf &D = S->dev[S->cur];
-                int rc = grow_keep(ctx, D, S->dev_fill + take + 64, S->dev_fill);
-                if (rc != S3G_OK) { stream_state_free(ctx); return rc; }
-                S3G_CUDA(cudaMemcpyAsync(D.as<uint8_t>() + S->dev_fill, S->h_stage, take, cudaMemcpyHostToDevice, ctx->stream));
-                S3G_CUDA(cudaStreamSynchronize(ctx->stream));
-                S->dev_fill += take; S->stage_fill = 0;
+                // no line ends in this range (a line longer than the range): the range grows to hold it
+                uint8_t *p = nullptr;
+                if (cudaMallocHost(&p, S->range_bytes * 2) != cudaSuccess) { cudaGetLastError(); stream_state_free(ctx); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+                memcpy(p, S->h_stage, S->stage_fill);
+                cudaFreeHost(S->h_stage);
+                S->h_stage = p; S->range_bytes *= 2;
             }
         }
     }
@@ -1290,12 +1341,16 @@ int s3g_stream_end(s3g_ctx *ctx, s3g_result *res)
     S3G_CUDA(cudaSetDevice(ctx->device));
     memset(res, 0, sizeof *res);
     int rc = stream_flush(ctx, *S, S->stage_fill, true);
+    if (rc == S3G_OK && S->chain.open) { set_error("stream entry: a stream was left open"); rc = S3G_E_CUDA; }
     if (rc != S3G_OK) { stream_state_free(ctx); return rc; }
-    { uint64_t t = 0; for (s3g_chrom &c : S->chroms) { c.tf_off = t; t += c.tf_len; c.name_off = 0; } }   // no input buffer to point into
-    S->names.push_back(0);
-    std::vector<uint64_t> name_off(S->chroms.size() + 1, 0);
-    for (size_t c = 0; c < S->chroms.size(); c++) name_off[c + 1] = name_off[c] + S->chroms[c].name_len;
-    std::string hdr = build_header(S->names.data(), name_off, S->chroms, S->level, S->note.c_str());
+    std::vector<s3g_chrom> chroms;
+    std::vector<uint8_t> names;
+    S->chain.result(res, chroms, names);
+    if (S->ranges == 0) res->dropped_tail_bytes = S->stage_fill;          // nothing but an unterminated fragment (or nothing at all)
+    for (s3g_chrom &c : chroms) c.name_off = 0;                           // no input buffer to point into
+    std::vector<uint64_t> name_off(chroms.size() + 1, 0);
+    for (size_t c = 0; c < chroms.size(); c++) name_off[c + 1] = name_off[c] + chroms[c].name_len;
+    std::string hdr = build_header(names.data(), name_off, chroms, S->chain.level, S->note.c_str());
     const uint64_t streams_off = 4 + hdr.size() + 1;
     rc = ensure_archive(ctx, streams_off + S->streams.size());
     if (rc != S3G_OK) { stream_state_free(ctx); return rc; }
@@ -1306,11 +1361,9 @@ int s3g_stream_end(s3g_ctx *ctx, s3g_result *res)
     if (!S->streams.empty()) memcpy(ctx->h_archive + streams_off, S->streams.data(), S->streams.size());
     res->archive = ctx->h_archive; res->archive_size = streams_off + S->streams.size(); res->streams_off = streams_off;
     res->streams_size = S->streams.size(); res->d_streams = nullptr;
-    res->n_blocks = S->n_blocks; res->rle_bytes = S->rle_bytes; res->mtf_symbols = S->mtf_symbols; res->dropped_tail_bytes = S->dropped;
-    res->unsorted_lines = S->unsorted; res->crlf_lines = S->crlf; res->device_ms = S->device_ms;
-    res->reappearing_chroms = count_reappearing(S->chroms, S->names.data());
-    ctx->h_chroms = S->chroms;
-    fill_result(res, S->chroms);
+    res->device_ms = S->device_ms;
+    ctx->h_chroms = chroms;
+    fill_result(res, chroms);
     ctx->last_streams_size = S->streams.size();
     ctx->last_streams_host = ctx->h_archive + streams_off;
     stream_state_free(ctx);

@@ -109,6 +109,7 @@ struct Ctx {
     DevBuf sa, rk, kv0, kv1, hist, bwt_misc, bwt_ghist, lcol;
     size_t sweep_cap = 0;                  // capacity of `hist` when its look-back status words were last cleared
     uint32_t sweep_gen = 0;                // generation tag of the last radix pass (1..255)
+    int last_host_entry = 0;               // s3g_last_host_entry
     uint64_t sort_retries = 0;             // times the radix passes had to be repeated with peer-mask ranking (expected: never)
     DevBuf mtf0, mtfv16, mtf_freq, ztiles, bits, pool, pool_woff, streams, stream_meta;
     DevBuf io_a, io_b, io_c, io_d, io_e;   // staging for the stage entry points

@@ -252,6 +252,38 @@ def test_chained_host_entry_edge_inputs(ctx, oracle, monkeypatch):
     assert ctx.compress_bed(b"chrZ\t0\t1\n", 9).n_lines == 1        # the context is still usable
 
 
+def test_chained_host_entry_random_inputs(ctx, oracle, monkeypatch):
+    """random chromosome lengths, line shapes, levels and range sizes (from less than a line to many blocks): the seams between
+    steps fall on every kind of place -- inside a block, at a block end, at a chromosome change, one byte before the end"""
+    rng = np.random.default_rng(20260119)
+    for case in range(24):
+        level = int(rng.integers(1, 4))
+        n_chr = int(rng.integers(1, 5))
+        lines = []
+        for c in range(n_chr):
+            pos = 0
+            shape = int(rng.integers(0, 3))
+            for _ in range(int(rng.integers(1, 30000))):
+                pos += int(rng.integers(0, 50))
+                ln = int(rng.integers(1, 4)) if shape == 0 else 20 if shape == 1 else int(rng.integers(1, 3000))
+                rest = b"" if shape != 2 else b"\tid-%d\t%d" % (int(rng.integers(0, 10 ** 6)), int(rng.integers(0, 1000)))
+                lines.append(b"c%d\t%d\t%d%s\n" % (c, pos, pos + ln, rest))
+                pos += ln
+        bed = b"".join(lines)
+        if case % 5 == 4:
+            bed = bed[:-1]                       # unterminated last line: dropped and reported
+        monkeypatch.setenv("S3G_PARTS", "1")
+        one = ctx.compress_bed(bed, level)
+        monkeypatch.setenv("S3G_PARTS", "2")
+        monkeypatch.setenv("S3G_CHAIN", "1")
+        monkeypatch.setenv("S3G_CHAIN_BYTES", str(int(rng.choice([20, 333, 5000, 70_000, 250_000, 1_000_000]))))
+        res = ctx.compress_bed(bed, level)
+        assert res.archive == one.archive, case
+        assert _stats(res) == _stats(one), case
+        monkeypatch.delenv("S3G_CHAIN"); monkeypatch.delenv("S3G_CHAIN_BYTES")
+    assert one.archive == oracle.archive(bed, level, "")
+
+
 @pytest.mark.parametrize("cfg,lines,rng,piece", [(2, 60000, 200_000, 65536), (5, 60000, 4096, 1000), (1, 60000, 300_000, 7), (2, 30000, 1 << 20, 1 << 22)])
 def test_bounded_memory_ingestion(ctx, oracle, cfg, lines, rng, piece):
     """s3g_stream_*: the input arrives in pieces, at most one range of it is resident beside the open chromosome; ranges
