@@ -537,6 +537,36 @@ static unsigned cluster_size(uint64_t nb, uint64_t slots)
     return cs;
 }
 
+// A launch with one CTA per block runs in waves of `W` CTAs (W = resident CTAs of the kernel on the GPU); a batch of
+// 300 blocks over W = 296 would hold the GPU for two waves, the second one nearly empty, and a batch of 178 for a whole wave
+// at 60 % of the slots.  So a batch is cut into chunks: whole waves of one CTA per block, then the remainder as clusters of
+// 2, 4 and 8 CTAs per block -- a chunk of m blocks with c CTAs each (c m <= W) takes about 1 / c of a wave.
+// plan: (first block of the chunk relative to the batch, blocks, CTAs per block); single = the batch as ONE launch with the
+// largest cluster size that fits (the form the tests force with S3G_CLUSTER / S3G_ZRUN).
+struct Chunk { uint64_t s0, n; unsigned cs; };
+static void plan_chunks(uint64_t nb, uint64_t W, bool single, std::vector<Chunk> &out)
+{
+    out.clear();
+    if (single) { out.push_back({0, nb, nb > W / 2 ? 1u : cluster_size(nb, W)}); return; }
+    uint64_t s = 0;
+    if (nb >= W) { const uint64_t m = nb / W * W; out.push_back({0, m, 1}); s = m; }
+    uint64_t rem = nb - s;
+    // what one launch would take against the chunks below (a cluster costs about a fifth more per block)
+    if (rem == 0) return;
+    const unsigned c1 = rem > W / 2 ? 1u : cluster_size(rem, W);
+    const double one = (c1 > 1 ? 1.2 : 1.0) / c1;
+    std::vector<Chunk> cut;
+    double t = 0;
+    uint64_t r = rem, at = s;
+    for (unsigned c = 2; c <= 8 && r; c *= 2) {
+        const uint64_t cap = W / c;
+        if (r >= cap) { cut.push_back({at, cap, c}); at += cap; r -= cap; t += 1.2 / c; }
+    }
+    if (r) { cut.push_back({at, r, 8}); t += 1.2 / 8; }
+    if (t < 0.85 * one) out.insert(out.end(), cut.begin(), cut.end());
+    else out.push_back({s, rem, c1});
+}
+
 int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
 {
     if (nb == 0) return S3G_OK;
@@ -544,53 +574,59 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
     S3G_TRY(ctx->mtf0.ensure(slots));                 // MTF ranks before zero-run coding
     S3G_TRY(ctx->mtfv16.ensure(slots * 2));
     S3G_TRY(ctx->mtf_freq.ensure((size_t)nb * 258 * 4));
-    // alphabets of <= MTF_REG_MAX symbols take the register-list kernel, larger ones the warp-cooperative one
-    double N = 0;
-    int rows = 1;
-    for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) {
-        N += ctx->h_blocks[b0 + b].nblock;
-        int a = (int)ctx->h_blocks[b0 + b].n_in_use;
-        if (a <= MTF_REG_MAX && a > rows) rows = a;
-        if (a == 0) rows = MTF_REG_MAX;                        // alphabet not mirrored on the host: size for the worst case
-    }
-    if (ctx->h_blocks.size() < b0 + nb) rows = MTF_REG_MAX;
-    bool any_small = false, any_big = false;                   // which forms of the register-list kernel this batch needs
-    for (uint64_t b = 0; b < nb; b++) {
-        int a = b0 + b < ctx->h_blocks.size() ? (int)ctx->h_blocks[b0 + b].n_in_use : 0;
-        if (a == 0) any_small = any_big = true;
-        else if (a <= 24) any_small = true;
-        else if (a <= MTF_REG_MAX) any_big = true;
-    }
-    const size_t tail_smem = 260 * 4 + 40 * 4 + 256 * 4;
-    // zero-run coding inside the MTF kernels (one CTA per block) when the batch fills the SMs, as tile-parallel kernels of
-    // its own when it does not (S3G_ZRUN=fused|split overrides: both forms are tested)
-    int fused = nb > (uint64_t)SM_COUNT ? 1 : 0;             // up to one block per SM: clusters of 2 or more CTAs per block
-    if (const char *e = getenv("S3G_ZRUN")) fused = !strcmp(e, "split") ? 0 : !strcmp(e, "fused") ? 1 : fused;
+    S3G_TRY(ctx->ztiles.ensure((size_t)nb * ZNT * sizeof(ZTileInfo)));
     if (!ctx->attr_mtf) {
-        S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)24 * MS_SMALL * 4 + tail_smem)));
-        S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MTF_REG_MAX * MS_BIG * 4 + tail_smem)));
+        const size_t tail_smem0 = 260 * 4 + 40 * 4 + 256 * 4;
+        S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)24 * MS_SMALL * 4 + tail_smem0)));
+        S3G_CUDA(cudaFuncSetAttribute(k_mtf_list_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)MTF_REG_MAX * MS_BIG * 4 + tail_smem0)));
         ctx->attr_mtf = true;
     }
-    S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
-    // a batch that leaves SMs idle spreads every block over a cluster of cs CTAs (cs * nb <= two CTAs per SM)
-    const unsigned cs = fused ? 1u : cluster_size(nb, 2 * SM_COUNT);
-    if (any_small)
-        S3G_LAUNCH_CLUSTER(ctx, k_mtf_list_small, dim3(cs, (unsigned)nb), MS_SMALL, (size_t)std::min(rows, 24) * MS_SMALL * 4 + tail_smem, cs, ctx->lcol.as<uint8_t>(),
-                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, std::min(rows, 24), fused);
-    if (any_big)
-        S3G_LAUNCH_CLUSTER(ctx, k_mtf_list_big, dim3(cs, (unsigned)nb), MS_BIG, (size_t)rows * MS_BIG * 4 + tail_smem, cs, ctx->lcol.as<uint8_t>(),
-                   ctx->mtf0.as<uint8_t>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, rows, fused);
-    S3G_LAUNCH(ctx, k_mtf, (unsigned)nb, MT, 0, ctx->lcol.as<uint8_t>(), ctx->mtf0.as<uint8_t>(),
-               ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(), ctx->blocks.as<BlockInfo>() + b0, fused);
-    if (!fused) {
-        // zero-run coding, tile-parallel over the ranks
-        S3G_TRY(ctx->ztiles.ensure((size_t)nb * ZNT * sizeof(ZTileInfo)));
-        S3G_CUDA(cudaMemsetAsync(ctx->mtf_freq.p, 0, (size_t)nb * 258 * 4, ctx->stream));
-        S3G_LAUNCH(ctx, k_zrun_tiles, dim3(ZNT, (unsigned)nb), ZT, 0, ctx->mtf0.as<uint8_t>(), ctx->blocks.as<BlockInfo>() + b0, ctx->ztiles.as<ZTileInfo>());
-        S3G_LAUNCH(ctx, k_zrun_offsets, (unsigned)nb, 256, 0, ctx->ztiles.as<ZTileInfo>(), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
-                   ctx->blocks.as<BlockInfo>() + b0);
-        S3G_LAUNCH(ctx, k_zrun_emit, dim3(ZNT, (unsigned)nb), ZT, 0, ctx->mtf0.as<uint8_t>(), ctx->blocks.as<BlockInfo>() + b0, ctx->ztiles.as<ZTileInfo>(),
-                   ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>());
+    // zero-run coding inside the MTF kernels (one CTA per block) for the chunks of whole waves, as tile-parallel kernels of
+    // its own for the chunks that spread a block over a cluster (S3G_ZRUN=fused|split, S3G_CLUSTER=n: one launch in the
+    // form asked for -- the tests run every form)
+    const char *ez = getenv("S3G_ZRUN");
+    const bool forced = ez || getenv("S3G_CLUSTER");
+    std::vector<Chunk> chunks;
+    plan_chunks(nb, 2 * SM_COUNT, forced, chunks);
+    for (const Chunk &ck : chunks) {
+        const uint64_t s0 = ck.s0, n = ck.n;
+        // alphabets of <= MTF_REG_MAX symbols take the register-list kernel, larger ones the warp-cooperative one
+        double N = 0;
+        int rows = 1;
+        bool any_small = false, any_big = false;                   // which forms of the register-list kernel this chunk needs
+        for (uint64_t b = s0; b < s0 + n; b++) {
+            int a = b0 + b < ctx->h_blocks.size() ? (int)ctx->h_blocks[b0 + b].n_in_use : 0;
+            if (b0 + b < ctx->h_blocks.size()) N += ctx->h_blocks[b0 + b].nblock;
+            if (a <= MTF_REG_MAX && a > rows) rows = a;
+            if (a == 0) { rows = MTF_REG_MAX; any_small = any_big = true; }     // alphabet not mirrored on the host: size for the worst case
+            else if (a <= 24) any_small = true;
+            else if (a <= MTF_REG_MAX) any_big = true;
+        }
+        const size_t tail_smem = 260 * 4 + 40 * 4 + 256 * 4;
+        int fused = ck.cs == 1 && n > (uint64_t)SM_COUNT ? 1 : 0;
+        if (ez) fused = !strcmp(ez, "split") ? 0 : !strcmp(ez, "fused") ? 1 : fused;
+        const unsigned cs = fused ? 1u : (forced ? cluster_size(n, 2 * SM_COUNT) : ck.cs);
+        const uint8_t *lcol = ctx->lcol.as<uint8_t>() + s0 * BLK_STRIDE;
+        uint8_t *mtf0 = ctx->mtf0.as<uint8_t>() + s0 * BLK_STRIDE;
+        uint16_t *mtfv = ctx->mtfv16.as<uint16_t>() + s0 * BLK_STRIDE;
+        int32_t *freq = ctx->mtf_freq.as<int32_t>() + s0 * 258;
+        BlockInfo *blocks = ctx->blocks.as<BlockInfo>() + b0 + s0;
+        S3G_BYTES(ctx, 3 * N + 2 * 0.67 * N);            // L in, ranks out and in, uint16 symbols out (~0.67 per byte)
+        if (any_small)
+            S3G_LAUNCH_CLUSTER(ctx, k_mtf_list_small, dim3(cs, (unsigned)n), MS_SMALL, (size_t)std::min(rows, 24) * MS_SMALL * 4 + tail_smem, cs, lcol,
+                       mtf0, mtfv, freq, blocks, std::min(rows, 24), fused);
+        if (any_big)
+            S3G_LAUNCH_CLUSTER(ctx, k_mtf_list_big, dim3(cs, (unsigned)n), MS_BIG, (size_t)rows * MS_BIG * 4 + tail_smem, cs, lcol,
+                       mtf0, mtfv, freq, blocks, rows, fused);
+        S3G_LAUNCH(ctx, k_mtf, (unsigned)n, MT, 0, lcol, mtf0, mtfv, freq, blocks, fused);
+        if (!fused) {
+            // zero-run coding, tile-parallel over the ranks
+            ZTileInfo *zt = ctx->ztiles.as<ZTileInfo>() + s0 * ZNT;
+            S3G_CUDA(cudaMemsetAsync(freq, 0, (size_t)n * 258 * 4, ctx->stream));
+            S3G_LAUNCH(ctx, k_zrun_tiles, dim3(ZNT, (unsigned)n), ZT, 0, mtf0, blocks, zt);
+            S3G_LAUNCH(ctx, k_zrun_offsets, (unsigned)n, 256, 0, zt, mtfv, freq, blocks);
+            S3G_LAUNCH(ctx, k_zrun_emit, dim3(ZNT, (unsigned)n), ZT, 0, mtf0, blocks, zt, mtfv, freq);
+        }
     }
     return check_launch("mtf");
 }
@@ -998,19 +1034,39 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
         S3G_CUDA(cudaFuncSetAttribute(k_huff<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
         ctx->attr_huff = true;
     }
-    double N = 0;
-    for (uint64_t b = 0; b < nb && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
-    S3G_BYTES(ctx, 6 * 2 * 0.67 * N + 0.25 * N);      // 4 selection passes + size + emit over uint16 symbols, bits out
-    if (nb > (uint64_t)SM_COUNT)
-        S3G_LAUNCH(ctx, k_huff<512>, dim3(1, (unsigned)nb), 512, sizeof(HuffSmem), ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
-                   ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
-                   d_sel_out, d_len_out, with_block_header);
+    // chunks as in run_mtf: whole waves of two 512-thread CTAs per SM, then the remainder with one 1024-thread CTA per SM,
+    // a block spread over a cluster of 1, 2, 4 or 8 of them
+    const bool forced = getenv("S3G_CLUSTER") != nullptr;
+    std::vector<Chunk> chunks;
+    if (forced || nb <= (uint64_t)SM_COUNT) chunks.push_back({0, nb, nb > (uint64_t)SM_COUNT ? 0u : cluster_size(nb, SM_COUNT)});
     else {
-        // fewer blocks than SMs: every block over a cluster of cs CTAs (one CTA of 1024 threads per SM)
-        const unsigned cs = cluster_size(nb, SM_COUNT);
-        S3G_LAUNCH_CLUSTER(ctx, k_huff<1024>, dim3(cs, (unsigned)nb), 1024, sizeof(HuffSmem), cs, ctx->mtfv16.as<uint16_t>(), ctx->mtf_freq.as<int32_t>(),
-                   ctx->in_use.as<uint8_t>() + b0 * 256, ctx->blocks.as<BlockInfo>() + b0, ctx->bits.as<uint32_t>(),
-                   d_sel_out, d_len_out, with_block_header);
+        const uint64_t W = 2 * SM_COUNT;
+        uint64_t s = nb / W * W;
+        if (s) chunks.push_back({0, s, 0});                    // cs 0: the 512-thread form
+        const uint64_t rem = nb - s;
+        if (rem > W * 3 / 4) chunks.push_back({s, rem, 0});                  // nearly a wave: as it is
+        else if (rem) {
+            std::vector<Chunk> tail;
+            plan_chunks(rem, SM_COUNT, false, tail);                          // one 1024-thread CTA per SM: waves of 148
+            for (Chunk &t : tail) { t.s0 += s; chunks.push_back(t); }
+        }
+    }
+    for (const Chunk &ck : chunks) {
+        const uint64_t s0 = ck.s0, n = ck.n;
+        double N = 0;
+        for (uint64_t b = s0; b < s0 + n && b0 + b < ctx->h_blocks.size(); b++) N += ctx->h_blocks[b0 + b].nblock;
+        S3G_BYTES(ctx, 6 * 2 * 0.67 * N + 0.25 * N);      // 4 selection passes + size + emit over uint16 symbols, bits out
+        const uint16_t *mtfv = ctx->mtfv16.as<uint16_t>() + s0 * BLK_STRIDE;
+        const int32_t *freq = ctx->mtf_freq.as<int32_t>() + s0 * 258;
+        const uint8_t *in_use = ctx->in_use.as<uint8_t>() + (b0 + s0) * 256;
+        BlockInfo *blocks = ctx->blocks.as<BlockInfo>() + b0 + s0;
+        uint32_t *bits = ctx->bits.as<uint32_t>() + s0 * BITS_WORDS;
+        uint8_t *sel = d_sel_out ? d_sel_out + s0 * (MAX_SEL + 2) : nullptr, *len = d_len_out ? d_len_out + s0 * 6 * ALPHA_MAX : nullptr;
+        if (ck.cs == 0)
+            S3G_LAUNCH(ctx, k_huff<512>, dim3(1, (unsigned)n), 512, sizeof(HuffSmem), mtfv, freq, in_use, blocks, bits, sel, len, with_block_header);
+        else        // one CTA of 1024 threads per SM, every block over a cluster of cs CTAs
+            S3G_LAUNCH_CLUSTER(ctx, k_huff<1024>, dim3(ck.cs, (unsigned)n), 1024, sizeof(HuffSmem), ck.cs, mtfv, freq, in_use, blocks, bits, sel, len,
+                               with_block_header);
     }
     return check_launch("huff");
 }

@@ -146,3 +146,27 @@ def test_decoder_roundtrip_at_size(ctx, cfg, lines):
     got, info = ctx.decompress_archive(arc)
     assert info["n_blocks"] == n_blocks
     assert len(got) == bed.nbytes and np.array_equal(np.frombuffer(got, dtype=np.uint8), bed)
+
+
+@pytest.mark.parametrize("batch", [75, 178, 230, 300, 450, 0])
+def test_batches_that_leave_partial_waves(ctx, oracle, batch, monkeypatch):
+    """MTF and Huffman cut a batch into whole waves of one CTA per block plus a remainder spread over clusters of 2, 4 and 8
+    CTAs per block (mtf_huff.cu, plan_chunks).  700 small streams and a few multi-block ones, in batches whose sizes leave every
+    kind of remainder (0 = one batch of all blocks)."""
+    monkeypatch.setenv("S3G_PARTS", "1")
+    if batch:
+        monkeypatch.setenv("S3G_BATCH", str(batch))
+    rng = np.random.default_rng(11)
+    lines = []
+    for c in range(700):
+        pos = 0
+        n = 30000 if c % 97 == 5 else int(rng.integers(1, 40))
+        for _ in range(n):
+            pos += int(rng.integers(1, 1000))
+            ln = int(rng.integers(1, 400))
+            lines.append(b"ctg%04d\t%d\t%d\tf%d\n" % (c, pos, pos + ln, int(rng.integers(0, 99))))
+            pos += ln
+    bed = b"".join(lines)
+    res = ctx.compress_bed(bed, 1, note="w")
+    assert res.n_blocks > 720
+    _same(res.archive, oracle.archive_mt(bed, 1, "w"))
