@@ -529,9 +529,14 @@ static void pipe_worker(Ctx *main_ctx, Ctx *w, int wid, int nparts, const std::v
 
 // Pageable input (the CLI reads files into malloc'd memory): cudaMemcpyAsync from it is synchronous and staged by the
 // driver at a third of the link's speed, and it would hold up the calling thread while the workers wait.  Instead
-// STAGE_THREADS copier threads move the input through pinned pieces of their own (two each, so a thread copies one
+// stage_threads() copier threads (8; S3G_STAGE_THREADS) move the input through pinned pieces of their own (two each, so a thread copies one
 // while the other is on its way to the device); the thread that queues the last piece of a range records the range's event.
-constexpr int STAGE_THREADS = 4;
+constexpr int STAGE_THREADS_MAX = 16;
+static int stage_threads()
+{
+    static const int n = [] { int v = 8; if (const char *e = getenv("S3G_STAGE_THREADS")) v = atoi(e); return std::max(1, std::min(STAGE_THREADS_MAX, v)); }();
+    return n;
+}
 constexpr uint64_t STAGE_PIECE = 8ull << 20;
 static void stage_copier(Ctx *ctx, int tid, const uint8_t *bed, uint64_t n, const std::vector<uint64_t> &cut, int nparts,
                          std::vector<int> &left, PipeShared &sh)
@@ -545,7 +550,7 @@ static void stage_copier(Ctx *ctx, int tid, const uint8_t *bed, uint64_t n, cons
     for (int i = 0; i < nparts; i++) {
         for (uint64_t off = cut[i]; off < cut[i + 1] || (off == cut[i] && cut[i] == cut[i + 1]); off += STAGE_PIECE, piece++) {
             const uint64_t len = std::min<uint64_t>(STAGE_PIECE, cut[i + 1] - off);
-            if ((int)(piece % STAGE_THREADS) == tid) {
+            if ((int)(piece % stage_threads()) == tid) {
                 bool ok = true;
                 if (len) {
                     if (used[k]) ok = cudaEventSynchronize(ev[k]) == cudaSuccess;
@@ -595,15 +600,15 @@ static int start_upload(Ctx *ctx, const uint8_t *bed, uint64_t n, const std::vec
         }
     } else {
         if (!ctx->h_stage) {
-            if (cudaMallocHost(&ctx->h_stage, 2ull * STAGE_THREADS * STAGE_PIECE) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
-            for (int q = 0; q < 2 * STAGE_THREADS; q++) {
+            if (cudaMallocHost(&ctx->h_stage, 2ull * STAGE_THREADS_MAX * STAGE_PIECE) != cudaSuccess) { cudaGetLastError(); set_error("out of pinned host memory"); return S3G_E_NOMEM; }
+            for (int q = 0; q < 2 * STAGE_THREADS_MAX; q++) {
                 cudaEvent_t e;
                 S3G_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 ctx->stage_ev.push_back(e);
             }
         }
         for (int i = 0; i < nparts; i++) left[i] = cut[i + 1] > cut[i] ? (int)((cut[i + 1] - cut[i] + STAGE_PIECE - 1) / STAGE_PIECE) : 1;
-        for (int t = 0; t < STAGE_THREADS; t++)
+        for (int t = 0; t < stage_threads(); t++)
             copiers.emplace_back(stage_copier, ctx, t, bed, n, std::cref(cut), nparts, std::ref(left), std::ref(sh));
     }
     return S3G_OK;
