@@ -987,7 +987,9 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
             while (j + 1 < nparts && sh.queued[j + 1] && cudaEventQuery(ctx->part_ev[j + 1]) == cudaSuccess) j++;
             cudaGetLastError();                          // cudaErrorNotReady is not an error
         }
-        if (cudaStreamWaitEvent(ctx->stream, ctx->part_ev[j], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = S3G_E_CUDA; break; }
+        for (int k = i; k <= j; k++)                     // each one: copier threads finish the ranges of a pageable input in any order
+            if (cudaStreamWaitEvent(ctx->stream, ctx->part_ev[k], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = S3G_E_CUDA; }
+        if (rc != S3G_OK) break;
         const uint64_t lo = cut[i] - halo[i];
         rc = ch.step(d_bed + lo, cut[j + 1] - lo, halo[i], bed + cut[i], cut[i], j == nparts - 1);
         i = j + 1;
