@@ -110,7 +110,7 @@ static DevBuf *const *all_bufs(Ctx *c, size_t *n)
     B(rle_carry); B(rle_ebase); B(blocks); B(blk_prov); B(blk_bytes); B(in_use); B(seq_map); B(stream_tab);
     B(sa); B(rk); B(kv0); B(kv1); B(hist); B(bwt_misc); B(bwt_ghist); B(lcol);
     B(mtf0); B(mtfv16); B(mtf_freq); B(ztiles); B(bits); B(pool); B(pool_woff); B(streams); B(stream_meta);
-    B(io_a); B(io_b); B(io_c); B(io_d); B(io_e); B(chain_tf[0]); B(chain_tf[1]); B(chain_out);
+    B(io_a); B(io_b); B(io_c); B(io_d); B(io_e); B(chain_tf[0]); B(chain_tf[1]); B(chain_out); B(front_incl); B(front_flag);
 #undef B
     *n = k;
     return list;

@@ -101,6 +101,8 @@ struct Ctx {
     // stage buffers (grow-only)
     DevBuf bed, tile_cnt, line_start, start, stop, rem_off, flags, chrom_first;
     DevBuf scan_a, scan_b, scan_c, scalars;
+    DevBuf front_incl, front_flag;         // one-pass front end: inclusive prefix and status word per chunk
+    uint32_t front_gen = 0;                // generation tag of the status words (nothing is cleared between calls)
     DevBuf tf, chroms, stat_b, soff;
     // what run_tokenize measured (tokenize_transform.cu): inputs of run_transform_rest / run_range_summary
     uint32_t front_halo = 0, front_skip = 0, front_line1_flag = 0;

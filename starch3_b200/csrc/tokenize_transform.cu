@@ -399,23 +399,15 @@ __device__ __forceinline__ void warp_segmax_incl(int64_t &v, uint32_t &f)
     }
 }
 
-// ---- pass 1 -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FTH) k_front_measure(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo,
-                                                       FAgg *__restrict__ tile_agg, FAgg *__restrict__ chunk_pre, uint32_t *__restrict__ chunk_out,
-                                                       unsigned long long *sc)
+// one chunk's aggregate: lines, output bytes, chromosome starts, running max of stop.  Every lane of the warp calls; A and
+// malformed are the same in all lanes on return.
+__device__ __forceinline__ void measure_chunk(const WarpSh &W, const ChunkGeom &G, const uint8_t *__restrict__ bed, uint32_t halo,
+                                              unsigned long long *sc, FAgg &A, uint32_t &malformed)
 {
-    __shared__ WarpSh Ws[FWARPS];
-    __shared__ FAgg s_agg[FWARPS];
-    __shared__ unsigned long long s_lastnl[FWARPS];
-    __shared__ uint32_t s_mal[FWARPS];
-    const unsigned l = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint64_t chunk = (uint64_t)blockIdx.x * FWARPS + wid;
-    WarpSh &W = Ws[wid];
-    ChunkGeom G;
-    chunk_setup(W, G, bed, n, skip, chunk);
-    FAgg A = fagg_identity();
+    const unsigned l = threadIdx.x & 31;
+    A = fagg_identity();
     A.lines = G.k;
-    uint32_t malformed = 0;
+    malformed = 0;
     if (G.k > FMAXL) malformed = 1;                        // lines shorter than three bytes
     else if (G.k) {
         int64_t cs = 0, ce = 0;
@@ -437,35 +429,59 @@ __global__ void __launch_bounds__(FTH) k_front_measure(const uint8_t *__restrict
             if (L.owned && ((vv == 2 && !G.has_prev) || (vv == 1 && G.has_prev && !G.has_prev2))) sc[SC_LINE1] = L.flag;
         }
     }
+}
+
+// where the chunk's last line ends (+1), 0 if no line ends in it; every lane of the warp calls
+__device__ __forceinline__ unsigned long long chunk_last_newline(const WarpSh &W, const ChunkGeom &G, const uint8_t *__restrict__ bed, uint64_t n)
+{
+    const unsigned l = threadIdx.x & 31;
+    if (G.k == 0) return 0;
+    if (G.k <= FMAXL) return G.chunk0 + W.nl[G.k - 1] + 1;
+    // the compact list is cut short: the chunk's last newline from the masks
+    uint64_t mn, mt;
+    masks64(bed, n, G.chunk0 + 64ull * l, &mn, &mt);
+    unsigned nz = __ballot_sync(0xffffffffu, mn != 0);
+    int hl = 31 - __clz((int)nz);
+    uint64_t hw = __shfl_sync(0xffffffffu, mn, hl);
+    return G.chunk0 + 64ull * hl + (63 - __clzll((long long)hw)) + 1;
+}
+
+// ---- pass 1 -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FTH) k_front_measure(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo,
+                                                       FAgg *__restrict__ tile_agg, FAgg *__restrict__ chunk_pre, uint32_t *__restrict__ chunk_out,
+                                                       unsigned long long *sc)
+{
+    __shared__ WarpSh Ws[FWARPS];
+    __shared__ FAgg s_agg[FWARPS];
+    __shared__ unsigned long long s_lastnl[FWARPS];
+    __shared__ uint32_t s_mal[FWARPS];
+    const unsigned l = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t chunk = (uint64_t)blockIdx.x * FWARPS + wid;
+    WarpSh &W = Ws[wid];
+    ChunkGeom G;
+    chunk_setup(W, G, bed, n, skip, chunk);
+    FAgg A;
+    uint32_t malformed;
+    measure_chunk(W, G, bed, halo, sc, A, malformed);
+    const unsigned long long last = chunk_last_newline(W, G, bed, n);
     if (l == 0) {
         s_agg[wid] = A; s_mal[wid] = malformed;
-        unsigned long long last = 0;
-        if (G.k && G.k <= FMAXL) last = G.chunk0 + W.nl[G.k - 1] + 1;
         s_lastnl[wid] = last;
         chunk_out[chunk] = (uint32_t)A.out;
-    }
-    if (G.k > FMAXL) {
-        // the compact list is cut short: the chunk's last newline from the masks
-        uint64_t mn, mt;
-        masks64(bed, n, G.chunk0 + 64ull * l, &mn, &mt);
-        unsigned nz = __ballot_sync(0xffffffffu, mn != 0);
-        int hl = 31 - __clz((int)nz);
-        uint64_t hw = __shfl_sync(0xffffffffu, mn, hl);
-        if (l == 0) s_lastnl[wid] = G.chunk0 + 64ull * hl + (63 - __clzll((long long)hw)) + 1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         FAgg run = fagg_identity();
-        unsigned long long last = 0; uint32_t mal = 0;
+        unsigned long long lastm = 0; uint32_t mal = 0;
         for (int w = 0; w < FWARPS; w++) {
             chunk_pre[(uint64_t)blockIdx.x * FWARPS + w] = run;
             run = fagg_op(run, s_agg[w]);
-            if (s_lastnl[w] > last) last = s_lastnl[w];
+            if (s_lastnl[w] > lastm) lastm = s_lastnl[w];
             mal |= s_mal[w];
         }
         tile_agg[blockIdx.x] = run;
         if (mal) atomicAdd(&sc[SC_MALFORMED], 1ull);
-        if (last) atomicMax(&sc[SC_LASTNL], last);
+        if (lastm) atomicMax(&sc[SC_LASTNL], lastm);
     }
 }
 
@@ -532,28 +548,19 @@ struct DumpArrays {            // the per-line arrays of the s3g_tokenize entry 
     uint8_t *flags;
 };
 
+// the transformed lines of one chunk, given what everything before it leaves (ex0) and its own output bytes (o_len); every
+// lane of the warp calls.  obuf: the warp's strip of shared memory; slot_salt spreads a chromosome's sums over stat_slots.
 template <bool DUMP>
-__global__ void __launch_bounds__(FTH, 3) k_front_write(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo, int64_t carry_max,
-                                                     const FAgg *__restrict__ span_pre, const FAgg *__restrict__ tile_pre, const FAgg *__restrict__ chunk_pre,
-                                                     const uint32_t *__restrict__ chunk_out, uint64_t n_lines, const __grid_constant__ PeerDst pd,
-                                                     ChromSeed *seeds, unsigned long long *stat_len, unsigned long long *stat_uniq, uint32_t stat_slots,
-                                                     uint64_t diag_chroms, unsigned long long *sc, DumpArrays da)
+__device__ __forceinline__ void write_chunk(const WarpSh &W, const ChunkGeom &G, const uint8_t *__restrict__ bed, uint32_t halo, int64_t carry_max,
+                                            const FAgg &ex0, uint32_t o_len, uint64_t n_lines, const PeerDst &pd, uint8_t *obuf, uint32_t slot_salt,
+                                            ChromSeed *seeds, unsigned long long *stat_len, unsigned long long *stat_uniq, uint32_t stat_slots,
+                                            uint64_t diag_chroms, unsigned long long *sc, const DumpArrays &da)
 {
-    __shared__ WarpSh Ws[FWARPS];
-    __shared__ __align__(16) uint8_t s_out[FWARPS][FOB + 16];
-    const unsigned l = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint64_t chunk = (uint64_t)blockIdx.x * FWARPS + wid;
-    WarpSh &W = Ws[wid];
-    ChunkGeom G;
-    chunk_setup(W, G, bed, n, skip, chunk);
-    if (G.k == 0 || G.k > FMAXL) return;
-    const FAgg ex0 = fagg_op(fagg_op(span_pre[blockIdx.x / FSCAN_T], tile_pre[blockIdx.x]), chunk_pre[chunk]);
+    const unsigned l = threadIdx.x & 31;
     const uint64_t o_begin = ex0.out;
-    const uint32_t o_len = chunk_out[chunk];
     const bool staged = o_len <= FOB;
     uint8_t *const tf = pd.ptr[0] + pd.off;                // destination 0 (this GPU's own buffer); pd.off keeps 16-byte phase in mind:
     const uint32_t ph = (uint32_t)(pd.off + o_begin) & 15u; // every destination buffer is 16-byte aligned, so the phase is the same in all
-    uint8_t *const obuf = s_out[wid];
     uint64_t run_out = 0, run_ch = 0;
     int64_t run_v = ex0.v;                                 // largest stop of the current chromosome so far
     const uint64_t c0 = ex0.chroms - 1;                    // the chromosome the chunk begins in (unless its first line starts one)
@@ -594,7 +601,7 @@ __global__ void __launch_bounds__(FTH, 3) k_front_write(const uint8_t *__restric
                 const unsigned long long my_len = (unsigned long long)len, my_uniq = t > lo ? (unsigned long long)(t - lo) : 0ull;
                 if (chrom == c0) { acc_len += my_len; acc_uniq += my_uniq; }
                 else {
-                    const uint64_t slot = chrom * stat_slots + (blockIdx.x & (stat_slots - 1));
+                    const uint64_t slot = chrom * stat_slots + (slot_salt & (stat_slots - 1));
                     if (my_len) atomicAdd(&stat_len[slot], my_len);
                     if (my_uniq) atomicAdd(&stat_uniq[slot], my_uniq);
                 }
@@ -631,7 +638,7 @@ __global__ void __launch_bounds__(FTH, 3) k_front_write(const uint8_t *__restric
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) { acc_len += __shfl_xor_sync(0xffffffffu, acc_len, dd); acc_uniq += __shfl_xor_sync(0xffffffffu, acc_uniq, dd); }
     if (l == 0 && ex0.chroms) {
-        const uint64_t slot = c0 * stat_slots + (blockIdx.x & (stat_slots - 1));
+        const uint64_t slot = c0 * stat_slots + (slot_salt & (stat_slots - 1));
         if (acc_len) atomicAdd(&stat_len[slot], acc_len);
         if (acc_uniq) atomicAdd(&stat_uniq[slot], acc_uniq);
     }
@@ -667,6 +674,165 @@ __global__ void __launch_bounds__(FTH, 3) k_front_write(const uint8_t *__restric
             else for (uint32_t j = c > lo_b ? c : lo_b; j < c + 16 && j < hi_b; j++) dst[j] = obuf[j];
         }
     }
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(FTH, 3) k_front_write(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, uint32_t halo, int64_t carry_max,
+                                                     const FAgg *__restrict__ span_pre, const FAgg *__restrict__ tile_pre, const FAgg *__restrict__ chunk_pre,
+                                                     const uint32_t *__restrict__ chunk_out, uint64_t n_lines, const __grid_constant__ PeerDst pd,
+                                                     ChromSeed *seeds, unsigned long long *stat_len, unsigned long long *stat_uniq, uint32_t stat_slots,
+                                                     uint64_t diag_chroms, unsigned long long *sc, DumpArrays da)
+{
+    __shared__ WarpSh Ws[FWARPS];
+    __shared__ __align__(16) uint8_t s_out[FWARPS][FOB + 16];
+    const unsigned wid = threadIdx.x >> 5;
+    const uint64_t chunk = (uint64_t)blockIdx.x * FWARPS + wid;
+    WarpSh &W = Ws[wid];
+    ChunkGeom G;
+    chunk_setup(W, G, bed, n, skip, chunk);
+    if (G.k == 0 || G.k > FMAXL) return;
+    const FAgg ex0 = fagg_op(fagg_op(span_pre[blockIdx.x / FSCAN_T], tile_pre[blockIdx.x]), chunk_pre[chunk]);
+    write_chunk<DUMP>(W, G, bed, halo, carry_max, ex0, chunk_out[chunk], n_lines, pd, s_out[wid], blockIdx.x, seeds, stat_len, stat_uniq, stat_slots,
+                      diag_chroms, sc, da);
+}
+
+// ---- both passes in one kernel ------------------------------------------------------------------------------------
+// k_front_fused measures the 8 chunks of a tile, publishes the tile's aggregate, gets the aggregate of everything before the
+// tile by a decoupled look-back over the tiles (its first warp reads the status of 32 predecessors at a time and folds what
+// they have published: own aggregates up to the nearest one that already knows its inclusive prefix), and every warp writes
+// its chunk's transformed lines -- with the masks and the line list it already has.  No second read of the input from HBM, no second chunk setup, no scan kernels.
+// Tiles (8 chunks, one per warp) are taken from a ticket, so a chunk's predecessors have always started.  The totals are not
+// known before the launch: the destination and the chromosome tables have a capacity, a chunk that would exceed it raises
+// SC_OVERFLOW and writes nothing (the host then takes the two-pass form).  For the one-shot entries only: the ranges of the
+// N-GPU path and of the chained entry need their offsets from outside (k_front_measure / k_front_write).
+#ifndef S3G_FUSED_OCC
+#define S3G_FUSED_OCC 4
+#endif
+struct FusedTables {
+    FAgg *agg, *incl;             // per tile of 8 chunks: its own aggregate, the aggregate of everything up to and including it
+    uint32_t *flag;               // per tile: generation << 2 | state (1: aggregate published, 2: inclusive prefix published)
+    uint32_t *ticket;
+    uint32_t gen;
+    uint64_t n_chunks;
+    uint64_t tf_cap, chrom_cap;
+};
+enum { SC_OVERFLOW = 6, SC_TICKET = 7 };
+
+__device__ __forceinline__ FAgg fagg_load_cg(const FAgg *p)
+{
+    const unsigned long long *q = reinterpret_cast<const unsigned long long *>(p);
+    FAgg a;
+    a.lines = __ldcg(q); a.out = __ldcg(q + 1); a.chroms = __ldcg(q + 2); a.v = (int64_t)__ldcg(q + 3);
+    const unsigned long long t = __ldcg(q + 4);
+    a.seg = (uint32_t)t; a.pad = 0;
+    return a;
+}
+__device__ __forceinline__ FAgg fagg_shfl_down(const FAgg &a, int d)
+{
+    FAgg r;
+    r.lines = __shfl_down_sync(0xffffffffu, a.lines, d); r.out = __shfl_down_sync(0xffffffffu, a.out, d);
+    r.chroms = __shfl_down_sync(0xffffffffu, a.chroms, d); r.v = __shfl_down_sync(0xffffffffu, a.v, d);
+    r.seg = __shfl_down_sync(0xffffffffu, a.seg, d); r.pad = 0;
+    return r;
+}
+__device__ __forceinline__ FAgg fagg_shfl(const FAgg &a, int src)
+{
+    FAgg r;
+    r.lines = __shfl_sync(0xffffffffu, a.lines, src); r.out = __shfl_sync(0xffffffffu, a.out, src);
+    r.chroms = __shfl_sync(0xffffffffu, a.chroms, src); r.v = __shfl_sync(0xffffffffu, a.v, src);
+    r.seg = __shfl_sync(0xffffffffu, a.seg, src); r.pad = 0;
+    return r;
+}
+
+__global__ void __launch_bounds__(FTH, S3G_FUSED_OCC) k_front_fused(const uint8_t *__restrict__ bed, uint64_t n, uint32_t skip, FusedTables T,
+                                                     const __grid_constant__ PeerDst pd, ChromSeed *seeds, unsigned long long *stat_len,
+                                                     unsigned long long *stat_uniq, uint32_t stat_slots, unsigned long long *sc)
+{
+    __shared__ WarpSh Ws[FWARPS];
+    __shared__ __align__(16) uint8_t s_out[FWARPS][FOB + 16];
+    __shared__ FAgg s_agg[FWARPS];             // the chunks' own aggregates
+    __shared__ FAgg s_ex;                      // what everything before the tile leaves
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(T.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const unsigned l = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t chunk = (uint64_t)tile * FWARPS + wid;
+    WarpSh &W = Ws[wid];
+    ChunkGeom G;
+    chunk_setup(W, G, bed, n, skip, chunk);
+    FAgg A;
+    uint32_t malformed;
+    measure_chunk(W, G, bed, 0, sc, A, malformed);
+    const unsigned long long last = chunk_last_newline(W, G, bed, n);
+    if (l == 0) {
+        if (malformed) atomicAdd(&sc[SC_MALFORMED], 1ull);
+        if (last) atomicMax(&sc[SC_LASTNL], last);
+        s_agg[wid] = A;
+    }
+    __syncthreads();
+    // ---- the tile's first warp: publish the tile's aggregate, look back over the tiles before it ----
+    // (the status tables are per TILE: with a warp's chunk as the unit every warp of a wave that runs in step would have to
+    // fold the whole wave behind it, 3500 aggregates; 444 tiles are in flight at most, 14 steps of 32)
+    const uint32_t gtag = T.gen << 2;
+    if (wid == 0) {
+        FAgg TA = fagg_identity();
+#pragma unroll
+        for (int w = 0; w < FWARPS; w++) TA = fagg_op(TA, s_agg[w]);
+        if (l == 0) {
+            T.agg[tile] = TA;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t *>(&T.flag[tile]) = gtag | 1u;
+        }
+        FAgg ex = fagg_identity();
+        for (int64_t j = (int64_t)tile - 1; j >= 0; j -= 32) {
+            const int64_t idx = j - (int64_t)l;
+            uint32_t st;
+            uint32_t spins = 0;
+            for (;;) {
+                st = idx >= 0 ? *reinterpret_cast<volatile const uint32_t *>(&T.flag[idx]) : (gtag | 2u);
+                const bool ready = (st >> 2) == T.gen && (st & 3u) != 0;
+                if (__all_sync(0xffffffffu, ready)) break;
+                if (++spins > (1u << 24)) __trap();              // a predecessor never published: fail loudly instead of hanging
+                __nanosleep(40);
+            }
+            __threadfence();
+            const unsigned incl_m = __ballot_sync(0xffffffffu, (st & 3u) == 2u);
+            const int m = incl_m ? __ffs((int)incl_m) - 1 : 32;  // the nearest predecessor that knows its inclusive prefix
+            FAgg V = fagg_identity();
+            if (idx >= 0) {
+                if ((int)l < m) V = fagg_load_cg(&T.agg[idx]);
+                else if ((int)l == m) V = fagg_load_cg(&T.incl[idx]);
+            }
+            // lane 0 <- V[31] (+) .. (+) V[1] (+) V[0]: higher lanes are earlier tiles
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const FAgg O = fagg_shfl_down(V, d);
+                if (l + d < 32) V = fagg_op(O, V);
+            }
+            ex = fagg_op(fagg_shfl(V, 0), ex);
+            if (m < 32) break;
+        }
+        if (l == 0) {
+            const FAgg incl = fagg_op(ex, TA);
+            T.incl[tile] = incl;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t *>(&T.flag[tile]) = gtag | 2u;
+            s_ex = ex;
+            if ((uint64_t)tile * FWARPS + FWARPS == T.n_chunks) {
+                sc[SC_TOTAL + 0] = incl.lines; sc[SC_TOTAL + 1] = incl.out; sc[SC_TOTAL + 2] = incl.chroms;
+                sc[SC_TOTAL + 3] = (unsigned long long)incl.v; sc[SC_TOTAL + 4] = incl.seg;
+            }
+        }
+    }
+    __syncthreads();
+    if (G.k == 0 || G.k > FMAXL) return;
+    FAgg ex = s_ex;
+    for (unsigned w = 0; w < wid; w++) ex = fagg_op(ex, s_agg[w]);
+    const FAgg incl = fagg_op(ex, A);
+    if (incl.out > T.tf_cap || incl.chroms > T.chrom_cap) { if (l == 0) sc[SC_OVERFLOW] = 1; return; }
+    DumpArrays da = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    write_chunk<false>(W, G, bed, 0, INT64_MIN, ex, (uint32_t)A.out, 0, pd, s_out[wid], tile, seeds, stat_len, stat_uniq, stat_slots, ~0ull, sc, da);
 }
 
 __global__ void k_chrom_finish(const ChromSeed *seeds, const unsigned long long *stat_len, const unsigned long long *stat_uniq, uint32_t stat_slots,
@@ -793,8 +959,77 @@ int run_transform_rest(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out
     return check_launch("transform write");
 }
 
+// both kernels of the front end as one launch (k_front_fused); S3G_E_CAPACITY: the destination or the chromosome tables were
+// too small for this input -- the caller takes the two-pass form
+constexpr uint64_t FUSED_CHROM_CAP = 4096;
+static int run_transform_fused(Ctx *ctx, const uint8_t *d_bed, uint64_t n, uint32_t skip, TfResult *out)
+{
+    *out = TfResult();
+    uint64_t ntiles = (n + (uint64_t)FCH * FWARPS - 1) / ((uint64_t)FCH * FWARPS);
+    if (ntiles == 0) ntiles = 1;
+    if (ntiles > 0x7fffffffull) { set_error("input too large"); return S3G_E_LIMIT; }
+    const uint64_t n_chunks = ntiles * FWARPS;
+    S3G_TRY(ctx->scan_b.ensure(ntiles * sizeof(FAgg)));
+    S3G_TRY(ctx->front_incl.ensure(ntiles * sizeof(FAgg)));
+    const size_t flag_cap = ctx->front_flag.cap;
+    S3G_TRY(ctx->front_flag.ensure(ntiles * 4));
+    if (ctx->front_flag.cap != flag_cap || ctx->front_gen >= (1u << 29)) {       // new table (or the tag wraps): start from zero
+        S3G_CUDA(cudaMemsetAsync(ctx->front_flag.p, 0, ctx->front_flag.cap, ctx->stream));
+        ctx->front_gen = 0;
+    }
+    S3G_TRY(ctx->scalars.ensure(64 * 8));
+    uint64_t *d_sc = ctx->scalars.as<uint64_t>();
+    S3G_CUDA(cudaMemsetAsync(d_sc, 0, 64 * 8, ctx->stream));
+    const uint64_t tf_cap = n + n / 8 + 4096;
+    S3G_TRY(ctx->tf.ensure(tf_cap + 64));
+    const uint32_t slots = 32;
+    S3G_TRY(ctx->chrom_first.ensure((FUSED_CHROM_CAP + 1) * sizeof(ChromSeed)));
+    S3G_TRY(ctx->stat_b.ensure((FUSED_CHROM_CAP + 1) * slots * 16));
+    S3G_TRY(ctx->chroms.ensure((FUSED_CHROM_CAP + 1) * sizeof(s3g_chrom)));
+    unsigned long long *stat_len = ctx->stat_b.as<unsigned long long>(), *stat_uniq = stat_len + (FUSED_CHROM_CAP + 1) * slots;
+    S3G_CUDA(cudaMemsetAsync(stat_len, 0, (FUSED_CHROM_CAP + 1) * slots * 16, ctx->stream));
+    FusedTables T;
+    T.agg = ctx->scan_b.as<FAgg>(); T.incl = ctx->front_incl.as<FAgg>(); T.flag = ctx->front_flag.as<uint32_t>();
+    T.ticket = reinterpret_cast<uint32_t *>(d_sc + SC_TICKET);
+    T.gen = ++ctx->front_gen; T.n_chunks = n_chunks; T.tf_cap = tf_cap; T.chrom_cap = FUSED_CHROM_CAP;
+    PeerDst pd;
+    memset(&pd, 0, sizeof pd);
+    pd.ptr[0] = ctx->tf.as<uint8_t>(); pd.n = 1; pd.off = 0;
+    S3G_BYTES(ctx, 2.0 * (double)n);
+    S3G_LAUNCH(ctx, k_front_fused, (unsigned)ntiles, FTH, 0, d_bed, n, skip, T, pd, ctx->chrom_first.as<ChromSeed>(), stat_len, stat_uniq, slots,
+               (unsigned long long *)d_sc);
+    S3G_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_sc, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    S3G_CUDA(cudaStreamSynchronize(ctx->stream));
+    S3G_TRY(check_launch("front fused"));
+    const uint64_t *h = ctx->h_scalars;
+    out->n_lines = h[SC_TOTAL + 0];
+    out->tf_len = h[SC_TOTAL + 1];
+    out->n_chroms = h[SC_TOTAL + 2];
+    out->dropped = out->n_lines ? n - h[SC_LASTNL] : n - skip;
+    ctx->front_halo = 0; ctx->front_skip = skip;
+    ctx->front_tail_max = (int64_t)h[SC_TOTAL + 3];
+    if (out->n_lines && h[SC_MALFORMED]) {
+        set_error("malformed BED line(s): fewer than three fields (in %llu 2 KiB chunk(s) of the input)", (unsigned long long)h[SC_MALFORMED]);
+        return S3G_E_MALFORMED;
+    }
+    if (h[SC_OVERFLOW]) return S3G_E_CAPACITY;
+    if (out->n_lines)
+        S3G_LAUNCH(ctx, k_chrom_finish, (unsigned)((out->n_chroms + 127) / 128), 128, 0, ctx->chrom_first.as<ChromSeed>(), stat_len, stat_uniq, slots,
+                   out->n_chroms, out->n_lines, out->tf_len, ctx->chroms.as<s3g_chrom>(), 0u);
+    return check_launch("front fused");
+}
+
 int run_transform(Ctx *ctx, const uint8_t *d_bed, uint64_t n, TfResult *out, bool tokenize_only, uint32_t skip, bool last_part)
 {
+    // S3G_FRONT=one: one launch (k_front_fused) when nothing outside the range is needed and every chromosome of it is
+    // counted.  Not the default: measured on B200 it is 4-12 % slower than the two passes (cfg3, 30 M lines: 3.50 ms against
+    // 1.38 + 1.85 ms; cfg2: 1.63 against 1.57 ms) -- the measuring half runs at the writing half's register count, and what
+    // the second chunk setup costs the two barriers and the look-back take back.  Kept for the tests and the record.
+    const char *fe = getenv("S3G_FRONT");
+    if (!tokenize_only && last_part && fe && !strcmp(fe, "one")) {
+        int rc = run_transform_fused(ctx, d_bed, n, skip, out);
+        if (rc != S3G_E_CAPACITY) return rc;
+    }
     S3G_TRY(run_tokenize(ctx, d_bed, n, skip, out, 0));
     ctx->h_scalars[SC_UNSORTED] = 0; ctx->h_scalars[SC_CRLF] = 0;
     if (out->n_lines == 0) return S3G_OK;

@@ -69,13 +69,31 @@ def test_tokenize(ctx, oracle, name, bed):
     assert t["line_start"][len(lines)] == pos
 
 
+@pytest.mark.parametrize("front", ["one", "two"])
 @pytest.mark.parametrize("name,bed", BEDS, ids=[n for n, _ in BEDS])
-def test_transform(ctx, oracle, name, bed):
+def test_transform(ctx, oracle, name, bed, front, monkeypatch):
+    """the front end as one launch (k_front_fused: decoupled look-back over the chunk aggregates) and as its two passes"""
+    monkeypatch.setenv("S3G_FRONT", front)
     tf, chroms, dropped = ctx.transform(bed)
     otf, ochroms, odropped = oracle.transform(bed)
     assert tf == otf
     assert dropped == odropped
     assert chroms == ochroms
+
+
+def test_transform_one_launch_large_and_many_chromosomes(ctx, oracle, monkeypatch):
+    """thousands of chunks in flight (the look-back folds up to 32 predecessors a step), more chromosomes than the one-launch
+    form has table room for (it reports the overflow and the two passes take over), and the same answer from both forms"""
+    big = synth.bed(5, 1_500_000).tobytes()
+    many = b"".join(b"s%d\t%d\t%d\n" % (i, i, i + 3) for i in range(6000))
+    for bed in (big, many):
+        monkeypatch.setenv("S3G_FRONT", "one")
+        a = ctx.transform(bed)
+        monkeypatch.setenv("S3G_FRONT", "two")
+        b = ctx.transform(bed)
+        assert a == b
+        otf, ochroms, odropped = oracle.transform(bed)
+        assert a[0] == otf and a[1] == ochroms and a[2] == odropped
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg3const", "cfg4", "overlap", "zerolen"])
