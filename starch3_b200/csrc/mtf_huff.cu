@@ -1034,23 +1034,16 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
         S3G_CUDA(cudaFuncSetAttribute(k_huff<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HuffSmem)));
         ctx->attr_huff = true;
     }
-    // chunks as in run_mtf: whole waves of two 512-thread CTAs per SM, then the remainder with one 1024-thread CTA per SM,
-    // a block spread over a cluster of 1, 2, 4 or 8 of them
+    // One launch of 512-thread CTAs (two per SM) for a batch of more than 1.5 blocks per SM: the CTAs of this kernel take
+    // very different times, so the GPU stays full until the end whatever the count (cutting cfg4's 893 blocks into 888 + 5
+    // made it 9.6 ms instead of 9.15).  Up to one block per SM: one 1024-thread CTA per SM, a block spread over a cluster of
+    // 1, 2, 4 or 8 of them.  In between (149 .. 222 blocks, 60-75 % of the slots of the two-per-SM form): the first 148 as
+    // one CTA per SM, the rest over clusters.
     const bool forced = getenv("S3G_CLUSTER") != nullptr;
     std::vector<Chunk> chunks;
-    if (forced || nb <= (uint64_t)SM_COUNT) chunks.push_back({0, nb, nb > (uint64_t)SM_COUNT ? 0u : cluster_size(nb, SM_COUNT)});
-    else {
-        const uint64_t W = 2 * SM_COUNT;
-        uint64_t s = nb / W * W;
-        if (s) chunks.push_back({0, s, 0});                    // cs 0: the 512-thread form
-        const uint64_t rem = nb - s;
-        if (rem > W * 3 / 4) chunks.push_back({s, rem, 0});                  // nearly a wave: as it is
-        else if (rem) {
-            std::vector<Chunk> tail;
-            plan_chunks(rem, SM_COUNT, false, tail);                          // one 1024-thread CTA per SM: waves of 148
-            for (Chunk &t : tail) { t.s0 += s; chunks.push_back(t); }
-        }
-    }
+    if (nb <= (uint64_t)SM_COUNT) chunks.push_back({0, nb, cluster_size(nb, SM_COUNT)});
+    else if (forced || nb > (uint64_t)SM_COUNT * 3 / 2) chunks.push_back({0, nb, 0u});          // cs 0: the 512-thread form
+    else plan_chunks(nb, SM_COUNT, false, chunks);
     for (const Chunk &ck : chunks) {
         const uint64_t s0 = ck.s0, n = ck.n;
         double N = 0;
