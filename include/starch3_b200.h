@@ -196,6 +196,10 @@ S3G_API int s3g_multi_compress_bed(s3g_ctx **ctxs, int n_ctx, const uint8_t *bed
                                    const char *note, s3g_result *res);
 /* CUDA-event time per stage (indices as s3g_result.stage_ms) of the phases run on ctx since s3g_shard_tokenize. */
 S3G_API int s3g_stage_times(s3g_ctx *ctx, double *stage_ms8);
+/* Host logic only (no device needed): how a batch of n_blocks bzip2 blocks is dealt to the MTF (stage 3) or Huffman (stage 4)
+ * kernels -- chunks of consecutive blocks, ctas[i] CTAs per block (0: the Huffman form with two 512-thread CTAs per SM and one
+ * CTA per block).  DESIGN.md section 4, plan_chunks.  The tests check that the chunks tile the batch and fit the GPU. */
+S3G_API int s3g_batch_chunks(uint64_t n_blocks, int stage, uint64_t *first, uint64_t *count, uint32_t *ctas, uint64_t cap, uint64_t *n_chunks);
 
 /* ---- stage entry points (host buffers in / out), for the parity tests ---- */
 

@@ -21,7 +21,7 @@ C_ABI_SYMBOLS = [
     "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_last_host_entry", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_stream_begin", "s3g_stream_write", "s3g_stream_end",
-    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_multi_compress_bed", "s3g_stage_times",
+    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_multi_compress_bed", "s3g_stage_times", "s3g_batch_chunks",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
     "s3g_decompress_archive", "s3g_bz_decompress", "s3g_inverse_transform",
     "s3g_BZ2_bzCompressInit", "s3g_BZ2_bzCompress", "s3g_BZ2_bzCompressEnd",
@@ -97,6 +97,7 @@ def lib():
         L.s3g_launch_count.argtypes = [vp]; L.s3g_launch_count.restype = u64
         L.s3g_sort_retries.argtypes = [vp]; L.s3g_sort_retries.restype = u64
         L.s3g_last_host_entry.argtypes = [vp]; L.s3g_last_host_entry.restype = i32
+        L.s3g_batch_chunks.argtypes = [u64, i32, vp, vp, vp, u64, C.POINTER(u64)]
         L.s3g_sort_stats.argtypes = [vp, vp]
         L.s3g_profile.argtypes = [vp, i32]
         L.s3g_profile_report.argtypes = [vp, C.c_char_p, u64]
@@ -186,6 +187,17 @@ class Result:
         c = self.chroms[i]
         o = self.streams_off + c["bz_off"]
         return self.archive[o:o + c["bz_len"]]
+
+
+def batch_chunks(n_blocks, stage):
+    """how a batch of n_blocks bzip2 blocks is dealt to the MTF (stage 3) / Huffman (stage 4) kernels: [(first, count, ctas per block)];
+    host logic only, no device needed"""
+    cap = 64
+    first = (C.c_uint64 * cap)(); count = (C.c_uint64 * cap)(); ctas = (C.c_uint32 * cap)(); n = C.c_uint64(0)
+    rc = lib().s3g_batch_chunks(n_blocks, stage, first, count, ctas, cap, C.byref(n))
+    if rc != S3G_OK:
+        raise Starch3Error(rc, lib().s3g_last_error().decode("utf-8", "replace"))
+    return [(int(first[i]), int(count[i]), int(ctas[i])) for i in range(n.value)]
 
 
 def multi_compress_bed(contexts, bed, block_size_100k=9, note=None):

@@ -1025,6 +1025,15 @@ __global__ void __launch_bounds__(HT, 1024 / HT) k_huff(const uint16_t *mtfv_all
     }
 }
 
+// the Huffman stage's chunks (see run_huff); cs 0: the 512-thread form, one CTA per block
+static void plan_huff_chunks(uint64_t nb, bool forced, std::vector<Chunk> &chunks)
+{
+    chunks.clear();
+    if (nb <= (uint64_t)SM_COUNT) chunks.push_back({0, nb, cluster_size(nb, SM_COUNT)});
+    else if (forced || nb > (uint64_t)SM_COUNT * 3 / 2) chunks.push_back({0, nb, 0u});
+    else plan_chunks(nb, SM_COUNT, false, chunks);
+}
+
 int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t *d_sel_out, uint8_t *d_len_out)
 {
     if (nb == 0) return S3G_OK;
@@ -1039,11 +1048,8 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
     // made it 9.6 ms instead of 9.15).  Up to one block per SM: one 1024-thread CTA per SM, a block spread over a cluster of
     // 1, 2, 4 or 8 of them.  In between (149 .. 222 blocks, 60-75 % of the slots of the two-per-SM form): the first 148 as
     // one CTA per SM, the rest over clusters.
-    const bool forced = getenv("S3G_CLUSTER") != nullptr;
     std::vector<Chunk> chunks;
-    if (nb <= (uint64_t)SM_COUNT) chunks.push_back({0, nb, cluster_size(nb, SM_COUNT)});
-    else if (forced || nb > (uint64_t)SM_COUNT * 3 / 2) chunks.push_back({0, nb, 0u});          // cs 0: the 512-thread form
-    else plan_chunks(nb, SM_COUNT, false, chunks);
+    plan_huff_chunks(nb, getenv("S3G_CLUSTER") != nullptr, chunks);
     for (const Chunk &ck : chunks) {
         const uint64_t s0 = ck.s0, n = ck.n;
         double N = 0;
@@ -1065,3 +1071,19 @@ int run_huff(Ctx *ctx, uint64_t b0, uint64_t nb, int with_block_header, uint8_t 
 }
 
 }  // namespace s3g
+
+extern "C" int s3g_batch_chunks(uint64_t n_blocks, int stage, uint64_t *first, uint64_t *count, uint32_t *ctas, uint64_t cap, uint64_t *n_chunks)
+{
+    using namespace s3g;
+    if (!n_chunks || (stage != 3 && stage != 4)) { set_error("bad argument (stage 3 = MTF, 4 = Huffman)"); return S3G_E_PARAM; }
+    std::vector<Chunk> ch;
+    if (n_blocks) { if (stage == 3) plan_chunks(n_blocks, 2 * SM_COUNT, false, ch); else plan_huff_chunks(n_blocks, false, ch); }
+    *n_chunks = ch.size();
+    if (ch.size() > cap) { set_error("cap too small: need %llu", (unsigned long long)ch.size()); return S3G_E_CAPACITY; }
+    for (size_t i = 0; i < ch.size(); i++) {
+        if (first) first[i] = ch[i].s0;
+        if (count) count[i] = ch[i].n;
+        if (ctas) ctas[i] = ch[i].cs;
+    }
+    return S3G_OK;
+}

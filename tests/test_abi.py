@@ -62,3 +62,30 @@ def test_synth_is_deterministic():
     assert a.tobytes() == b.tobytes()
     assert a.tobytes().count(b"\n") == 5000
     assert s3.synth.bed(2, 5000, seed=43).tobytes() != a.tobytes()
+
+
+def test_batches_are_dealt_in_chunks_that_tile_them_and_fit_the_gpu():
+    """host logic of mtf_huff.cu (plan_chunks): for every batch size the chunks are consecutive, cover the batch exactly, and a
+    chunk's CTAs (blocks x CTAs per block) fit one wave -- 296 CTAs for the MTF kernels, 148 for the 1024-thread Huffman
+    form -- unless it is made of whole waves of one CTA per block"""
+    import starch3_b200 as s3
+    sm = 148
+    for stage, wave in ((3, 2 * sm), (4, sm)):
+        for nb in list(range(1, 700)) + [893, 1024, 5000]:
+            chunks = s3.batch_chunks(nb, stage)
+            at = 0
+            for first, count, ctas in chunks:
+                assert first == at and count > 0
+                at += count
+                if stage == 4 and ctas == 0:
+                    assert count > sm and len(chunks) == 1      # the 512-thread form takes a whole batch
+                elif ctas == 1:
+                    assert count % wave == 0 or count <= wave
+                else:
+                    assert ctas in (2, 4, 8) and ctas * count <= wave
+            assert at == nb
+            assert len(chunks) <= 6
+    assert s3.batch_chunks(0, 3) == []
+    assert s3.batch_chunks(296, 3) == [(0, 296, 1)] and s3.batch_chunks(178, 3) == [(0, 148, 2), (148, 30, 8)]
+    assert s3.batch_chunks(893, 3) == [(0, 888, 1), (888, 5, 8)] and s3.batch_chunks(893, 4) == [(0, 893, 0)]
+    assert s3.batch_chunks(178, 4) == [(0, 148, 1), (148, 30, 4)] and s3.batch_chunks(37, 4) == [(0, 37, 4)]
