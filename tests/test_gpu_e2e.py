@@ -284,6 +284,57 @@ def test_chained_host_entry_random_inputs(ctx, oracle, monkeypatch):
     assert one.archive == oracle.archive(bed, level, "")
 
 
+def test_random_small_inputs_against_the_oracle(ctx, oracle):
+    """150 inputs from a grammar of the BED domain and its edges: names and remainders of arbitrary bytes (0x00, 0xff, CR, runs of
+    one byte), numbers of 1 to 18 digits with or without a sign, unsorted and overlapping elements, empty remainders, a missing
+    last line feed, one to a few hundred lines over one to six chromosomes, every block size -- whole archives, byte for byte"""
+    rng = np.random.default_rng(424242)
+
+    def rbytes(n, alphabet=None):
+        if alphabet is None:
+            b = rng.integers(0, 256, n, dtype=np.uint8)
+            b[(b == 10) | (b == 9)] = 65
+            return b.tobytes()
+        return bytes(rng.choice(list(alphabet), n).astype(np.uint8))
+
+    def number():
+        k = int(rng.integers(0, 10))
+        d = int(rng.integers(1, 19)) if k == 0 else int(rng.integers(1, 9))
+        txt = str(int(rng.integers(1, 10))) + "".join(str(int(x)) for x in rng.integers(0, 10, d - 1))
+        if k == 1:
+            txt = "-" + txt
+        elif k == 2:
+            txt = "+" + txt
+        return txt.encode()
+
+    for case in range(150):
+        lines = []
+        for c in range(int(rng.integers(1, 7))):
+            name = rbytes(int(rng.integers(1, 12))) if rng.integers(0, 4) == 0 else b"chr%d" % c
+            pos = int(rng.integers(0, 1000))
+            shape = int(rng.integers(0, 5))
+            for _ in range(int(rng.integers(1, 120))):
+                if shape == 4:
+                    a, b = number(), number()
+                else:
+                    pos += int(rng.integers(0, 300)) - (20 if shape == 3 else 0)
+                    ln = 25 if shape == 1 else int(rng.integers(0, 500))
+                    a, b = b"%d" % pos, b"%d" % (pos + ln)
+                    pos += ln
+                kind = int(rng.integers(0, 6))
+                rest = b"" if kind < 2 else b"\t" if kind == 2 else b"\t" + rbytes(int(rng.integers(1, 40)), None if kind == 3 else b"ab\t\r .")
+                if kind == 5:
+                    rest = b"\t" + bytes([int(rng.integers(32, 127))]) * int(rng.integers(1, 600))
+                lines.append(name + b"\t" + a + b"\t" + b + rest + b"\n")
+        bed = b"".join(lines)
+        if case % 7 == 3:
+            bed = bed[:-1]
+        level = int(rng.integers(1, 10))
+        note = "" if case % 3 else "fuzz %d" % case
+        res = ctx.compress_bed(bed, level, note=note)
+        assert res.archive == oracle.archive(bed, level, note), (case, bed[:200])
+
+
 @pytest.mark.parametrize("cfg,lines,rng,piece", [(2, 60000, 200_000, 65536), (5, 60000, 4096, 1000), (1, 60000, 300_000, 7), (2, 30000, 1 << 20, 1 << 22)])
 def test_bounded_memory_ingestion(ctx, oracle, cfg, lines, rng, piece):
     """s3g_stream_*: the input arrives in pieces, at most one range of it is resident beside the open chromosome; ranges
