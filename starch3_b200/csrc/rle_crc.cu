@@ -559,17 +559,36 @@ __device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b)
     }
     return r;
 }
-// x^(8*nbytes) mod P
-__device__ uint32_t gf_xpow8(uint64_t nbytes)
+// x^(8 * 2^j) mod P for j = 0 .. 39, computed once on the host (a kernel argument: nothing per device to set up); a shift by n
+// bytes is the product of the entries of n's set bits -- ten multiplications on average where squaring on the device took forty
+struct XPow8 { uint32_t p[40]; };
+static uint32_t gf_mulmod_host(uint32_t a, uint32_t b)
 {
-    uint32_t result = 1;           // the polynomial "1"
-    uint32_t sq = 0x100;           // x^8
-    while (nbytes) {
-        if (nbytes & 1) result = gf_mulmod(result, sq);
-        sq = gf_mulmod(sq, sq);
-        nbytes >>= 1;
+    uint32_t r = 0;
+    for (int i = 31; i >= 0; i--) {
+        uint32_t msb = r & 0x80000000u;
+        r <<= 1;
+        if (msb) r ^= 0x04C11DB7u;
+        if ((b >> i) & 1u) r ^= a;
     }
-    return result;
+    return r;
+}
+static const XPow8 &xpow8_table()
+{
+    static const XPow8 t = [] {
+        XPow8 x;
+        uint32_t sq = 0x100;           // x^8
+        for (int j = 0; j < 40; j++) { x.p[j] = sq; sq = gf_mulmod_host(sq, sq); }
+        return x;
+    }();
+    return t;
+}
+// c * x^(8*nbytes) mod P
+__device__ __forceinline__ uint32_t gf_shift_bytes(uint32_t c, uint64_t nbytes, const XPow8 &X)
+{
+    for (int j = 0; nbytes && j < 40; j++, nbytes >>= 1)
+        if (nbytes & 1) c = gf_mulmod(c, X.p[j]);
+    return c;
 }
 
 constexpr int CRC_T = 512;
@@ -578,7 +597,7 @@ constexpr int CRC_T = 512;
 // piece into 512 segments, each by slicing-by-4 (four table look-ups per aligned 32-bit word, 16-byte loads).  A segment's
 // register is moved to the end of the BLOCK by a multiplication with x^(8 * bytes after it) mod P; what is left is a sum
 // (XOR) over segments and pieces: the pieces meet in BlockInfo.crc by atomicXor, k_crc_finish complements the sum.
-__global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInfo *blocks, uint32_t parts)
+__global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInfo *blocks, uint32_t parts, const __grid_constant__ XPow8 X)
 {
     __shared__ uint32_t tab[4][256];       // tab[k][b]: the CRC register after byte b and k zero bytes
     __shared__ uint32_t part[CRC_T];
@@ -618,7 +637,7 @@ __global__ void __launch_bounds__(CRC_T) k_block_crc(const uint8_t *in, BlockInf
     for (; i < hi; i++) c = (c << 8) ^ tab[0][(c >> 24) ^ p[i]];
     // shift by the bytes of the block that follow this segment
     uint64_t after = len - hi;
-    if (c != 0 && after) c = gf_mulmod(c, gf_xpow8(after));
+    if (c != 0 && after) c = gf_shift_bytes(c, after, X);
     part[threadIdx.x] = c;
     __syncthreads();
     for (int d = CRC_T / 2; d > 0; d >>= 1) {
@@ -739,7 +758,7 @@ int run_rle_fill(Ctx *ctx, uint64_t b_lo, uint64_t b_hi)
     {
         // the block table's crc fields are zero (the cut leaves them so): the pieces XOR into them
         const uint32_t parts = crc_parts(b_hi - b_lo);
-        S3G_LAUNCH(ctx, k_block_crc, (unsigned)((b_hi - b_lo) * parts), CRC_T, 0, d_in, blocks + b_lo, parts);
+        S3G_LAUNCH(ctx, k_block_crc, (unsigned)((b_hi - b_lo) * parts), CRC_T, 0, d_in, blocks + b_lo, parts, xpow8_table());
         S3G_LAUNCH(ctx, k_crc_finish, (unsigned)((b_hi - b_lo + 255) / 256), 256, 0, blocks + b_lo, b_hi - b_lo);
     }
     S3G_LAUNCH(ctx, k_block_maps, (unsigned)(b_hi - b_lo), 256, 0, ctx->in_use.as<uint8_t>() + b_lo * 256, blocks + b_lo, ctx->seq_map.as<uint8_t>() + b_lo * 256);
@@ -755,7 +774,7 @@ int run_block_crc(Ctx *ctx, const uint8_t *d_in, BlockInfo *d_blocks, uint64_t n
     if (!nb) return S3G_OK;
     S3G_BYTES(ctx, bytes);
     const uint32_t parts = crc_parts(nb);                  // the descriptors' crc fields must be zero on entry
-    S3G_LAUNCH(ctx, k_block_crc, (unsigned)(nb * parts), CRC_T, 0, d_in, d_blocks, parts);
+    S3G_LAUNCH(ctx, k_block_crc, (unsigned)(nb * parts), CRC_T, 0, d_in, d_blocks, parts, xpow8_table());
     S3G_LAUNCH(ctx, k_crc_finish, (unsigned)((nb + 255) / 256), 256, 0, d_blocks, nb);
     return check_launch("block crc");
 }
