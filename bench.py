@@ -68,7 +68,11 @@ class ClockSampler:
         for ln in self.p.stdout:
             self.rows.append(ln.strip())
 
-    def stop(self):
+    def mark(self):
+        """rows read so far: brackets the timed region (nvidia-smi needs ~0.1 s before its first row, so it is started early)"""
+        return len(self.rows)
+
+    def stop(self, i0=0, i1=None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -78,7 +82,8 @@ class ClockSampler:
             self.p.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[max(0, i0 - 1):(i1 + 1 if i1 is not None else None)]      # the rows of the timed region and its two neighbours
+        for r in rows or self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -211,6 +216,7 @@ def run_b200(args, rank, world, local_rank):
     def sync():
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)                # started before the warm-up: its rows are bracketed around the timed regions below
     # ---- device-resident: input already in HBM, output left in HBM ----
     # warm-up; the last warm-up step is timed kernel by kernel (two events around every launch) to get the
     # per-kernel table and to find the dominant kernel
@@ -228,7 +234,7 @@ def run_b200(args, rank, world, local_rank):
     ctx.profile_filter(top_name)
     sync()
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank)
+    clk0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     stage_sum = {}
@@ -254,7 +260,6 @@ def run_b200(args, rank, world, local_rank):
     f1.record(stream)
     sync()
     noprof_ms = f0.elapsed_time(f1) / args.steps
-    clocks = sampler.stop()
 
     # ---- end to end: host buffer in, archive in host memory out, through the C ABI ----
     def e2e(host_view):
@@ -268,6 +273,7 @@ def run_b200(args, rank, world, local_rank):
         return (time.perf_counter() - t0) * 1000.0 / args.steps, r
 
     e2e_ms, r2 = e2e(pinned.numpy())
+    clocks = sampler.stop(clk0, sampler.mark())               # sampled over the timed regions: device-resident steps and host-to-host calls
     he = ctx.last_host_entry
     host_entry = ("one piece" if he == 0 else "%d ranges by chromosome, two worker contexts" % he if he > 0 else
                   "%d ranges chained at bzip2-block granularity" % -he) + " (DESIGN.md section 5b)"

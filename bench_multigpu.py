@@ -38,11 +38,12 @@ def bench(args, rank, world, local_rank, METRIC, UNIT, WORKLOADS, measured_peak_
     def step_resident():
         return compress_sharded(ph, dist, rank, world, d_range, hi - lo, halo[rank], bed, lo, 9, device, torch)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # started before the warm-up: its rows are bracketed around the timed region
     for _ in range(max(args.warmup, 1)):
         out = step_resident()
     barrier()
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    clk0 = sampler.mark() if sampler else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_sum = {}
     e0.record(stream)
@@ -54,7 +55,7 @@ def bench(args, rank, world, local_rank, METRIC, UNIT, WORKLOADS, measured_peak_
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(clk0, sampler.mark()) if sampler else None
 
     # ---- end to end: every rank uploads its range from pinned host memory, rank 0 ends with the archive in host memory ----
     arc_host = None

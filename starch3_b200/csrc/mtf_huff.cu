@@ -593,14 +593,15 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
         // alphabets of <= MTF_REG_MAX symbols take the register-list kernel, larger ones the warp-cooperative one
         double N = 0;
         int rows = 1;
-        bool any_small = false, any_big = false;                   // which forms of the register-list kernel this chunk needs
+        bool any_small = false, any_big = false, any_huge = false; // which forms of the MTF kernel this chunk needs
         for (uint64_t b = s0; b < s0 + n; b++) {
             int a = b0 + b < ctx->h_blocks.size() ? (int)ctx->h_blocks[b0 + b].n_in_use : 0;
             if (b0 + b < ctx->h_blocks.size()) N += ctx->h_blocks[b0 + b].nblock;
             if (a <= MTF_REG_MAX && a > rows) rows = a;
-            if (a == 0) { rows = MTF_REG_MAX; any_small = any_big = true; }     // alphabet not mirrored on the host: size for the worst case
+            if (a == 0) { rows = MTF_REG_MAX; any_small = any_big = any_huge = true; }     // alphabet not mirrored on the host: size for the worst case
             else if (a <= 24) any_small = true;
             else if (a <= MTF_REG_MAX) any_big = true;
+            else any_huge = true;
         }
         const size_t tail_smem = 260 * 4 + 40 * 4 + 256 * 4;
         int fused = ck.cs == 1 && n > (uint64_t)SM_COUNT ? 1 : 0;
@@ -618,7 +619,7 @@ int run_mtf(Ctx *ctx, uint64_t b0, uint64_t nb)
         if (any_big)
             S3G_LAUNCH_CLUSTER(ctx, k_mtf_list_big, dim3(cs, (unsigned)n), MS_BIG, (size_t)rows * MS_BIG * 4 + tail_smem, cs, lcol,
                        mtf0, mtfv, freq, blocks, rows, fused);
-        S3G_LAUNCH(ctx, k_mtf, (unsigned)n, MT, 0, lcol, mtf0, mtfv, freq, blocks, fused);
+        if (any_huge) S3G_LAUNCH(ctx, k_mtf, (unsigned)n, MT, 0, lcol, mtf0, mtfv, freq, blocks, fused);
         if (!fused) {
             // zero-run coding, tile-parallel over the ranks
             ZTileInfo *zt = ctx->ztiles.as<ZTileInfo>() + s0 * ZNT;
