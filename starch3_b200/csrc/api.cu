@@ -744,7 +744,8 @@ struct Chain {
     bool open = false;                           // streams.back() has blocks still to come
     uint64_t open_bits = 0; uint32_t open_comb = 0;   // bits of the open stream so far (its header included), combined CRC so far
     uint64_t out_bytes = 0;                      // bytes of the closed streams = where the open / next stream starts
-    uint64_t tail_len = 0;                       // unfinished bytes of the open stream at the start of chain_tf[cur]
+    DevBuf *tf[2] = {nullptr, nullptr};          // the step's transformed bytes, ping-pong (the caller's: the tail lives there between steps)
+    uint64_t tail_len = 0;                       // unfinished bytes of the open stream at the start of tf[cur]
     int cur = 0;
     int64_t run_max = INT64_MIN;                 // largest stop since the last chromosome start (carry_chain of multi.cu)
     uint64_t tf_room = 4ull << 20;               // transformed bytes a step is expected to add (sizes the other buffer)
@@ -788,7 +789,7 @@ int Chain::step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8
     if (sm.n_lines) run_max = (sm.single_piece && sm.continues) ? std::max(sm.tail_max, carry) : sm.tail_max;
     n_lines += sm.n_lines;
     if (last) dropped = sm.dropped_tail_bytes;
-    DevBuf &T = ctx->chain_tf[cur];
+    DevBuf &T = *tf[cur];
     S3G_TRY(grow_keep(ctx, T, tail_len + sm.tf_bytes + 256, tail_len));
     uint64_t np = 0, tl = 0;
     for (;;) {
@@ -912,7 +913,7 @@ int Chain::step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8
     if (last) { tail_len = 0; return S3G_OK; }
     const uint64_t tail_start = (b_fin > 0 && hb[b_fin - 1].chrom == ns - 1) ? hb[b_fin - 1].in_end : soff[ns - 1];
     const uint64_t new_tail = n_step - tail_start;
-    DevBuf &N = ctx->chain_tf[cur ^ 1];
+    DevBuf &N = *tf[cur ^ 1];
     S3G_TRY(N.ensure(new_tail + tf_room));
     if (new_tail) S3G_CUDA(cudaMemcpyAsync(N.p, static_cast<const uint8_t *>(T.p) + tail_start, new_tail, cudaMemcpyDeviceToDevice, ctx->stream));
     tail_len = new_tail; cur ^= 1;
@@ -972,6 +973,7 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
 
     Chain ch;
     ch.ctx = ctx; ch.level = level; ch.tf_room = range_max + (4ull << 20);
+    ch.tf[0] = &ctx->chain_tf[0]; ch.tf[1] = &ctx->chain_tf[1];
     ch.d_out = ctx->chain_out.as<uint8_t>(); ch.out_cap = out_cap; ch.h_out = ctx->h_archive + HDR_RESERVE;
     ch.timing = getenv("S3G_TIMING") != nullptr; ch.tt0 = ch.timing ? host_ms() : 0;
     const uint8_t *d_bed = ctx->bed.as<uint8_t>();
@@ -1045,12 +1047,13 @@ struct StreamState {
     uint64_t range_bytes = 0;
     uint8_t *h_stage = nullptr; uint64_t stage_fill = 0;
     DevBuf dev;
+    DevBuf tf[2];                                // the chain's transformed bytes: the tail waits here between calls, whatever else the context does
     std::vector<uint8_t> halo;                   // the last line of the range before
     std::vector<uint8_t> streams;
     Chain chain;
     uint64_t ranges = 0;
     double device_ms = 0;
-    ~StreamState() { if (h_stage) cudaFreeHost(h_stage); dev.release(); }
+    ~StreamState() { if (h_stage) cudaFreeHost(h_stage); dev.release(); tf[0].release(); tf[1].release(); }
 };
 void stream_state_free(Ctx *ctx) { delete static_cast<StreamState *>(ctx->stream_state); ctx->stream_state = nullptr; }
 
@@ -1308,6 +1311,7 @@ int s3g_stream_begin(s3g_ctx *ctx, int level, const char *note, uint64_t range_b
     S->range_bytes = range_bytes ? std::max<uint64_t>(range_bytes, 4096) : (256ull << 20);
     if (cudaMallocHost(&S->h_stage, S->range_bytes) != cudaSuccess) { cudaGetLastError(); delete S; set_error("out of pinned host memory"); return S3G_E_NOMEM; }
     S->chain.ctx = ctx; S->chain.level = level; S->chain.v_out = &S->streams;
+    S->chain.tf[0] = &S->tf[0]; S->chain.tf[1] = &S->tf[1];
     ctx->stream_state = S;
     return S3G_OK;
 }

@@ -335,6 +335,34 @@ def test_random_small_inputs_against_the_oracle(ctx, oracle):
         assert res.archive == oracle.archive(bed, level, note), (case, bed[:200])
 
 
+def test_other_calls_between_the_pieces_of_a_stream(ctx, oracle, monkeypatch):
+    """the bounded-memory entry keeps its unfinished tail in buffers of its own: one-shot and chained calls on the same context
+    between two s3g_stream_write calls leave it alone"""
+    import ctypes as C
+    import starch3_b200 as s3
+    from starch3_b200.api import CResult, Result
+    bed = synth.bed(1, 120000).tobytes()
+    other = synth.bed(3, 90000).tobytes()
+    L, h = ctx._lib, ctx._h
+    ctx._check(L.s3g_stream_begin(h, 2, b"i", 200_000))
+    third = len(bed) // 3
+    for k in range(3):
+        piece = np.frombuffer(bed[k * third:(k + 1) * third if k < 2 else len(bed)], dtype=np.uint8)
+        ctx._check(L.s3g_stream_write(h, piece.ctypes.data_as(C.c_void_p), len(piece)))
+        monkeypatch.setenv("S3G_PARTS", "2"); monkeypatch.setenv("S3G_CHAIN", "1"); monkeypatch.setenv("S3G_CHAIN_BYTES", "300000")
+        assert ctx.compress_bed(other, 3).archive == oracle.archive(other, 3, "")
+        monkeypatch.setenv("S3G_PARTS", "1")
+        assert ctx.compress_bed(other, 9).archive == oracle.archive(other, 9, "")
+    r = CResult()
+    rc = L.s3g_stream_end(h, C.byref(r))
+    try:
+        ctx._check(rc)
+        res = Result(r, None)
+        assert res.archive == oracle.archive(bed, 2, "i")
+    finally:
+        L.s3g_result_free(C.byref(r))
+
+
 @pytest.mark.parametrize("cfg,lines,rng,piece", [(2, 60000, 200_000, 65536), (5, 60000, 4096, 1000), (1, 60000, 300_000, 7), (2, 30000, 1 << 20, 1 << 22)])
 def test_bounded_memory_ingestion(ctx, oracle, cfg, lines, rng, piece):
     """s3g_stream_*: the input arrives in pieces, at most one range of it is resident beside the open chromosome; ranges
