@@ -199,6 +199,16 @@ S3G_API int s3g_stage_times(s3g_ctx *ctx, double *stage_ms8);
 /* Host logic only (no device needed): how a batch of n_blocks bzip2 blocks is dealt to the MTF (stage 3) or Huffman (stage 4)
  * kernels -- chunks of consecutive blocks, ctas[i] CTAs per block (0: the Huffman form with two 512-thread CTAs per SM and one
  * CTA per block).  DESIGN.md section 4, plan_chunks.  The tests check that the chunks tile the batch and fit the GPU. */
+/* Host logic only: the bit layout of one step of the chained entries.  state[4] = {a stream is open, its
+ * bits so far, its combined CRC so far, bytes of the closed streams}, carried from step to step (all zero before the first).
+ * The step has n_streams streams and n_blocks blocks in stream order (stream_of ascending from 0), the first n_final of them
+ * final; its first stream continues the open stream when first_continues.  Out: block_pos[n_final] = bit position of every final
+ * block in the streams buffer; patch[2 i], patch[2 i + 1] = bit position and 32-bit word of the stream headers and trailers;
+ * stream_start[s] = byte offset a stream starts at in this step (~0: it continues), stream_len[s] = its byte length if it is closed
+ * in this step (0: still open). */
+S3G_API int s3g_chain_layout(uint64_t *state, int block_size_100k, uint64_t n_streams, int first_continues, const uint32_t *stream_of,
+                             const uint64_t *n_bits, const uint32_t *crc, uint64_t n_blocks, uint64_t n_final, uint64_t *block_pos,
+                             uint64_t *patch, uint64_t patch_cap, uint64_t *n_patch, uint64_t *stream_start, uint64_t *stream_len);
 S3G_API int s3g_batch_chunks(uint64_t n_blocks, int stage, uint64_t *first, uint64_t *count, uint32_t *ctas, uint64_t cap, uint64_t *n_chunks);
 
 /* ---- stage entry points (host buffers in / out), for the parity tests ---- */

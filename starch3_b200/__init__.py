@@ -5,7 +5,7 @@ this package is a thin ctypes binding over it plus the synthetic-input generator
 There is no CPU fallback: if the CUDA library is missing, or no GPU is present when a
 context is created, the call fails loudly.
 """
-from .api import (Starch3Error, Context, Result, lib, lib_path, have_library, build_library, multi_compress_bed, batch_chunks, C_ABI_SYMBOLS)  # noqa: F401
+from .api import (Starch3Error, Context, Result, lib, lib_path, have_library, build_library, multi_compress_bed, batch_chunks, chain_layout, C_ABI_SYMBOLS)  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = ["Starch3Error", "Context", "Result", "lib", "lib_path", "have_library", "build_library", "synth",

@@ -21,7 +21,7 @@ C_ABI_SYMBOLS = [
     "s3g_init", "s3g_destroy", "s3g_last_error", "s3g_set_stream", "s3g_launch_count", "s3g_last_host_entry", "s3g_sort_retries", "s3g_sort_stats", "s3g_profile", "s3g_profile_report", "s3g_profile_filter",
     "s3g_compress_bed", "s3g_compress_bed_device", "s3g_result_free", "s3g_read_streams",
     "s3g_stream_begin", "s3g_stream_write", "s3g_stream_end",
-    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_multi_compress_bed", "s3g_stage_times", "s3g_batch_chunks",
+    "s3g_shard_tokenize", "s3g_shard_transform", "s3g_shard_transform_peers", "s3g_shard_plan", "s3g_shard_compress", "s3g_shard_assemble", "s3g_shard_place", "s3g_multi_compress_bed", "s3g_stage_times", "s3g_batch_chunks", "s3g_chain_layout",
     "s3g_tokenize", "s3g_transform", "s3g_rle1", "s3g_bwt", "s3g_mtf", "s3g_huff", "s3g_bz_compress",
     "s3g_decompress_archive", "s3g_bz_decompress", "s3g_inverse_transform",
     "s3g_BZ2_bzCompressInit", "s3g_BZ2_bzCompress", "s3g_BZ2_bzCompressEnd",
@@ -98,6 +98,7 @@ def lib():
         L.s3g_sort_retries.argtypes = [vp]; L.s3g_sort_retries.restype = u64
         L.s3g_last_host_entry.argtypes = [vp]; L.s3g_last_host_entry.restype = i32
         L.s3g_batch_chunks.argtypes = [u64, i32, vp, vp, vp, u64, C.POINTER(u64)]
+        L.s3g_chain_layout.argtypes = [vp, i32, u64, i32, vp, vp, vp, u64, u64, vp, vp, u64, C.POINTER(u64), vp, vp]
         L.s3g_sort_stats.argtypes = [vp, vp]
         L.s3g_profile.argtypes = [vp, i32]
         L.s3g_profile_report.argtypes = [vp, C.c_char_p, u64]
@@ -187,6 +188,23 @@ class Result:
         c = self.chroms[i]
         o = self.streams_off + c["bz_off"]
         return self.archive[o:o + c["bz_len"]]
+
+
+def chain_layout(state, level, n_streams, first_continues, stream_of, n_bits, crc, n_final):
+    """one step of the chained entries' bit layout (s3g_chain_layout; host logic only): state = np.uint64[4], updated in place
+    -> (block positions, [(bit position, word)], stream starts, stream lengths)"""
+    stream_of = np.ascontiguousarray(stream_of, dtype=np.uint32); n_bits = np.ascontiguousarray(n_bits, dtype=np.uint64)
+    crc = np.ascontiguousarray(crc, dtype=np.uint32)
+    nb = len(stream_of)
+    pos = np.zeros(max(n_final, 1), dtype=np.uint64); cap = 4 * n_streams + 4
+    patch = np.zeros(2 * cap, dtype=np.uint64); npatch = C.c_uint64(0)
+    start = np.zeros(max(n_streams, 1), dtype=np.uint64); ln = np.zeros(max(n_streams, 1), dtype=np.uint64)
+    rc = lib().s3g_chain_layout(_p(state), level, n_streams, 1 if first_continues else 0, _p(stream_of), _p(n_bits), _p(crc), nb, n_final,
+                                _p(pos), _p(patch), cap, C.byref(npatch), _p(start), _p(ln))
+    if rc != S3G_OK:
+        raise Starch3Error(rc, lib().s3g_last_error().decode("utf-8", "replace"))
+    return (pos[:n_final].copy(), [(int(patch[2 * k]), int(patch[2 * k + 1])) for k in range(npatch.value)], start[:n_streams].copy(),
+            ln[:n_streams].copy())
 
 
 def batch_chunks(n_blocks, stage):

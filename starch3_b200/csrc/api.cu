@@ -736,14 +736,76 @@ struct ChainStream {
     s3g_chrom c;
 };
 
+// ---- the bit layout of one step: host arithmetic only (s3g_chain_layout exposes it to the CPU tests) ----
+// Carried from step to step: is the last stream still open, its bits so far (header included) and combined CRC so far, and the
+// bytes of the closed streams (= where the open or the next stream starts).
+struct ChainCarry {
+    bool open = false;
+    uint64_t open_bits = 0; uint32_t open_comb = 0;
+    uint64_t out_bytes = 0;
+};
+struct StepLayout {
+    std::vector<uint64_t> pos;        // bit position of every final block, in order
+    std::vector<uint64_t> patches;    // (bit position, 32-bit word) pairs: stream headers and trailers
+    uint64_t bit_lo = ~0ull, bit_hi = 0;
+    std::vector<uint64_t> started;    // per step stream: byte offset it starts at in this step, ~0 if it continues the open stream
+    std::vector<uint64_t> closed_len; // per step stream: its length in bytes if it is closed in this step, 0 if still open
+    std::vector<uint32_t> n_final;    // per step stream: blocks placed in this step
+};
+// blocks [0, nb) of the step in stream order (stream_of ascending from 0 to ns - 1), the first b_fin of them final; the
+// step's first stream continues the open stream when first_continues.  bz/compress.c:607-609, :622-628, :657-666.
+static int chain_layout_step(ChainCarry &st, int level, uint64_t ns, bool first_continues, const uint32_t *stream_of, const uint64_t *n_bits,
+                             const uint32_t *crc, uint64_t nb, uint64_t b_fin, StepLayout &L)
+{
+    L.pos.clear(); L.patches.clear(); L.bit_lo = ~0ull; L.bit_hi = 0;
+    L.started.assign(ns, ~0ull); L.closed_len.assign(ns, 0); L.n_final.assign(ns, 0);
+    auto mark = [&](uint64_t at, uint64_t nbits) { L.bit_lo = std::min(L.bit_lo, at); L.bit_hi = std::max(L.bit_hi, at + nbits); };
+    uint64_t b = 0;
+    for (uint64_t s = 0; s < ns; s++) {
+        uint64_t bits; uint32_t comb;
+        if (s == 0 && first_continues) {
+            if (!st.open) return S3G_E_PARAM;
+            bits = st.open_bits; comb = st.open_comb;
+        } else {
+            L.started[s] = st.out_bytes;
+            L.patches.push_back(st.out_bytes * 8); L.patches.push_back(0x425a6800u | (uint32_t)('0' + level));
+            mark(st.out_bytes * 8, 32);
+            bits = 32; comb = 0;
+        }
+        bool all_final = true;
+        for (; b < nb && stream_of[b] == s; b++) {
+            if (b >= b_fin) { all_final = false; continue; }
+            L.pos.push_back(st.out_bytes * 8 + bits);
+            mark(st.out_bytes * 8 + bits, n_bits[b]);
+            bits += n_bits[b];
+            comb = ((comb << 1) | (comb >> 31)) ^ crc[b];
+            L.n_final[s]++;
+        }
+        if (all_final) {
+            const uint64_t end = st.out_bytes * 8 + bits;
+            L.patches.push_back(end); L.patches.push_back(0x17724538u);
+            L.patches.push_back(end + 32); L.patches.push_back(0x50900000u | (comb >> 16));
+            L.patches.push_back(end + 64); L.patches.push_back((uint64_t)(uint32_t)(comb << 16));
+            mark(end, 80);
+            bits += 80;
+            L.closed_len[s] = (bits + 7) >> 3;
+            st.out_bytes += L.closed_len[s];
+            st.open = false;
+        } else {
+            st.open = true; st.open_bits = bits; st.open_comb = comb;
+        }
+    }
+    return b == nb ? S3G_OK : S3G_E_PARAM;
+}
+
 // the state that goes from one step to the next, and one step
 struct Chain {
     Ctx *ctx = nullptr;
     int level = 9;
     std::vector<ChainStream> streams;            // the archive's streams, in order; the last one may be open
-    bool open = false;                           // streams.back() has blocks still to come
-    uint64_t open_bits = 0; uint32_t open_comb = 0;   // bits of the open stream so far (its header included), combined CRC so far
-    uint64_t out_bytes = 0;                      // bytes of the closed streams = where the open / next stream starts
+    ChainCarry cst;                              // open: streams.back() has blocks still to come
+    StepLayout lay;
+    std::vector<uint32_t> l_stream, l_crc; std::vector<uint64_t> l_bits;
     DevBuf *tf[2] = {nullptr, nullptr};          // the step's transformed bytes, ping-pong (the caller's: the tail lives there between steps)
     uint64_t tail_len = 0;                       // unfinished bytes of the open stream at the start of tf[cur]
     int cur = 0;
@@ -809,7 +871,7 @@ int Chain::step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8
     uint64_t off = tail_len;
     for (uint64_t q = 0; q < np; q++) {
         const s3g_chrom &p = pc[q];
-        if (q == 0 && sm.continues && open) {
+        if (q == 0 && sm.continues && cst.open) {
             s3g_chrom &c = streams.back().c;
             c.tf_len += p.tf_len; c.line_count += p.line_count; c.bases_nonunique += p.bases_nonunique; c.bases_unique += p.bases_unique;
             if (!tail_len) { set_error("chained entry: an open stream without a tail"); return S3G_E_CUDA; }
@@ -843,44 +905,20 @@ int Chain::step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8
         fprintf(stderr, "[s3g timing] step %d: starts %.2f ms, range measured +%.2f, transformed +%.2f, plan +%.2f (%llu blocks, %llu final), coded +%.2f\n",
                 step_no - 1, ts0 - tt0, ts1 - ts0, ts2 - ts1, ts3 - ts2, (unsigned long long)nb, (unsigned long long)b_fin, host_ms() - ts3);
     // ---- where the step's bits go ----
-    items.clear(); patches.clear();
-    uint64_t bit_lo = ~0ull, bit_hi = 0, b = 0;
-    auto mark = [&](uint64_t at, uint64_t nbits) { bit_lo = std::min(bit_lo, at); bit_hi = std::max(bit_hi, at + nbits); };
-    for (uint64_t s = 0; s < ns; s++) {
-        s3g_chrom &c = streams[gidx[s]].c;
-        uint64_t bits; uint32_t comb;
-        if (s == 0 && tail_len) { bits = open_bits; comb = open_comb; }
-        else {
-            c.bz_off = out_bytes; c.tf_off = 0;
-            patches.push_back(out_bytes * 8); patches.push_back(0x425a6800u | (uint32_t)('0' + level));       // bz/compress.c:622-628
-            mark(out_bytes * 8, 32);
-            bits = 32; comb = 0;
-        }
-        bool all_final = true;
-        for (; b < nb && hb[b].chrom == s; b++) {
-            if (b >= b_fin) { all_final = false; continue; }
-            items.push_back(out_bytes * 8 + bits);
-            mark(out_bytes * 8 + bits, hb[b].n_bits);
-            bits += hb[b].n_bits;
-            comb = ((comb << 1) | (comb >> 31)) ^ hb[b].crc;                                                  // :607-608
-            c.n_blocks++;
-            n_blocks++; rle_bytes += hb[b].nblock; mtf_symbols += hb[b].n_mtf;
-        }
-        if (all_final) {
-            const uint64_t end = out_bytes * 8 + bits;                                                        // :657-666
-            patches.push_back(end); patches.push_back(0x17724538u);
-            patches.push_back(end + 32); patches.push_back(0x50900000u | (comb >> 16));
-            patches.push_back(end + 64); patches.push_back((uint64_t)(uint32_t)(comb << 16));
-            mark(end, 80);
-            bits += 80;
-            c.bz_len = (bits + 7) >> 3;
-            out_bytes += c.bz_len;
-            open = false;
-        } else {
-            open = true; open_bits = bits; open_comb = comb;
-        }
+    l_stream.resize(nb); l_bits.resize(nb); l_crc.resize(nb);
+    for (uint64_t k = 0; k < nb; k++) { l_stream[k] = hb[k].chrom; l_bits[k] = hb[k].n_bits; l_crc[k] = hb[k].crc; }
+    if (chain_layout_step(cst, level, ns, tail_len != 0, l_stream.data(), l_bits.data(), l_crc.data(), nb, b_fin, lay) != S3G_OK) {
+        set_error("chained entry: block table and stream table disagree"); return S3G_E_CUDA;
     }
-    if (b != nb) { set_error("chained entry: block table and stream table disagree"); return S3G_E_CUDA; }
+    for (uint64_t sidx = 0; sidx < ns; sidx++) {
+        s3g_chrom &c = streams[gidx[sidx]].c;
+        if (lay.started[sidx] != ~0ull) { c.bz_off = lay.started[sidx]; c.tf_off = 0; }
+        c.n_blocks += lay.n_final[sidx];
+        if (lay.closed_len[sidx]) c.bz_len = lay.closed_len[sidx];
+    }
+    for (uint64_t k = 0; k < b_fin; k++) { n_blocks++; rle_bytes += hb[k].nblock; mtf_symbols += hb[k].n_mtf; }
+    items = lay.pos; patches = lay.patches;
+    const uint64_t bit_lo = lay.bit_lo, bit_hi = lay.bit_hi;
     if (bit_hi > bit_lo) {
         const uint64_t byte_lo = bit_lo >> 3, byte_hi = (bit_hi + 7) >> 3, nbytes = byte_hi - byte_lo;
         if (d_out && byte_hi > out_cap) return S3G_E_CAPACITY;               // caller falls back to the one-shot path
@@ -892,7 +930,7 @@ int Chain::step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8
         if (d_out) {
             S3G_TRY(run_place_bytes(ctx, d_out, byte_lo, nbytes));
             // the bytes that are complete leave for the host beside the next step's kernels
-            const uint64_t done = last ? out_bytes : (bit_hi >> 3);
+            const uint64_t done = last ? cst.out_bytes : (bit_hi >> 3);
             if (h_out && done > copied) {
                 S3G_CUDA(cudaEventRecord(ctx->out_ev, ctx->stream));
                 S3G_CUDA(cudaStreamWaitEvent(ctx->out_stream, ctx->out_ev, 0));
@@ -999,7 +1037,7 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
     if (ch.timing) fprintf(stderr, "[s3g timing] last step ends %.2f ms\n", host_ms() - ch.tt0);
     for (std::thread &c : copiers) c.join();
     if (rc != S3G_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->out_stream); cudaStreamSynchronize(ctx->stream); return rc; }
-    if (ch.open) { set_error("chained entry: a stream was left open"); return S3G_E_CUDA; }
+    if (ch.cst.open) { set_error("chained entry: a stream was left open"); return S3G_E_CUDA; }
     S3G_CUDA(cudaEventRecord(t1, ctx->stream));
     S3G_CUDA(cudaStreamSynchronize(ctx->out_stream));
     S3G_CUDA(cudaEventSynchronize(t1));
@@ -1026,12 +1064,12 @@ static int compress_bed_chained(Ctx *ctx, const uint8_t *bed, uint64_t n, int le
     arc[4 + hdr.size()] = '\n';
     res->archive = arc;
     res->streams_off = streams_off;
-    res->streams_size = ch.out_bytes;
-    res->archive_size = streams_off + ch.out_bytes;
+    res->streams_size = ch.cst.out_bytes;
+    res->archive_size = streams_off + ch.cst.out_bytes;
     res->d_streams = ctx->chain_out.p;
-    ctx->last_streams_size = ch.out_bytes;
+    ctx->last_streams_size = ch.cst.out_bytes;
     ctx->last_streams_host = ctx->h_archive + HDR_RESERVE;
-    ctx->archive_hint = ch.out_bytes;
+    ctx->archive_hint = ch.cst.out_bytes;
     return S3G_OK;
 }
 
@@ -1178,6 +1216,26 @@ int s3g_set_stream(s3g_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) { set_error("null context"); return S3G_E_PARAM; }
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return S3G_OK;
+}
+
+int s3g_chain_layout(uint64_t *state, int level, uint64_t n_streams, int first_continues, const uint32_t *stream_of, const uint64_t *n_bits,
+                     const uint32_t *crc, uint64_t n_blocks, uint64_t n_final, uint64_t *block_pos, uint64_t *patch, uint64_t patch_cap,
+                     uint64_t *n_patch, uint64_t *stream_start, uint64_t *stream_len)
+{
+    if (!state || !n_patch || (n_blocks && (!stream_of || !n_bits || !crc)) || n_final > n_blocks) { set_error("bad argument"); return S3G_E_PARAM; }
+    ChainCarry st;
+    st.open = state[0] != 0; st.open_bits = state[1]; st.open_comb = (uint32_t)state[2]; st.out_bytes = state[3];
+    StepLayout L;
+    if (chain_layout_step(st, level, n_streams, first_continues != 0, stream_of, n_bits, crc, n_blocks, n_final, L) != S3G_OK) {
+        set_error("block table and stream table disagree"); return S3G_E_PARAM;
+    }
+    *n_patch = L.patches.size() / 2;
+    if (L.patches.size() > 2 * patch_cap) { set_error("patch table too small"); return S3G_E_CAPACITY; }
+    for (size_t k = 0; k < L.pos.size(); k++) if (block_pos) block_pos[k] = L.pos[k];
+    for (size_t k = 0; k < L.patches.size(); k++) if (patch) patch[k] = L.patches[k];
+    for (uint64_t q = 0; q < n_streams; q++) { if (stream_start) stream_start[q] = L.started[q]; if (stream_len) stream_len[q] = L.closed_len[q]; }
+    state[0] = st.open; state[1] = st.open_bits; state[2] = st.open_comb; state[3] = st.out_bytes;
     return S3G_OK;
 }
 
@@ -1352,7 +1410,7 @@ int s3g_stream_end(s3g_ctx *ctx, s3g_result *res)
     S3G_CUDA(cudaSetDevice(ctx->device));
     memset(res, 0, sizeof *res);
     int rc = stream_flush(ctx, *S, S->stage_fill, true);
-    if (rc == S3G_OK && S->chain.open) { set_error("stream entry: a stream was left open"); rc = S3G_E_CUDA; }
+    if (rc == S3G_OK && S->chain.cst.open) { set_error("stream entry: a stream was left open"); rc = S3G_E_CUDA; }
     if (rc != S3G_OK) { stream_state_free(ctx); return rc; }
     std::vector<s3g_chrom> chroms;
     std::vector<uint8_t> names;

@@ -89,3 +89,73 @@ def test_batches_are_dealt_in_chunks_that_tile_them_and_fit_the_gpu():
     assert s3.batch_chunks(296, 3) == [(0, 296, 1)] and s3.batch_chunks(178, 3) == [(0, 148, 2), (148, 30, 8)]
     assert s3.batch_chunks(893, 3) == [(0, 888, 1), (888, 5, 8)] and s3.batch_chunks(893, 4) == [(0, 893, 0)]
     assert s3.batch_chunks(178, 4) == [(0, 148, 1), (148, 30, 4)] and s3.batch_chunks(37, 4) == [(0, 37, 4)]
+
+
+def test_chained_steps_lay_the_bits_out_like_one_step():
+    """host logic of the chained entries (api.cu, chain_layout_step): streams of random block bit lengths and CRCs, laid out in one
+    step and in random chains of steps -- a step ends inside a stream, its last one or two blocks are not final and come back in
+    the next step -- give the same bytes (every block's bits, the "BZh" headers, the trailers with the folded CRC), the same
+    stream offsets and lengths"""
+    import numpy as np
+    import starch3_b200 as s3
+    rng = np.random.default_rng(99)
+
+    def render(total_bytes, placed):
+        bits = np.zeros(total_bytes * 8 + 64, dtype=np.uint8)
+        for pos, payload in placed:
+            assert not bits[pos:pos + len(payload)].any()          # nothing is written twice
+            bits[pos:pos + len(payload)] = payload
+        return np.packbits(bits[:total_bytes * 8]).tobytes()
+
+    def word_bits(w):
+        return np.array([(w >> (31 - k)) & 1 for k in range(32)], dtype=np.uint8)
+
+    for case in range(40):
+        level = int(rng.integers(1, 10))
+        n_streams = int(rng.integers(1, 7))
+        blocks = []                                               # (stream, n_bits, crc, payload)
+        for s in range(n_streams):
+            for _ in range(int(rng.integers(1, 9))):
+                nb_ = int(rng.integers(120, 4000))
+                blocks.append((s, nb_, int(rng.integers(0, 2 ** 32)), np.ones(nb_, dtype=np.uint8)))
+        def run(steps):
+            """steps: list of (first block, end block, final end) over the global block list; returns bytes, offsets, lengths"""
+            state = np.zeros(4, dtype=np.uint64)
+            placed, off, ln = [], {}, {}
+            for (b0, b1, bf) in steps:
+                streams = sorted(set(b[0] for b in blocks[b0:b1]))
+                local = {g: i for i, g in enumerate(streams)}
+                cont = bool(state[0]) and blocks[b0][0] == run.open_stream
+                pos, patches, start, lens = s3.chain_layout(state, level, len(streams), cont, [local[b[0]] for b in blocks[b0:b1]],
+                                                            [b[1] for b in blocks[b0:b1]], [b[2] for b in blocks[b0:b1]], bf - b0)
+                for k in range(bf - b0):
+                    placed.append((int(pos[k]), blocks[b0 + k][3]))
+                for p_, w in patches:
+                    placed.append((p_, word_bits(w)))
+                for g, i in local.items():
+                    if int(start[i]) != 2 ** 64 - 1:
+                        off[g] = int(start[i])
+                    if int(lens[i]):
+                        ln[g] = int(lens[i])
+                run.open_stream = blocks[b1 - 1][0] if state[0] else None
+            assert not state[0]
+            return render(int(state[3]), placed), off, ln
+        run.open_stream = None
+        one = run([(0, len(blocks), len(blocks))])
+        # a chain: a step covers the blocks up to a random point; the last one or two blocks of its last stream are not final
+        # (unless the step ends the input) and open the next step
+        fixed, b0 = [], 0
+        while b0 < len(blocks):
+            b1 = min(len(blocks), b0 + int(rng.integers(2, 9)))
+            if b1 == len(blocks):
+                fixed.append((b0, b1, b1)); break
+            last_stream = blocks[b1 - 1][0]
+            first_of_last = next(k for k in range(b0, b1) if blocks[k][0] == last_stream)
+            bf = max(first_of_last, b1 - int(rng.integers(1, 3)))
+            if bf == b0:                                          # a step that finishes nothing is not a step
+                continue
+            fixed.append((b0, b1, bf))
+            b0 = bf
+        run.open_stream = None
+        chained = run(fixed)
+        assert chained == one, case
