@@ -836,17 +836,8 @@ int Chain::step(const uint8_t *d_range, uint64_t len, uint64_t halo, const uint8
     double ts1 = 0, ts2 = 0, ts3 = 0;
     // ---- tokenise + transform the range behind the tail ----
     s3g_shard_summary sm;
-    cudaEvent_t ea = nullptr, eb = nullptr;
-    if (timing) { cudaEventCreate(&ea); cudaEventCreate(&eb); cudaEventRecord(ea, ctx->stream); }
     S3G_TRY(s3g_shard_tokenize(cx, d_range, len, halo, &sm));
-    if (timing) {
-        ts1 = host_ms();
-        cudaEventRecord(eb, ctx->stream); cudaEventSynchronize(eb);
-        float g = 0; cudaEventElapsedTime(&g, ea, eb);
-        fprintf(stderr, "[s3g timing]   tokenizer of %llu bytes (halo %llu): %.2f ms on the device, %.2f ms on the host clock\n", (unsigned long long)len,
-                (unsigned long long)halo, g, ts1 - ts0);
-        cudaEventDestroy(ea); cudaEventDestroy(eb);
-    }
+    if (timing) ts1 = host_ms();
     const int64_t carry = sm.continues ? run_max : INT64_MIN;
     if (sm.n_lines) run_max = (sm.single_piece && sm.continues) ? std::max(sm.tail_max, carry) : sm.tail_max;
     n_lines += sm.n_lines;
