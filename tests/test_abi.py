@@ -159,3 +159,23 @@ def test_chained_steps_lay_the_bits_out_like_one_step():
         run.open_stream = None
         chained = run(fixed)
         assert chained == one, case
+
+
+def test_host_only_entry_points_refuse_bad_arguments():
+    import numpy as np
+    import starch3_b200 as s3
+    with pytest.raises(s3.Starch3Error) as e:
+        s3.batch_chunks(10, 7)                                   # stages 3 (MTF) and 4 (Huffman) only
+    assert e.value.code == -2
+    state = np.zeros(4, dtype=np.uint64)
+    with pytest.raises(s3.Starch3Error) as e:                    # a step that continues a stream when none is open
+        s3.chain_layout(state, 9, 1, True, [0], [100], [1], 1)
+    assert e.value.code == -2
+    with pytest.raises(s3.Starch3Error) as e:                    # blocks that name a stream the step does not have
+        s3.chain_layout(state, 9, 1, False, [0, 3], [100, 100], [1, 2], 2)
+    assert e.value.code == -2
+    pos, patches, start, ln = s3.chain_layout(state, 9, 1, False, [0], [100], [0xdeadbeef], 1)
+    assert list(pos) == [32] and patches[0] == (0, 0x425a6839) and int(start[0]) == 0
+    assert int(ln[0]) == (32 + 100 + 80 + 7) // 8 and list(state) == [0, 0, 0, int(ln[0])]
+    # the trailer: 0x177245385090 then the combined CRC (one block: its CRC)
+    assert patches[1:] == [(132, 0x17724538), (164, 0x5090dead), (196, 0xbeef0000)]
